@@ -1,0 +1,156 @@
+"""ctypes binding of the CPU checker (oracle/liboracle.so and oracle/_ref/libsvref.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs -- never by the product package.
+"""
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+
+NV12, Y420P, BGRA, RGBA = 0, 1, 2, 3
+FORMAT_NAMES = {NV12: "nv12", Y420P: "y420p", BGRA: "bgra", RGBA: "rgba"}
+OK, ERR_KERNEL_NOT_FOUND, ERR_BAD_TARGET, ERR_BAD_INPUT = 0, -1, -2, -3
+
+
+class Uniforms(C.Structure):
+    """ImageUniforms, 236 bytes (reference compute.swift:76-86)."""
+
+    _fields_ = [
+        ("transform", C.c_float * 16),
+        ("textureTx", C.c_float * 16),
+        ("borderMatrix", C.c_float * 16),
+        ("fillColor", C.c_float * 4),
+        ("inSize", C.c_float * 2),
+        ("outSize", C.c_float * 2),
+        ("opacity", C.c_float),
+        ("sampleTime", C.c_float),
+        ("targetTime", C.c_float),
+    ]
+
+
+assert C.sizeof(Uniforms) == 236
+
+
+class _Plane(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32), ("stride", C.c_int32), ("ncomp", C.c_int32)]
+
+
+class _Image(C.Structure):
+    _fields_ = [("format", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("nplanes", C.c_int32), ("planes", _Plane * 3)]
+
+
+def plane_layout(fmt, w, h):
+    """[(offset, width, height, stride, ncomp)] as planesForFormat lays a contiguous sample out
+    (reference sample.pict.linux.swift:275-311)."""
+    if fmt == NV12:
+        return [(0, w, h, w, 1), (w * h, w // 2, h // 2, w, 2)], w * h + w * (h // 2)
+    if fmt == Y420P:
+        c = (w // 2) * (h // 2)
+        return [(0, w, h, w, 1), (w * h, w // 2, h // 2, w // 2, 1), (w * h + c, w // 2, h // 2, w // 2, 1)], w * h + 2 * c
+    if fmt in (BGRA, RGBA):
+        return [(0, w, h, 4 * w, 4)], 4 * w * h
+    raise ValueError(fmt)
+
+
+class Image:
+    """A contiguous 8-bit picture in the reference's Linux plane layout."""
+
+    def __init__(self, fmt, width, height, data=None):
+        self.format, self.width, self.height = fmt, width, height
+        self.layout, self.nbytes = plane_layout(fmt, width, height)
+        if data is None:
+            data = np.zeros(self.nbytes, dtype=np.uint8)
+        data = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1)
+        assert data.size == self.nbytes, (data.size, self.nbytes)
+        self.data = data
+
+    def copy(self):
+        return Image(self.format, self.width, self.height, self.data.copy())
+
+    def plane(self, i):
+        off, w, h, stride, nc = self.layout[i]
+        return self.data[off : off + stride * h].reshape(h, stride)[:, : w * nc]
+
+    def _c(self):
+        im = _Image()
+        im.format, im.width, im.height, im.nplanes = self.format, self.width, self.height, len(self.layout)
+        base = self.data.ctypes.data
+        for i, (off, w, h, stride, nc) in enumerate(self.layout):
+            im.planes[i] = _Plane(base + off, w, h, stride, nc)
+        return im
+
+
+def build(ref_root="/root/reference"):
+    """Compile liboracle.so (always) and _ref/libsvref.so (when the reference tree is present)."""
+    subprocess.run(["make", "-C", str(HERE), f"REF={ref_root}"], check=True, capture_output=True)
+
+
+class _Lib:
+    def __init__(self, path, prefix):
+        self.path = str(path)
+        self.lib = C.CDLL(self.path)
+        self.prefix = prefix
+        for name in ("clear", "apply", "mix", "mix_mt"):
+            getattr(self.lib, f"{prefix}_{name}").restype = C.c_int
+
+    def clear(self, target):
+        t = target._c()
+        return getattr(self.lib, f"{self.prefix}_clear")(C.byref(t))
+
+    def apply(self, target, src, uniforms):
+        t, s = target._c(), src._c()
+        return getattr(self.lib, f"{self.prefix}_apply")(C.byref(t), C.byref(s), C.byref(uniforms))
+
+    def mix(self, target, layers, uniforms, threads=0):
+        """clear + fold layers (already z-sorted) into target, in place. Returns the status code."""
+        n = len(layers)
+        t = target._c()
+        ls = (_Image * max(n, 1))(*[l._c() for l in layers])
+        us = (Uniforms * max(n, 1))(*uniforms)
+        if threads and threads > 1:
+            return getattr(self.lib, f"{self.prefix}_mix_mt")(C.byref(t), ls, us, n, int(threads))
+        return getattr(self.lib, f"{self.prefix}_mix")(C.byref(t), ls, us, n)
+
+
+_cache = {}
+
+
+def port():
+    """The hand-written restatement (mixer_oracle.c)."""
+    if "port" not in _cache:
+        p = HERE / "liboracle.so"
+        if not p.exists():
+            build()
+        _cache["port"] = _Lib(p, "svo")
+    return _cache["port"]
+
+
+def ref_available():
+    return (HERE / "_ref" / "libsvref.so").exists()
+
+
+def ref():
+    """The reference's own OpenCL kernel text compiled as C++ (oracle/_ref, built from /root/reference)."""
+    if "ref" not in _cache:
+        p = HERE / "_ref" / "libsvref.so"
+        if not p.exists():
+            raise FileNotFoundError(f"{p} missing: run `make -C oracle` where /root/reference is mounted")
+        _cache["ref"] = _Lib(p, "svr")
+    return _cache["ref"]
+
+
+def best():
+    """(lib, kind): the reference-text build when present, else the port."""
+    return (ref(), "reference") if ref_available() else (port(), "port")
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
