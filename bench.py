@@ -1,0 +1,319 @@
+#!/usr/bin/env python3
+"""bench.py -- BASELINE.json's metric: 4K 8-layer composite frames/s (+ achieved HBM GB/s) per B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]                 our CUDA path
+    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]  the reference's kernels on the host cores
+
+Workload (BASELINE.md cfg 4): every stream is one VideoMixer with a 3840x2160 NV12 target and 8
+NV12 layers -- one 3840x2160 full-canvas (opacity 1) and seven 1920x1080 scaled to 1600x900 (opacity 0.55..0.85).
+8 streams per GPU (64 over 8 GPUs), frames of different streams are independent: streams are sharded over
+ranks with no collective on the data path ("scaling": "weak").  One STEP = one tick of every stream of this
+rank = 8 composited 4K frames.
+
+  value   frames/s with layers resident in HBM: per step the layers are pushed to their mixers and all 8
+          mixers are folded into one fused launch (descriptor upload + kernel), no host sync inside the region.
+  e2e     the same metric through the public call sequence a SwiftVideo pipeline makes, with HOST buffers:
+          uploadComputePicture of every layer (pinned host -> device), VideoMixer.mix, downloadComputePicture of
+          the composited frame (device -> pinned host), all inside the timed region.
+  roofline  algorithmic bytes of one launch (46 656 000 B/frame x 8 frames) / that launch's device time
+          (CUDA events around the kernel on its stream) against the measured HBM copy bandwidth.
+  cpu_baseline / --impl reference
+          the reference's own OpenCL kernel text compiled for the host (oracle/_ref) -- or the C port when that
+          build is absent -- folding the same 4K 8-layer frame on all host threads.
+
+L2 hygiene: the 8 streams of a step read 8 x 34.2 MB of distinct sources and write 8 x 12.4 MB of distinct
+targets (373 MB per step, the backing ring makes it 10 distinct targets per stream), three times the 126 MB L2;
+sources alternate between two device copies on successive steps.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+CANVAS = (3840, 2160)
+NLAYERS = 8
+STREAMS_PER_GPU = 8
+ALG_BYTES_PER_FRAME = 12441600 + 7 * 3110400 + 12441600  # sources read once + target written once
+METRIC = "4K 8-layer composite frames/sec"
+WORKLOAD = ("cfg4: 3840x2160 NV12 target, 8 NV12 layers (1x 3840x2160 full canvas + 7x 1920x1080 -> 1600x900), "
+            f"{STREAMS_PER_GPU} streams per GPU")
+
+
+def geometry():
+    import scenes
+    return scenes.cfg34_geometry(NLAYERS)
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---- our arm -------------------------------------------------------------------------------------------------
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import scenes
+    import swiftvideo_b200 as sv
+    from oracle import oracle as O
+    from swiftvideo_b200 import animator
+
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = sv.make_compute_context(local)
+    geo = geometry()
+    S = STREAMS_PER_GPU
+    rng_base = 1000 * 4
+
+    # ---- synthetic layers: pinned host pictures (e2e source) and two device copies (device-resident source)
+    host = [[None] * NLAYERS for _ in range(S)]
+    dev = [[[None] * NLAYERS for _ in range(S)] for _ in range(2)]
+    mats = []
+    for k, (ssz, pos, dsz, op) in enumerate(geo):
+        mats.append((animator.picture_state(CANVAS, ssz, pos, dsz, z=float(k)), op))
+    for s in range(S):
+        gstream = rank * S + s
+        for k, (ssz, pos, dsz, op) in enumerate(geo):
+            rng = np.random.default_rng(rng_base + 16 * gstream + k)
+            h = sv.create_picture_sample(ssz[0], ssz[1], sv.NV12, f"s{gstream}l{k}", "bench", pinned_from=ctx)
+            h.set_host_bytes(rng.integers(0, 256, size=ssz[0] * ssz[1] * 3 // 2, dtype=np.uint8))
+            (m, t, b), opacity = mats[k]
+            host[s][k] = h.with_(matrix=m, texture_matrix=t, border_matrix=b, opacity=opacity)
+            for c in range(2):
+                dev[c][s][k] = host[s][k].upload(ctx)
+    mixers = [sv.VideoMixer(ctx, CANVAS[0], CANVAS[1], sv.NV12, asset_id=f"mixer{rank * S + s}", workspace_id="bench") for s in range(S)]
+    ctx.synchronize()
+
+    def step_resident(i):
+        for s in range(S):
+            mixers[s].push_many(dev[i & 1][s])
+        return sv.VideoMixer.mix_many(mixers, i, wait=False)
+
+    def step_e2e(i):
+        ups = []
+        for s in range(S):
+            up = [host[s][k].upload(ctx, retain_cpu_buffer=False) for k in range(NLAYERS)]
+            mixers[s].push_many(up)
+            ups.append(up)
+        outs = sv.VideoMixer.mix_many(mixers, i, wait=False)
+        return [o.download(ctx, retain_gpu_buffer=True, wait=False) for o in outs]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, sample_clocks=False):
+        for i in range(warmup):
+            fn(i)
+        ctx.synchronize()
+        barrier()
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        timer = sv.Timer(ctx)
+        launches0 = sv.kernel_launch_count()
+        timer.start()
+        last = None
+        for i in range(steps):
+            last = fn(warmup + i)
+        timer.stop()
+        ms = timer.elapsed_ms()
+        for o in last:
+            o.wait()
+        barrier()
+        launches = sv.kernel_launch_count() - launches0
+        clocks = sampler.stop() if sampler else None
+        timer.close()
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, clocks
+
+    # ---- value: layers resident in HBM
+    ctx.launch_timing(True)
+    ms, launches, clocks = timed(step_resident, args.steps, args.warmup, sample_clocks=True)
+    kern_ms, kern_n = ctx.launch_timing_read()
+    ctx.launch_timing(False)
+    frames = S * world * args.steps
+    value = frames / (ms / 1e3)
+
+    # ---- e2e: host buffers in, host buffers out
+    e2e_steps = max(3, min(args.steps, args.e2e_steps))
+    e_ms, _, _ = timed(step_e2e, e2e_steps, max(3, min(args.warmup, 3)))
+    e2e_value = S * world * e2e_steps / (e_ms / 1e3)
+    h2d = S * (12441600 + 7 * 3110400)
+    d2h = S * 12441600
+
+    peak, peak_src = peaks()
+    roof = None
+    if kern_n:
+        per_launch_ms = kern_ms / kern_n
+        # warm-up launches are inside the timing window too; they run the same work, so the average stands
+        achieved = ALG_BYTES_PER_FRAME * S / (per_launch_ms / 1e3) / 1e9
+        roof = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": None, "peak_source": peak_src, "kernel": "svb_mix_tiled", "kernel_ms_per_launch": round(per_launch_ms, 4),
+                "algorithmic_bytes_per_launch": ALG_BYTES_PER_FRAME * S, "launches_timed": int(kern_n)}
+        tr = ROOT / "profiles" / "traffic.json"
+        if tr.exists():
+            try:
+                roof["traffic"] = json.loads(tr.read_text()).get("svb_mix_tiled_dram_bytes_per_launch")
+            except Exception:
+                pass
+
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8 (fp32 arithmetic, no FMA contraction)", "data": "synthetic (uniform u8 planes, seeded)",
+        "config": {"workload": WORKLOAD, "streams_total": S * world, "frames_per_step": S * world, "parallelism": f"streams sharded, {S}/GPU, no collective",
+                   "l2": "373 MB of distinct sources+targets per step (> 126 MB L2); sources alternate between two device copies",
+                   "bit_exact_vs_oracle": "tests/test_gpu_parity.py::test_cfg34_full_size"},
+        "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "ms_per_step": round(e_ms / e2e_steps, 4)},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+        "hbm_gbs_per_gpu_algorithmic": round(ALG_BYTES_PER_FRAME * value / world / 1e9, 1),
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_reference(budget_s=args.cpu_seconds)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    for m in mixers:
+        m.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---- the reference's kernels on the host cores ---------------------------------------------------------------
+
+def cpu_scene():
+    import scenes
+    from oracle import oracle as O
+    canvas, tf, layers, us = scenes.cfg34_scene(NLAYERS)
+    return O.Image(tf, canvas[0], canvas[1]), layers, us
+
+
+def cpu_reference(budget_s=15.0, steps=None, warmup=0):
+    """Frames/s of the reference kernels (oracle/_ref: the reference's OpenCL kernel text compiled for the host;
+    falls back to the C port) on all host threads, one 4K 8-layer frame per step."""
+    from oracle import oracle as O
+    lib, kind = O.best()
+    threads = O.host_threads()
+    target, layers, us = cpu_scene()
+    for _ in range(warmup):
+        lib.mix(target, layers, us, threads=threads)
+    t0 = time.perf_counter()
+    assert lib.mix(target, layers, us, threads=threads) == 0
+    first = time.perf_counter() - t0
+    if steps is None:
+        steps = int(max(1, min(40, budget_s / max(first, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        lib.mix(target, layers, us, threads=threads)
+    dt = time.perf_counter() - t0
+    return {"value": round(steps / dt, 3), "unit": "frames/s", "cores": threads, "kind": kind,
+            "sample": f"{steps} frames of one stream of the workload (3840x2160, 8 layers), rows split over {threads} threads",
+            "ms_per_frame": round(dt / steps * 1e3, 2)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    t0 = time.perf_counter()
+    base = cpu_reference(steps=args.steps, warmup=min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": base["ms_per_frame"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8 (fp32 arithmetic, no FMA contraction)", "data": "synthetic (uniform u8 planes, seeded)",
+            "config": {"workload": WORKLOAD, "note": "host CPU only: one step = one 4K 8-layer frame of one stream"},
+            "cpu_baseline": base, "e2e": {"value": base["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": round(time.perf_counter() - t0, 2)}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

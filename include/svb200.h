@@ -1,0 +1,192 @@
+/*
+ * svb200.h -- C ABI of libsvb200.so, the B200-native VideoMixer compute path.
+ *
+ * The reference (unpause-live/SwiftVideo @113d3d9) has no bespoke C ABI on this path: its FFI is the CUDA
+ * driver API re-exported by Sources/CCUDA/shim.h:1-4, driven from Swift in compute.cuda.swift.  A
+ * replacement therefore plugs in at two levels, and this header declares both:
+ *
+ *  (1) DEVICE MODULE.  svb_kernel_module_image() returns an sm_100a cubin for cuModuleLoadData whose entry
+ *      points carry the ComputeKernel case names and the parameter convention of
+ *      compute.cuda.swift:294-303 -- the reference's own runComputeKernel can launch them unchanged
+ *      ("level 1").
+ *  (2) HOST OPERATORS.  One C function per Swift free function / method of the hot path, same names (snake
+ *      case), argument meaning and error behaviour, so that a thin Swift module (`CSVB200`, a modulemap over
+ *      this header like CCUDA's) lets compute.swift / mix.video.swift forward to it ("level 2").
+ *      Citations below are file:line under /root/reference/Sources/SwiftVideo/.
+ *
+ * Handles are opaque; every function returns svb_status (0 = ok) unless noted and records a message for
+ * svb_last_error().  No CPU fallback exists: without a B200 and its driver every compute entry point fails
+ * with SVB_ERROR_DEVICE_NOT_AVAILABLE.
+ */
+#ifndef SVB200_H
+#define SVB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ComputeError (compute.swift:22-39), in declaration order */
+typedef enum svb_status {
+    SVB_OK = 0,
+    SVB_ERROR_INVALID_PLATFORM = 1,
+    SVB_ERROR_INVALID_DEVICE = 2,
+    SVB_ERROR_INVALID_OPERATION = 3,
+    SVB_ERROR_INVALID_VALUE = 4,
+    SVB_ERROR_INVALID_PROGRAM = 5,
+    SVB_ERROR_INVALID_CONTEXT = 6,
+    SVB_ERROR_DEVICE_NOT_AVAILABLE = 7,
+    SVB_ERROR_OUT_OF_MEMORY = 8,
+    SVB_ERROR_COMPILER_NOT_AVAILABLE = 9,
+    SVB_ERROR_COMPUTE_KERNEL_NOT_FOUND = 10,
+    SVB_ERROR_BAD_TARGET = 11,
+    SVB_ERROR_BAD_INPUT_DATA = 12,
+    SVB_ERROR_BAD_CONTEXT_STATE = 13,
+    SVB_ERROR_COMPILER_ERROR = 14,
+    SVB_ERROR_UNKNOWN = 15,
+    SVB_ERROR_NOT_IMPLEMENTED = 16
+} svb_status;
+
+/* PixelFormat (sample.pict.swift:20-33), in declaration order */
+typedef enum svb_pixel_format {
+    SVB_PIXEL_NV12 = 0, SVB_PIXEL_NV21, SVB_PIXEL_YUVS, SVB_PIXEL_ZVUY, SVB_PIXEL_Y420P, SVB_PIXEL_Y422P, SVB_PIXEL_Y444P,
+    SVB_PIXEL_RGBA, SVB_PIXEL_BGRA, SVB_PIXEL_SHAPE, SVB_PIXEL_TEXT, SVB_PIXEL_INVALID
+} svb_pixel_format;
+
+/* BufferType (sample.pict.swift:58-63) */
+typedef enum svb_buffer_type { SVB_BUFFER_SHARED = 0, SVB_BUFFER_CPU, SVB_BUFFER_GPU, SVB_BUFFER_INVALID } svb_buffer_type;
+
+/* ComputeDeviceType (compute.swift:41-46) */
+typedef enum svb_device_type { SVB_DEVICE_GPU = 0, SVB_DEVICE_CPU, SVB_DEVICE_ACCELERATOR, SVB_DEVICE_DEFAULT } svb_device_type;
+
+/* ComputeKernel (compute.swift:49-74), in declaration order; SVB_KERNEL_CUSTOM takes a name */
+typedef enum svb_compute_kernel {
+    SVB_KERNEL_IMG_NV12_NV12 = 0, SVB_KERNEL_IMG_BGRA_NV12, SVB_KERNEL_IMG_RGBA_NV12, SVB_KERNEL_IMG_BGRA_BGRA,
+    SVB_KERNEL_IMG_Y420P_Y420P, SVB_KERNEL_IMG_Y420P_NV12, SVB_KERNEL_IMG_CLEAR_NV12, SVB_KERNEL_IMG_CLEAR_YUVS,
+    SVB_KERNEL_IMG_CLEAR_BGRA, SVB_KERNEL_IMG_CLEAR_Y420P, SVB_KERNEL_IMG_CLEAR_RGBA, SVB_KERNEL_IMG_RGBA_Y420P,
+    SVB_KERNEL_IMG_BGRA_Y420P, SVB_KERNEL_SND_S16I_S16I, SVB_KERNEL_ME_FULLSEARCH, SVB_KERNEL_CUSTOM
+} svb_compute_kernel;
+
+/* VideoMixer compose strategy (ours; the reference only has the per-layer sequence) */
+typedef enum svb_mix_mode { SVB_MIX_FUSED = 0, SVB_MIX_PER_LAYER = 1, SVB_MIX_GENERIC = 2 } svb_mix_mode;
+
+typedef struct svb_context svb_context; /* ComputeContext  (compute.cuda.swift:60-73) */
+typedef struct svb_picture svb_picture; /* PictureSample   (sample.pict.linux.swift:105-249), immutable */
+typedef struct svb_mixer svb_mixer;     /* VideoMixer      (mix.video.swift:21) */
+typedef struct svb_timer svb_timer;     /* a pair of CUDA events on the context's streams */
+
+/* ImageUniforms (compute.swift:76-86): 236 bytes, what applyComputeImage uploads */
+typedef struct svb_image_uniforms {
+    float transform[16], texture_transform[16], border_matrix[16];
+    float fill_color[4];
+    float input_size[2], output_size[2];
+    float opacity, image_time, target_time;
+} svb_image_uniforms;
+
+/* Plane (sample.pict.swift:46-56) + where its bytes are */
+typedef struct svb_plane_info {
+    float width, height;
+    int32_t stride, bit_depth, components;
+    void* host;                 /* NULL when the sample has no CPU buffer */
+    unsigned long long device;  /* CUdeviceptr, 0 when the sample has no GPU buffer */
+    size_t size;                /* stride * height */
+} svb_plane_info;
+
+typedef struct svb_picture_info {
+    int32_t pixel_format, buffer_type;
+    float width, height;
+    int32_t plane_count;
+    svb_plane_info planes[3];
+    float matrix[16], texture_matrix[16], border_matrix[16], fill_color[4], opacity;
+    int32_t z_index;            /* zIndex(), sample.pict.linux.swift:116 */
+    int64_t pts, time, timescale;
+} svb_picture_info;
+
+/* ---- errors ------------------------------------------------------------------------------------------ */
+const char* svb_last_error(void);   /* message of the calling thread's last failure ("" if none) */
+const char* svb_version(void);
+
+/* ---- devices and contexts ---------------------------------------------------------------------------- */
+int svb_available_compute_devices(void);                      /* availableComputeDevices().count, compute.cuda.swift:132-153 */
+int svb_has_available_compute_devices(int device_type);       /* hasAvailableComputeDevices(forType:), compute.swift:112-119 */
+/* makeComputeContext(forType:) compute.swift:121-129 (upstream always takes devices.first = index 0) */
+svb_status svb_make_compute_context(int device_type, int device_index, svb_context** out);
+svb_status svb_create_compute_context_sharing(const svb_context* sharing, svb_context** out); /* compute.cuda.swift:155-157 */
+svb_status svb_destroy_compute_context(svb_context* ctx);      /* compute.cuda.swift:167-169 (+ frees the handle) */
+svb_status svb_begin_compute_pass(svb_context* ctx);           /* compute.cuda.swift:308-311 */
+svb_status svb_end_compute_pass(svb_context* ctx, int wait_for_completion); /* compute.cuda.swift:313-319 */
+int svb_context_device_index(const svb_context* ctx);
+int svb_context_sm_count(const svb_context* ctx);
+
+/* ---- kernels ----------------------------------------------------------------------------------------- */
+/* The sm_100a module with every kernel: feed it to cuModuleLoadData (compute.cuda.swift:193). */
+svb_status svb_kernel_module_image(const void** image, size_t* size);
+svb_status svb_default_compute_kernel_from_string(const char* name, int* kernel); /* compute.swift:90-110 */
+const char* svb_compute_kernel_name(int kernel);               /* String(describing: kernel) */
+/* buildComputeKernel compute.cuda.swift:171-201; image NULL = the built-in module, else a cubin/PTX image */
+svb_status svb_build_compute_kernel(svb_context* ctx, const char* name, const void* image);
+/* runComputeKernel<T> compute.cuda.swift:260-306 */
+svb_status svb_run_compute_kernel(svb_context* ctx, const svb_picture* const* images, int image_count, const svb_picture* target,
+                                  int kernel, const char* custom_name, int max_planes, const void* uniforms, size_t uniforms_size,
+                                  int blends);
+/* applyComputeImage compute.swift:145-170 */
+svb_status svb_apply_compute_image(svb_context* ctx, const svb_picture* image, const svb_picture* target, int kernel);
+/* the uniforms applyComputeImage would upload (compute.swift:149-161) */
+svb_status svb_make_image_uniforms(const svb_picture* image, const svb_picture* target, svb_image_uniforms* out);
+
+/* ---- pictures ---------------------------------------------------------------------------------------- */
+/* createPictureSample sample.pict.linux.swift:254-273; pinned_from != NULL makes the CPU buffer page-locked */
+svb_status svb_create_picture_sample(float width, float height, int pixel_format, const char* asset_id, const char* workspace_id,
+                                     svb_context* pinned_from, svb_picture** out);
+/* PictureSample(other, matrix:textureMatrix:borderMatrix:fillColor:opacity:revision:assetId:) :194-226; NULL keeps other's value.
+ * Matrices are 16 floats in VectorMath memory order (m11,m12,m13,m14,m21,...). */
+svb_status svb_picture_with(const svb_picture* other, const float* matrix, const float* texture_matrix, const float* border_matrix,
+                            const float* fill_color, const float* opacity, const char* revision, const char* asset_id,
+                            svb_picture** out);
+svb_status svb_picture_info_get(const svb_picture* pict, svb_picture_info* out);
+svb_status svb_picture_wait(const svb_picture* pict);          /* block until an asynchronously produced sample is complete */
+void svb_picture_release(svb_picture* pict);
+/* uploadComputePicture / downloadComputePicture compute.cuda.swift:359-402.  wait=1 is upstream's
+ * endComputePass(ctx, true); wait=0 returns at once (call svb_picture_wait before touching host bytes). */
+svb_status svb_upload_compute_picture(svb_context* ctx, const svb_picture* pict, int max_planes, int retain_cpu_buffer, svb_picture** out);
+svb_status svb_download_compute_picture(svb_context* ctx, const svb_picture* pict, int retain_gpu_buffer, int wait, svb_picture** out);
+
+/* ---- VideoMixer -------------------------------------------------------------------------------------- */
+/* VideoMixer.init mix.video.swift:22-30; ctx NULL = makeComputeContext(forType: .GPU); asset_id NULL = generated */
+svb_status svb_video_mixer_create(const svb_context* ctx, float width, float height, int pixel_format, const char* asset_id,
+                                  const char* workspace_id, int64_t frame_duration, int64_t timescale, int64_t epoch, svb_mixer** out);
+void svb_video_mixer_destroy(svb_mixer* mixer);
+const char* svb_video_mixer_asset_id(const svb_mixer* mixer);
+svb_status svb_video_mixer_set_mode(svb_mixer* mixer, int mode);
+/* the ingest closure mix.video.swift:57-75: *stored = 1 when kept as a layer, 0 when passed through */
+svb_status svb_video_mixer_push(svb_mixer* mixer, const svb_picture* pict, int* stored);
+svb_status svb_video_mixer_push_many(svb_mixer* mixer, const svb_picture* const* picts, int count);
+/* mix(at:) mix.video.swift:95-140: returns the emitted sample (a GPU PictureSample on the backing ring) */
+svb_status svb_video_mixer_mix(svb_mixer* mixer, int64_t time, int wait, svb_picture** out);
+/* several mixers of one context folded into one launch */
+svb_status svb_video_mixer_mix_many(svb_mixer* const* mixers, int count, int64_t time, int wait, svb_picture** outs);
+/* clear + fold with explicit uniforms (layers already in z-order) */
+svb_status svb_compose(svb_context* ctx, const svb_picture* target, const svb_picture* const* layers, const svb_image_uniforms* uniforms,
+                       int count, int mode);
+
+/* ---- device-side timing (bench) ---------------------------------------------------------------------- */
+svb_status svb_timer_create(svb_context* ctx, svb_timer** out);
+svb_status svb_timer_start(svb_timer* t);  /* after everything queued so far on the context's streams */
+svb_status svb_timer_stop(svb_timer* t);   /* after everything queued so far on the context's streams */
+svb_status svb_timer_elapsed_ms(svb_timer* t, float* ms); /* waits for stop */
+void svb_timer_destroy(svb_timer* t);
+/* CUDA events around every fused-compose kernel on the compute stream: total device time and launch count
+ * since timing was (re-)enabled.  Reading waits for the launches queued so far. */
+svb_status svb_launch_timing(svb_context* ctx, int enable);
+svb_status svb_launch_timing_read(svb_context* ctx, double* total_ms, unsigned long long* launches);
+/* launches of our kernels issued by this process so far */
+unsigned long long svb_kernel_launch_count(void);
+/* 256 floats each: UNORM8 read by the division-free identity and by true division (device self-test) */
+svb_status svb_selftest_unorm(svb_context* ctx, float* fast256, float* divided256);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,385 @@
+"""ctypes binding of libsvb200.so (include/svb200.h), shaped like the reference's Swift surface:
+makeComputeContext / createPictureSample / uploadComputePicture / VideoMixer ... (compute.swift, compute.cuda.swift,
+sample.pict.linux.swift, mix.video.swift of unpause-live/SwiftVideo)."""
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+_PKG = Path(__file__).resolve().parent
+_LIB_PATH = _PKG / "libsvb200.so"
+
+# PixelFormat / ComputeKernel / modes (svb200.h enums)
+NV12, NV21, YUVS, ZVUY, Y420P, Y422P, Y444P, RGBA, BGRA, SHAPE, TEXT, INVALID = range(12)
+BUFFER_SHARED, BUFFER_CPU, BUFFER_GPU, BUFFER_INVALID = range(4)
+DEVICE_GPU = 0
+KERNEL_CUSTOM = 15
+
+
+class MixMode:
+    FUSED, PER_LAYER, GENERIC = 0, 1, 2
+
+
+STATUS_NAMES = ["ok", "invalidPlatform", "invalidDevice", "invalidOperation", "invalidValue", "invalidProgram", "invalidContext",
+                "deviceNotAvailable", "outOfMemory", "compilerNotAvailable", "computeKernelNotFound", "badTarget", "badInputData",
+                "badContextState", "compilerError", "unknownError", "notImplemented"]
+
+
+class ComputeError(RuntimeError):
+    """ComputeError (compute.swift:22-39)."""
+
+    def __init__(self, code, message):
+        super().__init__(f"{STATUS_NAMES[code] if 0 <= code < len(STATUS_NAMES) else code}: {message}")
+        self.code = code
+        self.name = STATUS_NAMES[code] if 0 <= code < len(STATUS_NAMES) else str(code)
+
+
+class ImageUniforms(C.Structure):
+    """svb_image_uniforms == ImageUniforms (compute.swift:76-86), 236 bytes."""
+
+    _fields_ = [("transform", C.c_float * 16), ("texture_transform", C.c_float * 16), ("border_matrix", C.c_float * 16),
+                ("fill_color", C.c_float * 4), ("input_size", C.c_float * 2), ("output_size", C.c_float * 2),
+                ("opacity", C.c_float), ("image_time", C.c_float), ("target_time", C.c_float)]
+
+
+class _PlaneInfo(C.Structure):
+    _fields_ = [("width", C.c_float), ("height", C.c_float), ("stride", C.c_int32), ("bit_depth", C.c_int32),
+                ("components", C.c_int32), ("host", C.c_void_p), ("device", C.c_ulonglong), ("size", C.c_size_t)]
+
+
+class _PictureInfo(C.Structure):
+    _fields_ = [("pixel_format", C.c_int32), ("buffer_type", C.c_int32), ("width", C.c_float), ("height", C.c_float),
+                ("plane_count", C.c_int32), ("planes", _PlaneInfo * 3), ("matrix", C.c_float * 16),
+                ("texture_matrix", C.c_float * 16), ("border_matrix", C.c_float * 16), ("fill_color", C.c_float * 4),
+                ("opacity", C.c_float), ("z_index", C.c_int32), ("pts", C.c_int64), ("time", C.c_int64), ("timescale", C.c_int64)]
+
+
+def _load():
+    if not _LIB_PATH.exists():
+        raise ImportError(f"{_LIB_PATH} is missing: build it with `python -m swiftvideo_b200.build` "
+                          "(there is no CPU fallback for the CUDA path)")
+    l = C.CDLL(str(_LIB_PATH))
+    l.svb_last_error.restype = C.c_char_p
+    l.svb_version.restype = C.c_char_p
+    l.svb_compute_kernel_name.restype = C.c_char_p
+    l.svb_video_mixer_asset_id.restype = C.c_char_p
+    l.svb_kernel_launch_count.restype = C.c_ulonglong
+    l.svb_picture_release.restype = None
+    l.svb_video_mixer_destroy.restype = None
+    l.svb_timer_destroy.restype = None
+    l.svb_create_picture_sample.argtypes = [C.c_float, C.c_float, C.c_int, C.c_char_p, C.c_char_p, C.c_void_p, C.c_void_p]
+    l.svb_video_mixer_create.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_char_p, C.c_char_p, C.c_int64, C.c_int64,
+                                         C.c_int64, C.c_void_p]
+    l.svb_video_mixer_mix.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
+    l.svb_video_mixer_mix_many.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p]
+    l.svb_video_mixer_push.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    l.svb_video_mixer_push_many.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    l.svb_video_mixer_set_mode.argtypes = [C.c_void_p, C.c_int]
+    l.svb_picture_with.argtypes = [C.c_void_p] * 6 + [C.c_char_p, C.c_char_p, C.c_void_p]
+    l.svb_picture_info_get.argtypes = [C.c_void_p, C.c_void_p]
+    l.svb_picture_wait.argtypes = [C.c_void_p]
+    l.svb_picture_release.argtypes = [C.c_void_p]
+    l.svb_upload_compute_picture.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    l.svb_download_compute_picture.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    l.svb_compose.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    l.svb_run_compute_kernel.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_void_p,
+                                         C.c_size_t, C.c_int]
+    l.svb_apply_compute_image.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    l.svb_make_image_uniforms.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    l.svb_make_compute_context.argtypes = [C.c_int, C.c_int, C.c_void_p]
+    l.svb_create_compute_context_sharing.argtypes = [C.c_void_p, C.c_void_p]
+    l.svb_destroy_compute_context.argtypes = [C.c_void_p]
+    l.svb_begin_compute_pass.argtypes = [C.c_void_p]
+    l.svb_end_compute_pass.argtypes = [C.c_void_p, C.c_int]
+    l.svb_context_sm_count.argtypes = [C.c_void_p]
+    l.svb_context_device_index.argtypes = [C.c_void_p]
+    l.svb_build_compute_kernel.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+    l.svb_default_compute_kernel_from_string.argtypes = [C.c_char_p, C.c_void_p]
+    l.svb_kernel_module_image.argtypes = [C.c_void_p, C.c_void_p]
+    l.svb_timer_create.argtypes = [C.c_void_p, C.c_void_p]
+    for n in ("svb_timer_start", "svb_timer_stop", "svb_timer_destroy"):
+        getattr(l, n).argtypes = [C.c_void_p]
+    l.svb_timer_elapsed_ms.argtypes = [C.c_void_p, C.c_void_p]
+    l.svb_video_mixer_destroy.argtypes = [C.c_void_p]
+    l.svb_video_mixer_asset_id.argtypes = [C.c_void_p]
+    l.svb_launch_timing.argtypes = [C.c_void_p, C.c_int]
+    l.svb_launch_timing_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    l.svb_selftest_unorm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    return l
+
+
+lib = _load()
+
+
+def _check(status):
+    if status != 0:
+        raise ComputeError(status, lib.svb_last_error().decode())
+
+
+def _b(s):
+    return None if s is None else s.encode()
+
+
+def _f(arr, n):
+    if arr is None:
+        return None
+    a = np.ascontiguousarray(np.asarray(arr, dtype=np.float32).reshape(-1))
+    assert a.size == n
+    return (C.c_float * n)(*a.tolist())
+
+
+def available_compute_devices():
+    return lib.svb_available_compute_devices()
+
+
+def kernel_launch_count():
+    return int(lib.svb_kernel_launch_count())
+
+
+def kernel_module_image():
+    """bytes of the sm_100a cubin a host can cuModuleLoadData itself (INTEGRATION.md level 1)."""
+    p, n = C.c_void_p(), C.c_size_t()
+    _check(lib.svb_kernel_module_image(C.byref(p), C.byref(n)))
+    return C.string_at(p.value, n.value)
+
+
+def default_compute_kernel_from_string(name):
+    k = C.c_int()
+    _check(lib.svb_default_compute_kernel_from_string(name.encode(), C.byref(k)))
+    return k.value
+
+
+class ComputeContext:
+    def __init__(self, handle):
+        self._h = handle
+
+    @property
+    def sm_count(self):
+        return lib.svb_context_sm_count(self._h)
+
+    @property
+    def device_index(self):
+        return lib.svb_context_device_index(self._h)
+
+    def sharing(self):
+        """createComputeContext(sharing:)"""
+        h = C.c_void_p()
+        _check(lib.svb_create_compute_context_sharing(self._h, C.byref(h)))
+        return ComputeContext(h)
+
+    def synchronize(self):
+        """beginComputePass + endComputePass(ctx, true)"""
+        _check(lib.svb_begin_compute_pass(self._h))
+        _check(lib.svb_end_compute_pass(self._h, 1))
+
+    def build_compute_kernel(self, name, image=None):
+        buf = None if image is None else C.create_string_buffer(image, len(image))
+        _check(lib.svb_build_compute_kernel(self._h, name.encode(), buf))
+
+    def selftest_unorm(self):
+        a, b = np.zeros(256, np.float32), np.zeros(256, np.float32)
+        _check(lib.svb_selftest_unorm(self._h, a.ctypes.data, b.ctypes.data))
+        return a, b
+
+    def launch_timing(self, enable=True):
+        _check(lib.svb_launch_timing(self._h, int(enable)))
+
+    def launch_timing_read(self):
+        """(total device ms, launches) of the fused kernels since timing was enabled."""
+        ms, n = C.c_double(), C.c_ulonglong()
+        _check(lib.svb_launch_timing_read(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def close(self):
+        if self._h:
+            lib.svb_destroy_compute_context(self._h)
+            self._h = None
+
+
+def make_compute_context(device_index=0):
+    """makeComputeContext(forType: .GPU) -- device_index is the one extension (upstream takes devices.first)."""
+    h = C.c_void_p()
+    _check(lib.svb_make_compute_context(DEVICE_GPU, device_index, C.byref(h)))
+    return ComputeContext(h)
+
+
+class PictureSample:
+    def __init__(self, handle):
+        self._h = handle
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib.svb_picture_release(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def info(self):
+        i = _PictureInfo()
+        _check(lib.svb_picture_info_get(self._h, C.byref(i)))
+        return i
+
+    def pixel_format(self):
+        return self.info().pixel_format
+
+    def buffer_type(self):
+        return self.info().buffer_type
+
+    def z_index(self):
+        return self.info().z_index
+
+    def device_planes(self):
+        i = self.info()
+        return [i.planes[k].device for k in range(i.plane_count)]
+
+    def host_planes(self):
+        """numpy views (height x stride) over the CPU buffers; keep this sample alive while using them."""
+        i = self.info()
+        out = []
+        for k in range(i.plane_count):
+            p = i.planes[k]
+            if not p.host:
+                raise ComputeError(12, "sample has no CPU buffer")
+            buf = (C.c_uint8 * p.size).from_address(p.host)
+            a = np.frombuffer(buf, dtype=np.uint8).reshape(int(p.height), p.stride)
+            out.append(a)
+        return out
+
+    def host_bytes(self):
+        """All planes concatenated (the contiguous layout of createPictureSample)."""
+        return np.concatenate([p.reshape(-1) for p in self.host_planes()])
+
+    def set_host_bytes(self, data):
+        data = np.asarray(data, dtype=np.uint8).reshape(-1)
+        off = 0
+        for p in self.host_planes():
+            n = p.size
+            p.reshape(-1)[:] = data[off : off + n]
+            off += n
+        assert off == data.size, (off, data.size)
+
+    def with_(self, matrix=None, texture_matrix=None, border_matrix=None, fill_color=None, opacity=None, revision=None, asset_id=None):
+        """PictureSample(other, matrix:textureMatrix:borderMatrix:fillColor:opacity:revision:assetId:)."""
+        h = C.c_void_p()
+        op = None if opacity is None else C.c_float(opacity)
+        _check(lib.svb_picture_with(self._h, _f(matrix, 16), _f(texture_matrix, 16), _f(border_matrix, 16), _f(fill_color, 4),
+                                    C.cast(C.pointer(op), C.c_void_p) if op is not None else None, _b(revision), _b(asset_id), C.byref(h)))
+        return PictureSample(h)
+
+    def upload(self, ctx, max_planes=3, retain_cpu_buffer=True):
+        """uploadComputePicture"""
+        h = C.c_void_p()
+        _check(lib.svb_upload_compute_picture(ctx._h, self._h, max_planes, int(retain_cpu_buffer), C.byref(h)))
+        return PictureSample(h)
+
+    def download(self, ctx, retain_gpu_buffer=False, wait=True):
+        """downloadComputePicture"""
+        h = C.c_void_p()
+        _check(lib.svb_download_compute_picture(ctx._h, self._h, int(retain_gpu_buffer), int(wait), C.byref(h)))
+        return PictureSample(h)
+
+    def wait(self):
+        _check(lib.svb_picture_wait(self._h))
+
+
+def create_picture_sample(width, height, pixel_format, asset_id="", workspace_id="", pinned_from=None):
+    """createPictureSample; pinned_from=ctx makes the CPU buffer page-locked."""
+    h = C.c_void_p()
+    _check(lib.svb_create_picture_sample(width, height, pixel_format, asset_id.encode(), workspace_id.encode(),
+                                         pinned_from._h if pinned_from else None, C.byref(h)))
+    return PictureSample(h)
+
+
+def make_image_uniforms(image, target):
+    u = ImageUniforms()
+    _check(lib.svb_make_image_uniforms(image._h, target._h, C.byref(u)))
+    return u
+
+
+def apply_compute_image(ctx, image, target, kernel):
+    _check(lib.svb_apply_compute_image(ctx._h, image._h, target._h, kernel))
+
+
+def run_compute_kernel(ctx, images, target, kernel, uniforms=None, custom_name=None, blends=False):
+    arr = (C.c_void_p * max(len(images), 1))(*[i._h for i in images])
+    _check(lib.svb_run_compute_kernel(ctx._h, arr, len(images), target._h, kernel, _b(custom_name), 3,
+                                      C.cast(C.pointer(uniforms), C.c_void_p) if uniforms is not None else None,
+                                      C.sizeof(uniforms) if uniforms is not None else 0, int(blends)))
+
+
+def compose(ctx, target, layers, uniforms, mode=MixMode.FUSED):
+    """clear + fold `layers` (z-sorted) into `target` with explicit ImageUniforms (any 236-byte ctypes struct)."""
+    n = len(layers)
+    arr = (C.c_void_p * max(n, 1))(*[l._h for l in layers])
+    us = (ImageUniforms * max(n, 1))()
+    for i, u in enumerate(uniforms):
+        C.memmove(C.byref(us[i]), C.byref(u), 236)
+    _check(lib.svb_compose(ctx._h, target._h, arr, us, n, mode))
+
+
+class VideoMixer:
+    def __init__(self, ctx, width, height, pixel_format=NV12, asset_id=None, workspace_id="", frame_duration=1000, timescale=30000,
+                 epoch=0):
+        h = C.c_void_p()
+        _check(lib.svb_video_mixer_create(ctx._h if ctx else None, width, height, pixel_format, _b(asset_id), workspace_id.encode(),
+                                          frame_duration, timescale, epoch, C.byref(h)))
+        self._h = h
+
+    def asset_id(self):
+        return lib.svb_video_mixer_asset_id(self._h).decode()
+
+    def set_mode(self, mode):
+        _check(lib.svb_video_mixer_set_mode(self._h, mode))
+
+    def push(self, pict):
+        stored = C.c_int()
+        _check(lib.svb_video_mixer_push(self._h, pict._h, C.byref(stored)))
+        return bool(stored.value)
+
+    def push_many(self, picts):
+        arr = (C.c_void_p * len(picts))(*[p._h for p in picts])
+        _check(lib.svb_video_mixer_push_many(self._h, arr, len(picts)))
+
+    def mix(self, time, wait=True):
+        h = C.c_void_p()
+        _check(lib.svb_video_mixer_mix(self._h, time, int(wait), C.byref(h)))
+        return PictureSample(h)
+
+    @staticmethod
+    def mix_many(mixers, time, wait=True):
+        n = len(mixers)
+        arr = (C.c_void_p * n)(*[m._h for m in mixers])
+        outs = (C.c_void_p * n)()
+        _check(lib.svb_video_mixer_mix_many(arr, n, time, int(wait), outs))
+        return [PictureSample(C.c_void_p(outs[i])) for i in range(n)]
+
+    def close(self):
+        if self._h:
+            lib.svb_video_mixer_destroy(self._h)
+            self._h = None
+
+
+class Timer:
+    """CUDA-event stopwatch over the context's three streams."""
+
+    def __init__(self, ctx):
+        h = C.c_void_p()
+        _check(lib.svb_timer_create(ctx._h, C.byref(h)))
+        self._h = h
+
+    def start(self):
+        _check(lib.svb_timer_start(self._h))
+
+    def stop(self):
+        _check(lib.svb_timer_stop(self._h))
+
+    def elapsed_ms(self):
+        ms = C.c_float()
+        _check(lib.svb_timer_elapsed_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def close(self):
+        if self._h:
+            lib.svb_timer_destroy(self._h)
+            self._h = None

@@ -1,0 +1,408 @@
+// abi.cpp -- the C ABI declared in include/svb200.h over the C++ host side.
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/svb200.h"
+#include "compute.h"
+#include "cu_driver.h"
+#include "mix_video.h"
+
+using namespace svb;
+
+struct svb_context {
+    ComputeContext c;
+};
+struct svb_picture {
+    std::shared_ptr<const PictureSample> p;
+};
+struct svb_mixer {
+    std::unique_ptr<VideoMixer> m;
+};
+struct svb_timer {
+    std::shared_ptr<InternalContext> ic;
+    CUevent e0 = nullptr, e1 = nullptr, tmp = nullptr;
+};
+
+static thread_local std::string g_err;
+
+template <class F>
+static svb_status guard(F&& f) {
+    try {
+        f();
+        g_err.clear();
+        return SVB_OK;
+    } catch (const ComputeError& e) {
+        g_err = e.what();
+        return (svb_status)(int)e.code;
+    } catch (const std::bad_alloc&) {
+        g_err = "out of host memory";
+        return SVB_ERROR_OUT_OF_MEMORY;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return SVB_ERROR_UNKNOWN;
+    }
+}
+static void need(const void* p, const char* what) {
+    if (!p) throw ComputeError(ErrorCode::invalidValue, std::string(what) + " is NULL");
+}
+static svb_picture* wrap(PictureSample&& s) { return new svb_picture{std::make_shared<const PictureSample>(std::move(s))}; }
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+const char* svb_last_error(void) { return g_err.c_str(); }
+const char* svb_version(void) { return "svb200 0.1 (sm_100a)"; }
+
+int svb_available_compute_devices(void) { return (int)availableComputeDevices().size(); }
+int svb_has_available_compute_devices(int device_type) {
+    int n = 0;
+    for (const ComputeDevice& d : availableComputeDevices())
+        if ((int)d.deviceType == device_type && d.available) ++n;
+    return n > 0;
+}
+svb_status svb_make_compute_context(int device_type, int device_index, svb_context** out) {
+    return guard([&] {
+        need(out, "out");
+        *out = new svb_context{makeComputeContext((ComputeDeviceType)device_type, device_index)};
+    });
+}
+svb_status svb_create_compute_context_sharing(const svb_context* sharing, svb_context** out) {
+    return guard([&] {
+        need(sharing, "sharing");
+        need(out, "out");
+        *out = new svb_context{createComputeContext(sharing->c)};
+    });
+}
+svb_status svb_destroy_compute_context(svb_context* ctx) {
+    return guard([&] {
+        if (!ctx) return;
+        destroyComputeContext(ctx->c);
+        delete ctx;
+    });
+}
+svb_status svb_begin_compute_pass(svb_context* ctx) {
+    return guard([&] {
+        need(ctx, "ctx");
+        ctx->c = beginComputePass(ctx->c);
+    });
+}
+svb_status svb_end_compute_pass(svb_context* ctx, int wait) {
+    return guard([&] {
+        need(ctx, "ctx");
+        if (!ctx->c.ctx) throw ComputeError(ErrorCode::badContextState, "No context");
+        ctx->c = endComputePass(ctx->c, wait != 0);
+    });
+}
+int svb_context_device_index(const svb_context* ctx) { return ctx && ctx->c.ctx ? ctx->c.ctx->deviceIndex : -1; }
+int svb_context_sm_count(const svb_context* ctx) { return ctx && ctx->c.ctx ? ctx->c.ctx->smCount : 0; }
+
+svb_status svb_kernel_module_image(const void** image, size_t* size) {
+    return guard([&] {
+        need(image, "image");
+        need(size, "size");
+        kernelModuleImage(image, size);
+    });
+}
+svb_status svb_default_compute_kernel_from_string(const char* name, int* kernel) {
+    return guard([&] {
+        need(name, "name");
+        need(kernel, "kernel");
+        *kernel = (int)defaultComputeKernelFromString(name);
+    });
+}
+const char* svb_compute_kernel_name(int kernel) {
+    return kernel >= 0 && kernel < (int)ComputeKernel::count_ ? computeKernelName((ComputeKernel)kernel) : "invalid";
+}
+svb_status svb_build_compute_kernel(svb_context* ctx, const char* name, const void* image) {
+    return guard([&] {
+        need(ctx, "ctx");
+        need(name, "name");
+        ctx->c = buildComputeKernel(ctx->c, name, image);
+    });
+}
+svb_status svb_run_compute_kernel(svb_context* ctx, const svb_picture* const* images, int image_count, const svb_picture* target, int kernel,
+                                  const char* custom_name, int max_planes, const void* uniforms, size_t uniforms_size, int blends) {
+    return guard([&] {
+        need(ctx, "ctx");
+        need(target, "target");
+        std::vector<const PictureSample*> im;
+        for (int i = 0; i < image_count; ++i) {
+            need(images[i], "image");
+            im.push_back(images[i]->p.get());
+        }
+        if (kernel < 0 || kernel > (int)ComputeKernel::custom) throw ComputeError(ErrorCode::invalidValue, "bad kernel id");
+        ctx->c = runComputeKernel(ctx->c, im, *target->p, (ComputeKernel)kernel, custom_name ? custom_name : "", max_planes, uniforms,
+                                  uniforms_size, blends != 0);
+    });
+}
+svb_status svb_apply_compute_image(svb_context* ctx, const svb_picture* image, const svb_picture* target, int kernel) {
+    return guard([&] {
+        need(ctx, "ctx");
+        need(image, "image");
+        need(target, "target");
+        ctx->c = applyComputeImage(ctx->c, *image->p, *target->p, (ComputeKernel)kernel);
+    });
+}
+svb_status svb_make_image_uniforms(const svb_picture* image, const svb_picture* target, svb_image_uniforms* out) {
+    return guard([&] {
+        need(image, "image");
+        need(target, "target");
+        need(out, "out");
+        const ImageUniforms u = makeImageUniforms(*image->p, *target->p);
+        static_assert(sizeof(svb_image_uniforms) == sizeof(ImageUniforms), "uniform layout");
+        std::memcpy(out, &u, sizeof(u));
+    });
+}
+
+svb_status svb_create_picture_sample(float width, float height, int pixel_format, const char* asset_id, const char* workspace_id,
+                                     svb_context* pinned_from, svb_picture** out) {
+    return guard([&] {
+        need(out, "out");
+        if (pixel_format < 0 || pixel_format > (int)PixelFormat::invalid) throw ComputeError(ErrorCode::badInputData, "Invalid pixel format");
+        *out = wrap(createPictureSample(Vector2{width, height}, (PixelFormat)pixel_format, asset_id ? asset_id : "", workspace_id ? workspace_id : "",
+                                        pinned_from ? &pinned_from->c : nullptr));
+    });
+}
+svb_status svb_picture_with(const svb_picture* other, const float* matrix, const float* texture_matrix, const float* border_matrix,
+                            const float* fill_color, const float* opacity, const char* revision, const char* asset_id, svb_picture** out) {
+    return guard([&] {
+        need(other, "other");
+        need(out, "out");
+        PictureSample s = *other->p;  // sample.pict.linux.swift:194-226: every argument defaults to other's value
+        if (matrix) s.transform = Matrix4::from_array(matrix);
+        if (texture_matrix) s.texTransform = Matrix4::from_array(texture_matrix);
+        if (border_matrix) s.borderTransform = Matrix4::from_array(border_matrix);
+        if (fill_color) s.bgColor = Vector4{fill_color[0], fill_color[1], fill_color[2], fill_color[3]};
+        if (opacity) s.alpha = *opacity;
+        if (revision) s.idRevision = revision;
+        if (asset_id) s.idAsset = asset_id;
+        *out = wrap(std::move(s));
+    });
+}
+svb_status svb_picture_info_get(const svb_picture* pict, svb_picture_info* out) {
+    return guard([&] {
+        need(pict, "pict");
+        need(out, "out");
+        const PictureSample& s = *pict->p;
+        std::memset(out, 0, sizeof(*out));
+        out->pixel_format = (int)s.pixelFormat();
+        out->buffer_type = (int)s.bufferType();
+        out->width = s.size().x;
+        out->height = s.size().y;
+        out->plane_count = (int)s.imgBuffer.planes.size();
+        for (int i = 0; i < out->plane_count && i < 3; ++i) {
+            const Plane& p = s.imgBuffer.planes[i];
+            svb_plane_info& o = out->planes[i];
+            o.width = p.size.x, o.height = p.size.y, o.stride = p.stride, o.bit_depth = p.bitDepth, o.components = (int)p.components.size();
+            o.size = (size_t)p.stride * (size_t)(int)p.size.y;
+            o.host = i < (int)s.imgBuffer.buffers.size() ? s.imgBuffer.buffers[i].ptr : nullptr;
+            o.device = i < (int)s.imgBuffer.computeTextures.size() ? s.imgBuffer.computeTextures[i]->mem : 0;
+        }
+        std::memcpy(out->matrix, s.transform.data(), 64);
+        std::memcpy(out->texture_matrix, s.texTransform.data(), 64);
+        std::memcpy(out->border_matrix, s.borderTransform.data(), 64);
+        out->fill_color[0] = s.bgColor.x, out->fill_color[1] = s.bgColor.y, out->fill_color[2] = s.bgColor.z, out->fill_color[3] = s.bgColor.w;
+        out->opacity = s.alpha;
+        out->z_index = s.zIndex();
+        out->pts = s.ptsValue, out->time = s.timeValue, out->timescale = s.timescale;
+    });
+}
+svb_status svb_picture_wait(const svb_picture* pict) {
+    return guard([&] {
+        need(pict, "pict");
+        waitPicture(*pict->p);
+    });
+}
+void svb_picture_release(svb_picture* pict) { delete pict; }
+
+svb_status svb_upload_compute_picture(svb_context* ctx, const svb_picture* pict, int max_planes, int retain_cpu_buffer, svb_picture** out) {
+    return guard([&] {
+        need(ctx, "ctx");
+        need(pict, "pict");
+        need(out, "out");
+        *out = wrap(uploadComputePicture(ctx->c, *pict->p, max_planes, retain_cpu_buffer != 0));
+    });
+}
+svb_status svb_download_compute_picture(svb_context* ctx, const svb_picture* pict, int retain_gpu_buffer, int wait, svb_picture** out) {
+    return guard([&] {
+        need(ctx, "ctx");
+        need(pict, "pict");
+        need(out, "out");
+        *out = wrap(downloadComputePicture(ctx->c, *pict->p, retain_gpu_buffer != 0, wait != 0));
+    });
+}
+
+svb_status svb_video_mixer_create(const svb_context* ctx, float width, float height, int pixel_format, const char* asset_id,
+                                  const char* workspace_id, int64_t frame_duration, int64_t timescale, int64_t epoch, svb_mixer** out) {
+    return guard([&] {
+        need(out, "out");
+        if (pixel_format < 0 || pixel_format > (int)PixelFormat::invalid) throw ComputeError(ErrorCode::badInputData, "Invalid pixel format");
+        *out = new svb_mixer{std::make_unique<VideoMixer>(ctx ? &ctx->c : nullptr, Vector2{width, height}, (PixelFormat)pixel_format,
+                                                          asset_id ? asset_id : "", workspace_id ? workspace_id : "", frame_duration,
+                                                          timescale, epoch)};
+    });
+}
+void svb_video_mixer_destroy(svb_mixer* mixer) { delete mixer; }
+const char* svb_video_mixer_asset_id(const svb_mixer* mixer) { return mixer ? mixer->m->assetId().c_str() : ""; }
+svb_status svb_video_mixer_set_mode(svb_mixer* mixer, int mode) {
+    return guard([&] {
+        need(mixer, "mixer");
+        if (mode < 0 || mode > 2) throw ComputeError(ErrorCode::invalidValue, "bad mix mode");
+        mixer->m->setMode((VideoMixer::Mode)mode);
+    });
+}
+svb_status svb_video_mixer_push(svb_mixer* mixer, const svb_picture* pict, int* stored) {
+    return guard([&] {
+        need(mixer, "mixer");
+        need(pict, "pict");
+        const bool s = mixer->m->push(pict->p);
+        if (stored) *stored = s ? 1 : 0;
+    });
+}
+svb_status svb_video_mixer_push_many(svb_mixer* mixer, const svb_picture* const* picts, int count) {
+    return guard([&] {
+        need(mixer, "mixer");
+        for (int i = 0; i < count; ++i) {
+            need(picts[i], "pict");
+            mixer->m->push(picts[i]->p);
+        }
+    });
+}
+svb_status svb_video_mixer_mix(svb_mixer* mixer, int64_t time, int wait, svb_picture** out) {
+    return guard([&] {
+        need(mixer, "mixer");
+        need(out, "out");
+        *out = wrap(mixer->m->mix(time, wait != 0));
+    });
+}
+svb_status svb_video_mixer_mix_many(svb_mixer* const* mixers, int count, int64_t time, int wait, svb_picture** outs) {
+    return guard([&] {
+        need(mixers, "mixers");
+        need(outs, "outs");
+        std::vector<VideoMixer*> ms;
+        for (int i = 0; i < count; ++i) {
+            need(mixers[i], "mixer");
+            ms.push_back(mixers[i]->m.get());
+        }
+        std::vector<PictureSample> res(count);
+        VideoMixer::mixMany(ms.data(), count, time, res.data(), wait != 0);
+        for (int i = 0; i < count; ++i) outs[i] = wrap(std::move(res[i]));
+    });
+}
+svb_status svb_compose(svb_context* ctx, const svb_picture* target, const svb_picture* const* layers, const svb_image_uniforms* uniforms,
+                       int count, int mode) {
+    return guard([&] {
+        need(ctx, "ctx");
+        need(target, "target");
+        if (mode < 0 || mode > 2) throw ComputeError(ErrorCode::invalidValue, "bad mix mode");
+        std::vector<const PictureSample*> ls;
+        for (int i = 0; i < count; ++i) {
+            need(layers[i], "layer");
+            ls.push_back(layers[i]->p.get());
+        }
+        ctx->c = VideoMixer::composeRaw(ctx->c, *target->p, ls, (const ImageUniforms*)uniforms, (VideoMixer::Mode)mode);
+    });
+}
+
+svb_status svb_timer_create(svb_context* ctx, svb_timer** out) {
+    return guard([&] {
+        need(ctx, "ctx");
+        need(out, "out");
+        if (!ctx->c.ctx) throw ComputeError(ErrorCode::badContextState, "No context");
+        auto t = std::make_unique<svb_timer>();
+        t->ic = ctx->c.ctx;
+        CtxGuard g(t->ic);
+        check(cu().cuEventCreate(&t->e0, CU_EVENT_DEFAULT), "cuEventCreate");
+        check(cu().cuEventCreate(&t->e1, CU_EVENT_DEFAULT), "cuEventCreate");
+        check(cu().cuEventCreate(&t->tmp, CU_EVENT_DISABLE_TIMING), "cuEventCreate");
+        *out = t.release();
+    });
+}
+// Join the upload and download streams into the compute stream, then stamp the compute stream.
+static void stamp(svb_timer* t, CUevent e) {
+    CtxGuard g(t->ic);
+    for (CUstream s : {t->ic->upload, t->ic->download}) {
+        check(cu().cuEventRecord(t->tmp, s), "cuEventRecord");
+        check(cu().cuStreamWaitEvent(t->ic->compute, t->tmp, 0), "cuStreamWaitEvent");
+    }
+    check(cu().cuEventRecord(e, t->ic->compute), "cuEventRecord");
+    // and nothing queued later on the side streams may start before the stamp
+    check(cu().cuStreamWaitEvent(t->ic->upload, e, 0), "cuStreamWaitEvent");
+    check(cu().cuStreamWaitEvent(t->ic->download, e, 0), "cuStreamWaitEvent");
+}
+svb_status svb_timer_start(svb_timer* t) {
+    return guard([&] {
+        need(t, "timer");
+        stamp(t, t->e0);
+    });
+}
+svb_status svb_timer_stop(svb_timer* t) {
+    return guard([&] {
+        need(t, "timer");
+        stamp(t, t->e1);
+    });
+}
+svb_status svb_timer_elapsed_ms(svb_timer* t, float* ms) {
+    return guard([&] {
+        need(t, "timer");
+        need(ms, "ms");
+        CtxGuard g(t->ic);
+        check(cu().cuEventSynchronize(t->e1), "cuEventSynchronize");
+        check(cu().cuEventElapsedTime(ms, t->e0, t->e1), "cuEventElapsedTime");
+    });
+}
+void svb_timer_destroy(svb_timer* t) {
+    if (!t) return;
+    if (cu().ok) {
+        cu().cuCtxPushCurrent(t->ic->ctx);
+        for (CUevent e : {t->e0, t->e1, t->tmp})
+            if (e) cu().cuEventDestroy(e);
+        CUcontext old;
+        cu().cuCtxPopCurrent(&old);
+    }
+    delete t;
+}
+
+svb_status svb_launch_timing(svb_context* ctx, int enable) {
+    return guard([&] {
+        need(ctx, "ctx");
+        if (!ctx->c.ctx) throw ComputeError(ErrorCode::badContextState, "No context");
+        setLaunchTiming(ctx->c, enable != 0);
+    });
+}
+svb_status svb_launch_timing_read(svb_context* ctx, double* total_ms, unsigned long long* launches) {
+    return guard([&] {
+        need(ctx, "ctx");
+        need(total_ms, "total_ms");
+        need(launches, "launches");
+        if (!ctx->c.ctx) throw ComputeError(ErrorCode::badContextState, "No context");
+        readLaunchTiming(ctx->c, total_ms, launches);
+    });
+}
+
+unsigned long long svb_kernel_launch_count(void) { return kernelLaunchCount(); }
+
+svb_status svb_selftest_unorm(svb_context* ctx, float* fast256, float* divided256) {
+    return guard([&] {
+        need(ctx, "ctx");
+        need(fast256, "fast256");
+        need(divided256, "divided256");
+        if (!ctx->c.ctx) throw ComputeError(ErrorCode::badContextState, "No context");
+        auto ic = ctx->c.ctx;
+        CtxGuard g(ic);
+        CUdeviceptr buf = ic->alloc(2048);
+        CUdeviceptr a = buf, b = buf + 1024;
+        void* args[] = {&a, &b};
+        check(cu().cuLaunchKernel(ic->builtin("svb_selftest_unorm"), 1, 1, 1, 256, 1, 1, 0, ic->compute, args, nullptr), "cuLaunchKernel");
+        noteKernelLaunch();
+        check(cu().cuStreamSynchronize(ic->compute), "cuStreamSynchronize");
+        check(cu().cuMemcpyDtoH(fast256, a, 1024), "cuMemcpyDtoH");
+        check(cu().cuMemcpyDtoH(divided256, b, 1024), "cuMemcpyDtoH");
+        ic->release(buf, 2048);
+    });
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

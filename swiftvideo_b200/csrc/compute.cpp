@@ -1,0 +1,542 @@
+// compute.cpp -- host side of the compute path (see compute.h for the reference map).
+#include "compute.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+
+#include "cu_driver.h"
+
+extern "C" {
+extern const unsigned char svb200_kernels_cubin[];  // generated from kernels.cu by build.py
+extern const unsigned long long svb200_kernels_cubin_len;
+}
+
+namespace svb {
+
+static std::atomic<unsigned long long> g_launches{0};
+unsigned long long kernelLaunchCount() { return g_launches.load(); }
+void noteKernelLaunch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---- errors ---------------------------------------------------------------------------------------------
+
+void check(CUresult r, const char* where) {  // compute.cuda.swift:102-112
+    if (r == CUDA_SUCCESS) return;
+    const char* s = nullptr;
+    if (cu().ok) cu().cuGetErrorString(r, &s);
+    std::string msg = std::string(where) + ": " + (s ? s : "CUDA error") + " (" + std::to_string((int)r) + ")";
+    switch (r) {
+    case CUDA_ERROR_INVALID_VALUE: throw ComputeError(ErrorCode::invalidValue, msg);
+    case CUDA_ERROR_OUT_OF_MEMORY: throw ComputeError(ErrorCode::outOfMemory, msg);
+    case CUDA_ERROR_INVALID_CONTEXT: throw ComputeError(ErrorCode::invalidContext, msg);
+    case CUDA_ERROR_ILLEGAL_ADDRESS: throw ComputeError(ErrorCode::badContextState, "Illegal address access: " + msg);
+    case CUDA_ERROR_NOT_FOUND: throw ComputeError(ErrorCode::badInputData, "Symbol not found: " + msg);
+    default: throw ComputeError(ErrorCode::unknownError, msg);
+    }
+}
+
+static const CuDriver& drv() {
+    const CuDriver& d = cu();
+    if (!d.ok) throw ComputeError(ErrorCode::deviceNotAvailable, std::string("CUDA driver unavailable: ") + d.why);
+    return d;
+}
+
+// ---- kernel names ---------------------------------------------------------------------------------------
+
+static const char* kKernelNames[] = {"img_nv12_nv12",  "img_bgra_nv12",  "img_rgba_nv12",  "img_bgra_bgra",   "img_y420p_y420p",
+                                     "img_y420p_nv12", "img_clear_nv12", "img_clear_yuvs", "img_clear_bgra",  "img_clear_y420p",
+                                     "img_clear_rgba", "img_rgba_y420p", "img_bgra_y420p", "snd_s16i_s16i",   "me_fullsearch",
+                                     "custom"};
+
+const char* computeKernelName(ComputeKernel k) { return kKernelNames[(int)k]; }
+
+ComputeKernel defaultComputeKernelFromString(const std::string& name) {  // compute.swift:90-110
+    static const std::map<std::string, ComputeKernel> m = {
+        {"img_nv12_nv12", ComputeKernel::img_nv12_nv12},     {"img_bgra_nv12", ComputeKernel::img_bgra_nv12},
+        {"img_rgba_nv12", ComputeKernel::img_rgba_nv12},     {"img_bgra_bgra", ComputeKernel::img_bgra_bgra},
+        {"img_y420p_y420p", ComputeKernel::img_y420p_y420p}, {"img_y420p_nv12", ComputeKernel::img_y420p_nv12},
+        {"img_clear_nv12", ComputeKernel::img_clear_nv12},   {"img_clear_yuvs", ComputeKernel::img_clear_yuvs},
+        {"img_clear_bgra", ComputeKernel::img_clear_bgra},   {"img_clear_rgba", ComputeKernel::img_clear_bgra},  // :101
+        {"img_rgba_y420p", ComputeKernel::img_rgba_y420p},   {"img_bgra_y420p", ComputeKernel::img_bgra_y420p},
+        {"img_clear_y420p", ComputeKernel::img_clear_y420p}};
+    auto it = m.find(name);
+    if (it == m.end()) throw ComputeError(ErrorCode::invalidValue, "no default compute kernel named " + name);
+    return it->second;
+}
+
+const char* pixelFormatName(PixelFormat f) {
+    static const char* n[] = {"nv12", "nv21", "yuvs", "zvuy", "y420p", "y422p", "y444p", "rgba", "bgra", "shape", "text", "invalid"};
+    return n[(int)f];
+}
+
+// ---- context --------------------------------------------------------------------------------------------
+
+CtxGuard::CtxGuard(const std::shared_ptr<InternalContext>& c) { check(drv().cuCtxPushCurrent(c->ctx), "cuCtxPushCurrent"); }
+CtxGuard::~CtxGuard() {
+    CUcontext old;
+    cu().cuCtxPopCurrent(&old);
+}
+
+InternalContext::~InternalContext() {
+    if (!ctx || !cu().ok) return;
+    cu().cuCtxPushCurrent(ctx);
+    cu().cuCtxSynchronize();
+    if (mixerSharedFree) mixerSharedFree(this);
+    for (auto& kv : pool) {
+        cu().cuMemFree(kv.second.p);
+        for (CUevent e : kv.second.after)
+            if (e) cu().cuEventDestroy(e);
+    }
+    for (CUevent e : spareEvents) cu().cuEventDestroy(e);
+    if (module) cu().cuModuleUnload(module);
+    if (compute) cu().cuStreamDestroy(compute);
+    if (upload) cu().cuStreamDestroy(upload);
+    if (download) cu().cuStreamDestroy(download);
+    CUcontext old;
+    cu().cuCtxPopCurrent(&old);
+    cu().cuDevicePrimaryCtxRelease(device);
+}
+
+// Freed blocks are recycled (upstream cuMemAllocs per upload and frees in deinit).  A block can be released
+// while work that touches it is still queued, so release() records the tail of each stream and alloc()
+// makes every stream wait for those tails before the block's next user can touch it.  By the time a block
+// comes round again the events have normally fired and the waits cost nothing.
+CUdeviceptr InternalContext::alloc(size_t size) {
+    size = (size + 255) & ~(size_t)255;
+    Block b;
+    bool hit = false;
+    {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = pool.find(size);
+        if (it != pool.end()) {
+            b = it->second;
+            pool.erase(it);
+            hit = true;
+        }
+    }
+    if (hit) {
+        CUstream all[3] = {compute, upload, download};
+        for (CUevent e : b.after) {
+            if (!e) continue;
+            if (cu().cuEventQuery(e) != CUDA_SUCCESS)
+                for (CUstream s : all) cu().cuStreamWaitEvent(s, e, 0);
+            std::lock_guard<std::mutex> g(mu);
+            spareEvents.push_back(e);
+        }
+        return b.p;
+    }
+    CUdeviceptr p = 0;
+    check(drv().cuMemAlloc(&p, size), "cuMemAlloc");
+    return p;
+}
+void InternalContext::release(CUdeviceptr p, size_t size) {
+    size = (size + 255) & ~(size_t)255;
+    Block b;
+    b.p = p;
+    if (cu().ok && ctx) {
+        cu().cuCtxPushCurrent(ctx);
+        CUstream all[3] = {compute, upload, download};
+        for (int i = 0; i < 3; ++i) {
+            CUevent e = nullptr;
+            {
+                std::lock_guard<std::mutex> g(mu);
+                if (!spareEvents.empty()) {
+                    e = spareEvents.back();
+                    spareEvents.pop_back();
+                }
+            }
+            if (!e && cu().cuEventCreate(&e, CU_EVENT_DISABLE_TIMING) != CUDA_SUCCESS) e = nullptr;
+            if (e && cu().cuEventRecord(e, all[i]) == CUDA_SUCCESS) b.after[i] = e;
+        }
+        CUcontext old;
+        cu().cuCtxPopCurrent(&old);
+    }
+    std::lock_guard<std::mutex> g(mu);
+    pool.emplace(size, b);
+}
+
+CUfunction InternalContext::builtin(const char* name) {
+    CUfunction f = nullptr;
+    check(drv().cuModuleGetFunction(&f, module, name), name);
+    return f;
+}
+
+Event::Event(std::shared_ptr<InternalContext> c) : ctx(std::move(c)) {
+    CtxGuard g(ctx);
+    check(drv().cuEventCreate(&e, CU_EVENT_DISABLE_TIMING), "cuEventCreate");
+}
+Event::~Event() {
+    if (e && cu().ok) {
+        cu().cuCtxPushCurrent(ctx->ctx);
+        cu().cuEventDestroy(e);
+        CUcontext old;
+        cu().cuCtxPopCurrent(&old);
+    }
+}
+
+ComputeBuffer::~ComputeBuffer() {  // compute.cuda.swift:82-88
+    if (mem && ctx) ctx->release(mem, size);
+}
+
+CUDAProgram::~CUDAProgram() {
+    if (ownsModule && module && cu().ok && ctx) {
+        cu().cuCtxPushCurrent(ctx->ctx);
+        cu().cuModuleUnload(module);
+        CUcontext old;
+        cu().cuCtxPopCurrent(&old);
+    }
+}
+
+std::vector<ComputeDevice> availableComputeDevices() {  // compute.cuda.swift:132-153
+    std::vector<ComputeDevice> out;
+    if (!cu().ok) return out;  // upstream: catch -> []
+    int n = 0;
+    if (cu().cuDeviceGetCount(&n) != CUDA_SUCCESS) return out;
+    for (int i = 0; i < n; ++i) {
+        ComputeDevice d;
+        int mode = 0;
+        if (cu().cuDeviceGet(&d.device, i) != CUDA_SUCCESS) return {};
+        if (cu().cuDeviceGetAttribute(&mode, CU_DEVICE_ATTRIBUTE_COMPUTE_MODE, d.device) != CUDA_SUCCESS) return {};
+        d.index = i;
+        d.available = mode == CU_COMPUTEMODE_DEFAULT;
+        out.push_back(d);
+    }
+    return out;
+}
+
+void kernelModuleImage(const void** image, size_t* size) {
+    *image = svb200_kernels_cubin;
+    *size = (size_t)svb200_kernels_cubin_len;
+}
+
+ComputeContext createComputeContext(const ComputeDevice& device) {  // compute.cuda.swift:159-165
+    const CuDriver& d = drv();
+    auto ic = std::make_shared<InternalContext>();
+    ic->device = device.device;
+    ic->deviceIndex = device.index;
+    // Upstream: cuCtxCreate_v2.  We retain the device's primary context instead so that memory and streams
+    // interoperate with anything else in the process that uses the CUDA runtime (torch in tests/bench).
+    check(d.cuDevicePrimaryCtxRetain(&ic->ctx, device.device), "cuDevicePrimaryCtxRetain");
+    CtxGuard g(ic);
+    check(d.cuDeviceGetAttribute(&ic->smCount, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, device.device), "cuDeviceGetAttribute");
+    check(d.cuStreamCreate(&ic->compute, CU_STREAM_NON_BLOCKING), "cuStreamCreate");
+    check(d.cuStreamCreate(&ic->upload, CU_STREAM_NON_BLOCKING), "cuStreamCreate");
+    check(d.cuStreamCreate(&ic->download, CU_STREAM_NON_BLOCKING), "cuStreamCreate");
+    CUresult r = d.cuModuleLoadData(&ic->module, svb200_kernels_cubin);
+    if (r != CUDA_SUCCESS)
+        throw ComputeError(ErrorCode::invalidProgram,
+                           "cuModuleLoadData(svb200 sm_100a module) failed (" + std::to_string((int)r) +
+                               "): this build runs on B200 (sm_100a) only");
+    ComputeContext c;
+    c.ctx = ic;
+    return c;
+}
+
+ComputeContext createComputeContext(const ComputeContext& sharing) {  // :155-157
+    ComputeContext c;
+    c.ctx = sharing.ctx;
+    return c;
+}
+
+void destroyComputeContext(ComputeContext& ctx) {  // :167-169: released with the last reference
+    ctx.library.clear();
+    ctx.ctx.reset();
+}
+
+ComputeContext makeComputeContext(ComputeDeviceType type, int deviceIndex) {  // compute.swift:121-129
+    std::vector<ComputeDevice> devs;
+    for (const ComputeDevice& d : availableComputeDevices())
+        if (d.deviceType == type && d.available) devs.push_back(d);
+    if (deviceIndex < 0 || deviceIndex >= (int)devs.size())
+        throw ComputeError(ErrorCode::deviceNotAvailable, cu().ok ? "no such compute device" : std::string("no compute device: ") + cu().why);
+    return createComputeContext(devs[deviceIndex]);
+}
+
+ComputeContext buildComputeKernel(const ComputeContext& ctx, const std::string& name, const void* image) {  // :171-201
+    if (!ctx.ctx) throw ComputeError(ErrorCode::badContextState, "No context");
+    CtxGuard g(ctx.ctx);
+    auto prog = std::make_shared<CUDAProgram>();
+    prog->ctx = ctx.ctx;
+    if (image) {
+        check(drv().cuModuleLoadData(&prog->module, image), "cuModuleLoadData");
+        prog->ownsModule = true;
+    } else {
+        prog->module = ctx.ctx->module;
+    }
+    CUresult r = drv().cuModuleGetFunction(&prog->function, prog->module, name.c_str());
+    if (r == CUDA_ERROR_NOT_FOUND) throw ComputeError(ErrorCode::badInputData, "Symbol not found: " + name);
+    check(r, "cuModuleGetFunction");
+    ComputeContext out = ctx;
+    out.library[name] = prog;  // merging { $1 }: the new program replaces an older one of the same name
+    return out;
+}
+
+// maybeBuildKernel (:203-218): a name already in the library wins; otherwise the built-in of that name is
+// loaded; a name with no built-in throws computeKernelNotFound.
+static ComputeContext maybeBuildKernel(const ComputeContext& ctx, ComputeKernel kernel, const std::string& customName) {
+    const std::string name = kernel == ComputeKernel::custom ? customName : computeKernelName(kernel);
+    if (ctx.library.count(name)) return ctx;
+    static const char* builtins[] = {"img_clear_nv12", "img_clear_y420p", "img_clear_bgra", "img_nv12_nv12",
+                                     "img_y420p_nv12", "img_y420p_y420p", "img_bgra_nv12",  "img_rgba_nv12",
+                                     "img_bgra_y420p", "img_rgba_y420p"};
+    bool have = false;
+    for (const char* b : builtins) have = have || name == b;
+    if (!have) throw ComputeError(ErrorCode::computeKernelNotFound, "computeKernelNotFound(" + name + ")");
+    return buildComputeKernel(ctx, name, nullptr);
+}
+
+ComputeContext beginComputePass(const ComputeContext& ctx) {  // :308-311
+    if (!ctx.ctx) throw ComputeError(ErrorCode::badContextState, "No context");
+    check(drv().cuCtxPushCurrent(ctx.ctx->ctx), "cuCtxPushCurrent");
+    return ctx;
+}
+ComputeContext endComputePass(const ComputeContext& ctx, bool waitForCompletion) {  // :313-319
+    if (waitForCompletion) {
+        // upstream: cuCtxSynchronize. Equivalent for our work: drain the streams this context launches on.
+        cu().cuStreamSynchronize(ctx.ctx->upload);
+        cu().cuStreamSynchronize(ctx.ctx->compute);
+        cu().cuStreamSynchronize(ctx.ctx->download);
+    }
+    CUcontext old;
+    cu().cuCtxPopCurrent(&old);
+    return ctx;
+}
+
+// ---- buffers --------------------------------------------------------------------------------------------
+
+static std::shared_ptr<ComputeBuffer> createBuffer(const ComputeContext& ctx, size_t size) {  // :404-410
+    CtxGuard g(ctx.ctx);
+    return std::make_shared<ComputeBuffer>(ctx.ctx->alloc(size), size, ctx.ctx);
+}
+
+std::shared_ptr<ComputeBuffer> uploadComputeBuffer(const ComputeContext& ctx, const void* src, size_t size,
+                                                   std::shared_ptr<ComputeBuffer> dst) {  // :330-342
+    if (!src) throw ComputeError(ErrorCode::invalidValue, "uploadComputeBuffer: null source");
+    auto buf = dst ? dst : createBuffer(ctx, size);
+    if (buf->size < size) throw ComputeError(ErrorCode::badInputData, "Compute buffer needs to be >= to data.count");
+    CtxGuard g(ctx.ctx);
+    check(drv().cuMemcpyHtoDAsync(buf->mem, src, size, ctx.ctx->upload), "cuMemcpyHtoDAsync");
+    if (!buf->ready) buf->ready = std::make_shared<Event>(ctx.ctx);
+    check(drv().cuEventRecord(buf->ready->e, ctx.ctx->upload), "cuEventRecord");
+    return buf;
+}
+
+void downloadComputeBuffer(const ComputeContext& ctx, const ComputeBuffer& src, void* dst, size_t dstSize) {  // :344-357
+    if (dstSize < src.size) throw ComputeError(ErrorCode::badInputData, "Destination data buffer must be >= buffer.size");
+    CtxGuard g(ctx.ctx);
+    check(drv().cuMemcpyDtoHAsync(dst, src.mem, src.size, ctx.ctx->download), "cuMemcpyDtoHAsync");
+}
+
+// ---- pictures -------------------------------------------------------------------------------------------
+
+std::vector<Plane> planesForFormat(PixelFormat f, Vector2 size) {  // sample.pict.linux.swift:275-294
+    const int width = (int)size.x;
+    const Vector2 half{size.x / 2, size.y / 2};
+    switch (f) {
+    case PixelFormat::nv12:
+        return {Plane{size, width, 8, {Component::y}}, Plane{half, width, 8, {Component::cb, Component::cr}}};
+    case PixelFormat::BGRA:
+    case PixelFormat::RGBA:
+        return {Plane{size, width * 4, 8, {Component::r, Component::g, Component::b, Component::a}}};
+    case PixelFormat::yuvs:
+        return {Plane{size, width * 2, 8, {Component::cr, Component::y, Component::cb, Component::y}}};
+    case PixelFormat::zvuy:
+        return {Plane{size, width * 2, 8, {Component::y, Component::cb, Component::y, Component::cr}}};
+    case PixelFormat::y420p:
+        return {Plane{size, width, 8, {Component::y}}, Plane{half, width / 2, 8, {Component::cb}}, Plane{half, width / 2, 8, {Component::cr}}};
+    default:
+        throw ComputeError(ErrorCode::badInputData, "Invalid pixel format");
+    }
+}
+
+PictureSample createPictureSample(Vector2 size, PixelFormat format, const std::string& assetId,
+                                  const std::string& workspaceId, ComputeContext* pinnedFrom) {  // :254-273
+    if (!(size.x > 0 && size.y > 0)) throw ComputeError(ErrorCode::invalidOperation, "createPictureSample: empty size");
+    PictureSample s;
+    s.imgBuffer.planes = planesForFormat(format, size);
+    size_t total = 0;
+    for (const Plane& p : s.imgBuffer.planes) total += (size_t)p.stride * (size_t)(int)p.size.y;
+    std::shared_ptr<uint8_t> base;
+    if (pinnedFrom && pinnedFrom->ctx) {
+        CtxGuard g(pinnedFrom->ctx);
+        void* p = nullptr;
+        check(drv().cuMemHostAlloc(&p, total, 0), "cuMemHostAlloc");
+        auto ic = pinnedFrom->ctx;
+        base = std::shared_ptr<uint8_t>((uint8_t*)p, [ic](uint8_t* q) {
+            if (cu().ok) {
+                cu().cuCtxPushCurrent(ic->ctx);
+                cu().cuMemFreeHost(q);
+                CUcontext old;
+                cu().cuCtxPopCurrent(&old);
+            }
+        });
+    } else {
+        void* p = nullptr;
+        if (posix_memalign(&p, 4096, std::max<size_t>(total, 1)) != 0) throw ComputeError(ErrorCode::outOfMemory, "host allocation failed");
+        base = std::shared_ptr<uint8_t>((uint8_t*)p, [](uint8_t* q) { free(q); });
+    }
+    size_t off = 0;
+    for (const Plane& p : s.imgBuffer.planes) {
+        size_t len = (size_t)p.stride * (size_t)(int)p.size.y;
+        s.imgBuffer.buffers.push_back(HostData{base, base.get() + off, len});
+        off += len;
+    }
+    s.imgBuffer.pixelFormat = format;
+    s.imgBuffer.bufferType = BufferType::cpu;
+    s.imgBuffer.size = size;
+    s.idAsset = assetId;
+    s.idWorkspace = workspaceId;
+    s.idRevision = assetId;  // :214
+    return s;
+}
+
+// createTexture (compute.cuda.swift:413-431): one device buffer of stride*height per plane.
+static std::vector<std::shared_ptr<ComputeBuffer>> createTexture(const ComputeContext& ctx, const ImageBuffer& image, int maxPlanes) {
+    if (image.bufferType != BufferType::cpu) return image.computeTextures;
+    const int planeCount = (int)image.planes.size();
+    if (!(planeCount <= 3 && planeCount > 0)) throw ComputeError(ErrorCode::badInputData, "Input image must have 1, 2, or 3 planes");
+    if (planeCount != (int)image.buffers.size())
+        throw ComputeError(ErrorCode::badInputData, "Input image must have the same number of buffers as planes");
+    std::vector<std::shared_ptr<ComputeBuffer>> out;
+    for (int i = 0; i < std::min(planeCount, maxPlanes); ++i)
+        out.push_back(createBuffer(ctx, (size_t)(int)image.planes[i].size.y * (size_t)image.planes[i].stride));
+    return out;
+}
+
+PictureSample uploadComputePicture(const ComputeContext& ctx, const PictureSample& pict, int maxPlanes, bool retainCpuBuffer) {  // :359-381
+    if (pict.bufferType() != BufferType::cpu) return pict;
+    if (pict.imgBuffer.planes.empty()) throw ComputeError(ErrorCode::badInputData, "Missing image buffer");
+    if (!ctx.ctx) throw ComputeError(ErrorCode::badContextState, "No context");
+    auto textures = createTexture(ctx, pict.imgBuffer, maxPlanes);
+    for (size_t i = 0; i < textures.size(); ++i)
+    {
+        uploadComputeBuffer(ctx, pict.imgBuffer.buffers[i].ptr, std::min(pict.imgBuffer.buffers[i].size, textures[i]->size), textures[i]);
+        textures[i]->hostKeep = pict.imgBuffer.buffers[i].base;
+    }
+    PictureSample out = pict;
+    out.imgBuffer.computeTextures = textures;
+    if (!retainCpuBuffer) out.imgBuffer.buffers.clear();
+    out.imgBuffer.bufferType = BufferType::gpu;
+    return out;
+}
+
+void waitPicture(const PictureSample& pict) {
+    if (!pict.done) return;
+    CtxGuard g(pict.done->ctx);
+    check(drv().cuEventSynchronize(pict.done->e), "cuEventSynchronize");
+}
+
+PictureSample downloadComputePicture(const ComputeContext& ctx, const PictureSample& pict, bool retainGpuBuffer, bool wait) {  // :383-402
+    if (pict.bufferType() != BufferType::gpu) return pict;
+    if (pict.imgBuffer.planes.empty()) throw ComputeError(ErrorCode::badInputData, "Missing image buffer");
+    if (!ctx.ctx) throw ComputeError(ErrorCode::badContextState, "No context");
+    PictureSample out = pict;
+    const size_t n = pict.imgBuffer.computeTextures.size();
+    if (out.imgBuffer.buffers.size() < n) {  // upstream: `dst ?? Data(capacity:)` -- allocate what is missing
+        PictureSample host = createPictureSample(pict.size(), pict.pixelFormat(), pict.idAsset, pict.idWorkspace);
+        out.imgBuffer.buffers = host.imgBuffer.buffers;
+    }
+    CtxGuard g(ctx.ctx);
+    if (pict.done) check(drv().cuStreamWaitEvent(ctx.ctx->download, pict.done->e, 0), "cuStreamWaitEvent");
+    for (size_t i = 0; i < n; ++i) {
+        const auto& tex = pict.imgBuffer.computeTextures[i];
+        if (tex->ready) check(drv().cuStreamWaitEvent(ctx.ctx->download, tex->ready->e, 0), "cuStreamWaitEvent");
+        downloadComputeBuffer(ctx, *tex, out.imgBuffer.buffers[i].ptr, out.imgBuffer.buffers[i].size);
+    }
+    out.done = nullptr;
+    if (wait) {
+        check(drv().cuStreamSynchronize(ctx.ctx->download), "cuStreamSynchronize");  // endComputePass(ctx, true), :396
+    } else {
+        out.done = std::make_shared<Event>(ctx.ctx);
+        check(drv().cuEventRecord(out.done->e, ctx.ctx->download), "cuEventRecord");
+    }
+    if (!retainGpuBuffer) out.imgBuffer.computeTextures.clear();
+    out.imgBuffer.bufferType = BufferType::cpu;
+    return out;
+}
+
+// ---- kernels --------------------------------------------------------------------------------------------
+
+static unsigned gcdu(unsigned a, unsigned b) {  // clock.swift:197, used for block sizing at :290-291
+    while (b) {
+        unsigned t = a % b;
+        a = b;
+        b = t;
+    }
+    return a;
+}
+
+ComputeContext runComputeKernel(const ComputeContext& ctxIn, const std::vector<const PictureSample*>& images,
+                                const PictureSample& target, ComputeKernel kernel, const std::string& customName,
+                                int maxPlanes, const void* uniforms, size_t uniformsSize, bool /*blends*/) {  // :260-306
+    (void)maxPlanes;
+    for (const PictureSample* im : images)
+        if (im->bufferType() != BufferType::gpu) throw ComputeError(ErrorCode::badInputData, "Input images must be uploaded to GPU");
+    if (target.imgBuffer.planes.empty() || target.imgBuffer.computeTextures.empty()) throw ComputeError(ErrorCode::badTarget, "badTarget");
+    ComputeContext ctx = maybeBuildKernel(ctxIn, kernel, customName);
+    const std::string name = kernel == ComputeKernel::custom ? customName : computeKernelName(kernel);
+    auto it = ctx.library.find(name);
+    if (it == ctx.library.end()) throw ComputeError(ErrorCode::computeKernelNotFound, "computeKernelNotFound(" + name + ")");
+    const CUDAProgram& prog = *it->second;
+
+    CtxGuard g(ctx.ctx);
+    const CuDriver& d = drv();
+    std::vector<std::shared_ptr<ComputeBuffer>> keep;  // buffers in marshalling order (:294-297)
+    for (const auto& t : target.imgBuffer.computeTextures) keep.push_back(t);
+    std::vector<int32_t> inputStride;
+    for (const PictureSample* im : images) {
+        for (const auto& t : im->imgBuffer.computeTextures) {
+            if (t->ready) check(d.cuStreamWaitEvent(ctx.ctx->compute, t->ready->e, 0), "cuStreamWaitEvent");
+            keep.push_back(t);
+        }
+        for (const Plane& p : im->imgBuffer.planes) inputStride.push_back((int32_t)p.stride);
+    }
+    for (const auto& t : target.imgBuffer.computeTextures)
+        if (t->ready) check(d.cuStreamWaitEvent(ctx.ctx->compute, t->ready->e, 0), "cuStreamWaitEvent");
+    // uniforms and the stride array travel as two small device buffers, as upstream (:278-289); both copies are
+    // ordered on the compute stream ahead of the launch.
+    if (uniforms && uniformsSize) {
+        auto ub = createBuffer(ctx, uniformsSize);
+        check(d.cuMemcpyHtoDAsync(ub->mem, uniforms, uniformsSize, ctx.ctx->compute), "cuMemcpyHtoDAsync");
+        keep.push_back(ub);
+    }
+    if (!inputStride.empty()) {
+        auto sb = createBuffer(ctx, inputStride.size() * sizeof(int32_t));
+        check(d.cuMemcpyHtoDAsync(sb->mem, inputStride.data(), inputStride.size() * sizeof(int32_t), ctx.ctx->compute), "cuMemcpyHtoDAsync");
+        keep.push_back(sb);
+    }
+    // pageable sources: the async copies above have completed their host read on return (staged by the driver)
+    const unsigned W = (unsigned)target.size().x, H = (unsigned)target.size().y;
+    const unsigned bx = gcdu(W, 16), by = gcdu(H, 16);
+    std::vector<void*> args;
+    for (auto& b : keep) args.push_back(&b->mem);
+    check(d.cuLaunchKernel(prog.function, W / bx, H / by, 1, bx, by, 1, 0, ctx.ctx->compute, args.data(), nullptr), "cuLaunchKernel");
+    noteKernelLaunch();
+    // `keep` may drop its temporaries now: release() orders every stream behind the launch before reuse.
+    return ctx;
+}
+
+ImageUniforms makeImageUniforms(const PictureSample& image, const PictureSample& target) {  // compute.swift:149-161
+    ImageUniforms u;
+    std::memcpy(u.transform, image.matrix().inverse().transpose().data(), 64);
+    std::memcpy(u.textureTransform, image.textureMatrix().inverse().transpose().data(), 64);
+    std::memcpy(u.borderMatrix, image.borderMatrix().inverse().transpose().data(), 64);
+    const Vector4 f = image.fillColor();
+    u.fillColor[0] = f.x, u.fillColor[1] = f.y, u.fillColor[2] = f.z, u.fillColor[3] = f.w;
+    u.inputSize[0] = image.size().x, u.inputSize[1] = image.size().y;
+    u.outputSize[0] = target.size().x, u.outputSize[1] = target.size().y;
+    u.opacity = image.opacity();
+    u.imageTime = image.timescale ? (float)((double)image.timeValue / (double)image.timescale) : 0.f;
+    u.targetTime = target.timescale ? (float)((double)target.timeValue / (double)target.timescale) : 0.f;
+    return u;
+}
+
+ComputeContext applyComputeImage(const ComputeContext& ctx, const PictureSample& image, const PictureSample& target,
+                                 ComputeKernel kernel) {  // compute.swift:145-170
+    const ImageUniforms u = makeImageUniforms(image, target);
+    return runComputeKernel(ctx, {&image}, target, kernel, "", 3, &u, sizeof(u), true);
+}
+
+}  // namespace svb

@@ -1,0 +1,258 @@
+// compute.h -- host side of the compute path, mirroring the reference's operator surface name for name:
+//   compute.swift            ComputeError, ComputeKernel, ImageUniforms, defaultComputeKernelFromString,
+//                            makeComputeContext, usingContext, applyComputeImage                (:22-170)
+//   compute.cuda.swift       ComputeDevice, ComputeContext, ComputeBuffer, availableComputeDevices,
+//                            createComputeContext, buildComputeKernel, runComputeKernel,
+//                            begin/endComputePass, upload/downloadComputeBuffer/Picture         (:23-440)
+//   sample.pict*.swift       PixelFormat, Component, Plane, BufferType, ImageBuffer, PictureSample,
+//                            createPictureSample                                                (sample.pict.swift:20-101,
+//                                                                                                sample.pict.linux.swift:23-311)
+// The reference is Swift; no Swift toolchain exists in this image, so the host side is C++ above the same
+// driver API and below the C ABI in include/svb200.h.
+#pragma once
+#include <cuda.h>
+#include <stdint.h>
+
+#include <map>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "vector_math.h"
+
+namespace svb {
+
+// ---- ComputeError (compute.swift:22-39) ---------------------------------------------------------------
+enum class ErrorCode : int {
+    ok = 0,
+    invalidPlatform = 1,
+    invalidDevice = 2,
+    invalidOperation = 3,
+    invalidValue = 4,
+    invalidProgram = 5,
+    invalidContext = 6,
+    deviceNotAvailable = 7,
+    outOfMemory = 8,
+    compilerNotAvailable = 9,
+    computeKernelNotFound = 10,
+    badTarget = 11,
+    badInputData = 12,
+    badContextState = 13,
+    compilerError = 14,
+    unknownError = 15,
+    notImplemented = 16,
+};
+struct ComputeError : std::runtime_error {
+    ErrorCode code;
+    ComputeError(ErrorCode c, const std::string& what) : std::runtime_error(what), code(c) {}
+};
+void check(CUresult r, const char* where);  // CUresult -> ComputeError, compute.cuda.swift:102-112
+
+// ---- ComputeKernel (compute.swift:49-74) ---------------------------------------------------------------
+enum class ComputeKernel : int {
+    img_nv12_nv12 = 0,
+    img_bgra_nv12,
+    img_rgba_nv12,
+    img_bgra_bgra,
+    img_y420p_y420p,
+    img_y420p_nv12,
+    img_clear_nv12,
+    img_clear_yuvs,
+    img_clear_bgra,
+    img_clear_y420p,
+    img_clear_rgba,
+    img_rgba_y420p,
+    img_bgra_y420p,
+    snd_s16i_s16i,
+    me_fullsearch,
+    custom,
+    count_
+};
+const char* computeKernelName(ComputeKernel k);                          // String(describing:)
+ComputeKernel defaultComputeKernelFromString(const std::string& name);  // compute.swift:90-110 (throws invalidValue)
+
+// ---- picture data model --------------------------------------------------------------------------------
+enum class PixelFormat : int { nv12 = 0, nv21, yuvs, zvuy, y420p, y422p, y444p, RGBA, BGRA, shape, text, invalid };
+enum class BufferType : int { shared = 0, cpu, gpu, invalid };
+enum class Component : int { r, g, b, a, y, cr, cb };
+const char* pixelFormatName(PixelFormat f);  // lower-cased case name, as VideoMixer.findKernel builds it
+
+struct Plane {  // sample.pict.swift:46-56
+    Vector2 size;
+    int stride = 0;
+    int bitDepth = 8;
+    std::vector<Component> components;
+};
+
+struct InternalContext;  // owns the CUcontext + streams + pools
+struct Event {           // a CUevent that dies with its last holder
+    CUevent e = nullptr;
+    std::shared_ptr<InternalContext> ctx;
+    explicit Event(std::shared_ptr<InternalContext> c);
+    ~Event();
+    Event(const Event&) = delete;
+};
+class ComputeBuffer {    // compute.cuda.swift:75-92: owns device memory, released in the destructor
+  public:
+    ComputeBuffer(CUdeviceptr p, size_t size, std::shared_ptr<InternalContext> ctx) : mem(p), size(size), ctx(std::move(ctx)) {}
+    ~ComputeBuffer();
+    ComputeBuffer(const ComputeBuffer&) = delete;
+    CUdeviceptr mem;  // non-const: its address is what cuLaunchKernel's param array points at (:297)
+    const size_t size;
+    std::shared_ptr<Event> ready;  // recorded after the last async write (upload); consumers wait on it
+    std::shared_ptr<uint8_t> hostKeep;  // source of an in-flight async upload stays alive with the texture
+    std::shared_ptr<InternalContext> ctx;
+};
+
+// Host bytes of one plane: a slice of a shared allocation (buffersForPlanes slices one ByteBuffer, :296-311)
+struct HostData {
+    std::shared_ptr<uint8_t> base;  // keeps the allocation alive
+    uint8_t* ptr = nullptr;
+    size_t size = 0;
+};
+
+struct ImageBuffer {  // sample.pict.linux.swift:23-72
+    PixelFormat pixelFormat = PixelFormat::invalid;
+    BufferType bufferType = BufferType::invalid;
+    Vector2 size;
+    std::vector<std::shared_ptr<ComputeBuffer>> computeTextures;
+    std::vector<HostData> buffers;
+    std::vector<Plane> planes;
+};
+
+class PictureSample {  // sample.pict.linux.swift:105-249 (immutable upstream; copied-with-changes here too)
+  public:
+    ImageBuffer imgBuffer;
+    Matrix4 transform, texTransform, borderTransform;
+    Vector4 bgColor{0, 0, 0, 1};  // default fillColor, :158
+    float alpha = 1.0f;
+    std::string idAsset, idWorkspace, idRevision;
+    int64_t ptsValue = 0, timeValue = 0;
+    int64_t timescale = 1;
+    std::shared_ptr<Event> done;  // set on samples produced asynchronously (mix / download): wait before reading
+
+    Matrix4 matrix() const { return transform; }
+    Matrix4 textureMatrix() const { return texTransform; }
+    Matrix4 borderMatrix() const { return borderTransform; }
+    Vector4 fillColor() const { return bgColor; }
+    float opacity() const { return alpha; }
+    Vector2 size() const { return imgBuffer.size; }
+    PixelFormat pixelFormat() const { return imgBuffer.pixelFormat; }
+    BufferType bufferType() const { return imgBuffer.bufferType; }
+    const std::string& revision() const { return idRevision; }
+    const std::string& assetId() const { return idAsset; }
+    int zIndex() const { return (int)std::round((Vector3{0, 0, 0} * transform).z); }  // :116
+};
+
+std::vector<Plane> planesForFormat(PixelFormat f, Vector2 size);  // :275-294
+// createPictureSample (:254-273): one contiguous CPU allocation sliced into planes. `pinned` (ours) asks
+// for page-locked memory from `ctx` so uploads/downloads run at PCIe rate; the layout is unchanged.
+PictureSample createPictureSample(Vector2 size, PixelFormat format, const std::string& assetId,
+                                  const std::string& workspaceId, struct ComputeContext* pinnedFrom = nullptr);
+
+// ---- devices / context ---------------------------------------------------------------------------------
+enum class ComputeDeviceType : int { GPU, CPU, Accelerator, Default };
+struct ComputeDevice {  // compute.cuda.swift:23-30
+    CUdevice device = 0;
+    int index = 0;
+    bool available = false;
+    ComputeDeviceType deviceType = ComputeDeviceType::GPU;
+    bool supportsImages = true;
+};
+
+struct CUDAProgram {  // compute.cuda.swift:43-58 -- a loaded module + one entry point
+    CUmodule module = nullptr;
+    CUfunction function = nullptr;
+    bool ownsModule = false;
+    std::shared_ptr<InternalContext> ctx;
+    ~CUDAProgram();
+};
+
+struct ComputeContext {  // compute.cuda.swift:60-73: shared InternalContext + this holder's kernel library
+    std::shared_ptr<InternalContext> ctx;
+    std::map<std::string, std::shared_ptr<CUDAProgram>> library;
+};
+
+std::vector<ComputeDevice> availableComputeDevices();  // :132-153
+// makeComputeContext(forType:) (compute.swift:121-129) picks devices.first; `deviceIndex` is the minimal
+// extension SURVEY.md section 8e asks for so that streams can be placed one-per-GPU (default 0 = upstream behaviour).
+ComputeContext makeComputeContext(ComputeDeviceType type, int deviceIndex = 0);
+ComputeContext createComputeContext(const ComputeDevice& device);  // :159-165
+ComputeContext createComputeContext(const ComputeContext& sharing);  // :155-157 (empty kernel library)
+void destroyComputeContext(ComputeContext& ctx);                     // :167-169 (no-op upstream too)
+
+// The sm_100a module holding every kernel (what buildComputeKernel's NVRTC step produced upstream).
+void kernelModuleImage(const void** image, size_t* size);
+// buildComputeKernel (:171-201).  Upstream compiles `source` with NVRTC then cuModuleLoadData +
+// cuModuleGetFunction(name); here `image` is a ready cubin/PTX (NULL = our built-in module).
+ComputeContext buildComputeKernel(const ComputeContext& ctx, const std::string& name, const void* image);
+
+ComputeContext beginComputePass(const ComputeContext& ctx);                        // :308-311
+ComputeContext endComputePass(const ComputeContext& ctx, bool waitForCompletion);  // :313-319
+template <class F>
+ComputeContext usingContext(const ComputeContext& ctx, F&& fn) {  // compute.swift:131-134
+    return endComputePass(fn(beginComputePass(ctx)), true);
+}
+
+std::shared_ptr<ComputeBuffer> uploadComputeBuffer(const ComputeContext& ctx, const void* src, size_t size,
+                                                   std::shared_ptr<ComputeBuffer> dst);  // :330-342
+void downloadComputeBuffer(const ComputeContext& ctx, const ComputeBuffer& src, void* dst, size_t dstSize);  // :344-357
+PictureSample uploadComputePicture(const ComputeContext& ctx, const PictureSample& pict, int maxPlanes = 3,
+                                   bool retainCpuBuffer = true);                          // :359-381
+// `wait` = upstream's endComputePass(ctx, true) at :396; wait=false (ours) returns at once with `done` set.
+PictureSample downloadComputePicture(const ComputeContext& ctx, const PictureSample& pict,
+                                     bool retainGpuBuffer = false, bool wait = true);     // :383-402
+void waitPicture(const PictureSample& pict);  // block until `done` (if any) has fired
+
+// runComputeKernel<T> (:260-306): params [outputs..., inputs..., uniforms, inStride[]], block (gcd(W,16),
+// gcd(H,16)), grid (W/bx, H/by), 0 B smem.  `blends` is accepted and ignored exactly as upstream (:267).
+ComputeContext runComputeKernel(const ComputeContext& ctx, const std::vector<const PictureSample*>& images,
+                                const PictureSample& target, ComputeKernel kernel, const std::string& customName,
+                                int maxPlanes, const void* uniforms, size_t uniformsSize, bool blends);
+
+// ImageUniforms (compute.swift:76-86), 236 bytes, and applyComputeImage (:145-170)
+struct ImageUniforms {
+    float transform[16], textureTransform[16], borderMatrix[16];
+    float fillColor[4];
+    float inputSize[2], outputSize[2];
+    float opacity, imageTime, targetTime;
+};
+static_assert(sizeof(ImageUniforms) == 236, "ImageUniforms must be 236 bytes");
+ImageUniforms makeImageUniforms(const PictureSample& image, const PictureSample& target);
+ComputeContext applyComputeImage(const ComputeContext& ctx, const PictureSample& image, const PictureSample& target,
+                                 ComputeKernel kernel);
+
+unsigned long long kernelLaunchCount();  // launches of our kernels issued by this process
+void noteKernelLaunch();
+
+// ---- plumbing shared with mix_video.cpp ----------------------------------------------------------------
+struct InternalContext {
+    CUcontext ctx = nullptr;
+    CUdevice device = 0;
+    int deviceIndex = 0;
+    int smCount = 0;
+    CUstream compute = nullptr, upload = nullptr, download = nullptr;
+    CUmodule module = nullptr;  // built-in kernel module, loaded once per context
+    std::mutex mu;
+    struct Block {
+        CUdeviceptr p = 0;
+        CUevent after[3] = {nullptr, nullptr, nullptr};  // tails of compute/upload/download at release time
+    };
+    std::multimap<size_t, Block> pool;  // freed device blocks by size (upstream cuMemAllocs per upload)
+    std::vector<CUevent> spareEvents;
+    // state shared by every VideoMixer of this context (descriptor ring, tensor-map cache); owned by mix_video.cpp
+    void* mixerShared = nullptr;
+    void (*mixerSharedFree)(InternalContext*) = nullptr;
+    ~InternalContext();
+    CUdeviceptr alloc(size_t size);
+    void release(CUdeviceptr p, size_t size);
+    CUfunction builtin(const char* name);
+};
+struct CtxGuard {  // cuCtxPushCurrent / cuCtxPopCurrent pair
+    explicit CtxGuard(const std::shared_ptr<InternalContext>& c);
+    ~CtxGuard();
+};
+
+}  // namespace svb

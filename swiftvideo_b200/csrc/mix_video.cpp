@@ -1,0 +1,531 @@
+// mix_video.cpp -- VideoMixer and the fused-frame planner (see mix_video.h for the reference map).
+#include "mix_video.h"
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstring>
+
+#include "cu_driver.h"
+
+namespace svb {
+
+static const CuDriver& drv() {
+    const CuDriver& d = cu();
+    if (!d.ok) throw ComputeError(ErrorCode::deviceNotAvailable, std::string("CUDA driver unavailable: ") + d.why);
+    return d;
+}
+
+// ---- per-context state: descriptor ring + tensor-map cache ----------------------------------------------
+
+namespace {
+
+constexpr int kSegments = 8;     // batches in flight before the host has to wait for the oldest
+constexpr int kSegFrames = 64;   // frame descriptors per batch
+
+struct MixerShared {
+    uint8_t* host = nullptr;  // pinned staging, kSegments * kSegFrames descriptors
+    CUdeviceptr dev = 0;
+    CUevent ev[kSegments] = {};
+    bool used[kSegments] = {};
+    int next = 0;
+    std::map<std::array<uint64_t, 4>, std::array<uint8_t, 128>> tmaps;
+    CUfunction fTiled = nullptr, fGeneric = nullptr;
+    std::mutex mu;
+    // optional per-launch device timing of the fused kernels (bench.py's roofline leg)
+    bool timing = false;
+    std::vector<std::pair<CUevent, CUevent>> timed, spare;
+    double timedMs = 0.0;
+    unsigned long long timedLaunches = 0;
+};
+
+void harvest(MixerShared& s) {  // caller holds a CtxGuard
+    for (auto& pr : s.timed) {
+        float ms = 0.f;
+        if (cu().cuEventSynchronize(pr.second) == CUDA_SUCCESS && cu().cuEventElapsedTime(&ms, pr.first, pr.second) == CUDA_SUCCESS) {
+            s.timedMs += ms;
+            ++s.timedLaunches;
+        }
+        s.spare.push_back(pr);
+    }
+    s.timed.clear();
+}
+
+void freeShared(InternalContext* ic) {
+    auto* s = (MixerShared*)ic->mixerShared;
+    if (!s) return;
+    if (s->host) cu().cuMemFreeHost(s->host);
+    if (s->dev) cu().cuMemFree(s->dev);
+    for (CUevent e : s->ev)
+        if (e) cu().cuEventDestroy(e);
+    for (auto* v : {&s->timed, &s->spare})
+        for (auto& pr : *v) {
+            cu().cuEventDestroy(pr.first);
+            cu().cuEventDestroy(pr.second);
+        }
+    delete s;
+    ic->mixerShared = nullptr;
+}
+
+MixerShared& shared(const std::shared_ptr<InternalContext>& ic) {  // caller holds a CtxGuard
+    std::lock_guard<std::mutex> g(ic->mu);
+    if (!ic->mixerShared) {
+        auto* s = new MixerShared();
+        ic->mixerShared = s;
+        ic->mixerSharedFree = freeShared;
+        const size_t bytes = (size_t)kSegments * kSegFrames * sizeof(SvbFrameDesc);
+        check(drv().cuMemHostAlloc((void**)&s->host, bytes, 0), "cuMemHostAlloc");
+        check(drv().cuMemAlloc(&s->dev, bytes), "cuMemAlloc");
+        for (CUevent& e : s->ev) check(drv().cuEventCreate(&e, CU_EVENT_DISABLE_TIMING), "cuEventCreate");
+        s->fTiled = ic->builtin("svb_mix_tiled");
+        s->fGeneric = ic->builtin("svb_mix_generic");
+    }
+    return *(MixerShared*)ic->mixerShared;
+}
+
+int svbFormat(PixelFormat f) {
+    switch (f) {
+    case PixelFormat::nv12: return SVB_NV12;
+    case PixelFormat::y420p: return SVB_Y420P;
+    case PixelFormat::BGRA: return SVB_BGRA;
+    case PixelFormat::RGBA: return SVB_RGBA;
+    default: return -1;
+    }
+}
+
+bool finite16(const float* m) {
+    for (int i = 0; i < 16; ++i)
+        if (!std::isfinite(m[i])) return false;
+    return true;
+}
+
+int roundUp(int v, int m) { return (v + m - 1) / m * m; }
+
+// 2-D tensor map over one plane; cached, the encode costs ~1 us and layers rarely change geometry.
+bool tensorMap(MixerShared& sh, unsigned char out[128], CUdeviceptr ptr, int elemBytes, int w, int h, int strideBytes, int boxW, int boxH) {
+    if ((ptr & 15) || (strideBytes & 15) || w <= 0 || h <= 0 || boxW > 256 || boxH > 256 || (boxW * elemBytes) % 16) return false;
+    const std::array<uint64_t, 4> key = {(uint64_t)ptr, ((uint64_t)(uint32_t)w << 32) | (uint32_t)h,
+                                         ((uint64_t)(uint32_t)strideBytes << 32) | (uint32_t)elemBytes,
+                                         ((uint64_t)(uint32_t)boxW << 32) | (uint32_t)boxH};
+    auto it = sh.tmaps.find(key);
+    if (it == sh.tmaps.end()) {
+        alignas(64) CUtensorMap tm;
+        const cuuint64_t gdim[2] = {(cuuint64_t)w, (cuuint64_t)h};
+        const cuuint64_t gstride[1] = {(cuuint64_t)strideBytes};
+        const cuuint32_t box[2] = {(cuuint32_t)boxW, (cuuint32_t)boxH};
+        const cuuint32_t estride[2] = {1, 1};
+        CUresult r = drv().cuTensorMapEncodeTiled(&tm, elemBytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
+                                                  (void*)ptr, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return false;
+        if (sh.tmaps.size() > 8192) sh.tmaps.clear();
+        std::array<uint8_t, 128> bytes;
+        static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+        std::memcpy(bytes.data(), &tm, 128);
+        it = sh.tmaps.emplace(key, bytes).first;
+    }
+    std::memcpy(out, it->second.data(), 128);
+    return true;
+}
+
+// Canvas rectangle outside which `border` cannot land in [0,1]^2: the unit square pushed through the forward
+// border map, grown by 2 px (fp32 rounding of the kernel's chain moves an edge by far less than a pixel).
+void layerRect(const SvbUniforms& u, int W, int H, int32_t rect[4]) {
+    rect[0] = 0, rect[1] = 0, rect[2] = W, rect[3] = H;
+    const double a = u.borderMatrix[0], b = u.borderMatrix[1], c = u.borderMatrix[4], d = u.borderMatrix[5];
+    const double e = u.borderMatrix[3], f = u.borderMatrix[7];
+    const double det = a * d - b * c;
+    if (!finite16(u.borderMatrix) || !(std::fabs(det) > 1e-30)) return;
+    double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+    for (int k = 0; k < 4; ++k) {
+        const double bx = (k & 1) - e, by = (k >> 1) - f;  // border = (k&1, k>>1)
+        const double nx = (d * bx - b * by) / det, ny = (-c * bx + a * by) / det;
+        const double px = (nx + 1.0) * 0.5 * W, py = (ny + 1.0) * 0.5 * H;
+        xmin = std::min(xmin, px), xmax = std::max(xmax, px), ymin = std::min(ymin, py), ymax = std::max(ymax, py);
+    }
+    if (!(std::isfinite(xmin) && std::isfinite(xmax) && std::isfinite(ymin) && std::isfinite(ymax))) return;
+    auto clampi = [](double v, int lo, int hi) { return (int)std::min<double>(std::max<double>(v, lo), hi); };
+    rect[0] = clampi(std::floor(xmin) - 2, 0, W);
+    rect[1] = clampi(std::floor(ymin) - 2, 0, H);
+    rect[2] = clampi(std::ceil(xmax) + 3, 0, W);
+    rect[3] = clampi(std::ceil(ymax) + 3, 0, H);
+}
+
+}  // namespace
+
+// ---- planner --------------------------------------------------------------------------------------------
+
+FramePlan planFrame(const ComputeContext& ctx, const PictureSample& target, const std::vector<const PictureSample*>& layers,
+                    const ImageUniforms* uniforms) {
+    FramePlan plan;
+    const int tf = svbFormat(target.pixelFormat());
+    if (tf != SVB_NV12 && tf != SVB_Y420P) throw ComputeError(ErrorCode::badTarget, "fused compose needs an nv12 or y420p target");
+    const int W = (int)target.size().x, H = (int)target.size().y;
+    if (W <= 0 || H <= 0 || (W & 1) || (H & 1)) throw ComputeError(ErrorCode::badTarget, "target size must be even");
+    const auto& tex = target.imgBuffer.computeTextures;
+    const auto& planes = target.imgBuffer.planes;
+    const size_t np = tf == SVB_NV12 ? 2 : 3;
+    if (tex.size() < np || planes.size() < np) throw ComputeError(ErrorCode::badTarget, "badTarget");
+
+    SvbFrameDesc base;
+    std::memset(&base, 0, sizeof(base));
+    for (size_t i = 0; i < np; ++i) {
+        base.out_plane[i] = tex[i]->mem;
+        base.out_stride[i] = planes[i].stride;
+    }
+    base.width = W, base.height = H, base.format = tf;
+    base.tiles_x = (W + SVB_TILE_W - 1) / SVB_TILE_W;
+    base.tiles_y = (H + SVB_TILE_H - 1) / SVB_TILE_H;
+    for (size_t i = 0; i < np; ++i)
+        if (planes[i].stride & 1) throw ComputeError(ErrorCode::badTarget, "target strides must be even");
+    plan.tiledOk = (W % 4 == 0) && (base.out_stride[0] % 4 == 0) && (base.out_plane[0] % 4 == 0) &&
+                   (tf == SVB_NV12 ? (base.out_stride[1] % 4 == 0 && base.out_plane[1] % 4 == 0)
+                                   : (base.out_plane[1] % 2 == 0 && base.out_plane[2] % 2 == 0));
+
+    MixerShared& sh = shared(ctx.ctx);
+    const size_t n = layers.size();
+    const size_t npass = std::max<size_t>(1, (n + SVB_MAX_LAYERS - 1) / SVB_MAX_LAYERS);
+    plan.passes.assign(npass, base);
+    for (size_t p = 0; p < npass; ++p)
+        if (p) plan.passes[p].flags |= SVB_FRAME_LOAD_CUR;
+    for (size_t k = 0; k < n; ++k) {
+        SvbFrameDesc& F = plan.passes[k / SVB_MAX_LAYERS];
+        SvbLayerDesc& L = F.layers[F.nlayers++];
+        const PictureSample& img = *layers[k];
+        const int sf = svbFormat(img.pixelFormat());
+        if (sf < 0) throw ComputeError(ErrorCode::computeKernelNotFound, std::string("computeKernelNotFound(img_") + pixelFormatName(img.pixelFormat()) + "_" + pixelFormatName(target.pixelFormat()) + ")");
+        if (img.bufferType() != BufferType::gpu) throw ComputeError(ErrorCode::badInputData, "Input images must be uploaded to GPU");
+        const size_t snp = sf == SVB_NV12 ? 2 : (sf == SVB_Y420P ? 3 : 1);
+        if (img.imgBuffer.computeTextures.size() < snp || img.imgBuffer.planes.size() < snp) throw ComputeError(ErrorCode::badInputData, "Bad input image");
+        std::memcpy(&L.u, &uniforms[k], sizeof(ImageUniforms));
+        L.u.pad_ = 0.f;
+        for (size_t i = 0; i < snp; ++i) {
+            L.plane[i] = img.imgBuffer.computeTextures[i]->mem;
+            L.stride[i] = img.imgBuffer.planes[i].stride;
+        }
+        L.width = (int)img.imgBuffer.planes[0].size.x;
+        L.height = (int)img.imgBuffer.planes[0].size.y;
+        L.format = sf;
+        const SvbUniforms& u = L.u;
+        const float *T = u.transform, *X = u.textureTx, *B = u.borderMatrix;
+        const bool finite = finite16(T) && finite16(X) && finite16(B) && std::isfinite(u.opacity);
+        int flags = 0;
+        if (finite && T[1] == 0.f && T[4] == 0.f && T[8] == 0.f && T[9] == 0.f && T[12] == 0.f && T[13] == 0.f && B[1] == 0.f &&
+            B[4] == 0.f && X[1] == 0.f && X[4] == 0.f && (sf != SVB_Y420P || L.stride[1] == L.stride[2]))
+            flags |= SVB_LAYER_SEPARABLE;
+        if (u.opacity == 1.0f) flags |= SVB_LAYER_UNIT_OPACITY;
+        if (u.opacity >= 0.f && u.opacity <= 1.f) flags |= SVB_LAYER_OPACITY_01;
+        layerRect(u, W, H, L.rect);
+        if ((flags & SVB_LAYER_SEPARABLE) && (sf == SVB_NV12 || sf == SVB_Y420P) && L.width >= 2 && L.height >= 2) {
+            // source texels per output pixel along each axis (double is plenty: the device re-checks the fit per tile)
+            const double sx = std::fabs((double)L.width * X[0] * T[0] * 2.0 / W), sy = std::fabs((double)L.height * X[5] * T[5] * 2.0 / H);
+            const int cw = L.width / 2, ch = L.height / 2;
+            int bw = roundUp((int)std::ceil(sx * (SVB_TILE_W - 1)) + 3, 16), bh = (int)std::ceil(sy * (SVB_TILE_H - 1)) + 3;
+            int bcw = roundUp((int)std::ceil(sx * 0.5 * (SVB_TILE_W - 2)) + 3, sf == SVB_NV12 ? 8 : 16);
+            int bch = (int)std::ceil(sy * 0.5 * (SVB_TILE_H - 2)) + 3;
+            const int cbytes = bcw * bch * (sf == SVB_NV12 ? 2 : 1);
+            const bool fits = std::isfinite(sx) && std::isfinite(sy) && bw <= 256 && bh <= 256 && bw * bh <= SVB_BOX_Y_BYTES &&
+                              bcw <= 256 && bch <= 256 && cbytes <= (sf == SVB_NV12 ? SVB_BOX_C_BYTES : SVB_BOX_C_BYTES / 2);
+            if (fits && tensorMap(sh, L.tmap[0], L.plane[0], 1, L.width, L.height, L.stride[0], bw, bh) &&
+                (sf == SVB_NV12 ? tensorMap(sh, L.tmap[1], L.plane[1], 2, cw, ch, L.stride[1], bcw, bch)
+                                : (tensorMap(sh, L.tmap[1], L.plane[1], 1, cw, ch, L.stride[1], bcw, bch) &&
+                                   tensorMap(sh, L.tmap[2], L.plane[2], 1, cw, ch, L.stride[2], bcw, bch)))) {
+                flags |= SVB_LAYER_STAGED;
+                L.box_w = bw, L.box_h = bh, L.box_cw = bcw, L.box_ch = bch;
+            }
+        }
+        L.flags = flags;
+    }
+    return plan;
+}
+
+// ---- launch ---------------------------------------------------------------------------------------------
+
+namespace {
+
+// One launch over `frames` (all tiled-capable, or all generic).  Caller holds a CtxGuard.
+void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, bool tiled) {
+    const CuDriver& d = drv();
+    MixerShared& sh = shared(ctx.ctx);
+    InternalContext& ic = *ctx.ctx;
+    for (size_t start = 0; start < frames.size(); start += kSegFrames) {
+        const int n = (int)std::min<size_t>(kSegFrames, frames.size() - start);
+        int seg;
+        {
+            std::lock_guard<std::mutex> g(sh.mu);
+            seg = sh.next;
+            sh.next = (sh.next + 1) % kSegments;
+        }
+        if (sh.used[seg]) check(d.cuEventSynchronize(sh.ev[seg]), "cuEventSynchronize");
+        SvbFrameDesc* host = (SvbFrameDesc*)(sh.host + (size_t)seg * kSegFrames * sizeof(SvbFrameDesc));
+        int total = 0, maxW = 0, maxH = 0;
+        for (int i = 0; i < n; ++i) {
+            frames[start + i].first_tile = total;
+            total += frames[start + i].tiles_x * frames[start + i].tiles_y;
+            maxW = std::max(maxW, frames[start + i].width), maxH = std::max(maxH, frames[start + i].height);
+            // copy only the header and the layers in use
+            const size_t used = offsetof(SvbFrameDesc, layers) + sizeof(SvbLayerDesc) * (size_t)frames[start + i].nlayers;
+            std::memcpy(&host[i], &frames[start + i], used);
+        }
+        CUdeviceptr dev = sh.dev + (size_t)seg * kSegFrames * sizeof(SvbFrameDesc);
+        check(d.cuMemcpyHtoDAsync(dev, host, (size_t)n * sizeof(SvbFrameDesc), ic.compute), "cuMemcpyHtoDAsync");
+        std::pair<CUevent, CUevent> tev{nullptr, nullptr};
+        if (sh.timing) {
+            if (sh.timed.size() >= 256) harvest(sh);
+            if (!sh.spare.empty()) {
+                tev = sh.spare.back();
+                sh.spare.pop_back();
+            } else {
+                check(d.cuEventCreate(&tev.first, CU_EVENT_DEFAULT), "cuEventCreate");
+                check(d.cuEventCreate(&tev.second, CU_EVENT_DEFAULT), "cuEventCreate");
+            }
+            check(d.cuEventRecord(tev.first, ic.compute), "cuEventRecord");
+        }
+        if (tiled) {
+            int nframes = n;
+            void* args[] = {&dev, &nframes, &total};
+            const unsigned grid = (unsigned)std::min(total, ic.smCount * 2);
+            check(d.cuLaunchKernel(sh.fTiled, grid, 1, 1, 256, 1, 1, 0, ic.compute, args, nullptr), "cuLaunchKernel(svb_mix_tiled)");
+            noteKernelLaunch();
+        } else {
+            void* args[] = {&dev};
+            check(d.cuLaunchKernel(sh.fGeneric, (unsigned)((maxW / 2 + 31) / 32), (unsigned)((maxH / 2 + 7) / 8), (unsigned)n, 32, 8, 1, 0,
+                                   ic.compute, args, nullptr),
+                  "cuLaunchKernel(svb_mix_generic)");
+            noteKernelLaunch();
+        }
+        if (tev.first) {
+            check(d.cuEventRecord(tev.second, ic.compute), "cuEventRecord");
+            sh.timed.push_back(tev);
+        }
+        check(d.cuEventRecord(sh.ev[seg], ic.compute), "cuEventRecord");
+        sh.used[seg] = true;
+    }
+}
+
+void waitInputs(const ComputeContext& ctx, const PictureSample& p) {
+    for (const auto& t : p.imgBuffer.computeTextures)
+        if (t->ready) check(drv().cuStreamWaitEvent(ctx.ctx->compute, t->ready->e, 0), "cuStreamWaitEvent");
+}
+
+struct Job {
+    const PictureSample* target;
+    std::vector<const PictureSample*> layers;
+    std::vector<ImageUniforms> uniforms;
+};
+
+// Fused compose of several independent targets on one context.
+void composeFused(const ComputeContext& ctx, std::vector<Job>& jobs, bool forceGeneric) {
+    CtxGuard g(ctx.ctx);
+    std::vector<FramePlan> plans;
+    bool allTiled = !forceGeneric;
+    size_t maxPass = 0;
+    for (Job& j : jobs) {
+        plans.push_back(planFrame(ctx, *j.target, j.layers, j.uniforms.data()));
+        allTiled = allTiled && plans.back().tiledOk;
+        maxPass = std::max(maxPass, plans.back().passes.size());
+        waitInputs(ctx, *j.target);
+        for (const PictureSample* l : j.layers) waitInputs(ctx, *l);
+    }
+    for (size_t p = 0; p < maxPass; ++p) {  // a later pass of a frame reads what its earlier pass wrote: separate launches
+        std::vector<SvbFrameDesc> frames;
+        for (FramePlan& pl : plans)
+            if (p < pl.passes.size()) frames.push_back(pl.passes[p]);
+        launchFrames(ctx, frames, allTiled);
+    }
+}
+
+}  // namespace
+
+void setLaunchTiming(const ComputeContext& ctx, bool on) {
+    CtxGuard g(ctx.ctx);
+    MixerShared& sh = shared(ctx.ctx);
+    harvest(sh);
+    sh.timing = on;
+    sh.timedMs = 0.0;
+    sh.timedLaunches = 0;
+}
+void readLaunchTiming(const ComputeContext& ctx, double* totalMs, unsigned long long* launches) {
+    CtxGuard g(ctx.ctx);
+    MixerShared& sh = shared(ctx.ctx);
+    harvest(sh);
+    *totalMs = sh.timedMs;
+    *launches = sh.timedLaunches;
+}
+
+// ---- VideoMixer -----------------------------------------------------------------------------------------
+
+VideoMixer::VideoMixer(const ComputeContext* computeContext, Vector2 outputSize, PixelFormat outputFormat, const std::string& assetId,
+                       const std::string& workspaceId, int64_t frameDuration, int64_t timescale, int64_t epoch)
+    : frameDuration(frameDuration), timescale(timescale), epoch(epoch), backingFormat(outputFormat), backingSize(outputSize),
+      idWorkspace(workspaceId) {
+    if (computeContext) {  // mix.video.swift:32-40
+        clContext = createComputeContext(*computeContext);
+        hasContext = (bool)clContext.ctx;
+    } else {
+        try {
+            clContext = makeComputeContext(ComputeDeviceType::GPU);
+            hasContext = true;
+        } catch (const ComputeError&) {
+            hasContext = false;  // upstream prints "Error making compute context!" and carries on without one
+        }
+    }
+    static int counter = 0;
+    idAsset = assetId.empty() ? "mixer-" + std::to_string(++counter) : assetId;  // upstream: UUID().uuidString
+}
+
+bool VideoMixer::push(const PictureSample& pic) { return push(std::make_shared<const PictureSample>(pic)); }
+bool VideoMixer::push(std::shared_ptr<const PictureSample> pic) {  // :57-75
+    if (!hasContext) throw ComputeError(ErrorCode::badContextState, "No Compute Context");
+    if (pic->assetId() != idAsset) {
+        samples[0][pic->revision()] = std::move(pic);
+        return true;
+    }
+    return false;
+}
+
+ComputeKernel VideoMixer::findKernel(const PictureSample* image, const PictureSample& target) const {  // :142-146
+    const std::string inp = image ? pixelFormatName(image->pixelFormat()) : "clear";
+    return defaultComputeKernelFromString("img_" + inp + "_" + pixelFormatName(target.pixelFormat()));
+}
+
+PictureSample VideoMixer::getBacking() {  // :148-165
+    if (!hasContext) throw ComputeError(ErrorCode::badContextState, "No context");
+    if ((int)backing.size() < numberBackingImages) {
+        // page-locked CPU side (ours): downloads of emitted frames then run at PCIe rate
+        PictureSample image = createPictureSample(backingSize, backingFormat, idAsset, idWorkspace, &clContext);
+        // upstream uploads the (uninitialised) CPU image to obtain the GPU planes; the bytes are never read
+        // because every compose starts with the clear kernel, so only the allocation is kept here.
+        PictureSample gpu = image;
+        gpu.imgBuffer.computeTextures.clear();
+        CtxGuard g(clContext.ctx);
+        for (const Plane& p : image.imgBuffer.planes) {
+            const size_t sz = (size_t)p.stride * (size_t)(int)p.size.y;
+            gpu.imgBuffer.computeTextures.push_back(std::make_shared<ComputeBuffer>(clContext.ctx->alloc(sz), sz, clContext.ctx));
+        }
+        gpu.imgBuffer.bufferType = BufferType::gpu;
+        gpu.done = std::make_shared<Event>(clContext.ctx);
+        backing.push_back(gpu);
+        return gpu;
+    }
+    PictureSample image = backing[currentBacking];
+    currentBacking = (currentBacking + 1) % (int)backing.size();
+    return image;
+}
+
+VideoMixer::Tick VideoMixer::beginTick() {  // :113-115
+    Tick tk;
+    tk.backing = getBacking();
+    std::map<std::string, std::shared_ptr<const PictureSample>> merged = samples[1];
+    for (const auto& kv : samples[0]) merged[kv.first] = kv.second;  // merging { lhs, _ in lhs }: generation 0 wins
+    for (const auto& kv : merged) tk.images.push_back(kv.second);
+    // upstream's sort is unstable and the source is a dictionary: equal zIndex has no defined order there.
+    // Here ties fall back to the revision string so that a frame is reproducible.
+    std::stable_sort(tk.images.begin(), tk.images.end(), [](const std::shared_ptr<const PictureSample>& a, const std::shared_ptr<const PictureSample>& b) { return a->zIndex() < b->zIndex(); });
+    return tk;
+}
+
+void VideoMixer::endTick() {  // the `defer` block, :104-107
+    samples[1] = samples[0];
+    samples[0].clear();
+}
+
+ComputeContext VideoMixer::composeRaw(const ComputeContext& ctxIn, const PictureSample& target, const std::vector<const PictureSample*>& layers,
+                                      const ImageUniforms* uniforms, Mode mode) {
+    const std::string tname = pixelFormatName(target.pixelFormat());
+    // findKernel for the clear pass and every layer first: an unsupported pair fails before any work is queued
+    const ComputeKernel clearKernel = defaultComputeKernelFromString("img_clear_" + tname);
+    std::vector<ComputeKernel> kernels;
+    for (const PictureSample* l : layers) kernels.push_back(defaultComputeKernelFromString(std::string("img_") + pixelFormatName(l->pixelFormat()) + "_" + tname));
+    const int tf = svbFormat(target.pixelFormat());
+    if (mode == Mode::perLayer || (tf != SVB_NV12 && tf != SVB_Y420P)) {
+        // the reference's own sequence (mix.video.swift:117-124): clear, then one launch per layer
+        ComputeContext ctx = runComputeKernel(ctxIn, {}, target, clearKernel, "", 3, nullptr, 0, false);
+        for (size_t k = 0; k < layers.size(); ++k) ctx = runComputeKernel(ctx, {layers[k]}, target, kernels[k], "", 3, &uniforms[k], sizeof(ImageUniforms), true);
+        return ctx;
+    }
+    for (ComputeKernel k : kernels)
+        if (k == ComputeKernel::img_bgra_bgra) throw ComputeError(ErrorCode::computeKernelNotFound, "computeKernelNotFound(img_bgra_bgra)");
+    std::vector<Job> jobs(1);
+    jobs[0].target = &target;
+    jobs[0].layers = layers;
+    jobs[0].uniforms.assign(uniforms, uniforms + layers.size());
+    composeFused(ctxIn, jobs, mode == Mode::generic);
+    return ctxIn;
+}
+
+PictureSample VideoMixer::mix(int64_t time, bool wait) {
+    VideoMixer* self = this;
+    PictureSample out;
+    mixMany(&self, 1, time, &out, wait);
+    return out;
+}
+
+void VideoMixer::mixMany(VideoMixer* const* mixers, int n, int64_t time, PictureSample* outs, bool wait) {
+    if (n <= 0) return;
+    for (int i = 0; i < n; ++i) {
+        if (!mixers[i]->hasContext) throw ComputeError(ErrorCode::badContextState, "No context");
+        if (mixers[i]->clContext.ctx != mixers[0]->clContext.ctx) throw ComputeError(ErrorCode::invalidContext, "mixMany: mixers must share one compute context");
+    }
+    struct EndTicks {  // the `defer` of mix(at:): generations rotate even when compose throws
+        VideoMixer* const* m;
+        int n;
+        ~EndTicks() {
+            for (int i = 0; i < n; ++i) m[i]->endTick();
+        }
+    } defer{mixers, n};
+
+    std::vector<Tick> ticks;
+    ticks.reserve(n);
+    std::vector<Job> jobs;
+    bool fusedAll = true;
+    for (int i = 0; i < n; ++i) {
+        ticks.push_back(mixers[i]->beginTick());
+        const int tf = svbFormat(ticks.back().backing.pixelFormat());
+        fusedAll = fusedAll && mixers[i]->mode != Mode::perLayer && (tf == SVB_NV12 || tf == SVB_Y420P);
+    }
+    ComputeContext ctx0 = mixers[0]->clContext;
+    if (fusedAll) {
+        jobs.resize(n);
+        bool generic = false;
+        for (int i = 0; i < n; ++i) {
+            Tick& tk = ticks[i];
+            jobs[i].target = &tk.backing;
+            mixers[i]->findKernel(nullptr, tk.backing);
+            for (const auto& im : tk.images) {
+                const ComputeKernel k = mixers[i]->findKernel(im.get(), tk.backing);  // throws invalidValue for an unknown pair, as upstream
+                if (k == ComputeKernel::img_bgra_bgra) throw ComputeError(ErrorCode::computeKernelNotFound, "computeKernelNotFound(img_bgra_bgra)");
+                jobs[i].layers.push_back(im.get());
+                jobs[i].uniforms.push_back(makeImageUniforms(*im, tk.backing));
+            }
+            generic = generic || mixers[i]->mode == Mode::generic;
+        }
+        composeFused(ctx0, jobs, generic);
+    } else {
+        for (int i = 0; i < n; ++i) {
+            Tick& tk = ticks[i];
+            std::vector<const PictureSample*> layers;
+            std::vector<ImageUniforms> us;
+            for (const auto& im : tk.images) {
+                layers.push_back(im.get());
+                us.push_back(makeImageUniforms(*im, tk.backing));
+            }
+            mixers[i]->clContext = composeRaw(mixers[i]->clContext, tk.backing, layers, us.data(), mixers[i]->mode);
+        }
+    }
+    {
+        CtxGuard g(ctx0.ctx);
+        for (int i = 0; i < n; ++i) {
+            PictureSample& b = ticks[i].backing;
+            if (b.done) check(drv().cuEventRecord(b.done->e, ctx0.ctx->compute), "cuEventRecord");
+            outs[i] = b;  // PictureSample(backing, pts:, time:) :127-130
+            outs[i].timeValue = time;
+            outs[i].ptsValue = time - mixers[i]->epoch;
+            outs[i].timescale = mixers[i]->timescale;
+        }
+        if (wait) check(drv().cuStreamSynchronize(ctx0.ctx->compute), "cuStreamSynchronize");  // endComputePass(ctx, true)
+    }
+}
+
+}  // namespace svb

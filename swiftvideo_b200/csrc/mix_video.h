@@ -1,0 +1,92 @@
+// mix_video.h -- VideoMixer, mirroring /root/reference/Sources/SwiftVideo/mix.video.swift:21-184.
+//
+// What is kept: the constructor's parameters that matter to compositing (:22-30), the ingest rule of the
+// closure (:57-75: a sample of another asset is stored by revision, the mixer's own samples pass through),
+// the two-generation sample store (:104-107,114), z-ordering (:115), the backing ring of 10 GPU targets
+// (:148-167), findKernel's name construction (:142-146) with its error behaviour, clear-then-fold (:116-125),
+// the emitted sample (:127-131).  What is not rebuilt: the Clock/Bus/Source plumbing around it (SURVEY.md
+// section 2.1 #11, out of scope) -- the caller drives mix(at:) instead of a WallClock timer.
+//
+// What is ours: the fold is one fused launch (svb_mix_tiled / svb_mix_generic) instead of L+1 launches,
+// 2L allocations and 2L synchronous copies; several mixers of one GPU can be folded into
+// the same launch (mixMany); waiting for completion is optional.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "compute.h"
+#include "svb_desc.h"
+
+namespace svb {
+
+class VideoMixer {
+  public:
+    enum class Mode : int {
+        fused = 0,     // tiled kernel where its preconditions hold, else the generic fused kernel
+        perLayer = 1,  // the reference's own sequence: clear kernel + one applyComputeImage per layer
+        generic = 2    // the generic fused kernel only
+    };
+
+    VideoMixer(const ComputeContext* computeContext, Vector2 outputSize, PixelFormat outputFormat = PixelFormat::nv12,
+               const std::string& assetId = "", const std::string& workspaceId = "", int64_t frameDuration = 1000,
+               int64_t timescale = 30000, int64_t epoch = 0);
+
+    const std::string& assetId() const { return idAsset; }
+    const std::string& workspaceId() const { return idWorkspace; }
+    ComputeContext* computeContext() { return hasContext ? &clContext : nullptr; }
+    void setMode(Mode m) { mode = m; }
+
+    // The body of the ingest closure (mix.video.swift:57-75).  Returns true when the sample was stored as a
+    // layer (`.nothing`), false when it is the mixer's own asset and simply passes through (`.just`).
+    bool push(const PictureSample& pic);
+    bool push(std::shared_ptr<const PictureSample> pic);
+
+    // mix(at:) (:95-140): compose the stored layers into the next backing image and return the emitted
+    // sample.  `time` is the tick time in `timescale` units.  wait=true is upstream's endComputePass(ctx, true).
+    PictureSample mix(int64_t time, bool wait = true);
+
+    // Fold the ticks of several mixers that share one GPU context into one launch.
+    static void mixMany(VideoMixer* const* mixers, int n, int64_t time, PictureSample* outs, bool wait);
+
+    // Low-level fold used by mix(): clear + layers (already z-sorted) into `target`, uniforms given.
+    static ComputeContext composeRaw(const ComputeContext& ctx, const PictureSample& target,
+                                     const std::vector<const PictureSample*>& layers, const ImageUniforms* uniforms, Mode mode);
+
+    int64_t frameDuration, timescale, epoch;
+
+  private:
+    struct Tick {
+        PictureSample backing;
+        std::vector<std::shared_ptr<const PictureSample>> images;  // z-sorted, kept alive until the launch is queued
+    };
+    Tick beginTick();                                                          // :113-115
+    ComputeKernel findKernel(const PictureSample* image, const PictureSample& target) const;  // :142-146
+    PictureSample getBacking();                                                // :148-165
+    void endTick();                                                            // :104-107
+
+    static const int numberBackingImages = 10;  // :167
+    std::vector<PictureSample> backing;
+    int currentBacking = 0;
+    PixelFormat backingFormat;
+    Vector2 backingSize;
+    ComputeContext clContext;
+    bool hasContext = false;
+    std::map<std::string, std::shared_ptr<const PictureSample>> samples[2];
+    std::string idAsset, idWorkspace;
+    Mode mode = Mode::fused;
+};
+
+// Device time of the fused launches (CUDA events around each kernel on the compute stream), for the roofline.
+void setLaunchTiming(const ComputeContext& ctx, bool on);
+void readLaunchTiming(const ComputeContext& ctx, double* totalMs, unsigned long long* launches);
+
+// Planner: fills frame descriptors (one per pass of 16 layers) for one target.  Exposed for tests.
+struct FramePlan {
+    std::vector<SvbFrameDesc> passes;
+    bool tiledOk = false;
+};
+FramePlan planFrame(const ComputeContext& ctx, const PictureSample& target, const std::vector<const PictureSample*>& layers,
+                    const ImageUniforms* uniforms);
+
+}  // namespace svb

@@ -1,0 +1,73 @@
+// svb_desc.h -- frame/layer descriptors shared by the host planner (mix_video.cpp) and the fused kernels.
+// Plain C structs: compiled by g++ and nvcc alike.
+#pragma once
+#include <stdint.h>
+
+#define SVB_MAX_LAYERS 16
+
+// tile of the tiled kernel (luma pixels); chroma is TILE_W/2 x TILE_H/2
+#define SVB_TILE_W 128
+#define SVB_TILE_H 32
+// largest source footprint the tiled kernel stages in shared memory per tile and layer
+#define SVB_BOX_Y_BYTES (20 * 1024)
+#define SVB_BOX_C_BYTES (12 * 1024)
+
+enum SvbFormat { SVB_NV12 = 0, SVB_Y420P = 1, SVB_BGRA = 2, SVB_RGBA = 3 };
+
+enum {
+    SVB_FRAME_LOAD_CUR = 1  // continue an earlier pass: start from the target's bytes, not from clear
+};
+enum {
+    SVB_LAYER_SEPARABLE = 1,     // x outputs depend only on x and y outputs only on y (no rotation/shear)
+    SVB_LAYER_UNIT_OPACITY = 2,  // opacity == 1: cur*(1-1) + v*1 == v exactly, the blend is skipped
+    SVB_LAYER_STAGED = 4,        // tensor maps below are valid: source footprints are staged by TMA
+    SVB_LAYER_OPACITY_01 = 8     // 0 <= opacity <= 1: blended values cannot leave [0,1], store clamps are no-ops
+};
+
+// ImageUniforms as uploaded by applyComputeImage (reference compute.swift:76-86; device mirror
+// kernels.cl.swift:49-59): 236 bytes of payload, padded to 240 so the float4 rows stay 16-byte aligned.
+typedef struct __attribute__((aligned(16))) SvbUniforms {
+    float transform[16];
+    float textureTx[16];
+    float borderMatrix[16];
+    float fillColor[4];
+    float inSize[2];
+    float outSize[2];
+    float opacity;
+    float sampleTime;
+    float targetTime;
+    float pad_;
+} SvbUniforms;
+
+typedef struct __attribute__((aligned(64))) SvbLayerDesc {
+    unsigned char tmap[3][128];  // CUtensorMap per source plane (valid when SVB_LAYER_STAGED), 64-byte aligned
+    SvbUniforms u;               // 240
+    unsigned long long plane[3]; // device pointers
+    int32_t stride[3];
+    int32_t width, height;       // luma / RGBA size; chroma planes are (width/2, height/2)
+    int32_t format;
+    int32_t flags;               // SVB_LAYER_*
+    int32_t rect[4];             // x0,y0,x1,y1: outside this canvas rectangle the layer touches nothing
+    int32_t box_w, box_h;        // staged luma box (elements); chroma box is box_cw x box_ch
+    int32_t box_cw, box_ch;
+    int32_t pad_[9];
+} SvbLayerDesc;
+
+typedef struct __attribute__((aligned(64))) SvbFrameDesc {
+    unsigned long long out_plane[3];
+    int32_t out_stride[3];
+    int32_t width, height;
+    int32_t format;
+    int32_t nlayers;
+    int32_t flags;       // SVB_FRAME_*
+    int32_t first_tile;  // prefix sum of tiles over the batch
+    int32_t tiles_x, tiles_y;
+    int32_t pad_[5];
+    SvbLayerDesc layers[SVB_MAX_LAYERS];
+} SvbFrameDesc;
+
+#ifdef __cplusplus
+static_assert(sizeof(SvbUniforms) == 240, "SvbUniforms layout");
+static_assert(sizeof(SvbLayerDesc) % 64 == 0, "SvbLayerDesc alignment");
+static_assert(sizeof(SvbFrameDesc) % 64 == 0, "SvbFrameDesc alignment");
+#endif

@@ -1,0 +1,195 @@
+// svb_device.cuh -- device-side types and the bit-exact per-pixel arithmetic shared by every kernel.
+//
+// What is computed is fixed by the reference's OpenCL kernels (the parity target named by north_star):
+//   /root/reference/Sources/SwiftVideo/kernels.cl.swift:63-108 (img_nv12_nv12 and its YUV siblings),
+//   :283-334,:485-531 (BGRA/RGBA sources), :38-46,:174-185,:257-265 (clear),
+// with OpenCL 1.2 image semantics (UNORM8 read c/255.0f, write sat_rte(f*255.0f), linear sampler
+// section 8.2).  HOW it is computed is ours.  Every multiply and add must round separately (the
+// reference builds its CUDA with --fmad=false, compute.cuda.swift:177): all arithmetic below goes
+// through __fmul_rn/__fadd_rn/__fsub_rn/__fdiv_rn, which the compiler never contracts or reassociates.
+#pragma once
+#include <stdint.h>
+
+#include "svb_desc.h"
+
+// The drop-in kernels receive the reference's own 236-byte ImageUniforms upload; SvbUniforms has the same
+// offsets (the device-side struct pads to 240 upstream as well, kernels.cl.swift:49-59).
+typedef SvbUniforms ImageUniforms;
+
+namespace svb {
+
+__device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+
+__device__ __forceinline__ float4 ldrow(const float* m, int row) { return __ldg((const float4*)m + row); }
+
+// dot(float4,float4) summed left to right
+__device__ __forceinline__ float dot4(float x, float y, float z, float w, const float4 m) {
+    return add(add(add(mul(x, m.x), mul(y, m.y)), mul(z, m.z)), mul(w, m.w));
+}
+
+// OpenCL clamp = fmin(fmax(x, lo), hi); CUDA fminf/fmaxf drop a NaN operand the same way
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+
+// UNORM8 read: c / 255.0f, correctly rounded.  Division-free and exact for every byte: with K1 = fl(1/255)
+// and K2 = fl(1/255 - K1), fma(c, K1, fl(c*K2)) carries ~48 bits of c/255 into one rounding, and c/255 (an
+// 8-bit pattern repeating in binary) is never that close to a rounding boundary.  tests/test_gpu_parity.py
+// checks all 256 values against __fdiv_rn on the device.
+#define SVB_K1 __uint_as_float(0x3b808081u)
+#define SVB_K2 __uint_as_float(0xaf7efeffu)
+__device__ __forceinline__ float unorm_f(float c) { return __fmaf_rn(c, SVB_K1, __fmul_rn(c, SVB_K2)); }
+__device__ __forceinline__ float unorm(unsigned c) { return unorm_f((float)c); }
+__device__ __forceinline__ float unorm_div(unsigned c) { return __fdiv_rn((float)c, 255.0f); }
+
+// UNORM8 write: convert_uchar_sat_rte(f * 255.0f); NaN -> 0
+__device__ __forceinline__ unsigned rte8(float f) {
+    float v = fminf(fmaxf(mul(f, 255.0f), 0.0f), 255.0f);
+    return (unsigned)__float2int_rn(v);
+}
+
+__device__ __forceinline__ bool in01(float x, float y) { return x >= 0.f && y >= 0.f && x <= 1.f && y <= 1.f; }
+
+// Linear sampler footprint: OpenCL 1.2 section 8.2, normalised coords, clamp-to-edge.
+struct Taps {
+    int i0, i1, j0, j1;
+    float w00, w10, w01, w11;
+};
+__device__ __forceinline__ Taps make_taps(float s, float t, int w, int h) {
+    Taps k;
+    float u = mul(s, (float)w), v = mul(t, (float)h);
+    float um = sub(u, 0.5f), vm = sub(v, 0.5f);
+    float fu = floorf(um), fv = floorf(vm);
+    float a = sub(um, fu), b = sub(vm, fv);
+    int i = (int)fu, j = (int)fv;
+    k.i0 = min(max(i, 0), w - 1);
+    k.i1 = min(max(i + 1, 0), w - 1);
+    k.j0 = min(max(j, 0), h - 1);
+    k.j1 = min(max(j + 1, 0), h - 1);
+    float na = sub(1.0f, a), nb = sub(1.0f, b);
+    k.w00 = mul(na, nb);
+    k.w10 = mul(a, nb);
+    k.w01 = mul(na, b);
+    k.w11 = mul(a, b);
+    return k;
+}
+// (1-a)(1-b)T00 + a(1-b)T10 + (1-a)b T01 + ab T11, left to right
+__device__ __forceinline__ float filt(const Taps& k, float t00, float t10, float t01, float t11) {
+    return add(add(add(mul(k.w00, t00), mul(k.w10, t10)), mul(k.w01, t01)), mul(k.w11, t11));
+}
+__device__ __forceinline__ float sample1(const uint8_t* __restrict__ p, int stride, int ncomp, int c, const Taps& k) {
+    const uint8_t* r0 = p + (size_t)k.j0 * stride + c;
+    const uint8_t* r1 = p + (size_t)k.j1 * stride + c;
+    return filt(k, unorm(__ldg(r0 + k.i0 * ncomp)), unorm(__ldg(r0 + k.i1 * ncomp)), unorm(__ldg(r1 + k.i0 * ncomp)),
+                unorm(__ldg(r1 + k.i1 * ncomp)));
+}
+__device__ __forceinline__ float4 sample4(const uint8_t* __restrict__ p, int stride, const Taps& k) {
+    const uchar4 a = __ldg((const uchar4*)(p + (size_t)k.j0 * stride) + k.i0);
+    const uchar4 b = __ldg((const uchar4*)(p + (size_t)k.j0 * stride) + k.i1);
+    const uchar4 c = __ldg((const uchar4*)(p + (size_t)k.j1 * stride) + k.i0);
+    const uchar4 d = __ldg((const uchar4*)(p + (size_t)k.j1 * stride) + k.i1);
+    float4 r;
+    r.x = filt(k, unorm(a.x), unorm(b.x), unorm(c.x), unorm(d.x));
+    r.y = filt(k, unorm(a.y), unorm(b.y), unorm(c.y), unorm(d.y));
+    r.z = filt(k, unorm(a.z), unorm(b.z), unorm(c.z), unorm(d.z));
+    r.w = filt(k, unorm(a.w), unorm(b.w), unorm(c.w), unorm(d.w));
+    return r;
+}
+
+// RGB2YUV rows, kernels.cl.swift:96-99 (0.113 as written upstream); v.w is always 1
+__device__ __forceinline__ float3 rgb2yuv(float r, float g, float b) {
+    float3 o;
+    o.x = dot4(r, g, b, 1.0f, make_float4(0.299f, 0.587f, 0.113f, 0.f));
+    o.y = dot4(r, g, b, 1.0f, make_float4(-0.169f, -0.331f, 0.5f, 0.5f));
+    o.z = dot4(r, g, b, 1.0f, make_float4(0.5f, -0.419f, -0.081f, 0.5f));
+    return o;
+}
+
+// Source picture as the kernels see it.
+struct Src {
+    const uint8_t* p[3];
+    int stride[3];
+    int w, h;    // luma / RGBA plane size
+    int cw, ch;  // chroma plane size
+    int format;
+};
+
+// One work-item of img_<src>_<dst> on luma pixel (x,y) of a WxH target.
+//   cy/cu/cv : current target values as UNORM floats (cu/cv only meaningful when `chroma`)
+//   returns false when the pixel is left untouched; otherwise oy (and ou/ov when `chroma`) hold the
+//   floats the reference hands to write_imagef.
+__device__ __forceinline__ bool eval_pixel(const ImageUniforms* __restrict__ U, const Src& s, int x, int y, float W,
+                                           float H, bool chroma, float cy, float cu, float cv, float& oy, float& ou,
+                                           float& ov) {
+    const float nx = sub(mul(__fdiv_rn((float)x, W), 2.f), 1.f);
+    const float ny = sub(mul(__fdiv_rn((float)y, H), 2.f), 1.f);
+    const float bx = dot4(nx, ny, 0.f, 1.f, ldrow(U->borderMatrix, 0));
+    const float by = dot4(nx, ny, 0.f, 1.f, ldrow(U->borderMatrix, 1));
+    if (!in01(bx, by)) return false;
+    const float t0 = dot4(nx, ny, 0.f, 1.f, ldrow(U->transform, 0));
+    const float t1 = dot4(nx, ny, 0.f, 1.f, ldrow(U->transform, 1));
+    const float t2 = dot4(nx, ny, 0.f, 1.f, ldrow(U->transform, 2));
+    const float t3 = dot4(nx, ny, 0.f, 1.f, ldrow(U->transform, 3));
+    const float uu = dot4(t0, t1, t2, t3, ldrow(U->textureTx, 0));
+    const float vv = dot4(t0, t1, t2, t3, ldrow(U->textureTx, 1));
+    const float opacity = __ldg(&U->opacity);
+    const float4 fc = ldrow(U->fillColor, 0);
+    const bool in_tx = in01(t0, t1), in_uv = in01(uu, vv);
+
+    if (s.format == SVB_NV12 || s.format == SVB_Y420P) {
+        if (in_tx && in_uv) {
+            const float na = sub(1.f, opacity);
+            Taps k = make_taps(uu, vv, s.w, s.h);
+            oy = add(mul(cy, na), mul(sample1(s.p[0], s.stride[0], 1, 0, k), opacity));
+            if (chroma) {
+                Taps kc = make_taps(uu, vv, s.cw, s.ch);
+                float cb, cr;
+                if (s.format == SVB_NV12) {
+                    cb = sample1(s.p[1], s.stride[1], 2, 0, kc);
+                    cr = sample1(s.p[1], s.stride[1], 2, 1, kc);
+                } else {
+                    cb = sample1(s.p[1], s.stride[1], 1, 0, kc);
+                    cr = sample1(s.p[2], s.stride[2], 1, 0, kc);
+                }
+                ou = add(mul(cu, na), mul(cb, opacity));
+                ov = add(mul(cv, na), mul(cr, opacity));
+            }
+            return true;
+        }
+        const float3 f = rgb2yuv(fc.x, fc.y, fc.z);
+        const float a = mul(opacity, fc.w), na = sub(1.f, a);
+        oy = clampf(add(mul(cy, na), mul(f.x, a)), 0.f, 1.f);
+        if (chroma) {
+            ou = clampf(add(mul(cu, na), mul(f.y, a)), -1.f, 1.f);
+            ov = clampf(add(mul(cv, na), mul(f.z, a)), -1.f, 1.f);
+        }
+        return true;
+    }
+    // BGRA / RGBA sources
+    if (!in_tx) return false;
+    const float a = mul(opacity, fc.w), na = sub(1.f, a);
+    const float3 f = rgb2yuv(mul(fc.x, a), mul(fc.y, a), mul(fc.z, a));
+    float r0 = add(mul(cy, na), mul(f.x, a));
+    float r1 = clampf(add(mul(cu, na), mul(f.y, a)), -1.f, 1.f);
+    float r2 = clampf(add(mul(cv, na), mul(f.z, a)), -1.f, 1.f);
+    if (in_uv) {
+        Taps k = make_taps(uu, vv, s.w, s.h);
+        float4 px = sample4(s.p[0], s.stride[0], k);
+        if (s.format == SVB_BGRA) {
+            float t = px.x;
+            px.x = px.z;
+            px.z = t;
+        }
+        const float a2 = mul(px.w, opacity), n2 = sub(1.f, a2);
+        const float3 q = rgb2yuv(mul(px.x, a2), mul(px.y, a2), mul(px.z, a2));
+        r0 = add(mul(r0, n2), mul(q.x, a2));
+        r1 = add(mul(r1, n2), mul(q.y, a2));
+        r2 = add(mul(r2, n2), mul(q.z, a2));
+    }
+    oy = r0;
+    ou = r1;
+    ov = r2;
+    return true;
+}
+
+}  // namespace svb

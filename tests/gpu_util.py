@@ -1,0 +1,48 @@
+"""Helpers shared by the -m gpu tests: move oracle images onto the device and back through the C ABI."""
+import numpy as np
+
+import swiftvideo_b200 as sv
+from oracle import oracle as O
+
+FMT = {O.NV12: sv.NV12, O.Y420P: sv.Y420P, O.BGRA: sv.BGRA, O.RGBA: sv.RGBA}
+
+_ctx = None
+
+
+def context():
+    global _ctx
+    if _ctx is None:
+        _ctx = sv.make_compute_context(0)
+    return _ctx
+
+
+def to_gpu(ctx, img, asset="layer", pinned=False):
+    """O.Image -> uploaded PictureSample (same contiguous plane layout on both sides)."""
+    p = sv.create_picture_sample(img.width, img.height, FMT[img.format], asset, "test", pinned_from=ctx if pinned else None)
+    p.set_host_bytes(img.data)
+    return p.upload(ctx)
+
+
+def gpu_target(ctx, fmt, w, h, asset="target"):
+    p = sv.create_picture_sample(w, h, FMT[fmt], asset, "test")
+    p.set_host_bytes(np.full(O.Image(fmt, w, h).nbytes, 0xA5, dtype=np.uint8))  # stale bytes the clear must overwrite
+    return p.upload(ctx)
+
+
+def fetch(ctx, pict):
+    return pict.download(ctx, retain_gpu_buffer=True).host_bytes().copy()
+
+
+def gpu_case(ctx, case, mode):
+    """Run a scenes.Case through svb_compose with the oracle's own uniforms; returns the target bytes."""
+    layers = [to_gpu(ctx, l, f"l{i}") for i, l in enumerate(case.layers)]
+    target = gpu_target(ctx, case.target_fmt, case.canvas[0], case.canvas[1])
+    sv.compose(ctx, target, layers, case.uniforms, mode)
+    return fetch(ctx, target)
+
+
+def first_diff(a, b, case=None):
+    d = np.nonzero(a != b)[0]
+    if d.size == 0:
+        return "identical"
+    return f"{d.size} bytes differ, first at {d[0]}: got {a[d[0]]} want {b[d[0]]}"

@@ -210,3 +210,23 @@ def run_case(lib, case, threads=0):
     target.data[:] = 0xA5  # stale bytes: the clear pass must overwrite them
     rc = lib.mix(target, case.layers, case.uniforms, threads=threads)
     return rc, target
+
+
+def golden_cases():
+    """Cases stored in tests/golden/cases.npz (inputs + the bytes oracle/_ref produced): [(Case, expected bytes)]."""
+    import ctypes as C
+    from pathlib import Path
+    z = np.load(Path(__file__).resolve().parent / "golden" / "cases.npz")
+    out = []
+    for name in z["names"]:
+        name = str(name)
+        tf, w, h, n = (int(v) for v in z[f"{name}/meta"])
+        layers, us = [], []
+        for i in range(n):
+            lf, lw, lh = (int(v) for v in z[f"{name}/l{i}/meta"])
+            layers.append(O.Image(lf, lw, lh, z[f"{name}/l{i}/data"]))
+            u = O.Uniforms()
+            C.memmove(C.byref(u), z[f"{name}/l{i}/uniforms"].tobytes(), 236)
+            us.append(u)
+        out.append((Case(name, tf, (w, h), layers, us), z[f"{name}/out"]))
+    return out

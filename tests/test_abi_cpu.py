@@ -1,0 +1,109 @@
+"""CPU: the C-ABI library loads, exports every symbol include/svb200.h declares, and its host-side logic
+(kernel-name map, picture layouts, zIndex, uniforms) behaves like the reference's.  No compute calls."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import scenes
+import swiftvideo_b200 as sv
+from oracle import oracle as O
+from swiftvideo_b200 import animator, api
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_every_declared_symbol_is_exported():
+    header = (ROOT / "include" / "svb200.h").read_text()
+    names = set(re.findall(r"^(?:svb_status|int|void|const char\*|unsigned long long)\s+(svb_[a-z0-9_]+)\s*\(", header, re.M))
+    assert len(names) >= 40
+    for n in sorted(names):
+        assert hasattr(sv.lib, n), f"{n} declared in include/svb200.h but not exported by libsvb200.so"
+
+
+def test_kernel_name_map():
+    """The reference's only compute test (Tests/swiftVideoInternalTests/computeTests.swift:9-39): name -> enum."""
+    names = ["img_nv12_nv12", "img_bgra_nv12", "img_rgba_nv12", "img_bgra_bgra", "img_y420p_y420p", "img_y420p_nv12", "img_clear_nv12",
+             "img_clear_yuvs", "img_clear_bgra", "img_clear_y420p", "img_rgba_y420p", "img_bgra_y420p"]
+    for n in names:
+        k = api.default_compute_kernel_from_string(n)
+        assert sv.lib.svb_compute_kernel_name(k).decode() == n
+    # img_clear_rgba maps to img_clear_bgra (compute.swift:101)
+    assert sv.lib.svb_compute_kernel_name(api.default_compute_kernel_from_string("img_clear_rgba")).decode() == "img_clear_bgra"
+    with pytest.raises(sv.ComputeError) as e:
+        api.default_compute_kernel_from_string("img_nv12_y420p")
+    assert e.value.name == "invalidValue"
+
+
+def test_module_image_has_the_reference_entry_points():
+    img = sv.kernel_module_image()
+    assert img[:4] == b"\x7fELF"
+    for n in ("img_clear_nv12", "img_clear_y420p", "img_clear_bgra", "img_nv12_nv12", "img_y420p_nv12", "img_y420p_y420p",
+              "img_bgra_nv12", "img_rgba_nv12", "img_bgra_y420p", "img_rgba_y420p", "svb_mix_tiled", "svb_mix_generic"):
+        assert n.encode() in img
+
+
+def test_picture_layouts():
+    """planesForFormat / buffersForPlanes (sample.pict.linux.swift:275-311): one allocation, planes back to back."""
+    for fmt, ofmt in ((sv.NV12, O.NV12), (sv.Y420P, O.Y420P), (sv.BGRA, O.BGRA), (sv.RGBA, O.RGBA)):
+        p = sv.create_picture_sample(64, 36, fmt, "a", "w")
+        i = p.info()
+        layout, total = O.plane_layout(ofmt, 64, 36)
+        assert i.plane_count == len(layout)
+        base = i.planes[0].host
+        for k, (off, w, h, stride, nc) in enumerate(layout):
+            pl = i.planes[k]
+            assert (int(pl.width), int(pl.height), pl.stride, pl.components, pl.bit_depth) == (w, h, stride, nc, 8)
+            assert pl.host - base == off
+        assert i.buffer_type == api.BUFFER_CPU and list(i.fill_color) == [0, 0, 0, 1] and i.opacity == 1.0
+    with pytest.raises(sv.ComputeError) as e:
+        sv.create_picture_sample(0, 10, sv.NV12)
+    assert e.value.name == "invalidOperation"
+    with pytest.raises(sv.ComputeError) as e:
+        sv.create_picture_sample(16, 16, api.Y444P)
+    assert e.value.name == "badInputData"
+
+
+def test_z_index_and_with():
+    p = sv.create_picture_sample(16, 16, sv.NV12, "asset", "w")
+    for z in (0.0, 1.4, 2.5, -1.0):
+        m, t, b = animator.picture_state((64, 64), (16, 16), (3, 4), (20, 20), z=z)
+        q = p.with_(matrix=m)
+        assert q.z_index() == int(np.floor(abs(z + 1) + 0.5) * np.sign(z + 1))  # round(pos.z + 1), half away from zero
+    q = p.with_(opacity=0.25, fill_color=(0.1, 0.2, 0.3, 0.4), revision="rev")
+    i = q.info()
+    assert i.opacity == 0.25 and np.allclose(list(i.fill_color), [0.1, 0.2, 0.3, 0.4])
+    assert list(p.info().fill_color) == [0, 0, 0, 1]  # the original is immutable
+
+
+def test_uniforms_host_logic():
+    """applyComputeImage's uniforms (inverse.transpose of the three matrices, compute.swift:149-161) against an
+    independent float64 construction; fp32 inverse rounding is unpinned upstream, hence a tolerance."""
+    canvas = (1280, 720)
+    tgt = sv.create_picture_sample(canvas[0], canvas[1], sv.NV12, "t", "w")
+    src = sv.create_picture_sample(640, 360, sv.Y420P, "s", "w")
+    for kw in (dict(pos=(0, 0), size=(640, 720), aspect="fill"), dict(pos=(100, 50), size=(320, 200), rotation=0.4, border=(3, 4, 5, 6)),
+               dict(pos=(-20, 600), size=(900, 300), aspect="fit", z=3.0)):
+        m, t, b = animator.picture_state(canvas, (640, 360), **kw)
+        q = src.with_(matrix=m, texture_matrix=t, border_matrix=b, opacity=0.5, fill_color=(1, 0, 0, 1))
+        u = api.make_image_uniforms(q, tgt)
+        want = scenes.layer_uniforms(canvas, (640, 360), kw["pos"], kw["size"], rotation=kw.get("rotation", 0.0), z=kw.get("z", 0.0),
+                                     opacity=0.5, fill=(1, 0, 0, 1), border=kw.get("border", (0, 0, 0, 0)), aspect=kw.get("aspect", "none"))
+        for a, w in ((u.transform, want.transform), (u.texture_transform, want.textureTx), (u.border_matrix, want.borderMatrix)):
+            assert np.allclose(np.array(a[:]), np.array(w[:]), rtol=2e-5, atol=2e-5)
+        assert list(u.input_size) == [640, 360] and list(u.output_size) == [1280, 720] and u.opacity == 0.5
+        if not kw.get("rotation"):  # axis-aligned layers must give exact zeros: the separable fast path keys on them
+            tr = np.array(u.transform[:]).reshape(4, 4)
+            assert tr[0, 1] == 0 and tr[1, 0] == 0 and tr[2, 0] == 0 and tr[2, 1] == 0 and tr[3, 0] == 0 and tr[3, 1] == 0
+
+
+@pytest.mark.skipif(sv.available_compute_devices() > 0, reason="a GPU is present")
+def test_no_cpu_fallback():
+    """Without a device every compute entry point fails loudly (ComputeError.deviceNotAvailable)."""
+    with pytest.raises(sv.ComputeError) as e:
+        sv.make_compute_context()
+    assert e.value.name == "deviceNotAvailable"
+    with pytest.raises(sv.ComputeError):
+        sv.VideoMixer(None, 64, 64).mix(0)

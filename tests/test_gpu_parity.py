@@ -1,0 +1,128 @@
+"""-m gpu: the CUDA path through the C ABI against the oracle -- bit-exact bytes.
+
+Every case runs in all three compose modes: the tiled TMA kernel (FUSED), the generic fused kernel (GENERIC)
+and the reference's own per-layer launch sequence over the drop-in kernels (PER_LAYER)."""
+import numpy as np
+import pytest
+
+import scenes
+import swiftvideo_b200 as sv
+from gpu_util import context, fetch, first_diff, gpu_case, gpu_target, to_gpu
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+MODES = [(sv.MixMode.FUSED, "fused"), (sv.MixMode.GENERIC, "generic"), (sv.MixMode.PER_LAYER, "per_layer")]
+CASES = scenes.parity_cases()
+
+
+def test_unorm_identity():
+    """The division-free UNORM8 read equals c/255.0f for every byte, on the device and against numpy."""
+    fast, divided = context().selftest_unorm()
+    want = np.arange(256, dtype=np.float32) / np.float32(255.0)
+    assert (fast.view(np.uint32) == divided.view(np.uint32)).all()
+    assert (fast.view(np.uint32) == want.view(np.uint32)).all()
+
+
+@pytest.mark.parametrize("mode,mname", MODES, ids=[m[1] for m in MODES])
+@pytest.mark.parametrize("case", CASES, ids=[c.name for c in CASES])
+def test_small_scenes(case, mode, mname):
+    rc, want = scenes.run_case(O.port(), case)
+    assert rc == 0
+    got = gpu_case(context(), case, mode)
+    assert (got == want.data).all(), f"{case.name}/{mname}: {first_diff(got, want.data)}"
+
+
+def _tiled_cases():
+    """Bigger canvases so that tiles lie fully inside layers (the TMA-staged table path) and on their edges."""
+    cases = []
+    canvas = (640, 352)
+    rng_seed = 7000
+    for sf, tf in ((O.NV12, O.NV12), (O.Y420P, O.NV12), (O.Y420P, O.Y420P)):
+        layers = [scenes.random_image(sf, 640, 352, rng_seed), scenes.random_image(sf, 960, 540, rng_seed + 1),
+                  scenes.random_image(sf, 320, 180, rng_seed + 2), scenes.random_image(sf, 400, 300, rng_seed + 3),
+                  scenes.random_image(sf, 512, 288, rng_seed + 4)]
+        us = [scenes.layer_uniforms(canvas, (640, 352), (0, 0), canvas, z=1, opacity=1.0),                       # 1:1
+              scenes.layer_uniforms(canvas, (960, 540), (40, 20), (480, 270), z=2, opacity=0.6),                 # 2x downscale
+              scenes.layer_uniforms(canvas, (320, 180), (100, 60), (500, 280), z=3, opacity=0.45),               # upscale
+              scenes.layer_uniforms(canvas, (400, 300), (-30, 100), (400, 250), z=4, opacity=0.8,                # off-canvas, fit + fill
+                                    fill=(0.3, 0.5, 0.7, 0.6), aspect="fit", border=(5, 5, 5, 5)),
+              scenes.layer_uniforms(canvas, (512, 288), (600, 330), (-560, -300), z=5, opacity=0.7)]             # mirrored in x and y
+        cases.append(scenes.Case(f"tiled_{O.FORMAT_NAMES[sf]}_{O.FORMAT_NAMES[tf]}", tf, canvas, layers, us))
+        rng_seed += 10
+    # heavy downscale (footprint does not fit the staged box -> global taps) and a 17-layer stack (two passes)
+    src = scenes.random_image(O.NV12, 1920, 1080, 7100)
+    cases.append(scenes.Case("tiled_downscale_4x", O.NV12, (480, 256), [src],
+                             [scenes.layer_uniforms((480, 256), (1920, 1080), (0, 0), (480, 256), z=1)]))
+    many_l, many_u = [], []
+    for k in range(17):
+        many_l.append(scenes.random_image(O.NV12, 160 + 16 * k, 96 + 8 * k, 7200 + k))
+        many_u.append(scenes.layer_uniforms((512, 288), (160 + 16 * k, 96 + 8 * k), (10 * k, 6 * k), (300, 170), z=k + 1, opacity=0.3 + 0.04 * k))
+    cases.append(scenes.Case("tiled_17_layers", O.NV12, (512, 288), many_l, many_u))
+    # odd plane strides / widths that break the tiled kernel's alignment preconditions fall back to generic
+    src = scenes.random_image(O.NV12, 250, 130, 7300)
+    cases.append(scenes.Case("unaligned_250x130_src", O.NV12, (384, 224), [src],
+                             [scenes.layer_uniforms((384, 224), (250, 130), (0, 0), (384, 224), z=1, opacity=0.9)]))
+    return cases
+
+
+TILED = _tiled_cases()
+
+
+@pytest.mark.parametrize("mode,mname", MODES, ids=[m[1] for m in MODES])
+@pytest.mark.parametrize("case", TILED, ids=[c.name for c in TILED])
+def test_tiled_scenes(case, mode, mname):
+    rc, want = scenes.run_case(O.port(), case, threads=O.host_threads())
+    assert rc == 0
+    got = gpu_case(context(), case, mode)
+    assert (got == want.data).all(), f"{case.name}/{mname}: {first_diff(got, want.data)}"
+
+
+def test_cfg2_full_size():
+    """BASELINE config 2 at full size: 1920x1080 NV12 -> 1280x720 NV12, bytes against the oracle."""
+    canvas, tf, layers, us = scenes.cfg2_scene()
+    case = scenes.Case("cfg2", tf, canvas, layers, us)
+    rc, want = scenes.run_case(O.port(), case, threads=O.host_threads())
+    assert rc == 0
+    for mode, mname in MODES:
+        got = gpu_case(context(), case, mode)
+        assert (got == want.data).all(), f"cfg2/{mname}: {first_diff(got, want.data)}"
+
+
+@pytest.mark.parametrize("nlayers", [4, 8])
+def test_cfg34_full_size(nlayers):
+    """BASELINE configs 3 and 4 (one stream) at 3840x2160: fused and generic against the oracle, and against each
+    other and the per-layer sequence (a size-independent cross-check: three independent code paths, same bytes)."""
+    canvas, tf, layers, us = scenes.cfg34_scene(nlayers)
+    case = scenes.Case(f"cfg{3 if nlayers == 4 else 4}", tf, canvas, layers, us)
+    rc, want = scenes.run_case(O.port(), case, threads=O.host_threads())
+    assert rc == 0
+    ctx = context()
+    outs = {}
+    for mode, mname in MODES:
+        outs[mname] = gpu_case(ctx, case, mode)
+        assert (outs[mname] == want.data).all(), f"{case.name}/{mname}: {first_diff(outs[mname], want.data)}"
+
+
+def test_properties_full_size():
+    """Size-independent properties at 4K: (1) an opaque full-canvas top layer hides everything below it;
+    (2) composing twice gives the same bytes (no state leaks between launches); (3) opacity 0 leaves the clear."""
+    ctx = context()
+    canvas, tf, layers, us = scenes.cfg34_scene(4)
+    gl = [to_gpu(ctx, l, f"p{i}") for i, l in enumerate(layers)]
+    top_only = gpu_target(ctx, tf, *canvas)
+    sv.compose(ctx, top_only, [gl[0]], [us[0]], sv.MixMode.FUSED)
+    stacked = gpu_target(ctx, tf, *canvas)
+    sv.compose(ctx, stacked, gl[1:] + [gl[0]], us[1:] + [us[0]], sv.MixMode.FUSED)  # layer 0 (opacity 1, full canvas) on top
+    a, b = fetch(ctx, top_only), fetch(ctx, stacked)
+    assert (a == b).all(), first_diff(a, b)
+    again = gpu_target(ctx, tf, *canvas)
+    sv.compose(ctx, again, gl[1:] + [gl[0]], us[1:] + [us[0]], sv.MixMode.FUSED)
+    assert (fetch(ctx, again) == b).all()
+    # opacity 0 everywhere: cur*(1-0) + v*0 == cur, so the picture stays at the clear values
+    zero = [scenes.layer_uniforms(canvas, (l.width, l.height), (0, 0), canvas, z=i + 1, opacity=0.0) for i, l in enumerate(layers)]
+    cleared = gpu_target(ctx, tf, *canvas)
+    sv.compose(ctx, cleared, gl, zero, sv.MixMode.FUSED)
+    want = O.Image(tf, *canvas)
+    O.port().clear(want)
+    assert (fetch(ctx, cleared) == want.data).all()
