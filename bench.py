@@ -147,6 +147,8 @@ def run_ours(args):
             for c in range(2):
                 dev[c][s][k] = host[s][k].upload(ctx)
     mixers = [sv.VideoMixer(ctx, CANVAS[0], CANVAS[1], sv.NV12, asset_id=f"mixer{rank * S + s}", workspace_id="bench") for s in range(S)]
+    for i in range(10):  # setup, untimed: fill every mixer's backing ring (10 targets, allocated on first use upstream too)
+        sv.VideoMixer.mix_many(mixers, -1 - i, wait=False)
     ctx.synchronize()
 
     def step_resident(i):

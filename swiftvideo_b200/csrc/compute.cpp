@@ -514,8 +514,16 @@ ComputeContext runComputeKernel(const ComputeContext& ctxIn, const std::vector<c
     for (auto& b : keep) args.push_back(&b->mem);
     check(d.cuLaunchKernel(prog.function, W / bx, H / by, 1, bx, by, 1, 0, ctx.ctx->compute, args.data(), nullptr), "cuLaunchKernel");
     noteKernelLaunch();
+    markWritten(ctx, target);
     // `keep` may drop its temporaries now: release() orders every stream behind the launch before reuse.
     return ctx;
+}
+
+void markWritten(const ComputeContext& ctx, const PictureSample& target) {  // caller holds a CtxGuard
+    for (const auto& t : target.imgBuffer.computeTextures) {
+        if (!t->ready) t->ready = std::make_shared<Event>(ctx.ctx);
+        check(drv().cuEventRecord(t->ready->e, ctx.ctx->compute), "cuEventRecord");
+    }
 }
 
 ImageUniforms makeImageUniforms(const PictureSample& image, const PictureSample& target) {  // compute.swift:149-161

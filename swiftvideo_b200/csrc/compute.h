@@ -224,6 +224,9 @@ ImageUniforms makeImageUniforms(const PictureSample& image, const PictureSample&
 ComputeContext applyComputeImage(const ComputeContext& ctx, const PictureSample& image, const PictureSample& target,
                                  ComputeKernel kernel);
 
+// After queueing a kernel that writes `target` on the compute stream: later consumers on other streams
+// (downloads) order themselves behind it through the textures' `ready` events.
+void markWritten(const ComputeContext& ctx, const PictureSample& target);
 unsigned long long kernelLaunchCount();  // launches of our kernels issued by this process
 void noteKernelLaunch();
 

@@ -1,18 +1,22 @@
 // kernels_tiled.cuh -- svb_mix_tiled: the fused compositor's fast path.
 //
-// A CTA owns a 128x32 luma tile of one output frame (tiles of every frame of the batch are dealt round-robin
-// to a grid sized to the SM count).  The running picture of the tile lives in registers as packed bytes
-// (a thread owns 4 columns x 4 rows of luma and the 2x2 chroma texels under them) and is re-quantised to
+// A CTA owns 128x32 luma tiles of the output frames of a batch (tiles are numbered column-major inside a
+// frame and every CTA of a grid sized to the SM count takes one contiguous run of them, so that it walks down
+// a 128-pixel column strip).  The running picture of a tile lives in registers -- a thread owns 4 columns x 4
+// rows of luma and the 2x2 chroma texels under them, held as integer-valued floats -- and is re-quantised to
 // 8 bits after every layer, so the bytes equal the reference's clear-then-fold over an 8-bit target
 // (mix.video.swift:113-125).  Layers whose rectangle misses the tile are skipped.
 //
-// Separable layers (no rotation: x outputs depend on x only, y outputs on y only -- the planner proves it
-// from the uniforms) take the table path: 128 threads evaluate the reference's per-pixel coordinate chain
-// (kernels.cl.swift:70-78 + the OpenCL 1.2 linear sampler) once per COLUMN and 32 once per ROW, bit-exactly,
-// into shared memory; the source footprint of the tile is staged by one TMA 2-D tensor copy per plane
-// (cp.async.bulk.tensor, mbarrier completion) and every pixel then costs four byte taps, the bilinear
-// sum and the blend.  Everything else (rotated layers, BGRA/RGBA sources, tiles straddling a layer edge)
-// runs the generic per-pixel evaluator of svb_device.cuh for that layer on that tile.
+// Separable YUV layers (no rotation: x outputs depend on x only, y outputs on y only -- the planner proves it
+// from the uniforms) take the table path.  The reference's per-pixel coordinate chain (kernels.cl.swift:70-78
+// followed by the OpenCL 1.2 linear sampler's i0/i1/frac) is evaluated bit-exactly once per COLUMN of the
+// strip and once per ROW of the tile into shared memory, for all layers at once.  For a tile that lies wholly
+// inside the layer's picture the source footprint is staged by one TMA 2-D tensor copy per plane
+// (cp.async.bulk.tensor + mbarrier) and every pixel then costs: four byte taps from shared memory, the UNORM8
+// reads, the bilinear sum, the blend and the re-quantisation -- all as packed fp32x2 instructions (FMUL2 /
+// FADD2 / FFMA2: two pixels per issue slot, each lane rounded separately, so nothing is contracted or
+// reassociated).  Everything else (rotated layers, BGRA/RGBA sources, tiles straddling a layer edge, footprints
+// too large to stage) runs the generic per-pixel evaluator of svb_device.cuh for that layer on that tile.
 #pragma once
 #include "svb_device.cuh"
 
@@ -21,7 +25,7 @@
 namespace svb {
 
 struct __align__(16) Ent {
-    float a;  // fractional weight of the i1 tap
+    float a;     // fractional weight of the i1 tap
     int i0, i1;  // clamped source indices (plane coordinates)
     int ok;      // bit0 border in [0,1], bit1 tx in [0,1], bit2 uv in [0,1]
 };
@@ -56,6 +60,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
 __device__ __forceinline__ void tmap_acquire(const void* tmap) {
     asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmap) : "memory");
 }
+// The box origin must be 16-byte aligned along the row (x * element size); y is free.
 __device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int x, int y, uint64_t* bar) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
@@ -96,25 +101,173 @@ __device__ __forceinline__ Ent axis_entry(const Axis& c, int n) {
     return e;
 }
 
-__device__ __forceinline__ unsigned get8(unsigned w, int k) { return (w >> (8 * k)) & 0xffu; }
-__device__ __forceinline__ unsigned put8(unsigned w, int k, unsigned v) { return (w & ~(0xffu << (8 * k))) | (v << (8 * k)); }
+// ---- packed fp32x2 (sm_100): two independent IEEE operations per instruction, each rounded on its own --------
+// PK=false spells the same operations as two scalar instructions (identical results; kept for A/B timing:
+// SVB_FP32X2=0 in the environment of the host selects it).
+template <bool PK> __device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    return PK ? __fmul2_rn(a, b) : make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y));
+}
+// ptxas 12.9 contracts  mul.rn.f32x2 + add.rn.f32x2  into FFMA2 even under -fmad=false (it does not for the scalar
+// .rn forms), which would round once where the reference rounds twice.  The packed add is therefore issued as
+// fma(a, ONE, b) with ONE == 1.0f arriving as a kernel argument: bit-identical to a + b (a*1 is exact), one
+// instruction like FADD2, and opaque to the contraction because the multiplicand is not a compile-time constant.
+template <bool PK> __device__ __forceinline__ float2 add2(float2 a, float2 b, float2 one) {
+    return PK ? __ffma2_rn(a, one, b) : make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y));
+}
+template <bool PK> __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    return PK ? __ffma2_rn(a, b, c) : make_float2(__fmaf_rn(a.x, b.x, c.x), __fmaf_rn(a.y, b.y, c.y));
+}
+__device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
+// UNORM8 read of two integer-valued floats (same identity as unorm_f)
+template <bool PK> __device__ __forceinline__ float2 unorm2(float2 c) { return fma2<PK>(c, splat(SVB_K1), mul2<PK>(c, splat(SVB_K2))); }
+__device__ __forceinline__ float2 bytes2(unsigned b0, unsigned b1) { return make_float2(__uint2float_rn(b0), __uint2float_rn(b1)); }
+// UNORM8 write of two values, kept as integer-valued floats: rint(clamp(v*255, 0, 255)).  Adding 2^23 rounds to
+// the nearest integer, ties to even, exactly like rint; without CLAMP the caller guarantees 0 <= v*255 < 255.5.
+template <bool CLAMP, bool PK>
+__device__ __forceinline__ float2 quant2(float2 v, float2 one) {
+    float2 x = mul2<PK>(v, splat(255.f));
+    if (CLAMP) {
+        x.x = fminf(fmaxf(x.x, 0.f), 255.f);
+        x.y = fminf(fmaxf(x.y, 0.f), 255.f);
+    }
+    return add2<PK>(add2<PK>(x, splat(8388608.f), one), splat(-8388608.f), one);
+}
+template <bool PK>
+__device__ __forceinline__ float2 bilin2(float2 w00, float2 w10, float2 w01, float2 w11, float2 t00, float2 t10, float2 t01, float2 t11,
+                                         float2 one) {
+    return add2<PK>(add2<PK>(add2<PK>(mul2<PK>(w00, t00), mul2<PK>(w10, t10), one), mul2<PK>(w01, t01), one), mul2<PK>(w11, t11), one);
+}
 
-struct TiledSmem {
+struct TiledSmem {  // fixed part; the per-layer tables follow in dynamic shared memory
     alignas(128) uint8_t boxY[SVB_BOX_Y_BYTES];
     alignas(128) uint8_t boxC[SVB_BOX_C_BYTES];
-    Ent colY[SVB_TILE_W];
-    Ent colC[SVB_TILE_W / 2];
-    Ent rowY[SVB_TILE_H];
-    Ent rowC[SVB_TILE_H / 2];
     alignas(8) uint64_t bar;
 };
+#define SVB_TABLE_ENTS (SVB_TILE_W + SVB_TILE_W / 2 + SVB_TILE_H + SVB_TILE_H / 2)  // per layer: colY, colC, rowY, rowC
+#define SVB_TILED_SMEM_FIXED ((sizeof(svb::TiledSmem) + 127) / 128 * 128)
+#define SVB_TILED_SMEM_PER_LAYER (SVB_TABLE_ENTS * sizeof(svb::Ent))
+
+// One separable YUV layer over a tile that lies wholly inside the picture, taps staged in shared memory.
+//   Yi / Ui / Vi: the running picture as integer-valued floats; pairs hold two horizontally adjacent samples.
+template <bool UNIT, bool CLAMP, bool PK>
+__device__ __forceinline__ void fast_layer(const TiledSmem& sm, const Ent* __restrict__ colY, const Ent* __restrict__ colC,
+                                           const Ent* __restrict__ rowY, const Ent* __restrict__ rowC, int lane, int warp, int iy0,
+                                           int jy0, int ic0, int jc0, int pitchY, int pitchC, int stepC, int voff, float alpha, float onef,
+                                           float2 (&Yi)[4][2], float2 (&Ui)[2], float2 (&Vi)[2]) {
+    const float2 AL = splat(alpha), NAL = splat(sub(1.f, alpha)), ONE = splat(onef);
+    int o0[4], o1[4];
+    float2 A[2], NA[2];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const Ent e0 = colY[4 * lane + 2 * p], e1 = colY[4 * lane + 2 * p + 1];
+        o0[2 * p] = e0.i0 - iy0, o1[2 * p] = e0.i1 - iy0, o0[2 * p + 1] = e1.i0 - iy0, o1[2 * p + 1] = e1.i1 - iy0;
+        A[p] = make_float2(e0.a, e1.a);
+        NA[p] = make_float2(sub(1.f, e0.a), sub(1.f, e1.a));
+    }
+    const Ent c0 = colC[2 * lane], c1 = colC[2 * lane + 1];
+    const int oc00 = (c0.i0 - ic0) * stepC, oc01 = (c0.i1 - ic0) * stepC, oc10 = (c1.i0 - ic0) * stepC, oc11 = (c1.i1 - ic0) * stepC;
+    const float2 AC = make_float2(c0.a, c1.a), NAC = make_float2(sub(1.f, c0.a), sub(1.f, c1.a));
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const Ent ry = rowY[4 * warp + r];
+        const int r0 = (ry.i0 - jy0) * pitchY, r1 = (ry.i1 - jy0) * pitchY;
+        const float2 B = splat(ry.a), NB = splat(sub(1.f, ry.a));
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const int a0 = o0[2 * p], a1 = o1[2 * p], b0 = o0[2 * p + 1], b1 = o1[2 * p + 1];
+            const float2 t00 = unorm2<PK>(bytes2(sm.boxY[r0 + a0], sm.boxY[r0 + b0]));
+            const float2 t10 = unorm2<PK>(bytes2(sm.boxY[r0 + a1], sm.boxY[r0 + b1]));
+            const float2 t01 = unorm2<PK>(bytes2(sm.boxY[r1 + a0], sm.boxY[r1 + b0]));
+            const float2 t11 = unorm2<PK>(bytes2(sm.boxY[r1 + a1], sm.boxY[r1 + b1]));
+            const float2 v = bilin2<PK>(mul2<PK>(NA[p], NB), mul2<PK>(A[p], NB), mul2<PK>(NA[p], B), mul2<PK>(A[p], B), t00, t10, t01, t11, ONE);
+            const float2 res = UNIT ? v : add2<PK>(mul2<PK>(unorm2<PK>(Yi[r][p]), NAL), mul2<PK>(v, AL), ONE);
+            Yi[r][p] = quant2<CLAMP, PK>(res, ONE);
+        }
+        if ((r & 1) == 0) {
+            const int k = r >> 1;
+            const Ent rc = rowC[2 * warp + k];
+            const int q0 = (rc.i0 - jc0) * pitchC, q1 = (rc.i1 - jc0) * pitchC;
+            const float2 BC = splat(rc.a), NBC = splat(sub(1.f, rc.a));
+            const float2 w00 = mul2<PK>(NAC, NBC), w10 = mul2<PK>(AC, NBC), w01 = mul2<PK>(NAC, BC), w11 = mul2<PK>(AC, BC);
+            const uint8_t* bu = sm.boxC;
+            const uint8_t* bv = sm.boxC + voff;
+            const float2 u = bilin2<PK>(w00, w10, w01, w11, unorm2<PK>(bytes2(bu[q0 + oc00], bu[q0 + oc10])), unorm2<PK>(bytes2(bu[q0 + oc01], bu[q0 + oc11])),
+                                    unorm2<PK>(bytes2(bu[q1 + oc00], bu[q1 + oc10])), unorm2<PK>(bytes2(bu[q1 + oc01], bu[q1 + oc11])), ONE);
+            const float2 v = bilin2<PK>(w00, w10, w01, w11, unorm2<PK>(bytes2(bv[q0 + oc00], bv[q0 + oc10])), unorm2<PK>(bytes2(bv[q0 + oc01], bv[q0 + oc11])),
+                                    unorm2<PK>(bytes2(bv[q1 + oc00], bv[q1 + oc10])), unorm2<PK>(bytes2(bv[q1 + oc01], bv[q1 + oc11])), ONE);
+            Ui[k] = quant2<CLAMP, PK>(UNIT ? u : add2<PK>(mul2<PK>(unorm2<PK>(Ui[k]), NAL), mul2<PK>(u, AL), ONE), ONE);
+            Vi[k] = quant2<CLAMP, PK>(UNIT ? v : add2<PK>(mul2<PK>(unorm2<PK>(Vi[k]), NAL), mul2<PK>(v, AL), ONE), ONE);
+        }
+    }
+}
+
+// Same layer, taps read straight from the planes in global memory (footprint too large to stage).
+__device__ __forceinline__ void slow_table_layer(const SvbLayerDesc* __restrict__ L, const Ent* __restrict__ colY, const Ent* __restrict__ colC,
+                                                 const Ent* __restrict__ rowY, const Ent* __restrict__ rowC, int lane, int warp, float alpha,
+                                                 float2 (&Yi)[4][2], float2 (&Ui)[2], float2 (&Vi)[2]) {
+    const uint8_t* __restrict__ pY = (const uint8_t*)L->plane[0];
+    const uint8_t* __restrict__ pU = (const uint8_t*)L->plane[1];
+    const bool nv12 = L->format == SVB_NV12;
+    const uint8_t* __restrict__ pV = nv12 ? pU + 1 : (const uint8_t*)L->plane[2];
+    const int pitchY = L->stride[0], pitchC = L->stride[1], stepC = nv12 ? 2 : 1;
+    const float nalpha = sub(1.f, alpha);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const Ent ry = rowY[4 * warp + r];
+        const float b = ry.a, nb = sub(1.f, b);
+        const uint8_t* q0 = pY + (size_t)ry.i0 * pitchY;
+        const uint8_t* q1 = pY + (size_t)ry.i1 * pitchY;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const Ent cy = colY[4 * lane + c];
+            const float a = cy.a, na = sub(1.f, a);
+            const float v = add(add(add(mul(mul(na, nb), unorm(__ldg(q0 + cy.i0))), mul(mul(a, nb), unorm(__ldg(q0 + cy.i1)))),
+                                    mul(mul(na, b), unorm(__ldg(q1 + cy.i0)))),
+                                mul(mul(a, b), unorm(__ldg(q1 + cy.i1))));
+            float& dst = (c & 1) ? Yi[r][c >> 1].y : Yi[r][c >> 1].x;
+            dst = (float)rte8(add(mul(unorm_f(dst), nalpha), mul(v, alpha)));
+        }
+        if ((r & 1) == 0) {
+            const int k = r >> 1;
+            const Ent rc = rowC[2 * warp + k];
+            const float bb = rc.a, nbb = sub(1.f, bb);
+            const size_t z0 = (size_t)rc.i0 * pitchC, z1 = (size_t)rc.i1 * pitchC;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const Ent cc = colC[2 * lane + c];
+                const float a = cc.a, na = sub(1.f, a);
+                const float w00 = mul(na, nbb), w10 = mul(a, nbb), w01 = mul(na, bb), w11 = mul(a, bb);
+                const int e0 = cc.i0 * stepC, e1 = cc.i1 * stepC;
+                const float vu = add(add(add(mul(w00, unorm(__ldg(pU + z0 + e0))), mul(w10, unorm(__ldg(pU + z0 + e1)))), mul(w01, unorm(__ldg(pU + z1 + e0)))),
+                                     mul(w11, unorm(__ldg(pU + z1 + e1))));
+                const float vv = add(add(add(mul(w00, unorm(__ldg(pV + z0 + e0))), mul(w10, unorm(__ldg(pV + z0 + e1)))), mul(w01, unorm(__ldg(pV + z1 + e0)))),
+                                     mul(w11, unorm(__ldg(pV + z1 + e1))));
+                float& du = c ? Ui[k].y : Ui[k].x;
+                float& dv = c ? Vi[k].y : Vi[k].x;
+                du = (float)rte8(add(mul(unorm_f(du), nalpha), mul(vu, alpha)));
+                dv = (float)rte8(add(mul(unorm_f(dv), nalpha), mul(vv, alpha)));
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ unsigned pack4(float2 a, float2 b) {  // four integer-valued floats in 0..255 -> bytes
+    return __float2uint_rn(a.x) | (__float2uint_rn(a.y) << 8) | (__float2uint_rn(b.x) << 16) | (__float2uint_rn(b.y) << 24);
+}
 
 }  // namespace svb
 
 extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, 2)
-    svb_mix_tiled(const SvbFrameDesc* __restrict__ frames, int nframes, int total_tiles) {
+    svb_mix_tiled(const SvbFrameDesc* __restrict__ frames, int nframes, int total_tiles, int max_layers, float one) {
     using namespace svb;
-    __shared__ TiledSmem sm;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TiledSmem& sm = *reinterpret_cast<TiledSmem*>(smem_raw);
+    Ent* const tables = reinterpret_cast<Ent*>(smem_raw + SVB_TILED_SMEM_FIXED);
+    Ent* const colYs = tables;                                         // [max_layers][128]
+    Ent* const colCs = colYs + (size_t)max_layers * SVB_TILE_W;        // [max_layers][64]
+    Ent* const rowYs = colCs + (size_t)max_layers * (SVB_TILE_W / 2);  // [max_layers][32]
+    Ent* const rowCs = rowYs + (size_t)max_layers * SVB_TILE_H;        // [max_layers][16]
+
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     unsigned phase = 0;
     if (t == 0) {
@@ -123,13 +276,17 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, 2)
     }
     __syncthreads();
 
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int f = 0;
+    // a contiguous run of tiles per CTA; tiles are column-major inside a frame, so a run walks down a column strip
+    const int tile_begin = (int)((long long)total_tiles * blockIdx.x / gridDim.x);
+    const int tile_end = (int)((long long)total_tiles * (blockIdx.x + 1) / gridDim.x);
+    int f = 0, strip_f = -1, strip_x0 = -1;
+
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
         while (f + 1 < nframes && frames[f + 1].first_tile <= tile) ++f;
         const SvbFrameDesc* __restrict__ F = frames + f;
         const int local = tile - F->first_tile;
-        const int W = F->width, H = F->height;
-        const int x0 = (local % F->tiles_x) * SVB_TILE_W, y0 = (local / F->tiles_x) * SVB_TILE_H;
+        const int W = F->width, H = F->height, nl = F->nlayers;
+        const int x0 = (local / F->tiles_y) * SVB_TILE_W, y0 = (local % F->tiles_y) * SVB_TILE_H;
         const int xt = x0 + 4 * lane, yt = y0 + 4 * warp;  // this thread's 4x4 block
         const bool live = xt < W && yt < H;                 // W % 4 == 0 and H even are planner preconditions
         const bool nv12 = F->format == SVB_NV12;
@@ -139,63 +296,81 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, 2)
         uint8_t* const oV = (uint8_t*)F->out_plane[2];
         const int sY = F->out_stride[0], sU = F->out_stride[1], sV = F->out_stride[2];
 
-        // running picture: Yb[r] = 4 luma bytes of row yt+r; Cb[k] = (u0,v0,u1,v1) of chroma row (yt/2)+k
-        unsigned Yb[4] = {0u, 0u, 0u, 0u}, Cb[2] = {0x80808080u, 0x80808080u};  // img_clear_*: Y=0, C=0.5->128
+        // ---- tables for every separable YUV layer that touches the tile: rows always, columns on a new strip ----
+        {
+            const bool new_strip = f != strip_f || x0 != strip_x0;
+            const int per = new_strip ? SVB_TILE_W + SVB_TILE_H : SVB_TILE_H;
+            for (int e = t; e < nl * per; e += SVB_TILED_THREADS) {
+                const int l = e / per, k = e - l * per;
+                const SvbLayerDesc* __restrict__ L = &F->layers[l];
+                if (!(L->flags & SVB_LAYER_SEPARABLE) || (L->format != SVB_NV12 && L->format != SVB_Y420P)) continue;
+                if (new_strip && k < SVB_TILE_W) {
+                    if (L->rect[0] >= x0 + SVB_TILE_W || L->rect[2] <= x0) continue;
+                    const Axis c = axis_chain(&L->u, 0, x0 + k, fW);
+                    colYs[l * SVB_TILE_W + k] = axis_entry(c, L->width);
+                    if ((k & 1) == 0) colCs[l * (SVB_TILE_W / 2) + (k >> 1)] = axis_entry(c, L->width / 2);
+                } else {
+                    const int r = new_strip ? k - SVB_TILE_W : k;
+                    if (L->rect[1] >= y0 + SVB_TILE_H || L->rect[3] <= y0) continue;
+                    const Axis c = axis_chain(&L->u, 1, y0 + r, fH);
+                    rowYs[l * SVB_TILE_H + r] = axis_entry(c, L->height);
+                    if ((r & 1) == 0) rowCs[l * (SVB_TILE_H / 2) + (r >> 1)] = axis_entry(c, L->height / 2);
+                }
+            }
+            strip_f = f, strip_x0 = x0;
+        }
+
+        // ---- running picture: integer-valued floats ------------------------------------------------------------
+        float2 Yi[4][2], Ui[2], Vi[2];  // Yi[r][p] = columns (2p, 2p+1) of row yt+r; Ui/Vi[k] = the two chroma texels of chroma row yt/2+k
+#pragma unroll
+        for (int r = 0; r < 4; ++r) Yi[r][0] = Yi[r][1] = splat(0.f);  // img_clear_*: Y = 0, chroma = 0.5 -> 128
+        Ui[0] = Ui[1] = Vi[0] = Vi[1] = splat(128.f);
         if ((F->flags & SVB_FRAME_LOAD_CUR) && live) {
 #pragma unroll
             for (int r = 0; r < 4; ++r)
-                if (yt + r < H) Yb[r] = *(const unsigned*)(oY + (size_t)(yt + r) * sY + xt);
+                if (yt + r < H) {
+                    const unsigned w = *(const unsigned*)(oY + (size_t)(yt + r) * sY + xt);
+                    Yi[r][0] = bytes2(w & 0xff, (w >> 8) & 0xff), Yi[r][1] = bytes2((w >> 16) & 0xff, w >> 24);
+                }
 #pragma unroll
             for (int k = 0; k < 2; ++k)
                 if (yt + 2 * k < H) {
                     if (nv12) {
-                        Cb[k] = *(const unsigned*)(oU + (size_t)((yt >> 1) + k) * sU + xt);
+                        const unsigned w = *(const unsigned*)(oU + (size_t)((yt >> 1) + k) * sU + xt);
+                        Ui[k] = bytes2(w & 0xff, (w >> 16) & 0xff), Vi[k] = bytes2((w >> 8) & 0xff, w >> 24);
                     } else {
                         const uchar2 u = *(const uchar2*)(oU + (size_t)((yt >> 1) + k) * sU + (xt >> 1));
                         const uchar2 v = *(const uchar2*)(oV + (size_t)((yt >> 1) + k) * sV + (xt >> 1));
-                        Cb[k] = u.x | (v.x << 8) | (u.y << 16) | (v.y << 24);
+                        Ui[k] = bytes2(u.x, u.y), Vi[k] = bytes2(v.x, v.y);
                     }
                 }
         }
+        __syncthreads();  // tables visible
 
-        for (int l = 0; l < F->nlayers; ++l) {
+        for (int l = 0; l < nl; ++l) {
             const SvbLayerDesc* __restrict__ L = &F->layers[l];
             if (L->rect[0] >= x0 + SVB_TILE_W || L->rect[2] <= x0 || L->rect[1] >= y0 + SVB_TILE_H || L->rect[3] <= y0) continue;
             const SvbUniforms* __restrict__ U = &L->u;
             const int fmt = L->format, lflags = L->flags;
-            const bool yuv = fmt == SVB_NV12 || fmt == SVB_Y420P;
+            const Ent* colY = colYs + l * SVB_TILE_W;
+            const Ent* colC = colCs + l * (SVB_TILE_W / 2);
+            const Ent* rowY = rowYs + l * SVB_TILE_H;
+            const Ent* rowC = rowCs + l * (SVB_TILE_H / 2);
             bool full = false;
-            if ((lflags & SVB_LAYER_SEPARABLE) && yuv) {
-                // ---- tables: one column / row of the reference's coordinate chain per thread ----------
-                bool mine_ok = true;
-                if (t < SVB_TILE_W) {
-                    const Axis c = axis_chain(U, 0, x0 + t, fW);
-                    const Ent e = axis_entry(c, L->width);
-                    sm.colY[t] = e;
-                    if ((t & 1) == 0) sm.colC[t >> 1] = axis_entry(c, L->width / 2);
-                    mine_ok = e.ok == 7 || x0 + t >= W;
-                } else if (t < SVB_TILE_W + SVB_TILE_H) {
-                    const int r = t - SVB_TILE_W;
-                    const Axis c = axis_chain(U, 1, y0 + r, fH);
-                    const Ent e = axis_entry(c, L->height);
-                    sm.rowY[r] = e;
-                    if ((r & 1) == 0) sm.rowC[r >> 1] = axis_entry(c, L->height / 2);
-                    mine_ok = e.ok == 7 || y0 + r >= H;
-                }
-                full = __syncthreads_and(mine_ok);  // every pixel of the tile is inside the picture
-            }
+            const int lastc = min(SVB_TILE_W, W - x0) - 1, lastr = min(SVB_TILE_H, H - y0) - 1;
+            if ((lflags & SVB_LAYER_SEPARABLE) && (fmt == SVB_NV12 || fmt == SVB_Y420P))
+                // border, tx and uv are monotone along each axis: both ends inside [0,1] means everything between is
+                full = colY[0].ok == 7 && colY[lastc].ok == 7 && rowY[0].ok == 7 && rowY[lastr].ok == 7;
             if (full) {
-                // ---- source footprint of the tile (indices are monotone in x and y) ---------------------
-                const int lastc = min(SVB_TILE_W, W - x0) - 1, lastr = min(SVB_TILE_H, H - y0) - 1;
-                const int iy0 = min(sm.colY[0].i0, sm.colY[lastc].i0), iy1 = max(sm.colY[0].i1, sm.colY[lastc].i1);
-                const int jy0 = min(sm.rowY[0].i0, sm.rowY[lastr].i0), jy1 = max(sm.rowY[0].i1, sm.rowY[lastr].i1);
+                // source footprint of the tile (indices are monotone too); x origins rounded down to 16 bytes for TMA
                 const int lc = lastc >> 1, lr = lastr >> 1;
-                const int ic0 = min(sm.colC[0].i0, sm.colC[lc].i0), ic1 = max(sm.colC[0].i1, sm.colC[lc].i1);
-                const int jc0 = min(sm.rowC[0].i0, sm.rowC[lr].i0), jc1 = max(sm.rowC[0].i1, sm.rowC[lr].i1);
-                const bool staged = (lflags & SVB_LAYER_STAGED) && iy1 - iy0 < L->box_w && jy1 - jy0 < L->box_h &&
-                                    ic1 - ic0 < L->box_cw && jc1 - jc0 < L->box_ch;
-                const uint8_t *pY, *pU, *pV;  // tap(i,j) = p[j*pitch + i*step]
-                int pitchY, pitchC, stepC;
+                const int iy0 = min(colY[0].i0, colY[lastc].i0) & ~15, iy1 = max(colY[0].i1, colY[lastc].i1);
+                const int jy0 = min(rowY[0].i0, rowY[lastr].i0), jy1 = max(rowY[0].i1, rowY[lastr].i1);
+                const int ic0 = min(colC[0].i0, colC[lc].i0) & (fmt == SVB_NV12 ? ~7 : ~15), ic1 = max(colC[0].i1, colC[lc].i1);
+                const int jc0 = min(rowC[0].i0, rowC[lr].i0), jc1 = max(rowC[0].i1, rowC[lr].i1);
+                const bool staged = (lflags & SVB_LAYER_STAGED) && iy1 - iy0 < L->box_w && jy1 - jy0 < L->box_h && ic1 - ic0 < L->box_cw &&
+                                    jc1 - jc0 < L->box_ch;
+                const float alpha = U->opacity;
                 if (staged) {
                     const int cbytes = fmt == SVB_NV12 ? L->box_cw * L->box_ch * 2 : L->box_cw * L->box_ch;
                     if (t == 0) {
@@ -207,112 +382,66 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, 2)
                         tma_load_2d(sm.boxC, L->tmap[1], ic0, jc0, &sm.bar);
                         if (fmt == SVB_Y420P) tma_load_2d(sm.boxC + SVB_BOX_C_BYTES / 2, L->tmap[2], ic0, jc0, &sm.bar);
                     }
-                    pitchY = L->box_w;
-                    pY = sm.boxY - ((size_t)jy0 * pitchY + iy0);
-                    if (fmt == SVB_NV12) {
-                        pitchC = L->box_cw * 2, stepC = 2;
-                        pU = sm.boxC - ((size_t)jc0 * pitchC + ic0 * 2);
-                        pV = pU + 1;
-                    } else {
-                        pitchC = L->box_cw, stepC = 1;
-                        pU = sm.boxC - ((size_t)jc0 * pitchC + ic0);
-                        pV = pU + SVB_BOX_C_BYTES / 2;
-                    }
+                    const int pitchC = fmt == SVB_NV12 ? L->box_cw * 2 : L->box_cw, stepC = fmt == SVB_NV12 ? 2 : 1;
+                    const int voff = fmt == SVB_NV12 ? 1 : SVB_BOX_C_BYTES / 2;
                     mbar_wait(&sm.bar, phase);
                     phase ^= 1;
-                } else {
-                    pitchY = L->stride[0];
-                    pY = (const uint8_t*)L->plane[0];
-                    pitchC = L->stride[1];
-                    pU = (const uint8_t*)L->plane[1];
-                    if (fmt == SVB_NV12) {
-                        stepC = 2, pV = pU + 1;
-                    } else {
-                        stepC = 1, pV = (const uint8_t*)L->plane[2];  // stride[2] == stride[1] is a planner precondition
-                    }
-                }
-                // ---- pixels ----------------------------------------------------------------------------
-                if (live) {
-                    const float alpha = U->opacity, nalpha = sub(1.f, alpha);
-                    Ent cy[4];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) cy[c] = sm.colY[4 * lane + c];
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const Ent ry = sm.rowY[4 * warp + r];
-                        const float b = ry.a, nb = sub(1.f, b);
-                        const uint8_t* q0 = pY + (size_t)ry.i0 * pitchY;
-                        const uint8_t* q1 = pY + (size_t)ry.i1 * pitchY;
-                        unsigned out = 0;
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const float a = cy[c].a, na = sub(1.f, a);
-                            const float v = add(add(add(mul(mul(na, nb), unorm(q0[cy[c].i0])), mul(mul(a, nb), unorm(q0[cy[c].i1]))),
-                                                    mul(mul(na, b), unorm(q1[cy[c].i0]))),
-                                                mul(mul(a, b), unorm(q1[cy[c].i1])));
-                            const float res = add(mul(unorm(get8(Yb[r], c)), nalpha), mul(v, alpha));
-                            out |= rte8(res) << (8 * c);
+#define SVB_FAST(UNIT, CLAMP, PK) \
+    fast_layer<UNIT, CLAMP, PK>(sm, colY, colC, rowY, rowC, lane, warp, iy0, jy0, ic0, jc0, L->box_w, pitchC, stepC, voff, alpha, one, Yi, Ui, Vi)
+                    if (live) {
+                        if (F->flags & SVB_FRAME_SCALAR_FP) {
+                            if (lflags & SVB_LAYER_UNIT_OPACITY) SVB_FAST(true, false, false);
+                            else if (lflags & SVB_LAYER_OPACITY_01) SVB_FAST(false, false, false);
+                            else SVB_FAST(false, true, false);
+                        } else {
+                            if (lflags & SVB_LAYER_UNIT_OPACITY) SVB_FAST(true, false, true);
+                            else if (lflags & SVB_LAYER_OPACITY_01) SVB_FAST(false, false, true);
+                            else SVB_FAST(false, true, true);
                         }
-                        Yb[r] = out;
                     }
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const Ent rc = sm.rowC[2 * warp + k];
-                        const float b = rc.a, nb = sub(1.f, b);
-                        const size_t o0 = (size_t)rc.i0 * pitchC, o1 = (size_t)rc.i1 * pitchC;
-                        unsigned out = 0;
-#pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            const Ent cc = sm.colC[2 * lane + c];
-                            const float a = cc.a, na = sub(1.f, a);
-                            const float w00 = mul(na, nb), w10 = mul(a, nb), w01 = mul(na, b), w11 = mul(a, b);
-                            const int e0 = cc.i0 * stepC, e1 = cc.i1 * stepC;
-                            const float vu = add(add(add(mul(w00, unorm(pU[o0 + e0])), mul(w10, unorm(pU[o0 + e1]))), mul(w01, unorm(pU[o1 + e0]))),
-                                                 mul(w11, unorm(pU[o1 + e1])));
-                            const float vv = add(add(add(mul(w00, unorm(pV[o0 + e0])), mul(w10, unorm(pV[o0 + e1]))), mul(w01, unorm(pV[o1 + e0]))),
-                                                 mul(w11, unorm(pV[o1 + e1])));
-                            const float ru = add(mul(unorm(get8(Cb[k], 2 * c)), nalpha), mul(vu, alpha));
-                            const float rv = add(mul(unorm(get8(Cb[k], 2 * c + 1)), nalpha), mul(vv, alpha));
-                            out |= (rte8(ru) << (16 * c)) | (rte8(rv) << (16 * c + 8));
-                        }
-                        Cb[k] = out;
-                    }
+#undef SVB_FAST
+                    __syncthreads();  // the boxes are free for the next layer
+                } else if (live) {
+                    slow_table_layer(L, colY, colC, rowY, rowC, lane, warp, alpha, Yi, Ui, Vi);
                 }
             } else if (live) {
-                // ---- generic per-pixel evaluation of this layer on this thread's 4x4 block --------------
+                // ---- generic per-pixel evaluation of this layer on this thread's 4x4 block ----------------------
                 const Src s = layer_src(L);
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         const bool chroma = ((r | c) & 1) == 0;
-                        const int k = r >> 1, cc = c >> 1;
+                        const int k = r >> 1;
+                        float& py = (c & 1) ? Yi[r][c >> 1].y : Yi[r][c >> 1].x;
+                        float& pu = (c >> 1) ? Ui[k].y : Ui[k].x;
+                        float& pv = (c >> 1) ? Vi[k].y : Vi[k].x;
                         float oy, ou, ov;
-                        const float cu = chroma ? unorm(get8(Cb[k], 2 * cc)) : 0.f, cv = chroma ? unorm(get8(Cb[k], 2 * cc + 1)) : 0.f;
-                        if (yt + r < H && eval_pixel(U, s, xt + c, yt + r, fW, fH, chroma, unorm(get8(Yb[r], c)), cu, cv, oy, ou, ov)) {
-                            Yb[r] = put8(Yb[r], c, rte8(oy));
-                            if (chroma) Cb[k] = put8(put8(Cb[k], 2 * cc, rte8(ou)), 2 * cc + 1, rte8(ov));
+                        if (yt + r < H && eval_pixel(U, s, xt + c, yt + r, fW, fH, chroma, unorm_f(py), chroma ? unorm_f(pu) : 0.f,
+                                                     chroma ? unorm_f(pv) : 0.f, oy, ou, ov)) {
+                            py = (float)rte8(oy);
+                            if (chroma) pu = (float)rte8(ou), pv = (float)rte8(ov);
                         }
                     }
                 }
             }
-            __syncthreads();  // tables and boxes are free for the next layer
         }
 
         if (live) {
 #pragma unroll
             for (int r = 0; r < 4; ++r)
-                if (yt + r < H) *(unsigned*)(oY + (size_t)(yt + r) * sY + xt) = Yb[r];
+                if (yt + r < H) *(unsigned*)(oY + (size_t)(yt + r) * sY + xt) = pack4(Yi[r][0], Yi[r][1]);
 #pragma unroll
             for (int k = 0; k < 2; ++k)
                 if (yt + 2 * k < H) {
                     if (nv12) {
-                        *(unsigned*)(oU + (size_t)((yt >> 1) + k) * sU + xt) = Cb[k];
+                        *(unsigned*)(oU + (size_t)((yt >> 1) + k) * sU + xt) = pack4(make_float2(Ui[k].x, Vi[k].x), make_float2(Ui[k].y, Vi[k].y));
                     } else {
-                        *(uchar2*)(oU + (size_t)((yt >> 1) + k) * sU + (xt >> 1)) = make_uchar2(get8(Cb[k], 0), get8(Cb[k], 2));
-                        *(uchar2*)(oV + (size_t)((yt >> 1) + k) * sV + (xt >> 1)) = make_uchar2(get8(Cb[k], 1), get8(Cb[k], 3));
+                        *(uchar2*)(oU + (size_t)((yt >> 1) + k) * sU + (xt >> 1)) = make_uchar2(__float2uint_rn(Ui[k].x), __float2uint_rn(Ui[k].y));
+                        *(uchar2*)(oV + (size_t)((yt >> 1) + k) * sV + (xt >> 1)) = make_uchar2(__float2uint_rn(Vi[k].x), __float2uint_rn(Vi[k].y));
                     }
                 }
         }
+        __syncthreads();  // row tables are rewritten by the next tile
     }
 }

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <array>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "cu_driver.h"
@@ -19,6 +20,8 @@ static const CuDriver& drv() {
 // ---- per-context state: descriptor ring + tensor-map cache ----------------------------------------------
 
 namespace {
+
+unsigned tiledSmemBytes(int maxLayers);
 
 constexpr int kSegments = 8;     // batches in flight before the host has to wait for the oldest
 constexpr int kSegFrames = 64;   // frame descriptors per batch
@@ -78,9 +81,18 @@ MixerShared& shared(const std::shared_ptr<InternalContext>& ic) {  // caller hol
         check(drv().cuMemAlloc(&s->dev, bytes), "cuMemAlloc");
         for (CUevent& e : s->ev) check(drv().cuEventCreate(&e, CU_EVENT_DISABLE_TIMING), "cuEventCreate");
         s->fTiled = ic->builtin("svb_mix_tiled");
+        check(drv().cuFuncSetAttribute(s->fTiled, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)tiledSmemBytes(SVB_MAX_LAYERS)),
+              "cuFuncSetAttribute(max dynamic shared memory)");
         s->fGeneric = ic->builtin("svb_mix_generic");
     }
     return *(MixerShared*)ic->mixerShared;
+}
+
+// dynamic shared memory of svb_mix_tiled: staged boxes + mbarrier (kernels_tiled.cuh: TiledSmem, padded to 128) and
+// 240 table entries of 16 bytes per layer
+unsigned tiledSmemBytes(int maxLayers) {
+    const unsigned fixed = (SVB_BOX_Y_BYTES + SVB_BOX_C_BYTES + 8 + 127) / 128 * 128;
+    return fixed + (unsigned)maxLayers * (SVB_TILE_W + SVB_TILE_W / 2 + SVB_TILE_H + SVB_TILE_H / 2) * 16u;
 }
 
 int svbFormat(PixelFormat f) {
@@ -175,10 +187,12 @@ FramePlan planFrame(const ComputeContext& ctx, const PictureSample& target, cons
         base.out_stride[i] = planes[i].stride;
     }
     base.width = W, base.height = H, base.format = tf;
+    static const bool scalarFp = std::getenv("SVB_FP32X2") && std::getenv("SVB_FP32X2")[0] == '0';  // A/B timing aid
+    if (scalarFp) base.flags |= SVB_FRAME_SCALAR_FP;
     base.tiles_x = (W + SVB_TILE_W - 1) / SVB_TILE_W;
     base.tiles_y = (H + SVB_TILE_H - 1) / SVB_TILE_H;
-    for (size_t i = 0; i < np; ++i)
-        if (planes[i].stride & 1) throw ComputeError(ErrorCode::badTarget, "target strides must be even");
+    // the generic kernel stores luma (and NV12 chroma) two bytes at a time
+    if ((planes[0].stride & 1) || (tf == SVB_NV12 && (planes[1].stride & 1))) throw ComputeError(ErrorCode::badTarget, "target strides must be even");
     plan.tiledOk = (W % 4 == 0) && (base.out_stride[0] % 4 == 0) && (base.out_plane[0] % 4 == 0) &&
                    (tf == SVB_NV12 ? (base.out_stride[1] % 4 == 0 && base.out_plane[1] % 4 == 0)
                                    : (base.out_plane[1] % 2 == 0 && base.out_plane[2] % 2 == 0));
@@ -211,7 +225,8 @@ FramePlan planFrame(const ComputeContext& ctx, const PictureSample& target, cons
         const float *T = u.transform, *X = u.textureTx, *B = u.borderMatrix;
         const bool finite = finite16(T) && finite16(X) && finite16(B) && std::isfinite(u.opacity);
         int flags = 0;
-        if (finite && T[1] == 0.f && T[4] == 0.f && T[8] == 0.f && T[9] == 0.f && T[12] == 0.f && T[13] == 0.f && B[1] == 0.f &&
+        static const bool noTables = std::getenv("SVB_NO_TABLES") != nullptr, noTma = std::getenv("SVB_NO_TMA") != nullptr;  // debugging aids
+        if (!noTables && finite && T[1] == 0.f && T[4] == 0.f && T[8] == 0.f && T[9] == 0.f && T[12] == 0.f && T[13] == 0.f && B[1] == 0.f &&
             B[4] == 0.f && X[1] == 0.f && X[4] == 0.f && (sf != SVB_Y420P || L.stride[1] == L.stride[2]))
             flags |= SVB_LAYER_SEPARABLE;
         if (u.opacity == 1.0f) flags |= SVB_LAYER_UNIT_OPACITY;
@@ -221,13 +236,15 @@ FramePlan planFrame(const ComputeContext& ctx, const PictureSample& target, cons
             // source texels per output pixel along each axis (double is plenty: the device re-checks the fit per tile)
             const double sx = std::fabs((double)L.width * X[0] * T[0] * 2.0 / W), sy = std::fabs((double)L.height * X[5] * T[5] * 2.0 / H);
             const int cw = L.width / 2, ch = L.height / 2;
-            int bw = roundUp((int)std::ceil(sx * (SVB_TILE_W - 1)) + 3, 16), bh = (int)std::ceil(sy * (SVB_TILE_H - 1)) + 3;
-            int bcw = roundUp((int)std::ceil(sx * 0.5 * (SVB_TILE_W - 2)) + 3, sf == SVB_NV12 ? 8 : 16);
+            // +15 bytes of slack: the kernel rounds the box's x origin down to a 16-byte boundary (a TMA requirement)
+            int bw = roundUp((int)std::ceil(sx * (SVB_TILE_W - 1)) + 3 + 15, 16), bh = (int)std::ceil(sy * (SVB_TILE_H - 1)) + 3;
+            int bcw = sf == SVB_NV12 ? roundUp((int)std::ceil(sx * 0.5 * (SVB_TILE_W - 2)) + 3 + 7, 8)
+                                     : roundUp((int)std::ceil(sx * 0.5 * (SVB_TILE_W - 2)) + 3 + 15, 16);
             int bch = (int)std::ceil(sy * 0.5 * (SVB_TILE_H - 2)) + 3;
             const int cbytes = bcw * bch * (sf == SVB_NV12 ? 2 : 1);
             const bool fits = std::isfinite(sx) && std::isfinite(sy) && bw <= 256 && bh <= 256 && bw * bh <= SVB_BOX_Y_BYTES &&
                               bcw <= 256 && bch <= 256 && cbytes <= (sf == SVB_NV12 ? SVB_BOX_C_BYTES : SVB_BOX_C_BYTES / 2);
-            if (fits && tensorMap(sh, L.tmap[0], L.plane[0], 1, L.width, L.height, L.stride[0], bw, bh) &&
+            if (!noTma && fits && tensorMap(sh, L.tmap[0], L.plane[0], 1, L.width, L.height, L.stride[0], bw, bh) &&
                 (sf == SVB_NV12 ? tensorMap(sh, L.tmap[1], L.plane[1], 2, cw, ch, L.stride[1], bcw, bch)
                                 : (tensorMap(sh, L.tmap[1], L.plane[1], 1, cw, ch, L.stride[1], bcw, bch) &&
                                    tensorMap(sh, L.tmap[2], L.plane[2], 1, cw, ch, L.stride[2], bcw, bch)))) {
@@ -283,10 +300,13 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
             check(d.cuEventRecord(tev.first, ic.compute), "cuEventRecord");
         }
         if (tiled) {
-            int nframes = n;
-            void* args[] = {&dev, &nframes, &total};
+            int nframes = n, maxLayers = 1;
+            for (int i = 0; i < n; ++i) maxLayers = std::max(maxLayers, frames[start + i].nlayers);
+            float one = 1.0f;  // see add2() in kernels_tiled.cuh
+            void* args[] = {&dev, &nframes, &total, &maxLayers, &one};
             const unsigned grid = (unsigned)std::min(total, ic.smCount * 2);
-            check(d.cuLaunchKernel(sh.fTiled, grid, 1, 1, 256, 1, 1, 0, ic.compute, args, nullptr), "cuLaunchKernel(svb_mix_tiled)");
+            const unsigned smem = tiledSmemBytes(maxLayers);
+            check(d.cuLaunchKernel(sh.fTiled, grid, 1, 1, 256, 1, 1, smem, ic.compute, args, nullptr), "cuLaunchKernel(svb_mix_tiled)");
             noteKernelLaunch();
         } else {
             void* args[] = {&dev};
@@ -334,6 +354,7 @@ void composeFused(const ComputeContext& ctx, std::vector<Job>& jobs, bool forceG
             if (p < pl.passes.size()) frames.push_back(pl.passes[p]);
         launchFrames(ctx, frames, allTiled);
     }
+    for (Job& j : jobs) markWritten(ctx, *j.target);
 }
 
 }  // namespace

@@ -15,7 +15,8 @@
 enum SvbFormat { SVB_NV12 = 0, SVB_Y420P = 1, SVB_BGRA = 2, SVB_RGBA = 3 };
 
 enum {
-    SVB_FRAME_LOAD_CUR = 1  // continue an earlier pass: start from the target's bytes, not from clear
+    SVB_FRAME_LOAD_CUR = 1,   // continue an earlier pass: start from the target's bytes, not from clear
+    SVB_FRAME_SCALAR_FP = 2   // tuning aid: spell the packed fp32x2 arithmetic as scalar instructions (same results)
 };
 enum {
     SVB_LAYER_SEPARABLE = 1,     // x outputs depend only on x and y outputs only on y (no rotation/shear)
