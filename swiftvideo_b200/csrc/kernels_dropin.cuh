@@ -32,11 +32,11 @@ __device__ __forceinline__ void dropin_blend(uint8_t* __restrict__ o0, uint8_t* 
             pu = o1 + (size_t)(y >> 1) * (W >> 1) + (x >> 1);
             pv = o2 + (size_t)(y >> 1) * (W >> 1) + (x >> 1);
         }
-        cu = unorm(*pu);
-        cv = unorm(*pv);
+        cu = unorm(opaque(*pu));
+        cv = unorm(opaque(*pv));
     }
     float oy, ou, ov;
-    if (!eval_pixel(U, s, x, y, (float)W, (float)H, chroma, unorm(*py), cu, cv, oy, ou, ov)) return;
+    if (!eval_pixel(U, s, x, y, (float)W, (float)H, chroma, unorm(opaque(*py)), cu, cv, oy, ou, ov)) return;
     *py = (uint8_t)rte8(oy);
     if (chroma) {
         *pu = (uint8_t)rte8(ou);

@@ -57,7 +57,7 @@ extern "C" __global__ void __launch_bounds__(SVB_GEN_BX* SVB_GEN_BY)
         for (int q = 0; q < 4; ++q) {
             float oy, ou, ov;
             const bool chroma = q == 0;
-            if (eval_pixel(&L->u, s, x + (q & 1), y + (q >> 1), fW, fH, chroma, unorm(Y[q]), unorm(Cu), unorm(Cv), oy, ou, ov)) {
+            if (eval_pixel(&L->u, s, x + (q & 1), y + (q >> 1), fW, fH, chroma, unorm(opaque(Y[q])), unorm(opaque(Cu)), unorm(opaque(Cv)), oy, ou, ov)) {
                 Y[q] = rte8(oy);
                 if (chroma) {
                     Cu = rte8(ou);

@@ -1,22 +1,25 @@
 // kernels_tiled.cuh -- svb_mix_tiled: the fused compositor's fast path.
 //
-// A CTA owns 128x32 luma tiles of the output frames of a batch (tiles are numbered column-major inside a
-// frame and every CTA of a grid sized to the SM count takes one contiguous run of them, so that it walks down
-// a 128-pixel column strip).  The running picture of a tile lives in registers -- a thread owns 4 columns x 4
+// svb_mix_tables (a small pre-pass per batch): for every separable YUV layer (no rotation: x outputs depend on x
+// only and y outputs on y only -- the planner proves it from the uniforms) the reference's per-pixel coordinate
+// chain (kernels.cl.swift:70-78 followed by the OpenCL 1.2 linear sampler's i0/i1/frac) is evaluated bit-exactly
+// once per output COLUMN and once per output ROW, into a table in global memory (L2-resident).
+//
+// svb_mix_tiled: a CTA owns 128x32 luma tiles of the output frames of the batch, dealt round-robin in row-major
+// order to a grid sized to the SM count (neighbouring tiles run at the same time, so the source lines they share
+// are fetched from HBM once).  The running picture of a tile lives in registers -- a thread owns 4 columns x 4
 // rows of luma and the 2x2 chroma texels under them, held as integer-valued floats -- and is re-quantised to
 // 8 bits after every layer, so the bytes equal the reference's clear-then-fold over an 8-bit target
-// (mix.video.swift:113-125).  Layers whose rectangle misses the tile are skipped.
-//
-// Separable YUV layers (no rotation: x outputs depend on x only, y outputs on y only -- the planner proves it
-// from the uniforms) take the table path.  The reference's per-pixel coordinate chain (kernels.cl.swift:70-78
-// followed by the OpenCL 1.2 linear sampler's i0/i1/frac) is evaluated bit-exactly once per COLUMN of the
-// strip and once per ROW of the tile into shared memory, for all layers at once.  For a tile that lies wholly
-// inside the layer's picture the source footprint is staged by one TMA 2-D tensor copy per plane
-// (cp.async.bulk.tensor + mbarrier) and every pixel then costs: four byte taps from shared memory, the UNORM8
-// reads, the bilinear sum, the blend and the re-quantisation -- all as packed fp32x2 instructions (FMUL2 /
-// FADD2 / FFMA2: two pixels per issue slot, each lane rounded separately, so nothing is contracted or
-// reassociated).  Everything else (rotated layers, BGRA/RGBA sources, tiles straddling a layer edge, footprints
-// too large to stage) runs the generic per-pixel evaluator of svb_device.cuh for that layer on that tile.
+// (mix.video.swift:113-125).  Per tile every layer is planned first (one thread per layer):
+//   skip     the layer's rectangle misses the tile
+//   staged   the tile lies wholly inside the layer's picture: the source footprint is staged by one TMA 2-D
+//            tensor copy per plane (cp.async.bulk.tensor + mbarrier), double-buffered so that the copy of the
+//            next staged layer flies while this one is computed; a pixel then costs four byte taps from shared
+//            memory, the UNORM8 reads, the bilinear sum, the blend and the re-quantisation -- all as packed
+//            fp32x2 instructions (FMUL2 / FFMA2: two pixels per issue slot, each lane rounded separately)
+//   direct   same, footprint too large to stage: taps come straight from the planes
+//   edge     the tile straddles the picture's edge: table path with a per-pixel class (picture / fill / untouched)
+//   generic  rotated layers and BGRA/RGBA sources: the per-pixel evaluator of svb_device.cuh.
 #pragma once
 #include "svb_device.cuh"
 
@@ -138,114 +141,161 @@ __device__ __forceinline__ float2 bilin2(float2 w00, float2 w10, float2 w01, flo
     return add2<PK>(add2<PK>(add2<PK>(mul2<PK>(w00, t00), mul2<PK>(w10, t10), one), mul2<PK>(w01, t01), one), mul2<PK>(w11, t11), one);
 }
 
-struct TiledSmem {  // fixed part; the per-layer tables follow in dynamic shared memory
-    alignas(128) uint8_t boxY[SVB_BOX_Y_BYTES];
-    alignas(128) uint8_t boxC[SVB_BOX_C_BYTES];
-    alignas(8) uint64_t bar;
+struct TiledSmem {
+    alignas(128) uint8_t boxY[2][SVB_BOX_Y_BYTES];
+    alignas(128) uint8_t boxC[2][SVB_BOX_C_BYTES];
+    alignas(8) uint64_t bar[2];
+    int4 plan[SVB_MAX_LAYERS][2];  // [l][0] = (mode, iy0, jy0, ic0), [l][1] = (jc0, 0, 0, 0)
 };
-#define SVB_TABLE_ENTS (SVB_TILE_W + SVB_TILE_W / 2 + SVB_TILE_H + SVB_TILE_H / 2)  // per layer: colY, colC, rowY, rowC
-#define SVB_TILED_SMEM_FIXED ((sizeof(svb::TiledSmem) + 127) / 128 * 128)
-#define SVB_TILED_SMEM_PER_LAYER (SVB_TABLE_ENTS * sizeof(svb::Ent))
+static_assert(sizeof(TiledSmem) <= SVB_TILED_SMEM_BYTES, "SVB_TILED_SMEM_BYTES (svb_desc.h) must cover TiledSmem");
+enum { PLAN_SKIP = 0, PLAN_GENERIC = 1, PLAN_EDGE = 2, PLAN_DIRECT = 3, PLAN_STAGED = 4 };
+
+__device__ __forceinline__ Ent ld_ent(const Ent* __restrict__ p) {
+    const int4 v = __ldg(reinterpret_cast<const int4*>(p));
+    Ent e;
+    e.a = __int_as_float(v.x), e.i0 = v.y, e.i1 = v.z, e.ok = v.w;
+    return e;
+}
+__device__ __forceinline__ unsigned lds_u8(unsigned addr) {  // opaque u32 (see ldg_u8)
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// Tables of one layer of one frame
+struct Tabs {
+    const Ent* colY;
+    const Ent* colC;
+    const Ent* rowY;
+    const Ent* rowC;
+};
+__device__ __forceinline__ Tabs layer_tabs(const Ent* __restrict__ tables, const SvbFrameDesc* __restrict__ F, int l) {
+    const int W = F->width, H = F->height;
+    Tabs t;
+    t.colY = tables + F->table_base + (size_t)l * SVB_TABLE_ENTRIES(W, H);
+    t.colC = t.colY + W;
+    t.rowY = t.colC + W / 2;
+    t.rowC = t.rowY + H;
+    return t;
+}
 
 // One separable YUV layer over a tile that lies wholly inside the picture, taps staged in shared memory.
 //   Yi / Ui / Vi: the running picture as integer-valued floats; pairs hold two horizontally adjacent samples.
 template <bool UNIT, bool CLAMP, bool PK>
-__device__ __forceinline__ void fast_layer(const TiledSmem& sm, const Ent* __restrict__ colY, const Ent* __restrict__ colC,
-                                           const Ent* __restrict__ rowY, const Ent* __restrict__ rowC, int lane, int warp, int iy0,
-                                           int jy0, int ic0, int jc0, int pitchY, int pitchC, int stepC, int voff, float alpha, float onef,
+__device__ __forceinline__ void fast_layer(unsigned boxY, unsigned boxU, unsigned boxV, const Tabs& tb, int xt, int yt, int H, int iy0, int jy0,
+                                           int ic0, int jc0, int pitchY, int pitchC, int stepC, float alpha, float onef,
                                            float2 (&Yi)[4][2], float2 (&Ui)[2], float2 (&Vi)[2]) {
     const float2 AL = splat(alpha), NAL = splat(sub(1.f, alpha)), ONE = splat(onef);
-    int o0[4], o1[4];
+    unsigned o0[4], o1[4];
     float2 A[2], NA[2];
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
-        const Ent e0 = colY[4 * lane + 2 * p], e1 = colY[4 * lane + 2 * p + 1];
-        o0[2 * p] = e0.i0 - iy0, o1[2 * p] = e0.i1 - iy0, o0[2 * p + 1] = e1.i0 - iy0, o1[2 * p + 1] = e1.i1 - iy0;
+        const Ent e0 = ld_ent(tb.colY + xt + 2 * p), e1 = ld_ent(tb.colY + xt + 2 * p + 1);
+        o0[2 * p] = boxY + (e0.i0 - iy0), o1[2 * p] = boxY + (e0.i1 - iy0);
+        o0[2 * p + 1] = boxY + (e1.i0 - iy0), o1[2 * p + 1] = boxY + (e1.i1 - iy0);
         A[p] = make_float2(e0.a, e1.a);
         NA[p] = make_float2(sub(1.f, e0.a), sub(1.f, e1.a));
     }
-    const Ent c0 = colC[2 * lane], c1 = colC[2 * lane + 1];
-    const int oc00 = (c0.i0 - ic0) * stepC, oc01 = (c0.i1 - ic0) * stepC, oc10 = (c1.i0 - ic0) * stepC, oc11 = (c1.i1 - ic0) * stepC;
+    const Ent c0 = ld_ent(tb.colC + (xt >> 1)), c1 = ld_ent(tb.colC + (xt >> 1) + 1);
+    const unsigned oc00 = (c0.i0 - ic0) * stepC, oc01 = (c0.i1 - ic0) * stepC, oc10 = (c1.i0 - ic0) * stepC, oc11 = (c1.i1 - ic0) * stepC;
     const float2 AC = make_float2(c0.a, c1.a), NAC = make_float2(sub(1.f, c0.a), sub(1.f, c1.a));
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        const Ent ry = rowY[4 * warp + r];
-        const int r0 = (ry.i0 - jy0) * pitchY, r1 = (ry.i1 - jy0) * pitchY;
+        const Ent ry = ld_ent(tb.rowY + min(yt + r, H - 1));  // rows past the frame's bottom are computed and dropped
+        const unsigned r0 = (ry.i0 - jy0) * pitchY, r1 = (ry.i1 - jy0) * pitchY;
         const float2 B = splat(ry.a), NB = splat(sub(1.f, ry.a));
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
-            const int a0 = o0[2 * p], a1 = o1[2 * p], b0 = o0[2 * p + 1], b1 = o1[2 * p + 1];
-            const float2 t00 = unorm2<PK>(bytes2(sm.boxY[r0 + a0], sm.boxY[r0 + b0]));
-            const float2 t10 = unorm2<PK>(bytes2(sm.boxY[r0 + a1], sm.boxY[r0 + b1]));
-            const float2 t01 = unorm2<PK>(bytes2(sm.boxY[r1 + a0], sm.boxY[r1 + b0]));
-            const float2 t11 = unorm2<PK>(bytes2(sm.boxY[r1 + a1], sm.boxY[r1 + b1]));
+            const unsigned a0 = o0[2 * p], a1 = o1[2 * p], b0 = o0[2 * p + 1], b1 = o1[2 * p + 1];
+            const float2 t00 = unorm2<PK>(bytes2(lds_u8(r0 + a0), lds_u8(r0 + b0)));
+            const float2 t10 = unorm2<PK>(bytes2(lds_u8(r0 + a1), lds_u8(r0 + b1)));
+            const float2 t01 = unorm2<PK>(bytes2(lds_u8(r1 + a0), lds_u8(r1 + b0)));
+            const float2 t11 = unorm2<PK>(bytes2(lds_u8(r1 + a1), lds_u8(r1 + b1)));
             const float2 v = bilin2<PK>(mul2<PK>(NA[p], NB), mul2<PK>(A[p], NB), mul2<PK>(NA[p], B), mul2<PK>(A[p], B), t00, t10, t01, t11, ONE);
             const float2 res = UNIT ? v : add2<PK>(mul2<PK>(unorm2<PK>(Yi[r][p]), NAL), mul2<PK>(v, AL), ONE);
             Yi[r][p] = quant2<CLAMP, PK>(res, ONE);
         }
         if ((r & 1) == 0) {
             const int k = r >> 1;
-            const Ent rc = rowC[2 * warp + k];
-            const int q0 = (rc.i0 - jc0) * pitchC, q1 = (rc.i1 - jc0) * pitchC;
+            const Ent rc = ld_ent(tb.rowC + min((yt >> 1) + k, (H >> 1) - 1));
+            const unsigned q0 = (rc.i0 - jc0) * pitchC, q1 = (rc.i1 - jc0) * pitchC;
             const float2 BC = splat(rc.a), NBC = splat(sub(1.f, rc.a));
             const float2 w00 = mul2<PK>(NAC, NBC), w10 = mul2<PK>(AC, NBC), w01 = mul2<PK>(NAC, BC), w11 = mul2<PK>(AC, BC);
-            const uint8_t* bu = sm.boxC;
-            const uint8_t* bv = sm.boxC + voff;
-            const float2 u = bilin2<PK>(w00, w10, w01, w11, unorm2<PK>(bytes2(bu[q0 + oc00], bu[q0 + oc10])), unorm2<PK>(bytes2(bu[q0 + oc01], bu[q0 + oc11])),
-                                    unorm2<PK>(bytes2(bu[q1 + oc00], bu[q1 + oc10])), unorm2<PK>(bytes2(bu[q1 + oc01], bu[q1 + oc11])), ONE);
-            const float2 v = bilin2<PK>(w00, w10, w01, w11, unorm2<PK>(bytes2(bv[q0 + oc00], bv[q0 + oc10])), unorm2<PK>(bytes2(bv[q0 + oc01], bv[q0 + oc11])),
-                                    unorm2<PK>(bytes2(bv[q1 + oc00], bv[q1 + oc10])), unorm2<PK>(bytes2(bv[q1 + oc01], bv[q1 + oc11])), ONE);
+            const unsigned u0 = boxU + q0, u1 = boxU + q1, v0 = boxV + q0, v1 = boxV + q1;
+            const float2 u = bilin2<PK>(w00, w10, w01, w11, unorm2<PK>(bytes2(lds_u8(u0 + oc00), lds_u8(u0 + oc10))), unorm2<PK>(bytes2(lds_u8(u0 + oc01), lds_u8(u0 + oc11))),
+                                        unorm2<PK>(bytes2(lds_u8(u1 + oc00), lds_u8(u1 + oc10))), unorm2<PK>(bytes2(lds_u8(u1 + oc01), lds_u8(u1 + oc11))), ONE);
+            const float2 v = bilin2<PK>(w00, w10, w01, w11, unorm2<PK>(bytes2(lds_u8(v0 + oc00), lds_u8(v0 + oc10))), unorm2<PK>(bytes2(lds_u8(v0 + oc01), lds_u8(v0 + oc11))),
+                                        unorm2<PK>(bytes2(lds_u8(v1 + oc00), lds_u8(v1 + oc10))), unorm2<PK>(bytes2(lds_u8(v1 + oc01), lds_u8(v1 + oc11))), ONE);
             Ui[k] = quant2<CLAMP, PK>(UNIT ? u : add2<PK>(mul2<PK>(unorm2<PK>(Ui[k]), NAL), mul2<PK>(u, AL), ONE), ONE);
             Vi[k] = quant2<CLAMP, PK>(UNIT ? v : add2<PK>(mul2<PK>(unorm2<PK>(Vi[k]), NAL), mul2<PK>(v, AL), ONE), ONE);
         }
     }
 }
 
-// Same layer, taps read straight from the planes in global memory (footprint too large to stage).
-__device__ __forceinline__ void slow_table_layer(const SvbLayerDesc* __restrict__ L, const Ent* __restrict__ colY, const Ent* __restrict__ colC,
-                                                 const Ent* __restrict__ rowY, const Ent* __restrict__ rowC, int lane, int warp, float alpha,
-                                                 float2 (&Yi)[4][2], float2 (&Ui)[2], float2 (&Vi)[2]) {
+// A separable YUV layer through the tables with taps straight from the planes: tiles that straddle the picture's
+// edge (per-pixel class from the ok bits: picture / fill / untouched, kernels.cl.swift:77,84-85,96-105) and tiles
+// whose footprint is too large to stage.  Scalar arithmetic in the reference's own order.
+__device__ __forceinline__ void table_layer(const SvbLayerDesc* __restrict__ L, const Tabs& tb, int xt, int yt, int H,
+                                            float2 (&Yi)[4][2], float2 (&Ui)[2], float2 (&Vi)[2]) {
     const uint8_t* __restrict__ pY = (const uint8_t*)L->plane[0];
     const uint8_t* __restrict__ pU = (const uint8_t*)L->plane[1];
     const bool nv12 = L->format == SVB_NV12;
     const uint8_t* __restrict__ pV = nv12 ? pU + 1 : (const uint8_t*)L->plane[2];
     const int pitchY = L->stride[0], pitchC = L->stride[1], stepC = nv12 ? 2 : 1;
-    const float nalpha = sub(1.f, alpha);
+    const float alpha = L->u.opacity, nalpha = sub(1.f, alpha);
+    const float4 fc = ldrow(L->u.fillColor, 0);
+    const float3 fill = rgb2yuv(fc.x, fc.y, fc.z);
+    const float af = mul(alpha, fc.w), naf = sub(1.f, af);
+    Ent cy[4], cc[2];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) cy[c] = ld_ent(tb.colY + xt + c);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) cc[c] = ld_ent(tb.colC + (xt >> 1) + c);
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        const Ent ry = rowY[4 * warp + r];
+        if (yt + r >= H) break;
+        const Ent ry = ld_ent(tb.rowY + yt + r);
         const float b = ry.a, nb = sub(1.f, b);
         const uint8_t* q0 = pY + (size_t)ry.i0 * pitchY;
         const uint8_t* q1 = pY + (size_t)ry.i1 * pitchY;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            const Ent cy = colY[4 * lane + c];
-            const float a = cy.a, na = sub(1.f, a);
-            const float v = add(add(add(mul(mul(na, nb), unorm(__ldg(q0 + cy.i0))), mul(mul(a, nb), unorm(__ldg(q0 + cy.i1)))),
-                                    mul(mul(na, b), unorm(__ldg(q1 + cy.i0)))),
-                                mul(mul(a, b), unorm(__ldg(q1 + cy.i1))));
+            const int ok = cy[c].ok & ry.ok;
             float& dst = (c & 1) ? Yi[r][c >> 1].y : Yi[r][c >> 1].x;
-            dst = (float)rte8(add(mul(unorm_f(dst), nalpha), mul(v, alpha)));
+            if (ok == 7) {
+                const float a = cy[c].a, na = sub(1.f, a);
+                const float v = add(add(add(mul(mul(na, nb), unorm(ldg_u8(q0 + cy[c].i0))), mul(mul(a, nb), unorm(ldg_u8(q0 + cy[c].i1)))),
+                                        mul(mul(na, b), unorm(ldg_u8(q1 + cy[c].i0)))),
+                                    mul(mul(a, b), unorm(ldg_u8(q1 + cy[c].i1))));
+                dst = quantf(add(mul(unorm_f(dst), nalpha), mul(v, alpha)));
+            } else if (ok & 1) {
+                dst = quantf(clampf(add(mul(unorm_f(dst), naf), mul(fill.x, af)), 0.f, 1.f));
+            }
         }
         if ((r & 1) == 0) {
             const int k = r >> 1;
-            const Ent rc = rowC[2 * warp + k];
+            const Ent rc = ld_ent(tb.rowC + (yt >> 1) + k);
             const float bb = rc.a, nbb = sub(1.f, bb);
             const size_t z0 = (size_t)rc.i0 * pitchC, z1 = (size_t)rc.i1 * pitchC;
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
-                const Ent cc = colC[2 * lane + c];
-                const float a = cc.a, na = sub(1.f, a);
-                const float w00 = mul(na, nbb), w10 = mul(a, nbb), w01 = mul(na, bb), w11 = mul(a, bb);
-                const int e0 = cc.i0 * stepC, e1 = cc.i1 * stepC;
-                const float vu = add(add(add(mul(w00, unorm(__ldg(pU + z0 + e0))), mul(w10, unorm(__ldg(pU + z0 + e1)))), mul(w01, unorm(__ldg(pU + z1 + e0)))),
-                                     mul(w11, unorm(__ldg(pU + z1 + e1))));
-                const float vv = add(add(add(mul(w00, unorm(__ldg(pV + z0 + e0))), mul(w10, unorm(__ldg(pV + z0 + e1)))), mul(w01, unorm(__ldg(pV + z1 + e0)))),
-                                     mul(w11, unorm(__ldg(pV + z1 + e1))));
+                const int ok = cc[c].ok & rc.ok;
                 float& du = c ? Ui[k].y : Ui[k].x;
                 float& dv = c ? Vi[k].y : Vi[k].x;
-                du = (float)rte8(add(mul(unorm_f(du), nalpha), mul(vu, alpha)));
-                dv = (float)rte8(add(mul(unorm_f(dv), nalpha), mul(vv, alpha)));
+                if (ok == 7) {
+                    const float a = cc[c].a, na = sub(1.f, a);
+                    const float w00 = mul(na, nbb), w10 = mul(a, nbb), w01 = mul(na, bb), w11 = mul(a, bb);
+                    const int e0 = cc[c].i0 * stepC, e1 = cc[c].i1 * stepC;
+                    const float vu = add(add(add(mul(w00, unorm(ldg_u8(pU + z0 + e0))), mul(w10, unorm(ldg_u8(pU + z0 + e1)))), mul(w01, unorm(ldg_u8(pU + z1 + e0)))),
+                                         mul(w11, unorm(ldg_u8(pU + z1 + e1))));
+                    const float vv = add(add(add(mul(w00, unorm(ldg_u8(pV + z0 + e0))), mul(w10, unorm(ldg_u8(pV + z0 + e1)))), mul(w01, unorm(ldg_u8(pV + z1 + e0)))),
+                                         mul(w11, unorm(ldg_u8(pV + z1 + e1))));
+                    du = quantf(add(mul(unorm_f(du), nalpha), mul(vu, alpha)));
+                    dv = quantf(add(mul(unorm_f(dv), nalpha), mul(vv, alpha)));
+                } else if (ok & 1) {
+                    du = quantf(clampf(add(mul(unorm_f(du), naf), mul(fill.y, af)), -1.f, 1.f));
+                    dv = quantf(clampf(add(mul(unorm_f(dv), naf), mul(fill.z, af)), -1.f, 1.f));
+                }
             }
         }
     }
@@ -257,36 +307,51 @@ __device__ __forceinline__ unsigned pack4(float2 a, float2 b) {  // four integer
 
 }  // namespace svb
 
+// ---- pre-pass: coordinate tables of every separable YUV layer of every frame of the batch -----------------------
+// grid (ceil(max entries / 256), max layers, frames); one entry per thread.
+extern "C" __global__ void __launch_bounds__(256) svb_mix_tables(const SvbFrameDesc* __restrict__ frames, svb::Ent* __restrict__ tables) {
+    using namespace svb;
+    const SvbFrameDesc* __restrict__ F = frames + blockIdx.z;
+    const int l = blockIdx.y;
+    if (l >= F->nlayers) return;
+    const SvbLayerDesc* __restrict__ L = &F->layers[l];
+    if (!(L->flags & SVB_LAYER_SEPARABLE) || (L->format != SVB_NV12 && L->format != SVB_Y420P)) return;
+    const int W = F->width, H = F->height;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= SVB_TABLE_ENTRIES(W, H)) return;
+    Ent* __restrict__ out = tables + F->table_base + (size_t)l * SVB_TABLE_ENTRIES(W, H) + e;
+    if (e < W) {
+        *out = axis_entry(axis_chain(&L->u, 0, e, (float)W), L->width);
+    } else if (e < W + W / 2) {  // chroma is produced by the even luma column (kernels.cl.swift:76)
+        *out = axis_entry(axis_chain(&L->u, 0, 2 * (e - W), (float)W), L->width / 2);
+    } else if (e < W + W / 2 + H) {
+        *out = axis_entry(axis_chain(&L->u, 1, e - W - W / 2, (float)H), L->height);
+    } else {
+        *out = axis_entry(axis_chain(&L->u, 1, 2 * (e - W - W / 2 - H), (float)H), L->height / 2);
+    }
+}
+
 extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, 2)
-    svb_mix_tiled(const SvbFrameDesc* __restrict__ frames, int nframes, int total_tiles, int max_layers, float one) {
+    svb_mix_tiled(const SvbFrameDesc* __restrict__ frames, const svb::Ent* __restrict__ tables, int nframes, int total_tiles, float one) {
     using namespace svb;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TiledSmem& sm = *reinterpret_cast<TiledSmem*>(smem_raw);
-    Ent* const tables = reinterpret_cast<Ent*>(smem_raw + SVB_TILED_SMEM_FIXED);
-    Ent* const colYs = tables;                                         // [max_layers][128]
-    Ent* const colCs = colYs + (size_t)max_layers * SVB_TILE_W;        // [max_layers][64]
-    Ent* const rowYs = colCs + (size_t)max_layers * (SVB_TILE_W / 2);  // [max_layers][32]
-    Ent* const rowCs = rowYs + (size_t)max_layers * SVB_TILE_H;        // [max_layers][16]
-
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    unsigned phase = 0;
+    unsigned phase0 = 0, phase1 = 0;
     if (t == 0) {
-        mbar_init(&sm.bar, 1);
+        mbar_init(&sm.bar[0], 1);
+        mbar_init(&sm.bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    int f = 0;
 
-    // a contiguous run of tiles per CTA; tiles are column-major inside a frame, so a run walks down a column strip
-    const int tile_begin = (int)((long long)total_tiles * blockIdx.x / gridDim.x);
-    const int tile_end = (int)((long long)total_tiles * (blockIdx.x + 1) / gridDim.x);
-    int f = 0, strip_f = -1, strip_x0 = -1;
-
-    for (int tile = tile_begin; tile < tile_end; ++tile) {
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         while (f + 1 < nframes && frames[f + 1].first_tile <= tile) ++f;
         const SvbFrameDesc* __restrict__ F = frames + f;
         const int local = tile - F->first_tile;
         const int W = F->width, H = F->height, nl = F->nlayers;
-        const int x0 = (local / F->tiles_y) * SVB_TILE_W, y0 = (local % F->tiles_y) * SVB_TILE_H;
+        const int x0 = (local % F->tiles_x) * SVB_TILE_W, y0 = (local / F->tiles_x) * SVB_TILE_H;
         const int xt = x0 + 4 * lane, yt = y0 + 4 * warp;  // this thread's 4x4 block
         const bool live = xt < W && yt < H;                 // W % 4 == 0 and H even are planner preconditions
         const bool nv12 = F->format == SVB_NV12;
@@ -295,29 +360,37 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, 2)
         uint8_t* const oU = (uint8_t*)F->out_plane[1];
         uint8_t* const oV = (uint8_t*)F->out_plane[2];
         const int sY = F->out_stride[0], sU = F->out_stride[1], sV = F->out_stride[2];
+        const int lastc = min(SVB_TILE_W, W - x0) - 1, lastr = min(SVB_TILE_H, H - y0) - 1;
 
-        // ---- tables for every separable YUV layer that touches the tile: rows always, columns on a new strip ----
-        {
-            const bool new_strip = f != strip_f || x0 != strip_x0;
-            const int per = new_strip ? SVB_TILE_W + SVB_TILE_H : SVB_TILE_H;
-            for (int e = t; e < nl * per; e += SVB_TILED_THREADS) {
-                const int l = e / per, k = e - l * per;
-                const SvbLayerDesc* __restrict__ L = &F->layers[l];
-                if (!(L->flags & SVB_LAYER_SEPARABLE) || (L->format != SVB_NV12 && L->format != SVB_Y420P)) continue;
-                if (new_strip && k < SVB_TILE_W) {
-                    if (L->rect[0] >= x0 + SVB_TILE_W || L->rect[2] <= x0) continue;
-                    const Axis c = axis_chain(&L->u, 0, x0 + k, fW);
-                    colYs[l * SVB_TILE_W + k] = axis_entry(c, L->width);
-                    if ((k & 1) == 0) colCs[l * (SVB_TILE_W / 2) + (k >> 1)] = axis_entry(c, L->width / 2);
+        // ---- plan: one thread per layer --------------------------------------------------------------------------
+        if (t < nl) {
+            const SvbLayerDesc* __restrict__ L = &F->layers[t];
+            int mode, iy0 = 0, jy0 = 0, ic0 = 0, jc0 = 0;
+            if (L->rect[0] >= x0 + SVB_TILE_W || L->rect[2] <= x0 || L->rect[1] >= y0 + SVB_TILE_H || L->rect[3] <= y0) {
+                mode = PLAN_SKIP;
+            } else if (!(L->flags & SVB_LAYER_SEPARABLE) || (L->format != SVB_NV12 && L->format != SVB_Y420P)) {
+                mode = PLAN_GENERIC;
+            } else {
+                const Tabs tb = layer_tabs(tables, F, t);
+                const Ent cA = ld_ent(tb.colY + x0), cB = ld_ent(tb.colY + x0 + lastc), rA = ld_ent(tb.rowY + y0), rB = ld_ent(tb.rowY + y0 + lastr);
+                // border, tx and uv are monotone along each axis: both ends inside [0,1] means everything between is
+                if (cA.ok == 7 && cB.ok == 7 && rA.ok == 7 && rB.ok == 7) {
+                    // source footprint of the tile (indices are monotone too); x origins rounded down to 16 bytes for TMA
+                    const Ent ccA = ld_ent(tb.colC + (x0 >> 1)), ccB = ld_ent(tb.colC + ((x0 + lastc) >> 1));
+                    const Ent rcA = ld_ent(tb.rowC + (y0 >> 1)), rcB = ld_ent(tb.rowC + ((y0 + lastr) >> 1));
+                    iy0 = min(cA.i0, cB.i0) & ~15;
+                    jy0 = min(rA.i0, rB.i0);
+                    ic0 = min(ccA.i0, ccB.i0) & (L->format == SVB_NV12 ? ~7 : ~15);
+                    jc0 = min(rcA.i0, rcB.i0);
+                    const bool fits = max(cA.i1, cB.i1) - iy0 < L->box_w && max(rA.i1, rB.i1) - jy0 < L->box_h &&
+                                      max(ccA.i1, ccB.i1) - ic0 < L->box_cw && max(rcA.i1, rcB.i1) - jc0 < L->box_ch;
+                    mode = ((L->flags & SVB_LAYER_STAGED) && fits) ? PLAN_STAGED : PLAN_DIRECT;
                 } else {
-                    const int r = new_strip ? k - SVB_TILE_W : k;
-                    if (L->rect[1] >= y0 + SVB_TILE_H || L->rect[3] <= y0) continue;
-                    const Axis c = axis_chain(&L->u, 1, y0 + r, fH);
-                    rowYs[l * SVB_TILE_H + r] = axis_entry(c, L->height);
-                    if ((r & 1) == 0) rowCs[l * (SVB_TILE_H / 2) + (r >> 1)] = axis_entry(c, L->height / 2);
+                    mode = PLAN_EDGE;
                 }
             }
-            strip_f = f, strip_x0 = x0;
+            sm.plan[t][0] = make_int4(mode, iy0, jy0, ic0);
+            sm.plan[t][1] = make_int4(jc0, 0, 0, 0);
         }
 
         // ---- running picture: integer-valued floats ------------------------------------------------------------
@@ -330,83 +403,95 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, 2)
             for (int r = 0; r < 4; ++r)
                 if (yt + r < H) {
                     const unsigned w = *(const unsigned*)(oY + (size_t)(yt + r) * sY + xt);
-                    Yi[r][0] = bytes2(w & 0xff, (w >> 8) & 0xff), Yi[r][1] = bytes2((w >> 16) & 0xff, w >> 24);
+                    Yi[r][0] = bytes2(opaque(w & 0xff), opaque((w >> 8) & 0xff)), Yi[r][1] = bytes2(opaque((w >> 16) & 0xff), opaque(w >> 24));
                 }
 #pragma unroll
             for (int k = 0; k < 2; ++k)
                 if (yt + 2 * k < H) {
                     if (nv12) {
                         const unsigned w = *(const unsigned*)(oU + (size_t)((yt >> 1) + k) * sU + xt);
-                        Ui[k] = bytes2(w & 0xff, (w >> 16) & 0xff), Vi[k] = bytes2((w >> 8) & 0xff, w >> 24);
+                        Ui[k] = bytes2(opaque(w & 0xff), opaque((w >> 16) & 0xff)), Vi[k] = bytes2(opaque((w >> 8) & 0xff), opaque(w >> 24));
                     } else {
                         const uchar2 u = *(const uchar2*)(oU + (size_t)((yt >> 1) + k) * sU + (xt >> 1));
                         const uchar2 v = *(const uchar2*)(oV + (size_t)((yt >> 1) + k) * sV + (xt >> 1));
-                        Ui[k] = bytes2(u.x, u.y), Vi[k] = bytes2(v.x, v.y);
+                        Ui[k] = bytes2(opaque(u.x), opaque(u.y)), Vi[k] = bytes2(opaque(v.x), opaque(v.y));
                     }
                 }
         }
-        __syncthreads();  // tables visible
+        __syncthreads();  // plan visible; nobody still reads the boxes of the previous tile
+
+        // TMA of one staged layer into box buffer `b`
+        auto issue = [&](int l, int b) {
+            const SvbLayerDesc* __restrict__ L = &F->layers[l];
+            const int4 p0 = sm.plan[l][0], p1 = sm.plan[l][1];
+            const bool n12 = L->format == SVB_NV12;
+            const int cbytes = n12 ? L->box_cw * L->box_ch * 2 : L->box_cw * L->box_ch;
+            tmap_acquire(L->tmap[0]);
+            tmap_acquire(L->tmap[1]);
+            if (!n12) tmap_acquire(L->tmap[2]);
+            mbar_expect_tx(&sm.bar[b], L->box_w * L->box_h + cbytes * (n12 ? 1 : 2));
+            tma_load_2d(sm.boxY[b], L->tmap[0], p0.y, p0.z, &sm.bar[b]);
+            tma_load_2d(sm.boxC[b], L->tmap[1], p0.w, p1.x, &sm.bar[b]);
+            if (!n12) tma_load_2d(sm.boxC[b] + SVB_BOX_C_BYTES / 2, L->tmap[2], p0.w, p1.x, &sm.bar[b]);
+        };
+        int stage = 0;
+        if (t == 0)
+            for (int l = 0; l < nl; ++l)
+                if (sm.plan[l][0].x == PLAN_STAGED) {
+                    issue(l, 0);
+                    break;
+                }
 
         for (int l = 0; l < nl; ++l) {
+            const int4 p0 = sm.plan[l][0];
+            const int mode = p0.x;
+            if (mode == PLAN_SKIP) continue;
             const SvbLayerDesc* __restrict__ L = &F->layers[l];
-            if (L->rect[0] >= x0 + SVB_TILE_W || L->rect[2] <= x0 || L->rect[1] >= y0 + SVB_TILE_H || L->rect[3] <= y0) continue;
-            const SvbUniforms* __restrict__ U = &L->u;
-            const int fmt = L->format, lflags = L->flags;
-            const Ent* colY = colYs + l * SVB_TILE_W;
-            const Ent* colC = colCs + l * (SVB_TILE_W / 2);
-            const Ent* rowY = rowYs + l * SVB_TILE_H;
-            const Ent* rowC = rowCs + l * (SVB_TILE_H / 2);
-            bool full = false;
-            const int lastc = min(SVB_TILE_W, W - x0) - 1, lastr = min(SVB_TILE_H, H - y0) - 1;
-            if ((lflags & SVB_LAYER_SEPARABLE) && (fmt == SVB_NV12 || fmt == SVB_Y420P))
-                // border, tx and uv are monotone along each axis: both ends inside [0,1] means everything between is
-                full = colY[0].ok == 7 && colY[lastc].ok == 7 && rowY[0].ok == 7 && rowY[lastr].ok == 7;
-            if (full) {
-                // source footprint of the tile (indices are monotone too); x origins rounded down to 16 bytes for TMA
-                const int lc = lastc >> 1, lr = lastr >> 1;
-                const int iy0 = min(colY[0].i0, colY[lastc].i0) & ~15, iy1 = max(colY[0].i1, colY[lastc].i1);
-                const int jy0 = min(rowY[0].i0, rowY[lastr].i0), jy1 = max(rowY[0].i1, rowY[lastr].i1);
-                const int ic0 = min(colC[0].i0, colC[lc].i0) & (fmt == SVB_NV12 ? ~7 : ~15), ic1 = max(colC[0].i1, colC[lc].i1);
-                const int jc0 = min(rowC[0].i0, rowC[lr].i0), jc1 = max(rowC[0].i1, rowC[lr].i1);
-                const bool staged = (lflags & SVB_LAYER_STAGED) && iy1 - iy0 < L->box_w && jy1 - jy0 < L->box_h && ic1 - ic0 < L->box_cw &&
-                                    jc1 - jc0 < L->box_ch;
-                const float alpha = U->opacity;
-                if (staged) {
-                    const int cbytes = fmt == SVB_NV12 ? L->box_cw * L->box_ch * 2 : L->box_cw * L->box_ch;
-                    if (t == 0) {
-                        tmap_acquire(L->tmap[0]);
-                        tmap_acquire(L->tmap[1]);
-                        if (fmt == SVB_Y420P) tmap_acquire(L->tmap[2]);
-                        mbar_expect_tx(&sm.bar, L->box_w * L->box_h + cbytes * (fmt == SVB_NV12 ? 1 : 2));
-                        tma_load_2d(sm.boxY, L->tmap[0], iy0, jy0, &sm.bar);
-                        tma_load_2d(sm.boxC, L->tmap[1], ic0, jc0, &sm.bar);
-                        if (fmt == SVB_Y420P) tma_load_2d(sm.boxC + SVB_BOX_C_BYTES / 2, L->tmap[2], ic0, jc0, &sm.bar);
-                    }
-                    const int pitchC = fmt == SVB_NV12 ? L->box_cw * 2 : L->box_cw, stepC = fmt == SVB_NV12 ? 2 : 1;
-                    const int voff = fmt == SVB_NV12 ? 1 : SVB_BOX_C_BYTES / 2;
-                    mbar_wait(&sm.bar, phase);
-                    phase ^= 1;
-#define SVB_FAST(UNIT, CLAMP, PK) \
-    fast_layer<UNIT, CLAMP, PK>(sm, colY, colC, rowY, rowC, lane, warp, iy0, jy0, ic0, jc0, L->box_w, pitchC, stepC, voff, alpha, one, Yi, Ui, Vi)
-                    if (live) {
-                        if (F->flags & SVB_FRAME_SCALAR_FP) {
-                            if (lflags & SVB_LAYER_UNIT_OPACITY) SVB_FAST(true, false, false);
-                            else if (lflags & SVB_LAYER_OPACITY_01) SVB_FAST(false, false, false);
-                            else SVB_FAST(false, true, false);
-                        } else {
-                            if (lflags & SVB_LAYER_UNIT_OPACITY) SVB_FAST(true, false, true);
-                            else if (lflags & SVB_LAYER_OPACITY_01) SVB_FAST(false, false, true);
-                            else SVB_FAST(false, true, true);
+            if (mode == PLAN_STAGED) {
+                const int jc0 = sm.plan[l][1].x;
+                __syncthreads();  // every warp is past its reads of the other buffer: it may be refilled
+                if (t == 0)
+                    for (int j = l + 1; j < nl; ++j)
+                        if (sm.plan[j][0].x == PLAN_STAGED) {
+                            issue(j, stage ^ 1);
+                            break;
                         }
+                if (stage == 0) {
+                    mbar_wait(&sm.bar[0], phase0);
+                    phase0 ^= 1;
+                } else {
+                    mbar_wait(&sm.bar[1], phase1);
+                    phase1 ^= 1;
+                }
+                if (live) {
+                    const Tabs tb = layer_tabs(tables, F, l);
+                    const int fmt = L->format, lflags = L->flags;
+                    const int pitchC = fmt == SVB_NV12 ? L->box_cw * 2 : L->box_cw, stepC = fmt == SVB_NV12 ? 2 : 1;
+                    const unsigned bY = smem_u32(sm.boxY[stage]), bU = smem_u32(sm.boxC[stage]);
+                    const unsigned bV = bU + (fmt == SVB_NV12 ? 1 : SVB_BOX_C_BYTES / 2);
+                    const float alpha = L->u.opacity;
+#define SVB_FAST(UNIT, CLAMP, PK) \
+    fast_layer<UNIT, CLAMP, PK>(bY, bU, bV, tb, xt, yt, H, p0.y, p0.z, p0.w, jc0, L->box_w, pitchC, stepC, alpha, one, Yi, Ui, Vi)
+                    if (F->flags & SVB_FRAME_SCALAR_FP) {
+                        if (lflags & SVB_LAYER_UNIT_OPACITY) SVB_FAST(true, false, false);
+                        else if (lflags & SVB_LAYER_OPACITY_01) SVB_FAST(false, false, false);
+                        else SVB_FAST(false, true, false);
+                    } else {
+                        if (lflags & SVB_LAYER_UNIT_OPACITY) SVB_FAST(true, false, true);
+                        else if (lflags & SVB_LAYER_OPACITY_01) SVB_FAST(false, false, true);
+                        else SVB_FAST(false, true, true);
                     }
 #undef SVB_FAST
-                    __syncthreads();  // the boxes are free for the next layer
-                } else if (live) {
-                    slow_table_layer(L, colY, colC, rowY, rowC, lane, warp, alpha, Yi, Ui, Vi);
                 }
-            } else if (live) {
+                stage ^= 1;
+            } else if (!live) {
+                continue;
+            } else if (mode == PLAN_EDGE || mode == PLAN_DIRECT) {
+                table_layer(L, layer_tabs(tables, F, l), xt, yt, H, Yi, Ui, Vi);
+            } else {
                 // ---- generic per-pixel evaluation of this layer on this thread's 4x4 block ----------------------
                 const Src s = layer_src(L);
+                const SvbUniforms* __restrict__ U = &L->u;
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
 #pragma unroll
@@ -419,8 +504,8 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, 2)
                         float oy, ou, ov;
                         if (yt + r < H && eval_pixel(U, s, xt + c, yt + r, fW, fH, chroma, unorm_f(py), chroma ? unorm_f(pu) : 0.f,
                                                      chroma ? unorm_f(pv) : 0.f, oy, ou, ov)) {
-                            py = (float)rte8(oy);
-                            if (chroma) pu = (float)rte8(ou), pv = (float)rte8(ov);
+                            py = quantf(oy);
+                            if (chroma) pu = quantf(ou), pv = quantf(ov);
                         }
                     }
                 }
@@ -442,6 +527,6 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, 2)
                     }
                 }
         }
-        __syncthreads();  // row tables are rewritten by the next tile
+        __syncthreads();  // the plan and the boxes are rewritten by the next tile
     }
 }

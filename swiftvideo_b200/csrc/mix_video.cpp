@@ -21,8 +21,6 @@ static const CuDriver& drv() {
 
 namespace {
 
-unsigned tiledSmemBytes(int maxLayers);
-
 constexpr int kSegments = 8;     // batches in flight before the host has to wait for the oldest
 constexpr int kSegFrames = 64;   // frame descriptors per batch
 
@@ -33,7 +31,7 @@ struct MixerShared {
     bool used[kSegments] = {};
     int next = 0;
     std::map<std::array<uint64_t, 4>, std::array<uint8_t, 128>> tmaps;
-    CUfunction fTiled = nullptr, fGeneric = nullptr;
+    CUfunction fTiled = nullptr, fGeneric = nullptr, fTables = nullptr;
     std::mutex mu;
     // optional per-launch device timing of the fused kernels (bench.py's roofline leg)
     bool timing = false;
@@ -81,18 +79,12 @@ MixerShared& shared(const std::shared_ptr<InternalContext>& ic) {  // caller hol
         check(drv().cuMemAlloc(&s->dev, bytes), "cuMemAlloc");
         for (CUevent& e : s->ev) check(drv().cuEventCreate(&e, CU_EVENT_DISABLE_TIMING), "cuEventCreate");
         s->fTiled = ic->builtin("svb_mix_tiled");
-        check(drv().cuFuncSetAttribute(s->fTiled, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)tiledSmemBytes(SVB_MAX_LAYERS)),
+        check(drv().cuFuncSetAttribute(s->fTiled, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, SVB_TILED_SMEM_BYTES),
               "cuFuncSetAttribute(max dynamic shared memory)");
+        s->fTables = ic->builtin("svb_mix_tables");
         s->fGeneric = ic->builtin("svb_mix_generic");
     }
     return *(MixerShared*)ic->mixerShared;
-}
-
-// dynamic shared memory of svb_mix_tiled: staged boxes + mbarrier (kernels_tiled.cuh: TiledSmem, padded to 128) and
-// 240 table entries of 16 bytes per layer
-unsigned tiledSmemBytes(int maxLayers) {
-    const unsigned fixed = (SVB_BOX_Y_BYTES + SVB_BOX_C_BYTES + 8 + 127) / 128 * 128;
-    return fixed + (unsigned)maxLayers * (SVB_TILE_W + SVB_TILE_W / 2 + SVB_TILE_H + SVB_TILE_H / 2) * 16u;
 }
 
 int svbFormat(PixelFormat f) {
@@ -276,14 +268,20 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
         }
         if (sh.used[seg]) check(d.cuEventSynchronize(sh.ev[seg]), "cuEventSynchronize");
         SvbFrameDesc* host = (SvbFrameDesc*)(sh.host + (size_t)seg * kSegFrames * sizeof(SvbFrameDesc));
-        int total = 0, maxW = 0, maxH = 0;
+        int total = 0, maxW = 0, maxH = 0, maxLayers = 1, maxEnts = 1;
+        size_t tableEnts = 0;
         for (int i = 0; i < n; ++i) {
-            frames[start + i].first_tile = total;
-            total += frames[start + i].tiles_x * frames[start + i].tiles_y;
-            maxW = std::max(maxW, frames[start + i].width), maxH = std::max(maxH, frames[start + i].height);
+            SvbFrameDesc& fr = frames[start + i];
+            fr.first_tile = total;
+            total += fr.tiles_x * fr.tiles_y;
+            maxW = std::max(maxW, fr.width), maxH = std::max(maxH, fr.height);
+            const int ents = SVB_TABLE_ENTRIES(fr.width, fr.height);
+            fr.table_base = (int32_t)tableEnts;
+            tableEnts += (size_t)ents * (size_t)fr.nlayers;
+            maxLayers = std::max(maxLayers, fr.nlayers), maxEnts = std::max(maxEnts, ents);
             // copy only the header and the layers in use
-            const size_t used = offsetof(SvbFrameDesc, layers) + sizeof(SvbLayerDesc) * (size_t)frames[start + i].nlayers;
-            std::memcpy(&host[i], &frames[start + i], used);
+            const size_t used = offsetof(SvbFrameDesc, layers) + sizeof(SvbLayerDesc) * (size_t)fr.nlayers;
+            std::memcpy(&host[i], &fr, used);
         }
         CUdeviceptr dev = sh.dev + (size_t)seg * kSegFrames * sizeof(SvbFrameDesc);
         check(d.cuMemcpyHtoDAsync(dev, host, (size_t)n * sizeof(SvbFrameDesc), ic.compute), "cuMemcpyHtoDAsync");
@@ -297,17 +295,24 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
                 check(d.cuEventCreate(&tev.first, CU_EVENT_DEFAULT), "cuEventCreate");
                 check(d.cuEventCreate(&tev.second, CU_EVENT_DEFAULT), "cuEventCreate");
             }
-            check(d.cuEventRecord(tev.first, ic.compute), "cuEventRecord");
         }
+        if (!tiled && tev.first) check(d.cuEventRecord(tev.first, ic.compute), "cuEventRecord");
         if (tiled) {
-            int nframes = n, maxLayers = 1;
-            for (int i = 0; i < n; ++i) maxLayers = std::max(maxLayers, frames[start + i].nlayers);
-            float one = 1.0f;  // see add2() in kernels_tiled.cuh
-            void* args[] = {&dev, &nframes, &total, &maxLayers, &one};
-            const unsigned grid = (unsigned)std::min(total, ic.smCount * 2);
-            const unsigned smem = tiledSmemBytes(maxLayers);
-            check(d.cuLaunchKernel(sh.fTiled, grid, 1, 1, 256, 1, 1, smem, ic.compute, args, nullptr), "cuLaunchKernel(svb_mix_tiled)");
+            // pre-pass: per-column / per-row coordinate tables of the batch (16 bytes per entry), then the compositor
+            const size_t tableBytes = std::max<size_t>(tableEnts, 1) * 16;
+            CUdeviceptr tables = ic.alloc(tableBytes);
+            void* targs[] = {&dev, &tables};
+            check(d.cuLaunchKernel(sh.fTables, (unsigned)((maxEnts + 255) / 256), (unsigned)maxLayers, (unsigned)n, 256, 1, 1, 0, ic.compute, targs, nullptr),
+                  "cuLaunchKernel(svb_mix_tables)");
             noteKernelLaunch();
+            if (tev.first) check(d.cuEventRecord(tev.first, ic.compute), "cuEventRecord");  // time svb_mix_tiled alone
+            int nframes = n;
+            float one = 1.0f;  // see add2() in kernels_tiled.cuh
+            void* args[] = {&dev, &tables, &nframes, &total, &one};
+            const unsigned grid = (unsigned)std::min(total, ic.smCount * 2);
+            check(d.cuLaunchKernel(sh.fTiled, grid, 1, 1, 256, 1, 1, SVB_TILED_SMEM_BYTES, ic.compute, args, nullptr), "cuLaunchKernel(svb_mix_tiled)");
+            noteKernelLaunch();
+            ic.release(tables, tableBytes);  // recycled only after the streams have drained past this point
         } else {
             void* args[] = {&dev};
             check(d.cuLaunchKernel(sh.fGeneric, (unsigned)((maxW / 2 + 31) / 32), (unsigned)((maxH / 2 + 7) / 8), (unsigned)n, 32, 8, 1, 0,

@@ -63,9 +63,16 @@ typedef struct __attribute__((aligned(64))) SvbFrameDesc {
     int32_t flags;       // SVB_FRAME_*
     int32_t first_tile;  // prefix sum of tiles over the batch
     int32_t tiles_x, tiles_y;
-    int32_t pad_[5];
+    int32_t table_base;  // first entry of this frame's coordinate tables in the batch's table buffer (svb_mix_tables)
+    int32_t pad_[4];
     SvbLayerDesc layers[SVB_MAX_LAYERS];
 } SvbFrameDesc;
+
+// dynamic shared memory of svb_mix_tiled: two staged box pairs, two mbarriers, one 32-byte plan per layer
+#define SVB_TILED_SMEM_BYTES (2 * SVB_BOX_Y_BYTES + 2 * SVB_BOX_C_BYTES + 128 + SVB_MAX_LAYERS * 32)
+
+// Coordinate-table entries per layer of a WxH frame: colY[W] colC[W/2] rowY[H] rowC[H/2], 16 bytes each.
+#define SVB_TABLE_ENTRIES(W, H) ((W) + (W) / 2 + (H) + (H) / 2)
 
 #ifdef __cplusplus
 static_assert(sizeof(SvbUniforms) == 240, "SvbUniforms layout");

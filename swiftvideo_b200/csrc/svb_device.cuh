@@ -39,13 +39,32 @@ __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fm
 #define SVB_K1 __uint_as_float(0x3b808081u)
 #define SVB_K2 __uint_as_float(0xaf7efeffu)
 __device__ __forceinline__ float unorm_f(float c) { return __fmaf_rn(c, SVB_K1, __fmul_rn(c, SVB_K2)); }
-__device__ __forceinline__ float unorm(unsigned c) { return unorm_f((float)c); }
+// Byte loads that hand the compiler an opaque 32-bit value: knowing the 8-bit range it would convert with
+// I2F.U8/U16, which runs on the quarter-rate XU pipe (profiles/: the XU pipe saturated at 149 % before this);
+// an unknown u32 converts with the full-rate I2FP.F32.U32.
+__device__ __forceinline__ unsigned ldg_u8(const uint8_t* p) {
+    unsigned v;
+    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ unsigned opaque(unsigned v) {
+    asm volatile("" : "+r"(v));
+    return v;
+}
+__device__ __forceinline__ float unorm(unsigned c) { return unorm_f(__uint2float_rn(c)); }
 __device__ __forceinline__ float unorm_div(unsigned c) { return __fdiv_rn((float)c, 255.0f); }
 
 // UNORM8 write: convert_uchar_sat_rte(f * 255.0f); NaN -> 0
 __device__ __forceinline__ unsigned rte8(float f) {
     float v = fminf(fmaxf(mul(f, 255.0f), 0.0f), 255.0f);
     return (unsigned)__float2int_rn(v);
+}
+
+// The same write kept as an integer-valued float (no int conversion at all): adding 2^23 rounds to the nearest
+// integer, ties to even, exactly like rint.
+__device__ __forceinline__ float quantf(float f) {
+    const float v = fminf(fmaxf(mul(f, 255.0f), 0.0f), 255.0f);
+    return sub(add(v, 8388608.0f), 8388608.0f);
 }
 
 __device__ __forceinline__ bool in01(float x, float y) { return x >= 0.f && y >= 0.f && x <= 1.f && y <= 1.f; }
@@ -80,19 +99,21 @@ __device__ __forceinline__ float filt(const Taps& k, float t00, float t10, float
 __device__ __forceinline__ float sample1(const uint8_t* __restrict__ p, int stride, int ncomp, int c, const Taps& k) {
     const uint8_t* r0 = p + (size_t)k.j0 * stride + c;
     const uint8_t* r1 = p + (size_t)k.j1 * stride + c;
-    return filt(k, unorm(__ldg(r0 + k.i0 * ncomp)), unorm(__ldg(r0 + k.i1 * ncomp)), unorm(__ldg(r1 + k.i0 * ncomp)),
-                unorm(__ldg(r1 + k.i1 * ncomp)));
+    return filt(k, unorm(ldg_u8(r0 + k.i0 * ncomp)), unorm(ldg_u8(r0 + k.i1 * ncomp)), unorm(ldg_u8(r1 + k.i0 * ncomp)),
+                unorm(ldg_u8(r1 + k.i1 * ncomp)));
 }
 __device__ __forceinline__ float4 sample4(const uint8_t* __restrict__ p, int stride, const Taps& k) {
-    const uchar4 a = __ldg((const uchar4*)(p + (size_t)k.j0 * stride) + k.i0);
-    const uchar4 b = __ldg((const uchar4*)(p + (size_t)k.j0 * stride) + k.i1);
-    const uchar4 c = __ldg((const uchar4*)(p + (size_t)k.j1 * stride) + k.i0);
-    const uchar4 d = __ldg((const uchar4*)(p + (size_t)k.j1 * stride) + k.i1);
+    const unsigned a = __ldg((const unsigned*)(p + (size_t)k.j0 * stride) + k.i0);
+    const unsigned b = __ldg((const unsigned*)(p + (size_t)k.j0 * stride) + k.i1);
+    const unsigned c = __ldg((const unsigned*)(p + (size_t)k.j1 * stride) + k.i0);
+    const unsigned d = __ldg((const unsigned*)(p + (size_t)k.j1 * stride) + k.i1);
     float4 r;
-    r.x = filt(k, unorm(a.x), unorm(b.x), unorm(c.x), unorm(d.x));
-    r.y = filt(k, unorm(a.y), unorm(b.y), unorm(c.y), unorm(d.y));
-    r.z = filt(k, unorm(a.z), unorm(b.z), unorm(c.z), unorm(d.z));
-    r.w = filt(k, unorm(a.w), unorm(b.w), unorm(c.w), unorm(d.w));
+#define SVB_CH(w, n) unorm(opaque(((w) >> (8 * (n))) & 0xffu))
+    r.x = filt(k, SVB_CH(a, 0), SVB_CH(b, 0), SVB_CH(c, 0), SVB_CH(d, 0));
+    r.y = filt(k, SVB_CH(a, 1), SVB_CH(b, 1), SVB_CH(c, 1), SVB_CH(d, 1));
+    r.z = filt(k, SVB_CH(a, 2), SVB_CH(b, 2), SVB_CH(c, 2), SVB_CH(d, 2));
+    r.w = filt(k, SVB_CH(a, 3), SVB_CH(b, 3), SVB_CH(c, 3), SVB_CH(d, 3));
+#undef SVB_CH
     return r;
 }
 
