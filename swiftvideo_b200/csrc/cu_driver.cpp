@@ -53,6 +53,7 @@ static void load() {
     SVB_CU_FN(cuModuleGetFunction)
     SVB_CU_FN(cuFuncSetAttribute)
     SVB_CU_FN(cuFuncGetAttribute)
+    SVB_CU_FN(cuOccupancyMaxActiveBlocksPerMultiprocessor)
     SVB_CU_FN(cuLaunchKernel)
     SVB_CU_FN(cuStreamCreate)
     SVB_CU_FN(cuStreamDestroy)

@@ -141,14 +141,22 @@ __device__ __forceinline__ float2 bilin2(float2 w00, float2 w10, float2 w01, flo
     return add2<PK>(add2<PK>(add2<PK>(mul2<PK>(w00, t00), mul2<PK>(w10, t10), one), mul2<PK>(w01, t01), one), mul2<PK>(w11, t11), one);
 }
 
+#define SVB_TILE_TAB_ENTS (SVB_TILE_W + SVB_TILE_W / 2 + SVB_TILE_H + SVB_TILE_H / 2)  // colY | colC | rowY | rowC of one tile
 struct TiledSmem {
     alignas(128) uint8_t boxY[2][SVB_BOX_Y_BYTES];
     alignas(128) uint8_t boxC[2][SVB_BOX_C_BYTES];
+    alignas(16) Ent tabs[2][SVB_TILE_TAB_ENTS];  // the staged layer's table slices, copied with its boxes
     alignas(8) uint64_t bar[2];
-    int4 plan[SVB_MAX_LAYERS][2];  // [l][0] = (mode, iy0, jy0, ic0), [l][1] = (jc0, 0, 0, 0)
+    int4 plan[2][SVB_MAX_LAYERS][2];  // [tile parity][l][0] = (mode, iy0, jy0, ic0), [..][1] = (jc0, 0, 0, 0)
 };
 static_assert(sizeof(TiledSmem) <= SVB_TILED_SMEM_BYTES, "SVB_TILED_SMEM_BYTES (svb_desc.h) must cover TiledSmem");
-enum { PLAN_SKIP = 0, PLAN_GENERIC = 1, PLAN_EDGE = 2, PLAN_DIRECT = 3, PLAN_STAGED = 4 };
+enum { PLAN_SKIP = 0, PLAN_GENERIC = 1, PLAN_STAGED = 4, PLAN_STAGED_EDGE = 5 };  // >= PLAN_STAGED: boxes come by TMA
+
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, uint64_t* bar) {  // 16-byte granules
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 
 __device__ __forceinline__ Ent ld_ent(const Ent* __restrict__ p) {
     const int4 v = __ldg(reinterpret_cast<const int4*>(p));
@@ -179,29 +187,53 @@ __device__ __forceinline__ Tabs layer_tabs(const Ent* __restrict__ tables, const
     return t;
 }
 
-// One separable YUV layer over a tile that lies wholly inside the picture, taps staged in shared memory.
+// One separable YUV layer over one tile, taps staged in shared memory.
 //   Yi / Ui / Vi: the running picture as integer-valued floats; pairs hold two horizontally adjacent samples.
-template <bool UNIT, bool CLAMP, bool PK>
-__device__ __forceinline__ void fast_layer(unsigned boxY, unsigned boxU, unsigned boxV, const Tabs& tb, int xt, int yt, int H, int iy0, int jy0,
-                                           int ic0, int jc0, int pitchY, int pitchC, int stepC, float alpha, float onef,
+//   MODE 0: tile wholly inside the picture, opacity == 1 (cur*(1-1) + v*1 == v exactly: no blend)
+//   MODE 1: tile wholly inside the picture, 0 <= opacity <= 1 (blended values stay in [0,1]: no store clamp)
+//   MODE 2: anything: per-pixel class from the tables' ok bits -- picture / fill / untouched
+//           (kernels.cl.swift:77,84-85,96-105) -- and saturating stores
+struct FillTerms {
+    float2 fy, fu, fv, af, naf;  // RGB2YUV(fillColor.rgb, 1) splat; opacity*fillColor.w and its complement
+};
+template <int MODE, bool PK>
+__device__ __forceinline__ void fast_layer(unsigned boxY, unsigned boxU, unsigned boxV, const Ent* __restrict__ tabs, int lane, int warp, int lastr, int iy0, int jy0,
+                                           int ic0, int jc0, int pitchY, int pitchC, int stepC, float alpha, float onef, const FillTerms& ft,
                                            float2 (&Yi)[4][2], float2 (&Ui)[2], float2 (&Vi)[2]) {
+    constexpr bool UNIT = MODE == 0, GEN = MODE == 2;
     const float2 AL = splat(alpha), NAL = splat(sub(1.f, alpha)), ONE = splat(onef);
     unsigned o0[4], o1[4];
+    int okc[4];
     float2 A[2], NA[2];
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
-        const Ent e0 = ld_ent(tb.colY + xt + 2 * p), e1 = ld_ent(tb.colY + xt + 2 * p + 1);
+        const Ent e0 = tabs[4 * lane + 2 * p], e1 = tabs[4 * lane + 2 * p + 1];
         o0[2 * p] = boxY + (e0.i0 - iy0), o1[2 * p] = boxY + (e0.i1 - iy0);
         o0[2 * p + 1] = boxY + (e1.i0 - iy0), o1[2 * p + 1] = boxY + (e1.i1 - iy0);
+        okc[2 * p] = e0.ok, okc[2 * p + 1] = e1.ok;
         A[p] = make_float2(e0.a, e1.a);
         NA[p] = make_float2(sub(1.f, e0.a), sub(1.f, e1.a));
     }
-    const Ent c0 = ld_ent(tb.colC + (xt >> 1)), c1 = ld_ent(tb.colC + (xt >> 1) + 1);
+    const Ent c0 = tabs[SVB_TILE_W + 2 * lane], c1 = tabs[SVB_TILE_W + 2 * lane + 1];
     const unsigned oc00 = (c0.i0 - ic0) * stepC, oc01 = (c0.i1 - ic0) * stepC, oc10 = (c1.i0 - ic0) * stepC, oc11 = (c1.i1 - ic0) * stepC;
     const float2 AC = make_float2(c0.a, c1.a), NAC = make_float2(sub(1.f, c0.a), sub(1.f, c1.a));
+    // blend -> UNORM8 write -> the next layer's UNORM8 read stays an integer-valued float
+    auto settle = [&](float2 cur_i, float2 v, float2 fillc, float lo, int ok0, int ok1) -> float2 {
+        if (UNIT) return quant2<false, PK>(v, ONE);
+        const float2 cur = unorm2<PK>(cur_i);
+        const float2 qi = quant2<GEN, PK>(add2<PK>(mul2<PK>(cur, NAL), mul2<PK>(v, AL), ONE), ONE);
+        if (!GEN) return qi;
+        float2 rf = add2<PK>(mul2<PK>(cur, ft.naf), mul2<PK>(fillc, ft.af), ONE);
+        rf.x = fminf(fmaxf(rf.x, lo), 1.f), rf.y = fminf(fmaxf(rf.y, lo), 1.f);
+        const float2 qf = quant2<true, PK>(rf, ONE);
+        float2 out;
+        out.x = ok0 == 7 ? qi.x : ((ok0 & 1) ? qf.x : cur_i.x);
+        out.y = ok1 == 7 ? qi.y : ((ok1 & 1) ? qf.y : cur_i.y);
+        return out;
+    };
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        const Ent ry = ld_ent(tb.rowY + min(yt + r, H - 1));  // rows past the frame's bottom are computed and dropped
+        const Ent ry = tabs[SVB_TILE_W + SVB_TILE_W / 2 + min(4 * warp + r, lastr)];  // rows past the frame's bottom are computed and dropped
         const unsigned r0 = (ry.i0 - jy0) * pitchY, r1 = (ry.i1 - jy0) * pitchY;
         const float2 B = splat(ry.a), NB = splat(sub(1.f, ry.a));
 #pragma unroll
@@ -212,12 +244,11 @@ __device__ __forceinline__ void fast_layer(unsigned boxY, unsigned boxU, unsigne
             const float2 t01 = unorm2<PK>(bytes2(lds_u8(r1 + a0), lds_u8(r1 + b0)));
             const float2 t11 = unorm2<PK>(bytes2(lds_u8(r1 + a1), lds_u8(r1 + b1)));
             const float2 v = bilin2<PK>(mul2<PK>(NA[p], NB), mul2<PK>(A[p], NB), mul2<PK>(NA[p], B), mul2<PK>(A[p], B), t00, t10, t01, t11, ONE);
-            const float2 res = UNIT ? v : add2<PK>(mul2<PK>(unorm2<PK>(Yi[r][p]), NAL), mul2<PK>(v, AL), ONE);
-            Yi[r][p] = quant2<CLAMP, PK>(res, ONE);
+            Yi[r][p] = settle(Yi[r][p], v, ft.fy, 0.f, okc[2 * p] & ry.ok, okc[2 * p + 1] & ry.ok);
         }
         if ((r & 1) == 0) {
             const int k = r >> 1;
-            const Ent rc = ld_ent(tb.rowC + min((yt >> 1) + k, (H >> 1) - 1));
+            const Ent rc = tabs[SVB_TILE_W + SVB_TILE_W / 2 + SVB_TILE_H + min(2 * warp + k, lastr >> 1)];
             const unsigned q0 = (rc.i0 - jc0) * pitchC, q1 = (rc.i1 - jc0) * pitchC;
             const float2 BC = splat(rc.a), NBC = splat(sub(1.f, rc.a));
             const float2 w00 = mul2<PK>(NAC, NBC), w10 = mul2<PK>(AC, NBC), w01 = mul2<PK>(NAC, BC), w11 = mul2<PK>(AC, BC);
@@ -226,77 +257,29 @@ __device__ __forceinline__ void fast_layer(unsigned boxY, unsigned boxU, unsigne
                                         unorm2<PK>(bytes2(lds_u8(u1 + oc00), lds_u8(u1 + oc10))), unorm2<PK>(bytes2(lds_u8(u1 + oc01), lds_u8(u1 + oc11))), ONE);
             const float2 v = bilin2<PK>(w00, w10, w01, w11, unorm2<PK>(bytes2(lds_u8(v0 + oc00), lds_u8(v0 + oc10))), unorm2<PK>(bytes2(lds_u8(v0 + oc01), lds_u8(v0 + oc11))),
                                         unorm2<PK>(bytes2(lds_u8(v1 + oc00), lds_u8(v1 + oc10))), unorm2<PK>(bytes2(lds_u8(v1 + oc01), lds_u8(v1 + oc11))), ONE);
-            Ui[k] = quant2<CLAMP, PK>(UNIT ? u : add2<PK>(mul2<PK>(unorm2<PK>(Ui[k]), NAL), mul2<PK>(u, AL), ONE), ONE);
-            Vi[k] = quant2<CLAMP, PK>(UNIT ? v : add2<PK>(mul2<PK>(unorm2<PK>(Vi[k]), NAL), mul2<PK>(v, AL), ONE), ONE);
+            Ui[k] = settle(Ui[k], u, ft.fu, -1.f, c0.ok & rc.ok, c1.ok & rc.ok);
+            Vi[k] = settle(Vi[k], v, ft.fv, -1.f, c0.ok & rc.ok, c1.ok & rc.ok);
         }
     }
 }
 
-// A separable YUV layer through the tables with taps straight from the planes: tiles that straddle the picture's
-// edge (per-pixel class from the ok bits: picture / fill / untouched, kernels.cl.swift:77,84-85,96-105) and tiles
-// whose footprint is too large to stage.  Scalar arithmetic in the reference's own order.
-__device__ __forceinline__ void table_layer(const SvbLayerDesc* __restrict__ L, const Tabs& tb, int xt, int yt, int H,
-                                            float2 (&Yi)[4][2], float2 (&Ui)[2], float2 (&Vi)[2]) {
-    const uint8_t* __restrict__ pY = (const uint8_t*)L->plane[0];
-    const uint8_t* __restrict__ pU = (const uint8_t*)L->plane[1];
-    const bool nv12 = L->format == SVB_NV12;
-    const uint8_t* __restrict__ pV = nv12 ? pU + 1 : (const uint8_t*)L->plane[2];
-    const int pitchY = L->stride[0], pitchC = L->stride[1], stepC = nv12 ? 2 : 1;
-    const float alpha = L->u.opacity, nalpha = sub(1.f, alpha);
-    const float4 fc = ldrow(L->u.fillColor, 0);
-    const float3 fill = rgb2yuv(fc.x, fc.y, fc.z);
-    const float af = mul(alpha, fc.w), naf = sub(1.f, af);
-    Ent cy[4], cc[2];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) cy[c] = ld_ent(tb.colY + xt + c);
-#pragma unroll
-    for (int c = 0; c < 2; ++c) cc[c] = ld_ent(tb.colC + (xt >> 1) + c);
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
+// Any layer, any tile: the per-pixel evaluator of svb_device.cuh over this thread's 4x4 block.  Kept compact (one
+// copy of the evaluator, pixels in a rolled loop over a local copy of the block) so that it does not crowd the
+// instruction cache of the fast path; rotated layers, BGRA/RGBA sources and footprints too large to stage come here.
+__device__ __noinline__ void generic_layer(const SvbLayerDesc* __restrict__ L, int xt, int yt, float fW, float fH, int H, float* __restrict__ st) {
+    const Src s = layer_src(L);
+    const SvbUniforms* __restrict__ U = &L->u;
+#pragma unroll 1
+    for (int q = 0; q < 16; ++q) {
+        const int r = q >> 2, c = q & 3;
         if (yt + r >= H) break;
-        const Ent ry = ld_ent(tb.rowY + yt + r);
-        const float b = ry.a, nb = sub(1.f, b);
-        const uint8_t* q0 = pY + (size_t)ry.i0 * pitchY;
-        const uint8_t* q1 = pY + (size_t)ry.i1 * pitchY;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int ok = cy[c].ok & ry.ok;
-            float& dst = (c & 1) ? Yi[r][c >> 1].y : Yi[r][c >> 1].x;
-            if (ok == 7) {
-                const float a = cy[c].a, na = sub(1.f, a);
-                const float v = add(add(add(mul(mul(na, nb), unorm(ldg_u8(q0 + cy[c].i0))), mul(mul(a, nb), unorm(ldg_u8(q0 + cy[c].i1)))),
-                                        mul(mul(na, b), unorm(ldg_u8(q1 + cy[c].i0)))),
-                                    mul(mul(a, b), unorm(ldg_u8(q1 + cy[c].i1))));
-                dst = quantf(add(mul(unorm_f(dst), nalpha), mul(v, alpha)));
-            } else if (ok & 1) {
-                dst = quantf(clampf(add(mul(unorm_f(dst), naf), mul(fill.x, af)), 0.f, 1.f));
-            }
-        }
-        if ((r & 1) == 0) {
-            const int k = r >> 1;
-            const Ent rc = ld_ent(tb.rowC + (yt >> 1) + k);
-            const float bb = rc.a, nbb = sub(1.f, bb);
-            const size_t z0 = (size_t)rc.i0 * pitchC, z1 = (size_t)rc.i1 * pitchC;
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const int ok = cc[c].ok & rc.ok;
-                float& du = c ? Ui[k].y : Ui[k].x;
-                float& dv = c ? Vi[k].y : Vi[k].x;
-                if (ok == 7) {
-                    const float a = cc[c].a, na = sub(1.f, a);
-                    const float w00 = mul(na, nbb), w10 = mul(a, nbb), w01 = mul(na, bb), w11 = mul(a, bb);
-                    const int e0 = cc[c].i0 * stepC, e1 = cc[c].i1 * stepC;
-                    const float vu = add(add(add(mul(w00, unorm(ldg_u8(pU + z0 + e0))), mul(w10, unorm(ldg_u8(pU + z0 + e1)))), mul(w01, unorm(ldg_u8(pU + z1 + e0)))),
-                                         mul(w11, unorm(ldg_u8(pU + z1 + e1))));
-                    const float vv = add(add(add(mul(w00, unorm(ldg_u8(pV + z0 + e0))), mul(w10, unorm(ldg_u8(pV + z0 + e1)))), mul(w01, unorm(ldg_u8(pV + z1 + e0)))),
-                                         mul(w11, unorm(ldg_u8(pV + z1 + e1))));
-                    du = quantf(add(mul(unorm_f(du), nalpha), mul(vu, alpha)));
-                    dv = quantf(add(mul(unorm_f(dv), nalpha), mul(vv, alpha)));
-                } else if (ok & 1) {
-                    du = quantf(clampf(add(mul(unorm_f(du), naf), mul(fill.y, af)), -1.f, 1.f));
-                    dv = quantf(clampf(add(mul(unorm_f(dv), naf), mul(fill.z, af)), -1.f, 1.f));
-                }
-            }
+        const bool chroma = ((r | c) & 1) == 0;
+        const int ci = 16 + (r >> 1) * 2 + (c >> 1);  // st[16..19] = U texels, st[20..23] = V texels
+        float oy, ou, ov;
+        if (eval_pixel(U, s, xt + c, yt + r, fW, fH, chroma, unorm_f(st[q]), chroma ? unorm_f(st[ci]) : 0.f, chroma ? unorm_f(st[ci + 4]) : 0.f, oy, ou,
+                       ov)) {
+            st[q] = quantf(oy);
+            if (chroma) st[ci] = quantf(ou), st[ci + 4] = quantf(ov);
         }
     }
 }
@@ -331,7 +314,62 @@ extern "C" __global__ void __launch_bounds__(256) svb_mix_tables(const SvbFrameD
     }
 }
 
-extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, 2)
+#ifndef SVB_TILED_MIN_CTAS
+#define SVB_TILED_MIN_CTAS 2
+#endif
+
+namespace svb {
+
+struct TileGeo {
+    const SvbFrameDesc* F;
+    int x0, y0, lastc, lastr;
+};
+__device__ __forceinline__ TileGeo tile_geo(const SvbFrameDesc* __restrict__ frames, int nframes, int& f, int tile) {
+    while (f + 1 < nframes && frames[f + 1].first_tile <= tile) ++f;
+    TileGeo g;
+    g.F = frames + f;
+    const int local = tile - g.F->first_tile;
+    g.x0 = (local % g.F->tiles_x) * SVB_TILE_W;
+    g.y0 = (local / g.F->tiles_x) * SVB_TILE_H;
+    g.lastc = min(SVB_TILE_W, g.F->width - g.x0) - 1;
+    g.lastr = min(SVB_TILE_H, g.F->height - g.y0) - 1;
+    return g;
+}
+
+// Plan of layer `l` on one tile (executed by one thread per layer).
+__device__ __forceinline__ void plan_layer(const Ent* __restrict__ tables, const TileGeo& g, int l, int4* __restrict__ out) {
+    const SvbFrameDesc* __restrict__ F = g.F;
+    const SvbLayerDesc* __restrict__ L = &F->layers[l];
+    const int x0 = g.x0, y0 = g.y0;
+    int mode, iy0 = 0, jy0 = 0, ic0 = 0, jc0 = 0;
+    if (L->rect[0] >= x0 + SVB_TILE_W || L->rect[2] <= x0 || L->rect[1] >= y0 + SVB_TILE_H || L->rect[3] <= y0) {
+        mode = PLAN_SKIP;
+    } else if (!(L->flags & SVB_LAYER_SEPARABLE) || (L->format != SVB_NV12 && L->format != SVB_Y420P)) {
+        mode = PLAN_GENERIC;
+    } else {
+        const Tabs tb = layer_tabs(tables, F, l);
+        const Ent cA = ld_ent(tb.colY + x0), cB = ld_ent(tb.colY + x0 + g.lastc), rA = ld_ent(tb.rowY + y0), rB = ld_ent(tb.rowY + y0 + g.lastr);
+        const Ent ccA = ld_ent(tb.colC + (x0 >> 1)), ccB = ld_ent(tb.colC + ((x0 + g.lastc) >> 1));
+        const Ent rcA = ld_ent(tb.rowC + (y0 >> 1)), rcB = ld_ent(tb.rowC + ((y0 + g.lastr) >> 1));
+        // source footprint of the tile: the clamped tap indices are monotone along each axis, so the ends bound it;
+        // x origins are rounded down to 16 bytes for TMA
+        iy0 = min(cA.i0, cB.i0) & ~15;
+        jy0 = min(rA.i0, rB.i0);
+        ic0 = min(ccA.i0, ccB.i0) & (L->format == SVB_NV12 ? ~7 : ~15);
+        jc0 = min(rcA.i0, rcB.i0);
+        const bool fits = max(cA.i1, cB.i1) - iy0 < L->box_w && max(rA.i1, rB.i1) - jy0 < L->box_h && max(ccA.i1, ccB.i1) - ic0 < L->box_cw &&
+                          max(rcA.i1, rcB.i1) - jc0 < L->box_ch;
+        // border, tx and uv are monotone too: both ends inside [0,1] means every pixel of the tile is inside the picture
+        const bool full = cA.ok == 7 && cB.ok == 7 && rA.ok == 7 && rB.ok == 7;
+        mode = !((L->flags & SVB_LAYER_STAGED) && fits) ? PLAN_GENERIC : (full ? PLAN_STAGED : PLAN_STAGED_EDGE);
+    }
+    out[0] = make_int4(mode, iy0, jy0, ic0);
+    out[1] = make_int4(jc0, 0, 0, 0);
+}
+
+}  // namespace svb
+
+extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CTAS)
     svb_mix_tiled(const SvbFrameDesc* __restrict__ frames, const svb::Ent* __restrict__ tables, int nframes, int total_tiles, float one) {
     using namespace svb;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -343,15 +381,20 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, 2)
         mbar_init(&sm.bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    int f = 0, fnext = 0, cur = 0;
+    int stage = 0;        // box buffer that holds (or is about to receive) the next staged layer to consume
+    bool primed = false;  // this tile's first staged layer was already put in flight by the previous tile
+    if (blockIdx.x < total_tiles) {
+        const TileGeo g0 = tile_geo(frames, nframes, fnext, blockIdx.x);
+        if (t < g0.F->nlayers) plan_layer(tables, g0, t, sm.plan[0][t]);
+    }
     __syncthreads();
-    int f = 0;
 
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        while (f + 1 < nframes && frames[f + 1].first_tile <= tile) ++f;
-        const SvbFrameDesc* __restrict__ F = frames + f;
-        const int local = tile - F->first_tile;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, cur ^= 1) {
+        const TileGeo g = tile_geo(frames, nframes, f, tile);
+        const SvbFrameDesc* __restrict__ F = g.F;
         const int W = F->width, H = F->height, nl = F->nlayers;
-        const int x0 = (local % F->tiles_x) * SVB_TILE_W, y0 = (local / F->tiles_x) * SVB_TILE_H;
+        const int x0 = g.x0, y0 = g.y0, lastr = g.lastr;
         const int xt = x0 + 4 * lane, yt = y0 + 4 * warp;  // this thread's 4x4 block
         const bool live = xt < W && yt < H;                 // W % 4 == 0 and H even are planner preconditions
         const bool nv12 = F->format == SVB_NV12;
@@ -360,37 +403,47 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, 2)
         uint8_t* const oU = (uint8_t*)F->out_plane[1];
         uint8_t* const oV = (uint8_t*)F->out_plane[2];
         const int sY = F->out_stride[0], sU = F->out_stride[1], sV = F->out_stride[2];
-        const int lastc = min(SVB_TILE_W, W - x0) - 1, lastr = min(SVB_TILE_H, H - y0) - 1;
+        const int4(*plan)[2] = sm.plan[cur];
 
-        // ---- plan: one thread per layer --------------------------------------------------------------------------
-        if (t < nl) {
-            const SvbLayerDesc* __restrict__ L = &F->layers[t];
-            int mode, iy0 = 0, jy0 = 0, ic0 = 0, jc0 = 0;
-            if (L->rect[0] >= x0 + SVB_TILE_W || L->rect[2] <= x0 || L->rect[1] >= y0 + SVB_TILE_H || L->rect[3] <= y0) {
-                mode = PLAN_SKIP;
-            } else if (!(L->flags & SVB_LAYER_SEPARABLE) || (L->format != SVB_NV12 && L->format != SVB_Y420P)) {
-                mode = PLAN_GENERIC;
-            } else {
-                const Tabs tb = layer_tabs(tables, F, t);
-                const Ent cA = ld_ent(tb.colY + x0), cB = ld_ent(tb.colY + x0 + lastc), rA = ld_ent(tb.rowY + y0), rB = ld_ent(tb.rowY + y0 + lastr);
-                // border, tx and uv are monotone along each axis: both ends inside [0,1] means everything between is
-                if (cA.ok == 7 && cB.ok == 7 && rA.ok == 7 && rB.ok == 7) {
-                    // source footprint of the tile (indices are monotone too); x origins rounded down to 16 bytes for TMA
-                    const Ent ccA = ld_ent(tb.colC + (x0 >> 1)), ccB = ld_ent(tb.colC + ((x0 + lastc) >> 1));
-                    const Ent rcA = ld_ent(tb.rowC + (y0 >> 1)), rcB = ld_ent(tb.rowC + ((y0 + lastr) >> 1));
-                    iy0 = min(cA.i0, cB.i0) & ~15;
-                    jy0 = min(rA.i0, rB.i0);
-                    ic0 = min(ccA.i0, ccB.i0) & (L->format == SVB_NV12 ? ~7 : ~15);
-                    jc0 = min(rcA.i0, rcB.i0);
-                    const bool fits = max(cA.i1, cB.i1) - iy0 < L->box_w && max(rA.i1, rB.i1) - jy0 < L->box_h &&
-                                      max(ccA.i1, ccB.i1) - ic0 < L->box_cw && max(rcA.i1, rcB.i1) - jc0 < L->box_ch;
-                    mode = ((L->flags & SVB_LAYER_STAGED) && fits) ? PLAN_STAGED : PLAN_DIRECT;
-                } else {
-                    mode = PLAN_EDGE;
-                }
-            }
-            sm.plan[t][0] = make_int4(mode, iy0, jy0, ic0);
-            sm.plan[t][1] = make_int4(jc0, 0, 0, 0);
+        // TMA of one staged layer into buffer `b`: the source boxes and the tile's slices of the coordinate tables
+        auto issue = [&](const TileGeo& tg, const int4(*pl)[2], int l, int b) {
+            const SvbFrameDesc* __restrict__ TF = tg.F;
+            const SvbLayerDesc* __restrict__ L = &TF->layers[l];
+            const int4 p0 = pl[l][0], p1 = pl[l][1];
+            const bool n12 = L->format == SVB_NV12;
+            const int cbytes = n12 ? L->box_cw * L->box_ch * 2 : L->box_cw * L->box_ch;
+            const int ncy = tg.lastc + 1, nry = tg.lastr + 1;
+            const Tabs tb = layer_tabs(tables, TF, l);
+            tmap_acquire(L->tmap[0]);
+            tmap_acquire(L->tmap[1]);
+            if (!n12) tmap_acquire(L->tmap[2]);
+            mbar_expect_tx(&sm.bar[b], L->box_w * L->box_h + cbytes * (n12 ? 1 : 2) + (ncy + ncy / 2 + nry + nry / 2) * (int)sizeof(Ent));
+            tma_load_2d(sm.boxY[b], L->tmap[0], p0.y, p0.z, &sm.bar[b]);
+            tma_load_2d(sm.boxC[b], L->tmap[1], p0.w, p1.x, &sm.bar[b]);
+            if (!n12) tma_load_2d(sm.boxC[b] + SVB_BOX_C_BYTES / 2, L->tmap[2], p0.w, p1.x, &sm.bar[b]);
+            Ent* dst = sm.tabs[b];
+            bulk_load(dst, tb.colY + tg.x0, ncy * sizeof(Ent), &sm.bar[b]);
+            bulk_load(dst + SVB_TILE_W, tb.colC + (tg.x0 >> 1), (ncy / 2) * sizeof(Ent), &sm.bar[b]);
+            bulk_load(dst + SVB_TILE_W + SVB_TILE_W / 2, tb.rowY + tg.y0, nry * sizeof(Ent), &sm.bar[b]);
+            bulk_load(dst + SVB_TILE_W + SVB_TILE_W / 2 + SVB_TILE_H, tb.rowC + (tg.y0 >> 1), (nry / 2) * sizeof(Ent), &sm.bar[b]);
+        };
+        // first staged layer of `pl`, or -1
+        auto first_staged = [&](const int4(*pl)[2], int from, int n) {
+            for (int l = from; l < n; ++l)
+                if (pl[l][0].x >= PLAN_STAGED) return l;
+            return -1;
+        };
+        if (!primed && t == 0) {
+            const int l = first_staged(plan, 0, nl);
+            if (l >= 0) issue(g, plan, l, stage);
+        }
+        primed = false;
+        // plan of this CTA's next tile, off the critical path (its loads overlap the copy in flight)
+        const bool has_next = tile + (int)gridDim.x < total_tiles;
+        TileGeo gn = g;
+        if (has_next) {
+            gn = tile_geo(frames, nframes, fnext, tile + gridDim.x);
+            if (t < gn.F->nlayers) plan_layer(tables, gn, t, sm.plan[cur ^ 1][t]);
         }
 
         // ---- running picture: integer-valued floats ------------------------------------------------------------
@@ -418,44 +471,27 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, 2)
                     }
                 }
         }
-        __syncthreads();  // plan visible; nobody still reads the boxes of the previous tile
-
-        // TMA of one staged layer into box buffer `b`
-        auto issue = [&](int l, int b) {
-            const SvbLayerDesc* __restrict__ L = &F->layers[l];
-            const int4 p0 = sm.plan[l][0], p1 = sm.plan[l][1];
-            const bool n12 = L->format == SVB_NV12;
-            const int cbytes = n12 ? L->box_cw * L->box_ch * 2 : L->box_cw * L->box_ch;
-            tmap_acquire(L->tmap[0]);
-            tmap_acquire(L->tmap[1]);
-            if (!n12) tmap_acquire(L->tmap[2]);
-            mbar_expect_tx(&sm.bar[b], L->box_w * L->box_h + cbytes * (n12 ? 1 : 2));
-            tma_load_2d(sm.boxY[b], L->tmap[0], p0.y, p0.z, &sm.bar[b]);
-            tma_load_2d(sm.boxC[b], L->tmap[1], p0.w, p1.x, &sm.bar[b]);
-            if (!n12) tma_load_2d(sm.boxC[b] + SVB_BOX_C_BYTES / 2, L->tmap[2], p0.w, p1.x, &sm.bar[b]);
-        };
-        int stage = 0;
-        if (t == 0)
-            for (int l = 0; l < nl; ++l)
-                if (sm.plan[l][0].x == PLAN_STAGED) {
-                    issue(l, 0);
-                    break;
-                }
 
         for (int l = 0; l < nl; ++l) {
-            const int4 p0 = sm.plan[l][0];
+            const int4 p0 = plan[l][0];
             const int mode = p0.x;
             if (mode == PLAN_SKIP) continue;
             const SvbLayerDesc* __restrict__ L = &F->layers[l];
-            if (mode == PLAN_STAGED) {
-                const int jc0 = sm.plan[l][1].x;
-                __syncthreads();  // every warp is past its reads of the other buffer: it may be refilled
-                if (t == 0)
-                    for (int j = l + 1; j < nl; ++j)
-                        if (sm.plan[j][0].x == PLAN_STAGED) {
-                            issue(j, stage ^ 1);
-                            break;
+            if (mode >= PLAN_STAGED) {
+                const int jc0 = plan[l][1].x;
+                __syncthreads();  // every warp is past its reads of the other buffer (and the next tile's plan is written)
+                {   // refill the other buffer: the next staged layer of this tile, else the first one of the next tile
+                    const int j = first_staged(plan, l + 1, nl);
+                    if (j >= 0) {
+                        if (t == 0) issue(g, plan, j, stage ^ 1);
+                    } else if (has_next) {
+                        const int jn = first_staged(sm.plan[cur ^ 1], 0, gn.F->nlayers);
+                        if (jn >= 0) {
+                            if (t == 0) issue(gn, sm.plan[cur ^ 1], jn, stage ^ 1);
+                            primed = true;
                         }
+                    }
+                }
                 if (stage == 0) {
                     mbar_wait(&sm.bar[0], phase0);
                     phase0 ^= 1;
@@ -464,51 +500,38 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, 2)
                     phase1 ^= 1;
                 }
                 if (live) {
-                    const Tabs tb = layer_tabs(tables, F, l);
                     const int fmt = L->format, lflags = L->flags;
                     const int pitchC = fmt == SVB_NV12 ? L->box_cw * 2 : L->box_cw, stepC = fmt == SVB_NV12 ? 2 : 1;
                     const unsigned bY = smem_u32(sm.boxY[stage]), bU = smem_u32(sm.boxC[stage]);
                     const unsigned bV = bU + (fmt == SVB_NV12 ? 1 : SVB_BOX_C_BYTES / 2);
                     const float alpha = L->u.opacity;
-#define SVB_FAST(UNIT, CLAMP, PK) \
-    fast_layer<UNIT, CLAMP, PK>(bY, bU, bV, tb, xt, yt, H, p0.y, p0.z, p0.w, jc0, L->box_w, pitchC, stepC, alpha, one, Yi, Ui, Vi)
-                    if (F->flags & SVB_FRAME_SCALAR_FP) {
-                        if (lflags & SVB_LAYER_UNIT_OPACITY) SVB_FAST(true, false, false);
-                        else if (lflags & SVB_LAYER_OPACITY_01) SVB_FAST(false, false, false);
-                        else SVB_FAST(false, true, false);
+                    FillTerms ft;
+                    if (mode == PLAN_STAGED_EDGE || !(lflags & SVB_LAYER_OPACITY_01)) {
+                        const float4 fc = ldrow(L->u.fillColor, 0);
+                        const float3 fill = rgb2yuv(fc.x, fc.y, fc.z);
+                        const float af = mul(alpha, fc.w);
+                        ft.fy = splat(fill.x), ft.fu = splat(fill.y), ft.fv = splat(fill.z), ft.af = splat(af), ft.naf = splat(sub(1.f, af));
+                        fast_layer<2, true>(bY, bU, bV, sm.tabs[stage], lane, warp, lastr, p0.y, p0.z, p0.w, jc0, L->box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
+                    } else if (lflags & SVB_LAYER_UNIT_OPACITY) {
+                        fast_layer<0, true>(bY, bU, bV, sm.tabs[stage], lane, warp, lastr, p0.y, p0.z, p0.w, jc0, L->box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
                     } else {
-                        if (lflags & SVB_LAYER_UNIT_OPACITY) SVB_FAST(true, false, true);
-                        else if (lflags & SVB_LAYER_OPACITY_01) SVB_FAST(false, false, true);
-                        else SVB_FAST(false, true, true);
+                        fast_layer<1, true>(bY, bU, bV, sm.tabs[stage], lane, warp, lastr, p0.y, p0.z, p0.w, jc0, L->box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
                     }
-#undef SVB_FAST
                 }
                 stage ^= 1;
             } else if (!live) {
                 continue;
-            } else if (mode == PLAN_EDGE || mode == PLAN_DIRECT) {
-                table_layer(L, layer_tabs(tables, F, l), xt, yt, H, Yi, Ui, Vi);
             } else {
-                // ---- generic per-pixel evaluation of this layer on this thread's 4x4 block ----------------------
-                const Src s = layer_src(L);
-                const SvbUniforms* __restrict__ U = &L->u;
+                float st[24];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
+                for (int r = 0; r < 4; ++r) st[4 * r] = Yi[r][0].x, st[4 * r + 1] = Yi[r][0].y, st[4 * r + 2] = Yi[r][1].x, st[4 * r + 3] = Yi[r][1].y;
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const bool chroma = ((r | c) & 1) == 0;
-                        const int k = r >> 1;
-                        float& py = (c & 1) ? Yi[r][c >> 1].y : Yi[r][c >> 1].x;
-                        float& pu = (c >> 1) ? Ui[k].y : Ui[k].x;
-                        float& pv = (c >> 1) ? Vi[k].y : Vi[k].x;
-                        float oy, ou, ov;
-                        if (yt + r < H && eval_pixel(U, s, xt + c, yt + r, fW, fH, chroma, unorm_f(py), chroma ? unorm_f(pu) : 0.f,
-                                                     chroma ? unorm_f(pv) : 0.f, oy, ou, ov)) {
-                            py = quantf(oy);
-                            if (chroma) pu = quantf(ou), pv = quantf(ov);
-                        }
-                    }
-                }
+                for (int k = 0; k < 2; ++k) st[16 + 2 * k] = Ui[k].x, st[17 + 2 * k] = Ui[k].y, st[20 + 2 * k] = Vi[k].x, st[21 + 2 * k] = Vi[k].y;
+                generic_layer(L, xt, yt, fW, fH, H, st);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) Yi[r][0] = make_float2(st[4 * r], st[4 * r + 1]), Yi[r][1] = make_float2(st[4 * r + 2], st[4 * r + 3]);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) Ui[k] = make_float2(st[16 + 2 * k], st[17 + 2 * k]), Vi[k] = make_float2(st[20 + 2 * k], st[21 + 2 * k]);
             }
         }
 
@@ -527,6 +550,6 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, 2)
                     }
                 }
         }
-        __syncthreads();  // the plan and the boxes are rewritten by the next tile
+        __syncthreads();  // the next tile's plan is visible; the boxes are free
     }
 }

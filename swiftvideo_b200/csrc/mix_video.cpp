@@ -32,6 +32,7 @@ struct MixerShared {
     int next = 0;
     std::map<std::array<uint64_t, 4>, std::array<uint8_t, 128>> tmaps;
     CUfunction fTiled = nullptr, fGeneric = nullptr, fTables = nullptr;
+    int tiledCtasPerSm = 2;  // resident CTAs of svb_mix_tiled per SM: the persistent grid is smCount times this
     std::mutex mu;
     // optional per-launch device timing of the fused kernels (bench.py's roofline leg)
     bool timing = false;
@@ -82,6 +83,9 @@ MixerShared& shared(const std::shared_ptr<InternalContext>& ic) {  // caller hol
         check(drv().cuFuncSetAttribute(s->fTiled, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, SVB_TILED_SMEM_BYTES),
               "cuFuncSetAttribute(max dynamic shared memory)");
         s->fTables = ic->builtin("svb_mix_tables");
+        int perSm = 0;
+        check(drv().cuOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, s->fTiled, 256, SVB_TILED_SMEM_BYTES), "cuOccupancyMaxActiveBlocksPerMultiprocessor");
+        s->tiledCtasPerSm = std::max(1, perSm);
         s->fGeneric = ic->builtin("svb_mix_generic");
     }
     return *(MixerShared*)ic->mixerShared;
@@ -309,7 +313,7 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
             int nframes = n;
             float one = 1.0f;  // see add2() in kernels_tiled.cuh
             void* args[] = {&dev, &tables, &nframes, &total, &one};
-            const unsigned grid = (unsigned)std::min(total, ic.smCount * 2);
+            const unsigned grid = (unsigned)std::min(total, ic.smCount * sh.tiledCtasPerSm);
             check(d.cuLaunchKernel(sh.fTiled, grid, 1, 1, 256, 1, 1, SVB_TILED_SMEM_BYTES, ic.compute, args, nullptr), "cuLaunchKernel(svb_mix_tiled)");
             noteKernelLaunch();
             ic.release(tables, tableBytes);  // recycled only after the streams have drained past this point

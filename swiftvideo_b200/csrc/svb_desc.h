@@ -68,8 +68,9 @@ typedef struct __attribute__((aligned(64))) SvbFrameDesc {
     SvbLayerDesc layers[SVB_MAX_LAYERS];
 } SvbFrameDesc;
 
-// dynamic shared memory of svb_mix_tiled: two staged box pairs, two mbarriers, one 32-byte plan per layer
-#define SVB_TILED_SMEM_BYTES (2 * SVB_BOX_Y_BYTES + 2 * SVB_BOX_C_BYTES + 128 + SVB_MAX_LAYERS * 32)
+// dynamic shared memory of svb_mix_tiled: two staged box pairs, two table slices (240 entries of 16 bytes), two
+// mbarriers, two plans of 32 bytes per layer
+#define SVB_TILED_SMEM_BYTES (2 * SVB_BOX_Y_BYTES + 2 * SVB_BOX_C_BYTES + 2 * 240 * 16 + 128 + 2 * SVB_MAX_LAYERS * 32)
 
 // Coordinate-table entries per layer of a WxH frame: colY[W] colC[W/2] rowY[H] rowC[H/2], 16 bytes each.
 #define SVB_TABLE_ENTRIES(W, H) ((W) + (W) / 2 + (H) + (H) / 2)
