@@ -49,6 +49,21 @@ WORKLOAD = ("cfg4: 3840x2160 NV12 target, 8 NV12 layers (1x 3840x2160 full canva
             f"{STREAMS_PER_GPU} streams per GPU")
 
 
+def shard_streams(rank, world, per_gpu=STREAMS_PER_GPU):
+    """Global stream ids owned by `rank`: streams are independent, so sharding is a plain partition (no collective)."""
+    return list(range(rank * per_gpu, (rank + 1) * per_gpu))
+
+
+def max_over_ranks(ms, world, dist=None, device=None):
+    """The step time of the job is the slowest rank's device time."""
+    if world <= 1:
+        return float(ms)
+    import torch
+    t = torch.tensor([ms], dtype=torch.float64, device=device or "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
 def geometry():
     import scenes
     return scenes.cfg34_geometry(NLAYERS)
@@ -137,7 +152,7 @@ def run_ours(args):
     for k, (ssz, pos, dsz, op) in enumerate(geo):
         mats.append((animator.picture_state(CANVAS, ssz, pos, dsz, z=float(k)), op))
     for s in range(S):
-        gstream = rank * S + s
+        gstream = shard_streams(rank, world, S)[s]
         for k, (ssz, pos, dsz, op) in enumerate(geo):
             rng = np.random.default_rng(rng_base + 16 * gstream + k)
             h = sv.create_picture_sample(ssz[0], ssz[1], sv.NV12, f"s{gstream}l{k}", "bench", pinned_from=ctx)
@@ -193,10 +208,7 @@ def run_ours(args):
         launches = sv.kernel_launch_count() - launches0
         clocks = sampler.stop() if sampler else None
         timer.close()
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        ms = max_over_ranks(ms, world, dist, "cuda")
         return ms, launches, clocks
 
     # ---- value: layers resident in HBM
