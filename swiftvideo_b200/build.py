@@ -19,7 +19,7 @@ CUDA_HOME = Path(os.environ.get("CUDA_HOME", "/usr/local/cuda"))
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17"]
 NVCC_FLAGS += os.environ.get("SVB_NVCC_DEFS", "").split()  # tuning builds, e.g. SVB_NVCC_DEFS="-DSVB_TILED_MIN_CTAS=3"
-CXX_FLAGS = ["-O2", "-g1", "-fPIC", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-Wall", "-Wno-unused-function",
+CXX_FLAGS = [f for f in os.environ.get("SVB_NVCC_DEFS", "").split() if f.startswith("-D")] + ["-O2", "-g1", "-fPIC", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-Wall", "-Wno-unused-function",
              "-fvisibility=hidden", f"-I{CUDA_HOME}/include"]
 
 

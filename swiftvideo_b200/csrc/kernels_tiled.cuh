@@ -23,7 +23,6 @@
 #pragma once
 #include "svb_device.cuh"
 
-#define SVB_TILED_THREADS 256
 
 namespace svb {
 

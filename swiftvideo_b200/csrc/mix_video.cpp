@@ -84,7 +84,7 @@ MixerShared& shared(const std::shared_ptr<InternalContext>& ic) {  // caller hol
               "cuFuncSetAttribute(max dynamic shared memory)");
         s->fTables = ic->builtin("svb_mix_tables");
         int perSm = 0;
-        check(drv().cuOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, s->fTiled, 256, SVB_TILED_SMEM_BYTES), "cuOccupancyMaxActiveBlocksPerMultiprocessor");
+        check(drv().cuOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, s->fTiled, SVB_TILED_THREADS, SVB_TILED_SMEM_BYTES), "cuOccupancyMaxActiveBlocksPerMultiprocessor");
         s->tiledCtasPerSm = std::max(1, perSm);
         s->fGeneric = ic->builtin("svb_mix_generic");
     }
@@ -314,7 +314,7 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
             float one = 1.0f;  // see add2() in kernels_tiled.cuh
             void* args[] = {&dev, &tables, &nframes, &total, &one};
             const unsigned grid = (unsigned)std::min(total, ic.smCount * sh.tiledCtasPerSm);
-            check(d.cuLaunchKernel(sh.fTiled, grid, 1, 1, 256, 1, 1, SVB_TILED_SMEM_BYTES, ic.compute, args, nullptr), "cuLaunchKernel(svb_mix_tiled)");
+            check(d.cuLaunchKernel(sh.fTiled, grid, 1, 1, SVB_TILED_THREADS, 1, 1, SVB_TILED_SMEM_BYTES, ic.compute, args, nullptr), "cuLaunchKernel(svb_mix_tiled)");
             noteKernelLaunch();
             ic.release(tables, tableBytes);  // recycled only after the streams have drained past this point
         } else {

@@ -7,10 +7,13 @@
 
 // tile of the tiled kernel (luma pixels); chroma is TILE_W/2 x TILE_H/2
 #define SVB_TILE_W 128
+#ifndef SVB_TILE_H
 #define SVB_TILE_H 32
+#endif
+#define SVB_TILED_THREADS (SVB_TILE_H * 8)  // a warp covers 128 columns x 4 rows
 // largest source footprint the tiled kernel stages in shared memory per tile and layer
-#define SVB_BOX_Y_BYTES (20 * 1024)
-#define SVB_BOX_C_BYTES (12 * 1024)
+#define SVB_BOX_Y_BYTES (SVB_TILE_H * 640)
+#define SVB_BOX_C_BYTES (SVB_TILE_H * 384)
 
 enum SvbFormat { SVB_NV12 = 0, SVB_Y420P = 1, SVB_BGRA = 2, SVB_RGBA = 3 };
 
@@ -70,7 +73,8 @@ typedef struct __attribute__((aligned(64))) SvbFrameDesc {
 
 // dynamic shared memory of svb_mix_tiled: two staged box pairs, two table slices (240 entries of 16 bytes), two
 // mbarriers, two plans of 32 bytes per layer
-#define SVB_TILED_SMEM_BYTES (2 * SVB_BOX_Y_BYTES + 2 * SVB_BOX_C_BYTES + 2 * 240 * 16 + 128 + 2 * SVB_MAX_LAYERS * 32)
+#define SVB_TILED_SMEM_BYTES \
+    (2 * SVB_BOX_Y_BYTES + 2 * SVB_BOX_C_BYTES + 2 * (SVB_TILE_W + SVB_TILE_W / 2 + SVB_TILE_H + SVB_TILE_H / 2) * 16 + 128 + 2 * SVB_MAX_LAYERS * 32)
 
 // Coordinate-table entries per layer of a WxH frame: colY[W] colC[W/2] rowY[H] rowC[H/2], 16 bytes each.
 #define SVB_TABLE_ENTRIES(W, H) ((W) + (W) / 2 + (H) + (H) / 2)

@@ -1,0 +1,3 @@
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
+for i in 1 2; do timeout 300 python bench.py --steps 30 --warmup 3 --no-cpu-baseline 2> gpurun_out/bench7.err | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('bench', d['value'], d['ms_per_step'], d['roofline']['kernel_ms_per_launch'], d['roofline']['frac'], d['e2e']['value'], d['gpu_launches'])"; done
+tail -3 gpurun_out/bench7.err
