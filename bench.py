@@ -256,6 +256,10 @@ def run_ours(args):
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference(budget_s=args.cpu_seconds)
+        try:
+            line["cpu_baseline"]["swscale_scale_stage_only"] = swscale_scale_stage()
+        except Exception as e:  # context figure only
+            line["cpu_baseline"]["swscale_scale_stage_only"] = {"unavailable": str(e)[:200]}
     if rank == 0:
         print(json.dumps(line), flush=True)
     for m in mixers:
@@ -294,6 +298,52 @@ def cpu_reference(budget_s=15.0, steps=None, warmup=0):
     return {"value": round(steps / dt, 3), "unit": "frames/s", "cores": threads, "kind": kind,
             "sample": f"{steps} frames of one stream of the workload (3840x2160, 8 layers), rows split over {threads} threads",
             "ms_per_frame": round(dt / steps * 1e3, 2)}
+
+
+def swscale_scale_stage(seconds=3.0):
+    """Context only (BASELINE.json names swscale; the reference itself never calls it): FFmpeg libswscale
+    (the copy bundled in the OpenCV wheel, via ctypes) doing just the SCALE stage of one frame of the workload -- one
+    3840x2160 NV12 1:1 pass and seven 1920x1080 -> 1600x900 NV12 bilinear scales, no blending (swscale has none) -- on all
+    host threads, one frame per thread at a time."""
+    import ctypes as C
+    import glob
+    from concurrent.futures import ThreadPoolExecutor
+
+    import cv2
+    from oracle import oracle as O
+    libdir = os.path.join(os.path.dirname(cv2.__file__), "..", "opencv_python_headless.libs")
+    avutil = C.CDLL(glob.glob(libdir + "/libavutil*")[0], mode=C.RTLD_GLOBAL)
+    sws = C.CDLL(glob.glob(libdir + "/libswscale*")[0])
+    avutil.av_get_pix_fmt.argtypes = [C.c_char_p]
+    nv12 = avutil.av_get_pix_fmt(b"nv12")
+    sws.sws_getContext.restype = C.c_void_p
+    sws.sws_getContext.argtypes = [C.c_int] * 7 + [C.c_void_p] * 3
+    sws.sws_scale.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    threads = min(O.host_threads(), 64)
+    jobs = [((3840, 2160), (3840, 2160), 1), ((1920, 1080), (1600, 900), 7)]
+
+    def worker(_):
+        ctxs = []
+        for (sw, sh), (dw, dh), n in jobs:
+            ctx = sws.sws_getContext(sw, sh, nv12, dw, dh, nv12, 2, None, None, None)  # SWS_BILINEAR
+            src = np.zeros(sw * sh * 3 // 2, np.uint8)
+            dst = np.zeros(dw * dh * 3 // 2, np.uint8)
+            sp = (C.c_void_p * 4)(src.ctypes.data, src.ctypes.data + sw * sh, None, None)
+            dp = (C.c_void_p * 4)(dst.ctypes.data, dst.ctypes.data + dw * dh, None, None)
+            ctxs.append((ctx, sp, (C.c_int * 4)(sw, sw, 0, 0), sh, dp, (C.c_int * 4)(dw, dw, 0, 0), n, src, dst))
+        frames, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < seconds:
+            for ctx, sp, ss, sh, dp, ds, n, _, _ in ctxs:
+                for _ in range(n):
+                    sws.sws_scale(ctx, sp, ss, 0, sh, dp, ds)
+            frames += 1
+        return frames, time.perf_counter() - t0
+
+    with ThreadPoolExecutor(threads) as ex:
+        res = list(ex.map(worker, range(threads)))
+    fps = sum(f / dt for f, dt in res)
+    return {"value": round(fps, 2), "unit": "frames/s", "cores": threads,
+            "what": "libswscale 9.1 SWS_BILINEAR, scale stage only (8 NV12 scales per frame, no blend)"}
 
 
 def run_reference(args):

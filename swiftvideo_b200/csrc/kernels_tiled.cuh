@@ -368,12 +368,17 @@ __device__ __forceinline__ void plan_layer(const Ent* __restrict__ tables, const
 
 }  // namespace svb
 
-extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CTAS)
+extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CTAS)  // 8 compute warps + 1 producer warp
     svb_mix_tiled(const SvbFrameDesc* __restrict__ frames, const svb::Ent* __restrict__ tables, int nframes, int total_tiles, float one) {
     using namespace svb;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TiledSmem& sm = *reinterpret_cast<TiledSmem*>(smem_raw);
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    // Warps 0..7 compute; warp 8 is the producer: it plans the tiles and issues the TMA copies, so that no computing
+    // warp runs late into a barrier because it also had the copies to launch (profiles/r1_history.md, v6).
+    const bool producer = SVB_PRODUCER_WARP && warp == SVB_TILED_COMPUTE_WARPS;
+    const int pt = SVB_PRODUCER_WARP ? t - SVB_TILED_COMPUTE_WARPS * 32 : t;  // index among the planning threads (negative: not one)
+    const SvbFrameDesc* fenced = nullptr;              // frame whose tensor maps this CTA's producer has acquired
     unsigned phase0 = 0, phase1 = 0;
     if (t == 0) {
         mbar_init(&sm.bar[0], 1);
@@ -385,7 +390,7 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CT
     bool primed = false;  // this tile's first staged layer was already put in flight by the previous tile
     if (blockIdx.x < total_tiles) {
         const TileGeo g0 = tile_geo(frames, nframes, fnext, blockIdx.x);
-        if (t < g0.F->nlayers) plan_layer(tables, g0, t, sm.plan[0][t]);
+        if (pt >= 0 && pt < g0.F->nlayers) plan_layer(tables, g0, pt, sm.plan[0][pt]);
     }
     __syncthreads();
 
@@ -395,7 +400,7 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CT
         const int W = F->width, H = F->height, nl = F->nlayers;
         const int x0 = g.x0, y0 = g.y0, lastr = g.lastr;
         const int xt = x0 + 4 * lane, yt = y0 + 4 * warp;  // this thread's 4x4 block
-        const bool live = xt < W && yt < H;                 // W % 4 == 0 and H even are planner preconditions
+        const bool live = !producer && xt < W && yt < H;    // W % 4 == 0 and H even are planner preconditions
         const bool nv12 = F->format == SVB_NV12;
         const float fW = (float)W, fH = (float)H;
         uint8_t* const oY = (uint8_t*)F->out_plane[0];
@@ -413,9 +418,15 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CT
             const int cbytes = n12 ? L->box_cw * L->box_ch * 2 : L->box_cw * L->box_ch;
             const int ncy = tg.lastc + 1, nry = tg.lastr + 1;
             const Tabs tb = layer_tabs(tables, TF, l);
-            tmap_acquire(L->tmap[0]);
-            tmap_acquire(L->tmap[1]);
-            if (!n12) tmap_acquire(L->tmap[2]);
+            if (TF != fenced) {  // the host rewrites the descriptors between launches: acquire a frame's maps once per CTA
+                for (int q = 0; q < TF->nlayers; ++q)
+                    if (TF->layers[q].flags & SVB_LAYER_STAGED) {
+                        tmap_acquire(TF->layers[q].tmap[0]);
+                        tmap_acquire(TF->layers[q].tmap[1]);
+                        if (TF->layers[q].format != SVB_NV12) tmap_acquire(TF->layers[q].tmap[2]);
+                    }
+                fenced = TF;
+            }
             mbar_expect_tx(&sm.bar[b], L->box_w * L->box_h + cbytes * (n12 ? 1 : 2) + (ncy + ncy / 2 + nry + nry / 2) * (int)sizeof(Ent));
             tma_load_2d(sm.boxY[b], L->tmap[0], p0.y, p0.z, &sm.bar[b]);
             tma_load_2d(sm.boxC[b], L->tmap[1], p0.w, p1.x, &sm.bar[b]);
@@ -432,7 +443,7 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CT
                 if (pl[l][0].x >= PLAN_STAGED) return l;
             return -1;
         };
-        if (!primed && t == 0) {
+        if (!primed && pt == 0) {
             const int l = first_staged(plan, 0, nl);
             if (l >= 0) issue(g, plan, l, stage);
         }
@@ -442,7 +453,7 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CT
         TileGeo gn = g;
         if (has_next) {
             gn = tile_geo(frames, nframes, fnext, tile + gridDim.x);
-            if (t < gn.F->nlayers) plan_layer(tables, gn, t, sm.plan[cur ^ 1][t]);
+            if (pt >= 0 && pt < gn.F->nlayers) plan_layer(tables, gn, pt, sm.plan[cur ^ 1][pt]);
         }
 
         // ---- running picture: integer-valued floats ------------------------------------------------------------
@@ -482,22 +493,21 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CT
                 {   // refill the other buffer: the next staged layer of this tile, else the first one of the next tile
                     const int j = first_staged(plan, l + 1, nl);
                     if (j >= 0) {
-                        if (t == 0) issue(g, plan, j, stage ^ 1);
+                        if (pt == 0) issue(g, plan, j, stage ^ 1);
                     } else if (has_next) {
                         const int jn = first_staged(sm.plan[cur ^ 1], 0, gn.F->nlayers);
                         if (jn >= 0) {
-                            if (t == 0) issue(gn, sm.plan[cur ^ 1], jn, stage ^ 1);
+                            if (pt == 0) issue(gn, sm.plan[cur ^ 1], jn, stage ^ 1);
                             primed = true;
                         }
                     }
                 }
-                if (stage == 0) {
-                    mbar_wait(&sm.bar[0], phase0);
-                    phase0 ^= 1;
-                } else {
-                    mbar_wait(&sm.bar[1], phase1);
-                    phase1 ^= 1;
+                if (!producer) {
+                    if (stage == 0) mbar_wait(&sm.bar[0], phase0);
+                    else mbar_wait(&sm.bar[1], phase1);
                 }
+                if (stage == 0) phase0 ^= 1;
+                else phase1 ^= 1;
                 if (live) {
                     const int fmt = L->format, lflags = L->flags;
                     const int pitchC = fmt == SVB_NV12 ? L->box_cw * 2 : L->box_cw, stepC = fmt == SVB_NV12 ? 2 : 1;

@@ -1,0 +1,7 @@
+B() { timeout 300 python bench.py --steps 30 --warmup 3 --no-cpu-baseline 2> gpurun_out/bench12.err | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$1', d['value'], d['ms_per_step'], d['roofline']['kernel_ms_per_launch'], d['roofline']['frac'], d['e2e']['value'], d['gpu_launches'])"; }
+timeout 600 python -m pytest tests -m gpu -q -x 2>&1 | tail -2
+B base; B base
+SVB_NVCC_DEFS="-DSVB_TAP_UNORM_PK=false" python -m swiftvideo_b200.build --force > /dev/null 2>&1
+B scalar_unorm; B scalar_unorm
+python -m swiftvideo_b200.build --force > /dev/null 2>&1
+tail -3 gpurun_out/bench12.err
