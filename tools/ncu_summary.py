@@ -42,7 +42,7 @@ def main():
         secs = m["gpu__time_duration.sum"]["value"] * tscale[m["gpu__time_duration.sum"]["unit"]]
         summary["derived"] = {"frames_per_launch": frames, "algorithmic_bytes_per_launch": frames * alg, "dram_bytes_per_launch": traffic,
                               "dram_over_algorithmic": traffic / (frames * alg), "seconds_under_profiler": secs,
-                              "warp_instructions_per_output_pixel": m["smsp__inst_executed.sum"]["value"] * 32 / (frames * 3840 * 2160)}
+                              "thread_instructions_per_output_pixel": m["smsp__inst_executed.sum"]["value"] * 32 / (frames * 3840 * 2160)}
     json.dump(summary, open(out, "w"), indent=1)
     print(json.dumps(summary.get("derived", {}), indent=1))
 
