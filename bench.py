@@ -90,7 +90,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -186,14 +186,11 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, sample_clocks=False):
+    def timed(fn, steps, warmup):
         for i in range(warmup):
             fn(i)
         ctx.synchronize()
         barrier()
-        sampler = ClockSampler(local) if sample_clocks else None
-        if sampler:
-            sampler.start()
         timer = sv.Timer(ctx)
         launches0 = sv.kernel_launch_count()
         timer.start()
@@ -206,14 +203,17 @@ def run_ours(args):
             o.wait()
         barrier()
         launches = sv.kernel_launch_count() - launches0
-        clocks = sampler.stop() if sampler else None
         timer.close()
         ms = max_over_ranks(ms, world, dist, "cuda")
-        return ms, launches, clocks
+        return ms, launches
 
+    # clocks and throttle reasons are sampled (nvidia-smi, every 50 ms) from here to the end of the e2e leg: the GPU is
+    # busy throughout, and the resident leg alone can be shorter than one sampling period
+    sampler = ClockSampler(local)
+    sampler.start()
     # ---- value: layers resident in HBM
     ctx.launch_timing(True)
-    ms, launches, clocks = timed(step_resident, args.steps, args.warmup, sample_clocks=True)
+    ms, launches = timed(step_resident, args.steps, args.warmup)
     kern_ms, kern_n = ctx.launch_timing_read()
     ctx.launch_timing(False)
     frames = S * world * args.steps
@@ -221,7 +221,8 @@ def run_ours(args):
 
     # ---- e2e: host buffers in, host buffers out
     e2e_steps = max(3, min(args.steps, args.e2e_steps))
-    e_ms, _, _ = timed(step_e2e, e2e_steps, max(3, min(args.warmup, 3)))
+    e_ms, _ = timed(step_e2e, e2e_steps, max(3, min(args.warmup, 3)))
+    clocks = sampler.stop()
     e2e_value = S * world * e2e_steps / (e_ms / 1e3)
     h2d = S * (12441600 + 7 * 3110400)
     d2h = S * 12441600
