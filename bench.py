@@ -162,6 +162,9 @@ def run_ours(args):
             for c in range(2):
                 dev[c][s][k] = host[s][k].upload(ctx)
     mixers = [sv.VideoMixer(ctx, CANVAS[0], CANVAS[1], sv.NV12, asset_id=f"mixer{rank * S + s}", workspace_id="bench") for s in range(S)]
+    mode = {"fused": sv.MixMode.FUSED, "generic": sv.MixMode.GENERIC, "per_layer": sv.MixMode.PER_LAYER}[args.mode]
+    for m in mixers:
+        m.set_mode(mode)
     for i in range(10):  # setup, untimed: fill every mixer's backing ring (10 targets, allocated on first use upstream too)
         sv.VideoMixer.mix_many(mixers, -1 - i, wait=False)
     ctx.synchronize()
@@ -229,15 +232,15 @@ def run_ours(args):
 
     peak, peak_src = peaks()
     roof = None
-    if kern_n:
+    if kern_n and args.mode != "per_layer":  # the per-layer sequence has no single dominant launch to put on a roofline
         per_launch_ms = kern_ms / kern_n
         # warm-up launches are inside the timing window too; they run the same work, so the average stands
         achieved = ALG_BYTES_PER_FRAME * S / (per_launch_ms / 1e3) / 1e9
         roof = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": None, "peak_source": peak_src, "kernel": "svb_mix_tiled", "kernel_ms_per_launch": round(per_launch_ms, 4),
+                "traffic": None, "peak_source": peak_src, "kernel": "svb_mix_tiled" if args.mode == "fused" else "svb_mix_generic", "kernel_ms_per_launch": round(per_launch_ms, 4),
                 "algorithmic_bytes_per_launch": ALG_BYTES_PER_FRAME * S, "launches_timed": int(kern_n)}
         tr = ROOT / "profiles" / "traffic.json"
-        if tr.exists():
+        if tr.exists() and args.mode == "fused":
             try:
                 roof["traffic"] = json.loads(tr.read_text()).get("svb_mix_tiled_dram_bytes_per_launch")
             except Exception:
@@ -247,7 +250,7 @@ def run_ours(args):
         "metric": METRIC, "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8 (fp32 arithmetic, no FMA contraction)", "data": "synthetic (uniform u8 planes, seeded)",
-        "config": {"workload": WORKLOAD, "streams_total": S * world, "frames_per_step": S * world, "parallelism": f"streams sharded, {S}/GPU, no collective",
+        "config": {"workload": WORKLOAD, "mode": args.mode, "streams_total": S * world, "frames_per_step": S * world, "parallelism": f"streams sharded, {S}/GPU, no collective",
                    "l2": "373 MB of distinct sources+targets per step (> 126 MB L2); sources alternate between two device copies",
                    "bit_exact_vs_oracle": "tests/test_gpu_parity.py::test_cfg34_full_size"},
         "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
@@ -372,6 +375,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="fused", choices=["fused", "generic", "per_layer"],
+                    help="compose strategy: fused (default, svb_mix_tiled), generic (svb_mix_generic), per_layer (the reference's own "
+                         "launch sequence over the drop-in kernels: clear + one launch per layer)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
