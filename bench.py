@@ -133,7 +133,6 @@ def run_ours(args):
     import scenes
     import swiftvideo_b200 as sv
     from oracle import oracle as O
-    from swiftvideo_b200 import animator
 
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -148,17 +147,14 @@ def run_ours(args):
     # ---- synthetic layers: pinned host pictures (e2e source) and two device copies (device-resident source)
     host = [[None] * NLAYERS for _ in range(S)]
     dev = [[[None] * NLAYERS for _ in range(S)] for _ in range(2)]
-    mats = []
-    for k, (ssz, pos, dsz, op) in enumerate(geo):
-        mats.append((animator.picture_state(CANVAS, ssz, pos, dsz, z=float(k)), op))
     for s in range(S):
         gstream = shard_streams(rank, world, S)[s]
         for k, (ssz, pos, dsz, op) in enumerate(geo):
             rng = np.random.default_rng(rng_base + 16 * gstream + k)
             h = sv.create_picture_sample(ssz[0], ssz[1], sv.NV12, f"s{gstream}l{k}", "bench", pinned_from=ctx)
             h.set_host_bytes(rng.integers(0, 256, size=ssz[0] * ssz[1] * 3 // 2, dtype=np.uint8))
-            (m, t, b), opacity = mats[k]
-            host[s][k] = h.with_(matrix=m, texture_matrix=t, border_matrix=b, opacity=opacity)
+            # PictureAnimator.impl in native code: matrix = ortho(canvas) * T(pos) * S(size), opacity = 1 - transparency
+            host[s][k] = h.animate(CANVAS, (pos[0], pos[1], float(k)), dsz, transparency=1.0 - op)
             for c in range(2):
                 dev[c][s][k] = host[s][k].upload(ctx)
     mixers = [sv.VideoMixer(ctx, CANVAS[0], CANVAS[1], sv.NV12, asset_id=f"mixer{rank * S + s}", workspace_id="bench") for s in range(S)]

@@ -153,6 +153,23 @@ void svb_picture_release(svb_picture* pict);
 svb_status svb_upload_compute_picture(svb_context* ctx, const svb_picture* pict, int max_planes, int retain_cpu_buffer, svb_picture** out);
 svb_status svb_download_compute_picture(svb_context* ctx, const svb_picture* pict, int retain_gpu_buffer, int wait, svb_picture** out);
 
+/* ---- PictureAnimator's state -> matrices (animator.pic.swift:107-128,207-272,326-333) ------------------ */
+typedef struct svb_element_state {   /* the ElementState fields computePictureState reads (Proto/Composition.proto:56-71) */
+    float pic_pos[3];
+    float size[2];
+    float texture_offset[2];
+    float border_size[4];            /* left, top, right, bottom */
+    float fill_color[4];
+    float rotation, transparency;
+    int32_t pic_aspect;              /* 0 none, 1 aspectFit, 2 aspectFill */
+    int32_t pic_origin;              /* 0 centre, 1 top-left */
+    int32_t has_fill_color;
+} svb_element_state;
+/* PictureAnimator.impl: `pict` re-issued with matrix = ortho(canvas) * T(pos) * Rz(rotation) * S(size), textureMatrix by
+ * aspect mode, borderMatrix, fillColor, opacity = (1 - transparency) * parent_opacity, revision (NULL keeps it). */
+svb_status svb_animate_picture(const svb_picture* pict, float canvas_width, float canvas_height, const svb_element_state* state,
+                               float parent_opacity, const char* revision, svb_picture** out);
+
 /* ---- VideoMixer -------------------------------------------------------------------------------------- */
 /* VideoMixer.init mix.video.swift:22-30; ctx NULL = makeComputeContext(forType: .GPU); asset_id NULL = generated */
 svb_status svb_video_mixer_create(const svb_context* ctx, float width, float height, int pixel_format, const char* asset_id,

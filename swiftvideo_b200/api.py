@@ -42,6 +42,14 @@ class ImageUniforms(C.Structure):
                 ("opacity", C.c_float), ("image_time", C.c_float), ("target_time", C.c_float)]
 
 
+class ElementState(C.Structure):
+    """svb_element_state: the ElementState fields PictureAnimator reads."""
+
+    _fields_ = [("pic_pos", C.c_float * 3), ("size", C.c_float * 2), ("texture_offset", C.c_float * 2), ("border_size", C.c_float * 4),
+                ("fill_color", C.c_float * 4), ("rotation", C.c_float), ("transparency", C.c_float), ("pic_aspect", C.c_int32),
+                ("pic_origin", C.c_int32), ("has_fill_color", C.c_int32)]
+
+
 class _PlaneInfo(C.Structure):
     _fields_ = [("width", C.c_float), ("height", C.c_float), ("stride", C.c_int32), ("bit_depth", C.c_int32),
                 ("components", C.c_int32), ("host", C.c_void_p), ("device", C.c_ulonglong), ("size", C.c_size_t)]
@@ -102,6 +110,7 @@ def _load():
     l.svb_timer_elapsed_ms.argtypes = [C.c_void_p, C.c_void_p]
     l.svb_video_mixer_destroy.argtypes = [C.c_void_p]
     l.svb_video_mixer_asset_id.argtypes = [C.c_void_p]
+    l.svb_animate_picture.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_float, C.c_char_p, C.c_void_p]
     l.svb_launch_timing.argtypes = [C.c_void_p, C.c_int]
     l.svb_launch_timing_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     l.svb_selftest_unorm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -265,6 +274,23 @@ class PictureSample:
         op = None if opacity is None else C.c_float(opacity)
         _check(lib.svb_picture_with(self._h, _f(matrix, 16), _f(texture_matrix, 16), _f(border_matrix, 16), _f(fill_color, 4),
                                     C.cast(C.pointer(op), C.c_void_p) if op is not None else None, _b(revision), _b(asset_id), C.byref(h)))
+        return PictureSample(h)
+
+    def animate(self, canvas, pos, size, rotation=0.0, border=(0, 0, 0, 0), aspect=0, tex_offset=(0, 0), fill=None, transparency=0.0,
+                top_left=True, parent_opacity=1.0, revision=None):
+        """PictureAnimator.impl in native code (svb_animate_picture)."""
+        st = ElementState()
+        st.pic_pos[:] = [float(v) for v in (tuple(pos) + (0.0,))[:3]]
+        st.size[:] = [float(size[0]), float(size[1])]
+        st.texture_offset[:] = [float(tex_offset[0]), float(tex_offset[1])]
+        st.border_size[:] = [float(v) for v in border]
+        if fill is not None:
+            st.fill_color[:] = [float(v) for v in fill]
+            st.has_fill_color = 1
+        st.rotation, st.transparency = float(rotation), float(transparency)
+        st.pic_aspect, st.pic_origin = int(aspect), 1 if top_left else 0
+        h = C.c_void_p()
+        _check(lib.svb_animate_picture(self._h, float(canvas[0]), float(canvas[1]), C.byref(st), float(parent_opacity), _b(revision), C.byref(h)))
         return PictureSample(h)
 
     def upload(self, ctx, max_planes=3, retain_cpu_buffer=True):

@@ -8,6 +8,7 @@
 #include "compute.h"
 #include "cu_driver.h"
 #include "mix_video.h"
+#include "animator.h"
 
 using namespace svb;
 
@@ -231,6 +232,25 @@ svb_status svb_download_compute_picture(svb_context* ctx, const svb_picture* pic
         need(pict, "pict");
         need(out, "out");
         *out = wrap(downloadComputePicture(ctx->c, *pict->p, retain_gpu_buffer != 0, wait != 0));
+    });
+}
+
+svb_status svb_animate_picture(const svb_picture* pict, float canvas_width, float canvas_height, const svb_element_state* st, float parent_opacity,
+                               const char* revision, svb_picture** out) {
+    return guard([&] {
+        need(pict, "pict");
+        need(st, "state");
+        need(out, "out");
+        ElementState e;
+        e.picPos = Vector3{st->pic_pos[0], st->pic_pos[1], st->pic_pos[2]};
+        e.size = Vector2{st->size[0], st->size[1]};
+        e.textureOffset = Vector2{st->texture_offset[0], st->texture_offset[1]};
+        e.borderSize = Vector4{st->border_size[0], st->border_size[1], st->border_size[2], st->border_size[3]};
+        e.fillColor = Vector4{st->fill_color[0], st->fill_color[1], st->fill_color[2], st->fill_color[3]};
+        e.rotation = st->rotation, e.transparency = st->transparency;
+        if (st->pic_aspect < 0 || st->pic_aspect > 2 || st->pic_origin < 0 || st->pic_origin > 1) throw ComputeError(ErrorCode::invalidValue, "bad element state");
+        e.picAspect = (AspectMode)st->pic_aspect, e.picOrigin = (PicOrigin)st->pic_origin, e.hasFillColor = st->has_fill_color != 0;
+        *out = wrap(animatePicture(*pict->p, Vector2{canvas_width, canvas_height}, e, parent_opacity, revision ? revision : ""));
     });
 }
 

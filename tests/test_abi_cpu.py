@@ -107,3 +107,27 @@ def test_no_cpu_fallback():
     assert e.value.name == "deviceNotAvailable"
     with pytest.raises(sv.ComputeError):
         sv.VideoMixer(None, 64, 64).mix(0)
+
+
+def test_animate_picture_matches_python_animator():
+    """PictureAnimator.impl in native code (svb_animate_picture) against the numpy helper the tests place layers with."""
+    canvas = (1280, 720)
+    src = sv.create_picture_sample(640, 360, sv.NV12, "s", "w")
+    for kw, asp in ((dict(pos=(0, 0), size=(640, 720)), "fill"), (dict(pos=(100.5, 50.25), size=(320, 200), rotation=0.4, border=(3, 4, 5, 6)), "none"),
+                    (dict(pos=(-20, 600, 3.0), size=(900, 300)), "fit")):
+        pos = kw["pos"]
+        m, t, b = animator.picture_state(canvas, (640, 360), pos[:2], kw["size"], rotation=kw.get("rotation", 0.0), z=pos[2] if len(pos) > 2 else 0.0,
+                                         border=kw.get("border", (0, 0, 0, 0)), aspect=asp)
+        q = src.animate(canvas, pos, kw["size"], rotation=kw.get("rotation", 0.0), border=kw.get("border", (0, 0, 0, 0)),
+                        aspect={"none": 0, "fit": 1, "fill": 2}[asp], fill=(0.2, 0.4, 0.6, 0.8), transparency=0.25, parent_opacity=0.5, revision="r")
+        i = q.info()
+        assert np.allclose(np.array(i.matrix[:]), m, rtol=1e-5, atol=1e-6)
+        assert np.allclose(np.array(i.texture_matrix[:]), t, rtol=1e-5, atol=1e-6)
+        assert np.allclose(np.array(i.border_matrix[:]), b, rtol=1e-5, atol=1e-6)
+        assert abs(i.opacity - 0.375) < 1e-7 and np.allclose(list(i.fill_color), [0.2, 0.4, 0.6, 0.8])
+        assert i.z_index == int(round((pos[2] if len(pos) > 2 else 0.0) + 1))       # ortho's m43 = 1
+    # no fill colour set -> (0,0,0,0) (animator.pic.swift:334-342); centre origin shifts by half the size
+    q = src.animate(canvas, (100, 100), (50, 40), top_left=False)
+    assert list(q.info().fill_color) == [0, 0, 0, 0]
+    mm = np.array(q.info().matrix[:]).reshape(4, 4)
+    assert abs(mm[3, 0] - (2.0 / 1280 * 75 - 1)) < 1e-6 and abs(mm[3, 1] - (2.0 / 720 * 80 - 1)) < 1e-6
