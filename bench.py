@@ -124,6 +124,30 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def bind_to_gpu_numa(index):
+    """Best effort: run this rank (and first-touch its pinned buffers) on the CPU cores next to its GPU, so that host<->device
+    copies do not cross the socket interconnect.  Returns a short description for the bench line."""
+    try:
+        bdf = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(index)], capture_output=True, text=True,
+                             timeout=20).stdout.strip().lower()
+        if bdf.startswith("00000000:"):
+            bdf = bdf[4:]
+        base = Path("/sys/bus/pci/devices") / bdf
+        node = int((base / "numa_node").read_text().strip())
+        cpulist = (base / "local_cpulist").read_text().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= set(os.sched_getaffinity(0))
+        if node >= 0 and cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"numa node {node} ({len(cpus)} cpus)"
+        return f"numa node {node} (not bound)"
+    except Exception as e:
+        return f"unbound ({type(e).__name__})"
+
+
 # ---- our arm -------------------------------------------------------------------------------------------------
 
 def run_ours(args):
@@ -137,6 +161,7 @@ def run_ours(args):
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa(local) if not args.no_numa_bind else "unbound (--no-numa-bind)"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = sv.make_compute_context(local)
@@ -194,8 +219,10 @@ def run_ours(args):
         launches0 = sv.kernel_launch_count()
         timer.start()
         last = None
+        h0 = time.perf_counter()
         for i in range(steps):
             last = fn(warmup + i)
+        host_ms = (time.perf_counter() - h0) * 1e3  # time the host needs to queue the steps (device runs behind it)
         timer.stop()
         ms = timer.elapsed_ms()
         for o in last:
@@ -204,7 +231,7 @@ def run_ours(args):
         launches = sv.kernel_launch_count() - launches0
         timer.close()
         ms = max_over_ranks(ms, world, dist, "cuda")
-        return ms, launches
+        return ms, launches, host_ms
 
     # clocks and throttle reasons are sampled (nvidia-smi, every 50 ms) from here to the end of the e2e leg: the GPU is
     # busy throughout, and the resident leg alone can be shorter than one sampling period
@@ -212,7 +239,7 @@ def run_ours(args):
     sampler.start()
     # ---- value: layers resident in HBM
     ctx.launch_timing(True)
-    ms, launches = timed(step_resident, args.steps, args.warmup)
+    ms, launches, host_ms = timed(step_resident, args.steps, args.warmup)
     kern_ms, kern_n = ctx.launch_timing_read()
     ctx.launch_timing(False)
     frames = S * world * args.steps
@@ -220,7 +247,7 @@ def run_ours(args):
 
     # ---- e2e: host buffers in, host buffers out
     e2e_steps = max(3, min(args.steps, args.e2e_steps))
-    e_ms, _ = timed(step_e2e, e2e_steps, max(3, min(args.warmup, 3)))
+    e_ms, _, e_host_ms = timed(step_e2e, e2e_steps, max(3, min(args.warmup, 3)))
     clocks = sampler.stop()
     e2e_value = S * world * e2e_steps / (e_ms / 1e3)
     h2d = S * (12441600 + 7 * 3110400)
@@ -244,13 +271,13 @@ def run_ours(args):
 
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": round(ms / args.steps, 4), "host_queue_ms_per_step": round(host_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8 (fp32 arithmetic, no FMA contraction)", "data": "synthetic (uniform u8 planes, seeded)",
-        "config": {"workload": WORKLOAD, "mode": args.mode, "streams_total": S * world, "frames_per_step": S * world, "parallelism": f"streams sharded, {S}/GPU, no collective",
+        "config": {"workload": WORKLOAD, "mode": args.mode, "streams_total": S * world, "frames_per_step": S * world, "parallelism": f"streams sharded, {S}/GPU, no collective", "host_affinity": numa,
                    "l2": "373 MB of distinct sources+targets per step (> 126 MB L2); sources alternate between two device copies",
                    "bit_exact_vs_oracle": "tests/test_gpu_parity.py::test_cfg34_full_size"},
         "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                "ms_per_step": round(e_ms / e2e_steps, 4)},
+                "ms_per_step": round(e_ms / e2e_steps, 4), "host_queue_ms_per_step": round(e_host_ms / e2e_steps, 4)},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
         "hbm_gbs_per_gpu_algorithmic": round(ALG_BYTES_PER_FRAME * value / world / 1e9, 1),
     }
@@ -371,6 +398,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to the CPU cores local to its GPU")
     ap.add_argument("--mode", default="fused", choices=["fused", "generic", "per_layer"],
                     help="compose strategy: fused (default, svb_mix_tiled), generic (svb_mix_generic), per_layer (the reference's own "
                          "launch sequence over the drop-in kernels: clear + one launch per layer)")
