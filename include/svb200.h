@@ -140,6 +140,12 @@ svb_status svb_make_image_uniforms(const svb_picture* image, const svb_picture* 
 /* createPictureSample sample.pict.linux.swift:254-273; pinned_from != NULL makes the CPU buffer page-locked */
 svb_status svb_create_picture_sample(float width, float height, int pixel_format, const char* asset_id, const char* workspace_id,
                                      svb_context* pinned_from, svb_picture** out);
+/* A CPU sample over caller-described planes with their own strides -- ImageBuffer(pixelFormat:bufferType:size:buffers:planes:)
+ * + PictureSample(img, ...) sample.pict.linux.swift:23-39,160-189, as the FFmpeg decoder builds them with linesize strides
+ * (SwiftVideo_FFmpeg/dec.video.ffmpeg.swift:144-220).  The bytes are copied. */
+svb_status svb_picture_sample_from_planes(float width, float height, int pixel_format, const void* const* planes, const int32_t* strides,
+                                          int plane_count, const char* asset_id, const char* workspace_id, svb_context* pinned_from,
+                                          svb_picture** out);
 /* PictureSample(other, matrix:textureMatrix:borderMatrix:fillColor:opacity:revision:assetId:) :194-226; NULL keeps other's value.
  * Matrices are 16 floats in VectorMath memory order (m11,m12,m13,m14,m21,...). */
 svb_status svb_picture_with(const svb_picture* other, const float* matrix, const float* texture_matrix, const float* border_matrix,

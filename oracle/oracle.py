@@ -60,9 +60,17 @@ def plane_layout(fmt, w, h):
 class Image:
     """A contiguous 8-bit picture in the reference's Linux plane layout."""
 
-    def __init__(self, fmt, width, height, data=None):
+    def __init__(self, fmt, width, height, data=None, strides=None):
+        """strides: optional per-plane row strides in bytes (decoder-style padded rows); default = the reference's layout."""
         self.format, self.width, self.height = fmt, width, height
         self.layout, self.nbytes = plane_layout(fmt, width, height)
+        if strides is not None:
+            off, lay = 0, []
+            for (_, w, h, st, nc), s2 in zip(self.layout, strides):
+                assert s2 >= w * nc
+                lay.append((off, w, h, int(s2), nc))
+                off += int(s2) * h
+            self.layout, self.nbytes = lay, off
         if data is None:
             data = np.zeros(self.nbytes, dtype=np.uint8)
         data = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1)
@@ -70,7 +78,11 @@ class Image:
         self.data = data
 
     def copy(self):
-        return Image(self.format, self.width, self.height, self.data.copy())
+        return Image(self.format, self.width, self.height, self.data.copy(), [l[3] for l in self.layout])
+
+    def padded_planes(self):
+        """Each plane as a (rows x stride) array, padding included."""
+        return [self.data[off : off + stride * h].reshape(h, stride) for off, w, h, stride, nc in self.layout]
 
     def plane(self, i):
         off, w, h, stride, nc = self.layout[i]

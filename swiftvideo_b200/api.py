@@ -110,6 +110,8 @@ def _load():
     l.svb_timer_elapsed_ms.argtypes = [C.c_void_p, C.c_void_p]
     l.svb_video_mixer_destroy.argtypes = [C.c_void_p]
     l.svb_video_mixer_asset_id.argtypes = [C.c_void_p]
+    l.svb_picture_sample_from_planes.argtypes = [C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_void_p,
+                                                 C.c_void_p]
     l.svb_animate_picture.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_float, C.c_char_p, C.c_void_p]
     l.svb_launch_timing.argtypes = [C.c_void_p, C.c_int]
     l.svb_launch_timing_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -314,6 +316,17 @@ def create_picture_sample(width, height, pixel_format, asset_id="", workspace_id
     h = C.c_void_p()
     _check(lib.svb_create_picture_sample(width, height, pixel_format, asset_id.encode(), workspace_id.encode(),
                                          pinned_from._h if pinned_from else None, C.byref(h)))
+    return PictureSample(h)
+
+
+def picture_sample_from_planes(width, height, pixel_format, planes, asset_id="", workspace_id="", pinned_from=None):
+    """CPU sample over numpy planes (2-D uint8 arrays whose row length in bytes is the stride) -- decoder-style strides."""
+    arrs = [np.ascontiguousarray(p, dtype=np.uint8) for p in planes]
+    ptrs = (C.c_void_p * 3)(*[a.ctypes.data for a in arrs] + [None] * (3 - len(arrs)))
+    strides = (C.c_int32 * 3)(*[a.shape[1] for a in arrs] + [0] * (3 - len(arrs)))
+    h = C.c_void_p()
+    _check(lib.svb_picture_sample_from_planes(width, height, pixel_format, ptrs, strides, len(arrs), asset_id.encode(), workspace_id.encode(),
+                                              pinned_from._h if pinned_from else None, C.byref(h)))
     return PictureSample(h)
 
 

@@ -166,6 +166,21 @@ svb_status svb_create_picture_sample(float width, float height, int pixel_format
                                         pinned_from ? &pinned_from->c : nullptr));
     });
 }
+svb_status svb_picture_sample_from_planes(float width, float height, int pixel_format, const void* const* planes, const int32_t* strides,
+                                          int plane_count, const char* asset_id, const char* workspace_id, svb_context* pinned_from, svb_picture** out) {
+    return guard([&] {
+        need(planes, "planes");
+        need(strides, "strides");
+        need(out, "out");
+        if (pixel_format < 0 || pixel_format > (int)PixelFormat::invalid) throw ComputeError(ErrorCode::badInputData, "Invalid pixel format");
+        if (plane_count < 1 || plane_count > 3) throw ComputeError(ErrorCode::badInputData, "Input image must have 1, 2, or 3 planes");
+        const uint8_t* p[3] = {nullptr, nullptr, nullptr};
+        int st[3] = {0, 0, 0};
+        for (int i = 0; i < plane_count; ++i) p[i] = (const uint8_t*)planes[i], st[i] = strides[i];
+        *out = wrap(pictureSampleFromPlanes((PixelFormat)pixel_format, Vector2{width, height}, p, st, plane_count, asset_id ? asset_id : "",
+                                            workspace_id ? workspace_id : "", pinned_from ? &pinned_from->c : nullptr));
+    });
+}
 svb_status svb_picture_with(const svb_picture* other, const float* matrix, const float* texture_matrix, const float* border_matrix,
                             const float* fill_color, const float* opacity, const char* revision, const char* asset_id, svb_picture** out) {
     return guard([&] {

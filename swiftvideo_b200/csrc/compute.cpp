@@ -392,6 +392,42 @@ PictureSample createPictureSample(Vector2 size, PixelFormat format, const std::s
     return s;
 }
 
+PictureSample pictureSampleFromPlanes(PixelFormat format, Vector2 size, const uint8_t* const* planes, const int* strides, int planeCount,
+                                      const std::string& assetId, const std::string& workspaceId, ComputeContext* pinnedFrom) {
+    if (!(size.x > 0 && size.y > 0)) throw ComputeError(ErrorCode::invalidOperation, "empty size");
+    std::vector<Plane> layout = planesForFormat(format, size);
+    if (planeCount != (int)layout.size()) throw ComputeError(ErrorCode::badInputData, "Input image must have the same number of buffers as planes");
+    for (int i = 0; i < planeCount; ++i) {
+        const int minStride = (int)layout[i].size.x * (int)layout[i].components.size();
+        if (!planes[i] || strides[i] < minStride) throw ComputeError(ErrorCode::badInputData, "plane stride smaller than its row");
+        layout[i].stride = strides[i];
+    }
+    // one allocation, planes back to back at their own strides (each plane start 64-byte aligned)
+    size_t total = 0;
+    std::vector<size_t> offs;
+    for (const Plane& p : layout) {
+        total = (total + 63) & ~(size_t)63;
+        offs.push_back(total);
+        total += (size_t)p.stride * (size_t)(int)p.size.y;
+    }
+    PictureSample proto = createPictureSample(Vector2{(float)((total + 3) / 4 + 1), 1.f}, PixelFormat::RGBA, assetId, workspaceId, pinnedFrom);
+    std::shared_ptr<uint8_t> base = proto.imgBuffer.buffers[0].base;  // borrow the allocator (pinned or not)
+    PictureSample s;
+    s.imgBuffer.pixelFormat = format;
+    s.imgBuffer.bufferType = BufferType::cpu;
+    s.imgBuffer.size = size;
+    s.imgBuffer.planes = layout;
+    for (int i = 0; i < planeCount; ++i) {
+        const size_t len = (size_t)layout[i].stride * (size_t)(int)layout[i].size.y;
+        std::memcpy(base.get() + offs[i], planes[i], len);
+        s.imgBuffer.buffers.push_back(HostData{base, base.get() + offs[i], len});
+    }
+    s.idAsset = assetId;
+    s.idWorkspace = workspaceId;
+    s.idRevision = assetId;
+    return s;
+}
+
 // createTexture (compute.cuda.swift:413-431): one device buffer of stride*height per plane.
 static std::vector<std::shared_ptr<ComputeBuffer>> createTexture(const ComputeContext& ctx, const ImageBuffer& image, int maxPlanes) {
     if (image.bufferType != BufferType::cpu) return image.computeTextures;
@@ -475,6 +511,10 @@ ComputeContext runComputeKernel(const ComputeContext& ctxIn, const std::vector<c
     for (const PictureSample* im : images)
         if (im->bufferType() != BufferType::gpu) throw ComputeError(ErrorCode::badInputData, "Input images must be uploaded to GPU");
     if (target.imgBuffer.planes.empty() || target.imgBuffer.computeTextures.empty()) throw ComputeError(ErrorCode::badTarget, "badTarget");
+    if (kernel != ComputeKernel::custom)  // the built-in kernels derive the output pitch from the launch size, as upstream's do
+        for (const Plane& p : target.imgBuffer.planes)
+            if (p.stride != (int)p.size.x * (int)p.components.size())
+                throw ComputeError(ErrorCode::badTarget, "badTarget: the per-layer kernels need a target without row padding");
     ComputeContext ctx = maybeBuildKernel(ctxIn, kernel, customName);
     const std::string name = kernel == ComputeKernel::custom ? customName : computeKernelName(kernel);
     auto it = ctx.library.find(name);

@@ -152,6 +152,12 @@ std::vector<Plane> planesForFormat(PixelFormat f, Vector2 size);  // :275-294
 PictureSample createPictureSample(Vector2 size, PixelFormat format, const std::string& assetId,
                                   const std::string& workspaceId, struct ComputeContext* pinnedFrom = nullptr);
 
+// ImageBuffer(pixelFormat:bufferType:size:buffers:planes:) + PictureSample(img, ...) (sample.pict.linux.swift:23-39,160-189):
+// a CPU sample over caller-described planes -- what the FFmpeg decoder builds with its own linesize as stride
+// (SwiftVideo_FFmpeg/dec.video.ffmpeg.swift:144-220).  The bytes are copied (stride * rows per plane).
+PictureSample pictureSampleFromPlanes(PixelFormat format, Vector2 size, const uint8_t* const* planes, const int* strides, int planeCount,
+                                      const std::string& assetId, const std::string& workspaceId, struct ComputeContext* pinnedFrom = nullptr);
+
 // ---- devices / context ---------------------------------------------------------------------------------
 enum class ComputeDeviceType : int { GPU, CPU, Accelerator, Default };
 struct ComputeDevice {  // compute.cuda.swift:23-30

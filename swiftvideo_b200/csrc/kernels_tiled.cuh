@@ -3,23 +3,28 @@
 // svb_mix_tables (a small pre-pass per batch): for every separable YUV layer (no rotation: x outputs depend on x
 // only and y outputs on y only -- the planner proves it from the uniforms) the reference's per-pixel coordinate
 // chain (kernels.cl.swift:70-78 followed by the OpenCL 1.2 linear sampler's i0/i1/frac) is evaluated bit-exactly
-// once per output COLUMN and once per output ROW, into a table in global memory (L2-resident).
+// once per output COLUMN and once per output ROW, into a table in global memory (L2-resident; layout: svb_desc.h).
 //
 // svb_mix_tiled: a CTA owns 128x32 luma tiles of the output frames of the batch, dealt round-robin in row-major
 // order to a grid sized to the SM count (neighbouring tiles run at the same time, so the source lines they share
-// are fetched from HBM once).  The running picture of a tile lives in registers -- a thread owns 4 columns x 4
-// rows of luma and the 2x2 chroma texels under them, held as integer-valued floats -- and is re-quantised to
-// 8 bits after every layer, so the bytes equal the reference's clear-then-fold over an 8-bit target
-// (mix.video.swift:113-125).  Per tile every layer is planned first (one thread per layer):
-//   skip     the layer's rectangle misses the tile
-//   staged   the tile lies wholly inside the layer's picture: the source footprint is staged by one TMA 2-D
-//            tensor copy per plane (cp.async.bulk.tensor + mbarrier), double-buffered so that the copy of the
-//            next staged layer flies while this one is computed; a pixel then costs four byte taps from shared
-//            memory, the UNORM8 reads, the bilinear sum, the blend and the re-quantisation -- all as packed
-//            fp32x2 instructions (FMUL2 / FFMA2: two pixels per issue slot, each lane rounded separately)
-//   direct   same, footprint too large to stage: taps come straight from the planes
-//   edge     the tile straddles the picture's edge: table path with a per-pixel class (picture / fill / untouched)
-//   generic  rotated layers and BGRA/RGBA sources: the per-pixel evaluator of svb_device.cuh.
+// are fetched from HBM once).  The running picture of a tile lives in registers -- a thread owns two column pairs
+// (2*lane, 2*lane+1) and (64+2*lane, 65+2*lane) x 4 rows of luma and the 2x2 chroma texels under them, held as
+// integer-valued floats -- and is re-quantised to 8 bits after every layer, so the bytes equal the reference's
+// clear-then-fold over an 8-bit target (mix.video.swift:113-125).  (Column pairs rather than four adjacent
+// columns: neighbouring lanes then read neighbouring taps, 2*scale bytes apart, so a warp's byte taps fall in
+// distinct banks up to a 2:1 downscale -- with four columns per lane 43 % of the shared-memory wavefronts of the
+// v6 kernel were bank-conflict replays.)  Per tile every layer is planned first (one thread per layer):
+//   skip         the layer's rectangle misses the tile
+//   staged       the tile lies wholly inside the layer's picture: the source footprint is staged by one TMA 2-D
+//                tensor copy per plane (cp.async.bulk.tensor + mbarrier) and the tile's table blocks by two bulk
+//                copies, double-buffered so that the copies of the next staged layer fly while this one is
+//                computed; a pixel then costs four byte taps from shared memory, the UNORM8 reads, the bilinear
+//                sum, the blend and the re-quantisation -- all as packed fp32x2 instructions (FMUL2 / FFMA2: two
+//                pixels per issue slot, each lane rounded separately)
+//   staged edge  the tile straddles the picture's edge: the same, with a per-pixel class (picture / fill /
+//                untouched) from the tables' ok bits
+//   generic      rotated layers, BGRA/RGBA sources and footprints too large to stage: the per-pixel evaluator of
+//                svb_device.cuh.
 #pragma once
 #include "svb_device.cuh"
 
@@ -140,11 +145,11 @@ __device__ __forceinline__ float2 bilin2(float2 w00, float2 w10, float2 w01, flo
     return add2<PK>(add2<PK>(add2<PK>(mul2<PK>(w00, t00), mul2<PK>(w10, t10), one), mul2<PK>(w01, t01), one), mul2<PK>(w11, t11), one);
 }
 
-#define SVB_TILE_TAB_ENTS (SVB_TILE_W + SVB_TILE_W / 2 + SVB_TILE_H + SVB_TILE_H / 2)  // colY | colC | rowY | rowC of one tile
+#define SVB_TILE_TAB_WORDS (SVB_TAB_COL_WORDS + SVB_TAB_ROW_WORDS)  // the column block and the row block of one tile
 struct TiledSmem {
     alignas(128) uint8_t boxY[2][SVB_BOX_Y_BYTES];
     alignas(128) uint8_t boxC[2][SVB_BOX_C_BYTES];
-    alignas(16) Ent tabs[2][SVB_TILE_TAB_ENTS];  // the staged layer's table slices, copied with its boxes
+    alignas(16) uint32_t tabs[2][SVB_TILE_TAB_WORDS];  // the staged layer's table blocks, copied with its boxes
     alignas(8) uint64_t bar[2];
     int4 plan[2][SVB_MAX_LAYERS][2];  // [tile parity][l][0] = (mode, iy0, jy0, ic0), [..][1] = (jc0, 0, 0, 0)
 };
@@ -157,10 +162,12 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned b
                  : "memory");
 }
 
-__device__ __forceinline__ Ent ld_ent(const Ent* __restrict__ p) {
-    const int4 v = __ldg(reinterpret_cast<const int4*>(p));
+// table words of an entry (svb_desc.h): a, and p = i0 | (i1 - i0) << 16 | ok << 17  (i1 - i0 is 0 or 1: both are clamps
+// of consecutive integers; the planner keeps planes wider than 65535 texels off this path)
+__device__ __forceinline__ uint32_t pack_ent(const Ent& e) { return (uint32_t)e.i0 | ((uint32_t)(e.i1 - e.i0) << 16) | ((uint32_t)e.ok << 17); }
+__device__ __forceinline__ Ent unpack_ent(uint32_t a, uint32_t p) {
     Ent e;
-    e.a = __int_as_float(v.x), e.i0 = v.y, e.i1 = v.z, e.ok = v.w;
+    e.a = __uint_as_float(a), e.i0 = (int)(p & 0xffffu), e.i1 = e.i0 + (int)((p >> 16) & 1u), e.ok = (int)(p >> 17);
     return e;
 }
 __device__ __forceinline__ unsigned lds_u8(unsigned addr) {  // opaque u32 (see ldg_u8)
@@ -169,22 +176,26 @@ __device__ __forceinline__ unsigned lds_u8(unsigned addr) {  // opaque u32 (see 
     return v;
 }
 
-// Tables of one layer of one frame
+// Tables of one layer of one frame: tiles_x column blocks, then tiles_y row blocks
 struct Tabs {
-    const Ent* colY;
-    const Ent* colC;
-    const Ent* rowY;
-    const Ent* rowC;
+    const uint32_t* col;
+    const uint32_t* row;
 };
-__device__ __forceinline__ Tabs layer_tabs(const Ent* __restrict__ tables, const SvbFrameDesc* __restrict__ F, int l) {
-    const int W = F->width, H = F->height;
+__device__ __forceinline__ Tabs layer_tabs(const uint32_t* __restrict__ tables, const SvbFrameDesc* __restrict__ F, int l) {
     Tabs t;
-    t.colY = tables + F->table_base + (size_t)l * SVB_TABLE_ENTRIES(W, H);
-    t.colC = t.colY + W;
-    t.rowY = t.colC + W / 2;
-    t.rowC = t.rowY + H;
+    t.col = tables + F->table_base + (size_t)l * (size_t)(F->tiles_x * SVB_TAB_COL_WORDS + F->tiles_y * SVB_TAB_ROW_WORDS);
+    t.row = t.col + F->tiles_x * SVB_TAB_COL_WORDS;
     return t;
 }
+// word offsets of an entry's `a` inside its layer's tables, and from there to its `p`
+__device__ __forceinline__ int col_y_word(int x) { return (x / SVB_TILE_W) * SVB_TAB_COL_WORDS + (x % SVB_TILE_W); }
+__device__ __forceinline__ int col_c_word(int c) { return (c / (SVB_TILE_W / 2)) * SVB_TAB_COL_WORDS + 2 * SVB_TILE_W + (c % (SVB_TILE_W / 2)); }
+__device__ __forceinline__ int row_y_word(int r) { return (r / SVB_TILE_H) * SVB_TAB_ROW_WORDS + 2 * (r % SVB_TILE_H); }
+__device__ __forceinline__ int row_c_word(int c) { return (c / (SVB_TILE_H / 2)) * SVB_TAB_ROW_WORDS + 2 * SVB_TILE_H + 2 * (c % (SVB_TILE_H / 2)); }
+__device__ __forceinline__ Ent ld_col_y(const Tabs& t, int x) { const uint32_t* p = t.col + col_y_word(x); return unpack_ent(__ldg(p), __ldg(p + SVB_TILE_W)); }
+__device__ __forceinline__ Ent ld_col_c(const Tabs& t, int c) { const uint32_t* p = t.col + col_c_word(c); return unpack_ent(__ldg(p), __ldg(p + SVB_TILE_W / 2)); }
+__device__ __forceinline__ Ent ld_row_y(const Tabs& t, int r) { const uint32_t* p = t.row + row_y_word(r); return unpack_ent(__ldg(p), __ldg(p + 1)); }
+__device__ __forceinline__ Ent ld_row_c(const Tabs& t, int c) { const uint32_t* p = t.row + row_c_word(c); return unpack_ent(__ldg(p), __ldg(p + 1)); }
 
 // One separable YUV layer over one tile, taps staged in shared memory.
 //   Yi / Ui / Vi: the running picture as integer-valued floats; pairs hold two horizontally adjacent samples.
@@ -196,7 +207,7 @@ struct FillTerms {
     float2 fy, fu, fv, af, naf;  // RGB2YUV(fillColor.rgb, 1) splat; opacity*fillColor.w and its complement
 };
 template <int MODE, bool PK>
-__device__ __forceinline__ void fast_layer(unsigned boxY, unsigned boxU, unsigned boxV, const Ent* __restrict__ tabs, int lane, int warp, int lastr, int iy0, int jy0,
+__device__ __forceinline__ void fast_layer(unsigned boxY, unsigned boxU, unsigned boxV, const uint32_t* __restrict__ tabs, int lane, int warp, int iy0, int jy0,
                                            int ic0, int jc0, int pitchY, int pitchC, int stepC, float alpha, float onef, const FillTerms& ft,
                                            float2 (&Yi)[4][2], float2 (&Ui)[2], float2 (&Vi)[2]) {
     constexpr bool UNIT = MODE == 0, GEN = MODE == 2;
@@ -205,17 +216,22 @@ __device__ __forceinline__ void fast_layer(unsigned boxY, unsigned boxU, unsigne
     int okc[4];
     float2 A[2], NA[2];
 #pragma unroll
-    for (int p = 0; p < 2; ++p) {
-        const Ent e0 = tabs[4 * lane + 2 * p], e1 = tabs[4 * lane + 2 * p + 1];
-        o0[2 * p] = boxY + (e0.i0 - iy0), o1[2 * p] = boxY + (e0.i1 - iy0);
-        o0[2 * p + 1] = boxY + (e1.i0 - iy0), o1[2 * p + 1] = boxY + (e1.i1 - iy0);
-        okc[2 * p] = e0.ok, okc[2 * p + 1] = e1.ok;
-        A[p] = make_float2(e0.a, e1.a);
-        NA[p] = make_float2(sub(1.f, e0.a), sub(1.f, e1.a));
+    for (int p = 0; p < 2; ++p) {  // pair p = luma columns 64p + 2*lane, +1 of the tile: 8-byte reads, lane after lane
+        const float2 a = *reinterpret_cast<const float2*>(tabs + 64 * p + 2 * lane);
+        const uint2 e = *reinterpret_cast<const uint2*>(tabs + SVB_TILE_W + 64 * p + 2 * lane);
+        o0[2 * p] = boxY + ((e.x & 0xffffu) - iy0), o1[2 * p] = o0[2 * p] + ((e.x >> 16) & 1u);
+        o0[2 * p + 1] = boxY + ((e.y & 0xffffu) - iy0), o1[2 * p + 1] = o0[2 * p + 1] + ((e.y >> 16) & 1u);
+        okc[2 * p] = (int)(e.x >> 17), okc[2 * p + 1] = (int)(e.y >> 17);
+        A[p] = a;
+        NA[p] = make_float2(sub(1.f, a.x), sub(1.f, a.y));
     }
-    const Ent c0 = tabs[SVB_TILE_W + 2 * lane], c1 = tabs[SVB_TILE_W + 2 * lane + 1];
-    const unsigned oc00 = (c0.i0 - ic0) * stepC, oc01 = (c0.i1 - ic0) * stepC, oc10 = (c1.i0 - ic0) * stepC, oc11 = (c1.i1 - ic0) * stepC;
-    const float2 AC = make_float2(c0.a, c1.a), NAC = make_float2(sub(1.f, c0.a), sub(1.f, c1.a));
+    // chroma columns lane and 32 + lane of the tile (the texels under the two luma pairs)
+    const uint32_t pc0 = tabs[2 * SVB_TILE_W + SVB_TILE_W / 2 + lane], pc1 = tabs[2 * SVB_TILE_W + SVB_TILE_W / 2 + 32 + lane];
+    const unsigned oc00 = ((pc0 & 0xffffu) - ic0) * stepC, oc01 = oc00 + ((pc0 >> 16) & 1u) * stepC;
+    const unsigned oc10 = ((pc1 & 0xffffu) - ic0) * stepC, oc11 = oc10 + ((pc1 >> 16) & 1u) * stepC;
+    const int okc0 = (int)(pc0 >> 17), okc1 = (int)(pc1 >> 17);
+    const float2 AC = make_float2(__uint_as_float(tabs[2 * SVB_TILE_W + lane]), __uint_as_float(tabs[2 * SVB_TILE_W + 32 + lane]));
+    const float2 NAC = make_float2(sub(1.f, AC.x), sub(1.f, AC.y));
     // blend -> UNORM8 write -> the next layer's UNORM8 read stays an integer-valued float
     auto settle = [&](float2 cur_i, float2 v, float2 fillc, float lo, int ok0, int ok1) -> float2 {
         if (UNIT) return quant2<false, PK>(v, ONE);
@@ -230,11 +246,13 @@ __device__ __forceinline__ void fast_layer(unsigned boxY, unsigned boxU, unsigne
         out.y = ok1 == 7 ? qi.y : ((ok1 & 1) ? qf.y : cur_i.y);
         return out;
     };
+    const uint32_t* __restrict__ rows = tabs + SVB_TAB_COL_WORDS;  // rows past the frame's bottom hold the last row's entry
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        const Ent ry = tabs[SVB_TILE_W + SVB_TILE_W / 2 + min(4 * warp + r, lastr)];  // rows past the frame's bottom are computed and dropped
-        const unsigned r0 = (ry.i0 - jy0) * pitchY, r1 = (ry.i1 - jy0) * pitchY;
-        const float2 B = splat(ry.a), NB = splat(sub(1.f, ry.a));
+        const uint2 ry = *reinterpret_cast<const uint2*>(rows + 2 * (4 * warp + r));
+        const unsigned r0 = ((ry.y & 0xffffu) - jy0) * pitchY, r1 = r0 + ((ry.y >> 16) & 1u) * pitchY;
+        const int okr = (int)(ry.y >> 17);
+        const float2 B = splat(__uint_as_float(ry.x)), NB = splat(sub(1.f, __uint_as_float(ry.x)));
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
             const unsigned a0 = o0[2 * p], a1 = o1[2 * p], b0 = o0[2 * p + 1], b1 = o1[2 * p + 1];
@@ -243,21 +261,22 @@ __device__ __forceinline__ void fast_layer(unsigned boxY, unsigned boxU, unsigne
             const float2 t01 = unorm2<PK>(bytes2(lds_u8(r1 + a0), lds_u8(r1 + b0)));
             const float2 t11 = unorm2<PK>(bytes2(lds_u8(r1 + a1), lds_u8(r1 + b1)));
             const float2 v = bilin2<PK>(mul2<PK>(NA[p], NB), mul2<PK>(A[p], NB), mul2<PK>(NA[p], B), mul2<PK>(A[p], B), t00, t10, t01, t11, ONE);
-            Yi[r][p] = settle(Yi[r][p], v, ft.fy, 0.f, okc[2 * p] & ry.ok, okc[2 * p + 1] & ry.ok);
+            Yi[r][p] = settle(Yi[r][p], v, ft.fy, 0.f, okc[2 * p] & okr, okc[2 * p + 1] & okr);
         }
         if ((r & 1) == 0) {
             const int k = r >> 1;
-            const Ent rc = tabs[SVB_TILE_W + SVB_TILE_W / 2 + SVB_TILE_H + min(2 * warp + k, lastr >> 1)];
-            const unsigned q0 = (rc.i0 - jc0) * pitchC, q1 = (rc.i1 - jc0) * pitchC;
-            const float2 BC = splat(rc.a), NBC = splat(sub(1.f, rc.a));
+            const uint2 rc = *reinterpret_cast<const uint2*>(rows + 2 * SVB_TILE_H + 2 * (2 * warp + k));
+            const unsigned q0 = ((rc.y & 0xffffu) - jc0) * pitchC, q1 = q0 + ((rc.y >> 16) & 1u) * pitchC;
+            const int okq = (int)(rc.y >> 17);
+            const float2 BC = splat(__uint_as_float(rc.x)), NBC = splat(sub(1.f, __uint_as_float(rc.x)));
             const float2 w00 = mul2<PK>(NAC, NBC), w10 = mul2<PK>(AC, NBC), w01 = mul2<PK>(NAC, BC), w11 = mul2<PK>(AC, BC);
             const unsigned u0 = boxU + q0, u1 = boxU + q1, v0 = boxV + q0, v1 = boxV + q1;
             const float2 u = bilin2<PK>(w00, w10, w01, w11, unorm2<PK>(bytes2(lds_u8(u0 + oc00), lds_u8(u0 + oc10))), unorm2<PK>(bytes2(lds_u8(u0 + oc01), lds_u8(u0 + oc11))),
                                         unorm2<PK>(bytes2(lds_u8(u1 + oc00), lds_u8(u1 + oc10))), unorm2<PK>(bytes2(lds_u8(u1 + oc01), lds_u8(u1 + oc11))), ONE);
             const float2 v = bilin2<PK>(w00, w10, w01, w11, unorm2<PK>(bytes2(lds_u8(v0 + oc00), lds_u8(v0 + oc10))), unorm2<PK>(bytes2(lds_u8(v0 + oc01), lds_u8(v0 + oc11))),
                                         unorm2<PK>(bytes2(lds_u8(v1 + oc00), lds_u8(v1 + oc10))), unorm2<PK>(bytes2(lds_u8(v1 + oc01), lds_u8(v1 + oc11))), ONE);
-            Ui[k] = settle(Ui[k], u, ft.fu, -1.f, c0.ok & rc.ok, c1.ok & rc.ok);
-            Vi[k] = settle(Vi[k], v, ft.fv, -1.f, c0.ok & rc.ok, c1.ok & rc.ok);
+            Ui[k] = settle(Ui[k], u, ft.fu, -1.f, okc0 & okq, okc1 & okq);
+            Vi[k] = settle(Vi[k], v, ft.fv, -1.f, okc0 & okq, okc1 & okq);
         }
     }
 }
@@ -265,17 +284,19 @@ __device__ __forceinline__ void fast_layer(unsigned boxY, unsigned boxU, unsigne
 // Any layer, any tile: the per-pixel evaluator of svb_device.cuh over this thread's 4x4 block.  Kept compact (one
 // copy of the evaluator, pixels in a rolled loop over a local copy of the block) so that it does not crowd the
 // instruction cache of the fast path; rotated layers, BGRA/RGBA sources and footprints too large to stage come here.
-__device__ __noinline__ void generic_layer(const SvbLayerDesc* __restrict__ L, int xt, int yt, float fW, float fH, int H, float* __restrict__ st) {
+__device__ __noinline__ void generic_layer(const SvbLayerDesc* __restrict__ L, int xt, int yt, float fW, float fH, int W, int H, float* __restrict__ st) {
     const Src s = layer_src(L);
     const SvbUniforms* __restrict__ U = &L->u;
 #pragma unroll 1
     for (int q = 0; q < 16; ++q) {
         const int r = q >> 2, c = q & 3;
         if (yt + r >= H) break;
+        const int x = xt + (c & 1) + (SVB_TILE_W / 2) * (c >> 1);  // columns xt, xt+1, xt+64, xt+65
+        if (x >= W) continue;
         const bool chroma = ((r | c) & 1) == 0;
         const int ci = 16 + (r >> 1) * 2 + (c >> 1);  // st[16..19] = U texels, st[20..23] = V texels
         float oy, ou, ov;
-        if (eval_pixel(U, s, xt + c, yt + r, fW, fH, chroma, unorm_f(st[q]), chroma ? unorm_f(st[ci]) : 0.f, chroma ? unorm_f(st[ci + 4]) : 0.f, oy, ou,
+        if (eval_pixel(U, s, x, yt + r, fW, fH, chroma, unorm_f(st[q]), chroma ? unorm_f(st[ci]) : 0.f, chroma ? unorm_f(st[ci + 4]) : 0.f, oy, ou,
                        ov)) {
             st[q] = quantf(oy);
             if (chroma) st[ci] = quantf(ou), st[ci + 4] = quantf(ov);
@@ -283,15 +304,15 @@ __device__ __noinline__ void generic_layer(const SvbLayerDesc* __restrict__ L, i
     }
 }
 
-__device__ __forceinline__ unsigned pack4(float2 a, float2 b) {  // four integer-valued floats in 0..255 -> bytes
-    return __float2uint_rn(a.x) | (__float2uint_rn(a.y) << 8) | (__float2uint_rn(b.x) << 16) | (__float2uint_rn(b.y) << 24);
+__device__ __forceinline__ unsigned short pack2(float a, float b) {  // two integer-valued floats in 0..255 -> bytes
+    return (unsigned short)(__float2uint_rn(a) | (__float2uint_rn(b) << 8));
 }
 
 }  // namespace svb
 
 // ---- pre-pass: coordinate tables of every separable YUV layer of every frame of the batch -----------------------
-// grid (ceil(max entries / 256), max layers, frames); one entry per thread.
-extern "C" __global__ void __launch_bounds__(256) svb_mix_tables(const SvbFrameDesc* __restrict__ frames, svb::Ent* __restrict__ tables) {
+// grid (ceil(entries / 256), max layers, frames); one entry (two words) per thread, blocks padded to whole tiles.
+extern "C" __global__ void __launch_bounds__(256) svb_mix_tables(const SvbFrameDesc* __restrict__ frames, uint32_t* __restrict__ tables) {
     using namespace svb;
     const SvbFrameDesc* __restrict__ F = frames + blockIdx.z;
     const int l = blockIdx.y;
@@ -299,17 +320,24 @@ extern "C" __global__ void __launch_bounds__(256) svb_mix_tables(const SvbFrameD
     const SvbLayerDesc* __restrict__ L = &F->layers[l];
     if (!(L->flags & SVB_LAYER_SEPARABLE) || (L->format != SVB_NV12 && L->format != SVB_Y420P)) return;
     const int W = F->width, H = F->height;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= SVB_TABLE_ENTRIES(W, H)) return;
-    Ent* __restrict__ out = tables + F->table_base + (size_t)l * SVB_TABLE_ENTRIES(W, H) + e;
-    if (e < W) {
-        *out = axis_entry(axis_chain(&L->u, 0, e, (float)W), L->width);
-    } else if (e < W + W / 2) {  // chroma is produced by the even luma column (kernels.cl.swift:76)
-        *out = axis_entry(axis_chain(&L->u, 0, 2 * (e - W), (float)W), L->width / 2);
-    } else if (e < W + W / 2 + H) {
-        *out = axis_entry(axis_chain(&L->u, 1, e - W - W / 2, (float)H), L->height);
+    const int ncy = F->tiles_x * SVB_TILE_W, ncc = ncy / 2, nry = F->tiles_y * SVB_TILE_H, nrc = nry / 2;
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ncy + ncc + nry + nrc) return;
+    uint32_t* __restrict__ base = tables + F->table_base + (size_t)l * (size_t)(F->tiles_x * SVB_TAB_COL_WORDS + F->tiles_y * SVB_TAB_ROW_WORDS);
+    uint32_t* __restrict__ rbase = base + F->tiles_x * SVB_TAB_COL_WORDS;
+    if (e < ncy) {
+        const Ent t = axis_entry(axis_chain(&L->u, 0, min(e, W - 1), (float)W), L->width);
+        base[col_y_word(e)] = __float_as_uint(t.a), base[col_y_word(e) + SVB_TILE_W] = pack_ent(t);
+    } else if ((e -= ncy) < ncc) {  // chroma is produced by the even luma column / row (kernels.cl.swift:76)
+        const Ent t = axis_entry(axis_chain(&L->u, 0, min(2 * e, W - 2), (float)W), L->width / 2);
+        base[col_c_word(e)] = __float_as_uint(t.a), base[col_c_word(e) + SVB_TILE_W / 2] = pack_ent(t);
+    } else if ((e -= ncc) < nry) {
+        const Ent t = axis_entry(axis_chain(&L->u, 1, min(e, H - 1), (float)H), L->height);
+        rbase[row_y_word(e)] = __float_as_uint(t.a), rbase[row_y_word(e) + 1] = pack_ent(t);
     } else {
-        *out = axis_entry(axis_chain(&L->u, 1, 2 * (e - W - W / 2 - H), (float)H), L->height / 2);
+        e -= nry;
+        const Ent t = axis_entry(axis_chain(&L->u, 1, min(2 * e, H - 2), (float)H), L->height / 2);
+        rbase[row_c_word(e)] = __float_as_uint(t.a), rbase[row_c_word(e) + 1] = pack_ent(t);
     }
 }
 
@@ -336,7 +364,7 @@ __device__ __forceinline__ TileGeo tile_geo(const SvbFrameDesc* __restrict__ fra
 }
 
 // Plan of layer `l` on one tile (executed by one thread per layer).
-__device__ __forceinline__ void plan_layer(const Ent* __restrict__ tables, const TileGeo& g, int l, int4* __restrict__ out) {
+__device__ __forceinline__ void plan_layer(const uint32_t* __restrict__ tables, const TileGeo& g, int l, int4* __restrict__ out) {
     const SvbFrameDesc* __restrict__ F = g.F;
     const SvbLayerDesc* __restrict__ L = &F->layers[l];
     const int x0 = g.x0, y0 = g.y0;
@@ -347,9 +375,9 @@ __device__ __forceinline__ void plan_layer(const Ent* __restrict__ tables, const
         mode = PLAN_GENERIC;
     } else {
         const Tabs tb = layer_tabs(tables, F, l);
-        const Ent cA = ld_ent(tb.colY + x0), cB = ld_ent(tb.colY + x0 + g.lastc), rA = ld_ent(tb.rowY + y0), rB = ld_ent(tb.rowY + y0 + g.lastr);
-        const Ent ccA = ld_ent(tb.colC + (x0 >> 1)), ccB = ld_ent(tb.colC + ((x0 + g.lastc) >> 1));
-        const Ent rcA = ld_ent(tb.rowC + (y0 >> 1)), rcB = ld_ent(tb.rowC + ((y0 + g.lastr) >> 1));
+        const Ent cA = ld_col_y(tb, x0), cB = ld_col_y(tb, x0 + g.lastc), rA = ld_row_y(tb, y0), rB = ld_row_y(tb, y0 + g.lastr);
+        const Ent ccA = ld_col_c(tb, x0 >> 1), ccB = ld_col_c(tb, (x0 + g.lastc) >> 1);
+        const Ent rcA = ld_row_c(tb, y0 >> 1), rcB = ld_row_c(tb, (y0 + g.lastr) >> 1);
         // source footprint of the tile: the clamped tap indices are monotone along each axis, so the ends bound it;
         // x origins are rounded down to 16 bytes for TMA
         iy0 = min(cA.i0, cB.i0) & ~15;
@@ -369,7 +397,7 @@ __device__ __forceinline__ void plan_layer(const Ent* __restrict__ tables, const
 }  // namespace svb
 
 extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CTAS)  // 8 compute warps + 1 producer warp
-    svb_mix_tiled(const SvbFrameDesc* __restrict__ frames, const svb::Ent* __restrict__ tables, int nframes, int total_tiles, float one) {
+    svb_mix_tiled(const SvbFrameDesc* __restrict__ frames, const uint32_t* __restrict__ tables, int nframes, int total_tiles, float one) {
     using namespace svb;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TiledSmem& sm = *reinterpret_cast<TiledSmem*>(smem_raw);
@@ -398,9 +426,10 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CT
         const TileGeo g = tile_geo(frames, nframes, f, tile);
         const SvbFrameDesc* __restrict__ F = g.F;
         const int W = F->width, H = F->height, nl = F->nlayers;
-        const int x0 = g.x0, y0 = g.y0, lastr = g.lastr;
-        const int xt = x0 + 4 * lane, yt = y0 + 4 * warp;  // this thread's 4x4 block
-        const bool live = !producer && xt < W && yt < H;    // W % 4 == 0 and H even are planner preconditions
+        const int x0 = g.x0, y0 = g.y0;
+        const int xt = x0 + 2 * lane, yt = y0 + 4 * warp;  // this thread's columns xt, xt+1, xt+64, xt+65 x rows yt..yt+3
+        const bool live = !producer && xt < W && yt < H;    // W and H even are planner preconditions
+        const bool live1 = xt + SVB_TILE_W / 2 < W;          // the second column pair is inside the frame
         const bool nv12 = F->format == SVB_NV12;
         const float fW = (float)W, fH = (float)H;
         uint8_t* const oY = (uint8_t*)F->out_plane[0];
@@ -416,7 +445,6 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CT
             const int4 p0 = pl[l][0], p1 = pl[l][1];
             const bool n12 = L->format == SVB_NV12;
             const int cbytes = n12 ? L->box_cw * L->box_ch * 2 : L->box_cw * L->box_ch;
-            const int ncy = tg.lastc + 1, nry = tg.lastr + 1;
             const Tabs tb = layer_tabs(tables, TF, l);
             if (TF != fenced) {  // the host rewrites the descriptors between launches: acquire a frame's maps once per CTA
                 for (int q = 0; q < TF->nlayers; ++q)
@@ -427,15 +455,12 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CT
                     }
                 fenced = TF;
             }
-            mbar_expect_tx(&sm.bar[b], L->box_w * L->box_h + cbytes * (n12 ? 1 : 2) + (ncy + ncy / 2 + nry + nry / 2) * (int)sizeof(Ent));
+            mbar_expect_tx(&sm.bar[b], L->box_w * L->box_h + cbytes * (n12 ? 1 : 2) + SVB_TILE_TAB_WORDS * 4);
             tma_load_2d(sm.boxY[b], L->tmap[0], p0.y, p0.z, &sm.bar[b]);
             tma_load_2d(sm.boxC[b], L->tmap[1], p0.w, p1.x, &sm.bar[b]);
             if (!n12) tma_load_2d(sm.boxC[b] + SVB_BOX_C_BYTES / 2, L->tmap[2], p0.w, p1.x, &sm.bar[b]);
-            Ent* dst = sm.tabs[b];
-            bulk_load(dst, tb.colY + tg.x0, ncy * sizeof(Ent), &sm.bar[b]);
-            bulk_load(dst + SVB_TILE_W, tb.colC + (tg.x0 >> 1), (ncy / 2) * sizeof(Ent), &sm.bar[b]);
-            bulk_load(dst + SVB_TILE_W + SVB_TILE_W / 2, tb.rowY + tg.y0, nry * sizeof(Ent), &sm.bar[b]);
-            bulk_load(dst + SVB_TILE_W + SVB_TILE_W / 2 + SVB_TILE_H, tb.rowC + (tg.y0 >> 1), (nry / 2) * sizeof(Ent), &sm.bar[b]);
+            bulk_load(sm.tabs[b], tb.col + (tg.x0 / SVB_TILE_W) * SVB_TAB_COL_WORDS, SVB_TAB_COL_WORDS * 4, &sm.bar[b]);
+            bulk_load(sm.tabs[b] + SVB_TAB_COL_WORDS, tb.row + (tg.y0 / SVB_TILE_H) * SVB_TAB_ROW_WORDS, SVB_TAB_ROW_WORDS * 4, &sm.bar[b]);
         };
         // first staged layer of `pl`, or -1
         auto first_staged = [&](const int4(*pl)[2], int from, int n) {
@@ -465,19 +490,21 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CT
 #pragma unroll
             for (int r = 0; r < 4; ++r)
                 if (yt + r < H) {
-                    const unsigned w = *(const unsigned*)(oY + (size_t)(yt + r) * sY + xt);
-                    Yi[r][0] = bytes2(opaque(w & 0xff), opaque((w >> 8) & 0xff)), Yi[r][1] = bytes2(opaque((w >> 16) & 0xff), opaque(w >> 24));
+                    const uint8_t* row = oY + (size_t)(yt + r) * sY + xt;
+                    const unsigned w0 = *(const unsigned short*)row, w1 = live1 ? *(const unsigned short*)(row + SVB_TILE_W / 2) : 0u;
+                    Yi[r][0] = bytes2(opaque(w0 & 0xff), opaque(w0 >> 8)), Yi[r][1] = bytes2(opaque(w1 & 0xff), opaque(w1 >> 8));
                 }
 #pragma unroll
             for (int k = 0; k < 2; ++k)
                 if (yt + 2 * k < H) {
-                    if (nv12) {
-                        const unsigned w = *(const unsigned*)(oU + (size_t)((yt >> 1) + k) * sU + xt);
-                        Ui[k] = bytes2(opaque(w & 0xff), opaque((w >> 16) & 0xff)), Vi[k] = bytes2(opaque((w >> 8) & 0xff), opaque(w >> 24));
+                    if (nv12) {  // chroma texel xt/2 = the (U, V) byte pair at byte xt of the row; texel xt/2 + 32 is 64 bytes on
+                        const uint8_t* row = oU + (size_t)((yt >> 1) + k) * sU + xt;
+                        const unsigned w0 = *(const unsigned short*)row, w1 = live1 ? *(const unsigned short*)(row + SVB_TILE_W / 2) : 0x8080u;
+                        Ui[k] = bytes2(opaque(w0 & 0xff), opaque(w1 & 0xff)), Vi[k] = bytes2(opaque(w0 >> 8), opaque(w1 >> 8));
                     } else {
-                        const uchar2 u = *(const uchar2*)(oU + (size_t)((yt >> 1) + k) * sU + (xt >> 1));
-                        const uchar2 v = *(const uchar2*)(oV + (size_t)((yt >> 1) + k) * sV + (xt >> 1));
-                        Ui[k] = bytes2(opaque(u.x), opaque(u.y)), Vi[k] = bytes2(opaque(v.x), opaque(v.y));
+                        const uint8_t* ru = oU + (size_t)((yt >> 1) + k) * sU + (xt >> 1);
+                        const uint8_t* rv = oV + (size_t)((yt >> 1) + k) * sV + (xt >> 1);
+                        Ui[k] = bytes2(opaque(ru[0]), opaque(live1 ? ru[SVB_TILE_W / 4] : 128u)), Vi[k] = bytes2(opaque(rv[0]), opaque(live1 ? rv[SVB_TILE_W / 4] : 128u));
                     }
                 }
         }
@@ -520,11 +547,11 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CT
                         const float3 fill = rgb2yuv(fc.x, fc.y, fc.z);
                         const float af = mul(alpha, fc.w);
                         ft.fy = splat(fill.x), ft.fu = splat(fill.y), ft.fv = splat(fill.z), ft.af = splat(af), ft.naf = splat(sub(1.f, af));
-                        fast_layer<2, true>(bY, bU, bV, sm.tabs[stage], lane, warp, lastr, p0.y, p0.z, p0.w, jc0, L->box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
+                        fast_layer<2, true>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, L->box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
                     } else if (lflags & SVB_LAYER_UNIT_OPACITY) {
-                        fast_layer<0, true>(bY, bU, bV, sm.tabs[stage], lane, warp, lastr, p0.y, p0.z, p0.w, jc0, L->box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
+                        fast_layer<0, true>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, L->box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
                     } else {
-                        fast_layer<1, true>(bY, bU, bV, sm.tabs[stage], lane, warp, lastr, p0.y, p0.z, p0.w, jc0, L->box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
+                        fast_layer<1, true>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, L->box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
                     }
                 }
                 stage ^= 1;
@@ -536,7 +563,7 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CT
                 for (int r = 0; r < 4; ++r) st[4 * r] = Yi[r][0].x, st[4 * r + 1] = Yi[r][0].y, st[4 * r + 2] = Yi[r][1].x, st[4 * r + 3] = Yi[r][1].y;
 #pragma unroll
                 for (int k = 0; k < 2; ++k) st[16 + 2 * k] = Ui[k].x, st[17 + 2 * k] = Ui[k].y, st[20 + 2 * k] = Vi[k].x, st[21 + 2 * k] = Vi[k].y;
-                generic_layer(L, xt, yt, fW, fH, H, st);
+                generic_layer(L, xt, yt, fW, fH, W, H, st);
 #pragma unroll
                 for (int r = 0; r < 4; ++r) Yi[r][0] = make_float2(st[4 * r], st[4 * r + 1]), Yi[r][1] = make_float2(st[4 * r + 2], st[4 * r + 3]);
 #pragma unroll
@@ -547,15 +574,23 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CT
         if (live) {
 #pragma unroll
             for (int r = 0; r < 4; ++r)
-                if (yt + r < H) *(unsigned*)(oY + (size_t)(yt + r) * sY + xt) = pack4(Yi[r][0], Yi[r][1]);
+                if (yt + r < H) {
+                    uint8_t* row = oY + (size_t)(yt + r) * sY + xt;
+                    *(unsigned short*)row = pack2(Yi[r][0].x, Yi[r][0].y);
+                    if (live1) *(unsigned short*)(row + SVB_TILE_W / 2) = pack2(Yi[r][1].x, Yi[r][1].y);
+                }
 #pragma unroll
             for (int k = 0; k < 2; ++k)
                 if (yt + 2 * k < H) {
                     if (nv12) {
-                        *(unsigned*)(oU + (size_t)((yt >> 1) + k) * sU + xt) = pack4(make_float2(Ui[k].x, Vi[k].x), make_float2(Ui[k].y, Vi[k].y));
+                        uint8_t* row = oU + (size_t)((yt >> 1) + k) * sU + xt;
+                        *(unsigned short*)row = pack2(Ui[k].x, Vi[k].x);
+                        if (live1) *(unsigned short*)(row + SVB_TILE_W / 2) = pack2(Ui[k].y, Vi[k].y);
                     } else {
-                        *(uchar2*)(oU + (size_t)((yt >> 1) + k) * sU + (xt >> 1)) = make_uchar2(__float2uint_rn(Ui[k].x), __float2uint_rn(Ui[k].y));
-                        *(uchar2*)(oV + (size_t)((yt >> 1) + k) * sV + (xt >> 1)) = make_uchar2(__float2uint_rn(Vi[k].x), __float2uint_rn(Vi[k].y));
+                        uint8_t* ru = oU + (size_t)((yt >> 1) + k) * sU + (xt >> 1);
+                        uint8_t* rv = oV + (size_t)((yt >> 1) + k) * sV + (xt >> 1);
+                        ru[0] = (uint8_t)__float2uint_rn(Ui[k].x), rv[0] = (uint8_t)__float2uint_rn(Vi[k].x);
+                        if (live1) ru[SVB_TILE_W / 4] = (uint8_t)__float2uint_rn(Ui[k].y), rv[SVB_TILE_W / 4] = (uint8_t)__float2uint_rn(Vi[k].y);
                     }
                 }
         }

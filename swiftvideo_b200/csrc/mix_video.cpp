@@ -189,9 +189,8 @@ FramePlan planFrame(const ComputeContext& ctx, const PictureSample& target, cons
     base.tiles_y = (H + SVB_TILE_H - 1) / SVB_TILE_H;
     // the generic kernel stores luma (and NV12 chroma) two bytes at a time
     if ((planes[0].stride & 1) || (tf == SVB_NV12 && (planes[1].stride & 1))) throw ComputeError(ErrorCode::badTarget, "target strides must be even");
-    plan.tiledOk = (W % 4 == 0) && (base.out_stride[0] % 4 == 0) && (base.out_plane[0] % 4 == 0) &&
-                   (tf == SVB_NV12 ? (base.out_stride[1] % 4 == 0 && base.out_plane[1] % 4 == 0)
-                                   : (base.out_plane[1] % 2 == 0 && base.out_plane[2] % 2 == 0));
+    // the tiled kernel stores luma and NV12 chroma two bytes at a time (Y420P chroma byte by byte)
+    plan.tiledOk = (W % 2 == 0) && (H % 2 == 0) && (base.out_plane[0] % 2 == 0) && (tf != SVB_NV12 || base.out_plane[1] % 2 == 0);
 
     MixerShared& sh = shared(ctx.ctx);
     const size_t n = layers.size();
@@ -223,7 +222,7 @@ FramePlan planFrame(const ComputeContext& ctx, const PictureSample& target, cons
         int flags = 0;
         static const bool noTables = std::getenv("SVB_NO_TABLES") != nullptr, noTma = std::getenv("SVB_NO_TMA") != nullptr;  // debugging aids
         if (!noTables && finite && T[1] == 0.f && T[4] == 0.f && T[8] == 0.f && T[9] == 0.f && T[12] == 0.f && T[13] == 0.f && B[1] == 0.f &&
-            B[4] == 0.f && X[1] == 0.f && X[4] == 0.f && (sf != SVB_Y420P || L.stride[1] == L.stride[2]))
+            B[4] == 0.f && X[1] == 0.f && X[4] == 0.f && (sf != SVB_Y420P || L.stride[1] == L.stride[2]) && L.width <= 65535 && L.height <= 65535)
             flags |= SVB_LAYER_SEPARABLE;
         if (u.opacity == 1.0f) flags |= SVB_LAYER_UNIT_OPACITY;
         if (u.opacity >= 0.f && u.opacity <= 1.f) flags |= SVB_LAYER_OPACITY_01;
@@ -279,7 +278,7 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
             fr.first_tile = total;
             total += fr.tiles_x * fr.tiles_y;
             maxW = std::max(maxW, fr.width), maxH = std::max(maxH, fr.height);
-            const int ents = SVB_TABLE_ENTRIES(fr.width, fr.height);
+            const int ents = SVB_TABLE_WORDS(fr.width, fr.height);  // 4-byte words per layer
             fr.table_base = (int32_t)tableEnts;
             tableEnts += (size_t)ents * (size_t)fr.nlayers;
             maxLayers = std::max(maxLayers, fr.nlayers), maxEnts = std::max(maxEnts, ents);
@@ -302,11 +301,11 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
         }
         if (!tiled && tev.first) check(d.cuEventRecord(tev.first, ic.compute), "cuEventRecord");
         if (tiled) {
-            // pre-pass: per-column / per-row coordinate tables of the batch (16 bytes per entry), then the compositor
-            const size_t tableBytes = std::max<size_t>(tableEnts, 1) * 16;
+            // pre-pass: per-column / per-row coordinate tables of the batch (two words per entry), then the compositor
+            const size_t tableBytes = std::max<size_t>(tableEnts, 4) * 4;
             CUdeviceptr tables = ic.alloc(tableBytes);
             void* targs[] = {&dev, &tables};
-            check(d.cuLaunchKernel(sh.fTables, (unsigned)((maxEnts + 255) / 256), (unsigned)maxLayers, (unsigned)n, 256, 1, 1, 0, ic.compute, targs, nullptr),
+            check(d.cuLaunchKernel(sh.fTables, (unsigned)((maxEnts / 2 + 255) / 256), (unsigned)maxLayers, (unsigned)n, 256, 1, 1, 0, ic.compute, targs, nullptr),
                   "cuLaunchKernel(svb_mix_tables)");
             noteKernelLaunch();
             if (tev.first) check(d.cuEventRecord(tev.first, ic.compute), "cuEventRecord");  // time svb_mix_tiled alone

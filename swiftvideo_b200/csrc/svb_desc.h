@@ -70,18 +70,28 @@ typedef struct __attribute__((aligned(64))) SvbFrameDesc {
     int32_t flags;       // SVB_FRAME_*
     int32_t first_tile;  // prefix sum of tiles over the batch
     int32_t tiles_x, tiles_y;
-    int32_t table_base;  // first entry of this frame's coordinate tables in the batch's table buffer (svb_mix_tables)
+    int32_t table_base;  // first word of this frame's coordinate tables in the batch's table buffer (svb_mix_tables)
     int32_t pad_[4];
     SvbLayerDesc layers[SVB_MAX_LAYERS];
 } SvbFrameDesc;
 
-// dynamic shared memory of svb_mix_tiled: two staged box pairs, two table slices (240 entries of 16 bytes), two
-// mbarriers, two plans of 32 bytes per layer
-#define SVB_TILED_SMEM_BYTES \
-    (2 * SVB_BOX_Y_BYTES + 2 * SVB_BOX_C_BYTES + 2 * (SVB_TILE_W + SVB_TILE_W / 2 + SVB_TILE_H + SVB_TILE_H / 2) * 16 + 128 + 2 * SVB_MAX_LAYERS * 32)
+// Coordinate tables of one layer of a WxH frame (svb_mix_tables), in 4-byte words.  An entry is a pair
+// (a, p): a = the fractional weight of the i1 tap (fp32), p = i0 | (i1 - i0) << 16 | ok << 17.  The entries are laid
+// out in tile-sized blocks, so that a tile's slice is ONE contiguous bulk copy per axis and the per-lane reads of
+// the compositor are conflict-free in shared memory:
+//   column block (one per tile column): aY[TILE_W] pY[TILE_W] aC[TILE_W/2] pC[TILE_W/2]
+//   row block    (one per tile row)   : (aY,pY)[TILE_H] (aC,pC)[TILE_H/2]
+// Blocks are padded to whole tiles with copies of the last valid entry.
+#define SVB_TAB_COL_WORDS (3 * SVB_TILE_W)
+#define SVB_TAB_ROW_WORDS (3 * SVB_TILE_H)
+#define SVB_TILES_X(W) (((W) + SVB_TILE_W - 1) / SVB_TILE_W)
+#define SVB_TILES_Y(H) (((H) + SVB_TILE_H - 1) / SVB_TILE_H)
+#define SVB_TABLE_WORDS(W, H) (SVB_TILES_X(W) * SVB_TAB_COL_WORDS + SVB_TILES_Y(H) * SVB_TAB_ROW_WORDS)
 
-// Coordinate-table entries per layer of a WxH frame: colY[W] colC[W/2] rowY[H] rowC[H/2], 16 bytes each.
-#define SVB_TABLE_ENTRIES(W, H) ((W) + (W) / 2 + (H) + (H) / 2)
+// dynamic shared memory of svb_mix_tiled: two staged box pairs, two table slices (a column block and a row block),
+// two mbarriers, two plans of 32 bytes per layer
+#define SVB_TILED_SMEM_BYTES \
+    (2 * SVB_BOX_Y_BYTES + 2 * SVB_BOX_C_BYTES + 2 * (SVB_TAB_COL_WORDS + SVB_TAB_ROW_WORDS) * 4 + 128 + 2 * SVB_MAX_LAYERS * 32)
 
 #ifdef __cplusplus
 static_assert(sizeof(SvbUniforms) == 240, "SvbUniforms layout");

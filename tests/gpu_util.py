@@ -17,7 +17,11 @@ def context():
 
 
 def to_gpu(ctx, img, asset="layer", pinned=False):
-    """O.Image -> uploaded PictureSample (same contiguous plane layout on both sides)."""
+    """O.Image -> uploaded PictureSample (same plane layout and strides on both sides)."""
+    default, _ = O.plane_layout(img.format, img.width, img.height)
+    if [l[3] for l in img.layout] != [l[3] for l in default]:  # decoder-style padded rows
+        from swiftvideo_b200 import api
+        return api.picture_sample_from_planes(img.width, img.height, FMT[img.format], img.padded_planes(), asset, "test").upload(ctx)
     p = sv.create_picture_sample(img.width, img.height, FMT[img.format], asset, "test", pinned_from=ctx if pinned else None)
     p.set_host_bytes(img.data)
     return p.upload(ctx)
@@ -33,10 +37,16 @@ def fetch(ctx, pict):
     return pict.download(ctx, retain_gpu_buffer=True).host_bytes().copy()
 
 
-def gpu_case(ctx, case, mode):
-    """Run a scenes.Case through svb_compose with the oracle's own uniforms; returns the target bytes."""
+def gpu_case(ctx, case, mode, target_strides=None):
+    """Run a scenes.Case through svb_compose with the oracle's own uniforms; returns the target bytes (padding included
+    when the target has padded rows)."""
     layers = [to_gpu(ctx, l, f"l{i}") for i, l in enumerate(case.layers)]
-    target = gpu_target(ctx, case.target_fmt, case.canvas[0], case.canvas[1])
+    if target_strides is None:
+        target = gpu_target(ctx, case.target_fmt, case.canvas[0], case.canvas[1])
+    else:
+        t = O.Image(case.target_fmt, case.canvas[0], case.canvas[1], strides=target_strides)
+        t.data[:] = 0xA5
+        target = to_gpu(ctx, t, "target")
     sv.compose(ctx, target, layers, case.uniforms, mode)
     return fetch(ctx, target)
 

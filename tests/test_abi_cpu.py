@@ -131,3 +131,28 @@ def test_animate_picture_matches_python_animator():
     assert list(q.info().fill_color) == [0, 0, 0, 0]
     mm = np.array(q.info().matrix[:]).reshape(4, 4)
     assert abs(mm[3, 0] - (2.0 / 1280 * 75 - 1)) < 1e-6 and abs(mm[3, 1] - (2.0 / 720 * 80 - 1)) < 1e-6
+
+
+def test_picture_sample_from_planes():
+    """Decoder-style planes with their own linesize (the reference wraps AVFrame.data/linesize into planes,
+    dec.video.ffmpeg.swift:176-190): strides are kept, bytes are copied, short strides are rejected."""
+    import swiftvideo_b200 as sv
+    from swiftvideo_b200 import api
+    rng = np.random.default_rng(5)
+    y = rng.integers(0, 256, (48, 64 + 16), dtype=np.uint8)
+    u = rng.integers(0, 256, (24, 32 + 16), dtype=np.uint8)
+    v = rng.integers(0, 256, (24, 32 + 8), dtype=np.uint8)
+    p = api.picture_sample_from_planes(64, 48, sv.Y420P, [y, u, v], "cam", "ws")
+    i = p.info()
+    assert i.plane_count == 3 and i.pixel_format == sv.Y420P
+    assert [i.planes[k].stride for k in range(3)] == [80, 48, 40]
+    assert [i.planes[k].width for k in range(3)] == [64, 32, 32]
+    got = p.host_planes()
+    assert (got[0] == y).all() and (got[1] == u).all() and (got[2] == v).all()
+    y[:] = 0  # the sample owns a copy
+    assert got[0].any()
+    with pytest.raises(sv.ComputeError) as e:
+        api.picture_sample_from_planes(64, 48, sv.NV12, [np.zeros((48, 60), np.uint8), np.zeros((24, 64), np.uint8)])
+    assert "stride" in str(e.value)
+    with pytest.raises(sv.ComputeError):
+        api.picture_sample_from_planes(64, 48, sv.NV12, [np.zeros((48, 64), np.uint8)])  # plane count

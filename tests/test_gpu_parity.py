@@ -126,3 +126,48 @@ def test_properties_full_size():
     want = O.Image(tf, *canvas)
     O.port().clear(want)
     assert (fetch(ctx, cleared) == want.data).all()
+
+
+def _padded(img, pads):
+    """The same picture with decoder-style padded rows (stride = row bytes + pad); padding bytes are junk."""
+    strides = [l[1] * l[4] + p for l, p in zip(img.layout, pads)]
+    out = O.Image(img.format, img.width, img.height, strides=strides)
+    out.data[:] = 0x5C
+    for i in range(len(img.layout)):
+        w, nc = img.layout[i][1], img.layout[i][4]
+        out.plane(i)[:, :] = img.plane(i)[:, : w * nc]
+    return out
+
+
+@pytest.mark.parametrize("mode,mname", MODES, ids=[m[1] for m in MODES])
+@pytest.mark.parametrize("pads", [(64, 64, 32), (16, 16, 16), (6, 6, 6), (6, 10, 2)],
+                         ids=["pad64_uv_differ", "pad16", "pad6_no_tma", "pad_unaligned"])
+def test_padded_strides(pads, mode, mname):
+    """FFmpeg hands the mixer planes whose stride is its linesize, not the width (dec.video.ffmpeg.swift:183): padded
+    sources (16-byte multiples keep the TMA path, others fall back) must give the same bytes as tight ones."""
+    base = TILED[1]  # y420p sources -> nv12 target: three planes per source
+    layers = [_padded(l, pads) for l in base.layers]
+    case = scenes.Case("padded", base.target_fmt, base.canvas, layers, base.uniforms)
+    rc, want = scenes.run_case(O.port(), base, threads=O.host_threads())
+    assert rc == 0
+    got = gpu_case(context(), case, mode)
+    assert (got == want.data).all(), f"padded/{mname}: {first_diff(got, want.data)}"
+
+
+def test_padded_target():
+    """A target with padded rows (fused and generic take explicit output strides; the per-layer kernels infer the stride
+    from the launch like the reference's, kernels.cuda.swift:151,205, so they only accept tight targets)."""
+    base = TILED[0]
+    rc, want = scenes.run_case(O.port(), base, threads=O.host_threads())
+    assert rc == 0
+    W, H = base.canvas
+    for mode, mname in MODES[:2]:
+        got = gpu_case(context(), base, mode, target_strides=[W + 64, W + 64])
+        tight = np.concatenate([got[: (W + 64) * H].reshape(H, W + 64)[:, :W].reshape(-1),
+                                got[(W + 64) * H :].reshape(H // 2, W + 64)[:, :W].reshape(-1)])
+        assert (tight == want.data).all(), f"padded target/{mname}: {first_diff(tight, want.data)}"
+        pad = got[: (W + 64) * H].reshape(H, W + 64)[:, W:]
+        assert (pad == 0xA5).all(), "padding bytes of the target were written"
+    with pytest.raises(sv.ComputeError) as e:
+        gpu_case(context(), base, sv.MixMode.PER_LAYER, target_strides=[W + 64, W + 64])
+    assert "badTarget" in str(e.value)
