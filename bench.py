@@ -150,6 +150,25 @@ def bind_to_gpu_numa(index):
 
 # ---- our arm -------------------------------------------------------------------------------------------------
 
+def measure_link(torch, device, nbytes=256 << 20, reps=5):
+    """Pinned-memory copy rate of this box's host link, each direction alone (best of `reps`, CUDA events): the bound of the
+    e2e leg, whose every step moves its inputs in and its results out."""
+    h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    out = {}
+    for name, (dst, src) in {"h2d_gbs": (d, h), "d2h_gbs": (h, d)}.items():
+        best = 1e30
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            dst.copy_(src, non_blocking=True)
+            b.record()
+            b.synchronize()
+            best = min(best, a.elapsed_time(b))
+        out[name] = round(nbytes / (best / 1e3) / 1e9, 1)
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -175,6 +194,8 @@ def run_ours(args):
     for s in range(S):
         gstream = shard_streams(rank, world, S)[s]
         for k, (ssz, pos, dsz, op) in enumerate(geo):
+            if args.pip_opacity is not None and k > 0:
+                op = args.pip_opacity
             rng = np.random.default_rng(rng_base + 16 * gstream + k)
             h = sv.create_picture_sample(ssz[0], ssz[1], sv.NV12, f"s{gstream}l{k}", "bench", pinned_from=ctx)
             h.set_host_bytes(rng.integers(0, 256, size=ssz[0] * ssz[1] * 3 // 2, dtype=np.uint8))
@@ -253,6 +274,10 @@ def run_ours(args):
     h2d = S * (12441600 + 7 * 3110400)
     d2h = S * 12441600
 
+    link = measure_link(torch, torch.device("cuda", local))
+    # both directions run at once (separate copy engines); indicative only -- the H2D rate of one big copy varies run to run (39-53 GB/s seen)
+    link["frames_per_s_at_this_copy_rate"] = round(S * world / max(h2d / (link["h2d_gbs"] * 1e9), d2h / (link["d2h_gbs"] * 1e9)), 1)
+
     peak, peak_src = peaks()
     roof = None
     if kern_n and args.mode != "per_layer":  # the per-layer sequence has no single dominant launch to put on a roofline
@@ -273,11 +298,11 @@ def run_ours(args):
         "metric": METRIC, "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms / args.steps, 4), "host_queue_ms_per_step": round(host_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8 (fp32 arithmetic, no FMA contraction)", "data": "synthetic (uniform u8 planes, seeded)",
-        "config": {"workload": WORKLOAD, "mode": args.mode, "streams_total": S * world, "frames_per_step": S * world, "parallelism": f"streams sharded, {S}/GPU, no collective", "host_affinity": numa,
+        "config": {"workload": WORKLOAD if args.pip_opacity is None else WORKLOAD + f" -- NOT the headline: picture-in-picture opacity forced to {args.pip_opacity}", "mode": args.mode, "streams_total": S * world, "frames_per_step": S * world, "parallelism": f"streams sharded, {S}/GPU, no collective", "host_affinity": numa,
                    "l2": "373 MB of distinct sources+targets per step (> 126 MB L2); sources alternate between two device copies",
                    "bit_exact_vs_oracle": "tests/test_gpu_parity.py::test_cfg34_full_size"},
         "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                "ms_per_step": round(e_ms / e2e_steps, 4), "host_queue_ms_per_step": round(e_host_ms / e2e_steps, 4)},
+                "ms_per_step": round(e_ms / e2e_steps, 4), "host_queue_ms_per_step": round(e_host_ms / e2e_steps, 4), "host_link": link},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
         "hbm_gbs_per_gpu_algorithmic": round(ALG_BYTES_PER_FRAME * value / world / 1e9, 1),
     }
@@ -402,6 +427,9 @@ def main():
     ap.add_argument("--mode", default="fused", choices=["fused", "generic", "per_layer"],
                     help="compose strategy: fused (default, svb_mix_tiled), generic (svb_mix_generic), per_layer (the reference's own "
                          "launch sequence over the drop-in kernels: clear + one launch per layer)")
+    ap.add_argument("--pip-opacity", type=float, default=None,
+                    help="side experiment, not the headline: opacity of layers 1..7 (1.0 = opaque pictures, which let the planner skip "
+                         "whatever they cover)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

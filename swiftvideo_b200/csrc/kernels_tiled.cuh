@@ -28,6 +28,12 @@
 #pragma once
 #include "svb_device.cuh"
 
+#ifndef SVB_PLAN_WARP
+// The warp that plans this CTA's next tile.  Not warp 0: thread 0 issues the TMA copies, and whatever a warp does alone
+// makes it late for the next CTA barrier -- two warps late by one chore each cost less than one warp late by both.
+#define SVB_PLAN_WARP (SVB_PRODUCER_WARP ? SVB_TILED_COMPUTE_WARPS : SVB_TILED_COMPUTE_WARPS - 1)
+#endif
+
 
 namespace svb {
 
@@ -152,7 +158,9 @@ struct TiledSmem {
     alignas(16) uint32_t tabs[2][SVB_TILE_TAB_WORDS];  // the staged layer's table blocks, copied with its boxes
     alignas(8) uint64_t bar[2];
     int4 plan[2][SVB_MAX_LAYERS][2];  // [tile parity][l][0] = (mode, iy0, jy0, ic0), [..][1] = (jc0, 0, 0, 0)
+    alignas(16) uint8_t cover[2][SVB_MAX_LAYERS];  // [tile parity][l] = l if layer l hides everything under it on this tile, else 0
 };
+static_assert(SVB_MAX_LAYERS == 16, "first_layer() reads the cover bytes as one 16-byte word");
 static_assert(sizeof(TiledSmem) <= SVB_TILED_SMEM_BYTES, "SVB_TILED_SMEM_BYTES (svb_desc.h) must cover TiledSmem");
 enum { PLAN_SKIP = 0, PLAN_GENERIC = 1, PLAN_STAGED = 4, PLAN_STAGED_EDGE = 5 };  // >= PLAN_STAGED: boxes come by TMA
 
@@ -364,11 +372,15 @@ __device__ __forceinline__ TileGeo tile_geo(const SvbFrameDesc* __restrict__ fra
 }
 
 // Plan of layer `l` on one tile (executed by one thread per layer).
-__device__ __forceinline__ void plan_layer(const uint32_t* __restrict__ tables, const TileGeo& g, int l, int4* __restrict__ out) {
+// *cover = l when the layer overwrites every sample of the tile whatever lies below: the tile is wholly inside the picture
+// and opacity == 1, so every pixel takes cur*(1-1) + v*1 == v (kernels.cl.swift:86-92).
+template <bool OCCL>
+__device__ __forceinline__ void plan_layer(const uint32_t* __restrict__ tables, const TileGeo& g, int l, int4* __restrict__ out, uint8_t* __restrict__ cover) {
     const SvbFrameDesc* __restrict__ F = g.F;
     const SvbLayerDesc* __restrict__ L = &F->layers[l];
     const int x0 = g.x0, y0 = g.y0;
     int mode, iy0 = 0, jy0 = 0, ic0 = 0, jc0 = 0;
+    bool covers = false;
     if (L->rect[0] >= x0 + SVB_TILE_W || L->rect[2] <= x0 || L->rect[1] >= y0 + SVB_TILE_H || L->rect[3] <= y0) {
         mode = PLAN_SKIP;
     } else if (!(L->flags & SVB_LAYER_SEPARABLE) || (L->format != SVB_NV12 && L->format != SVB_Y420P)) {
@@ -389,15 +401,35 @@ __device__ __forceinline__ void plan_layer(const uint32_t* __restrict__ tables, 
         // border, tx and uv are monotone too: both ends inside [0,1] means every pixel of the tile is inside the picture
         const bool full = cA.ok == 7 && cB.ok == 7 && rA.ok == 7 && rB.ok == 7;
         mode = !((L->flags & SVB_LAYER_STAGED) && fits) ? PLAN_GENERIC : (full ? PLAN_STAGED : PLAN_STAGED_EDGE);
+        covers = full && (L->flags & SVB_LAYER_UNIT_OPACITY);
     }
     out[0] = make_int4(mode, iy0, jy0, ic0);
     out[1] = make_int4(jc0, 0, 0, 0);
+    if (OCCL) *cover = (uint8_t)(covers ? l : 0);
+}
+// Occlusion: the layers under the topmost covering layer of a tile are skipped -- neither fetched nor computed -- and
+// the bytes are the same.  (Stale bytes of a frame with more layers are masked by `nl`.)
+__device__ __forceinline__ int first_layer(const uint8_t* cover, int nl) {
+    const uint4 w = *reinterpret_cast<const uint4*>(cover);
+    unsigned m = __vmaxu4(__vmaxu4(w.x, w.y), __vmaxu4(w.z, w.w));
+    m = max(max(m & 0xffu, (m >> 8) & 0xffu), max((m >> 16) & 0xffu, m >> 24));
+    return (int)m < nl ? (int)m : 0;
+}
+
+// Plan of a whole tile: lane l of the planning warp plans layer l (lanes up to SVB_MAX_LAYERS clear their cover byte).
+template <bool OCCL>
+__device__ __forceinline__ void plan_tile(const uint32_t* __restrict__ tables, const TileGeo& g, int lane, int4 (*__restrict__ out)[2], uint8_t* __restrict__ cover) {
+    if (lane < g.F->nlayers) plan_layer<OCCL>(tables, g, lane, out[lane], cover + lane);
+    else if (OCCL && lane < SVB_MAX_LAYERS) cover[lane] = 0;
 }
 
 }  // namespace svb
 
-extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CTAS)  // 8 compute warps + 1 producer warp
-    svb_mix_tiled(const SvbFrameDesc* __restrict__ frames, const uint32_t* __restrict__ tables, int nframes, int total_tiles, float one) {
+namespace svb {
+// OCCL: the batch holds an opaque picture above another layer, so occlusion can pay; without one the planner's cover
+// bytes and the per-tile first-layer lookup are compiled out (they cost 3 % on the headline workload, which has none).
+template <bool OCCL>
+__device__ __forceinline__ void mix_tiled_body(const SvbFrameDesc* __restrict__ frames, const uint32_t* __restrict__ tables, int nframes, int total_tiles, float one) {
     using namespace svb;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TiledSmem& sm = *reinterpret_cast<TiledSmem*>(smem_raw);
@@ -418,7 +450,7 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CT
     bool primed = false;  // this tile's first staged layer was already put in flight by the previous tile
     if (blockIdx.x < total_tiles) {
         const TileGeo g0 = tile_geo(frames, nframes, fnext, blockIdx.x);
-        if (pt >= 0 && pt < g0.F->nlayers) plan_layer(tables, g0, pt, sm.plan[0][pt]);
+        if (warp == SVB_PLAN_WARP) plan_tile<OCCL>(tables, g0, lane, sm.plan[0], sm.cover[0]);
     }
     __syncthreads();
 
@@ -437,6 +469,7 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CT
         uint8_t* const oV = (uint8_t*)F->out_plane[2];
         const int sY = F->out_stride[0], sU = F->out_stride[1], sV = F->out_stride[2];
         const int4(*plan)[2] = sm.plan[cur];
+        const int first = OCCL ? first_layer(sm.cover[cur], nl) : 0;  // layers below it are hidden on this tile
 
         // TMA of one staged layer into buffer `b`: the source boxes and the tile's slices of the coordinate tables
         auto issue = [&](const TileGeo& tg, const int4(*pl)[2], int l, int b) {
@@ -469,7 +502,7 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CT
             return -1;
         };
         if (!primed && pt == 0) {
-            const int l = first_staged(plan, 0, nl);
+            const int l = first_staged(plan, first, nl);
             if (l >= 0) issue(g, plan, l, stage);
         }
         primed = false;
@@ -478,7 +511,7 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CT
         TileGeo gn = g;
         if (has_next) {
             gn = tile_geo(frames, nframes, fnext, tile + gridDim.x);
-            if (pt >= 0 && pt < gn.F->nlayers) plan_layer(tables, gn, pt, sm.plan[cur ^ 1][pt]);
+            if (warp == SVB_PLAN_WARP) plan_tile<OCCL>(tables, gn, lane, sm.plan[cur ^ 1], sm.cover[cur ^ 1]);
         }
 
         // ---- running picture: integer-valued floats ------------------------------------------------------------
@@ -509,7 +542,7 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CT
                 }
         }
 
-        for (int l = 0; l < nl; ++l) {
+        for (int l = first; l < nl; ++l) {
             const int4 p0 = plan[l][0];
             const int mode = p0.x;
             if (mode == PLAN_SKIP) continue;
@@ -522,7 +555,7 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CT
                     if (j >= 0) {
                         if (pt == 0) issue(g, plan, j, stage ^ 1);
                     } else if (has_next) {
-                        const int jn = first_staged(sm.plan[cur ^ 1], 0, gn.F->nlayers);
+                        const int jn = first_staged(sm.plan[cur ^ 1], OCCL ? first_layer(sm.cover[cur ^ 1], gn.F->nlayers) : 0, gn.F->nlayers);
                         if (jn >= 0) {
                             if (pt == 0) issue(gn, sm.plan[cur ^ 1], jn, stage ^ 1);
                             primed = true;
@@ -596,4 +629,14 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CT
         }
         __syncthreads();  // the next tile's plan is visible; the boxes are free
     }
+}
+}  // namespace svb
+
+extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CTAS)
+    svb_mix_tiled(const SvbFrameDesc* __restrict__ frames, const uint32_t* __restrict__ tables, int nframes, int total_tiles, float one) {
+    svb::mix_tiled_body<false>(frames, tables, nframes, total_tiles, one);
+}
+extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CTAS)
+    svb_mix_tiled_occl(const SvbFrameDesc* __restrict__ frames, const uint32_t* __restrict__ tables, int nframes, int total_tiles, float one) {
+    svb::mix_tiled_body<true>(frames, tables, nframes, total_tiles, one);
 }

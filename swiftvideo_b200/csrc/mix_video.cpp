@@ -31,7 +31,7 @@ struct MixerShared {
     bool used[kSegments] = {};
     int next = 0;
     std::map<std::array<uint64_t, 4>, std::array<uint8_t, 128>> tmaps;
-    CUfunction fTiled = nullptr, fGeneric = nullptr, fTables = nullptr;
+    CUfunction fTiled = nullptr, fTiledOccl = nullptr, fGeneric = nullptr, fTables = nullptr;
     int tiledCtasPerSm = 2;  // resident CTAs of svb_mix_tiled per SM: the persistent grid is smCount times this
     std::mutex mu;
     // optional per-launch device timing of the fused kernels (bench.py's roofline leg)
@@ -81,6 +81,9 @@ MixerShared& shared(const std::shared_ptr<InternalContext>& ic) {  // caller hol
         for (CUevent& e : s->ev) check(drv().cuEventCreate(&e, CU_EVENT_DISABLE_TIMING), "cuEventCreate");
         s->fTiled = ic->builtin("svb_mix_tiled");
         check(drv().cuFuncSetAttribute(s->fTiled, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, SVB_TILED_SMEM_BYTES),
+              "cuFuncSetAttribute(max dynamic shared memory)");
+        s->fTiledOccl = ic->builtin("svb_mix_tiled_occl");  // same kernel with tile-level occlusion compiled in
+        check(drv().cuFuncSetAttribute(s->fTiledOccl, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, SVB_TILED_SMEM_BYTES),
               "cuFuncSetAttribute(max dynamic shared memory)");
         s->fTables = ic->builtin("svb_mix_tables");
         int perSm = 0;
@@ -273,8 +276,12 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
         SvbFrameDesc* host = (SvbFrameDesc*)(sh.host + (size_t)seg * kSegFrames * sizeof(SvbFrameDesc));
         int total = 0, maxW = 0, maxH = 0, maxLayers = 1, maxEnts = 1;
         size_t tableEnts = 0;
+        bool occluders = false;  // an opaque picture above another layer: tiles it covers can drop what lies below
         for (int i = 0; i < n; ++i) {
             SvbFrameDesc& fr = frames[start + i];
+            for (int l = 1; l < fr.nlayers; ++l)
+                occluders = occluders || ((fr.layers[l].flags & SVB_LAYER_UNIT_OPACITY) && (fr.layers[l].flags & SVB_LAYER_SEPARABLE) &&
+                                          (fr.layers[l].format == SVB_NV12 || fr.layers[l].format == SVB_Y420P));
             fr.first_tile = total;
             total += fr.tiles_x * fr.tiles_y;
             maxW = std::max(maxW, fr.width), maxH = std::max(maxH, fr.height);
@@ -313,7 +320,8 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
             float one = 1.0f;  // see add2() in kernels_tiled.cuh
             void* args[] = {&dev, &tables, &nframes, &total, &one};
             const unsigned grid = (unsigned)std::min(total, ic.smCount * sh.tiledCtasPerSm);
-            check(d.cuLaunchKernel(sh.fTiled, grid, 1, 1, SVB_TILED_THREADS, 1, 1, SVB_TILED_SMEM_BYTES, ic.compute, args, nullptr), "cuLaunchKernel(svb_mix_tiled)");
+            check(d.cuLaunchKernel(occluders ? sh.fTiledOccl : sh.fTiled, grid, 1, 1, SVB_TILED_THREADS, 1, 1, SVB_TILED_SMEM_BYTES, ic.compute, args, nullptr),
+                  "cuLaunchKernel(svb_mix_tiled)");
             noteKernelLaunch();
             ic.release(tables, tableBytes);  // recycled only after the streams have drained past this point
         } else {

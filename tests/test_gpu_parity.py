@@ -59,6 +59,16 @@ def _tiled_cases():
         many_l.append(scenes.random_image(O.NV12, 160 + 16 * k, 96 + 8 * k, 7200 + k))
         many_u.append(scenes.layer_uniforms((512, 288), (160 + 16 * k, 96 + 8 * k), (10 * k, 6 * k), (300, 170), z=k + 1, opacity=0.3 + 0.04 * k))
     cases.append(scenes.Case("tiled_17_layers", O.NV12, (512, 288), many_l, many_u))
+    # opaque pictures above other layers: tiles they cover completely skip everything underneath (planner occlusion)
+    canvas = (640, 352)
+    occ_l = [scenes.random_image(O.NV12, 640, 352, 7400), scenes.random_image(O.BGRA, 300, 200, 7401), scenes.random_image(O.NV12, 480, 270, 7402),
+             scenes.random_image(O.NV12, 320, 180, 7403), scenes.random_image(O.NV12, 256, 144, 7404)]
+    occ_u = [scenes.layer_uniforms(canvas, (640, 352), (0, 0), canvas, z=1, opacity=1.0),
+             scenes.layer_uniforms(canvas, (300, 200), (50, 40), (300, 200), z=2, opacity=0.7),
+             scenes.layer_uniforms(canvas, (480, 270), (64, 32), (384, 224), z=3, opacity=1.0),   # covers whole tiles: hides layers 0-1 there
+             scenes.layer_uniforms(canvas, (320, 180), (200, 100), (320, 180), z=4, opacity=0.5),
+             scenes.layer_uniforms(canvas, (256, 144), (300, 150), (256, 160), z=5, opacity=1.0)]  # on top, hides 0-3 in its interior tiles
+    cases.append(scenes.Case("tiled_occluders", O.NV12, canvas, occ_l, occ_u))
     # odd plane strides / widths that break the tiled kernel's alignment preconditions fall back to generic
     src = scenes.random_image(O.NV12, 250, 130, 7300)
     cases.append(scenes.Case("unaligned_250x130_src", O.NV12, (384, 224), [src],
