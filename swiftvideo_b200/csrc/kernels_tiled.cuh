@@ -28,6 +28,12 @@
 #pragma once
 #include "svb_device.cuh"
 
+#ifndef SVB_DYNAMIC_TILES
+// 1: CTAs claim tiles from a counter (row-major order, so neighbouring tiles still run together); 0: static round-robin.
+// Tiles cost between zero and eight layers, and with a static deal the slowest CTA's share decided the kernel time
+// (v7 profile: SM cycles active 1.01 M on average against 1.13 M elapsed).
+#define SVB_DYNAMIC_TILES 1
+#endif
 #ifndef SVB_PLAN_WARP
 // The warp that plans this CTA's next tile.  Not warp 0: thread 0 issues the TMA copies, and whatever a warp does alone
 // makes it late for the next CTA barrier -- two warps late by one chore each cost less than one warp late by both.
@@ -158,6 +164,7 @@ struct TiledSmem {
     alignas(16) uint32_t tabs[2][SVB_TILE_TAB_WORDS];  // the staged layer's table blocks, copied with its boxes
     alignas(8) uint64_t bar[2];
     int4 plan[2][SVB_MAX_LAYERS][2];  // [tile parity][l][0] = (mode, iy0, jy0, ic0), [..][1] = (jc0, 0, 0, 0)
+    int tile_idx[3];                 // ring over this CTA's tile sequence: index of its k-th tile in slot k % 3 (>= total: none)
     alignas(16) uint8_t cover[2][SVB_MAX_LAYERS];  // [tile parity][l] = l if layer l hides everything under it on this tile, else 0
 };
 static_assert(SVB_MAX_LAYERS == 16, "first_layer() reads the cover bytes as one 16-byte word");
@@ -320,8 +327,9 @@ __device__ __forceinline__ unsigned short pack2(float a, float b) {  // two inte
 
 // ---- pre-pass: coordinate tables of every separable YUV layer of every frame of the batch -----------------------
 // grid (ceil(entries / 256), max layers, frames); one entry (two words) per thread, blocks padded to whole tiles.
-extern "C" __global__ void __launch_bounds__(256) svb_mix_tables(const SvbFrameDesc* __restrict__ frames, uint32_t* __restrict__ tables) {
+extern "C" __global__ void __launch_bounds__(256) svb_mix_tables(const SvbFrameDesc* __restrict__ frames, uint32_t* __restrict__ tables, int* __restrict__ tile_counter) {
     using namespace svb;
+    if ((blockIdx.x | blockIdx.y | blockIdx.z | threadIdx.x) == 0) *tile_counter = 0;  // svb_mix_tiled claims its tiles from it
     const SvbFrameDesc* __restrict__ F = frames + blockIdx.z;
     const int l = blockIdx.y;
     if (l >= F->nlayers) return;
@@ -429,13 +437,13 @@ namespace svb {
 // OCCL: the batch holds an opaque picture above another layer, so occlusion can pay; without one the planner's cover
 // bytes and the per-tile first-layer lookup are compiled out (they cost 3 % on the headline workload, which has none).
 template <bool OCCL>
-__device__ __forceinline__ void mix_tiled_body(const SvbFrameDesc* __restrict__ frames, const uint32_t* __restrict__ tables, int nframes, int total_tiles, float one) {
+__device__ __forceinline__ void mix_tiled_body(const SvbFrameDesc* __restrict__ frames, const uint32_t* __restrict__ tables, int nframes, int total_tiles, float one,
+                                               int* __restrict__ tile_counter) {
     using namespace svb;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TiledSmem& sm = *reinterpret_cast<TiledSmem*>(smem_raw);
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    // Warps 0..7 compute; warp 8 is the producer: it plans the tiles and issues the TMA copies, so that no computing
-    // warp runs late into a barrier because it also had the copies to launch (profiles/r1_history.md, v6).
+    // SVB_PRODUCER_WARP (off; measured slower, profiles/r1_history.md): a ninth warp that only plans and issues copies.
     const bool producer = SVB_PRODUCER_WARP && warp == SVB_TILED_COMPUTE_WARPS;
     const int pt = SVB_PRODUCER_WARP ? t - SVB_TILED_COMPUTE_WARPS * 32 : t;  // index among the planning threads (negative: not one)
     const SvbFrameDesc* fenced = nullptr;              // frame whose tensor maps this CTA's producer has acquired
@@ -448,13 +456,27 @@ __device__ __forceinline__ void mix_tiled_body(const SvbFrameDesc* __restrict__ 
     int f = 0, fnext = 0, cur = 0;
     int stage = 0;        // box buffer that holds (or is about to receive) the next staged layer to consume
     bool primed = false;  // this tile's first staged layer was already put in flight by the previous tile
-    if (blockIdx.x < total_tiles) {
-        const TileGeo g0 = tile_geo(frames, nframes, fnext, blockIdx.x);
+    // Tiles are claimed two ahead by one lane (a global atomic whose latency hides behind the planning loads).
+    const bool claimer = t == SVB_PLAN_WARP * 32;
+    int nclaimed = 0;
+    auto claim = [&]() -> int {
+        if (SVB_DYNAMIC_TILES) return atomicAdd(tile_counter, 1);
+        return (int)blockIdx.x + (int)gridDim.x * nclaimed++;
+    };
+    if (claimer) {
+        sm.tile_idx[0] = claim();
+        sm.tile_idx[1] = claim();
+    }
+    __syncthreads();
+    int tile = sm.tile_idx[0];
+    int k3 = 0;  // ordinal of the tile in this CTA's sequence, modulo 3
+    if (tile < total_tiles) {
+        const TileGeo g0 = tile_geo(frames, nframes, fnext, tile);
         if (warp == SVB_PLAN_WARP) plan_tile<OCCL>(tables, g0, lane, sm.plan[0], sm.cover[0]);
     }
     __syncthreads();
 
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, cur ^= 1) {
+    while (tile < total_tiles) {
         const TileGeo g = tile_geo(frames, nframes, f, tile);
         const SvbFrameDesc* __restrict__ F = g.F;
         const int W = F->width, H = F->height, nl = F->nlayers;
@@ -507,11 +529,18 @@ __device__ __forceinline__ void mix_tiled_body(const SvbFrameDesc* __restrict__ 
         }
         primed = false;
         // plan of this CTA's next tile, off the critical path (its loads overlap the copy in flight)
-        const bool has_next = tile + (int)gridDim.x < total_tiles;
+        const int k3n = k3 == 2 ? 0 : k3 + 1;  // slot of the next tile's index; the slot after it receives the new claim
+        const int next_tile = sm.tile_idx[k3n];
+        const bool has_next = next_tile < total_tiles;
         TileGeo gn = g;
-        if (has_next) {
-            gn = tile_geo(frames, nframes, fnext, tile + gridDim.x);
-            if (warp == SVB_PLAN_WARP) plan_tile<OCCL>(tables, gn, lane, sm.plan[cur ^ 1], sm.cover[cur ^ 1]);
+        {
+            int claimed = 0;
+            if (claimer) claimed = claim();
+            if (has_next) {
+                gn = tile_geo(frames, nframes, fnext, next_tile);
+                if (warp == SVB_PLAN_WARP) plan_tile<OCCL>(tables, gn, lane, sm.plan[cur ^ 1], sm.cover[cur ^ 1]);
+            }
+            if (claimer) sm.tile_idx[k3n == 2 ? 0 : k3n + 1] = claimed;
         }
 
         // ---- running picture: integer-valued floats ------------------------------------------------------------
@@ -628,15 +657,17 @@ __device__ __forceinline__ void mix_tiled_body(const SvbFrameDesc* __restrict__ 
                 }
         }
         __syncthreads();  // the next tile's plan is visible; the boxes are free
+        tile = sm.tile_idx[k3n], k3 = k3n, cur ^= 1;
     }
 }
 }  // namespace svb
 
 extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CTAS)
-    svb_mix_tiled(const SvbFrameDesc* __restrict__ frames, const uint32_t* __restrict__ tables, int nframes, int total_tiles, float one) {
-    svb::mix_tiled_body<false>(frames, tables, nframes, total_tiles, one);
+    svb_mix_tiled(const SvbFrameDesc* __restrict__ frames, const uint32_t* __restrict__ tables, int nframes, int total_tiles, float one, int* __restrict__ tile_counter) {
+    svb::mix_tiled_body<false>(frames, tables, nframes, total_tiles, one, tile_counter);
 }
 extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CTAS)
-    svb_mix_tiled_occl(const SvbFrameDesc* __restrict__ frames, const uint32_t* __restrict__ tables, int nframes, int total_tiles, float one) {
-    svb::mix_tiled_body<true>(frames, tables, nframes, total_tiles, one);
+    svb_mix_tiled_occl(const SvbFrameDesc* __restrict__ frames, const uint32_t* __restrict__ tables, int nframes, int total_tiles, float one,
+                       int* __restrict__ tile_counter) {
+    svb::mix_tiled_body<true>(frames, tables, nframes, total_tiles, one, tile_counter);
 }

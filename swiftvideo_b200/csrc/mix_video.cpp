@@ -309,16 +309,19 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
         if (!tiled && tev.first) check(d.cuEventRecord(tev.first, ic.compute), "cuEventRecord");
         if (tiled) {
             // pre-pass: per-column / per-row coordinate tables of the batch (two words per entry), then the compositor
-            const size_t tableBytes = std::max<size_t>(tableEnts, 4) * 4;
+            // (+ the tile counter svb_mix_tiled claims its work from, zeroed by the pre-pass)
+            const size_t counterOff = (std::max<size_t>(tableEnts, 4) * 4 + 15) & ~(size_t)15;
+            const size_t tableBytes = counterOff + 16;
             CUdeviceptr tables = ic.alloc(tableBytes);
-            void* targs[] = {&dev, &tables};
+            CUdeviceptr counter = tables + counterOff;
+            void* targs[] = {&dev, &tables, &counter};
             check(d.cuLaunchKernel(sh.fTables, (unsigned)((maxEnts / 2 + 255) / 256), (unsigned)maxLayers, (unsigned)n, 256, 1, 1, 0, ic.compute, targs, nullptr),
                   "cuLaunchKernel(svb_mix_tables)");
             noteKernelLaunch();
             if (tev.first) check(d.cuEventRecord(tev.first, ic.compute), "cuEventRecord");  // time svb_mix_tiled alone
             int nframes = n;
             float one = 1.0f;  // see add2() in kernels_tiled.cuh
-            void* args[] = {&dev, &tables, &nframes, &total, &one};
+            void* args[] = {&dev, &tables, &nframes, &total, &one, &counter};
             const unsigned grid = (unsigned)std::min(total, ic.smCount * sh.tiledCtasPerSm);
             check(d.cuLaunchKernel(occluders ? sh.fTiledOccl : sh.fTiled, grid, 1, 1, SVB_TILED_THREADS, 1, 1, SVB_TILED_SMEM_BYTES, ic.compute, args, nullptr),
                   "cuLaunchKernel(svb_mix_tiled)");
