@@ -158,17 +158,15 @@ __device__ __forceinline__ float2 bilin2(float2 w00, float2 w10, float2 w01, flo
 }
 
 #define SVB_TILE_TAB_WORDS (SVB_TAB_COL_WORDS + SVB_TAB_ROW_WORDS)  // the column block and the row block of one tile
-struct TiledSmem {
-    alignas(128) uint8_t boxY[2][SVB_BOX_Y_BYTES];
-    alignas(128) uint8_t boxC[2][SVB_BOX_C_BYTES];
-    alignas(16) uint32_t tabs[2][SVB_TILE_TAB_WORDS];  // the staged layer's table blocks, copied with its boxes
+struct TiledSmem {  // the fixed part; the boxes follow at SVB_TILED_FIXED_BYTES: Y[0] Y[1] C[0] C[1]
+    alignas(128) uint32_t tabs[2][SVB_TILE_TAB_WORDS];  // the staged layer's table blocks, copied with its boxes
     alignas(8) uint64_t bar[2];
     int4 plan[2][SVB_MAX_LAYERS][2];  // [tile parity][l][0] = (mode, iy0, jy0, ic0), [..][1] = (jc0, 0, 0, 0)
     int tile_idx[3];                 // ring over this CTA's tile sequence: index of its k-th tile in slot k % 3 (>= total: none)
     alignas(16) uint8_t cover[2][SVB_MAX_LAYERS];  // [tile parity][l] = l if layer l hides everything under it on this tile, else 0
 };
 static_assert(SVB_MAX_LAYERS == 16, "first_layer() reads the cover bytes as one 16-byte word");
-static_assert(sizeof(TiledSmem) <= SVB_TILED_SMEM_BYTES, "SVB_TILED_SMEM_BYTES (svb_desc.h) must cover TiledSmem");
+static_assert(sizeof(TiledSmem) <= SVB_TILED_FIXED_BYTES && SVB_TILED_FIXED_BYTES % 128 == 0, "SVB_TILED_FIXED_BYTES (svb_desc.h) must cover TiledSmem");
 enum { PLAN_SKIP = 0, PLAN_GENERIC = 1, PLAN_STAGED = 4, PLAN_STAGED_EDGE = 5 };  // >= PLAN_STAGED: boxes come by TMA
 
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, uint64_t* bar) {  // 16-byte granules
@@ -358,7 +356,7 @@ extern "C" __global__ void __launch_bounds__(256) svb_mix_tables(const SvbFrameD
 }
 
 #ifndef SVB_TILED_MIN_CTAS
-#define SVB_TILED_MIN_CTAS 2
+#define SVB_TILED_MIN_CTAS 3  // 80 registers per thread (a few spills) and 24 resident warps beat 128 registers and 16 warps by 5.6 %
 #endif
 
 namespace svb {
@@ -438,10 +436,11 @@ namespace svb {
 // bytes and the per-tile first-layer lookup are compiled out (they cost 3 % on the headline workload, which has none).
 template <bool OCCL>
 __device__ __forceinline__ void mix_tiled_body(const SvbFrameDesc* __restrict__ frames, const uint32_t* __restrict__ tables, int nframes, int total_tiles, float one,
-                                               int* __restrict__ tile_counter) {
+                                               int* __restrict__ tile_counter, int box_y_bytes, int box_c_bytes) {
     using namespace svb;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TiledSmem& sm = *reinterpret_cast<TiledSmem*>(smem_raw);
+    uint8_t* const boxes = smem_raw + SVB_TILED_FIXED_BYTES;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     // SVB_PRODUCER_WARP (off; measured slower, profiles/r1_history.md): a ninth warp that only plans and issues copies.
     const bool producer = SVB_PRODUCER_WARP && warp == SVB_TILED_COMPUTE_WARPS;
@@ -511,9 +510,9 @@ __device__ __forceinline__ void mix_tiled_body(const SvbFrameDesc* __restrict__ 
                 fenced = TF;
             }
             mbar_expect_tx(&sm.bar[b], L->box_w * L->box_h + cbytes * (n12 ? 1 : 2) + SVB_TILE_TAB_WORDS * 4);
-            tma_load_2d(sm.boxY[b], L->tmap[0], p0.y, p0.z, &sm.bar[b]);
-            tma_load_2d(sm.boxC[b], L->tmap[1], p0.w, p1.x, &sm.bar[b]);
-            if (!n12) tma_load_2d(sm.boxC[b] + SVB_BOX_C_BYTES / 2, L->tmap[2], p0.w, p1.x, &sm.bar[b]);
+            tma_load_2d(boxes + b * box_y_bytes, L->tmap[0], p0.y, p0.z, &sm.bar[b]);
+            tma_load_2d(boxes + 2 * box_y_bytes + b * box_c_bytes, L->tmap[1], p0.w, p1.x, &sm.bar[b]);
+            if (!n12) tma_load_2d(boxes + 2 * box_y_bytes + b * box_c_bytes + box_c_bytes / 2, L->tmap[2], p0.w, p1.x, &sm.bar[b]);
             bulk_load(sm.tabs[b], tb.col + (tg.x0 / SVB_TILE_W) * SVB_TAB_COL_WORDS, SVB_TAB_COL_WORDS * 4, &sm.bar[b]);
             bulk_load(sm.tabs[b] + SVB_TAB_COL_WORDS, tb.row + (tg.y0 / SVB_TILE_H) * SVB_TAB_ROW_WORDS, SVB_TAB_ROW_WORDS * 4, &sm.bar[b]);
         };
@@ -600,8 +599,8 @@ __device__ __forceinline__ void mix_tiled_body(const SvbFrameDesc* __restrict__ 
                 if (live) {
                     const int fmt = L->format, lflags = L->flags;
                     const int pitchC = fmt == SVB_NV12 ? L->box_cw * 2 : L->box_cw, stepC = fmt == SVB_NV12 ? 2 : 1;
-                    const unsigned bY = smem_u32(sm.boxY[stage]), bU = smem_u32(sm.boxC[stage]);
-                    const unsigned bV = bU + (fmt == SVB_NV12 ? 1 : SVB_BOX_C_BYTES / 2);
+                    const unsigned bY = smem_u32(boxes + stage * box_y_bytes), bU = smem_u32(boxes + 2 * box_y_bytes + stage * box_c_bytes);
+                    const unsigned bV = bU + (fmt == SVB_NV12 ? 1 : box_c_bytes / 2);
                     const float alpha = L->u.opacity;
                     FillTerms ft;
                     if (mode == PLAN_STAGED_EDGE || !(lflags & SVB_LAYER_OPACITY_01)) {
@@ -663,11 +662,12 @@ __device__ __forceinline__ void mix_tiled_body(const SvbFrameDesc* __restrict__ 
 }  // namespace svb
 
 extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CTAS)
-    svb_mix_tiled(const SvbFrameDesc* __restrict__ frames, const uint32_t* __restrict__ tables, int nframes, int total_tiles, float one, int* __restrict__ tile_counter) {
-    svb::mix_tiled_body<false>(frames, tables, nframes, total_tiles, one, tile_counter);
+    svb_mix_tiled(const SvbFrameDesc* __restrict__ frames, const uint32_t* __restrict__ tables, int nframes, int total_tiles, float one, int* __restrict__ tile_counter,
+                  int box_y_bytes, int box_c_bytes) {
+    svb::mix_tiled_body<false>(frames, tables, nframes, total_tiles, one, tile_counter, box_y_bytes, box_c_bytes);
 }
 extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CTAS)
     svb_mix_tiled_occl(const SvbFrameDesc* __restrict__ frames, const uint32_t* __restrict__ tables, int nframes, int total_tiles, float one,
-                       int* __restrict__ tile_counter) {
-    svb::mix_tiled_body<true>(frames, tables, nframes, total_tiles, one, tile_counter);
+                       int* __restrict__ tile_counter, int box_y_bytes, int box_c_bytes) {
+    svb::mix_tiled_body<true>(frames, tables, nframes, total_tiles, one, tile_counter, box_y_bytes, box_c_bytes);
 }

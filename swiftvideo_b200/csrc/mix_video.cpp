@@ -32,7 +32,7 @@ struct MixerShared {
     int next = 0;
     std::map<std::array<uint64_t, 4>, std::array<uint8_t, 128>> tmaps;
     CUfunction fTiled = nullptr, fTiledOccl = nullptr, fGeneric = nullptr, fTables = nullptr;
-    int tiledCtasPerSm = 2;  // resident CTAs of svb_mix_tiled per SM: the persistent grid is smCount times this
+    std::map<size_t, int> tiledCtasPerSm;  // resident CTAs of svb_mix_tiled per SM by dynamic shared memory size: the persistent grid is smCount times this
     std::mutex mu;
     // optional per-launch device timing of the fused kernels (bench.py's roofline leg)
     bool timing = false;
@@ -80,15 +80,12 @@ MixerShared& shared(const std::shared_ptr<InternalContext>& ic) {  // caller hol
         check(drv().cuMemAlloc(&s->dev, bytes), "cuMemAlloc");
         for (CUevent& e : s->ev) check(drv().cuEventCreate(&e, CU_EVENT_DISABLE_TIMING), "cuEventCreate");
         s->fTiled = ic->builtin("svb_mix_tiled");
-        check(drv().cuFuncSetAttribute(s->fTiled, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, SVB_TILED_SMEM_BYTES),
+        check(drv().cuFuncSetAttribute(s->fTiled, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, SVB_TILED_SMEM_MAX),
               "cuFuncSetAttribute(max dynamic shared memory)");
         s->fTiledOccl = ic->builtin("svb_mix_tiled_occl");  // same kernel with tile-level occlusion compiled in
-        check(drv().cuFuncSetAttribute(s->fTiledOccl, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, SVB_TILED_SMEM_BYTES),
+        check(drv().cuFuncSetAttribute(s->fTiledOccl, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, SVB_TILED_SMEM_MAX),
               "cuFuncSetAttribute(max dynamic shared memory)");
         s->fTables = ic->builtin("svb_mix_tables");
-        int perSm = 0;
-        check(drv().cuOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, s->fTiled, SVB_TILED_THREADS, SVB_TILED_SMEM_BYTES), "cuOccupancyMaxActiveBlocksPerMultiprocessor");
-        s->tiledCtasPerSm = std::max(1, perSm);
         s->fGeneric = ic->builtin("svb_mix_generic");
     }
     return *(MixerShared*)ic->mixerShared;
@@ -277,8 +274,15 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
         int total = 0, maxW = 0, maxH = 0, maxLayers = 1, maxEnts = 1;
         size_t tableEnts = 0;
         bool occluders = false;  // an opaque picture above another layer: tiles it covers can drop what lies below
+        int boxY = 0, boxC = 0;   // largest staged footprint of the batch (bytes per box; chroma = both planes of a Y420P source)
         for (int i = 0; i < n; ++i) {
             SvbFrameDesc& fr = frames[start + i];
+            for (int l = 0; l < fr.nlayers; ++l) {
+                const SvbLayerDesc& L = fr.layers[l];
+                if (!(L.flags & SVB_LAYER_STAGED)) continue;
+                boxY = std::max(boxY, roundUp(L.box_w * L.box_h, 256));
+                boxC = std::max(boxC, L.format == SVB_NV12 ? roundUp(L.box_cw * L.box_ch * 2, 256) : 2 * roundUp(L.box_cw * L.box_ch, 128));
+            }
             for (int l = 1; l < fr.nlayers; ++l)
                 occluders = occluders || ((fr.layers[l].flags & SVB_LAYER_UNIT_OPACITY) && (fr.layers[l].flags & SVB_LAYER_SEPARABLE) &&
                                           (fr.layers[l].format == SVB_NV12 || fr.layers[l].format == SVB_Y420P));
@@ -321,9 +325,22 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
             if (tev.first) check(d.cuEventRecord(tev.first, ic.compute), "cuEventRecord");  // time svb_mix_tiled alone
             int nframes = n;
             float one = 1.0f;  // see add2() in kernels_tiled.cuh
-            void* args[] = {&dev, &tables, &nframes, &total, &one, &counter};
-            const unsigned grid = (unsigned)std::min(total, ic.smCount * sh.tiledCtasPerSm);
-            check(d.cuLaunchKernel(occluders ? sh.fTiledOccl : sh.fTiled, grid, 1, 1, SVB_TILED_THREADS, 1, 1, SVB_TILED_SMEM_BYTES, ic.compute, args, nullptr),
+            void* args[] = {&dev, &tables, &nframes, &total, &one, &counter, &boxY, &boxC};
+            // shared memory: the fixed part plus two box pairs sized for the largest staged footprint of this batch
+            size_t smem = SVB_TILED_SMEM_BYTES((size_t)boxY, (size_t)boxC);
+            int perSm;
+            {
+                std::lock_guard<std::mutex> g(sh.mu);
+                auto it = sh.tiledCtasPerSm.find(smem);
+                if (it == sh.tiledCtasPerSm.end()) {
+                    int n = 0;
+                    check(d.cuOccupancyMaxActiveBlocksPerMultiprocessor(&n, sh.fTiled, SVB_TILED_THREADS, smem), "cuOccupancyMaxActiveBlocksPerMultiprocessor");
+                    it = sh.tiledCtasPerSm.emplace(smem, std::max(1, n)).first;
+                }
+                perSm = it->second;
+            }
+            const unsigned grid = (unsigned)std::min(total, ic.smCount * perSm);
+            check(d.cuLaunchKernel(occluders ? sh.fTiledOccl : sh.fTiled, grid, 1, 1, SVB_TILED_THREADS, 1, 1, (unsigned)smem, ic.compute, args, nullptr),
                   "cuLaunchKernel(svb_mix_tiled)");
             noteKernelLaunch();
             ic.release(tables, tableBytes);  // recycled only after the streams have drained past this point

@@ -16,8 +16,12 @@
 #endif
 #define SVB_TILED_THREADS (SVB_TILED_COMPUTE_WARPS * 32 + 32 * SVB_PRODUCER_WARP)
 // largest source footprint the tiled kernel stages in shared memory per tile and layer
+#ifndef SVB_BOX_Y_BYTES
 #define SVB_BOX_Y_BYTES (SVB_TILE_H * 640)
+#endif
+#ifndef SVB_BOX_C_BYTES
 #define SVB_BOX_C_BYTES (SVB_TILE_H * 384)
+#endif
 
 enum SvbFormat { SVB_NV12 = 0, SVB_Y420P = 1, SVB_BGRA = 2, SVB_RGBA = 3 };
 
@@ -88,10 +92,13 @@ typedef struct __attribute__((aligned(64))) SvbFrameDesc {
 #define SVB_TILES_Y(H) (((H) + SVB_TILE_H - 1) / SVB_TILE_H)
 #define SVB_TABLE_WORDS(W, H) (SVB_TILES_X(W) * SVB_TAB_COL_WORDS + SVB_TILES_Y(H) * SVB_TAB_ROW_WORDS)
 
-// dynamic shared memory of svb_mix_tiled: two staged box pairs, two table slices (a column block and a row block),
-// two mbarriers, two plans of 32 bytes per layer
-#define SVB_TILED_SMEM_BYTES \
-    (2 * SVB_BOX_Y_BYTES + 2 * SVB_BOX_C_BYTES + 2 * (SVB_TAB_COL_WORDS + SVB_TAB_ROW_WORDS) * 4 + 128 + 2 * SVB_MAX_LAYERS * 32)
+// dynamic shared memory of svb_mix_tiled: a fixed part (two table slices, mbarriers, two tile plans, the tile ring) and
+// behind it two luma boxes and two chroma boxes whose size the host picks PER LAUNCH from the largest staged footprint
+// of the batch (box_y_bytes / box_c_bytes kernel arguments, multiples of 256, at most SVB_BOX_*_BYTES): shared memory
+// not taken stays L1, and the headline workload needs 11 KB per stage, not the 32 KB worst case.
+#define SVB_TILED_FIXED_BYTES (2 * (SVB_TAB_COL_WORDS + SVB_TAB_ROW_WORDS) * 4 + 256 + 2 * SVB_MAX_LAYERS * 32)
+#define SVB_TILED_SMEM_BYTES(boxY, boxC) (SVB_TILED_FIXED_BYTES + 2 * (boxY) + 2 * (boxC))
+#define SVB_TILED_SMEM_MAX SVB_TILED_SMEM_BYTES(SVB_BOX_Y_BYTES, SVB_BOX_C_BYTES)
 
 #ifdef __cplusplus
 static_assert(sizeof(SvbUniforms) == 240, "SvbUniforms layout");
