@@ -28,6 +28,9 @@
 #pragma once
 #include "svb_device.cuh"
 
+#ifndef SVB_ROLL_ROWS
+#define SVB_ROLL_ROWS 1  // the layer bodies run their two row pairs as a rolled loop (0: unrolled, 0.7 % slower at three CTAs per SM)
+#endif
 #ifndef SVB_DYNAMIC_TILES
 // 1: CTAs claim tiles from a counter (row-major order, so neighbouring tiles still run together); 0: static round-robin.
 // Tiles cost between zero and eight layers, and with a static deal the slowest CTA's share decided the kernel time
@@ -260,38 +263,60 @@ __device__ __forceinline__ void fast_layer(unsigned boxY, unsigned boxU, unsigne
         return out;
     };
     const uint32_t* __restrict__ rows = tabs + SVB_TAB_COL_WORDS;  // rows past the frame's bottom hold the last row's entry
+    // two luma rows (4*warp + 2*k, +1) and the chroma row under them (2*warp + k)
+    auto row_pair = [&](int k, float2 (&Y0)[2], float2 (&Y1)[2], float2& Uk, float2& Vk) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const uint2 ry = *reinterpret_cast<const uint2*>(rows + 2 * (4 * warp + r));
-        const unsigned r0 = ((ry.y & 0xffffu) - jy0) * pitchY, r1 = r0 + ((ry.y >> 16) & 1u) * pitchY;
-        const int okr = (int)(ry.y >> 17);
-        const float2 B = splat(__uint_as_float(ry.x)), NB = splat(sub(1.f, __uint_as_float(ry.x)));
+        for (int r = 0; r < 2; ++r) {
+            float2(&Yr)[2] = r == 0 ? Y0 : Y1;
+            const uint2 ry = *reinterpret_cast<const uint2*>(rows + 2 * (4 * warp + 2 * k + r));
+            const unsigned r0 = ((ry.y & 0xffffu) - jy0) * pitchY, r1 = r0 + ((ry.y >> 16) & 1u) * pitchY;
+            const int okr = (int)(ry.y >> 17);
+            const float2 B = splat(__uint_as_float(ry.x)), NB = splat(sub(1.f, __uint_as_float(ry.x)));
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                const unsigned a0 = o0[2 * p], a1 = o1[2 * p], b0 = o0[2 * p + 1], b1 = o1[2 * p + 1];
+                const float2 t00 = unorm2<PK>(bytes2(lds_u8(r0 + a0), lds_u8(r0 + b0)));
+                const float2 t10 = unorm2<PK>(bytes2(lds_u8(r0 + a1), lds_u8(r0 + b1)));
+                const float2 t01 = unorm2<PK>(bytes2(lds_u8(r1 + a0), lds_u8(r1 + b0)));
+                const float2 t11 = unorm2<PK>(bytes2(lds_u8(r1 + a1), lds_u8(r1 + b1)));
+                const float2 v = bilin2<PK>(mul2<PK>(NA[p], NB), mul2<PK>(A[p], NB), mul2<PK>(NA[p], B), mul2<PK>(A[p], B), t00, t10, t01, t11, ONE);
+                Yr[p] = settle(Yr[p], v, ft.fy, 0.f, okc[2 * p] & okr, okc[2 * p + 1] & okr);
+            }
+        }
+        const uint2 rc = *reinterpret_cast<const uint2*>(rows + 2 * SVB_TILE_H + 2 * (2 * warp + k));
+        const unsigned q0 = ((rc.y & 0xffffu) - jc0) * pitchC, q1 = q0 + ((rc.y >> 16) & 1u) * pitchC;
+        const int okq = (int)(rc.y >> 17);
+        const float2 BC = splat(__uint_as_float(rc.x)), NBC = splat(sub(1.f, __uint_as_float(rc.x)));
+        const float2 w00 = mul2<PK>(NAC, NBC), w10 = mul2<PK>(AC, NBC), w01 = mul2<PK>(NAC, BC), w11 = mul2<PK>(AC, BC);
+        const unsigned u0 = boxU + q0, u1 = boxU + q1, v0 = boxV + q0, v1 = boxV + q1;
+        const float2 u = bilin2<PK>(w00, w10, w01, w11, unorm2<PK>(bytes2(lds_u8(u0 + oc00), lds_u8(u0 + oc10))), unorm2<PK>(bytes2(lds_u8(u0 + oc01), lds_u8(u0 + oc11))),
+                                    unorm2<PK>(bytes2(lds_u8(u1 + oc00), lds_u8(u1 + oc10))), unorm2<PK>(bytes2(lds_u8(u1 + oc01), lds_u8(u1 + oc11))), ONE);
+        const float2 v = bilin2<PK>(w00, w10, w01, w11, unorm2<PK>(bytes2(lds_u8(v0 + oc00), lds_u8(v0 + oc10))), unorm2<PK>(bytes2(lds_u8(v0 + oc01), lds_u8(v0 + oc11))),
+                                    unorm2<PK>(bytes2(lds_u8(v1 + oc00), lds_u8(v1 + oc10))), unorm2<PK>(bytes2(lds_u8(v1 + oc01), lds_u8(v1 + oc11))), ONE);
+        Uk = settle(Uk, u, ft.fu, -1.f, okc0 & okq, okc1 & okq);
+        Vk = settle(Vk, v, ft.fv, -1.f, okc0 & okq, okc1 & okq);
+    };
+#if SVB_ROLL_ROWS
+    // one copy of the body, run twice; the two halves of the register block trade places after each pass (and are back
+    // where they were after the second): half the code for the instruction cache to hold, which three resident CTAs
+    // drifting apart make scarce (no_instruction stalls went from 0.36 to 1.34 per issue when the third CTA came in)
+#pragma unroll 1
+    for (int k = 0; k < 2; ++k) {
+        row_pair(k, Yi[0], Yi[1], Ui[0], Vi[0]);
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
-            const unsigned a0 = o0[2 * p], a1 = o1[2 * p], b0 = o0[2 * p + 1], b1 = o1[2 * p + 1];
-            const float2 t00 = unorm2<PK>(bytes2(lds_u8(r0 + a0), lds_u8(r0 + b0)));
-            const float2 t10 = unorm2<PK>(bytes2(lds_u8(r0 + a1), lds_u8(r0 + b1)));
-            const float2 t01 = unorm2<PK>(bytes2(lds_u8(r1 + a0), lds_u8(r1 + b0)));
-            const float2 t11 = unorm2<PK>(bytes2(lds_u8(r1 + a1), lds_u8(r1 + b1)));
-            const float2 v = bilin2<PK>(mul2<PK>(NA[p], NB), mul2<PK>(A[p], NB), mul2<PK>(NA[p], B), mul2<PK>(A[p], B), t00, t10, t01, t11, ONE);
-            Yi[r][p] = settle(Yi[r][p], v, ft.fy, 0.f, okc[2 * p] & okr, okc[2 * p + 1] & okr);
+            float2 x = Yi[0][p];
+            Yi[0][p] = Yi[2][p], Yi[2][p] = x;
+            x = Yi[1][p], Yi[1][p] = Yi[3][p], Yi[3][p] = x;
         }
-        if ((r & 1) == 0) {
-            const int k = r >> 1;
-            const uint2 rc = *reinterpret_cast<const uint2*>(rows + 2 * SVB_TILE_H + 2 * (2 * warp + k));
-            const unsigned q0 = ((rc.y & 0xffffu) - jc0) * pitchC, q1 = q0 + ((rc.y >> 16) & 1u) * pitchC;
-            const int okq = (int)(rc.y >> 17);
-            const float2 BC = splat(__uint_as_float(rc.x)), NBC = splat(sub(1.f, __uint_as_float(rc.x)));
-            const float2 w00 = mul2<PK>(NAC, NBC), w10 = mul2<PK>(AC, NBC), w01 = mul2<PK>(NAC, BC), w11 = mul2<PK>(AC, BC);
-            const unsigned u0 = boxU + q0, u1 = boxU + q1, v0 = boxV + q0, v1 = boxV + q1;
-            const float2 u = bilin2<PK>(w00, w10, w01, w11, unorm2<PK>(bytes2(lds_u8(u0 + oc00), lds_u8(u0 + oc10))), unorm2<PK>(bytes2(lds_u8(u0 + oc01), lds_u8(u0 + oc11))),
-                                        unorm2<PK>(bytes2(lds_u8(u1 + oc00), lds_u8(u1 + oc10))), unorm2<PK>(bytes2(lds_u8(u1 + oc01), lds_u8(u1 + oc11))), ONE);
-            const float2 v = bilin2<PK>(w00, w10, w01, w11, unorm2<PK>(bytes2(lds_u8(v0 + oc00), lds_u8(v0 + oc10))), unorm2<PK>(bytes2(lds_u8(v0 + oc01), lds_u8(v0 + oc11))),
-                                        unorm2<PK>(bytes2(lds_u8(v1 + oc00), lds_u8(v1 + oc10))), unorm2<PK>(bytes2(lds_u8(v1 + oc01), lds_u8(v1 + oc11))), ONE);
-            Ui[k] = settle(Ui[k], u, ft.fu, -1.f, okc0 & okq, okc1 & okq);
-            Vi[k] = settle(Vi[k], v, ft.fv, -1.f, okc0 & okq, okc1 & okq);
-        }
+        float2 x = Ui[0];
+        Ui[0] = Ui[1], Ui[1] = x;
+        x = Vi[0], Vi[0] = Vi[1], Vi[1] = x;
     }
+#else
+    row_pair(0, Yi[0], Yi[1], Ui[0], Vi[0]);
+    row_pair(1, Yi[2], Yi[3], Ui[1], Vi[1]);
+#endif
 }
 
 // Any layer, any tile: the per-pixel evaluator of svb_device.cuh over this thread's 4x4 block.  Kept compact (one
