@@ -164,7 +164,11 @@ __device__ __forceinline__ float2 bilin2(float2 w00, float2 w10, float2 w01, flo
 struct TiledSmem {  // the fixed part; the boxes follow at SVB_TILED_FIXED_BYTES: Y[0] Y[1] C[0] C[1]
     alignas(128) uint32_t tabs[2][SVB_TILE_TAB_WORDS];  // the staged layer's table blocks, copied with its boxes
     alignas(8) uint64_t bar[2];
-    int4 plan[2][SVB_MAX_LAYERS][2];  // [tile parity][l][0] = (mode, iy0, jy0, ic0), [..][1] = (jc0, 0, 0, 0)
+    // [tile parity][l]: [0] = (mode, iy0, jy0, ic0)   [1] = (jc0, format << 8 | flags, box_w | box_cw << 16, opacity bits)
+    // and, ready for the one thread that issues the copies (every instruction on its path makes its warp late for the
+    // next barrier): [2] = (&tmap Y, &tmap C)   [3] = (&tmap V or 0, table column block)   [4] = (table row block, tx bytes, frame)
+    int4 plan[2][SVB_MAX_LAYERS][5];
+    int nlayers[2];                  // [tile parity]: layers of the planned tile's frame
     int tile_idx[3];                 // ring over this CTA's tile sequence: index of its k-th tile in slot k % 3 (>= total: none)
     alignas(16) uint8_t cover[2][SVB_MAX_LAYERS];  // [tile parity][l] = l if layer l hides everything under it on this tile, else 0
 };
@@ -388,12 +392,13 @@ namespace svb {
 
 struct TileGeo {
     const SvbFrameDesc* F;
-    int x0, y0, lastc, lastr;
+    int frame, x0, y0, lastc, lastr;
 };
 __device__ __forceinline__ TileGeo tile_geo(const SvbFrameDesc* __restrict__ frames, int nframes, int& f, int tile) {
     while (f + 1 < nframes && frames[f + 1].first_tile <= tile) ++f;
     TileGeo g;
     g.F = frames + f;
+    g.frame = f;
     const int local = tile - g.F->first_tile;
     g.x0 = (local % g.F->tiles_x) * SVB_TILE_W;
     g.y0 = (local / g.F->tiles_x) * SVB_TILE_H;
@@ -435,7 +440,17 @@ __device__ __forceinline__ void plan_layer(const uint32_t* __restrict__ tables, 
         covers = full && (L->flags & SVB_LAYER_UNIT_OPACITY);
     }
     out[0] = make_int4(mode, iy0, jy0, ic0);
-    out[1] = make_int4(jc0, 0, 0, 0);
+    out[1] = make_int4(jc0, (L->format << 8) | (L->flags & 0xff), L->box_w | (L->box_cw << 16), __float_as_int(L->u.opacity));
+    if (mode >= PLAN_STAGED) {
+        const bool n12 = L->format == SVB_NV12;
+        const int cbytes = n12 ? L->box_cw * L->box_ch * 2 : L->box_cw * L->box_ch;
+        const Tabs tb = layer_tabs(tables, F, l);
+        const unsigned long long m0 = (unsigned long long)L->tmap[0], m1 = (unsigned long long)L->tmap[1], m2 = n12 ? 0ull : (unsigned long long)L->tmap[2];
+        const unsigned long long cb = (unsigned long long)(tb.col + (x0 / SVB_TILE_W) * SVB_TAB_COL_WORDS), rb = (unsigned long long)(tb.row + (y0 / SVB_TILE_H) * SVB_TAB_ROW_WORDS);
+        out[2] = make_int4((int)(unsigned)m0, (int)(m0 >> 32), (int)(unsigned)m1, (int)(m1 >> 32));
+        out[3] = make_int4((int)(unsigned)m2, (int)(m2 >> 32), (int)(unsigned)cb, (int)(cb >> 32));
+        out[4] = make_int4((int)(unsigned)rb, (int)(rb >> 32), L->box_w * L->box_h + cbytes * (n12 ? 1 : 2) + SVB_TILE_TAB_WORDS * 4, g.frame);
+    }
     if (OCCL) *cover = (uint8_t)(covers ? l : 0);
 }
 // Occlusion: the layers under the topmost covering layer of a tile are skipped -- neither fetched nor computed -- and
@@ -449,7 +464,7 @@ __device__ __forceinline__ int first_layer(const uint8_t* cover, int nl) {
 
 // Plan of a whole tile: lane l of the planning warp plans layer l (lanes up to SVB_MAX_LAYERS clear their cover byte).
 template <bool OCCL>
-__device__ __forceinline__ void plan_tile(const uint32_t* __restrict__ tables, const TileGeo& g, int lane, int4 (*__restrict__ out)[2], uint8_t* __restrict__ cover) {
+__device__ __forceinline__ void plan_tile(const uint32_t* __restrict__ tables, const TileGeo& g, int lane, int4 (*__restrict__ out)[5], uint8_t* __restrict__ cover) {
     if (lane < g.F->nlayers) plan_layer<OCCL>(tables, g, lane, out[lane], cover + lane);
     else if (OCCL && lane < SVB_MAX_LAYERS) cover[lane] = 0;
 }
@@ -470,7 +485,7 @@ __device__ __forceinline__ void mix_tiled_body(const SvbFrameDesc* __restrict__ 
     // SVB_PRODUCER_WARP (off; measured slower, profiles/r1_history.md): a ninth warp that only plans and issues copies.
     const bool producer = SVB_PRODUCER_WARP && warp == SVB_TILED_COMPUTE_WARPS;
     const int pt = SVB_PRODUCER_WARP ? t - SVB_TILED_COMPUTE_WARPS * 32 : t;  // index among the planning threads (negative: not one)
-    const SvbFrameDesc* fenced = nullptr;              // frame whose tensor maps this CTA's producer has acquired
+    int fenced = -1;  // frame whose tensor maps this CTA's issuing thread has acquired
     unsigned phase0 = 0, phase1 = 0;
     if (t == 0) {
         mbar_init(&sm.bar[0], 1);
@@ -514,55 +529,55 @@ __device__ __forceinline__ void mix_tiled_body(const SvbFrameDesc* __restrict__ 
         uint8_t* const oU = (uint8_t*)F->out_plane[1];
         uint8_t* const oV = (uint8_t*)F->out_plane[2];
         const int sY = F->out_stride[0], sU = F->out_stride[1], sV = F->out_stride[2];
-        const int4(*plan)[2] = sm.plan[cur];
+        const int4(*plan)[5] = sm.plan[cur];
         const int first = OCCL ? first_layer(sm.cover[cur], nl) : 0;  // layers below it are hidden on this tile
 
-        // TMA of one staged layer into buffer `b`: the source boxes and the tile's slices of the coordinate tables
-        auto issue = [&](const TileGeo& tg, const int4(*pl)[2], int l, int b) {
-            const SvbFrameDesc* __restrict__ TF = tg.F;
-            const SvbLayerDesc* __restrict__ L = &TF->layers[l];
-            const int4 p0 = pl[l][0], p1 = pl[l][1];
-            const bool n12 = L->format == SVB_NV12;
-            const int cbytes = n12 ? L->box_cw * L->box_ch * 2 : L->box_cw * L->box_ch;
-            const Tabs tb = layer_tabs(tables, TF, l);
-            if (TF != fenced) {  // the host rewrites the descriptors between launches: acquire a frame's maps once per CTA
+        // TMA of one staged layer into buffer `b`: the source boxes and the tile's blocks of the coordinate tables, all
+        // addresses and sizes precomputed by the planner
+        auto issue = [&](const int4(*pl)[5], int l, int b) {
+            const int4 q0 = pl[l][0], q1 = pl[l][1], q2 = pl[l][2], q3 = pl[l][3], q4 = pl[l][4];
+            auto ptr = [](int lo, int hi) { return (const void*)(((unsigned long long)(unsigned)hi << 32) | (unsigned)lo); };
+            if (q4.w != fenced) {  // the host rewrites the descriptors between launches: acquire a frame's maps once per CTA
+                const SvbFrameDesc* __restrict__ TF = frames + q4.w;
                 for (int q = 0; q < TF->nlayers; ++q)
                     if (TF->layers[q].flags & SVB_LAYER_STAGED) {
                         tmap_acquire(TF->layers[q].tmap[0]);
                         tmap_acquire(TF->layers[q].tmap[1]);
                         if (TF->layers[q].format != SVB_NV12) tmap_acquire(TF->layers[q].tmap[2]);
                     }
-                fenced = TF;
+                fenced = q4.w;
             }
-            mbar_expect_tx(&sm.bar[b], L->box_w * L->box_h + cbytes * (n12 ? 1 : 2) + SVB_TILE_TAB_WORDS * 4);
-            tma_load_2d(boxes + b * box_y_bytes, L->tmap[0], p0.y, p0.z, &sm.bar[b]);
-            tma_load_2d(boxes + 2 * box_y_bytes + b * box_c_bytes, L->tmap[1], p0.w, p1.x, &sm.bar[b]);
-            if (!n12) tma_load_2d(boxes + 2 * box_y_bytes + b * box_c_bytes + box_c_bytes / 2, L->tmap[2], p0.w, p1.x, &sm.bar[b]);
-            bulk_load(sm.tabs[b], tb.col + (tg.x0 / SVB_TILE_W) * SVB_TAB_COL_WORDS, SVB_TAB_COL_WORDS * 4, &sm.bar[b]);
-            bulk_load(sm.tabs[b] + SVB_TAB_COL_WORDS, tb.row + (tg.y0 / SVB_TILE_H) * SVB_TAB_ROW_WORDS, SVB_TAB_ROW_WORDS * 4, &sm.bar[b]);
+            uint8_t* const by = boxes + b * box_y_bytes;
+            uint8_t* const bc = boxes + 2 * box_y_bytes + b * box_c_bytes;
+            mbar_expect_tx(&sm.bar[b], q4.z);
+            tma_load_2d(by, ptr(q2.x, q2.y), q0.y, q0.z, &sm.bar[b]);
+            tma_load_2d(bc, ptr(q2.z, q2.w), q0.w, q1.x, &sm.bar[b]);
+            if (q3.x | q3.y) tma_load_2d(bc + box_c_bytes / 2, ptr(q3.x, q3.y), q0.w, q1.x, &sm.bar[b]);
+            bulk_load(sm.tabs[b], ptr(q3.z, q3.w), SVB_TAB_COL_WORDS * 4, &sm.bar[b]);
+            bulk_load(sm.tabs[b] + SVB_TAB_COL_WORDS, ptr(q4.x, q4.y), SVB_TAB_ROW_WORDS * 4, &sm.bar[b]);
         };
         // first staged layer of `pl`, or -1
-        auto first_staged = [&](const int4(*pl)[2], int from, int n) {
+        auto first_staged = [&](const int4(*pl)[5], int from, int n) {
             for (int l = from; l < n; ++l)
                 if (pl[l][0].x >= PLAN_STAGED) return l;
             return -1;
         };
         if (!primed && pt == 0) {
             const int l = first_staged(plan, first, nl);
-            if (l >= 0) issue(g, plan, l, stage);
+            if (l >= 0) issue(plan, l, stage);
         }
         primed = false;
         // plan of this CTA's next tile, off the critical path (its loads overlap the copy in flight)
         const int k3n = k3 == 2 ? 0 : k3 + 1;  // slot of the next tile's index; the slot after it receives the new claim
         const int next_tile = sm.tile_idx[k3n];
         const bool has_next = next_tile < total_tiles;
-        TileGeo gn = g;
-        {
+        if (warp == SVB_PLAN_WARP) {
             int claimed = 0;
             if (claimer) claimed = claim();
             if (has_next) {
-                gn = tile_geo(frames, nframes, fnext, next_tile);
-                if (warp == SVB_PLAN_WARP) plan_tile<OCCL>(tables, gn, lane, sm.plan[cur ^ 1], sm.cover[cur ^ 1]);
+                const TileGeo gn = tile_geo(frames, nframes, fnext, next_tile);
+                plan_tile<OCCL>(tables, gn, lane, sm.plan[cur ^ 1], sm.cover[cur ^ 1]);
+                if (lane == 0) sm.nlayers[cur ^ 1] = gn.F->nlayers;
             }
             if (claimer) sm.tile_idx[k3n == 2 ? 0 : k3n + 1] = claimed;
         }
@@ -601,17 +616,19 @@ __device__ __forceinline__ void mix_tiled_body(const SvbFrameDesc* __restrict__ 
             if (mode == PLAN_SKIP) continue;
             const SvbLayerDesc* __restrict__ L = &F->layers[l];
             if (mode >= PLAN_STAGED) {
-                const int jc0 = plan[l][1].x;
+                const int4 p1 = plan[l][1];
+                const int jc0 = p1.x;
                 __syncthreads();  // every warp is past its reads of the other buffer (and the next tile's plan is written)
-                {   // refill the other buffer: the next staged layer of this tile, else the first one of the next tile
+                if (pt == 0) {  // refill the other buffer: the next staged layer of this tile, else the first one of the next tile
                     const int j = first_staged(plan, l + 1, nl);
                     if (j >= 0) {
-                        if (pt == 0) issue(g, plan, j, stage ^ 1);
+                        issue(plan, j, stage ^ 1);
                     } else if (has_next) {
-                        const int jn = first_staged(sm.plan[cur ^ 1], OCCL ? first_layer(sm.cover[cur ^ 1], gn.F->nlayers) : 0, gn.F->nlayers);
+                        const int nln = sm.nlayers[cur ^ 1];
+                        const int jn = first_staged(sm.plan[cur ^ 1], OCCL ? first_layer(sm.cover[cur ^ 1], nln) : 0, nln);
                         if (jn >= 0) {
-                            if (pt == 0) issue(gn, sm.plan[cur ^ 1], jn, stage ^ 1);
-                            primed = true;
+                            issue(sm.plan[cur ^ 1], jn, stage ^ 1);
+                            primed = true;  // only this thread looks at it
                         }
                     }
                 }
@@ -622,22 +639,22 @@ __device__ __forceinline__ void mix_tiled_body(const SvbFrameDesc* __restrict__ 
                 if (stage == 0) phase0 ^= 1;
                 else phase1 ^= 1;
                 if (live) {
-                    const int fmt = L->format, lflags = L->flags;
-                    const int pitchC = fmt == SVB_NV12 ? L->box_cw * 2 : L->box_cw, stepC = fmt == SVB_NV12 ? 2 : 1;
+                    const int fmt = p1.y >> 8, lflags = p1.y & 0xff, box_w = p1.z & 0xffff, box_cw = p1.z >> 16;
+                    const int pitchC = fmt == SVB_NV12 ? box_cw * 2 : box_cw, stepC = fmt == SVB_NV12 ? 2 : 1;
                     const unsigned bY = smem_u32(boxes + stage * box_y_bytes), bU = smem_u32(boxes + 2 * box_y_bytes + stage * box_c_bytes);
                     const unsigned bV = bU + (fmt == SVB_NV12 ? 1 : box_c_bytes / 2);
-                    const float alpha = L->u.opacity;
+                    const float alpha = __int_as_float(p1.w);
                     FillTerms ft;
                     if (mode == PLAN_STAGED_EDGE || !(lflags & SVB_LAYER_OPACITY_01)) {
                         const float4 fc = ldrow(L->u.fillColor, 0);
                         const float3 fill = rgb2yuv(fc.x, fc.y, fc.z);
                         const float af = mul(alpha, fc.w);
                         ft.fy = splat(fill.x), ft.fu = splat(fill.y), ft.fv = splat(fill.z), ft.af = splat(af), ft.naf = splat(sub(1.f, af));
-                        fast_layer<2, true>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, L->box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
+                        fast_layer<2, true>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
                     } else if (lflags & SVB_LAYER_UNIT_OPACITY) {
-                        fast_layer<0, true>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, L->box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
+                        fast_layer<0, true>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
                     } else {
-                        fast_layer<1, true>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, L->box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
+                        fast_layer<1, true>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
                     }
                 }
                 stage ^= 1;

@@ -96,7 +96,7 @@ typedef struct __attribute__((aligned(64))) SvbFrameDesc {
 // behind it two luma boxes and two chroma boxes whose size the host picks PER LAUNCH from the largest staged footprint
 // of the batch (box_y_bytes / box_c_bytes kernel arguments, multiples of 256, at most SVB_BOX_*_BYTES): shared memory
 // not taken stays L1, and the headline workload needs 11 KB per stage, not the 32 KB worst case.
-#define SVB_TILED_FIXED_BYTES (2 * (SVB_TAB_COL_WORDS + SVB_TAB_ROW_WORDS) * 4 + 256 + 2 * SVB_MAX_LAYERS * 32)
+#define SVB_TILED_FIXED_BYTES (2 * (SVB_TAB_COL_WORDS + SVB_TAB_ROW_WORDS) * 4 + 256 + 2 * SVB_MAX_LAYERS * 80)
 #define SVB_TILED_SMEM_BYTES(boxY, boxC) (SVB_TILED_FIXED_BYTES + 2 * (boxY) + 2 * (boxC))
 #define SVB_TILED_SMEM_MAX SVB_TILED_SMEM_BYTES(SVB_BOX_Y_BYTES, SVB_BOX_C_BYTES)
 
