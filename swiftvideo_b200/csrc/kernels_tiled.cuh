@@ -196,6 +196,12 @@ __device__ __forceinline__ unsigned lds_u8(unsigned addr) {  // opaque u32 (see 
     return v;
 }
 
+template <int OFF> __device__ __forceinline__ unsigned lds_u8o(unsigned addr) {  // [addr + OFF] with OFF in the instruction
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+
 // Tables of one layer of one frame: tiles_x column blocks, then tiles_y row blocks
 struct Tabs {
     const uint32_t* col;
@@ -226,30 +232,41 @@ __device__ __forceinline__ Ent ld_row_c(const Tabs& t, int c) { const uint32_t* 
 struct FillTerms {
     float2 fy, fu, fv, af, naf;  // RGB2YUV(fillColor.rgb, 1) splat; opacity*fillColor.w and its complement
 };
-template <int MODE, bool PK>
+//   MODE 0 and 1 are only planned for tiles whose taps are never clamped along x (i1 == i0 + 1 for every column of
+//   the tile, luma and chroma): the second tap of a row is then the first one's address plus an immediate, and a pixel
+//   costs two address adds (one per tap row) instead of four.  N12 tells them the chroma layout (NV12: U and V
+//   interleaved, so all eight chroma taps of a texel hang off two addresses); MODE 2 reads it from pitchC / stepC.
+template <int MODE, bool PK, bool N12>
 __device__ __forceinline__ void fast_layer(unsigned boxY, unsigned boxU, unsigned boxV, const uint32_t* __restrict__ tabs, int lane, int warp, int iy0, int jy0,
                                            int ic0, int jc0, int pitchY, int pitchC, int stepC, float alpha, float onef, const FillTerms& ft,
                                            float2 (&Yi)[4][2], float2 (&Ui)[2], float2 (&Vi)[2]) {
     constexpr bool UNIT = MODE == 0, GEN = MODE == 2;
     const float2 AL = splat(alpha), NAL = splat(sub(1.f, alpha)), ONE = splat(onef);
-    unsigned o0[4], o1[4];
-    int okc[4];
+    unsigned o0[4], o1[4];  // o1 only where taps may be clamped along x (GEN)
+    int okc[4] = {7, 7, 7, 7};
     float2 A[2], NA[2];
 #pragma unroll
     for (int p = 0; p < 2; ++p) {  // pair p = luma columns 64p + 2*lane, +1 of the tile: 8-byte reads, lane after lane
         const float2 a = *reinterpret_cast<const float2*>(tabs + 64 * p + 2 * lane);
         const uint2 e = *reinterpret_cast<const uint2*>(tabs + SVB_TILE_W + 64 * p + 2 * lane);
-        o0[2 * p] = boxY + ((e.x & 0xffffu) - iy0), o1[2 * p] = o0[2 * p] + ((e.x >> 16) & 1u);
-        o0[2 * p + 1] = boxY + ((e.y & 0xffffu) - iy0), o1[2 * p + 1] = o0[2 * p + 1] + ((e.y >> 16) & 1u);
-        okc[2 * p] = (int)(e.x >> 17), okc[2 * p + 1] = (int)(e.y >> 17);
+        o0[2 * p] = boxY + ((e.x & 0xffffu) - iy0), o0[2 * p + 1] = boxY + ((e.y & 0xffffu) - iy0);
+        if (GEN) {
+            o1[2 * p] = o0[2 * p] + ((e.x >> 16) & 1u), o1[2 * p + 1] = o0[2 * p + 1] + ((e.y >> 16) & 1u);
+            okc[2 * p] = (int)(e.x >> 17), okc[2 * p + 1] = (int)(e.y >> 17);
+        }
         A[p] = a;
         NA[p] = make_float2(sub(1.f, a.x), sub(1.f, a.y));
     }
     // chroma columns lane and 32 + lane of the tile (the texels under the two luma pairs)
     const uint32_t pc0 = tabs[2 * SVB_TILE_W + SVB_TILE_W / 2 + lane], pc1 = tabs[2 * SVB_TILE_W + SVB_TILE_W / 2 + 32 + lane];
-    const unsigned oc00 = ((pc0 & 0xffffu) - ic0) * stepC, oc01 = oc00 + ((pc0 >> 16) & 1u) * stepC;
-    const unsigned oc10 = ((pc1 & 0xffffu) - ic0) * stepC, oc11 = oc10 + ((pc1 >> 16) & 1u) * stepC;
-    const int okc0 = (int)(pc0 >> 17), okc1 = (int)(pc1 >> 17);
+    const unsigned sC = GEN ? (unsigned)stepC : (N12 ? 2u : 1u);
+    const unsigned oc00 = ((pc0 & 0xffffu) - ic0) * sC, oc10 = ((pc1 & 0xffffu) - ic0) * sC;
+    unsigned oc01 = 0, oc11 = 0;
+    int okc0 = 7, okc1 = 7;
+    if (GEN) {
+        oc01 = oc00 + ((pc0 >> 16) & 1u) * sC, oc11 = oc10 + ((pc1 >> 16) & 1u) * sC;
+        okc0 = (int)(pc0 >> 17), okc1 = (int)(pc1 >> 17);
+    }
     const float2 AC = make_float2(__uint_as_float(tabs[2 * SVB_TILE_W + lane]), __uint_as_float(tabs[2 * SVB_TILE_W + 32 + lane]));
     const float2 NAC = make_float2(sub(1.f, AC.x), sub(1.f, AC.y));
     // blend -> UNORM8 write -> the next layer's UNORM8 read stays an integer-valued float
@@ -274,29 +291,54 @@ __device__ __forceinline__ void fast_layer(unsigned boxY, unsigned boxU, unsigne
             float2(&Yr)[2] = r == 0 ? Y0 : Y1;
             const uint2 ry = *reinterpret_cast<const uint2*>(rows + 2 * (4 * warp + 2 * k + r));
             const unsigned r0 = ((ry.y & 0xffffu) - jy0) * pitchY, r1 = r0 + ((ry.y >> 16) & 1u) * pitchY;
-            const int okr = (int)(ry.y >> 17);
+            const int okr = GEN ? (int)(ry.y >> 17) : 7;
             const float2 B = splat(__uint_as_float(ry.x)), NB = splat(sub(1.f, __uint_as_float(ry.x)));
 #pragma unroll
             for (int p = 0; p < 2; ++p) {
-                const unsigned a0 = o0[2 * p], a1 = o1[2 * p], b0 = o0[2 * p + 1], b1 = o1[2 * p + 1];
-                const float2 t00 = unorm2<PK>(bytes2(lds_u8(r0 + a0), lds_u8(r0 + b0)));
-                const float2 t10 = unorm2<PK>(bytes2(lds_u8(r0 + a1), lds_u8(r0 + b1)));
-                const float2 t01 = unorm2<PK>(bytes2(lds_u8(r1 + a0), lds_u8(r1 + b0)));
-                const float2 t11 = unorm2<PK>(bytes2(lds_u8(r1 + a1), lds_u8(r1 + b1)));
+                float2 t00, t10, t01, t11;
+                if (GEN) {
+                    const unsigned a0 = o0[2 * p], a1 = o1[2 * p], b0 = o0[2 * p + 1], b1 = o1[2 * p + 1];
+                    t00 = unorm2<PK>(bytes2(lds_u8(r0 + a0), lds_u8(r0 + b0)));
+                    t10 = unorm2<PK>(bytes2(lds_u8(r0 + a1), lds_u8(r0 + b1)));
+                    t01 = unorm2<PK>(bytes2(lds_u8(r1 + a0), lds_u8(r1 + b0)));
+                    t11 = unorm2<PK>(bytes2(lds_u8(r1 + a1), lds_u8(r1 + b1)));
+                } else {
+                    const unsigned a0 = r0 + o0[2 * p], b0 = r0 + o0[2 * p + 1], a1 = r1 + o0[2 * p], b1 = r1 + o0[2 * p + 1];
+                    t00 = unorm2<PK>(bytes2(lds_u8o<0>(a0), lds_u8o<0>(b0)));
+                    t10 = unorm2<PK>(bytes2(lds_u8o<1>(a0), lds_u8o<1>(b0)));
+                    t01 = unorm2<PK>(bytes2(lds_u8o<0>(a1), lds_u8o<0>(b1)));
+                    t11 = unorm2<PK>(bytes2(lds_u8o<1>(a1), lds_u8o<1>(b1)));
+                }
                 const float2 v = bilin2<PK>(mul2<PK>(NA[p], NB), mul2<PK>(A[p], NB), mul2<PK>(NA[p], B), mul2<PK>(A[p], B), t00, t10, t01, t11, ONE);
                 Yr[p] = settle(Yr[p], v, ft.fy, 0.f, okc[2 * p] & okr, okc[2 * p + 1] & okr);
             }
         }
         const uint2 rc = *reinterpret_cast<const uint2*>(rows + 2 * SVB_TILE_H + 2 * (2 * warp + k));
         const unsigned q0 = ((rc.y & 0xffffu) - jc0) * pitchC, q1 = q0 + ((rc.y >> 16) & 1u) * pitchC;
-        const int okq = (int)(rc.y >> 17);
+        const int okq = GEN ? (int)(rc.y >> 17) : 7;
         const float2 BC = splat(__uint_as_float(rc.x)), NBC = splat(sub(1.f, __uint_as_float(rc.x)));
         const float2 w00 = mul2<PK>(NAC, NBC), w10 = mul2<PK>(AC, NBC), w01 = mul2<PK>(NAC, BC), w11 = mul2<PK>(AC, BC);
-        const unsigned u0 = boxU + q0, u1 = boxU + q1, v0 = boxV + q0, v1 = boxV + q1;
-        const float2 u = bilin2<PK>(w00, w10, w01, w11, unorm2<PK>(bytes2(lds_u8(u0 + oc00), lds_u8(u0 + oc10))), unorm2<PK>(bytes2(lds_u8(u0 + oc01), lds_u8(u0 + oc11))),
-                                    unorm2<PK>(bytes2(lds_u8(u1 + oc00), lds_u8(u1 + oc10))), unorm2<PK>(bytes2(lds_u8(u1 + oc01), lds_u8(u1 + oc11))), ONE);
-        const float2 v = bilin2<PK>(w00, w10, w01, w11, unorm2<PK>(bytes2(lds_u8(v0 + oc00), lds_u8(v0 + oc10))), unorm2<PK>(bytes2(lds_u8(v0 + oc01), lds_u8(v0 + oc11))),
-                                    unorm2<PK>(bytes2(lds_u8(v1 + oc00), lds_u8(v1 + oc10))), unorm2<PK>(bytes2(lds_u8(v1 + oc01), lds_u8(v1 + oc11))), ONE);
+        const unsigned u0 = boxU + q0, u1 = boxU + q1;
+        float2 u, v;
+        if (GEN) {
+            const unsigned v0 = boxV + q0, v1 = boxV + q1;
+            u = bilin2<PK>(w00, w10, w01, w11, unorm2<PK>(bytes2(lds_u8(u0 + oc00), lds_u8(u0 + oc10))), unorm2<PK>(bytes2(lds_u8(u0 + oc01), lds_u8(u0 + oc11))),
+                           unorm2<PK>(bytes2(lds_u8(u1 + oc00), lds_u8(u1 + oc10))), unorm2<PK>(bytes2(lds_u8(u1 + oc01), lds_u8(u1 + oc11))), ONE);
+            v = bilin2<PK>(w00, w10, w01, w11, unorm2<PK>(bytes2(lds_u8(v0 + oc00), lds_u8(v0 + oc10))), unorm2<PK>(bytes2(lds_u8(v0 + oc01), lds_u8(v0 + oc11))),
+                           unorm2<PK>(bytes2(lds_u8(v1 + oc00), lds_u8(v1 + oc10))), unorm2<PK>(bytes2(lds_u8(v1 + oc01), lds_u8(v1 + oc11))), ONE);
+        } else if (N12) {  // (U, V) byte pairs: texel i0 at [c], [c+1], texel i0 + 1 at [c+2], [c+3]
+            const unsigned c00 = u0 + oc00, c10 = u0 + oc10, c01 = u1 + oc00, c11 = u1 + oc10;
+            u = bilin2<PK>(w00, w10, w01, w11, unorm2<PK>(bytes2(lds_u8o<0>(c00), lds_u8o<0>(c10))), unorm2<PK>(bytes2(lds_u8o<2>(c00), lds_u8o<2>(c10))),
+                           unorm2<PK>(bytes2(lds_u8o<0>(c01), lds_u8o<0>(c11))), unorm2<PK>(bytes2(lds_u8o<2>(c01), lds_u8o<2>(c11))), ONE);
+            v = bilin2<PK>(w00, w10, w01, w11, unorm2<PK>(bytes2(lds_u8o<1>(c00), lds_u8o<1>(c10))), unorm2<PK>(bytes2(lds_u8o<3>(c00), lds_u8o<3>(c10))),
+                           unorm2<PK>(bytes2(lds_u8o<1>(c01), lds_u8o<1>(c11))), unorm2<PK>(bytes2(lds_u8o<3>(c01), lds_u8o<3>(c11))), ONE);
+        } else {  // planar chroma: the V box lies boxV - boxU bytes behind the U box
+            const unsigned c00 = u0 + oc00, c10 = u0 + oc10, c01 = u1 + oc00, c11 = u1 + oc10, dv = boxV - boxU;
+            u = bilin2<PK>(w00, w10, w01, w11, unorm2<PK>(bytes2(lds_u8o<0>(c00), lds_u8o<0>(c10))), unorm2<PK>(bytes2(lds_u8o<1>(c00), lds_u8o<1>(c10))),
+                           unorm2<PK>(bytes2(lds_u8o<0>(c01), lds_u8o<0>(c11))), unorm2<PK>(bytes2(lds_u8o<1>(c01), lds_u8o<1>(c11))), ONE);
+            v = bilin2<PK>(w00, w10, w01, w11, unorm2<PK>(bytes2(lds_u8o<0>(c00 + dv), lds_u8o<0>(c10 + dv))), unorm2<PK>(bytes2(lds_u8o<1>(c00 + dv), lds_u8o<1>(c10 + dv))),
+                           unorm2<PK>(bytes2(lds_u8o<0>(c01 + dv), lds_u8o<0>(c11 + dv))), unorm2<PK>(bytes2(lds_u8o<1>(c01 + dv), lds_u8o<1>(c11 + dv))), ONE);
+        }
         Uk = settle(Uk, u, ft.fu, -1.f, okc0 & okq, okc1 & okq);
         Vk = settle(Vk, v, ft.fv, -1.f, okc0 & okq, okc1 & okq);
     };
@@ -436,7 +478,10 @@ __device__ __forceinline__ void plan_layer(const uint32_t* __restrict__ tables, 
                           max(rcA.i1, rcB.i1) - jc0 < L->box_ch;
         // border, tx and uv are monotone too: both ends inside [0,1] means every pixel of the tile is inside the picture
         const bool full = cA.ok == 7 && cB.ok == 7 && rA.ok == 7 && rB.ok == 7;
-        mode = !((L->flags & SVB_LAYER_STAGED) && fits) ? PLAN_GENERIC : (full ? PLAN_STAGED : PLAN_STAGED_EDGE);
+        // i1 - i0 is 0 only where the tap index was clamped, and the unclamped index is monotone: the ends decide for the tile.
+        // The interior layer bodies (MODE 0 / 1) address the second tap of a row as "first + 1".
+        const bool xfree = cA.i1 != cA.i0 && cB.i1 != cB.i0 && ccA.i1 != ccA.i0 && ccB.i1 != ccB.i0;
+        mode = !((L->flags & SVB_LAYER_STAGED) && fits) ? PLAN_GENERIC : (full && xfree ? PLAN_STAGED : PLAN_STAGED_EDGE);
         covers = full && (L->flags & SVB_LAYER_UNIT_OPACITY);
     }
     out[0] = make_int4(mode, iy0, jy0, ic0);
@@ -650,11 +695,13 @@ __device__ __forceinline__ void mix_tiled_body(const SvbFrameDesc* __restrict__ 
                         const float3 fill = rgb2yuv(fc.x, fc.y, fc.z);
                         const float af = mul(alpha, fc.w);
                         ft.fy = splat(fill.x), ft.fu = splat(fill.y), ft.fv = splat(fill.z), ft.af = splat(af), ft.naf = splat(sub(1.f, af));
-                        fast_layer<2, true>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
+                        fast_layer<2, true, false>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
                     } else if (lflags & SVB_LAYER_UNIT_OPACITY) {
-                        fast_layer<0, true>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
+                        if (fmt == SVB_NV12) fast_layer<0, true, true>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
+                        else fast_layer<0, true, false>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
                     } else {
-                        fast_layer<1, true>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
+                        if (fmt == SVB_NV12) fast_layer<1, true, true>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
+                        else fast_layer<1, true, false>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
                     }
                 }
                 stage ^= 1;
