@@ -31,6 +31,15 @@
 #ifndef SVB_ROLL_ROWS
 #define SVB_ROLL_ROWS 1  // the layer bodies run their two row pairs as a rolled loop (0: unrolled, 0.7 % slower at three CTAs per SM)
 #endif
+#ifndef SVB_EDGE_INLINE
+#define SVB_EDGE_INLINE 1  // 1: the edge-tile layer bodies (MODE 2 / 3) inlined into the compositor instead of called
+#endif
+#ifndef SVB_LEAN_EDGE
+#define SVB_LEAN_EDGE 1  // 0: every edge tile takes the general body (MODE 3)
+#endif
+#ifndef SVB_SPLIT_BARRIER
+#define SVB_SPLIT_BARRIER 0
+#endif
 #ifndef SVB_DYNAMIC_TILES
 // 1: CTAs claim tiles from a counter (row-major order, so neighbouring tiles still run together); 0: static round-robin.
 // Tiles cost between zero and eight layers, and with a static deal the slowest CTA's share decided the kernel time
@@ -123,6 +132,13 @@ __device__ __forceinline__ Ent axis_entry(const Axis& c, int n) {
     return e;
 }
 
+// The table entries of a layer, by output column / row (luma) or chroma texel column / row: chroma is produced by the even
+// luma column / row (kernels.cl.swift:76).  svb_mix_tables stores them, and plans tiles from the same functions.
+__device__ __forceinline__ Ent ent_col_y(const SvbLayerDesc* __restrict__ L, int W, int x) { return axis_entry(axis_chain(&L->u, 0, min(x, W - 1), (float)W), L->width); }
+__device__ __forceinline__ Ent ent_col_c(const SvbLayerDesc* __restrict__ L, int W, int c) { return axis_entry(axis_chain(&L->u, 0, min(2 * c, W - 2), (float)W), L->width / 2); }
+__device__ __forceinline__ Ent ent_row_y(const SvbLayerDesc* __restrict__ L, int H, int r) { return axis_entry(axis_chain(&L->u, 1, min(r, H - 1), (float)H), L->height); }
+__device__ __forceinline__ Ent ent_row_c(const SvbLayerDesc* __restrict__ L, int H, int c) { return axis_entry(axis_chain(&L->u, 1, min(2 * c, H - 2), (float)H), L->height / 2); }
+
 // ---- packed fp32x2 (sm_100): two independent IEEE operations per instruction, each rounded on its own --------
 // PK=false spells the same operations as two scalar instructions (identical results; kept for A/B timing:
 // SVB_FP32X2=0 in the environment of the host selects it).
@@ -163,16 +179,11 @@ __device__ __forceinline__ float2 bilin2(float2 w00, float2 w10, float2 w01, flo
 #define SVB_TILE_TAB_WORDS (SVB_TAB_COL_WORDS + SVB_TAB_ROW_WORDS)  // the column block and the row block of one tile
 struct TiledSmem {  // the fixed part; the boxes follow at SVB_TILED_FIXED_BYTES: Y[0] Y[1] C[0] C[1]
     alignas(128) uint32_t tabs[2][SVB_TILE_TAB_WORDS];  // the staged layer's table blocks, copied with its boxes
-    alignas(8) uint64_t bar[2];
-    // [tile parity][l]: [0] = (mode, iy0, jy0, ic0)   [1] = (jc0, format << 8 | flags, box_w | box_cw << 16, opacity bits)
-    // and, ready for the one thread that issues the copies (every instruction on its path makes its warp late for the
-    // next barrier): [2] = (&tmap Y, &tmap C)   [3] = (&tmap V or 0, table column block)   [4] = (table row block, tx bytes, frame)
-    int4 plan[2][SVB_MAX_LAYERS][5];
-    int nlayers[2];                  // [tile parity]: layers of the planned tile's frame
-    int tile_idx[3];                 // ring over this CTA's tile sequence: index of its k-th tile in slot k % 3 (>= total: none)
-    alignas(16) uint8_t cover[2][SVB_MAX_LAYERS];  // [tile parity][l] = l if layer l hides everything under it on this tile, else 0
+    alignas(16) SvbTilePlan plan[2];                    // [tile parity]: the tile's plan, fetched by one bulk copy (svb_mix_plan wrote it)
+    alignas(8) uint64_t bar[2];                         // box buffers
+    uint64_t pbar;                                      // plan slot
+    int tile_idx[3];                                    // ring over this CTA's tile sequence: index of its k-th tile in slot k % 3 (>= total: none)
 };
-static_assert(SVB_MAX_LAYERS == 16, "first_layer() reads the cover bytes as one 16-byte word");
 static_assert(sizeof(TiledSmem) <= SVB_TILED_FIXED_BYTES && SVB_TILED_FIXED_BYTES % 128 == 0, "SVB_TILED_FIXED_BYTES (svb_desc.h) must cover TiledSmem");
 enum { PLAN_SKIP = 0, PLAN_GENERIC = 1, PLAN_STAGED = 4, PLAN_STAGED_EDGE = 5 };  // >= PLAN_STAGED: boxes come by TMA
 
@@ -218,16 +229,15 @@ __device__ __forceinline__ int col_y_word(int x) { return (x / SVB_TILE_W) * SVB
 __device__ __forceinline__ int col_c_word(int c) { return (c / (SVB_TILE_W / 2)) * SVB_TAB_COL_WORDS + 2 * SVB_TILE_W + (c % (SVB_TILE_W / 2)); }
 __device__ __forceinline__ int row_y_word(int r) { return (r / SVB_TILE_H) * SVB_TAB_ROW_WORDS + 2 * (r % SVB_TILE_H); }
 __device__ __forceinline__ int row_c_word(int c) { return (c / (SVB_TILE_H / 2)) * SVB_TAB_ROW_WORDS + 2 * SVB_TILE_H + 2 * (c % (SVB_TILE_H / 2)); }
-__device__ __forceinline__ Ent ld_col_y(const Tabs& t, int x) { const uint32_t* p = t.col + col_y_word(x); return unpack_ent(__ldg(p), __ldg(p + SVB_TILE_W)); }
-__device__ __forceinline__ Ent ld_col_c(const Tabs& t, int c) { const uint32_t* p = t.col + col_c_word(c); return unpack_ent(__ldg(p), __ldg(p + SVB_TILE_W / 2)); }
-__device__ __forceinline__ Ent ld_row_y(const Tabs& t, int r) { const uint32_t* p = t.row + row_y_word(r); return unpack_ent(__ldg(p), __ldg(p + 1)); }
-__device__ __forceinline__ Ent ld_row_c(const Tabs& t, int c) { const uint32_t* p = t.row + row_c_word(c); return unpack_ent(__ldg(p), __ldg(p + 1)); }
 
 // One separable YUV layer over one tile, taps staged in shared memory.
 //   Yi / Ui / Vi: the running picture as integer-valued floats; pairs hold two horizontally adjacent samples.
 //   MODE 0: tile wholly inside the picture, opacity == 1 (cur*(1-1) + v*1 == v exactly: no blend)
 //   MODE 1: tile wholly inside the picture, 0 <= opacity <= 1 (blended values stay in [0,1]: no store clamp)
-//   MODE 2: anything: per-pixel class from the tables' ok bits -- picture / fill / untouched
+//   MODE 2: edge tile whose samples are either inside the picture or untouched (no fill sample in this warp's block, every
+//           row either wholly inside or outside the border rectangle; 0 <= opacity <= 1) -- the common edge.  Rows outside
+//           are skipped by their warp (rows are warp-uniform), columns outside keep their value through a 0/1 mask.
+//   MODE 3: anything: per-pixel class from the tables' ok bits -- picture / fill / untouched
 //           (kernels.cl.swift:77,84-85,96-105) -- and saturating stores
 struct FillTerms {
     float2 fy, fu, fv, af, naf;  // RGB2YUV(fillColor.rgb, 1) splat; opacity*fillColor.w and its complement
@@ -240,40 +250,41 @@ template <int MODE, bool PK, bool N12>
 __device__ __forceinline__ void fast_layer(unsigned boxY, unsigned boxU, unsigned boxV, const uint32_t* __restrict__ tabs, int lane, int warp, int iy0, int jy0,
                                            int ic0, int jc0, int pitchY, int pitchC, int stepC, float alpha, float onef, const FillTerms& ft,
                                            float2 (&Yi)[4][2], float2 (&Ui)[2], float2 (&Vi)[2]) {
-    constexpr bool UNIT = MODE == 0, GEN = MODE == 2;
+    constexpr bool UNIT = MODE == 0, EDGE = MODE == 2, GEN = MODE == 3, XCL = MODE >= 2;  // XCL: taps may be clamped along x
     const float2 AL = splat(alpha), NAL = splat(sub(1.f, alpha)), ONE = splat(onef);
-    unsigned o0[4], o1[4];  // o1 only where taps may be clamped along x (GEN)
+    unsigned o0[4], o1[4];
     int okc[4] = {7, 7, 7, 7};
-    float2 A[2], NA[2];
+    float2 A[2], NA[2], M[2];  // M (EDGE): 1 where the column is inside the picture, else 0
 #pragma unroll
     for (int p = 0; p < 2; ++p) {  // pair p = luma columns 64p + 2*lane, +1 of the tile: 8-byte reads, lane after lane
         const float2 a = *reinterpret_cast<const float2*>(tabs + 64 * p + 2 * lane);
         const uint2 e = *reinterpret_cast<const uint2*>(tabs + SVB_TILE_W + 64 * p + 2 * lane);
         o0[2 * p] = boxY + ((e.x & 0xffffu) - iy0), o0[2 * p + 1] = boxY + ((e.y & 0xffffu) - iy0);
-        if (GEN) {
-            o1[2 * p] = o0[2 * p] + ((e.x >> 16) & 1u), o1[2 * p + 1] = o0[2 * p + 1] + ((e.y >> 16) & 1u);
-            okc[2 * p] = (int)(e.x >> 17), okc[2 * p + 1] = (int)(e.y >> 17);
-        }
+        if (XCL) o1[2 * p] = o0[2 * p] + ((e.x >> 16) & 1u), o1[2 * p + 1] = o0[2 * p + 1] + ((e.y >> 16) & 1u);
+        if (GEN) okc[2 * p] = (int)(e.x >> 17), okc[2 * p + 1] = (int)(e.y >> 17);
+        if (EDGE) M[p] = make_float2((e.x >> 17) == 7u ? 1.f : 0.f, (e.y >> 17) == 7u ? 1.f : 0.f);
         A[p] = a;
         NA[p] = make_float2(sub(1.f, a.x), sub(1.f, a.y));
     }
     // chroma columns lane and 32 + lane of the tile (the texels under the two luma pairs)
     const uint32_t pc0 = tabs[2 * SVB_TILE_W + SVB_TILE_W / 2 + lane], pc1 = tabs[2 * SVB_TILE_W + SVB_TILE_W / 2 + 32 + lane];
-    const unsigned sC = GEN ? (unsigned)stepC : (N12 ? 2u : 1u);
+    const unsigned sC = XCL ? (unsigned)stepC : (N12 ? 2u : 1u);
     const unsigned oc00 = ((pc0 & 0xffffu) - ic0) * sC, oc10 = ((pc1 & 0xffffu) - ic0) * sC;
     unsigned oc01 = 0, oc11 = 0;
     int okc0 = 7, okc1 = 7;
-    if (GEN) {
-        oc01 = oc00 + ((pc0 >> 16) & 1u) * sC, oc11 = oc10 + ((pc1 >> 16) & 1u) * sC;
-        okc0 = (int)(pc0 >> 17), okc1 = (int)(pc1 >> 17);
-    }
+    float2 MC = splat(1.f);
+    if (XCL) oc01 = oc00 + ((pc0 >> 16) & 1u) * sC, oc11 = oc10 + ((pc1 >> 16) & 1u) * sC;
+    if (GEN) okc0 = (int)(pc0 >> 17), okc1 = (int)(pc1 >> 17);
+    if (EDGE) MC = make_float2((pc0 >> 17) == 7u ? 1.f : 0.f, (pc1 >> 17) == 7u ? 1.f : 0.f);
     const float2 AC = make_float2(__uint_as_float(tabs[2 * SVB_TILE_W + lane]), __uint_as_float(tabs[2 * SVB_TILE_W + 32 + lane]));
     const float2 NAC = make_float2(sub(1.f, AC.x), sub(1.f, AC.y));
     // blend -> UNORM8 write -> the next layer's UNORM8 read stays an integer-valued float
-    auto settle = [&](float2 cur_i, float2 v, float2 fillc, float lo, int ok0, int ok1) -> float2 {
+    auto settle = [&](float2 cur_i, float2 v, float2 fillc, float lo, int ok0, int ok1, float2 m) -> float2 {
         if (UNIT) return quant2<false, PK>(v, ONE);
         const float2 cur = unorm2<PK>(cur_i);
         const float2 qi = quant2<GEN, PK>(add2<PK>(mul2<PK>(cur, NAL), mul2<PK>(v, AL), ONE), ONE);
+        // columns outside the picture keep cur_i: cur_i + m*(qi - cur_i) in integer-valued floats, every step exact
+        if (EDGE) return fma2<PK>(m, fma2<PK>(cur_i, splat(-1.f), qi), cur_i);
         if (!GEN) return qi;
         float2 rf = add2<PK>(mul2<PK>(cur, ft.naf), mul2<PK>(fillc, ft.af), ONE);
         rf.x = fminf(fmaxf(rf.x, lo), 1.f), rf.y = fminf(fmaxf(rf.y, lo), 1.f);
@@ -290,13 +301,14 @@ __device__ __forceinline__ void fast_layer(unsigned boxY, unsigned boxU, unsigne
         for (int r = 0; r < 2; ++r) {
             float2(&Yr)[2] = r == 0 ? Y0 : Y1;
             const uint2 ry = *reinterpret_cast<const uint2*>(rows + 2 * (4 * warp + 2 * k + r));
+            const int okr = XCL ? (int)(ry.y >> 17) : 7;
+            if (EDGE && okr != 7) continue;  // a row outside the picture (warp-uniform): untouched
             const unsigned r0 = ((ry.y & 0xffffu) - jy0) * pitchY, r1 = r0 + ((ry.y >> 16) & 1u) * pitchY;
-            const int okr = GEN ? (int)(ry.y >> 17) : 7;
             const float2 B = splat(__uint_as_float(ry.x)), NB = splat(sub(1.f, __uint_as_float(ry.x)));
 #pragma unroll
             for (int p = 0; p < 2; ++p) {
                 float2 t00, t10, t01, t11;
-                if (GEN) {
+                if (XCL) {
                     const unsigned a0 = o0[2 * p], a1 = o1[2 * p], b0 = o0[2 * p + 1], b1 = o1[2 * p + 1];
                     t00 = unorm2<PK>(bytes2(lds_u8(r0 + a0), lds_u8(r0 + b0)));
                     t10 = unorm2<PK>(bytes2(lds_u8(r0 + a1), lds_u8(r0 + b1)));
@@ -310,17 +322,18 @@ __device__ __forceinline__ void fast_layer(unsigned boxY, unsigned boxU, unsigne
                     t11 = unorm2<PK>(bytes2(lds_u8o<1>(a1), lds_u8o<1>(b1)));
                 }
                 const float2 v = bilin2<PK>(mul2<PK>(NA[p], NB), mul2<PK>(A[p], NB), mul2<PK>(NA[p], B), mul2<PK>(A[p], B), t00, t10, t01, t11, ONE);
-                Yr[p] = settle(Yr[p], v, ft.fy, 0.f, okc[2 * p] & okr, okc[2 * p + 1] & okr);
+                Yr[p] = settle(Yr[p], v, ft.fy, 0.f, okc[2 * p] & okr, okc[2 * p + 1] & okr, M[p]);
             }
         }
         const uint2 rc = *reinterpret_cast<const uint2*>(rows + 2 * SVB_TILE_H + 2 * (2 * warp + k));
+        const int okq = XCL ? (int)(rc.y >> 17) : 7;
+        if (EDGE && okq != 7) return;
         const unsigned q0 = ((rc.y & 0xffffu) - jc0) * pitchC, q1 = q0 + ((rc.y >> 16) & 1u) * pitchC;
-        const int okq = GEN ? (int)(rc.y >> 17) : 7;
         const float2 BC = splat(__uint_as_float(rc.x)), NBC = splat(sub(1.f, __uint_as_float(rc.x)));
         const float2 w00 = mul2<PK>(NAC, NBC), w10 = mul2<PK>(AC, NBC), w01 = mul2<PK>(NAC, BC), w11 = mul2<PK>(AC, BC);
         const unsigned u0 = boxU + q0, u1 = boxU + q1;
         float2 u, v;
-        if (GEN) {
+        if (XCL) {
             const unsigned v0 = boxV + q0, v1 = boxV + q1;
             u = bilin2<PK>(w00, w10, w01, w11, unorm2<PK>(bytes2(lds_u8(u0 + oc00), lds_u8(u0 + oc10))), unorm2<PK>(bytes2(lds_u8(u0 + oc01), lds_u8(u0 + oc11))),
                            unorm2<PK>(bytes2(lds_u8(u1 + oc00), lds_u8(u1 + oc10))), unorm2<PK>(bytes2(lds_u8(u1 + oc01), lds_u8(u1 + oc11))), ONE);
@@ -339,8 +352,8 @@ __device__ __forceinline__ void fast_layer(unsigned boxY, unsigned boxU, unsigne
             v = bilin2<PK>(w00, w10, w01, w11, unorm2<PK>(bytes2(lds_u8o<0>(c00 + dv), lds_u8o<0>(c10 + dv))), unorm2<PK>(bytes2(lds_u8o<1>(c00 + dv), lds_u8o<1>(c10 + dv))),
                            unorm2<PK>(bytes2(lds_u8o<0>(c01 + dv), lds_u8o<0>(c11 + dv))), unorm2<PK>(bytes2(lds_u8o<1>(c01 + dv), lds_u8o<1>(c11 + dv))), ONE);
         }
-        Uk = settle(Uk, u, ft.fu, -1.f, okc0 & okq, okc1 & okq);
-        Vk = settle(Vk, v, ft.fv, -1.f, okc0 & okq, okc1 & okq);
+        Uk = settle(Uk, u, ft.fu, -1.f, okc0 & okq, okc1 & okq, MC);
+        Vk = settle(Vk, v, ft.fv, -1.f, okc0 & okq, okc1 & okq, MC);
     };
 #if SVB_ROLL_ROWS
     // one copy of the body, run twice; the two halves of the register block trade places after each pass (and are back
@@ -363,6 +376,29 @@ __device__ __forceinline__ void fast_layer(unsigned boxY, unsigned boxU, unsigne
     row_pair(0, Yi[0], Yi[1], Ui[0], Vi[0]);
     row_pair(1, Yi[2], Yi[3], Ui[1], Vi[1]);
 #endif
+}
+
+// MODE 2 and 3 out of line (edge tiles: one layer-tile in ten on the headline workload): their registers and instructions stay
+// out of the compositor's body, which then compiles without spills in its hot loops; the running picture crosses in a local
+// array like generic_layer's (48 local accesses against ~900 instructions of the layer).
+struct EdgeArgs {
+    unsigned boxY, boxU, boxV;
+    int iy0, jy0, ic0, jc0, pitchY, pitchC, stepC;
+    float alpha, onef;
+};
+template <int MODE>
+__device__ __noinline__ void edge_staged_layer(const EdgeArgs& a, const uint32_t* __restrict__ tabs, const FillTerms& ft, float* __restrict__ st) {
+    float2 Yi[4][2], Ui[2], Vi[2];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) Yi[r][0] = make_float2(st[4 * r], st[4 * r + 1]), Yi[r][1] = make_float2(st[4 * r + 2], st[4 * r + 3]);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) Ui[k] = make_float2(st[16 + 2 * k], st[17 + 2 * k]), Vi[k] = make_float2(st[20 + 2 * k], st[21 + 2 * k]);
+    fast_layer<MODE, true, false>(a.boxY, a.boxU, a.boxV, tabs, (int)(threadIdx.x & 31), (int)(threadIdx.x >> 5), a.iy0, a.jy0, a.ic0, a.jc0, a.pitchY, a.pitchC, a.stepC, a.alpha, a.onef, ft,
+                               Yi, Ui, Vi);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) st[4 * r] = Yi[r][0].x, st[4 * r + 1] = Yi[r][0].y, st[4 * r + 2] = Yi[r][1].x, st[4 * r + 3] = Yi[r][1].y;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) st[16 + 2 * k] = Ui[k].x, st[17 + 2 * k] = Ui[k].y, st[20 + 2 * k] = Vi[k].x, st[21 + 2 * k] = Vi[k].y;
 }
 
 // Any layer, any tile: the per-pixel evaluator of svb_device.cuh over this thread's 4x4 block.  Kept compact (one
@@ -388,43 +424,13 @@ __device__ __noinline__ void generic_layer(const SvbLayerDesc* __restrict__ L, i
     }
 }
 
-__device__ __forceinline__ unsigned short pack2(float a, float b) {  // two integer-valued floats in 0..255 -> bytes
-    return (unsigned short)(__float2uint_rn(a) | (__float2uint_rn(b) << 8));
+// two integer-valued floats in 0..255 -> two bytes: adding 2^23 leaves the integer in the low mantissa bits (exact), one
+// PRMT gathers the two low bytes (F2I runs on the quarter-rate pipe, and the tile epilogue had 24 of them)
+__device__ __forceinline__ unsigned short pack2(float a, float b) {
+    return (unsigned short)__byte_perm(__float_as_uint(__fadd_rn(a, 8388608.f)), __float_as_uint(__fadd_rn(b, 8388608.f)), 0x0040);
 }
 
 }  // namespace svb
-
-// ---- pre-pass: coordinate tables of every separable YUV layer of every frame of the batch -----------------------
-// grid (ceil(entries / 256), max layers, frames); one entry (two words) per thread, blocks padded to whole tiles.
-extern "C" __global__ void __launch_bounds__(256) svb_mix_tables(const SvbFrameDesc* __restrict__ frames, uint32_t* __restrict__ tables, int* __restrict__ tile_counter) {
-    using namespace svb;
-    if ((blockIdx.x | blockIdx.y | blockIdx.z | threadIdx.x) == 0) *tile_counter = 0;  // svb_mix_tiled claims its tiles from it
-    const SvbFrameDesc* __restrict__ F = frames + blockIdx.z;
-    const int l = blockIdx.y;
-    if (l >= F->nlayers) return;
-    const SvbLayerDesc* __restrict__ L = &F->layers[l];
-    if (!(L->flags & SVB_LAYER_SEPARABLE) || (L->format != SVB_NV12 && L->format != SVB_Y420P)) return;
-    const int W = F->width, H = F->height;
-    const int ncy = F->tiles_x * SVB_TILE_W, ncc = ncy / 2, nry = F->tiles_y * SVB_TILE_H, nrc = nry / 2;
-    int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= ncy + ncc + nry + nrc) return;
-    uint32_t* __restrict__ base = tables + F->table_base + (size_t)l * (size_t)(F->tiles_x * SVB_TAB_COL_WORDS + F->tiles_y * SVB_TAB_ROW_WORDS);
-    uint32_t* __restrict__ rbase = base + F->tiles_x * SVB_TAB_COL_WORDS;
-    if (e < ncy) {
-        const Ent t = axis_entry(axis_chain(&L->u, 0, min(e, W - 1), (float)W), L->width);
-        base[col_y_word(e)] = __float_as_uint(t.a), base[col_y_word(e) + SVB_TILE_W] = pack_ent(t);
-    } else if ((e -= ncy) < ncc) {  // chroma is produced by the even luma column / row (kernels.cl.swift:76)
-        const Ent t = axis_entry(axis_chain(&L->u, 0, min(2 * e, W - 2), (float)W), L->width / 2);
-        base[col_c_word(e)] = __float_as_uint(t.a), base[col_c_word(e) + SVB_TILE_W / 2] = pack_ent(t);
-    } else if ((e -= ncc) < nry) {
-        const Ent t = axis_entry(axis_chain(&L->u, 1, min(e, H - 1), (float)H), L->height);
-        rbase[row_y_word(e)] = __float_as_uint(t.a), rbase[row_y_word(e) + 1] = pack_ent(t);
-    } else {
-        e -= nry;
-        const Ent t = axis_entry(axis_chain(&L->u, 1, min(2 * e, H - 2), (float)H), L->height / 2);
-        rbase[row_c_word(e)] = __float_as_uint(t.a), rbase[row_c_word(e) + 1] = pack_ent(t);
-    }
-}
 
 #ifndef SVB_TILED_MIN_CTAS
 #define SVB_TILED_MIN_CTAS 3  // 80 registers per thread (a few spills) and 24 resident warps beat 128 registers and 16 warps by 5.6 %
@@ -436,38 +442,29 @@ struct TileGeo {
     const SvbFrameDesc* F;
     int frame, x0, y0, lastc, lastr;
 };
-__device__ __forceinline__ TileGeo tile_geo(const SvbFrameDesc* __restrict__ frames, int nframes, int& f, int tile) {
-    while (f + 1 < nframes && frames[f + 1].first_tile <= tile) ++f;
-    TileGeo g;
-    g.F = frames + f;
-    g.frame = f;
-    const int local = tile - g.F->first_tile;
-    g.x0 = (local % g.F->tiles_x) * SVB_TILE_W;
-    g.y0 = (local / g.F->tiles_x) * SVB_TILE_H;
-    g.lastc = min(SVB_TILE_W, g.F->width - g.x0) - 1;
-    g.lastr = min(SVB_TILE_H, g.F->height - g.y0) - 1;
-    return g;
-}
 
-// Plan of layer `l` on one tile (executed by one thread per layer).
-// *cover = l when the layer overwrites every sample of the tile whatever lies below: the tile is wholly inside the picture
-// and opacity == 1, so every pixel takes cur*(1-1) + v*1 == v (kernels.cl.swift:86-92).
-template <bool OCCL>
-__device__ __forceinline__ void plan_layer(const uint32_t* __restrict__ tables, const TileGeo& g, int l, int4* __restrict__ out, uint8_t* __restrict__ cover) {
+// Plan of layer `l` on one tile (one thread per layer).  Returns the mode; *covers = the layer overwrites every sample of
+// the tile whatever lies below: the tile is wholly inside the picture and opacity == 1, so every pixel takes
+// cur*(1-1) + v*1 == v (kernels.cl.swift:86-92).
+// out[0] = (mode | l << 8, iy0, jy0, ic0)   out[1] = (jc0, format << 8 | flags, box_w | box_cw << 16, opacity bits)
+// and, ready for the one thread that issues the copies (every instruction on its path makes its warp late for the next
+// barrier): out[2] = (&tmap Y, &tmap C)   out[3] = (&tmap V or 0, table column block)   out[4] = (table row block, tx bytes, frame)
+__device__ __forceinline__ int plan_layer(const uint32_t* __restrict__ tables, const TileGeo& g, int l, int4* __restrict__ out, bool* __restrict__ covers) {
     const SvbFrameDesc* __restrict__ F = g.F;
     const SvbLayerDesc* __restrict__ L = &F->layers[l];
-    const int x0 = g.x0, y0 = g.y0;
+    const int x0 = g.x0, y0 = g.y0, W = F->width, H = F->height;
     int mode, iy0 = 0, jy0 = 0, ic0 = 0, jc0 = 0;
-    bool covers = false;
+    *covers = false;
     if (L->rect[0] >= x0 + SVB_TILE_W || L->rect[2] <= x0 || L->rect[1] >= y0 + SVB_TILE_H || L->rect[3] <= y0) {
         mode = PLAN_SKIP;
     } else if (!(L->flags & SVB_LAYER_SEPARABLE) || (L->format != SVB_NV12 && L->format != SVB_Y420P)) {
         mode = PLAN_GENERIC;
     } else {
-        const Tabs tb = layer_tabs(tables, F, l);
-        const Ent cA = ld_col_y(tb, x0), cB = ld_col_y(tb, x0 + g.lastc), rA = ld_row_y(tb, y0), rB = ld_row_y(tb, y0 + g.lastr);
-        const Ent ccA = ld_col_c(tb, x0 >> 1), ccB = ld_col_c(tb, (x0 + g.lastc) >> 1);
-        const Ent rcA = ld_row_c(tb, y0 >> 1), rcB = ld_row_c(tb, (y0 + g.lastr) >> 1);
+        // the table entries of the tile's first and last column / row, recomputed (the same functions fill the tables, in this
+        // same launch: nothing to wait for)
+        const Ent cA = ent_col_y(L, W, x0), cB = ent_col_y(L, W, x0 + g.lastc), rA = ent_row_y(L, H, y0), rB = ent_row_y(L, H, y0 + g.lastr);
+        const Ent ccA = ent_col_c(L, W, x0 >> 1), ccB = ent_col_c(L, W, (x0 + g.lastc) >> 1);
+        const Ent rcA = ent_row_c(L, H, y0 >> 1), rcB = ent_row_c(L, H, (y0 + g.lastr) >> 1);
         // source footprint of the tile: the clamped tap indices are monotone along each axis, so the ends bound it;
         // x origins are rounded down to 16 bytes for TMA
         iy0 = min(cA.i0, cB.i0) & ~15;
@@ -482,10 +479,11 @@ __device__ __forceinline__ void plan_layer(const uint32_t* __restrict__ tables, 
         // The interior layer bodies (MODE 0 / 1) address the second tap of a row as "first + 1".
         const bool xfree = cA.i1 != cA.i0 && cB.i1 != cB.i0 && ccA.i1 != ccA.i0 && ccB.i1 != ccB.i0;
         mode = !((L->flags & SVB_LAYER_STAGED) && fits) ? PLAN_GENERIC : (full && xfree ? PLAN_STAGED : PLAN_STAGED_EDGE);
-        covers = full && (L->flags & SVB_LAYER_UNIT_OPACITY);
+        *covers = full && (L->flags & SVB_LAYER_UNIT_OPACITY);
     }
-    out[0] = make_int4(mode, iy0, jy0, ic0);
+    out[0] = make_int4(mode | (l << 8), iy0, jy0, ic0);
     out[1] = make_int4(jc0, (L->format << 8) | (L->flags & 0xff), L->box_w | (L->box_cw << 16), __float_as_int(L->u.opacity));
+    out[2] = out[3] = out[4] = make_int4(0, 0, 0, 0);
     if (mode >= PLAN_STAGED) {
         const bool n12 = L->format == SVB_NV12;
         const int cbytes = n12 ? L->box_cw * L->box_ch * 2 : L->box_cw * L->box_ch;
@@ -496,91 +494,149 @@ __device__ __forceinline__ void plan_layer(const uint32_t* __restrict__ tables, 
         out[3] = make_int4((int)(unsigned)m2, (int)(m2 >> 32), (int)(unsigned)cb, (int)(cb >> 32));
         out[4] = make_int4((int)(unsigned)rb, (int)(rb >> 32), L->box_w * L->box_h + cbytes * (n12 ? 1 : 2) + SVB_TILE_TAB_WORDS * 4, g.frame);
     }
-    if (OCCL) *cover = (uint8_t)(covers ? l : 0);
-}
-// Occlusion: the layers under the topmost covering layer of a tile are skipped -- neither fetched nor computed -- and
-// the bytes are the same.  (Stale bytes of a frame with more layers are masked by `nl`.)
-__device__ __forceinline__ int first_layer(const uint8_t* cover, int nl) {
-    const uint4 w = *reinterpret_cast<const uint4*>(cover);
-    unsigned m = __vmaxu4(__vmaxu4(w.x, w.y), __vmaxu4(w.z, w.w));
-    m = max(max(m & 0xffu, (m >> 8) & 0xffu), max((m >> 16) & 0xffu, m >> 24));
-    return (int)m < nl ? (int)m : 0;
+    return mode;
 }
 
-// Plan of a whole tile: lane l of the planning warp plans layer l (lanes up to SVB_MAX_LAYERS clear their cover byte).
-template <bool OCCL>
-__device__ __forceinline__ void plan_tile(const uint32_t* __restrict__ tables, const TileGeo& g, int lane, int4 (*__restrict__ out)[5], uint8_t* __restrict__ cover) {
-    if (lane < g.F->nlayers) plan_layer<OCCL>(tables, g, lane, out[lane], cover + lane);
-    else if (OCCL && lane < SVB_MAX_LAYERS) cover[lane] = 0;
+// The plan of one tile: one warp, lane l plans layer l of the tile's frame.  The plan that reaches the compositor
+// (SvbTilePlan, svb_desc.h) lists only the layers that touch the tile, bottom to top, starting at the topmost layer that
+// hides everything under it (occlusion: hidden layers are neither fetched nor computed, the bytes are the same), and carries
+// what a tile needs of its frame -- so that the compositor's CTAs fetch a tile's plan with ONE bulk copy and no warp of theirs
+// computes anything for it.  (Planning inside the compositor made its planning warp late for the first barrier of every
+// tile: barrier waits were 27 % of the stall samples, profiles/r1_history.md.)
+__device__ __forceinline__ void plan_tile(const SvbFrameDesc* __restrict__ F, int frame, int local, const uint32_t* __restrict__ tables, SvbTilePlan* __restrict__ plans, int lane) {
+    TileGeo g;
+    g.F = F, g.frame = frame;
+    g.x0 = (local % F->tiles_x) * SVB_TILE_W;
+    g.y0 = (local / F->tiles_x) * SVB_TILE_H;
+    g.lastc = min(SVB_TILE_W, F->width - g.x0) - 1;
+    g.lastr = min(SVB_TILE_H, F->height - g.y0) - 1;
+    int4 e[5];
+    bool covers = false;
+    int mode = PLAN_SKIP;
+    if (lane < F->nlayers) mode = plan_layer(tables, g, lane, e, &covers);
+    unsigned act = __ballot_sync(0xffffffffu, mode != PLAN_SKIP);
+    const unsigned cov = __ballot_sync(0xffffffffu, covers);
+    if (cov) act &= ~((1u << (31 - __clz(cov))) - 1u);  // drop what the topmost covering layer hides
+    int4* __restrict__ out = reinterpret_cast<int4*>(plans + F->first_tile + local);
+    if ((act >> lane) & 1u) {
+        int4* __restrict__ o = out + 5 * (1 + __popc(act & ((1u << lane) - 1u)));
+#pragma unroll
+        for (int q = 0; q < 5; ++q) o[q] = e[q];
+    }
+    if (lane == 0) {
+        const unsigned long long p0 = F->out_plane[0], p1 = F->out_plane[1], p2 = F->out_plane[2];
+        out[0] = make_int4(__popc(act), frame, g.x0, g.y0);
+        out[1] = make_int4(F->width, F->height, F->format, F->flags);
+        out[2] = make_int4((int)(unsigned)p0, (int)(p0 >> 32), (int)(unsigned)p1, (int)(p1 >> 32));
+        out[3] = make_int4((int)(unsigned)p2, (int)(p2 >> 32), F->out_stride[0], F->out_stride[1]);
+        out[4] = make_int4(F->out_stride[2], 0, 0, 0);
+    }
 }
 
 }  // namespace svb
 
-namespace svb {
-// OCCL: the batch holds an opaque picture above another layer, so occlusion can pay; without one the planner's cover
-// bytes and the per-tile first-layer lookup are compiled out (they cost 3 % on the headline workload, which has none).
-template <bool OCCL>
-__device__ __forceinline__ void mix_tiled_body(const SvbFrameDesc* __restrict__ frames, const uint32_t* __restrict__ tables, int nframes, int total_tiles, float one,
-                                               int* __restrict__ tile_counter, int box_y_bytes, int box_c_bytes) {
+// ---- pre-pass: coordinate tables of every separable YUV layer of every frame of the batch, and the plan of every tile ---
+// grid (table_blocks * max layers + plan_blocks, 1, frames), 256 threads; blockIdx.z = frame.
+//   blockIdx.x <  table_blocks * max layers: layer blockIdx.x / table_blocks, one table entry (two words) per thread, blocks
+//                                            padded to whole tiles
+//   beyond:                                  one tile of the frame per warp, see plan_tile
+extern "C" __global__ void __launch_bounds__(256) svb_mix_tables(const SvbFrameDesc* __restrict__ frames, uint32_t* __restrict__ tables, int* __restrict__ tile_counter,
+                                                                SvbTilePlan* __restrict__ plans, int table_blocks, int max_layers) {
+    using namespace svb;
+    if ((blockIdx.x | blockIdx.z | threadIdx.x) == 0) *tile_counter = 0;  // svb_mix_tiled claims its tiles from it
+    const SvbFrameDesc* __restrict__ F = frames + blockIdx.z;
+    if ((int)blockIdx.x >= table_blocks * max_layers) {
+        const int local = ((int)blockIdx.x - table_blocks * max_layers) * 8 + (int)(threadIdx.x >> 5);
+        if (local < F->tiles_x * F->tiles_y) plan_tile(F, (int)blockIdx.z, local, tables, plans, (int)(threadIdx.x & 31));
+        return;
+    }
+    const int l = (int)blockIdx.x / table_blocks;
+    if (l >= F->nlayers) return;
+    const SvbLayerDesc* __restrict__ L = &F->layers[l];
+    if (!(L->flags & SVB_LAYER_SEPARABLE) || (L->format != SVB_NV12 && L->format != SVB_Y420P)) return;
+    const int W = F->width, H = F->height;
+    const int ncy = F->tiles_x * SVB_TILE_W, ncc = ncy / 2, nry = F->tiles_y * SVB_TILE_H, nrc = nry / 2;
+    int e = ((int)blockIdx.x % table_blocks) * (int)blockDim.x + (int)threadIdx.x;
+    if (e >= ncy + ncc + nry + nrc) return;
+    uint32_t* __restrict__ base = tables + F->table_base + (size_t)l * (size_t)(F->tiles_x * SVB_TAB_COL_WORDS + F->tiles_y * SVB_TAB_ROW_WORDS);
+    uint32_t* __restrict__ rbase = base + F->tiles_x * SVB_TAB_COL_WORDS;
+    if (e < ncy) {
+        const Ent t = ent_col_y(L, W, e);
+        base[col_y_word(e)] = __float_as_uint(t.a), base[col_y_word(e) + SVB_TILE_W] = pack_ent(t);
+    } else if ((e -= ncy) < ncc) {
+        const Ent t = ent_col_c(L, W, e);
+        base[col_c_word(e)] = __float_as_uint(t.a), base[col_c_word(e) + SVB_TILE_W / 2] = pack_ent(t);
+    } else if ((e -= ncc) < nry) {
+        const Ent t = ent_row_y(L, H, e);
+        rbase[row_y_word(e)] = __float_as_uint(t.a), rbase[row_y_word(e) + 1] = pack_ent(t);
+    } else {
+        e -= nry;
+        const Ent t = ent_row_c(L, H, e);
+        rbase[row_c_word(e)] = __float_as_uint(t.a), rbase[row_c_word(e) + 1] = pack_ent(t);
+    }
+}
+
+// ---- the compositor --------------------------------------------------------------------------------------------------
+extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CTAS)
+    svb_mix_tiled(const SvbFrameDesc* __restrict__ frames, const SvbTilePlan* __restrict__ plans, int total_tiles, float one, int* __restrict__ tile_counter, int box_y_bytes,
+                  int box_c_bytes) {
     using namespace svb;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TiledSmem& sm = *reinterpret_cast<TiledSmem*>(smem_raw);
     uint8_t* const boxes = smem_raw + SVB_TILED_FIXED_BYTES;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    // SVB_PRODUCER_WARP (off; measured slower, profiles/r1_history.md): a ninth warp that only plans and issues copies.
-    const bool producer = SVB_PRODUCER_WARP && warp == SVB_TILED_COMPUTE_WARPS;
-    const int pt = SVB_PRODUCER_WARP ? t - SVB_TILED_COMPUTE_WARPS * 32 : t;  // index among the planning threads (negative: not one)
     int fenced = -1;  // frame whose tensor maps this CTA's issuing thread has acquired
-    unsigned phase0 = 0, phase1 = 0;
+    unsigned phase0 = 0, phase1 = 0, pphase = 0;
     if (t == 0) {
         mbar_init(&sm.bar[0], 1);
         mbar_init(&sm.bar[1], 1);
+        mbar_init(&sm.pbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    int f = 0, fnext = 0, cur = 0;
+    int cur = 0;
     int stage = 0;        // box buffer that holds (or is about to receive) the next staged layer to consume
     bool primed = false;  // this tile's first staged layer was already put in flight by the previous tile
-    // Tiles are claimed two ahead by one lane (a global atomic whose latency hides behind the planning loads).
+    // Tiles are claimed two ahead by one lane (a global atomic whose latency nobody waits for); the same lane fetches the plan
+    // of the CTA's next tile while the current one is computed.
     const bool claimer = t == SVB_PLAN_WARP * 32;
     int nclaimed = 0;
     auto claim = [&]() -> int {
         if (SVB_DYNAMIC_TILES) return atomicAdd(tile_counter, 1);
         return (int)blockIdx.x + (int)gridDim.x * nclaimed++;
     };
+    auto fetch_plan = [&](int tile_index, int slot) {
+        mbar_expect_tx(&sm.pbar, (unsigned)sizeof(SvbTilePlan));
+        bulk_load(&sm.plan[slot], plans + tile_index, (unsigned)sizeof(SvbTilePlan), &sm.pbar);
+    };
+    __syncthreads();  // the mbarriers are initialised
     if (claimer) {
-        sm.tile_idx[0] = claim();
+        const int t0 = claim();
+        sm.tile_idx[0] = t0;
         sm.tile_idx[1] = claim();
+        if (t0 < total_tiles) fetch_plan(t0, 0);
     }
     __syncthreads();
     int tile = sm.tile_idx[0];
     int k3 = 0;  // ordinal of the tile in this CTA's sequence, modulo 3
     if (tile < total_tiles) {
-        const TileGeo g0 = tile_geo(frames, nframes, fnext, tile);
-        if (warp == SVB_PLAN_WARP) plan_tile<OCCL>(tables, g0, lane, sm.plan[0], sm.cover[0]);
+        mbar_wait(&sm.pbar, pphase);
+        pphase ^= 1;
     }
-    __syncthreads();
 
     while (tile < total_tiles) {
-        const TileGeo g = tile_geo(frames, nframes, f, tile);
-        const SvbFrameDesc* __restrict__ F = g.F;
-        const int W = F->width, H = F->height, nl = F->nlayers;
-        const int x0 = g.x0, y0 = g.y0;
+        const int4(*plan)[5] = reinterpret_cast<const int4(*)[5]>(&sm.plan[cur]) + 1;  // plan[i] = the i-th layer that touches this tile
+        const int4* const hdr = reinterpret_cast<const int4*>(&sm.plan[cur]);
+        const int4 h0 = hdr[0], h1 = hdr[1];
+        const int nact = h0.x, x0 = h0.z, y0 = h0.w, W = h1.x, H = h1.y;
+        const SvbFrameDesc* __restrict__ F = frames + h0.y;
         const int xt = x0 + 2 * lane, yt = y0 + 4 * warp;  // this thread's columns xt, xt+1, xt+64, xt+65 x rows yt..yt+3
-        const bool live = !producer && xt < W && yt < H;    // W and H even are planner preconditions
-        const bool live1 = xt + SVB_TILE_W / 2 < W;          // the second column pair is inside the frame
-        const bool nv12 = F->format == SVB_NV12;
-        const float fW = (float)W, fH = (float)H;
-        uint8_t* const oY = (uint8_t*)F->out_plane[0];
-        uint8_t* const oU = (uint8_t*)F->out_plane[1];
-        uint8_t* const oV = (uint8_t*)F->out_plane[2];
-        const int sY = F->out_stride[0], sU = F->out_stride[1], sV = F->out_stride[2];
-        const int4(*plan)[5] = sm.plan[cur];
-        const int first = OCCL ? first_layer(sm.cover[cur], nl) : 0;  // layers below it are hidden on this tile
+        const bool live = xt < W && yt < H;                // W and H even are planner preconditions
+        const bool live1 = xt + SVB_TILE_W / 2 < W;         // the second column pair is inside the frame
 
         // TMA of one staged layer into buffer `b`: the source boxes and the tile's blocks of the coordinate tables, all
         // addresses and sizes precomputed by the planner
-        auto issue = [&](const int4(*pl)[5], int l, int b) {
-            const int4 q0 = pl[l][0], q1 = pl[l][1], q2 = pl[l][2], q3 = pl[l][3], q4 = pl[l][4];
+        auto issue = [&](const int4(*pl)[5], int i, int b) {
+            const int4 q0 = pl[i][0], q1 = pl[i][1], q2 = pl[i][2], q3 = pl[i][3], q4 = pl[i][4];
             auto ptr = [](int lo, int hi) { return (const void*)(((unsigned long long)(unsigned)hi << 32) | (unsigned)lo); };
             if (q4.w != fenced) {  // the host rewrites the descriptors between launches: acquire a frame's maps once per CTA
                 const SvbFrameDesc* __restrict__ TF = frames + q4.w;
@@ -601,30 +657,24 @@ __device__ __forceinline__ void mix_tiled_body(const SvbFrameDesc* __restrict__ 
             bulk_load(sm.tabs[b], ptr(q3.z, q3.w), SVB_TAB_COL_WORDS * 4, &sm.bar[b]);
             bulk_load(sm.tabs[b] + SVB_TAB_COL_WORDS, ptr(q4.x, q4.y), SVB_TAB_ROW_WORDS * 4, &sm.bar[b]);
         };
-        // first staged layer of `pl`, or -1
+        // first staged layer of `pl` from entry `from` on, or -1
         auto first_staged = [&](const int4(*pl)[5], int from, int n) {
-            for (int l = from; l < n; ++l)
-                if (pl[l][0].x >= PLAN_STAGED) return l;
+            for (int i = from; i < n; ++i)
+                if ((pl[i][0].x & 0xff) >= PLAN_STAGED) return i;
             return -1;
         };
-        if (!primed && pt == 0) {
-            const int l = first_staged(plan, first, nl);
-            if (l >= 0) issue(plan, l, stage);
+        if (!primed && t == 0) {
+            const int i = first_staged(plan, 0, nact);
+            if (i >= 0) issue(plan, i, stage);
         }
         primed = false;
-        // plan of this CTA's next tile, off the critical path (its loads overlap the copy in flight)
+        // this CTA's next tile: its plan is fetched now (one bulk copy), and the tile after it is claimed
         const int k3n = k3 == 2 ? 0 : k3 + 1;  // slot of the next tile's index; the slot after it receives the new claim
         const int next_tile = sm.tile_idx[k3n];
         const bool has_next = next_tile < total_tiles;
-        if (warp == SVB_PLAN_WARP) {
-            int claimed = 0;
-            if (claimer) claimed = claim();
-            if (has_next) {
-                const TileGeo gn = tile_geo(frames, nframes, fnext, next_tile);
-                plan_tile<OCCL>(tables, gn, lane, sm.plan[cur ^ 1], sm.cover[cur ^ 1]);
-                if (lane == 0) sm.nlayers[cur ^ 1] = gn.F->nlayers;
-            }
-            if (claimer) sm.tile_idx[k3n == 2 ? 0 : k3n + 1] = claimed;
+        if (claimer) {
+            if (has_next) fetch_plan(next_tile, cur ^ 1);
+            sm.tile_idx[k3n == 2 ? 0 : k3n + 1] = claim();
         }
 
         // ---- running picture: integer-valued floats ------------------------------------------------------------
@@ -632,7 +682,12 @@ __device__ __forceinline__ void mix_tiled_body(const SvbFrameDesc* __restrict__ 
 #pragma unroll
         for (int r = 0; r < 4; ++r) Yi[r][0] = Yi[r][1] = splat(0.f);  // img_clear_*: Y = 0, chroma = 0.5 -> 128
         Ui[0] = Ui[1] = Vi[0] = Vi[1] = splat(128.f);
-        if ((F->flags & SVB_FRAME_LOAD_CUR) && live) {
+        if ((h1.w & SVB_FRAME_LOAD_CUR) && live) {
+            const int4 h2 = hdr[2], h3 = hdr[3], h4 = hdr[4];
+            const uint8_t* const oY = (const uint8_t*)(((unsigned long long)(unsigned)h2.y << 32) | (unsigned)h2.x);
+            const uint8_t* const oU = (const uint8_t*)(((unsigned long long)(unsigned)h2.w << 32) | (unsigned)h2.z);
+            const uint8_t* const oV = (const uint8_t*)(((unsigned long long)(unsigned)h3.y << 32) | (unsigned)h3.x);
+            const int sY = h3.z, sU = h3.w, sV = h4.x;
 #pragma unroll
             for (int r = 0; r < 4; ++r)
                 if (yt + r < H) {
@@ -643,7 +698,7 @@ __device__ __forceinline__ void mix_tiled_body(const SvbFrameDesc* __restrict__ 
 #pragma unroll
             for (int k = 0; k < 2; ++k)
                 if (yt + 2 * k < H) {
-                    if (nv12) {  // chroma texel xt/2 = the (U, V) byte pair at byte xt of the row; texel xt/2 + 32 is 64 bytes on
+                    if (h1.z == SVB_NV12) {  // chroma texel xt/2 = the (U, V) byte pair at byte xt of the row; texel xt/2 + 32 is 64 bytes on
                         const uint8_t* row = oU + (size_t)((yt >> 1) + k) * sU + xt;
                         const unsigned w0 = *(const unsigned short*)row, w1 = live1 ? *(const unsigned short*)(row + SVB_TILE_W / 2) : 0x8080u;
                         Ui[k] = bytes2(opaque(w0 & 0xff), opaque(w1 & 0xff)), Vi[k] = bytes2(opaque(w0 >> 8), opaque(w1 >> 8));
@@ -655,34 +710,37 @@ __device__ __forceinline__ void mix_tiled_body(const SvbFrameDesc* __restrict__ 
                 }
         }
 
-        for (int l = first; l < nl; ++l) {
-            const int4 p0 = plan[l][0];
-            const int mode = p0.x;
-            if (mode == PLAN_SKIP) continue;
-            const SvbLayerDesc* __restrict__ L = &F->layers[l];
+        for (int i = 0; i < nact; ++i) {
+            const int4 p0 = plan[i][0];
+            const int mode = p0.x & 0xff;
             if (mode >= PLAN_STAGED) {
-                const int4 p1 = plan[l][1];
+                const int4 p1 = plan[i][1];
                 const int jc0 = p1.x;
-                __syncthreads();  // every warp is past its reads of the other buffer (and the next tile's plan is written)
-                if (pt == 0) {  // refill the other buffer: the next staged layer of this tile, else the first one of the next tile
-                    const int j = first_staged(plan, l + 1, nl);
+#if SVB_SPLIT_BARRIER
+                // only the warp that refills the other buffer has to know that every warp is past its reads of it: it waits on a named
+                // barrier (two, alternating with the buffers, so that a warp one layer ahead never arrives twice in one phase), the
+                // other warps arrive and go on to their data
+                if (warp == 0) asm volatile("barrier.sync %0, %1;" ::"r"(1 + stage), "n"(SVB_TILED_THREADS) : "memory");
+                else asm volatile("barrier.arrive %0, %1;" ::"r"(1 + stage), "n"(SVB_TILED_THREADS) : "memory");
+#else
+                __syncthreads();  // every warp is past its reads of the other buffer
+#endif
+                if (t == 0) {  // refill the other buffer: the next staged layer of this tile, else the first one of the next tile
+                    const int j = first_staged(plan, i + 1, nact);
                     if (j >= 0) {
                         issue(plan, j, stage ^ 1);
                     } else if (has_next) {
-                        const int nln = sm.nlayers[cur ^ 1];
-                        const int jn = first_staged(sm.plan[cur ^ 1], OCCL ? first_layer(sm.cover[cur ^ 1], nln) : 0, nln);
+                        mbar_wait(&sm.pbar, pphase);  // the next tile's plan has landed (it was requested a whole tile ago)
+                        const int4(*pn)[5] = reinterpret_cast<const int4(*)[5]>(&sm.plan[cur ^ 1]) + 1;
+                        const int jn = first_staged(pn, 0, sm.plan[cur ^ 1].e[0][0][0]);
                         if (jn >= 0) {
-                            issue(sm.plan[cur ^ 1], jn, stage ^ 1);
+                            issue(pn, jn, stage ^ 1);
                             primed = true;  // only this thread looks at it
                         }
                     }
                 }
-                if (!producer) {
-                    if (stage == 0) mbar_wait(&sm.bar[0], phase0);
-                    else mbar_wait(&sm.bar[1], phase1);
-                }
-                if (stage == 0) phase0 ^= 1;
-                else phase1 ^= 1;
+                if (stage == 0) mbar_wait(&sm.bar[0], phase0), phase0 ^= 1;
+                else mbar_wait(&sm.bar[1], phase1), phase1 ^= 1;
                 if (live) {
                     const int fmt = p1.y >> 8, lflags = p1.y & 0xff, box_w = p1.z & 0xffff, box_cw = p1.z >> 16;
                     const int pitchC = fmt == SVB_NV12 ? box_cw * 2 : box_cw, stepC = fmt == SVB_NV12 ? 2 : 1;
@@ -691,11 +749,39 @@ __device__ __forceinline__ void mix_tiled_body(const SvbFrameDesc* __restrict__ 
                     const float alpha = __int_as_float(p1.w);
                     FillTerms ft;
                     if (mode == PLAN_STAGED_EDGE || !(lflags & SVB_LAYER_OPACITY_01)) {
+                        const SvbLayerDesc* __restrict__ L = &F->layers[p0.x >> 8];
                         const float4 fc = ldrow(L->u.fillColor, 0);
                         const float3 fill = rgb2yuv(fc.x, fc.y, fc.z);
                         const float af = mul(alpha, fc.w);
                         ft.fy = splat(fill.x), ft.fu = splat(fill.y), ft.fv = splat(fill.z), ft.af = splat(af), ft.naf = splat(sub(1.f, af));
-                        fast_layer<2, true, false>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
+                        // Does this warp's block hold a sample inside the border rectangle but outside the picture (fill), or a row that is
+                        // so along its whole length?  Without a border or letterbox no tile does, and the lean edge body applies.
+                        const uint32_t* __restrict__ tb = sm.tabs[stage];
+                        auto odd = [](uint32_t p) { const unsigned ok = p >> 17; return (ok & 1u) != 0u && ok != 7u; };
+                        bool mixed = odd(tb[SVB_TILE_W + 2 * lane]) || odd(tb[SVB_TILE_W + 2 * lane + 1]) || odd(tb[SVB_TILE_W + 64 + 2 * lane]) ||
+                                     odd(tb[SVB_TILE_W + 65 + 2 * lane]) || odd(tb[2 * SVB_TILE_W + SVB_TILE_W / 2 + lane]) || odd(tb[2 * SVB_TILE_W + SVB_TILE_W / 2 + 32 + lane]);
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) mixed = mixed || odd(tb[SVB_TAB_COL_WORDS + 2 * (4 * warp + r) + 1]);
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) mixed = mixed || odd(tb[SVB_TAB_COL_WORDS + 2 * SVB_TILE_H + 2 * (2 * warp + k) + 1]);
+                        const bool lean = SVB_LEAN_EDGE && (lflags & SVB_LAYER_OPACITY_01) && !__any_sync(__activemask(), mixed);
+#if SVB_EDGE_INLINE
+                        if (lean) fast_layer<2, true, false>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
+                        else fast_layer<3, true, false>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
+#else
+                        float st[24];
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) st[4 * r] = Yi[r][0].x, st[4 * r + 1] = Yi[r][0].y, st[4 * r + 2] = Yi[r][1].x, st[4 * r + 3] = Yi[r][1].y;
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) st[16 + 2 * k] = Ui[k].x, st[17 + 2 * k] = Ui[k].y, st[20 + 2 * k] = Vi[k].x, st[21 + 2 * k] = Vi[k].y;
+                        const EdgeArgs ea = {bY, bU, bV, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one};
+                        if (lean) edge_staged_layer<2>(ea, sm.tabs[stage], ft, st);
+                        else edge_staged_layer<3>(ea, sm.tabs[stage], ft, st);
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) Yi[r][0] = make_float2(st[4 * r], st[4 * r + 1]), Yi[r][1] = make_float2(st[4 * r + 2], st[4 * r + 3]);
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) Ui[k] = make_float2(st[16 + 2 * k], st[17 + 2 * k]), Vi[k] = make_float2(st[20 + 2 * k], st[21 + 2 * k]);
+#endif
                     } else if (lflags & SVB_LAYER_UNIT_OPACITY) {
                         if (fmt == SVB_NV12) fast_layer<0, true, true>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
                         else fast_layer<0, true, false>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
@@ -705,15 +791,13 @@ __device__ __forceinline__ void mix_tiled_body(const SvbFrameDesc* __restrict__ 
                     }
                 }
                 stage ^= 1;
-            } else if (!live) {
-                continue;
-            } else {
+            } else if (live) {  // PLAN_GENERIC
                 float st[24];
 #pragma unroll
                 for (int r = 0; r < 4; ++r) st[4 * r] = Yi[r][0].x, st[4 * r + 1] = Yi[r][0].y, st[4 * r + 2] = Yi[r][1].x, st[4 * r + 3] = Yi[r][1].y;
 #pragma unroll
                 for (int k = 0; k < 2; ++k) st[16 + 2 * k] = Ui[k].x, st[17 + 2 * k] = Ui[k].y, st[20 + 2 * k] = Vi[k].x, st[21 + 2 * k] = Vi[k].y;
-                generic_layer(L, xt, yt, fW, fH, W, H, st);
+                generic_layer(&F->layers[p0.x >> 8], xt, yt, (float)W, (float)H, W, H, st);
 #pragma unroll
                 for (int r = 0; r < 4; ++r) Yi[r][0] = make_float2(st[4 * r], st[4 * r + 1]), Yi[r][1] = make_float2(st[4 * r + 2], st[4 * r + 3]);
 #pragma unroll
@@ -722,6 +806,11 @@ __device__ __forceinline__ void mix_tiled_body(const SvbFrameDesc* __restrict__ 
         }
 
         if (live) {
+            const int4 h2 = hdr[2], h3 = hdr[3], h4 = hdr[4];
+            uint8_t* const oY = (uint8_t*)(((unsigned long long)(unsigned)h2.y << 32) | (unsigned)h2.x);
+            uint8_t* const oU = (uint8_t*)(((unsigned long long)(unsigned)h2.w << 32) | (unsigned)h2.z);
+            uint8_t* const oV = (uint8_t*)(((unsigned long long)(unsigned)h3.y << 32) | (unsigned)h3.x);
+            const int sY = h3.z, sU = h3.w, sV = h4.x;
 #pragma unroll
             for (int r = 0; r < 4; ++r)
                 if (yt + r < H) {
@@ -732,7 +821,7 @@ __device__ __forceinline__ void mix_tiled_body(const SvbFrameDesc* __restrict__ 
 #pragma unroll
             for (int k = 0; k < 2; ++k)
                 if (yt + 2 * k < H) {
-                    if (nv12) {
+                    if (h1.z == SVB_NV12) {
                         uint8_t* row = oU + (size_t)((yt >> 1) + k) * sU + xt;
                         *(unsigned short*)row = pack2(Ui[k].x, Vi[k].x);
                         if (live1) *(unsigned short*)(row + SVB_TILE_W / 2) = pack2(Ui[k].y, Vi[k].y);
@@ -744,19 +833,11 @@ __device__ __forceinline__ void mix_tiled_body(const SvbFrameDesc* __restrict__ 
                     }
                 }
         }
-        __syncthreads();  // the next tile's plan is visible; the boxes are free
-        tile = sm.tile_idx[k3n], k3 = k3n, cur ^= 1;
+        if (has_next) {  // every thread sees the next plan's arrival for itself before anyone re-arms the barrier
+            mbar_wait(&sm.pbar, pphase);
+            pphase ^= 1;
+        }
+        __syncthreads();  // the boxes and this tile's plan slot are free
+        tile = next_tile, k3 = k3n, cur ^= 1;
     }
-}
-}  // namespace svb
-
-extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CTAS)
-    svb_mix_tiled(const SvbFrameDesc* __restrict__ frames, const uint32_t* __restrict__ tables, int nframes, int total_tiles, float one, int* __restrict__ tile_counter,
-                  int box_y_bytes, int box_c_bytes) {
-    svb::mix_tiled_body<false>(frames, tables, nframes, total_tiles, one, tile_counter, box_y_bytes, box_c_bytes);
-}
-extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CTAS)
-    svb_mix_tiled_occl(const SvbFrameDesc* __restrict__ frames, const uint32_t* __restrict__ tables, int nframes, int total_tiles, float one,
-                       int* __restrict__ tile_counter, int box_y_bytes, int box_c_bytes) {
-    svb::mix_tiled_body<true>(frames, tables, nframes, total_tiles, one, tile_counter, box_y_bytes, box_c_bytes);
 }

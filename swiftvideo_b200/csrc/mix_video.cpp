@@ -29,9 +29,16 @@ struct MixerShared {
     CUdeviceptr dev = 0;
     CUevent ev[kSegments] = {};
     bool used[kSegments] = {};
+    // The descriptor copy and the pre-pass of a batch run on their own stream: nothing in them depends on the compositor launch
+    // queued before them, so they slide under its tail instead of standing between two compositor launches.  Each segment
+    // owns its table / plan buffer (free again once ev[seg] has fired, which the host waits for before reusing the segment).
+    CUstream prep = nullptr;
+    CUevent evPrep[kSegments] = {};
+    CUdeviceptr tabBuf[kSegments] = {};
+    size_t tabBytes[kSegments] = {};
     int next = 0;
     std::map<std::array<uint64_t, 4>, std::array<uint8_t, 128>> tmaps;
-    CUfunction fTiled = nullptr, fTiledOccl = nullptr, fGeneric = nullptr, fTables = nullptr;
+    CUfunction fTiled = nullptr, fGeneric = nullptr, fTables = nullptr;
     std::map<size_t, int> tiledCtasPerSm;  // resident CTAs of svb_mix_tiled per SM by dynamic shared memory size: the persistent grid is smCount times this
     std::mutex mu;
     // optional per-launch device timing of the fused kernels (bench.py's roofline leg)
@@ -60,6 +67,11 @@ void freeShared(InternalContext* ic) {
     if (s->dev) cu().cuMemFree(s->dev);
     for (CUevent e : s->ev)
         if (e) cu().cuEventDestroy(e);
+    for (CUevent e : s->evPrep)
+        if (e) cu().cuEventDestroy(e);
+    for (CUdeviceptr b : s->tabBuf)
+        if (b) cu().cuMemFree(b);
+    if (s->prep) cu().cuStreamDestroy(s->prep);
     for (auto* v : {&s->timed, &s->spare})
         for (auto& pr : *v) {
             cu().cuEventDestroy(pr.first);
@@ -79,11 +91,10 @@ MixerShared& shared(const std::shared_ptr<InternalContext>& ic) {  // caller hol
         check(drv().cuMemHostAlloc((void**)&s->host, bytes, 0), "cuMemHostAlloc");
         check(drv().cuMemAlloc(&s->dev, bytes), "cuMemAlloc");
         for (CUevent& e : s->ev) check(drv().cuEventCreate(&e, CU_EVENT_DISABLE_TIMING), "cuEventCreate");
+        for (CUevent& e : s->evPrep) check(drv().cuEventCreate(&e, CU_EVENT_DISABLE_TIMING), "cuEventCreate");
+        check(drv().cuStreamCreate(&s->prep, CU_STREAM_NON_BLOCKING), "cuStreamCreate");
         s->fTiled = ic->builtin("svb_mix_tiled");
         check(drv().cuFuncSetAttribute(s->fTiled, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, SVB_TILED_SMEM_MAX),
-              "cuFuncSetAttribute(max dynamic shared memory)");
-        s->fTiledOccl = ic->builtin("svb_mix_tiled_occl");  // same kernel with tile-level occlusion compiled in
-        check(drv().cuFuncSetAttribute(s->fTiledOccl, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, SVB_TILED_SMEM_MAX),
               "cuFuncSetAttribute(max dynamic shared memory)");
         s->fTables = ic->builtin("svb_mix_tables");
         s->fGeneric = ic->builtin("svb_mix_generic");
@@ -271,9 +282,8 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
         }
         if (sh.used[seg]) check(d.cuEventSynchronize(sh.ev[seg]), "cuEventSynchronize");
         SvbFrameDesc* host = (SvbFrameDesc*)(sh.host + (size_t)seg * kSegFrames * sizeof(SvbFrameDesc));
-        int total = 0, maxW = 0, maxH = 0, maxLayers = 1, maxEnts = 1;
+        int total = 0, maxW = 0, maxH = 0, maxLayers = 1, maxEnts = 1, maxTiles = 1;
         size_t tableEnts = 0;
-        bool occluders = false;  // an opaque picture above another layer: tiles it covers can drop what lies below
         int boxY = 0, boxC = 0;   // largest staged footprint of the batch (bytes per box; chroma = both planes of a Y420P source)
         for (int i = 0; i < n; ++i) {
             SvbFrameDesc& fr = frames[start + i];
@@ -283,11 +293,9 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
                 boxY = std::max(boxY, roundUp(L.box_w * L.box_h, 256));
                 boxC = std::max(boxC, L.format == SVB_NV12 ? roundUp(L.box_cw * L.box_ch * 2, 256) : 2 * roundUp(L.box_cw * L.box_ch, 128));
             }
-            for (int l = 1; l < fr.nlayers; ++l)
-                occluders = occluders || ((fr.layers[l].flags & SVB_LAYER_UNIT_OPACITY) && (fr.layers[l].flags & SVB_LAYER_SEPARABLE) &&
-                                          (fr.layers[l].format == SVB_NV12 || fr.layers[l].format == SVB_Y420P));
             fr.first_tile = total;
             total += fr.tiles_x * fr.tiles_y;
+            maxTiles = std::max(maxTiles, fr.tiles_x * fr.tiles_y);
             maxW = std::max(maxW, fr.width), maxH = std::max(maxH, fr.height);
             const int ents = SVB_TABLE_WORDS(fr.width, fr.height);  // 4-byte words per layer
             fr.table_base = (int32_t)tableEnts;
@@ -298,7 +306,7 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
             std::memcpy(&host[i], &fr, used);
         }
         CUdeviceptr dev = sh.dev + (size_t)seg * kSegFrames * sizeof(SvbFrameDesc);
-        check(d.cuMemcpyHtoDAsync(dev, host, (size_t)n * sizeof(SvbFrameDesc), ic.compute), "cuMemcpyHtoDAsync");
+        check(d.cuMemcpyHtoDAsync(dev, host, (size_t)n * sizeof(SvbFrameDesc), sh.prep), "cuMemcpyHtoDAsync");
         std::pair<CUevent, CUevent> tev{nullptr, nullptr};
         if (sh.timing) {
             if (sh.timed.size() >= 256) harvest(sh);
@@ -310,22 +318,30 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
                 check(d.cuEventCreate(&tev.second, CU_EVENT_DEFAULT), "cuEventCreate");
             }
         }
-        if (!tiled && tev.first) check(d.cuEventRecord(tev.first, ic.compute), "cuEventRecord");
         if (tiled) {
-            // pre-pass: per-column / per-row coordinate tables of the batch (two words per entry), then the compositor
-            // (+ the tile counter svb_mix_tiled claims its work from, zeroed by the pre-pass)
+            // pre-pass (one launch): per-column / per-row coordinate tables of the batch (two words per entry) and the plan of every
+            // tile; then the compositor (+ the tile counter it claims its work from, zeroed by the pre-pass)
             const size_t counterOff = (std::max<size_t>(tableEnts, 4) * 4 + 15) & ~(size_t)15;
-            const size_t tableBytes = counterOff + 16;
-            CUdeviceptr tables = ic.alloc(tableBytes);
-            CUdeviceptr counter = tables + counterOff;
-            void* targs[] = {&dev, &tables, &counter};
-            check(d.cuLaunchKernel(sh.fTables, (unsigned)((maxEnts / 2 + 255) / 256), (unsigned)maxLayers, (unsigned)n, 256, 1, 1, 0, ic.compute, targs, nullptr),
+            const size_t plansOff = counterOff + 16;
+            const size_t tableBytes = plansOff + (size_t)total * sizeof(SvbTilePlan);
+            if (sh.tabBytes[seg] < tableBytes) {  // the segment is idle here (ev[seg] waited for above)
+                if (sh.tabBuf[seg]) check(d.cuMemFree(sh.tabBuf[seg]), "cuMemFree");
+                sh.tabBuf[seg] = 0, sh.tabBytes[seg] = 0;
+                check(d.cuMemAlloc(&sh.tabBuf[seg], tableBytes + tableBytes / 4), "cuMemAlloc");
+                sh.tabBytes[seg] = tableBytes + tableBytes / 4;
+            }
+            CUdeviceptr tables = sh.tabBuf[seg];
+            CUdeviceptr counter = tables + counterOff, plans = tables + plansOff;
+            int tableBlocks = (maxEnts / 2 + 255) / 256;
+            void* targs[] = {&dev, &tables, &counter, &plans, &tableBlocks, &maxLayers};
+            check(d.cuLaunchKernel(sh.fTables, (unsigned)(tableBlocks * maxLayers + (maxTiles + 7) / 8), 1, (unsigned)n, 256, 1, 1, 0, sh.prep, targs, nullptr),
                   "cuLaunchKernel(svb_mix_tables)");
             noteKernelLaunch();
+            check(d.cuEventRecord(sh.evPrep[seg], sh.prep), "cuEventRecord");
+            check(d.cuStreamWaitEvent(ic.compute, sh.evPrep[seg], 0), "cuStreamWaitEvent");
             if (tev.first) check(d.cuEventRecord(tev.first, ic.compute), "cuEventRecord");  // time svb_mix_tiled alone
-            int nframes = n;
             float one = 1.0f;  // see add2() in kernels_tiled.cuh
-            void* args[] = {&dev, &tables, &nframes, &total, &one, &counter, &boxY, &boxC};
+            void* args[] = {&dev, &plans, &total, &one, &counter, &boxY, &boxC};
             // shared memory: the fixed part plus two box pairs sized for the largest staged footprint of this batch
             size_t smem = SVB_TILED_SMEM_BYTES((size_t)boxY, (size_t)boxC);
             int perSm;
@@ -340,11 +356,13 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
                 perSm = it->second;
             }
             const unsigned grid = (unsigned)std::min(total, ic.smCount * perSm);
-            check(d.cuLaunchKernel(occluders ? sh.fTiledOccl : sh.fTiled, grid, 1, 1, SVB_TILED_THREADS, 1, 1, (unsigned)smem, ic.compute, args, nullptr),
+            check(d.cuLaunchKernel(sh.fTiled, grid, 1, 1, SVB_TILED_THREADS, 1, 1, (unsigned)smem, ic.compute, args, nullptr),
                   "cuLaunchKernel(svb_mix_tiled)");
             noteKernelLaunch();
-            ic.release(tables, tableBytes);  // recycled only after the streams have drained past this point
         } else {
+            check(d.cuEventRecord(sh.evPrep[seg], sh.prep), "cuEventRecord");  // the descriptor copy
+            check(d.cuStreamWaitEvent(ic.compute, sh.evPrep[seg], 0), "cuStreamWaitEvent");
+            if (tev.first) check(d.cuEventRecord(tev.first, ic.compute), "cuEventRecord");
             void* args[] = {&dev};
             check(d.cuLaunchKernel(sh.fGeneric, (unsigned)((maxW / 2 + 31) / 32), (unsigned)((maxH / 2 + 7) / 8), (unsigned)n, 32, 8, 1, 0,
                                    ic.compute, args, nullptr),

@@ -92,11 +92,19 @@ typedef struct __attribute__((aligned(64))) SvbFrameDesc {
 #define SVB_TILES_Y(H) (((H) + SVB_TILE_H - 1) / SVB_TILE_H)
 #define SVB_TABLE_WORDS(W, H) (SVB_TILES_X(W) * SVB_TAB_COL_WORDS + SVB_TILES_Y(H) * SVB_TAB_ROW_WORDS)
 
-// dynamic shared memory of svb_mix_tiled: a fixed part (two table slices, mbarriers, two tile plans, the tile ring) and
+// Plan of one tile, written by svb_mix_plan and fetched by the compositor's CTAs with one bulk copy.  Five 16-byte words
+// per entry; entry 0 is the header, entries 1..n the layers that touch the tile, bottom to top (kernels_tiled.cuh):
+//   header  [0] = (n, frame, x0, y0)  [1] = (width, height, format, frame flags)  [2] = (&Y, &U)  [3] = (&V, strideY, strideU)
+//           [4] = (strideV, 0, 0, 0)
+typedef struct __attribute__((aligned(16))) SvbTilePlan {
+    int32_t e[1 + SVB_MAX_LAYERS][5][4];
+} SvbTilePlan;
+
+// dynamic shared memory of svb_mix_tiled: a fixed part (two table slices, two tile plans, mbarriers, the tile ring) and
 // behind it two luma boxes and two chroma boxes whose size the host picks PER LAUNCH from the largest staged footprint
 // of the batch (box_y_bytes / box_c_bytes kernel arguments, multiples of 256, at most SVB_BOX_*_BYTES): shared memory
 // not taken stays L1, and the headline workload needs 11 KB per stage, not the 32 KB worst case.
-#define SVB_TILED_FIXED_BYTES (2 * (SVB_TAB_COL_WORDS + SVB_TAB_ROW_WORDS) * 4 + 256 + 2 * SVB_MAX_LAYERS * 80)
+#define SVB_TILED_FIXED_BYTES ((2 * (SVB_TAB_COL_WORDS + SVB_TAB_ROW_WORDS) * 4 + 2 * (1 + SVB_MAX_LAYERS) * 80 + 64 + 127) / 128 * 128)
 #define SVB_TILED_SMEM_BYTES(boxY, boxC) (SVB_TILED_FIXED_BYTES + 2 * (boxY) + 2 * (boxC))
 #define SVB_TILED_SMEM_MAX SVB_TILED_SMEM_BYTES(SVB_BOX_Y_BYTES, SVB_BOX_C_BYTES)
 
@@ -104,4 +112,5 @@ typedef struct __attribute__((aligned(64))) SvbFrameDesc {
 static_assert(sizeof(SvbUniforms) == 240, "SvbUniforms layout");
 static_assert(sizeof(SvbLayerDesc) % 64 == 0, "SvbLayerDesc alignment");
 static_assert(sizeof(SvbFrameDesc) % 64 == 0, "SvbFrameDesc alignment");
+static_assert(sizeof(SvbTilePlan) == (1 + SVB_MAX_LAYERS) * 80, "SvbTilePlan layout");
 #endif
