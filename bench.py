@@ -320,6 +320,121 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+
+# ---- side workloads: the convert+scale operator (BASELINE cfg 5 and cfg 2's convert leg) -- NOT the headline --------------
+
+SCALE_WORKLOADS = {
+    # name: (source format, filter, source size, destination size, swscale names)
+    "cfg5": ("p010", "lanczos3", (3840, 2160), (1920, 1080)),
+    "cfg2": ("nv12", "bilinear", (1920, 1080), (1280, 720)),
+}
+
+
+def run_scale(args):
+    """One step = 8 frames of `svb_scale_convert` (one launch each) over 8 distinct device-resident sources; value, e2e,
+    roofline and cpu_baseline (libswscale on the host cores, accurate mode off = its default speed path) as for the headline."""
+    import torch
+
+    import swiftvideo_b200 as sv
+    import swscale_util as SW
+    from oracle import oracle as O
+    fmt_name, filt_name, (sw, sh), (dw, dh) = SCALE_WORKLOADS[args.workload]
+    fmt = sv.P010 if fmt_name == "p010" else sv.NV12
+    filt = sv.FILTER_LANCZOS3 if filt_name == "lanczos3" else sv.FILTER_BILINEAR
+    bps = 2 if fmt_name == "p010" else 1
+    src_bytes, dst_bytes = sw * sh * 3 // 2 * bps, dw * dh * 4
+    torch.cuda.set_device(0)
+    ctx = sv.make_compute_context(0)
+    N = 8
+    rng = np.random.default_rng(5000)
+    hosts, devs = [], []
+    for i in range(N):
+        h = sv.create_picture_sample(sw, sh, fmt, f"src{i}", "bench", pinned_from=ctx)
+        data = rng.integers(0, 256, size=src_bytes, dtype=np.uint8) if bps == 1 else (rng.integers(0, 1024, size=src_bytes // 2, dtype=np.uint16) << 6).view(np.uint8)
+        h.set_host_bytes(data)
+        hosts.append(h)
+        devs.append(h.upload(ctx))
+    ctx.synchronize()
+
+    def step_resident(i):
+        return [devs[k].scale_convert(ctx, dw, dh, sv.BGRA, filt, wait=False) for k in range(N)]
+
+    def step_e2e(i):
+        outs = [hosts[k].upload(ctx, retain_cpu_buffer=False).scale_convert(ctx, dw, dh, sv.BGRA, filt, wait=False) for k in range(N)]
+        return [o.download(ctx, retain_gpu_buffer=True, wait=False) for o in outs]
+
+    def timed(fn, steps, warmup):
+        last = None
+        for i in range(warmup):  # same shape as the timed loop (the previous step's outputs die while this step is queued), so that
+            last = fn(i)         # the device and pinned-host pools hold every block the loop needs before the clock starts
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        timer = sv.Timer(ctx)
+        l0 = sv.kernel_launch_count()
+        timer.start()
+        for i in range(steps):
+            last = fn(warmup + i)
+        timer.stop()
+        ms = timer.elapsed_ms()
+        for o in last:
+            o.wait()
+        ctx.synchronize()
+        timer.close()
+        return ms, sv.kernel_launch_count() - l0
+
+    sampler = ClockSampler(0)
+    sampler.start()
+    ms, launches = timed(step_resident, args.steps, args.warmup)
+    e2e_steps = max(3, min(args.steps, args.e2e_steps))
+    e_ms, _ = timed(step_e2e, e2e_steps, 3)
+    clocks = sampler.stop()
+    value = N * args.steps / (ms / 1e3)
+    per_launch_ms = ms / (N * args.steps)
+    peak, peak_src = peaks()
+    alg = src_bytes + dst_bytes
+    achieved = alg / (per_launch_ms / 1e3) / 1e9
+    line = {
+        "metric": f"{sw}x{sh} {fmt_name} -> {dw}x{dh} bgra {filt_name} frames/sec (side workload, not the headline)", "value": round(value, 2), "unit": "frames/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8/u16 in, fp32 fused multiply-add arithmetic, u8 out", "data": "synthetic (uniform random codes, seeded)",
+        "config": {"workload": f"{args.workload}: {sw}x{sh} {fmt_name} -> {dw}x{dh} BGRA, {filt_name}, {N} frames per step over {N} distinct sources",
+                   "l2": f"{N * (src_bytes + dst_bytes) / 1e6:.0f} MB of distinct sources+targets per step (> 126 MB L2)" if N * (src_bytes + dst_bytes) > 126e6 else
+                         f"{N * (src_bytes + dst_bytes) / 1e6:.0f} MB per step: FITS in the 126 MB L2 (the sources are re-read from L2, not HBM)",
+                   "bit_exact_vs_oracle": "tests/test_scale.py::test_gpu_scale_full_size"},
+        "e2e": {"value": round(N * e2e_steps / (e_ms / 1e3), 2), "unit": "frames/s", "h2d_bytes_per_step": N * src_bytes, "d2h_bytes_per_step": N * dst_bytes,
+                "steps": e2e_steps, "ms_per_step": round(e_ms / e2e_steps, 4)},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                     "kernel": "svb_scale_convert", "kernel_ms_per_launch": round(per_launch_ms, 4), "algorithmic_bytes_per_launch": alg,
+                     "note": "launch time = step time / launches (back to back on one stream, gaps included)"},
+    }
+    if not args.no_cpu_baseline and SW.available():
+        # libswscale, the comparator BASELINE.json names, one SwsContext per host thread, default (fast) mode
+        from concurrent.futures import ThreadPoolExecutor
+        threads = min(O.host_threads(), 64)
+        pic = hosts[0].host_bytes().copy()
+        flag = SW.SWS_LANCZOS if filt_name == "lanczos3" else SW.SWS_BILINEAR
+
+        def worker(_):
+            sc = SW.Scaler("p010le" if bps == 2 else "nv12", sw, sh, dw, dh, flag)
+            n, t0 = 0, time.perf_counter()
+            while time.perf_counter() - t0 < min(args.cpu_seconds, 6.0):
+                sc.run(pic)
+                n += 1
+            dt = time.perf_counter() - t0
+            sc.close()
+            return n / dt
+
+        with ThreadPoolExecutor(threads) as ex:
+            fps = sum(ex.map(worker, range(threads)))
+        t0 = time.perf_counter()
+        O.scale_convert(O.SC_P010 if bps == 2 else O.SC_NV12, O.SC_LANCZOS3 if filt_name == "lanczos3" else O.SC_BILINEAR, pic, sw, sh, dw, dh)
+        line["cpu_baseline"] = {"value": round(fps, 2), "unit": "frames/s", "cores": threads, "kind": "libswscale 9.1 (external comparator; the reference has no such operator)",
+                                "sample": f"{min(args.cpu_seconds, 6.0):.0f} s of whole frames per thread, one SwsContext per thread",
+                                "definition_single_thread_frames_per_s": round(1.0 / (time.perf_counter() - t0), 3)}
+    print(json.dumps(line), flush=True)
+
+
 # ---- the reference's kernels on the host cores ---------------------------------------------------------------
 
 def cpu_scene():
@@ -430,9 +545,13 @@ def main():
     ap.add_argument("--pip-opacity", type=float, default=None,
                     help="side experiment, not the headline: opacity of layers 1..7 (1.0 = opaque pictures, which let the planner skip "
                          "whatever they cover)")
+    ap.add_argument("--workload", default="cfg4", choices=["cfg4", "cfg5", "cfg2"],
+                    help="cfg4 (default) = the headline; cfg5 / cfg2 = the convert+scale operator's side workloads (1 GPU, our arm only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    if args.impl == "reference":
+    if args.workload != "cfg4" and args.impl == "ours":
+        run_scale(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -52,7 +52,10 @@ typedef enum svb_status {
 /* PixelFormat (sample.pict.swift:20-33), in declaration order */
 typedef enum svb_pixel_format {
     SVB_PIXEL_NV12 = 0, SVB_PIXEL_NV21, SVB_PIXEL_YUVS, SVB_PIXEL_ZVUY, SVB_PIXEL_Y420P, SVB_PIXEL_Y422P, SVB_PIXEL_Y444P,
-    SVB_PIXEL_RGBA, SVB_PIXEL_BGRA, SVB_PIXEL_SHAPE, SVB_PIXEL_TEXT, SVB_PIXEL_INVALID
+    SVB_PIXEL_RGBA, SVB_PIXEL_BGRA, SVB_PIXEL_SHAPE, SVB_PIXEL_TEXT, SVB_PIXEL_INVALID,
+    /* ours (upstream: "TODO: Higher bit-depth formats", sample.pict.swift:19): NV12's plane shapes, 16-bit little-endian
+     * words with ten bits in the MSBs.  An input of svb_scale_convert_picture only. */
+    SVB_PIXEL_P010
 } svb_pixel_format;
 
 /* BufferType (sample.pict.swift:58-63) */
@@ -158,6 +161,20 @@ void svb_picture_release(svb_picture* pict);
  * endComputePass(ctx, true); wait=0 returns at once (call svb_picture_wait before touching host bytes). */
 svb_status svb_upload_compute_picture(svb_context* ctx, const svb_picture* pict, int max_planes, int retain_cpu_buffer, svb_picture** out);
 svb_status svb_download_compute_picture(svb_context* ctx, const svb_picture* pict, int retain_gpu_buffer, int wait, svb_picture** out);
+
+/* ---- convert + scale (an extension: no upstream counterpart) ------------------------------------------------ */
+/* The reference has no resize filter beyond the OpenCL linear sampler (kernels.cl.swift:61), no high-bit-depth format
+ * (sample.pict.swift:19) and, on Linux, no kernel that writes BGRA (compute.swift:54 reserves img_bgra_bgra; only a
+ * half-written Metal body exists, kernels.metal:51-62).  BASELINE.json's configs 2 and 5 name this operator with libswscale
+ * as comparator: src = a GPU NV12 or P010 sample, result = a new GPU BGRA sample of dst_width x dst_height, separable
+ * bilinear or Lanczos-3 resize, BT.601 limited-range YUV -> full-range RGB.  Defined bit for bit by oracle/scale_oracle.c;
+ * within one code value of libswscale 9.1 in its accurate mode.  wait=0 returns at once (svb_picture_wait before use). */
+typedef enum svb_scale_filter { SVB_FILTER_BILINEAR = 0, SVB_FILTER_LANCZOS3 = 1 } svb_scale_filter;
+svb_status svb_scale_convert_picture(svb_context* ctx, const svb_picture* src, float dst_width, float dst_height, int dst_pixel_format, int filter,
+                                     int wait, svb_picture** out);
+/* One axis of that resize: *taps weights per output sample (weights[dst_n * taps]) from source index first[x] on; call
+ * with first = weights = NULL to learn *taps.  No device needed. */
+svb_status svb_scale_filter_table(int filter, int src_n, int dst_n, int32_t* first, float* weights, int weights_capacity, int* taps);
 
 /* ---- PictureAnimator's state -> matrices (animator.pic.swift:107-128,207-272,326-333) ------------------ */
 typedef struct svb_element_state {   /* the ElementState fields computePictureState reads (Proto/Composition.proto:56-71) */

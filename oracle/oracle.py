@@ -166,3 +166,53 @@ def host_threads():
         return len(os.sched_getaffinity(0))
     except AttributeError:
         return os.cpu_count() or 1
+
+
+# ---- convert + scale operator (scale_oracle.c): NV12 / P010 -> BGRA, bilinear or Lanczos-3 ----------------------------
+SC_NV12, SC_P010 = 0, 1
+SC_BILINEAR, SC_LANCZOS3 = 0, 1
+
+
+def _scale_lib():
+    lib = port().lib
+    if not getattr(lib, "_scale_ready", False):
+        lib.svo_scale_taps.restype = C.c_int
+        lib.svo_scale_taps.argtypes = [C.c_int, C.c_int, C.c_int]
+        lib.svo_scale_table.restype = None
+        lib.svo_scale_table.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        lib.svo_scale_convert.restype = C.c_int
+        lib.svo_scale_convert.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        lib._scale_ready = True
+    return lib
+
+
+def scale_table(filt, src_n, dst_n):
+    """(first[dst_n] int32, weights[dst_n, taps] float32) of one axis."""
+    lib = _scale_lib()
+    n = lib.svo_scale_taps(filt, src_n, dst_n)
+    first = np.zeros(dst_n, dtype=np.int32)
+    w = np.zeros((dst_n, n), dtype=np.float32)
+    lib.svo_scale_table(filt, src_n, dst_n, first.ctypes.data, w.ctypes.data)
+    return first, w
+
+
+def scale_src_layout(fmt, w, h):
+    """(bytes per sample, luma stride, chroma stride, total bytes) of a contiguous NV12 / P010 picture."""
+    if fmt not in (SC_NV12, SC_P010):
+        raise ValueError(fmt)
+    bps = 1 if fmt == SC_NV12 else 2
+    return bps, w * bps, w * bps, w * h * bps + w * (h // 2) * bps
+
+
+def scale_convert(fmt, filt, src, src_w, src_h, dst_w, dst_h):
+    """src: contiguous uint8 buffer (luma plane, then the interleaved chroma plane).  Returns dst_h x dst_w x 4 BGRA bytes."""
+    lib = _scale_lib()
+    bps, sy, sc, total = scale_src_layout(fmt, src_w, src_h)
+    src = np.ascontiguousarray(src, dtype=np.uint8).reshape(-1)
+    assert src.size == total, (src.size, total)
+    dst = np.zeros((dst_h, dst_w, 4), dtype=np.uint8)
+    base = src.ctypes.data
+    rc = lib.svo_scale_convert(fmt, filt, base, sy, base + sy * src_h, sc, src_w, src_h, dst.ctypes.data, dst_w * 4, dst_w, dst_h)
+    if rc != 0:
+        raise ValueError("svo_scale_convert: bad argument")
+    return dst

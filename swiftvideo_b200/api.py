@@ -10,7 +10,8 @@ _PKG = Path(__file__).resolve().parent
 _LIB_PATH = _PKG / "libsvb200.so"
 
 # PixelFormat / ComputeKernel / modes (svb200.h enums)
-NV12, NV21, YUVS, ZVUY, Y420P, Y422P, Y444P, RGBA, BGRA, SHAPE, TEXT, INVALID = range(12)
+NV12, NV21, YUVS, ZVUY, Y420P, Y422P, Y444P, RGBA, BGRA, SHAPE, TEXT, INVALID, P010 = range(13)  # P010: ours (svb200.h)
+FILTER_BILINEAR, FILTER_LANCZOS3 = 0, 1
 BUFFER_SHARED, BUFFER_CPU, BUFFER_GPU, BUFFER_INVALID = range(4)
 DEVICE_GPU = 0
 KERNEL_CUSTOM = 15
@@ -116,6 +117,8 @@ def _load():
     l.svb_launch_timing.argtypes = [C.c_void_p, C.c_int]
     l.svb_launch_timing_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     l.svb_selftest_unorm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    l.svb_scale_convert_picture.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    l.svb_scale_filter_table.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     return l
 
 
@@ -309,6 +312,22 @@ class PictureSample:
 
     def wait(self):
         _check(lib.svb_picture_wait(self._h))
+
+    def scale_convert(self, ctx, width, height, pixel_format=BGRA, filter=FILTER_BILINEAR, wait=True):
+        """svb_scale_convert_picture (ours; no upstream counterpart): a GPU NV12 / P010 sample -> a new GPU BGRA sample."""
+        h = C.c_void_p()
+        _check(lib.svb_scale_convert_picture(ctx._h, self._h, width, height, pixel_format, filter, int(wait), C.byref(h)))
+        return PictureSample(h)
+
+
+def scale_filter_table(filter, src_n, dst_n):
+    """(first[dst_n] int32, weights[dst_n, taps] float32): one axis of the convert+scale operator's resize (host only)."""
+    taps = C.c_int()
+    _check(lib.svb_scale_filter_table(filter, src_n, dst_n, None, None, 0, C.byref(taps)))
+    first = np.zeros(dst_n, np.int32)
+    w = np.zeros((dst_n, taps.value), np.float32)
+    _check(lib.svb_scale_filter_table(filter, src_n, dst_n, first.ctypes.data, w.ctypes.data, w.size, C.byref(taps)))
+    return first, w
 
 
 def create_picture_sample(width, height, pixel_format, asset_id="", workspace_id="", pinned_from=None):

@@ -43,7 +43,7 @@ def build(force=False, verbose=False):
     log = ""
     if force or _newer(CUBIN, cu_sources):
         log += _run([CUDA_HOME / "bin" / "nvcc", "-cubin", *NVCC_FLAGS, "-Xptxas", "-v", "-o", CUBIN, CSRC / "kernels.cu"])
-    host_sources = [CSRC / n for n in ("cu_driver.cpp", "compute.cpp", "mix_video.cpp", "animator.cpp", "abi.cpp")]
+    host_sources = [CSRC / n for n in ("cu_driver.cpp", "compute.cpp", "mix_video.cpp", "scale.cpp", "animator.cpp", "abi.cpp")]
     headers = sorted(CSRC.glob("*.h")) + [PKG.parent / "include" / "svb200.h"]
     if force or _newer(LIB, host_sources + headers + [CUBIN]):
         blob = BUILD / "kernels_cubin.S"

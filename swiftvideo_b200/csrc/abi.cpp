@@ -161,7 +161,7 @@ svb_status svb_create_picture_sample(float width, float height, int pixel_format
                                      svb_context* pinned_from, svb_picture** out) {
     return guard([&] {
         need(out, "out");
-        if (pixel_format < 0 || pixel_format > (int)PixelFormat::invalid) throw ComputeError(ErrorCode::badInputData, "Invalid pixel format");
+        if (pixel_format < 0 || pixel_format > (int)PixelFormat::p010) throw ComputeError(ErrorCode::badInputData, "Invalid pixel format");
         *out = wrap(createPictureSample(Vector2{width, height}, (PixelFormat)pixel_format, asset_id ? asset_id : "", workspace_id ? workspace_id : "",
                                         pinned_from ? &pinned_from->c : nullptr));
     });
@@ -172,7 +172,7 @@ svb_status svb_picture_sample_from_planes(float width, float height, int pixel_f
         need(planes, "planes");
         need(strides, "strides");
         need(out, "out");
-        if (pixel_format < 0 || pixel_format > (int)PixelFormat::invalid) throw ComputeError(ErrorCode::badInputData, "Invalid pixel format");
+        if (pixel_format < 0 || pixel_format > (int)PixelFormat::p010) throw ComputeError(ErrorCode::badInputData, "Invalid pixel format");
         if (plane_count < 1 || plane_count > 3) throw ComputeError(ErrorCode::badInputData, "Input image must have 1, 2, or 3 planes");
         const uint8_t* p[3] = {nullptr, nullptr, nullptr};
         int st[3] = {0, 0, 0};
@@ -247,6 +247,31 @@ svb_status svb_download_compute_picture(svb_context* ctx, const svb_picture* pic
         need(pict, "pict");
         need(out, "out");
         *out = wrap(downloadComputePicture(ctx->c, *pict->p, retain_gpu_buffer != 0, wait != 0));
+    });
+}
+
+svb_status svb_scale_convert_picture(svb_context* ctx, const svb_picture* src, float dst_width, float dst_height, int dst_pixel_format, int filter, int wait,
+                                     svb_picture** out) {
+    return guard([&] {
+        need(ctx, "ctx");
+        need(src, "src");
+        need(out, "out");
+        if (filter != 0 && filter != 1) throw ComputeError(ErrorCode::invalidValue, "unknown scale filter");
+        if (dst_pixel_format < 0 || dst_pixel_format > (int)PixelFormat::p010) throw ComputeError(ErrorCode::invalidValue, "unknown pixel format");
+        *out = wrap(scaleConvertPicture(ctx->c, *src->p, Vector2{dst_width, dst_height}, (PixelFormat)dst_pixel_format, (ScaleFilter)filter, wait != 0));
+    });
+}
+svb_status svb_scale_filter_table(int filter, int src_n, int dst_n, int32_t* first, float* weights, int weights_capacity, int* taps) {
+    return guard([&] {
+        need(taps, "taps");
+        if (filter != 0 && filter != 1) throw ComputeError(ErrorCode::invalidValue, "unknown scale filter");
+        const ScaleTable t = makeScaleTable((ScaleFilter)filter, src_n, dst_n);
+        *taps = t.taps;
+        if (first && weights) {
+            if (weights_capacity < (int)t.weights.size()) throw ComputeError(ErrorCode::invalidValue, "weights_capacity too small");
+            std::memcpy(first, t.first.data(), sizeof(int32_t) * t.first.size());
+            std::memcpy(weights, t.weights.data(), sizeof(float) * t.weights.size());
+        }
     });
 }
 

@@ -67,7 +67,7 @@ ComputeKernel defaultComputeKernelFromString(const std::string& name) {  // comp
 }
 
 const char* pixelFormatName(PixelFormat f) {
-    static const char* n[] = {"nv12", "nv21", "yuvs", "zvuy", "y420p", "y422p", "y444p", "rgba", "bgra", "shape", "text", "invalid"};
+    static const char* n[] = {"nv12", "nv21", "yuvs", "zvuy", "y420p", "y422p", "y444p", "rgba", "bgra", "shape", "text", "invalid", "p010"};
     return n[(int)f];
 }
 
@@ -84,8 +84,14 @@ InternalContext::~InternalContext() {
     cu().cuCtxPushCurrent(ctx);
     cu().cuCtxSynchronize();
     if (mixerSharedFree) mixerSharedFree(this);
+    if (scaleSharedFree) scaleSharedFree(this);
     for (auto& kv : pool) {
         cu().cuMemFree(kv.second.p);
+        for (CUevent e : kv.second.after)
+            if (e) cu().cuEventDestroy(e);
+    }
+    for (auto& kv : hostPool) {
+        cu().cuMemFreeHost(kv.second.p);
         for (CUevent e : kv.second.after)
             if (e) cu().cuEventDestroy(e);
     }
@@ -155,6 +161,56 @@ void InternalContext::release(CUdeviceptr p, size_t size) {
     }
     std::lock_guard<std::mutex> g(mu);
     pool.emplace(size, b);
+}
+
+// caller holds a CtxGuard
+void* InternalContext::allocHost(size_t size) {
+    size = (size + 4095) & ~(size_t)4095;
+    HostBlock b;
+    {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = hostPool.find(size);
+        if (it != hostPool.end()) {
+            b = it->second;
+            hostPool.erase(it);
+        }
+    }
+    if (b.p) {
+        for (CUevent e : b.after) {
+            if (!e) continue;
+            cu().cuEventSynchronize(e);  // normally long fired
+            std::lock_guard<std::mutex> g(mu);
+            spareEvents.push_back(e);
+        }
+        return b.p;
+    }
+    void* p = nullptr;
+    check(drv().cuMemHostAlloc(&p, size, 0), "cuMemHostAlloc");
+    return p;
+}
+void InternalContext::releaseHost(void* p, size_t size) {
+    size = (size + 4095) & ~(size_t)4095;
+    if (!cu().ok || !ctx) return;
+    HostBlock b;
+    b.p = p;
+    cu().cuCtxPushCurrent(ctx);
+    CUstream two[2] = {upload, download};
+    for (int i = 0; i < 2; ++i) {
+        CUevent e = nullptr;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            if (!spareEvents.empty()) {
+                e = spareEvents.back();
+                spareEvents.pop_back();
+            }
+        }
+        if (!e && cu().cuEventCreate(&e, CU_EVENT_DISABLE_TIMING) != CUDA_SUCCESS) e = nullptr;
+        if (e && cu().cuEventRecord(e, two[i]) == CUDA_SUCCESS) b.after[i] = e;
+    }
+    CUcontext old;
+    cu().cuCtxPopCurrent(&old);
+    std::lock_guard<std::mutex> g(mu);
+    hostPool.emplace(size, b);
 }
 
 CUfunction InternalContext::builtin(const char* name) {
@@ -337,6 +393,8 @@ std::vector<Plane> planesForFormat(PixelFormat f, Vector2 size) {  // sample.pic
     switch (f) {
     case PixelFormat::nv12:
         return {Plane{size, width, 8, {Component::y}}, Plane{half, width, 8, {Component::cb, Component::cr}}};
+    case PixelFormat::p010:  // ours: 16-bit little-endian words, ten bits in the MSBs; same plane shapes as nv12
+        return {Plane{size, width * 2, 10, {Component::y}}, Plane{half, width * 2, 10, {Component::cb, Component::cr}}};
     case PixelFormat::BGRA:
     case PixelFormat::RGBA:
         return {Plane{size, width * 4, 8, {Component::r, Component::g, Component::b, Component::a}}};
@@ -361,17 +419,10 @@ PictureSample createPictureSample(Vector2 size, PixelFormat format, const std::s
     std::shared_ptr<uint8_t> base;
     if (pinnedFrom && pinnedFrom->ctx) {
         CtxGuard g(pinnedFrom->ctx);
-        void* p = nullptr;
-        check(drv().cuMemHostAlloc(&p, total, 0), "cuMemHostAlloc");
         auto ic = pinnedFrom->ctx;
-        base = std::shared_ptr<uint8_t>((uint8_t*)p, [ic](uint8_t* q) {
-            if (cu().ok) {
-                cu().cuCtxPushCurrent(ic->ctx);
-                cu().cuMemFreeHost(q);
-                CUcontext old;
-                cu().cuCtxPopCurrent(&old);
-            }
-        });
+        void* p = ic->allocHost(std::max<size_t>(total, 1));
+        const size_t n = std::max<size_t>(total, 1);
+        base = std::shared_ptr<uint8_t>((uint8_t*)p, [ic, n](uint8_t* q) { ic->releaseHost(q, n); });
     } else {
         void* p = nullptr;
         if (posix_memalign(&p, 4096, std::max<size_t>(total, 1)) != 0) throw ComputeError(ErrorCode::outOfMemory, "host allocation failed");
@@ -398,7 +449,7 @@ PictureSample pictureSampleFromPlanes(PixelFormat format, Vector2 size, const ui
     std::vector<Plane> layout = planesForFormat(format, size);
     if (planeCount != (int)layout.size()) throw ComputeError(ErrorCode::badInputData, "Input image must have the same number of buffers as planes");
     for (int i = 0; i < planeCount; ++i) {
-        const int minStride = (int)layout[i].size.x * (int)layout[i].components.size();
+        const int minStride = (int)layout[i].size.x * (int)layout[i].components.size() * (layout[i].bitDepth > 8 ? 2 : 1);
         if (!planes[i] || strides[i] < minStride) throw ComputeError(ErrorCode::badInputData, "plane stride smaller than its row");
         layout[i].stride = strides[i];
     }
@@ -471,7 +522,9 @@ PictureSample downloadComputePicture(const ComputeContext& ctx, const PictureSam
     PictureSample out = pict;
     const size_t n = pict.imgBuffer.computeTextures.size();
     if (out.imgBuffer.buffers.size() < n) {  // upstream: `dst ?? Data(capacity:)` -- allocate what is missing
-        PictureSample host = createPictureSample(pict.size(), pict.pixelFormat(), pict.idAsset, pict.idWorkspace);
+        // page-locked (pooled): a copy into pageable memory is staged by the driver at a fraction of the link rate
+        ComputeContext pin = ctx;
+        PictureSample host = createPictureSample(pict.size(), pict.pixelFormat(), pict.idAsset, pict.idWorkspace, &pin);
         out.imgBuffer.buffers = host.imgBuffer.buffers;
     }
     CtxGuard g(ctx.ctx);

@@ -74,7 +74,8 @@ const char* computeKernelName(ComputeKernel k);                          // Stri
 ComputeKernel defaultComputeKernelFromString(const std::string& name);  // compute.swift:90-110 (throws invalidValue)
 
 // ---- picture data model --------------------------------------------------------------------------------
-enum class PixelFormat : int { nv12 = 0, nv21, yuvs, zvuy, y420p, y422p, y444p, RGBA, BGRA, shape, text, invalid };
+// p010 is ours (upstream: "TODO: Higher bit-depth formats", sample.pict.swift:19); it comes after `invalid` so that the upstream cases keep their values
+enum class PixelFormat : int { nv12 = 0, nv21, yuvs, zvuy, y420p, y422p, y444p, RGBA, BGRA, shape, text, invalid, p010 };
 enum class BufferType : int { shared = 0, cpu, gpu, invalid };
 enum class Component : int { r, g, b, a, y, cr, cb };
 const char* pixelFormatName(PixelFormat f);  // lower-cased case name, as VideoMixer.findKernel builds it
@@ -230,6 +231,21 @@ ImageUniforms makeImageUniforms(const PictureSample& image, const PictureSample&
 ComputeContext applyComputeImage(const ComputeContext& ctx, const PictureSample& image, const PictureSample& target,
                                  ComputeKernel kernel);
 
+// ---- convert + scale (ours: no upstream counterpart; BASELINE.json configs 2 and 5 name it, oracle/scale_oracle.c defines it)
+enum class ScaleFilter : int { bilinear = 0, lanczos3 = 1 };
+// One axis of the resize: first[dstN] source index and n weights per output sample (swscale's filter construction in
+// floating point; scale.cpp).  Exposed so that the tests can hold the library's tables against the oracle's.
+struct ScaleTable {
+    int taps = 0;
+    std::vector<int32_t> first;
+    std::vector<float> weights;
+};
+ScaleTable makeScaleTable(ScaleFilter filter, int srcN, int dstN);
+// `src`: a GPU nv12 or p010 sample.  Returns a GPU BGRA sample of `dstSize` (a new texture); wait=false returns at once
+// with `done` set.  Throws notImplemented for ratios whose filter needs more than 16 taps.
+PictureSample scaleConvertPicture(const ComputeContext& ctx, const PictureSample& src, Vector2 dstSize, PixelFormat dstFormat, ScaleFilter filter,
+                                  bool wait = true);
+
 // After queueing a kernel that writes `target` on the compute stream: later consumers on other streams
 // (downloads) order themselves behind it through the textures' `ready` events.
 void markWritten(const ComputeContext& ctx, const PictureSample& target);
@@ -250,10 +266,22 @@ struct InternalContext {
         CUevent after[3] = {nullptr, nullptr, nullptr};  // tails of compute/upload/download at release time
     };
     std::multimap<size_t, Block> pool;  // freed device blocks by size (upstream cuMemAllocs per upload)
+    // page-locked host blocks by size (createPictureSample(pinnedFrom:), and the destination of a download that has none):
+    // cuMemHostAlloc costs milliseconds, and a download into pageable memory runs at a fraction of the link rate
+    struct HostBlock {
+        void* p = nullptr;
+        CUevent after[2] = {nullptr, nullptr};  // tails of upload/download at release time: an async copy may still touch it
+    };
+    std::multimap<size_t, HostBlock> hostPool;
+    void* allocHost(size_t size);
+    void releaseHost(void* p, size_t size);
     std::vector<CUevent> spareEvents;
     // state shared by every VideoMixer of this context (descriptor ring, tensor-map cache); owned by mix_video.cpp
     void* mixerShared = nullptr;
     void (*mixerSharedFree)(InternalContext*) = nullptr;
+    // filter tables of the convert+scale operator by (filter, srcN, dstN); owned by scale.cpp
+    void* scaleShared = nullptr;
+    void (*scaleSharedFree)(InternalContext*) = nullptr;
     ~InternalContext();
     CUdeviceptr alloc(size_t size);
     void release(CUdeviceptr p, size_t size);

@@ -108,6 +108,19 @@ typedef struct __attribute__((aligned(16))) SvbTilePlan {
 #define SVB_TILED_SMEM_BYTES(boxY, boxC) (SVB_TILED_FIXED_BYTES + 2 * (boxY) + 2 * (boxC))
 #define SVB_TILED_SMEM_MAX SVB_TILED_SMEM_BYTES(SVB_BOX_Y_BYTES, SVB_BOX_C_BYTES)
 
+// svb_scale_convert (kernels_scale.cuh): NV12 / P010 -> BGRA with a separable resize, passed by value as the kernel argument.
+// Tables per axis and plane kind (Y = luma plane, C = chroma plane): first[dstN] = first source index of each output
+// column / row (may lie outside the plane: indices are clamped when sampling), w[dstN * n] = its n tap weights.
+typedef struct SvbScaleDesc {
+    unsigned long long srcY, srcC, dst;
+    unsigned long long fYx, wYx, fYy, wYy, fCx, wCx, fCy, wCy;
+    int32_t strideY, strideC, dstStride;
+    int32_t srcW, srcH, dstW, dstH;
+    int32_t format;          // 0 NV12, 1 P010 (10 bits in the MSBs of little-endian 16-bit words)
+    int32_t nYx, nYy, nCx, nCy;
+    int32_t spanYy, spanCy;  // most horizontally filtered rows (luma / chroma) one 32-row output tile needs: shared-memory sizing
+} SvbScaleDesc;
+
 #ifdef __cplusplus
 static_assert(sizeof(SvbUniforms) == 240, "SvbUniforms layout");
 static_assert(sizeof(SvbLayerDesc) % 64 == 0, "SvbLayerDesc alignment");

@@ -1,0 +1,166 @@
+"""The convert+scale operator (NV12 / P010 -> BGRA, bilinear / Lanczos-3): BASELINE.json configs 2 and 5.
+
+The reference has no such operator (SURVEY.md "five facts" 2-3), so parity is pinned in two steps:
+  * oracle/scale_oracle.c is the definition; it is held against libswscale 9.1 -- the comparator BASELINE.json names -- in
+    swscale's accurate mode on smooth content: at most ONE code value apart (swscale accumulates in 14/15-bit fixed point),
+  * the CUDA kernel must equal the definition bit for bit (random content, ragged sizes, both formats, both filters, up- and
+    down-scaling, BASELINE's full sizes), called through the C ABI.
+"""
+import numpy as np
+import pytest
+
+import swscale_util as S
+from oracle import oracle as O
+
+needs_sws = pytest.mark.skipif(not S.available(), reason="libswscale (OpenCV wheel) not loadable")
+
+
+# ---- CPU: tables, the definition against libswscale ---------------------------------------------------------------------
+
+@pytest.mark.parametrize("filt", [O.SC_BILINEAR, O.SC_LANCZOS3])
+@pytest.mark.parametrize("src_n,dst_n", [(3840, 1920), (2160, 1080), (1920, 1280), (1080, 720), (360, 640), (1080, 1080), (959, 413), (2, 1), (2, 7)])
+def test_filter_tables_match_oracle(filt, src_n, dst_n):
+    """The library's filter tables (host code, no device) equal the oracle's bit for bit, sum to one and stay within reach."""
+    import swiftvideo_b200 as sv
+    f1, w1 = sv.scale_filter_table(filt, src_n, dst_n)
+    f2, w2 = O.scale_table(filt, src_n, dst_n)
+    assert w1.shape == w2.shape and (f1 == f2).all()
+    assert (w1.view(np.uint32) == w2.view(np.uint32)).all()
+    assert np.allclose(w1.sum(axis=1), 1.0, atol=1e-6)
+    assert (np.diff(f1) >= 0).all()  # firsts are monotone: a tile's footprint is bounded by its end rows / columns
+
+
+def test_filter_table_errors():
+    import swiftvideo_b200 as sv
+    with pytest.raises(sv.ComputeError) as e:
+        sv.scale_filter_table(7, 10, 10)
+    assert e.value.name == "invalidValue"
+    with pytest.raises(sv.ComputeError):
+        sv.scale_filter_table(0, 0, 10)
+
+
+SWS_CASES = [
+    ("nv12", 8, O.SC_NV12, O.SC_BILINEAR, S.SWS_BILINEAR, (640, 360), (426, 240)),
+    ("nv12", 8, O.SC_NV12, O.SC_BILINEAR, S.SWS_BILINEAR, (640, 360), (640, 360)),
+    ("nv12", 8, O.SC_NV12, O.SC_LANCZOS3, S.SWS_LANCZOS, (320, 180), (640, 360)),
+    ("p010le", 10, O.SC_P010, O.SC_LANCZOS3, S.SWS_LANCZOS, (960, 540), (480, 270)),
+    ("p010le", 10, O.SC_P010, O.SC_BILINEAR, S.SWS_BILINEAR, (480, 270), (854, 480)),
+    ("nv12", 8, O.SC_NV12, O.SC_BILINEAR, S.SWS_BILINEAR, (1920, 1080), (1280, 720)),  # BASELINE cfg 2's scale
+]
+
+
+@needs_sws
+@pytest.mark.parametrize("name,bits,fmt,filt,flag,src,dst", SWS_CASES)
+def test_definition_within_one_code_of_swscale(name, bits, fmt, filt, flag, src, dst):
+    pic = S.smooth_picture(bits, src[0], src[1], seed=3)
+    ours = O.scale_convert(fmt, filt, pic, src[0], src[1], dst[0], dst[1]).astype(np.int32)
+    sc = S.Scaler(name, src[0], src[1], dst[0], dst[1], flag | S.SWS_ACCURATE_RND | S.SWS_FULL_CHR_H_INT)
+    ref = sc.run(pic).astype(np.int32)
+    sc.close()
+    d = np.abs(ours - ref)
+    assert d[:, :, 3].max() == 0  # alpha 255 on both sides
+    assert d.max() <= 1, f"max |diff| {d.max()}"  # TOLERANCE: one 8-bit code value
+    assert d.mean() < 0.02
+
+
+def test_definition_known_answers():
+    """Flat pictures: a resize of a constant is that constant, and the colour matrix maps video black / white / grey as BT.601
+    limited range says."""
+    for bits, fmt in ((8, O.SC_NV12), (10, O.SC_P010)):
+        for (y, u, v), want in (((16, 128, 128), (0, 0, 0)), ((235, 128, 128), (255, 255, 255)), ((126, 128, 128), (128, 128, 128))):
+            w, h = 64, 36
+            if bits == 8:
+                pic = np.concatenate([np.full(w * h, y, np.uint8), np.tile(np.array([u, v], np.uint8), w * h // 4)])
+            else:
+                pic = np.concatenate([np.full(w * h, (y * 4) << 6, np.uint16), np.tile(np.array([(u * 4) << 6, (v * 4) << 6], np.uint16), w * h // 4)]).view(np.uint8)
+            for filt in (O.SC_BILINEAR, O.SC_LANCZOS3):
+                out = O.scale_convert(fmt, filt, pic, w, h, 40, 30)
+                assert (out[:, :, 3] == 255).all()
+                assert (out[:, :, :3] == np.array(want[::-1], np.uint8)).all(), (bits, filt, out[0, 0])
+
+
+def test_definition_bad_arguments():
+    pic = np.zeros(64 * 36 * 3 // 2, np.uint8)
+    with pytest.raises(ValueError):
+        O.scale_convert(5, O.SC_BILINEAR, pic, 64, 36, 32, 18)
+    with pytest.raises(ValueError):
+        O.scale_convert(O.SC_NV12, 9, pic, 64, 36, 32, 18)
+
+
+# ---- GPU: the kernel against the definition -------------------------------------------------------------------------------
+
+def _random_picture(fmt, w, h, seed):
+    rng = np.random.default_rng(seed)
+    if fmt == O.SC_NV12:
+        return rng.integers(0, 256, size=w * h * 3 // 2, dtype=np.uint8)
+    return (rng.integers(0, 1024, size=w * h * 3 // 2, dtype=np.uint16) << 6).view(np.uint8)  # every 10-bit code, full range
+
+
+def _gpu_scale(ctx, fmt, filt, pic, src, dst):
+    import swiftvideo_b200 as sv
+    p = sv.create_picture_sample(src[0], src[1], sv.NV12 if fmt == O.SC_NV12 else sv.P010, "src", "test")
+    p.set_host_bytes(pic)
+    out = p.upload(ctx).scale_convert(ctx, dst[0], dst[1], sv.BGRA, filt)
+    info = out.info()
+    assert info.pixel_format == sv.BGRA and int(info.width) == dst[0] and int(info.height) == dst[1]
+    return out.download(ctx).host_bytes().reshape(dst[1], dst[0], 4)
+
+
+GPU_CASES = [
+    (O.SC_NV12, O.SC_BILINEAR, (640, 360), (426, 240)),
+    (O.SC_NV12, O.SC_BILINEAR, (640, 360), (640, 360)),
+    (O.SC_NV12, O.SC_LANCZOS3, (320, 180), (640, 360)),
+    (O.SC_P010, O.SC_LANCZOS3, (960, 540), (480, 270)),
+    (O.SC_P010, O.SC_BILINEAR, (64, 36), (200, 100)),
+    (O.SC_NV12, O.SC_BILINEAR, (130, 70), (97, 53)),      # ragged: partial tiles on both axes, odd destination
+    (O.SC_P010, O.SC_LANCZOS3, (258, 130), (101, 67)),    # ragged, 2.55 : 1 (16 taps: the most the kernel takes)
+    (O.SC_NV12, O.SC_LANCZOS3, (2, 2), (5, 3)),           # the smallest source
+    (O.SC_NV12, O.SC_BILINEAR, (256, 64), (33, 9)),       # 7.8 : 1 bilinear (16 taps)
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmt,filt,src,dst", GPU_CASES)
+def test_gpu_scale_bit_exact(fmt, filt, src, dst):
+    import gpu_util
+    pic = _random_picture(fmt, src[0], src[1], seed=5000 + src[0] + dst[1])
+    got = _gpu_scale(gpu_util.context(), fmt, filt, pic, src, dst)
+    want = O.scale_convert(fmt, filt, pic, src[0], src[1], dst[0], dst[1])
+    bad = int((got != want).sum())
+    assert bad == 0, f"{bad} bytes differ; first rows got {got[0, :2]} want {want[0, :2]}"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmt,filt,src,dst", [(O.SC_NV12, O.SC_BILINEAR, (1920, 1080), (1280, 720)),     # BASELINE cfg 2's convert + scale
+                                              (O.SC_P010, O.SC_LANCZOS3, (3840, 2160), (1920, 1080))])  # BASELINE cfg 5
+def test_gpu_scale_full_size(fmt, filt, src, dst):
+    import gpu_util
+    pic = _random_picture(fmt, src[0], src[1], seed=5)
+    got = _gpu_scale(gpu_util.context(), fmt, filt, pic, src, dst)
+    want = O.scale_convert(fmt, filt, pic, src[0], src[1], dst[0], dst[1])
+    assert int((got != want).sum()) == 0
+
+
+@pytest.mark.gpu
+def test_gpu_scale_errors():
+    import gpu_util
+    import swiftvideo_b200 as sv
+    ctx = gpu_util.context()
+    host = sv.create_picture_sample(64, 36, sv.NV12, "a", "t")
+    with pytest.raises(sv.ComputeError) as e:  # not uploaded
+        host.scale_convert(ctx, 32, 18)
+    assert e.value.name == "badInputData"
+    nv = host.upload(ctx)
+    with pytest.raises(sv.ComputeError) as e:  # only BGRA targets exist
+        nv.scale_convert(ctx, 32, 18, sv.NV12)
+    assert e.value.name == "computeKernelNotFound"
+    with pytest.raises(sv.ComputeError) as e:  # Lanczos-3 at 4 : 1 would need 24 taps
+        nv.scale_convert(ctx, 16, 9, sv.BGRA, sv.FILTER_LANCZOS3)
+    assert e.value.name == "notImplemented"
+    bgra = sv.create_picture_sample(64, 36, sv.BGRA, "b", "t").upload(ctx)
+    with pytest.raises(sv.ComputeError) as e:  # sources are NV12 / P010
+        bgra.scale_convert(ctx, 32, 18)
+    assert e.value.name == "computeKernelNotFound"
+    with pytest.raises(sv.ComputeError) as e:
+        nv.scale_convert(ctx, 0, 18)
+    assert e.value.name == "badTarget"
