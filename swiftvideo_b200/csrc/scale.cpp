@@ -22,7 +22,7 @@ static const CuDriver& drv() {
 
 namespace {
 
-constexpr int kTileW = 64, kTileH = 32, kMaxTaps = 16;  // SVB_SCALE_TW / _TH / _MAX_TAPS of kernels_scale.cuh
+constexpr int kTileW = SVB_SCALE_TW, kTileH = SVB_SCALE_TH, kMaxTaps = SVB_SCALE_MAX_TAPS;
 
 double filterWeight(ScaleFilter f, double t) {
     t = std::fabs(t);
@@ -36,7 +36,7 @@ double filterWeight(ScaleFilter f, double t) {
 struct DeviceTable {
     ScaleTable host;
     CUdeviceptr first = 0, weights = 0;
-    int span32 = 0;  // most source samples any run of kTileH consecutive outputs reaches
+    int span32 = 0, span64 = 0;  // most source samples any aligned run of kTileH (span32) / kTileW (span64) consecutive outputs reaches
 };
 struct ScaleShared {
     std::mutex mu;
@@ -78,6 +78,10 @@ const DeviceTable& deviceTable(const std::shared_ptr<InternalContext>& ic, Scale
     for (int a = 0; a < dstN; a += kTileH) {
         const int b = std::min(a + kTileH, dstN) - 1;
         t.span32 = std::max(t.span32, t.host.first[b] + t.host.taps - t.host.first[a]);
+    }
+    for (int a = 0; a < dstN; a += kTileW) {
+        const int b = std::min(a + kTileW, dstN) - 1;
+        t.span64 = std::max(t.span64, t.host.first[b] + t.host.taps - t.host.first[a]);
     }
     check(drv().cuMemAlloc(&t.first, sizeof(int32_t) * (size_t)dstN), "cuMemAlloc");
     check(drv().cuMemAlloc(&t.weights, sizeof(float) * t.host.weights.size()), "cuMemAlloc");
@@ -138,7 +142,9 @@ PictureSample scaleConvertPicture(const ComputeContext& ctx, const PictureSample
     const DeviceTable& cy = deviceTable(ctx.ctx, sh, filter, srcH / 2, dstH);
     if (std::max(std::max(yx.host.taps, yy.host.taps), std::max(cx.host.taps, cy.host.taps)) > kMaxTaps)
         throw ComputeError(ErrorCode::notImplemented, "scaleConvertPicture: this ratio needs more than 16 filter taps");
-    const size_t smem = ((size_t)yy.span32 + 2 * (size_t)cy.span32) * kTileW * sizeof(float);
+    // filtered rows (luma + U + V, 64 floats each) + the staged source window (luma, reused for the two chroma components)
+    const size_t window = std::max((size_t)yy.span32 * (size_t)yx.span64, 2 * (size_t)cy.span32 * (size_t)cx.span64);
+    const size_t smem = (((size_t)yy.span32 + 2 * (size_t)cy.span32) * kTileW + window) * sizeof(float);
     if (smem > 200 * 1024) throw ComputeError(ErrorCode::notImplemented, "scaleConvertPicture: vertical footprint too large for one tile");
 
     PictureSample out;
@@ -161,7 +167,7 @@ PictureSample scaleConvertPicture(const ComputeContext& ctx, const PictureSample
     desc.srcW = srcW, desc.srcH = srcH, desc.dstW = dstW, desc.dstH = dstH;
     desc.format = sf == PixelFormat::p010 ? 1 : 0;
     desc.nYx = yx.host.taps, desc.nYy = yy.host.taps, desc.nCx = cx.host.taps, desc.nCy = cy.host.taps;
-    desc.spanYy = yy.span32, desc.spanCy = cy.span32;
+    desc.spanYy = yy.span32, desc.spanCy = cy.span32, desc.spanYx = yx.span64, desc.spanCx = cx.span64;
 
     if (src.done) check(d.cuStreamWaitEvent(ic.compute, src.done->e, 0), "cuStreamWaitEvent");
     for (const auto& t : src.imgBuffer.computeTextures)

@@ -108,6 +108,13 @@ typedef struct __attribute__((aligned(16))) SvbTilePlan {
 #define SVB_TILED_SMEM_BYTES(boxY, boxC) (SVB_TILED_FIXED_BYTES + 2 * (boxY) + 2 * (boxC))
 #define SVB_TILED_SMEM_MAX SVB_TILED_SMEM_BYTES(SVB_BOX_Y_BYTES, SVB_BOX_C_BYTES)
 
+// output tile of svb_scale_convert and the most filter taps per axis it takes (Lanczos-3 down to 1 : 2.66, bilinear down to 1 : 8)
+#define SVB_SCALE_TW 64
+#ifndef SVB_SCALE_TH
+#define SVB_SCALE_TH 16  // 16 rows: 47 KB of shared memory per CTA at 4K -> 1080p Lanczos (4 CTAs per SM); 32 rows halve the halo but leave 2 CTAs per SM (92 vs 66 us)
+#endif
+#define SVB_SCALE_MAX_TAPS 16
+
 // svb_scale_convert (kernels_scale.cuh): NV12 / P010 -> BGRA with a separable resize, passed by value as the kernel argument.
 // Tables per axis and plane kind (Y = luma plane, C = chroma plane): first[dstN] = first source index of each output
 // column / row (may lie outside the plane: indices are clamped when sampling), w[dstN * n] = its n tap weights.
@@ -118,7 +125,8 @@ typedef struct SvbScaleDesc {
     int32_t srcW, srcH, dstW, dstH;
     int32_t format;          // 0 NV12, 1 P010 (10 bits in the MSBs of little-endian 16-bit words)
     int32_t nYx, nYy, nCx, nCy;
-    int32_t spanYy, spanCy;  // most horizontally filtered rows (luma / chroma) one 32-row output tile needs: shared-memory sizing
+    int32_t spanYy, spanCy;  // most source rows (luma / chroma) one 32-row output tile reaches: shared-memory sizing
+    int32_t spanYx, spanCx;  // most source columns one 64-column output tile reaches = pitch of the staged window
 } SvbScaleDesc;
 
 #ifdef __cplusplus
