@@ -197,8 +197,9 @@ def run_ours(args):
             if args.pip_opacity is not None and k > 0:
                 op = args.pip_opacity
             rng = np.random.default_rng(rng_base + 16 * gstream + k)
-            h = sv.create_picture_sample(ssz[0], ssz[1], sv.NV12, f"s{gstream}l{k}", "bench", pinned_from=ctx)
-            h.set_host_bytes(rng.integers(0, 256, size=ssz[0] * ssz[1] * 3 // 2, dtype=np.uint8))
+            rgba = k >= NLAYERS - args.rgba_pips  # side experiment: the topmost pictures-in-picture as RGBA overlays (text / logo layers)
+            h = sv.create_picture_sample(ssz[0], ssz[1], sv.RGBA if rgba else sv.NV12, f"s{gstream}l{k}", "bench", pinned_from=ctx)
+            h.set_host_bytes(rng.integers(0, 256, size=ssz[0] * ssz[1] * (4 if rgba else 1) * (2 if rgba else 3) // 2, dtype=np.uint8))
             # PictureAnimator.impl in native code: matrix = ortho(canvas) * T(pos) * S(size), opacity = 1 - transparency
             host[s][k] = h.animate(CANVAS, (pos[0], pos[1], float(k)), dsz, transparency=1.0 - op)
             for c in range(2):
@@ -298,7 +299,8 @@ def run_ours(args):
         "metric": METRIC, "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms / args.steps, 4), "host_queue_ms_per_step": round(host_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8 (fp32 arithmetic, no FMA contraction)", "data": "synthetic (uniform u8 planes, seeded)",
-        "config": {"workload": WORKLOAD if args.pip_opacity is None else WORKLOAD + f" -- NOT the headline: picture-in-picture opacity forced to {args.pip_opacity}", "mode": args.mode, "streams_total": S * world, "frames_per_step": S * world, "parallelism": f"streams sharded, {S}/GPU, no collective", "host_affinity": numa,
+        "config": {"workload": (WORKLOAD if args.pip_opacity is None else WORKLOAD + f" -- NOT the headline: picture-in-picture opacity forced to {args.pip_opacity}") +
+                               (f" -- NOT the headline: the top {args.rgba_pips} pictures-in-picture are RGBA overlays" if args.rgba_pips else ""), "mode": args.mode, "streams_total": S * world, "frames_per_step": S * world, "parallelism": f"streams sharded, {S}/GPU, no collective", "host_affinity": numa,
                    "l2": "373 MB of distinct sources+targets per step (> 126 MB L2); sources alternate between two device copies",
                    "bit_exact_vs_oracle": "tests/test_gpu_parity.py::test_cfg34_full_size"},
         "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
@@ -545,6 +547,7 @@ def main():
     ap.add_argument("--pip-opacity", type=float, default=None,
                     help="side experiment, not the headline: opacity of layers 1..7 (1.0 = opaque pictures, which let the planner skip "
                          "whatever they cover)")
+    ap.add_argument("--rgba-pips", type=int, default=0, help="side experiment, not the headline: the topmost N pictures-in-picture are RGBA overlays")
     ap.add_argument("--workload", default="cfg4", choices=["cfg4", "cfg5", "cfg2"],
                     help="cfg4 (default) = the headline; cfg5 / cfg2 = the convert+scale operator's side workloads (1 GPU, our arm only)")
     args = ap.parse_args()

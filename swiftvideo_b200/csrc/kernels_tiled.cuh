@@ -31,25 +31,17 @@
 #ifndef SVB_ROLL_ROWS
 #define SVB_ROLL_ROWS 1  // the layer bodies run their two row pairs as a rolled loop (0: unrolled, 0.7 % slower at three CTAs per SM)
 #endif
-#ifndef SVB_EDGE_INLINE
-#define SVB_EDGE_INLINE 1  // 1: the edge-tile layer bodies (MODE 2 / 3) inlined into the compositor instead of called
-#endif
-#ifndef SVB_LEAN_EDGE
-#define SVB_LEAN_EDGE 1  // 0: every edge tile takes the general body (MODE 3)
-#endif
-#ifndef SVB_SPLIT_BARRIER
-#define SVB_SPLIT_BARRIER 0
-#endif
 #ifndef SVB_DYNAMIC_TILES
 // 1: CTAs claim tiles from a counter (row-major order, so neighbouring tiles still run together); 0: static round-robin.
 // Tiles cost between zero and eight layers, and with a static deal the slowest CTA's share decided the kernel time
 // (v7 profile: SM cycles active 1.01 M on average against 1.13 M elapsed).
 #define SVB_DYNAMIC_TILES 1
 #endif
-#ifndef SVB_PLAN_WARP
-// The warp that plans this CTA's next tile.  Not warp 0: thread 0 issues the TMA copies, and whatever a warp does alone
-// makes it late for the next CTA barrier -- two warps late by one chore each cost less than one warp late by both.
-#define SVB_PLAN_WARP (SVB_PRODUCER_WARP ? SVB_TILED_COMPUTE_WARPS : SVB_TILED_COMPUTE_WARPS - 1)
+#ifndef SVB_CLAIM_WARP
+// The warp whose lane 0 claims this CTA's tiles and fetches their plans.  Not warp 0: thread 0 issues the TMA copies, and
+// whatever a warp does alone makes it late for the next CTA barrier -- two warps late by one chore each cost less than one
+// warp late by both.
+#define SVB_CLAIM_WARP (SVB_TILED_COMPUTE_WARPS - 1)
 #endif
 
 
@@ -185,7 +177,7 @@ struct TiledSmem {  // the fixed part; the boxes follow at SVB_TILED_FIXED_BYTES
     int tile_idx[3];                                    // ring over this CTA's tile sequence: index of its k-th tile in slot k % 3 (>= total: none)
 };
 static_assert(sizeof(TiledSmem) <= SVB_TILED_FIXED_BYTES && SVB_TILED_FIXED_BYTES % 128 == 0, "SVB_TILED_FIXED_BYTES (svb_desc.h) must cover TiledSmem");
-enum { PLAN_SKIP = 0, PLAN_GENERIC = 1, PLAN_STAGED = 4, PLAN_STAGED_EDGE = 5 };  // >= PLAN_STAGED: boxes come by TMA
+enum { PLAN_SKIP = 0, PLAN_GENERIC = 1, PLAN_TABLE_RGBA = 2, PLAN_STAGED = 4, PLAN_STAGED_EDGE = 5 };  // >= PLAN_STAGED: boxes come by TMA
 
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, uint64_t* bar) {  // 16-byte granules
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
@@ -378,27 +370,19 @@ __device__ __forceinline__ void fast_layer(unsigned boxY, unsigned boxU, unsigne
 #endif
 }
 
-// MODE 2 and 3 out of line (edge tiles: one layer-tile in ten on the headline workload): their registers and instructions stay
-// out of the compositor's body, which then compiles without spills in its hot loops; the running picture crosses in a local
-// array like generic_layer's (48 local accesses against ~900 instructions of the layer).
-struct EdgeArgs {
-    unsigned boxY, boxU, boxV;
-    int iy0, jy0, ic0, jc0, pitchY, pitchC, stepC;
-    float alpha, onef;
-};
-template <int MODE>
-__device__ __noinline__ void edge_staged_layer(const EdgeArgs& a, const uint32_t* __restrict__ tabs, const FillTerms& ft, float* __restrict__ st) {
-    float2 Yi[4][2], Ui[2], Vi[2];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) Yi[r][0] = make_float2(st[4 * r], st[4 * r + 1]), Yi[r][1] = make_float2(st[4 * r + 2], st[4 * r + 3]);
-#pragma unroll
-    for (int k = 0; k < 2; ++k) Ui[k] = make_float2(st[16 + 2 * k], st[17 + 2 * k]), Vi[k] = make_float2(st[20 + 2 * k], st[21 + 2 * k]);
-    fast_layer<MODE, true, false>(a.boxY, a.boxU, a.boxV, tabs, (int)(threadIdx.x & 31), (int)(threadIdx.x >> 5), a.iy0, a.jy0, a.ic0, a.jc0, a.pitchY, a.pitchC, a.stepC, a.alpha, a.onef, ft,
-                               Yi, Ui, Vi);
+// The running picture of a thread as a local array (for the out-of-line layer bodies): st[0..15] luma, row-major over
+// columns (xt, xt+1, xt+64, xt+65); st[16..19] U texels, st[20..23] V texels.
+__device__ __forceinline__ void state_to_array(const float2 (&Yi)[4][2], const float2 (&Ui)[2], const float2 (&Vi)[2], float* __restrict__ st) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) st[4 * r] = Yi[r][0].x, st[4 * r + 1] = Yi[r][0].y, st[4 * r + 2] = Yi[r][1].x, st[4 * r + 3] = Yi[r][1].y;
 #pragma unroll
     for (int k = 0; k < 2; ++k) st[16 + 2 * k] = Ui[k].x, st[17 + 2 * k] = Ui[k].y, st[20 + 2 * k] = Vi[k].x, st[21 + 2 * k] = Vi[k].y;
+}
+__device__ __forceinline__ void array_to_state(const float* __restrict__ st, float2 (&Yi)[4][2], float2 (&Ui)[2], float2 (&Vi)[2]) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) Yi[r][0] = make_float2(st[4 * r], st[4 * r + 1]), Yi[r][1] = make_float2(st[4 * r + 2], st[4 * r + 3]);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) Ui[k] = make_float2(st[16 + 2 * k], st[17 + 2 * k]), Vi[k] = make_float2(st[20 + 2 * k], st[21 + 2 * k]);
 }
 
 // Any layer, any tile: the per-pixel evaluator of svb_device.cuh over this thread's 4x4 block.  Kept compact (one
@@ -418,6 +402,46 @@ __device__ __noinline__ void generic_layer(const SvbLayerDesc* __restrict__ L, i
         float oy, ou, ov;
         if (eval_pixel(U, s, x, yt + r, fW, fH, chroma, unorm_f(st[q]), chroma ? unorm_f(st[ci]) : 0.f, chroma ? unorm_f(st[ci + 4]) : 0.f, oy, ou,
                        ov)) {
+            st[q] = quantf(oy);
+            if (chroma) st[ci] = quantf(ou), st[ci + 4] = quantf(ov);
+        }
+    }
+}
+
+// A separable BGRA / RGBA layer (text and logo overlays: upright, any scale) over this thread's 4x4 block: the coordinate
+// chain comes from the layer's tables (two divisions and five dot products per pixel in the generic evaluator), the four
+// RGBA taps straight from global memory (L1/L2: neighbouring pixels share them), the arithmetic is rgba_pixel's.  Out of
+// line like generic_layer; 1.8x faster than it per RGBA picture-in-picture of the bench's geometry (profiles/r1_history.md).
+__device__ __noinline__ void rgba_table_layer(const SvbLayerDesc* __restrict__ L, const uint32_t* __restrict__ colblk, const uint32_t* __restrict__ rowblk, int xt, int yt,
+                                              int W, int H, float* __restrict__ st) {
+    const Src s = layer_src(L);
+    const float opacity = __ldg(&L->u.opacity);
+    const float4 fc = ldrow(L->u.fillColor, 0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Ent ce[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int x = 2 * lane + (c & 1) + (SVB_TILE_W / 2) * (c >> 1);  // tile-local columns 2l, 2l+1, 64+2l, 65+2l
+        ce[c] = unpack_ent(__ldg(colblk + x), __ldg(colblk + SVB_TILE_W + x));
+    }
+#pragma unroll 1
+    for (int r = 0; r < 4; ++r) {
+        if (yt + r >= H) break;
+        const Ent re = unpack_ent(__ldg(rowblk + 2 * (4 * warp + r)), __ldg(rowblk + 2 * (4 * warp + r) + 1));
+        if ((re.ok & 3) != 3) continue;  // the row lies outside the border rectangle or the picture's rectangle: untouched (kernels.cl.swift:77,509)
+        const float nb = sub(1.f, re.a);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int ok = ce[c].ok & re.ok;
+            if ((ok & 3) != 3 || xt + (c & 1) + (SVB_TILE_W / 2) * (c >> 1) >= W) continue;
+            const bool chroma = ((r | c) & 1) == 0;
+            const int q = 4 * r + c, ci = 16 + (r >> 1) * 2 + (c >> 1);
+            Taps k;
+            k.i0 = ce[c].i0, k.i1 = ce[c].i1, k.j0 = re.i0, k.j1 = re.i1;
+            const float na = sub(1.f, ce[c].a);
+            k.w00 = mul(na, nb), k.w10 = mul(ce[c].a, nb), k.w01 = mul(na, re.a), k.w11 = mul(ce[c].a, re.a);  // make_taps' weights
+            float oy, ou, ov;
+            rgba_pixel(s, opacity, fc, (ok & 4) != 0, k, unorm_f(st[q]), chroma ? unorm_f(st[ci]) : 0.f, chroma ? unorm_f(st[ci + 4]) : 0.f, oy, ou, ov);
             st[q] = quantf(oy);
             if (chroma) st[ci] = quantf(ou), st[ci + 4] = quantf(ov);
         }
@@ -457,8 +481,10 @@ __device__ __forceinline__ int plan_layer(const uint32_t* __restrict__ tables, c
     *covers = false;
     if (L->rect[0] >= x0 + SVB_TILE_W || L->rect[2] <= x0 || L->rect[1] >= y0 + SVB_TILE_H || L->rect[3] <= y0) {
         mode = PLAN_SKIP;
-    } else if (!(L->flags & SVB_LAYER_SEPARABLE) || (L->format != SVB_NV12 && L->format != SVB_Y420P)) {
+    } else if (!(L->flags & SVB_LAYER_SEPARABLE)) {
         mode = PLAN_GENERIC;
+    } else if (L->format != SVB_NV12 && L->format != SVB_Y420P) {
+        mode = PLAN_TABLE_RGBA;
     } else {
         // the table entries of the tile's first and last column / row, recomputed (the same functions fill the tables, in this
         // same launch: nothing to wait for)
@@ -484,6 +510,12 @@ __device__ __forceinline__ int plan_layer(const uint32_t* __restrict__ tables, c
     out[0] = make_int4(mode | (l << 8), iy0, jy0, ic0);
     out[1] = make_int4(jc0, (L->format << 8) | (L->flags & 0xff), L->box_w | (L->box_cw << 16), __float_as_int(L->u.opacity));
     out[2] = out[3] = out[4] = make_int4(0, 0, 0, 0);
+    if (mode == PLAN_TABLE_RGBA) {  // the tile's table blocks, read in place
+        const Tabs tb = layer_tabs(tables, F, l);
+        const unsigned long long cb = (unsigned long long)(tb.col + (x0 / SVB_TILE_W) * SVB_TAB_COL_WORDS), rb = (unsigned long long)(tb.row + (y0 / SVB_TILE_H) * SVB_TAB_ROW_WORDS);
+        out[3] = make_int4(0, 0, (int)(unsigned)cb, (int)(cb >> 32));
+        out[4] = make_int4((int)(unsigned)rb, (int)(rb >> 32), 0, g.frame);
+    }
     if (mode >= PLAN_STAGED) {
         const bool n12 = L->format == SVB_NV12;
         const int cbytes = n12 ? L->box_cw * L->box_ch * 2 : L->box_cw * L->box_ch;
@@ -553,7 +585,8 @@ extern "C" __global__ void __launch_bounds__(256) svb_mix_tables(const SvbFrameD
     const int l = (int)blockIdx.x / table_blocks;
     if (l >= F->nlayers) return;
     const SvbLayerDesc* __restrict__ L = &F->layers[l];
-    if (!(L->flags & SVB_LAYER_SEPARABLE) || (L->format != SVB_NV12 && L->format != SVB_Y420P)) return;
+    if (!(L->flags & SVB_LAYER_SEPARABLE)) return;
+    const bool yuv = L->format == SVB_NV12 || L->format == SVB_Y420P;  // BGRA / RGBA layers only use the luma-resolution entries
     const int W = F->width, H = F->height;
     const int ncy = F->tiles_x * SVB_TILE_W, ncc = ncy / 2, nry = F->tiles_y * SVB_TILE_H, nrc = nry / 2;
     int e = ((int)blockIdx.x % table_blocks) * (int)blockDim.x + (int)threadIdx.x;
@@ -564,12 +597,13 @@ extern "C" __global__ void __launch_bounds__(256) svb_mix_tables(const SvbFrameD
         const Ent t = ent_col_y(L, W, e);
         base[col_y_word(e)] = __float_as_uint(t.a), base[col_y_word(e) + SVB_TILE_W] = pack_ent(t);
     } else if ((e -= ncy) < ncc) {
+        if (!yuv) return;
         const Ent t = ent_col_c(L, W, e);
         base[col_c_word(e)] = __float_as_uint(t.a), base[col_c_word(e) + SVB_TILE_W / 2] = pack_ent(t);
     } else if ((e -= ncc) < nry) {
         const Ent t = ent_row_y(L, H, e);
         rbase[row_y_word(e)] = __float_as_uint(t.a), rbase[row_y_word(e) + 1] = pack_ent(t);
-    } else {
+    } else if (yuv) {
         e -= nry;
         const Ent t = ent_row_c(L, H, e);
         rbase[row_c_word(e)] = __float_as_uint(t.a), rbase[row_c_word(e) + 1] = pack_ent(t);
@@ -598,7 +632,7 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CT
     bool primed = false;  // this tile's first staged layer was already put in flight by the previous tile
     // Tiles are claimed two ahead by one lane (a global atomic whose latency nobody waits for); the same lane fetches the plan
     // of the CTA's next tile while the current one is computed.
-    const bool claimer = t == SVB_PLAN_WARP * 32;
+    const bool claimer = t == SVB_CLAIM_WARP * 32;
     int nclaimed = 0;
     auto claim = [&]() -> int {
         if (SVB_DYNAMIC_TILES) return atomicAdd(tile_counter, 1);
@@ -716,15 +750,7 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CT
             if (mode >= PLAN_STAGED) {
                 const int4 p1 = plan[i][1];
                 const int jc0 = p1.x;
-#if SVB_SPLIT_BARRIER
-                // only the warp that refills the other buffer has to know that every warp is past its reads of it: it waits on a named
-                // barrier (two, alternating with the buffers, so that a warp one layer ahead never arrives twice in one phase), the
-                // other warps arrive and go on to their data
-                if (warp == 0) asm volatile("barrier.sync %0, %1;" ::"r"(1 + stage), "n"(SVB_TILED_THREADS) : "memory");
-                else asm volatile("barrier.arrive %0, %1;" ::"r"(1 + stage), "n"(SVB_TILED_THREADS) : "memory");
-#else
                 __syncthreads();  // every warp is past its reads of the other buffer
-#endif
                 if (t == 0) {  // refill the other buffer: the next staged layer of this tile, else the first one of the next tile
                     const int j = first_staged(plan, i + 1, nact);
                     if (j >= 0) {
@@ -764,24 +790,11 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CT
                         for (int r = 0; r < 4; ++r) mixed = mixed || odd(tb[SVB_TAB_COL_WORDS + 2 * (4 * warp + r) + 1]);
 #pragma unroll
                         for (int k = 0; k < 2; ++k) mixed = mixed || odd(tb[SVB_TAB_COL_WORDS + 2 * SVB_TILE_H + 2 * (2 * warp + k) + 1]);
-                        const bool lean = SVB_LEAN_EDGE && (lflags & SVB_LAYER_OPACITY_01) && !__any_sync(__activemask(), mixed);
-#if SVB_EDGE_INLINE
+                        const bool lean = (lflags & SVB_LAYER_OPACITY_01) && !__any_sync(__activemask(), mixed);
+                        // (both inlined: called out of line, with the running picture through a local array, the edge bodies cost 8 % of
+                        // the whole kernel although edge tiles are one layer-tile in ten -- profiles/r1_history.md)
                         if (lean) fast_layer<2, true, false>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
                         else fast_layer<3, true, false>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
-#else
-                        float st[24];
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) st[4 * r] = Yi[r][0].x, st[4 * r + 1] = Yi[r][0].y, st[4 * r + 2] = Yi[r][1].x, st[4 * r + 3] = Yi[r][1].y;
-#pragma unroll
-                        for (int k = 0; k < 2; ++k) st[16 + 2 * k] = Ui[k].x, st[17 + 2 * k] = Ui[k].y, st[20 + 2 * k] = Vi[k].x, st[21 + 2 * k] = Vi[k].y;
-                        const EdgeArgs ea = {bY, bU, bV, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one};
-                        if (lean) edge_staged_layer<2>(ea, sm.tabs[stage], ft, st);
-                        else edge_staged_layer<3>(ea, sm.tabs[stage], ft, st);
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) Yi[r][0] = make_float2(st[4 * r], st[4 * r + 1]), Yi[r][1] = make_float2(st[4 * r + 2], st[4 * r + 3]);
-#pragma unroll
-                        for (int k = 0; k < 2; ++k) Ui[k] = make_float2(st[16 + 2 * k], st[17 + 2 * k]), Vi[k] = make_float2(st[20 + 2 * k], st[21 + 2 * k]);
-#endif
                     } else if (lflags & SVB_LAYER_UNIT_OPACITY) {
                         if (fmt == SVB_NV12) fast_layer<0, true, true>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
                         else fast_layer<0, true, false>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
@@ -791,17 +804,17 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CT
                     }
                 }
                 stage ^= 1;
-            } else if (live) {  // PLAN_GENERIC
+            } else if (live) {  // PLAN_GENERIC / PLAN_TABLE_RGBA: no staging, out of line
                 float st[24];
-#pragma unroll
-                for (int r = 0; r < 4; ++r) st[4 * r] = Yi[r][0].x, st[4 * r + 1] = Yi[r][0].y, st[4 * r + 2] = Yi[r][1].x, st[4 * r + 3] = Yi[r][1].y;
-#pragma unroll
-                for (int k = 0; k < 2; ++k) st[16 + 2 * k] = Ui[k].x, st[17 + 2 * k] = Ui[k].y, st[20 + 2 * k] = Vi[k].x, st[21 + 2 * k] = Vi[k].y;
-                generic_layer(&F->layers[p0.x >> 8], xt, yt, (float)W, (float)H, W, H, st);
-#pragma unroll
-                for (int r = 0; r < 4; ++r) Yi[r][0] = make_float2(st[4 * r], st[4 * r + 1]), Yi[r][1] = make_float2(st[4 * r + 2], st[4 * r + 3]);
-#pragma unroll
-                for (int k = 0; k < 2; ++k) Ui[k] = make_float2(st[16 + 2 * k], st[17 + 2 * k]), Vi[k] = make_float2(st[20 + 2 * k], st[21 + 2 * k]);
+                state_to_array(Yi, Ui, Vi, st);
+                if (mode == PLAN_TABLE_RGBA) {
+                    const int4 p3 = plan[i][3], p4 = plan[i][4];
+                    rgba_table_layer(&F->layers[p0.x >> 8], (const uint32_t*)(((unsigned long long)(unsigned)p3.w << 32) | (unsigned)p3.z),
+                                     (const uint32_t*)(((unsigned long long)(unsigned)p4.y << 32) | (unsigned)p4.x), xt, yt, W, H, st);
+                } else {
+                    generic_layer(&F->layers[p0.x >> 8], xt, yt, (float)W, (float)H, W, H, st);
+                }
+                array_to_state(st, Yi, Ui, Vi);
             }
         }
 

@@ -11,10 +11,7 @@
 #define SVB_TILE_H 32
 #endif
 #define SVB_TILED_COMPUTE_WARPS (SVB_TILE_H / 4)              // a warp covers 128 columns x 4 rows
-#ifndef SVB_PRODUCER_WARP
-#define SVB_PRODUCER_WARP 0  // 1: a ninth warp plans tiles and issues TMA (costs registers: 9 warps x 2 CTAs cap the kernel at 96)
-#endif
-#define SVB_TILED_THREADS (SVB_TILED_COMPUTE_WARPS * 32 + 32 * SVB_PRODUCER_WARP)
+#define SVB_TILED_THREADS (SVB_TILED_COMPUTE_WARPS * 32)
 // largest source footprint the tiled kernel stages in shared memory per tile and layer
 #ifndef SVB_BOX_Y_BYTES
 #define SVB_BOX_Y_BYTES (SVB_TILE_H * 640)

@@ -135,6 +135,34 @@ struct Src {
     int format;
 };
 
+// img_{bgra,rgba}_{nv12,y420p} for a pixel inside the picture's rectangle (kernels.cl.swift:509-528): the fill colour is
+// blended first, always; then, where uv is inside [0,1], the sampled pixel, premultiplied by a = alpha * opacity before the
+// colour matrix and blended with weight a again -- as written upstream.  `k` is only read when in_uv.
+__device__ __forceinline__ void rgba_pixel(const Src& s, float opacity, const float4 fc, bool in_uv, const Taps& k, float cy, float cu, float cv, float& oy,
+                                           float& ou, float& ov) {
+    const float a = mul(opacity, fc.w), na = sub(1.f, a);
+    const float3 f = rgb2yuv(mul(fc.x, a), mul(fc.y, a), mul(fc.z, a));
+    float r0 = add(mul(cy, na), mul(f.x, a));
+    float r1 = clampf(add(mul(cu, na), mul(f.y, a)), -1.f, 1.f);
+    float r2 = clampf(add(mul(cv, na), mul(f.z, a)), -1.f, 1.f);
+    if (in_uv) {
+        float4 px = sample4(s.p[0], s.stride[0], k);
+        if (s.format == SVB_BGRA) {
+            float t = px.x;
+            px.x = px.z;
+            px.z = t;
+        }
+        const float a2 = mul(px.w, opacity), n2 = sub(1.f, a2);
+        const float3 q = rgb2yuv(mul(px.x, a2), mul(px.y, a2), mul(px.z, a2));
+        r0 = add(mul(r0, n2), mul(q.x, a2));
+        r1 = add(mul(r1, n2), mul(q.y, a2));
+        r2 = add(mul(r2, n2), mul(q.z, a2));
+    }
+    oy = r0;
+    ou = r1;
+    ov = r2;
+}
+
 // One work-item of img_<src>_<dst> on luma pixel (x,y) of a WxH target.
 //   cy/cu/cv : current target values as UNORM floats (cu/cv only meaningful when `chroma`)
 //   returns false when the pixel is left untouched; otherwise oy (and ou/ov when `chroma`) hold the
@@ -188,28 +216,9 @@ __device__ __forceinline__ bool eval_pixel(const ImageUniforms* __restrict__ U, 
     }
     // BGRA / RGBA sources
     if (!in_tx) return false;
-    const float a = mul(opacity, fc.w), na = sub(1.f, a);
-    const float3 f = rgb2yuv(mul(fc.x, a), mul(fc.y, a), mul(fc.z, a));
-    float r0 = add(mul(cy, na), mul(f.x, a));
-    float r1 = clampf(add(mul(cu, na), mul(f.y, a)), -1.f, 1.f);
-    float r2 = clampf(add(mul(cv, na), mul(f.z, a)), -1.f, 1.f);
-    if (in_uv) {
-        Taps k = make_taps(uu, vv, s.w, s.h);
-        float4 px = sample4(s.p[0], s.stride[0], k);
-        if (s.format == SVB_BGRA) {
-            float t = px.x;
-            px.x = px.z;
-            px.z = t;
-        }
-        const float a2 = mul(px.w, opacity), n2 = sub(1.f, a2);
-        const float3 q = rgb2yuv(mul(px.x, a2), mul(px.y, a2), mul(px.z, a2));
-        r0 = add(mul(r0, n2), mul(q.x, a2));
-        r1 = add(mul(r1, n2), mul(q.y, a2));
-        r2 = add(mul(r2, n2), mul(q.z, a2));
-    }
-    oy = r0;
-    ou = r1;
-    ov = r2;
+    Taps k = {};
+    if (in_uv) k = make_taps(uu, vv, s.w, s.h);
+    rgba_pixel(s, opacity, fc, in_uv, k, cy, cu, cv, oy, ou, ov);
     return true;
 }
 
