@@ -66,7 +66,23 @@ def max_over_ranks(ms, world, dist=None, device=None):
 
 def geometry():
     import scenes
+    if CANVAS == (1280, 720):  # cfg 2: one 1080p picture over the whole 720p canvas
+        return [((1920, 1080), (0, 0), (1280, 720), 1.0)]
     return scenes.cfg34_geometry(NLAYERS)
+
+
+def configure_workload(name):
+    """The headline is cfg 4; cfg 3 and cfg 2 (BASELINE.md's other compositor rows) run through the same code as side workloads."""
+    global CANVAS, NLAYERS, ALG_BYTES_PER_FRAME, WORKLOAD
+    if name == "cfg3":
+        CANVAS, NLAYERS = (3840, 2160), 4
+        ALG_BYTES_PER_FRAME = 12441600 + 3 * 3110400 + 12441600
+        WORKLOAD = (f"cfg3 (side workload, not the headline): 3840x2160 NV12 target, 4 NV12 layers (1x 3840x2160 full canvas + 3x 1920x1080 -> 1600x900), {STREAMS_PER_GPU} streams per GPU")
+    elif name == "cfg2mix":
+        CANVAS, NLAYERS = (1280, 720), 1
+        ALG_BYTES_PER_FRAME = 3110400 + 1382400
+        WORKLOAD = (f"cfg2 (side workload, not the headline): 1280x720 NV12 target, one 1920x1080 NV12 picture over the whole canvas (clear + img_nv12_nv12), {STREAMS_PER_GPU} streams per GPU "
+                    "-- 36 MB per step: FITS in the 126 MB L2")
 
 
 def peaks():
@@ -187,6 +203,7 @@ def run_ours(args):
     geo = geometry()
     S = STREAMS_PER_GPU
     rng_base = 1000 * 4
+    yuv_fmt = sv.Y420P if args.format == "y420p" else sv.NV12  # same bytes per picture; y420p is what SwiftVideo composes on Linux (composer.swift:52-56)
 
     # ---- synthetic layers: pinned host pictures (e2e source) and two device copies (device-resident source)
     host = [[None] * NLAYERS for _ in range(S)]
@@ -198,13 +215,13 @@ def run_ours(args):
                 op = args.pip_opacity
             rng = np.random.default_rng(rng_base + 16 * gstream + k)
             rgba = k >= NLAYERS - args.rgba_pips  # side experiment: the topmost pictures-in-picture as RGBA overlays (text / logo layers)
-            h = sv.create_picture_sample(ssz[0], ssz[1], sv.RGBA if rgba else sv.NV12, f"s{gstream}l{k}", "bench", pinned_from=ctx)
+            h = sv.create_picture_sample(ssz[0], ssz[1], sv.RGBA if rgba else yuv_fmt, f"s{gstream}l{k}", "bench", pinned_from=ctx)
             h.set_host_bytes(rng.integers(0, 256, size=ssz[0] * ssz[1] * (4 if rgba else 1) * (2 if rgba else 3) // 2, dtype=np.uint8))
             # PictureAnimator.impl in native code: matrix = ortho(canvas) * T(pos) * S(size), opacity = 1 - transparency
             host[s][k] = h.animate(CANVAS, (pos[0], pos[1], float(k)), dsz, transparency=1.0 - op)
             for c in range(2):
                 dev[c][s][k] = host[s][k].upload(ctx)
-    mixers = [sv.VideoMixer(ctx, CANVAS[0], CANVAS[1], sv.NV12, asset_id=f"mixer{rank * S + s}", workspace_id="bench") for s in range(S)]
+    mixers = [sv.VideoMixer(ctx, CANVAS[0], CANVAS[1], yuv_fmt, asset_id=f"mixer{rank * S + s}", workspace_id="bench") for s in range(S)]
     mode = {"fused": sv.MixMode.FUSED, "generic": sv.MixMode.GENERIC, "per_layer": sv.MixMode.PER_LAYER}[args.mode]
     for m in mixers:
         m.set_mode(mode)
@@ -272,8 +289,8 @@ def run_ours(args):
     e_ms, _, e_host_ms = timed(step_e2e, e2e_steps, max(3, min(args.warmup, 3)))
     clocks = sampler.stop()
     e2e_value = S * world * e2e_steps / (e_ms / 1e3)
-    h2d = S * (12441600 + 7 * 3110400)
-    d2h = S * 12441600
+    h2d = S * sum(ssz[0] * ssz[1] * 3 // 2 for ssz, _, _, _ in geo)
+    d2h = S * CANVAS[0] * CANVAS[1] * 3 // 2
 
     link = measure_link(torch, torch.device("cuda", local))
     # both directions run at once (separate copy engines); indicative only -- the H2D rate of one big copy varies run to run (39-53 GB/s seen)
@@ -300,9 +317,13 @@ def run_ours(args):
         "ms_per_step": round(ms / args.steps, 4), "host_queue_ms_per_step": round(host_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8 (fp32 arithmetic, no FMA contraction)", "data": "synthetic (uniform u8 planes, seeded)",
         "config": {"workload": (WORKLOAD if args.pip_opacity is None else WORKLOAD + f" -- NOT the headline: picture-in-picture opacity forced to {args.pip_opacity}") +
-                               (f" -- NOT the headline: the top {args.rgba_pips} pictures-in-picture are RGBA overlays" if args.rgba_pips else ""), "mode": args.mode, "streams_total": S * world, "frames_per_step": S * world, "parallelism": f"streams sharded, {S}/GPU, no collective", "host_affinity": numa,
-                   "l2": "373 MB of distinct sources+targets per step (> 126 MB L2); sources alternate between two device copies",
-                   "bit_exact_vs_oracle": "tests/test_gpu_parity.py::test_cfg34_full_size"},
+                               (f" -- NOT the headline: the top {args.rgba_pips} pictures-in-picture are RGBA overlays" if args.rgba_pips else "") +
+                               (" -- NOT the headline: YUV420P layers and target instead of NV12" if args.format == "y420p" else ""), "mode": args.mode, "streams_total": S * world, "frames_per_step": S * world, "parallelism": f"streams sharded, {S}/GPU, no collective", "host_affinity": numa,
+                   "l2": (f"{ALG_BYTES_PER_FRAME * S / 1e6:.0f} MB of distinct sources+targets per step (> 126 MB L2); sources alternate between two device copies"
+                          if ALG_BYTES_PER_FRAME * S > 126e6 else
+                          f"{ALG_BYTES_PER_FRAME * S / 1e6:.0f} MB of distinct sources+targets per step: FITS in the 126 MB L2; sources alternate between two device copies "
+                          f"({2 * ALG_BYTES_PER_FRAME * S / 1e6:.0f} MB over two steps)"),
+                   "bit_exact_vs_oracle": "tests/test_gpu_parity.py::test_cfg2_full_size" if CANVAS == (1280, 720) else "tests/test_gpu_parity.py::test_cfg34_full_size"},
         "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "ms_per_step": round(e_ms / e2e_steps, 4), "host_queue_ms_per_step": round(e_host_ms / e2e_steps, 4), "host_link": link},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
@@ -442,7 +463,7 @@ def run_scale(args):
 def cpu_scene():
     import scenes
     from oracle import oracle as O
-    canvas, tf, layers, us = scenes.cfg34_scene(NLAYERS)
+    canvas, tf, layers, us = scenes.cfg2_scene() if CANVAS == (1280, 720) else scenes.cfg34_scene(NLAYERS)
     return O.Image(tf, canvas[0], canvas[1]), layers, us
 
 
@@ -547,12 +568,16 @@ def main():
     ap.add_argument("--pip-opacity", type=float, default=None,
                     help="side experiment, not the headline: opacity of layers 1..7 (1.0 = opaque pictures, which let the planner skip "
                          "whatever they cover)")
+    ap.add_argument("--format", default="nv12", choices=["nv12", "y420p"], help="side experiment, not the headline: y420p layers and target (the Linux Composer's format)")
     ap.add_argument("--rgba-pips", type=int, default=0, help="side experiment, not the headline: the topmost N pictures-in-picture are RGBA overlays")
-    ap.add_argument("--workload", default="cfg4", choices=["cfg4", "cfg5", "cfg2"],
-                    help="cfg4 (default) = the headline; cfg5 / cfg2 = the convert+scale operator's side workloads (1 GPU, our arm only)")
+    ap.add_argument("--workload", default="cfg4", choices=["cfg4", "cfg3", "cfg2mix", "cfg5", "cfg2"],
+                    help="cfg4 (default) = the headline; cfg3 / cfg2mix = BASELINE.md's other compositor rows through the same code; "
+                         "cfg5 / cfg2 = the convert+scale operator's side workloads (1 GPU, our arm only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    if args.workload != "cfg4" and args.impl == "ours":
+    if args.workload in ("cfg3", "cfg2mix"):
+        configure_workload(args.workload)
+    if args.workload in ("cfg5", "cfg2") and args.impl == "ours":
         run_scale(args)
     elif args.impl == "reference":
         run_reference(args)
