@@ -41,8 +41,11 @@ def test_module_image_has_the_reference_entry_points():
     img = sv.kernel_module_image()
     assert img[:4] == b"\x7fELF"
     for n in ("img_clear_nv12", "img_clear_y420p", "img_clear_bgra", "img_nv12_nv12", "img_y420p_nv12", "img_y420p_y420p",
-              "img_bgra_nv12", "img_rgba_nv12", "img_bgra_y420p", "img_rgba_y420p", "svb_mix_tiled", "svb_mix_generic"):
+              "img_bgra_nv12", "img_rgba_nv12", "img_bgra_y420p", "img_rgba_y420p", "svb_mix_tiled", "svb_mix_tables", "svb_mix_generic",
+              "svb_scale_convert"):
         assert n.encode() in img
+    # upstream has no img_bgra_bgra on Linux (compute.swift:54 names it, only a half-written Metal body exists): neither have we
+    assert b"img_bgra_bgra" not in img
 
 
 def test_picture_layouts():
@@ -58,9 +61,17 @@ def test_picture_layouts():
             assert (int(pl.width), int(pl.height), pl.stride, pl.components, pl.bit_depth) == (w, h, stride, nc, 8)
             assert pl.host - base == off
         assert i.buffer_type == api.BUFFER_CPU and list(i.fill_color) == [0, 0, 0, 1] and i.opacity == 1.0
+    # P010 (ours): NV12's plane shapes, two bytes per component, ten significant bits
+    i = sv.create_picture_sample(64, 36, sv.P010, "a", "w").info()
+    assert i.plane_count == 2 and i.pixel_format == sv.P010
+    assert [(int(pl.width), int(pl.height), pl.stride, pl.components, pl.bit_depth) for pl in (i.planes[0], i.planes[1])] == [(64, 36, 128, 1, 10), (32, 18, 128, 2, 10)]
+    assert i.planes[1].host - i.planes[0].host == 128 * 36
     with pytest.raises(sv.ComputeError) as e:
         sv.create_picture_sample(0, 10, sv.NV12)
     assert e.value.name == "invalidOperation"
+    with pytest.raises(sv.ComputeError) as e:
+        sv.create_picture_sample(16, 16, 13)  # past the last pixel format
+    assert e.value.name == "badInputData"
     with pytest.raises(sv.ComputeError) as e:
         sv.create_picture_sample(16, 16, api.Y444P)
     assert e.value.name == "badInputData"

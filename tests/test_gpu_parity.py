@@ -114,6 +114,34 @@ def test_cfg34_full_size(nlayers):
         assert (outs[mname] == want.data).all(), f"{case.name}/{mname}: {first_diff(outs[mname], want.data)}"
 
 
+def test_cfg4_variants_full_size():
+    """cfg 4's geometry at 3840x2160 in the two variants bench.py offers beside the headline: (1) YUV420P layers and target -- the
+    format SwiftVideo composes in on Linux (composer.swift:52-56); (2) the two topmost pictures-in-picture as RGBA / BGRA overlays
+    with per-pixel alpha, which take the table-driven RGBA body of the tiled kernel.  Fused path against the oracle, bytes."""
+    ctx = context()
+    canvas = (3840, 2160)
+    geo = scenes.cfg34_geometry(8)
+    # (1) planar
+    layers = [scenes.random_image(O.Y420P, ssz[0], ssz[1], scenes.cfg_seed(4, 1, k)) for k, (ssz, _, _, _) in enumerate(geo)]
+    us = [scenes.layer_uniforms(canvas, ssz, pos, dsz, z=float(k + 1), opacity=op) for k, (ssz, pos, dsz, op) in enumerate(geo)]
+    case = scenes.Case("cfg4_y420p", O.Y420P, canvas, layers, us)
+    rc, want = scenes.run_case(O.port(), case, threads=O.host_threads())
+    assert rc == 0
+    got = gpu_case(ctx, case, sv.MixMode.FUSED)
+    assert (got == want.data).all(), f"cfg4_y420p: {first_diff(got, want.data)}"
+    # (2) RGBA / BGRA overlays on an NV12 stack (4 layers keep the oracle's time down)
+    geo = scenes.cfg34_geometry(8)[:2] + scenes.cfg34_geometry(8)[5:7]
+    fmts = [O.NV12, O.NV12, O.RGBA, O.BGRA]
+    layers = [scenes.random_image(f, ssz[0], ssz[1], scenes.cfg_seed(4, 2, k)) for k, (f, (ssz, _, _, _)) in enumerate(zip(fmts, geo))]
+    us = [scenes.layer_uniforms(canvas, ssz, pos, dsz, z=float(k + 1), opacity=op) for k, (ssz, pos, dsz, op) in enumerate(geo)]
+    case = scenes.Case("cfg4_rgba_overlays", O.NV12, canvas, layers, us)
+    rc, want = scenes.run_case(O.port(), case, threads=O.host_threads())
+    assert rc == 0
+    for mode, mname in MODES:
+        got = gpu_case(ctx, case, mode)
+        assert (got == want.data).all(), f"cfg4_rgba_overlays/{mname}: {first_diff(got, want.data)}"
+
+
 def test_properties_full_size():
     """Size-independent properties at 4K: (1) an opaque full-canvas top layer hides everything below it;
     (2) composing twice gives the same bytes (no state leaks between launches); (3) opacity 0 leaves the clear."""
