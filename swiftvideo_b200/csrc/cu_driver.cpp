@@ -54,6 +54,8 @@ static void load() {
     SVB_CU_FN(cuFuncSetAttribute)
     SVB_CU_FN(cuFuncGetAttribute)
     SVB_CU_FN(cuOccupancyMaxActiveBlocksPerMultiprocessor)
+    SVB_CU_FN(cuTexObjectCreate)
+    SVB_CU_FN(cuTexObjectDestroy)
     SVB_CU_FN(cuLaunchKernel)
     SVB_CU_FN(cuStreamCreate)
     SVB_CU_FN(cuStreamDestroy)

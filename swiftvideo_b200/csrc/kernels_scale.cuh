@@ -21,11 +21,6 @@
 
 namespace svb {
 
-__device__ __forceinline__ unsigned ldg_u16(const uint8_t* p) {
-    unsigned v;
-    asm volatile("ld.global.nc.u16 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
 __device__ __forceinline__ unsigned ldg_u32(const uint8_t* p) {
     unsigned v;
     asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));

@@ -388,11 +388,11 @@ __device__ __forceinline__ void array_to_state(const float* __restrict__ st, flo
 // Any layer, any tile: the per-pixel evaluator of svb_device.cuh over this thread's 4x4 block.  Kept compact (one
 // copy of the evaluator, pixels in a rolled loop over a local copy of the block) so that it does not crowd the
 // instruction cache of the fast path; rotated layers, BGRA/RGBA sources and footprints too large to stage come here.
-__device__ __noinline__ void generic_layer(const SvbLayerDesc* __restrict__ L, int xt, int yt, float fW, float fH, int W, int H, float* __restrict__ st) {
+__device__ __noinline__ void generic_layer(const SvbLayerDesc* __restrict__ L, int xt, int yt, float fW, float fH, int W, int H, float* __restrict__ st, int rows = 4) {
     const Src s = layer_src(L);
     const SvbUniforms* __restrict__ U = &L->u;
 #pragma unroll 1
-    for (int q = 0; q < 16; ++q) {
+    for (int q = 0; q < 4 * rows; ++q) {
         const int r = q >> 2, c = q & 3;
         if (yt + r >= H) break;
         const int x = xt + (c & 1) + (SVB_TILE_W / 2) * (c >> 1);  // columns xt, xt+1, xt+64, xt+65
@@ -413,11 +413,11 @@ __device__ __noinline__ void generic_layer(const SvbLayerDesc* __restrict__ L, i
 // RGBA taps straight from global memory (L1/L2: neighbouring pixels share them), the arithmetic is rgba_pixel's.  Out of
 // line like generic_layer; 1.8x faster than it per RGBA picture-in-picture of the bench's geometry (profiles/r1_history.md).
 __device__ __noinline__ void rgba_table_layer(const SvbLayerDesc* __restrict__ L, const uint32_t* __restrict__ colblk, const uint32_t* __restrict__ rowblk, int xt, int yt,
-                                              int W, int H, float* __restrict__ st) {
+                                              int W, int H, float* __restrict__ st, int strip, int rows = 4) {  // strip: which `rows`-row strip of the tile this warp owns
     const Src s = layer_src(L);
     const float opacity = __ldg(&L->u.opacity);
     const float4 fc = ldrow(L->u.fillColor, 0);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = strip;
     Ent ce[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -425,9 +425,9 @@ __device__ __noinline__ void rgba_table_layer(const SvbLayerDesc* __restrict__ L
         ce[c] = unpack_ent(__ldg(colblk + x), __ldg(colblk + SVB_TILE_W + x));
     }
 #pragma unroll 1
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < rows; ++r) {
         if (yt + r >= H) break;
-        const Ent re = unpack_ent(__ldg(rowblk + 2 * (4 * warp + r)), __ldg(rowblk + 2 * (4 * warp + r) + 1));
+        const Ent re = unpack_ent(__ldg(rowblk + 2 * (rows * warp + r)), __ldg(rowblk + 2 * (rows * warp + r) + 1));
         if ((re.ok & 3) != 3) continue;  // the row lies outside the border rectangle or the picture's rectangle: untouched (kernels.cl.swift:77,509)
         const float nb = sub(1.f, re.a);
 #pragma unroll
@@ -504,7 +504,10 @@ __device__ __forceinline__ int plan_layer(const uint32_t* __restrict__ tables, c
         // i1 - i0 is 0 only where the tap index was clamped, and the unclamped index is monotone: the ends decide for the tile.
         // The interior layer bodies (MODE 0 / 1) address the second tap of a row as "first + 1".
         const bool xfree = cA.i1 != cA.i0 && cB.i1 != cB.i0 && ccA.i1 != ccA.i0 && ccB.i1 != ccB.i0;
-        mode = !((L->flags & SVB_LAYER_STAGED) && fits) ? PLAN_GENERIC : (full && xfree ? PLAN_STAGED : PLAN_STAGED_EDGE);
+        if (F->flags & SVB_FRAME_GATHER)  // texture path: nothing is staged and the unit clamps, so only inside / edge matters
+            mode = !(L->flags & SVB_LAYER_TEX) ? PLAN_GENERIC : (full ? PLAN_STAGED : PLAN_STAGED_EDGE);
+        else
+            mode = !((L->flags & SVB_LAYER_STAGED) && fits) ? PLAN_GENERIC : (full && xfree ? PLAN_STAGED : PLAN_STAGED_EDGE);
         *covers = full && (L->flags & SVB_LAYER_UNIT_OPACITY);
     }
     out[0] = make_int4(mode | (l << 8), iy0, jy0, ic0);
@@ -810,7 +813,7 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CT
                 if (mode == PLAN_TABLE_RGBA) {
                     const int4 p3 = plan[i][3], p4 = plan[i][4];
                     rgba_table_layer(&F->layers[p0.x >> 8], (const uint32_t*)(((unsigned long long)(unsigned)p3.w << 32) | (unsigned)p3.z),
-                                     (const uint32_t*)(((unsigned long long)(unsigned)p4.y << 32) | (unsigned)p4.x), xt, yt, W, H, st);
+                                     (const uint32_t*)(((unsigned long long)(unsigned)p4.y << 32) | (unsigned)p4.x), xt, yt, W, H, st, warp);
                 } else {
                     generic_layer(&F->layers[p0.x >> 8], xt, yt, (float)W, (float)H, W, H, st);
                 }

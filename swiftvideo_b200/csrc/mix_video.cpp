@@ -23,6 +23,9 @@ namespace {
 
 constexpr int kSegments = 8;     // batches in flight before the host has to wait for the oldest
 constexpr int kSegFrames = 64;   // frame descriptors per batch
+#ifndef SVB_DEFAULT_GATHER
+#define SVB_DEFAULT_GATHER 0     // which fused compositor runs unless SVB_COMPOSITOR says otherwise: 0 = svb_mix_tiled (TMA), 1 = svb_mix_gather
+#endif
 
 struct MixerShared {
     uint8_t* host = nullptr;  // pinned staging, kSegments * kSegFrames descriptors
@@ -38,7 +41,10 @@ struct MixerShared {
     size_t tabBytes[kSegments] = {};
     int next = 0;
     std::map<std::array<uint64_t, 4>, std::array<uint8_t, 128>> tmaps;
-    CUfunction fTiled = nullptr, fGeneric = nullptr, fTables = nullptr;
+    CUfunction fTiled = nullptr, fGather = nullptr, fGeneric = nullptr, fTables = nullptr;
+    int gatherCtasPerSm = 0;
+    int texAlign = 512, texPitchAlign = 32;
+    std::map<std::array<uint64_t, 3>, CUtexObject> texs;  // texture objects over source planes by (pointer, size, pitch | channels)
     std::map<size_t, int> tiledCtasPerSm;  // resident CTAs of svb_mix_tiled per SM by dynamic shared memory size: the persistent grid is smCount times this
     std::mutex mu;
     // optional per-launch device timing of the fused kernels (bench.py's roofline leg)
@@ -71,6 +77,7 @@ void freeShared(InternalContext* ic) {
         if (e) cu().cuEventDestroy(e);
     for (CUdeviceptr b : s->tabBuf)
         if (b) cu().cuMemFree(b);
+    for (auto& kv : s->texs) cu().cuTexObjectDestroy(kv.second);
     if (s->prep) cu().cuStreamDestroy(s->prep);
     for (auto* v : {&s->timed, &s->spare})
         for (auto& pr : *v) {
@@ -97,6 +104,16 @@ MixerShared& shared(const std::shared_ptr<InternalContext>& ic) {  // caller hol
         check(drv().cuFuncSetAttribute(s->fTiled, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, SVB_TILED_SMEM_MAX),
               "cuFuncSetAttribute(max dynamic shared memory)");
         s->fTables = ic->builtin("svb_mix_tables");
+        s->fGather = ic->builtin("svb_mix_gather");
+        {
+            int n = 0;
+            check(drv().cuOccupancyMaxActiveBlocksPerMultiprocessor(&n, s->fGather, SVB_TILED_THREADS, 0), "cuOccupancyMaxActiveBlocksPerMultiprocessor");
+            s->gatherCtasPerSm = std::max(1, n);
+            drv().cuDeviceGetAttribute(&s->texAlign, CU_DEVICE_ATTRIBUTE_TEXTURE_ALIGNMENT, ic->device);
+            drv().cuDeviceGetAttribute(&s->texPitchAlign, CU_DEVICE_ATTRIBUTE_TEXTURE_PITCH_ALIGNMENT, ic->device);
+            if (s->texAlign <= 0) s->texAlign = 512;
+            if (s->texPitchAlign <= 0) s->texPitchAlign = 32;
+        }
         s->fGeneric = ic->builtin("svb_mix_generic");
     }
     return *(MixerShared*)ic->mixerShared;
@@ -146,6 +163,38 @@ bool tensorMap(MixerShared& sh, unsigned char out[128], CUdeviceptr ptr, int ele
     }
     std::memcpy(out, it->second.data(), 128);
     return true;
+}
+
+// A texture object over one source plane for svb_mix_gather: 8-bit channels read as UNORM floats, unnormalised coordinates,
+// clamp addressing (the OpenCL sampler's CLAMP_TO_EDGE, kernels.cl.swift:61).  0 when the plane cannot be bound (base or pitch
+// alignment).  Cached by pointer and shape: the device pool recycles blocks, so the same few planes come round.
+CUtexObject textureObject(MixerShared& sh, CUdeviceptr ptr, int channels, int w, int h, int pitchBytes) {
+    if (!ptr || w <= 0 || h <= 0 || (ptr % (CUdeviceptr)sh.texAlign) || (pitchBytes % sh.texPitchAlign) || pitchBytes < w * channels) return 0;
+    const std::array<uint64_t, 3> key = {(uint64_t)ptr, ((uint64_t)(uint32_t)w << 32) | (uint32_t)h, ((uint64_t)(uint32_t)pitchBytes << 8) | (uint32_t)channels};
+    auto it = sh.texs.find(key);
+    if (it != sh.texs.end()) return it->second;
+    CUDA_RESOURCE_DESC rd;
+    std::memset(&rd, 0, sizeof(rd));
+    rd.resType = CU_RESOURCE_TYPE_PITCH2D;
+    rd.res.pitch2D.devPtr = ptr;
+    rd.res.pitch2D.format = CU_AD_FORMAT_UNSIGNED_INT8;
+    rd.res.pitch2D.numChannels = (unsigned)channels;
+    rd.res.pitch2D.width = (size_t)w;
+    rd.res.pitch2D.height = (size_t)h;
+    rd.res.pitch2D.pitchInBytes = (size_t)pitchBytes;
+    CUDA_TEXTURE_DESC td;
+    std::memset(&td, 0, sizeof(td));
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = CU_TR_ADDRESS_MODE_CLAMP;
+    td.filterMode = CU_TR_FILTER_MODE_POINT;  // tex2Dgather fetches the footprint; the filter runs in fp32 in the kernel
+    td.flags = 0;                             // UNORM8 -> float in the unit, unnormalised coordinates
+    CUtexObject obj = 0;
+    if (drv().cuTexObjectCreate(&obj, &rd, &td, nullptr) != CUDA_SUCCESS) return 0;
+    if (sh.texs.size() > 4096) {  // bounded: a cleared entry is simply created again
+        for (auto& kv : sh.texs) cu().cuTexObjectDestroy(kv.second);
+        sh.texs.clear();
+    }
+    sh.texs.emplace(key, obj);
+    return obj;
 }
 
 // Canvas rectangle outside which `border` cannot land in [0,1]^2: the unit square pushed through the forward
@@ -258,6 +307,16 @@ FramePlan planFrame(const ComputeContext& ctx, const PictureSample& target, cons
                 L.box_w = bw, L.box_h = bh, L.box_cw = bcw, L.box_ch = bch;
             }
         }
+        if ((flags & SVB_LAYER_SEPARABLE) && (sf == SVB_NV12 || sf == SVB_Y420P) && L.width >= 2 && L.height >= 2) {
+            const int cw = L.width / 2, ch = L.height / 2;
+            const CUtexObject t0 = textureObject(sh, L.plane[0], 1, L.width, L.height, L.stride[0]);
+            const CUtexObject t1 = sf == SVB_NV12 ? textureObject(sh, L.plane[1], 2, cw, ch, L.stride[1]) : textureObject(sh, L.plane[1], 1, cw, ch, L.stride[1]);
+            const CUtexObject t2 = sf == SVB_NV12 ? t1 : textureObject(sh, L.plane[2], 1, cw, ch, L.stride[2]);
+            if (t0 && t1 && t2) {
+                L.tex[0] = t0, L.tex[1] = t1, L.tex[2] = t2;
+                flags |= SVB_LAYER_TEX;
+            }
+        }
         L.flags = flags;
     }
     return plan;
@@ -266,6 +325,17 @@ FramePlan planFrame(const ComputeContext& ctx, const PictureSample& target, cons
 // ---- launch ---------------------------------------------------------------------------------------------
 
 namespace {
+
+// SVB_COMPOSITOR=gather|tma picks the fused compositor (default below); read once.
+bool gatherByDefault() {
+    static const int v = [] {
+        const char* e = std::getenv("SVB_COMPOSITOR");
+        if (e && std::strcmp(e, "gather") == 0) return 1;
+        if (e && std::strcmp(e, "tma") == 0) return 0;
+        return SVB_DEFAULT_GATHER;
+    }();
+    return v != 0;
+}
 
 // One launch over `frames` (all tiled-capable, or all generic).  Caller holds a CtxGuard.
 void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, bool tiled) {
@@ -285,8 +355,18 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
         int total = 0, maxW = 0, maxH = 0, maxLayers = 1, maxEnts = 1, maxTiles = 1;
         size_t tableEnts = 0;
         int boxY = 0, boxC = 0;   // largest staged footprint of the batch (bytes per box; chroma = both planes of a Y420P source)
+        // Which compositor: svb_mix_gather (taps through the texture unit) when every layer the TMA kernel would stage can be
+        // bound as a texture too (base / pitch alignment); SVB_COMPOSITOR=tma|gather overrides the default.
+        bool gather = tiled && gatherByDefault();
+        for (int i = 0; gather && i < n; ++i) {
+            const SvbFrameDesc& fr = frames[start + i];
+            for (int l = 0; l < fr.nlayers; ++l)
+                if ((fr.layers[l].flags & SVB_LAYER_STAGED) && !(fr.layers[l].flags & SVB_LAYER_TEX)) gather = false;
+        }
         for (int i = 0; i < n; ++i) {
             SvbFrameDesc& fr = frames[start + i];
+            if (gather) fr.flags |= SVB_FRAME_GATHER;
+            else fr.flags &= ~SVB_FRAME_GATHER;
             for (int l = 0; l < fr.nlayers; ++l) {
                 const SvbLayerDesc& L = fr.layers[l];
                 if (!(L.flags & SVB_LAYER_STAGED)) continue;
@@ -341,24 +421,31 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
             check(d.cuStreamWaitEvent(ic.compute, sh.evPrep[seg], 0), "cuStreamWaitEvent");
             if (tev.first) check(d.cuEventRecord(tev.first, ic.compute), "cuEventRecord");  // time svb_mix_tiled alone
             float one = 1.0f;  // see add2() in kernels_tiled.cuh
-            void* args[] = {&dev, &plans, &total, &one, &counter, &boxY, &boxC};
-            // shared memory: the fixed part plus two box pairs sized for the largest staged footprint of this batch
-            size_t smem = SVB_TILED_SMEM_BYTES((size_t)boxY, (size_t)boxC);
-            int perSm;
-            {
-                std::lock_guard<std::mutex> g(sh.mu);
-                auto it = sh.tiledCtasPerSm.find(smem);
-                if (it == sh.tiledCtasPerSm.end()) {
-                    int n = 0;
-                    check(d.cuOccupancyMaxActiveBlocksPerMultiprocessor(&n, sh.fTiled, SVB_TILED_THREADS, smem), "cuOccupancyMaxActiveBlocksPerMultiprocessor");
-                    it = sh.tiledCtasPerSm.emplace(smem, std::max(1, n)).first;
+            if (gather) {
+                int units = total * SVB_GATHER_STRIPS;  // (tile, strip) pairs, claimed by warps
+                void* args[] = {&dev, &plans, &units, &one, &counter};
+                const unsigned grid = (unsigned)std::min((units + SVB_TILED_COMPUTE_WARPS - 1) / SVB_TILED_COMPUTE_WARPS, ic.smCount * sh.gatherCtasPerSm);
+                check(d.cuLaunchKernel(sh.fGather, grid, 1, 1, SVB_TILED_THREADS, 1, 1, 0, ic.compute, args, nullptr), "cuLaunchKernel(svb_mix_gather)");
+                noteKernelLaunch();
+            } else {
+                void* args[] = {&dev, &plans, &total, &one, &counter, &boxY, &boxC};
+                // shared memory: the fixed part plus two box pairs sized for the largest staged footprint of this batch
+                size_t smem = SVB_TILED_SMEM_BYTES((size_t)boxY, (size_t)boxC);
+                int perSm;
+                {
+                    std::lock_guard<std::mutex> g(sh.mu);
+                    auto it = sh.tiledCtasPerSm.find(smem);
+                    if (it == sh.tiledCtasPerSm.end()) {
+                        int n = 0;
+                        check(d.cuOccupancyMaxActiveBlocksPerMultiprocessor(&n, sh.fTiled, SVB_TILED_THREADS, smem), "cuOccupancyMaxActiveBlocksPerMultiprocessor");
+                        it = sh.tiledCtasPerSm.emplace(smem, std::max(1, n)).first;
+                    }
+                    perSm = it->second;
                 }
-                perSm = it->second;
+                const unsigned grid = (unsigned)std::min(total, ic.smCount * perSm);
+                check(d.cuLaunchKernel(sh.fTiled, grid, 1, 1, SVB_TILED_THREADS, 1, 1, (unsigned)smem, ic.compute, args, nullptr), "cuLaunchKernel(svb_mix_tiled)");
+                noteKernelLaunch();
             }
-            const unsigned grid = (unsigned)std::min(total, ic.smCount * perSm);
-            check(d.cuLaunchKernel(sh.fTiled, grid, 1, 1, SVB_TILED_THREADS, 1, 1, (unsigned)smem, ic.compute, args, nullptr),
-                  "cuLaunchKernel(svb_mix_tiled)");
-            noteKernelLaunch();
         } else {
             check(d.cuEventRecord(sh.evPrep[seg], sh.prep), "cuEventRecord");  // the descriptor copy
             check(d.cuStreamWaitEvent(ic.compute, sh.evPrep[seg], 0), "cuStreamWaitEvent");

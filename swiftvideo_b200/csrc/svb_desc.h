@@ -12,6 +12,12 @@
 #endif
 #define SVB_TILED_COMPUTE_WARPS (SVB_TILE_H / 4)              // a warp covers 128 columns x 4 rows
 #define SVB_TILED_THREADS (SVB_TILED_COMPUTE_WARPS * 32)
+// svb_mix_gather: luma rows of a tile one warp owns (4 or 2: fewer rows = less state per thread = more warps in flight to cover
+// the texture latency); a work unit is one such strip of one tile
+#ifndef SVB_GATHER_ROWS
+#define SVB_GATHER_ROWS 4
+#endif
+#define SVB_GATHER_STRIPS (SVB_TILE_H / SVB_GATHER_ROWS)
 // largest source footprint the tiled kernel stages in shared memory per tile and layer
 #ifndef SVB_BOX_Y_BYTES
 #define SVB_BOX_Y_BYTES (SVB_TILE_H * 640)
@@ -24,13 +30,15 @@ enum SvbFormat { SVB_NV12 = 0, SVB_Y420P = 1, SVB_BGRA = 2, SVB_RGBA = 3 };
 
 enum {
     SVB_FRAME_LOAD_CUR = 1,   // continue an earlier pass: start from the target's bytes, not from clear
-    SVB_FRAME_SCALAR_FP = 2   // tuning aid: spell the packed fp32x2 arithmetic as scalar instructions (same results)
+    SVB_FRAME_SCALAR_FP = 2,  // tuning aid: spell the packed fp32x2 arithmetic as scalar instructions (same results)
+    SVB_FRAME_GATHER = 4      // the batch goes to svb_mix_gather: plan separable YUV layers for the texture path (no staging limits)
 };
 enum {
     SVB_LAYER_SEPARABLE = 1,     // x outputs depend only on x and y outputs only on y (no rotation/shear)
     SVB_LAYER_UNIT_OPACITY = 2,  // opacity == 1: cur*(1-1) + v*1 == v exactly, the blend is skipped
     SVB_LAYER_STAGED = 4,        // tensor maps below are valid: source footprints are staged by TMA
-    SVB_LAYER_OPACITY_01 = 8     // 0 <= opacity <= 1: blended values cannot leave [0,1], store clamps are no-ops
+    SVB_LAYER_OPACITY_01 = 8,    // 0 <= opacity <= 1: blended values cannot leave [0,1], store clamps are no-ops
+    SVB_LAYER_TEX = 16           // tex[] below holds texture objects over the source planes (svb_mix_gather)
 };
 
 // ImageUniforms as uploaded by applyComputeImage (reference compute.swift:76-86; device mirror
@@ -59,7 +67,9 @@ typedef struct __attribute__((aligned(64))) SvbLayerDesc {
     int32_t rect[4];             // x0,y0,x1,y1: outside this canvas rectangle the layer touches nothing
     int32_t box_w, box_h;        // staged luma box (elements); chroma box is box_cw x box_ch
     int32_t box_cw, box_ch;
-    int32_t pad_[9];
+    int32_t pad0_;
+    unsigned long long tex[3];   // CUtexObject per source plane (valid when SVB_LAYER_TEX): UNORM8, clamp, unnormalised coordinates
+    int32_t pad_[2];
 } SvbLayerDesc;
 
 typedef struct __attribute__((aligned(64))) SvbFrameDesc {

@@ -47,6 +47,11 @@ __device__ __forceinline__ unsigned ldg_u8(const uint8_t* p) {
     asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
+__device__ __forceinline__ unsigned ldg_u16(const uint8_t* p) {
+    unsigned v;
+    asm volatile("ld.global.nc.u16 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ unsigned opaque(unsigned v) {
     asm volatile("" : "+r"(v));
     return v;
