@@ -338,7 +338,7 @@ bool gatherByDefault() {
 }
 
 // One launch over `frames` (all tiled-capable, or all generic).  Caller holds a CtxGuard.
-void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, bool tiled) {
+void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, bool tiled, bool wantGather) {
     const CuDriver& d = drv();
     MixerShared& sh = shared(ctx.ctx);
     InternalContext& ic = *ctx.ctx;
@@ -357,7 +357,7 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
         int boxY = 0, boxC = 0;   // largest staged footprint of the batch (bytes per box; chroma = both planes of a Y420P source)
         // Which compositor: svb_mix_gather (taps through the texture unit) when every layer the TMA kernel would stage can be
         // bound as a texture too (base / pitch alignment); SVB_COMPOSITOR=tma|gather overrides the default.
-        bool gather = tiled && gatherByDefault();
+        bool gather = tiled && (wantGather || gatherByDefault());
         for (int i = 0; gather && i < n; ++i) {
             const SvbFrameDesc& fr = frames[start + i];
             for (int l = 0; l < fr.nlayers; ++l)
@@ -477,7 +477,7 @@ struct Job {
 };
 
 // Fused compose of several independent targets on one context.
-void composeFused(const ComputeContext& ctx, std::vector<Job>& jobs, bool forceGeneric) {
+void composeFused(const ComputeContext& ctx, std::vector<Job>& jobs, bool forceGeneric, bool wantGather = false) {
     CtxGuard g(ctx.ctx);
     std::vector<FramePlan> plans;
     bool allTiled = !forceGeneric;
@@ -493,7 +493,7 @@ void composeFused(const ComputeContext& ctx, std::vector<Job>& jobs, bool forceG
         std::vector<SvbFrameDesc> frames;
         for (FramePlan& pl : plans)
             if (p < pl.passes.size()) frames.push_back(pl.passes[p]);
-        launchFrames(ctx, frames, allTiled);
+        launchFrames(ctx, frames, allTiled, wantGather);
     }
     for (Job& j : jobs) markWritten(ctx, *j.target);
 }
@@ -613,7 +613,7 @@ ComputeContext VideoMixer::composeRaw(const ComputeContext& ctxIn, const Picture
     jobs[0].target = &target;
     jobs[0].layers = layers;
     jobs[0].uniforms.assign(uniforms, uniforms + layers.size());
-    composeFused(ctxIn, jobs, mode == Mode::generic);
+    composeFused(ctxIn, jobs, mode == Mode::generic, mode == Mode::fusedGather);
     return ctxIn;
 }
 
@@ -650,7 +650,7 @@ void VideoMixer::mixMany(VideoMixer* const* mixers, int n, int64_t time, Picture
     ComputeContext ctx0 = mixers[0]->clContext;
     if (fusedAll) {
         jobs.resize(n);
-        bool generic = false;
+        bool generic = false, wantGather = false;
         for (int i = 0; i < n; ++i) {
             Tick& tk = ticks[i];
             jobs[i].target = &tk.backing;
@@ -662,8 +662,9 @@ void VideoMixer::mixMany(VideoMixer* const* mixers, int n, int64_t time, Picture
                 jobs[i].uniforms.push_back(makeImageUniforms(*im, tk.backing));
             }
             generic = generic || mixers[i]->mode == Mode::generic;
+            wantGather = wantGather || mixers[i]->mode == Mode::fusedGather;
         }
-        composeFused(ctx0, jobs, generic);
+        composeFused(ctx0, jobs, generic, wantGather);
     } else {
         for (int i = 0; i < n; ++i) {
             Tick& tk = ticks[i];

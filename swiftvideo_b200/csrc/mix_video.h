@@ -25,7 +25,8 @@ class VideoMixer {
     enum class Mode : int {
         fused = 0,     // tiled kernel where its preconditions hold, else the generic fused kernel
         perLayer = 1,  // the reference's own sequence: clear kernel + one applyComputeImage per layer
-        generic = 2    // the generic fused kernel only
+        generic = 2,   // the generic fused kernel only
+        fusedGather = 3  // fused, with svb_mix_gather (taps through the texture unit) wherever every staged layer can be bound as a texture
     };
 
     VideoMixer(const ComputeContext* computeContext, Vector2 outputSize, PixelFormat outputFormat = PixelFormat::nv12,

@@ -13,6 +13,8 @@ from oracle import oracle as O
 pytestmark = pytest.mark.gpu
 
 MODES = [(sv.MixMode.FUSED, "fused"), (sv.MixMode.GENERIC, "generic"), (sv.MixMode.PER_LAYER, "per_layer")]
+# the fused compositor with its taps through the texture unit (svb_mix_gather): same plans, tables and bytes
+MODES_GATHER = MODES + [(sv.MixMode.FUSED_GATHER, "fused_gather")]
 CASES = scenes.parity_cases()
 
 
@@ -79,7 +81,7 @@ def _tiled_cases():
 TILED = _tiled_cases()
 
 
-@pytest.mark.parametrize("mode,mname", MODES, ids=[m[1] for m in MODES])
+@pytest.mark.parametrize("mode,mname", MODES_GATHER, ids=[m[1] for m in MODES_GATHER])
 @pytest.mark.parametrize("case", TILED, ids=[c.name for c in TILED])
 def test_tiled_scenes(case, mode, mname):
     rc, want = scenes.run_case(O.port(), case, threads=O.host_threads())
@@ -109,7 +111,7 @@ def test_cfg34_full_size(nlayers):
     assert rc == 0
     ctx = context()
     outs = {}
-    for mode, mname in MODES:
+    for mode, mname in MODES_GATHER:
         outs[mname] = gpu_case(ctx, case, mode)
         assert (outs[mname] == want.data).all(), f"{case.name}/{mname}: {first_diff(outs[mname], want.data)}"
 
@@ -127,8 +129,9 @@ def test_cfg4_variants_full_size():
     case = scenes.Case("cfg4_y420p", O.Y420P, canvas, layers, us)
     rc, want = scenes.run_case(O.port(), case, threads=O.host_threads())
     assert rc == 0
-    got = gpu_case(ctx, case, sv.MixMode.FUSED)
-    assert (got == want.data).all(), f"cfg4_y420p: {first_diff(got, want.data)}"
+    for mode, mname in ((sv.MixMode.FUSED, "fused"), (sv.MixMode.FUSED_GATHER, "fused_gather")):
+        got = gpu_case(ctx, case, mode)
+        assert (got == want.data).all(), f"cfg4_y420p/{mname}: {first_diff(got, want.data)}"
     # (2) RGBA / BGRA overlays on an NV12 stack (4 layers keep the oracle's time down)
     geo = scenes.cfg34_geometry(8)[:2] + scenes.cfg34_geometry(8)[5:7]
     fmts = [O.NV12, O.NV12, O.RGBA, O.BGRA]
@@ -137,7 +140,7 @@ def test_cfg4_variants_full_size():
     case = scenes.Case("cfg4_rgba_overlays", O.NV12, canvas, layers, us)
     rc, want = scenes.run_case(O.port(), case, threads=O.host_threads())
     assert rc == 0
-    for mode, mname in MODES:
+    for mode, mname in MODES_GATHER:
         got = gpu_case(ctx, case, mode)
         assert (got == want.data).all(), f"cfg4_rgba_overlays/{mname}: {first_diff(got, want.data)}"
 
