@@ -18,14 +18,6 @@
 
 namespace svb {
 
-// gather coordinate of a table entry: the footprint of tex2Dgather at coordinate c is texels floor(c - 1/2) and the next,
-// clamped one by one.  For an unclamped index i the table holds i0 = clamp(i), i1 = clamp(i + 1): c = i0 + 1 reproduces
-// (i0, i1) in every case but the left / top clamp (i < 0: i0 == i1 == 0), where c = 0 does.
-__device__ __forceinline__ float gather_coord(uint32_t p) {
-    const unsigned i0 = p & 0xffffu, d = (p >> 16) & 1u;
-    return (float)(int)(i0 + ((d | i0) != 0u ? 1u : 0u));
-}
-
 // One separable YUV layer over this warp's 128 x 4 strip.  MODE as in fast_layer (0: inside the picture, opacity 1; 1: inside,
 // 0 <= opacity <= 1; 2: lean edge; 3: anything).  N12: chroma is one two-channel plane (texU), else two planes.
 template <int MODE, bool N12>
@@ -62,13 +54,7 @@ __device__ __forceinline__ void gather_layer(const SvbLayerDesc* __restrict__ L,
         out.y = ok1 == 7 ? qi.y : ((ok1 & 1) ? qf.y : cur_i.y);
         return out;
     };
-    // (1-a)(1-b) T00 + a(1-b) T10 + (1-a)b T01 + ab T11, weights and sum in the sampler's order (svb_device.cuh: make_taps, filt)
-    // (scalar on purpose: the gather returns (T01, T11, T10, T00); pairing weights to that order costs two moves per use, and
-    // scalar multiplies and adds issue on both FMA pipes while the packed forms only take the heavy one)
-    auto filter = [&](const float4 g, float na, float a, float b, float nb) -> float {
-        const float w00 = mul(na, nb), w10 = mul(a, nb), w01 = mul(na, b), w11 = mul(a, b);
-        return add(add(add(mul(w00, g.w), mul(w10, g.z)), mul(w01, g.x)), mul(w11, g.y));
-    };
+    auto filter = [](const float4 g, float na, float a, float b, float nb) -> float { return gather_filter(g, na, a, b, nb); };
 #pragma unroll
     for (int r = 0; r < SVB_GATHER_ROWS; ++r) {
         const uint2 ry = __ldg(reinterpret_cast<const uint2*>(rowblk + 2 * (SVB_GATHER_ROWS * strip + r)));

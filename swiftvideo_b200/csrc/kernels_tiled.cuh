@@ -31,6 +31,13 @@
 #ifndef SVB_ROLL_ROWS
 #define SVB_ROLL_ROWS 1  // the layer bodies run their two row pairs as a rolled loop (0: unrolled, 0.7 % slower at three CTAs per SM)
 #endif
+#ifndef SVB_TILED_CHROMA_GATHER
+// EXPERIMENT, off and not yet measured (the round's GPU budget ran out): interior tiles fetch their CHROMA footprints with
+// tex2Dgather while luma stays on the staged shared-memory path -- svb_mix_tiled is issue-bound and svb_mix_gather
+// texture-latency-bound, so a body that uses both units should beat either (profiles/r1_history.md).  Same bytes by construction:
+// the gather path is svb_mix_gather's, which passes the whole GPU suite.
+#define SVB_TILED_CHROMA_GATHER 0
+#endif
 #ifndef SVB_DYNAMIC_TILES
 // 1: CTAs claim tiles from a counter (row-major order, so neighbouring tiles still run together); 0: static round-robin.
 // Tiles cost between zero and eight layers, and with a static deal the slowest CTA's share decided the kernel time
@@ -205,6 +212,22 @@ template <int OFF> __device__ __forceinline__ unsigned lds_u8o(unsigned addr) { 
     return v;
 }
 
+// gather coordinate of a table entry: the footprint of tex2Dgather at coordinate c is texels floor(c - 1/2) and the next,
+// clamped one by one.  For an unclamped index i the table holds i0 = clamp(i), i1 = clamp(i + 1): c = i0 + 1 reproduces
+// (i0, i1) in every case but the left / top clamp (i < 0: i0 == i1 == 0), where c = 0 does.
+__device__ __forceinline__ float gather_coord(uint32_t p) {
+    const unsigned i0 = p & 0xffffu, d = (p >> 16) & 1u;
+    return (float)(int)(i0 + ((d | i0) != 0u ? 1u : 0u));
+}
+
+// (1-a)(1-b) T00 + a(1-b) T10 + (1-a)b T01 + ab T11 over a gathered footprint g = (T01, T11, T10, T00) -- tools/tex_probe.cu --
+// with the sampler's weights and summation order (svb_device.cuh: make_taps, filt).  Scalar on purpose: pairing weights to the
+// gather's component order costs two moves per use, and scalar multiplies and adds issue on both FMA pipes.
+__device__ __forceinline__ float gather_filter(const float4 g, float na, float a, float b, float nb) {
+    const float w00 = mul(na, nb), w10 = mul(a, nb), w01 = mul(na, b), w11 = mul(a, b);
+    return add(add(add(mul(w00, g.w), mul(w10, g.z)), mul(w01, g.x)), mul(w11, g.y));
+}
+
 // Tables of one layer of one frame: tiles_x column blocks, then tiles_y row blocks
 struct Tabs {
     const uint32_t* col;
@@ -241,7 +264,7 @@ struct FillTerms {
 template <int MODE, bool PK, bool N12>
 __device__ __forceinline__ void fast_layer(unsigned boxY, unsigned boxU, unsigned boxV, const uint32_t* __restrict__ tabs, int lane, int warp, int iy0, int jy0,
                                            int ic0, int jc0, int pitchY, int pitchC, int stepC, float alpha, float onef, const FillTerms& ft,
-                                           float2 (&Yi)[4][2], float2 (&Ui)[2], float2 (&Vi)[2]) {
+                                           float2 (&Yi)[4][2], float2 (&Ui)[2], float2 (&Vi)[2], unsigned long long texU = 0, unsigned long long texV = 0) {
     constexpr bool UNIT = MODE == 0, EDGE = MODE == 2, GEN = MODE == 3, XCL = MODE >= 2;  // XCL: taps may be clamped along x
     const float2 AL = splat(alpha), NAL = splat(sub(1.f, alpha)), ONE = splat(onef);
     unsigned o0[4], o1[4];
@@ -331,6 +354,12 @@ __device__ __forceinline__ void fast_layer(unsigned boxY, unsigned boxU, unsigne
                            unorm2<PK>(bytes2(lds_u8(u1 + oc00), lds_u8(u1 + oc10))), unorm2<PK>(bytes2(lds_u8(u1 + oc01), lds_u8(u1 + oc11))), ONE);
             v = bilin2<PK>(w00, w10, w01, w11, unorm2<PK>(bytes2(lds_u8(v0 + oc00), lds_u8(v0 + oc10))), unorm2<PK>(bytes2(lds_u8(v0 + oc01), lds_u8(v0 + oc11))),
                            unorm2<PK>(bytes2(lds_u8(v1 + oc00), lds_u8(v1 + oc10))), unorm2<PK>(bytes2(lds_u8(v1 + oc01), lds_u8(v1 + oc11))), ONE);
+        } else if (SVB_TILED_CHROMA_GATHER && texU != 0ull) {  // (uniform) chroma footprints through the texture unit, see the toggle
+            const cudaTextureObject_t tu = (cudaTextureObject_t)texU, tv = (cudaTextureObject_t)(N12 ? texU : texV);
+            const float xc0 = gather_coord(pc0), xc1 = gather_coord(pc1), yc = gather_coord(rc.y), bq = __uint_as_float(rc.x), nbq = sub(1.f, bq);
+            u = make_float2(gather_filter(tex2Dgather<float4>(tu, xc0, yc, 0), NAC.x, AC.x, bq, nbq), gather_filter(tex2Dgather<float4>(tu, xc1, yc, 0), NAC.y, AC.y, bq, nbq));
+            v = make_float2(gather_filter(tex2Dgather<float4>(tv, xc0, yc, N12 ? 1 : 0), NAC.x, AC.x, bq, nbq),
+                            gather_filter(tex2Dgather<float4>(tv, xc1, yc, N12 ? 1 : 0), NAC.y, AC.y, bq, nbq));
         } else if (N12) {  // (U, V) byte pairs: texel i0 at [c], [c+1], texel i0 + 1 at [c+2], [c+3]
             const unsigned c00 = u0 + oc00, c10 = u0 + oc10, c01 = u1 + oc00, c11 = u1 + oc10;
             u = bilin2<PK>(w00, w10, w01, w11, unorm2<PK>(bytes2(lds_u8o<0>(c00), lds_u8o<0>(c10))), unorm2<PK>(bytes2(lds_u8o<2>(c00), lds_u8o<2>(c10))),
@@ -776,6 +805,8 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CT
                     const unsigned bY = smem_u32(boxes + stage * box_y_bytes), bU = smem_u32(boxes + 2 * box_y_bytes + stage * box_c_bytes);
                     const unsigned bV = bU + (fmt == SVB_NV12 ? 1 : box_c_bytes / 2);
                     const float alpha = __int_as_float(p1.w);
+                    unsigned long long tU = 0, tV = 0;
+                    if (SVB_TILED_CHROMA_GATHER && (lflags & SVB_LAYER_TEX)) tU = F->layers[p0.x >> 8].tex[1], tV = F->layers[p0.x >> 8].tex[2];
                     FillTerms ft;
                     if (mode == PLAN_STAGED_EDGE || !(lflags & SVB_LAYER_OPACITY_01)) {
                         const SvbLayerDesc* __restrict__ L = &F->layers[p0.x >> 8];
@@ -799,11 +830,11 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CT
                         if (lean) fast_layer<2, true, false>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
                         else fast_layer<3, true, false>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
                     } else if (lflags & SVB_LAYER_UNIT_OPACITY) {
-                        if (fmt == SVB_NV12) fast_layer<0, true, true>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
-                        else fast_layer<0, true, false>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
+                        if (fmt == SVB_NV12) fast_layer<0, true, true>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi, tU, tV);
+                        else fast_layer<0, true, false>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi, tU, tV);
                     } else {
-                        if (fmt == SVB_NV12) fast_layer<1, true, true>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
-                        else fast_layer<1, true, false>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
+                        if (fmt == SVB_NV12) fast_layer<1, true, true>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi, tU, tV);
+                        else fast_layer<1, true, false>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi, tU, tV);
                     }
                 }
                 stage ^= 1;
