@@ -140,6 +140,7 @@ int roundUp(int v, int m) { return (v + m - 1) / m * m; }
 // 2-D tensor map over one plane; cached, the encode costs ~1 us and layers rarely change geometry.
 bool tensorMap(MixerShared& sh, unsigned char out[128], CUdeviceptr ptr, int elemBytes, int w, int h, int strideBytes, int boxW, int boxH) {
     if ((ptr & 15) || (strideBytes & 15) || w <= 0 || h <= 0 || boxW > 256 || boxH > 256 || (boxW * elemBytes) % 16) return false;
+    std::lock_guard<std::mutex> lock(sh.mu);  // mixers of one context may plan from different threads
     const std::array<uint64_t, 4> key = {(uint64_t)ptr, ((uint64_t)(uint32_t)w << 32) | (uint32_t)h,
                                          ((uint64_t)(uint32_t)strideBytes << 32) | (uint32_t)elemBytes,
                                          ((uint64_t)(uint32_t)boxW << 32) | (uint32_t)boxH};
@@ -171,6 +172,7 @@ bool tensorMap(MixerShared& sh, unsigned char out[128], CUdeviceptr ptr, int ele
 CUtexObject textureObject(MixerShared& sh, CUdeviceptr ptr, int channels, int w, int h, int pitchBytes) {
     if (!ptr || w <= 0 || h <= 0 || (ptr % (CUdeviceptr)sh.texAlign) || (pitchBytes % sh.texPitchAlign) || pitchBytes < w * channels) return 0;
     const std::array<uint64_t, 3> key = {(uint64_t)ptr, ((uint64_t)(uint32_t)w << 32) | (uint32_t)h, ((uint64_t)(uint32_t)pitchBytes << 8) | (uint32_t)channels};
+    std::lock_guard<std::mutex> lock(sh.mu);  // mixers of one context may plan from different threads
     auto it = sh.texs.find(key);
     if (it != sh.texs.end()) return it->second;
     CUDA_RESOURCE_DESC rd;
