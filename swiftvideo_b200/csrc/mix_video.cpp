@@ -191,7 +191,8 @@ CUtexObject textureObject(MixerShared& sh, CUdeviceptr ptr, int channels, int w,
     td.flags = 0;                             // UNORM8 -> float in the unit, unnormalised coordinates
     CUtexObject obj = 0;
     if (drv().cuTexObjectCreate(&obj, &rd, &td, nullptr) != CUDA_SUCCESS) return 0;
-    if (sh.texs.size() > 4096) {  // bounded: a cleared entry is simply created again
+    if (sh.texs.size() > 4096) {  // bounded: a cleared entry is simply created again (rare: drain the launches that may still use one)
+        cu().cuCtxSynchronize();
         for (auto& kv : sh.texs) cu().cuTexObjectDestroy(kv.second);
         sh.texs.clear();
     }
