@@ -189,13 +189,12 @@ CUtexObject textureObject(MixerShared& sh, CUdeviceptr ptr, int channels, int w,
     td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = CU_TR_ADDRESS_MODE_CLAMP;
     td.filterMode = CU_TR_FILTER_MODE_POINT;  // tex2Dgather fetches the footprint; the filter runs in fp32 in the kernel
     td.flags = 0;                             // UNORM8 -> float in the unit, unnormalised coordinates
+    // bounded: the device pool recycles blocks, so a long run meets the same few hundred planes again; past the bound a plane simply
+    // goes without (its batch then takes the TMA compositor).  Nothing is destroyed before the context goes: a descriptor already
+    // handed to a launch may hold the handle.
+    if (sh.texs.size() >= 4096) return 0;
     CUtexObject obj = 0;
     if (drv().cuTexObjectCreate(&obj, &rd, &td, nullptr) != CUDA_SUCCESS) return 0;
-    if (sh.texs.size() > 4096) {  // bounded: a cleared entry is simply created again (rare: drain the launches that may still use one)
-        cu().cuCtxSynchronize();
-        for (auto& kv : sh.texs) cu().cuTexObjectDestroy(kv.second);
-        sh.texs.clear();
-    }
     sh.texs.emplace(key, obj);
     return obj;
 }
