@@ -38,6 +38,11 @@
 // the gather path is svb_mix_gather's, which passes the whole GPU suite.
 #define SVB_TILED_CHROMA_GATHER 0
 #endif
+#ifndef SVB_TILED_LUMA_GATHER
+// the same experiment the other way round: LUMA footprints by tex2Dgather, chroma staged (two thirds of the samples on the texture
+// unit -- the split the two measured rates favour).  The luma boxes are still copied while this is a scaffold; off, unmeasured.
+#define SVB_TILED_LUMA_GATHER 0
+#endif
 #ifndef SVB_DYNAMIC_TILES
 // 1: CTAs claim tiles from a counter (row-major order, so neighbouring tiles still run together); 0: static round-robin.
 // Tiles cost between zero and eight layers, and with a static deal the slowest CTA's share decided the kernel time
@@ -264,7 +269,7 @@ struct FillTerms {
 template <int MODE, bool PK, bool N12>
 __device__ __forceinline__ void fast_layer(unsigned boxY, unsigned boxU, unsigned boxV, const uint32_t* __restrict__ tabs, int lane, int warp, int iy0, int jy0,
                                            int ic0, int jc0, int pitchY, int pitchC, int stepC, float alpha, float onef, const FillTerms& ft,
-                                           float2 (&Yi)[4][2], float2 (&Ui)[2], float2 (&Vi)[2], unsigned long long texU = 0, unsigned long long texV = 0) {
+                                           float2 (&Yi)[4][2], float2 (&Ui)[2], float2 (&Vi)[2], unsigned long long texU = 0, unsigned long long texV = 0, unsigned long long texY = 0) {
     constexpr bool UNIT = MODE == 0, EDGE = MODE == 2, GEN = MODE == 3, XCL = MODE >= 2;  // XCL: taps may be clamped along x
     const float2 AL = splat(alpha), NAL = splat(sub(1.f, alpha)), ONE = splat(onef);
     unsigned o0[4], o1[4];
@@ -280,6 +285,14 @@ __device__ __forceinline__ void fast_layer(unsigned boxY, unsigned boxU, unsigne
         if (EDGE) M[p] = make_float2((e.x >> 17) == 7u ? 1.f : 0.f, (e.y >> 17) == 7u ? 1.f : 0.f);
         A[p] = a;
         NA[p] = make_float2(sub(1.f, a.x), sub(1.f, a.y));
+    }
+    float xgl[4] = {0.f, 0.f, 0.f, 0.f};  // gather coordinates of the four luma columns (SVB_TILED_LUMA_GATHER)
+    if (SVB_TILED_LUMA_GATHER && !XCL && texY != 0ull) {
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const uint2 e = *reinterpret_cast<const uint2*>(tabs + SVB_TILE_W + 64 * p + 2 * lane);
+            xgl[2 * p] = gather_coord(e.x), xgl[2 * p + 1] = gather_coord(e.y);
+        }
     }
     // chroma columns lane and 32 + lane of the tile (the texels under the two luma pairs)
     const uint32_t pc0 = tabs[2 * SVB_TILE_W + SVB_TILE_W / 2 + lane], pc1 = tabs[2 * SVB_TILE_W + SVB_TILE_W / 2 + 32 + lane];
@@ -322,6 +335,13 @@ __device__ __forceinline__ void fast_layer(unsigned boxY, unsigned boxU, unsigne
             const float2 B = splat(__uint_as_float(ry.x)), NB = splat(sub(1.f, __uint_as_float(ry.x)));
 #pragma unroll
             for (int p = 0; p < 2; ++p) {
+                if (SVB_TILED_LUMA_GATHER && !XCL && texY != 0ull) {  // (uniform) luma footprints through the texture unit, see the toggle
+                    const float yg = gather_coord(ry.y), bq = __uint_as_float(ry.x), nbq = sub(1.f, bq);
+                    const float2 v = make_float2(gather_filter(tex2Dgather<float4>((cudaTextureObject_t)texY, xgl[2 * p], yg, 0), NA[p].x, A[p].x, bq, nbq),
+                                                 gather_filter(tex2Dgather<float4>((cudaTextureObject_t)texY, xgl[2 * p + 1], yg, 0), NA[p].y, A[p].y, bq, nbq));
+                    Yr[p] = settle(Yr[p], v, ft.fy, 0.f, okc[2 * p] & okr, okc[2 * p + 1] & okr, M[p]);
+                    continue;
+                }
                 float2 t00, t10, t01, t11;
                 if (XCL) {
                     const unsigned a0 = o0[2 * p], a1 = o1[2 * p], b0 = o0[2 * p + 1], b1 = o1[2 * p + 1];
@@ -805,8 +825,9 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CT
                     const unsigned bY = smem_u32(boxes + stage * box_y_bytes), bU = smem_u32(boxes + 2 * box_y_bytes + stage * box_c_bytes);
                     const unsigned bV = bU + (fmt == SVB_NV12 ? 1 : box_c_bytes / 2);
                     const float alpha = __int_as_float(p1.w);
-                    unsigned long long tU = 0, tV = 0;
+                    unsigned long long tU = 0, tV = 0, tY = 0;
                     if (SVB_TILED_CHROMA_GATHER && (lflags & SVB_LAYER_TEX)) tU = F->layers[p0.x >> 8].tex[1], tV = F->layers[p0.x >> 8].tex[2];
+                    if (SVB_TILED_LUMA_GATHER && (lflags & SVB_LAYER_TEX)) tY = F->layers[p0.x >> 8].tex[0];
                     FillTerms ft;
                     if (mode == PLAN_STAGED_EDGE || !(lflags & SVB_LAYER_OPACITY_01)) {
                         const SvbLayerDesc* __restrict__ L = &F->layers[p0.x >> 8];
@@ -830,11 +851,11 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CT
                         if (lean) fast_layer<2, true, false>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
                         else fast_layer<3, true, false>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
                     } else if (lflags & SVB_LAYER_UNIT_OPACITY) {
-                        if (fmt == SVB_NV12) fast_layer<0, true, true>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi, tU, tV);
-                        else fast_layer<0, true, false>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi, tU, tV);
+                        if (fmt == SVB_NV12) fast_layer<0, true, true>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi, tU, tV, tY);
+                        else fast_layer<0, true, false>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi, tU, tV, tY);
                     } else {
-                        if (fmt == SVB_NV12) fast_layer<1, true, true>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi, tU, tV);
-                        else fast_layer<1, true, false>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi, tU, tV);
+                        if (fmt == SVB_NV12) fast_layer<1, true, true>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi, tU, tV, tY);
+                        else fast_layer<1, true, false>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi, tU, tV, tY);
                     }
                 }
                 stage ^= 1;
