@@ -8,7 +8,7 @@
 //     x = (i0, j0+1)   y = (i0+1, j0+1)   z = (i0+1, j0)   w = (i0, j0)
 // The filter itself stays in fp32 with the reference's weights and summation order (the unit's own bilinear filter has 8-bit
 // weights and is not used), so the bytes are the same as the TMA-staged kernel's; per sample the gather replaces four
-// shared-memory byte reads, four conversions and four UNORM8 reads (12 of ~24 issue slots), and nothing is staged: no shared
+// shared-memory byte reads, four conversions and four UNORM8 reads, and nothing is staged: no shared
 // memory boxes, no mbarriers, no CTA barrier -- a warp owns a 128 x 4 strip of a tile and never waits for another warp.
 //
 // Work units = (tile, strip) claimed by warps from the launch's counter; the tile's plan (SvbTilePlan, written by the
