@@ -39,8 +39,7 @@
 #define SVB_TILED_CHROMA_GATHER 0
 #endif
 #ifndef SVB_TILED_LUMA_GATHER
-// the same experiment the other way round: LUMA footprints by tex2Dgather, chroma staged (two thirds of the samples on the texture
-// unit -- the split the two measured rates favour).  The luma boxes are still copied while this is a scaffold; off, unmeasured.
+// the same experiment the other way round: LUMA footprints by tex2Dgather, chroma staged (two thirds of the samples on the texture unit).  The luma boxes are still copied while this is a scaffold; off, unmeasured.
 #define SVB_TILED_LUMA_GATHER 0
 #endif
 #ifndef SVB_DYNAMIC_TILES
