@@ -63,6 +63,24 @@ def test_definition_within_one_code_of_swscale(name, bits, fmt, filt, flag, src,
     assert d.mean() < 0.02
 
 
+def _scale_golden():
+    from pathlib import Path
+    z = np.load(Path(__file__).resolve().parent / "golden" / "scale_cases.npz")
+    return z, [str(n) for n in z["names"]]
+
+
+@pytest.mark.parametrize("name", _scale_golden()[1])
+def test_definition_against_committed_fixtures(name):
+    """tests/golden/scale_cases.npz (made by make_scale_golden.py): the definition still produces its stored bytes, and they lie within
+    one code value of the stored libswscale bytes -- checked without libswscale at hand."""
+    z, _ = _scale_golden()
+    fmt, filt, sw, sh, dw, dh = (int(v) for v in z[f"{name}/meta"])
+    got = O.scale_convert(fmt, filt, z[f"{name}/src"], sw, sh, dw, dh)
+    assert (got == z[f"{name}/definition"]).all()
+    d = np.abs(got.astype(np.int32) - z[f"{name}/swscale"].astype(np.int32))
+    assert d.max() <= 1  # TOLERANCE: one 8-bit code value
+
+
 def test_definition_known_answers():
     """Flat pictures: a resize of a constant is that constant, and the colour matrix maps video black / white / grey as BT.601
     limited range says."""
@@ -139,6 +157,18 @@ def test_gpu_scale_full_size(fmt, filt, src, dst):
     got = _gpu_scale(gpu_util.context(), fmt, filt, pic, src, dst)
     want = O.scale_convert(fmt, filt, pic, src[0], src[1], dst[0], dst[1])
     assert int((got != want).sum()) == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", _scale_golden()[1])
+def test_gpu_scale_against_committed_fixtures(name):
+    """The kernel against the committed fixtures: the definition's bytes exactly, libswscale's within one code value."""
+    import gpu_util
+    z, _ = _scale_golden()
+    fmt, filt, sw, sh, dw, dh = (int(v) for v in z[f"{name}/meta"])
+    got = _gpu_scale(gpu_util.context(), fmt, filt, z[f"{name}/src"], (sw, sh), (dw, dh))
+    assert (got == z[f"{name}/definition"]).all()
+    assert np.abs(got.astype(np.int32) - z[f"{name}/swscale"].astype(np.int32)).max() <= 1
 
 
 @pytest.mark.gpu
