@@ -16,6 +16,10 @@
 #pragma once
 #include "kernels_tiled.cuh"
 
+#ifndef SVB_GATHER_CHROMA_LDG
+#define SVB_GATHER_CHROMA_LDG 0  // 1: chroma taps as plain byte loads instead of gathers -- measured slower (0.470 vs 0.394 ms), kept for A/B
+#endif
+
 namespace svb {
 
 // One separable YUV layer over this warp's 128 x 4 strip.  MODE as in fast_layer (0: inside the picture, opacity 1; 1: inside,
@@ -119,9 +123,6 @@ __device__ __forceinline__ void gather_layer(const SvbLayerDesc* __restrict__ L,
 
 }  // namespace svb
 
-#ifndef SVB_GATHER_CHROMA_LDG
-#define SVB_GATHER_CHROMA_LDG 0
-#endif
 #ifndef SVB_GATHER_MIN_CTAS
 #define SVB_GATHER_MIN_CTAS 4  // 64 registers, 32 warps per SM: 0.377 ms per launch against 0.394 (3 CTAs, 80 registers) and 0.454 (2 CTAs, 126)
 #endif
