@@ -31,16 +31,6 @@
 #ifndef SVB_ROLL_ROWS
 #define SVB_ROLL_ROWS 1  // the layer bodies run their two row pairs as a rolled loop (0: unrolled, 0.7 % slower at three CTAs per SM)
 #endif
-#ifndef SVB_TILED_CHROMA_GATHER
-// EXPERIMENT, off and not yet measured (the round's GPU budget ran out): interior tiles fetch their CHROMA footprints with
-// tex2Dgather while luma stays on the staged shared-memory path -- svb_mix_tiled is issue-bound and svb_mix_gather
-// texture-latency-bound, so a body that uses both units should beat either (profiles/r1_history.md).  Same bytes by construction:
-// the gather path is svb_mix_gather's, which passes the whole GPU suite.
-#define SVB_TILED_CHROMA_GATHER 0
-#endif
-// SVB_TILED_LUMA_GATHER (svb_desc.h): the same experiment the other way round -- LUMA footprints by tex2Dgather in every layer body,
-// only chroma staged (two thirds of the samples on the texture unit); batches whose staged layers all have textures then copy no luma
-// boxes and need no shared memory for them.  Off, unmeasured.
 #ifndef SVB_DYNAMIC_TILES
 // 1: CTAs claim tiles from a counter (row-major order, so neighbouring tiles still run together); 0: static round-robin.
 // Tiles cost between zero and eight layers, and with a static deal the slowest CTA's share decided the kernel time
@@ -267,7 +257,7 @@ struct FillTerms {
 template <int MODE, bool PK, bool N12>
 __device__ __forceinline__ void fast_layer(unsigned boxY, unsigned boxU, unsigned boxV, const uint32_t* __restrict__ tabs, int lane, int warp, int iy0, int jy0,
                                            int ic0, int jc0, int pitchY, int pitchC, int stepC, float alpha, float onef, const FillTerms& ft,
-                                           float2 (&Yi)[4][2], float2 (&Ui)[2], float2 (&Vi)[2], unsigned long long texU = 0, unsigned long long texV = 0, unsigned long long texY = 0) {
+                                           float2 (&Yi)[4][2], float2 (&Ui)[2], float2 (&Vi)[2]) {
     constexpr bool UNIT = MODE == 0, EDGE = MODE == 2, GEN = MODE == 3, XCL = MODE >= 2;  // XCL: taps may be clamped along x
     const float2 AL = splat(alpha), NAL = splat(sub(1.f, alpha)), ONE = splat(onef);
     unsigned o0[4], o1[4];
@@ -283,14 +273,6 @@ __device__ __forceinline__ void fast_layer(unsigned boxY, unsigned boxU, unsigne
         if (EDGE) M[p] = make_float2((e.x >> 17) == 7u ? 1.f : 0.f, (e.y >> 17) == 7u ? 1.f : 0.f);
         A[p] = a;
         NA[p] = make_float2(sub(1.f, a.x), sub(1.f, a.y));
-    }
-    float xgl[4] = {0.f, 0.f, 0.f, 0.f};  // gather coordinates of the four luma columns (SVB_TILED_LUMA_GATHER)
-    if (SVB_TILED_LUMA_GATHER && texY != 0ull) {
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
-            const uint2 e = *reinterpret_cast<const uint2*>(tabs + SVB_TILE_W + 64 * p + 2 * lane);
-            xgl[2 * p] = gather_coord(e.x), xgl[2 * p + 1] = gather_coord(e.y);
-        }
     }
     // chroma columns lane and 32 + lane of the tile (the texels under the two luma pairs)
     const uint32_t pc0 = tabs[2 * SVB_TILE_W + SVB_TILE_W / 2 + lane], pc1 = tabs[2 * SVB_TILE_W + SVB_TILE_W / 2 + 32 + lane];
@@ -333,13 +315,6 @@ __device__ __forceinline__ void fast_layer(unsigned boxY, unsigned boxU, unsigne
             const float2 B = splat(__uint_as_float(ry.x)), NB = splat(sub(1.f, __uint_as_float(ry.x)));
 #pragma unroll
             for (int p = 0; p < 2; ++p) {
-                if (SVB_TILED_LUMA_GATHER && texY != 0ull) {  // (uniform) luma footprints through the texture unit: clamps like the sampler in every mode
-                    const float yg = gather_coord(ry.y), bq = __uint_as_float(ry.x), nbq = sub(1.f, bq);
-                    const float2 v = make_float2(gather_filter(tex2Dgather<float4>((cudaTextureObject_t)texY, xgl[2 * p], yg, 0), NA[p].x, A[p].x, bq, nbq),
-                                                 gather_filter(tex2Dgather<float4>((cudaTextureObject_t)texY, xgl[2 * p + 1], yg, 0), NA[p].y, A[p].y, bq, nbq));
-                    Yr[p] = settle(Yr[p], v, ft.fy, 0.f, okc[2 * p] & okr, okc[2 * p + 1] & okr, M[p]);
-                    continue;
-                }
                 float2 t00, t10, t01, t11;
                 if (XCL) {
                     const unsigned a0 = o0[2 * p], a1 = o1[2 * p], b0 = o0[2 * p + 1], b1 = o1[2 * p + 1];
@@ -372,12 +347,6 @@ __device__ __forceinline__ void fast_layer(unsigned boxY, unsigned boxU, unsigne
                            unorm2<PK>(bytes2(lds_u8(u1 + oc00), lds_u8(u1 + oc10))), unorm2<PK>(bytes2(lds_u8(u1 + oc01), lds_u8(u1 + oc11))), ONE);
             v = bilin2<PK>(w00, w10, w01, w11, unorm2<PK>(bytes2(lds_u8(v0 + oc00), lds_u8(v0 + oc10))), unorm2<PK>(bytes2(lds_u8(v0 + oc01), lds_u8(v0 + oc11))),
                            unorm2<PK>(bytes2(lds_u8(v1 + oc00), lds_u8(v1 + oc10))), unorm2<PK>(bytes2(lds_u8(v1 + oc01), lds_u8(v1 + oc11))), ONE);
-        } else if (SVB_TILED_CHROMA_GATHER && texU != 0ull) {  // (uniform) chroma footprints through the texture unit, see the toggle
-            const cudaTextureObject_t tu = (cudaTextureObject_t)texU, tv = (cudaTextureObject_t)(N12 ? texU : texV);
-            const float xc0 = gather_coord(pc0), xc1 = gather_coord(pc1), yc = gather_coord(rc.y), bq = __uint_as_float(rc.x), nbq = sub(1.f, bq);
-            u = make_float2(gather_filter(tex2Dgather<float4>(tu, xc0, yc, 0), NAC.x, AC.x, bq, nbq), gather_filter(tex2Dgather<float4>(tu, xc1, yc, 0), NAC.y, AC.y, bq, nbq));
-            v = make_float2(gather_filter(tex2Dgather<float4>(tv, xc0, yc, N12 ? 1 : 0), NAC.x, AC.x, bq, nbq),
-                            gather_filter(tex2Dgather<float4>(tv, xc1, yc, N12 ? 1 : 0), NAC.y, AC.y, bq, nbq));
         } else if (N12) {  // (U, V) byte pairs: texel i0 at [c], [c+1], texel i0 + 1 at [c+2], [c+3]
             const unsigned c00 = u0 + oc00, c10 = u0 + oc10, c01 = u1 + oc00, c11 = u1 + oc10;
             u = bilin2<PK>(w00, w10, w01, w11, unorm2<PK>(bytes2(lds_u8o<0>(c00), lds_u8o<0>(c10))), unorm2<PK>(bytes2(lds_u8o<2>(c00), lds_u8o<2>(c10))),
@@ -544,8 +513,7 @@ __device__ __forceinline__ int plan_layer(const uint32_t* __restrict__ tables, c
         jy0 = min(rA.i0, rB.i0);
         ic0 = min(ccA.i0, ccB.i0) & (L->format == SVB_NV12 ? ~7 : ~15);
         jc0 = min(rcA.i0, rcB.i0);
-        const bool lumaTex = SVB_TILED_LUMA_GATHER && (F->flags & SVB_FRAME_LUMA_TEX);  // luma is gathered: no luma box to fit
-        const bool fits = (lumaTex || (max(cA.i1, cB.i1) - iy0 < L->box_w && max(rA.i1, rB.i1) - jy0 < L->box_h)) && max(ccA.i1, ccB.i1) - ic0 < L->box_cw &&
+        const bool fits = max(cA.i1, cB.i1) - iy0 < L->box_w && max(rA.i1, rB.i1) - jy0 < L->box_h && max(ccA.i1, ccB.i1) - ic0 < L->box_cw &&
                           max(rcA.i1, rcB.i1) - jc0 < L->box_ch;
         // border, tx and uv are monotone too: both ends inside [0,1] means every pixel of the tile is inside the picture
         const bool full = cA.ok == 7 && cB.ok == 7 && rA.ok == 7 && rB.ok == 7;
@@ -575,8 +543,7 @@ __device__ __forceinline__ int plan_layer(const uint32_t* __restrict__ tables, c
         const unsigned long long cb = (unsigned long long)(tb.col + (x0 / SVB_TILE_W) * SVB_TAB_COL_WORDS), rb = (unsigned long long)(tb.row + (y0 / SVB_TILE_H) * SVB_TAB_ROW_WORDS);
         out[2] = make_int4((int)(unsigned)m0, (int)(m0 >> 32), (int)(unsigned)m1, (int)(m1 >> 32));
         out[3] = make_int4((int)(unsigned)m2, (int)(m2 >> 32), (int)(unsigned)cb, (int)(cb >> 32));
-        const int ybytes = (SVB_TILED_LUMA_GATHER && (F->flags & SVB_FRAME_LUMA_TEX)) ? 0 : L->box_w * L->box_h;
-        out[4] = make_int4((int)(unsigned)rb, (int)(rb >> 32), ybytes + cbytes * (n12 ? 1 : 2) + SVB_TILE_TAB_WORDS * 4, g.frame);
+        out[4] = make_int4((int)(unsigned)rb, (int)(rb >> 32), L->box_w * L->box_h + cbytes * (n12 ? 1 : 2) + SVB_TILE_TAB_WORDS * 4, g.frame);
     }
     return mode;
 }
@@ -737,7 +704,7 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CT
             uint8_t* const by = boxes + b * box_y_bytes;
             uint8_t* const bc = boxes + 2 * box_y_bytes + b * box_c_bytes;
             mbar_expect_tx(&sm.bar[b], q4.z);
-            if (!(SVB_TILED_LUMA_GATHER && ((frames + q4.w)->flags & SVB_FRAME_LUMA_TEX))) tma_load_2d(by, ptr(q2.x, q2.y), q0.y, q0.z, &sm.bar[b]);
+            tma_load_2d(by, ptr(q2.x, q2.y), q0.y, q0.z, &sm.bar[b]);
             tma_load_2d(bc, ptr(q2.z, q2.w), q0.w, q1.x, &sm.bar[b]);
             if (q3.x | q3.y) tma_load_2d(bc + box_c_bytes / 2, ptr(q3.x, q3.y), q0.w, q1.x, &sm.bar[b]);
             bulk_load(sm.tabs[b], ptr(q3.z, q3.w), SVB_TAB_COL_WORDS * 4, &sm.bar[b]);
@@ -825,9 +792,6 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CT
                     const unsigned bY = smem_u32(boxes + stage * box_y_bytes), bU = smem_u32(boxes + 2 * box_y_bytes + stage * box_c_bytes);
                     const unsigned bV = bU + (fmt == SVB_NV12 ? 1 : box_c_bytes / 2);
                     const float alpha = __int_as_float(p1.w);
-                    unsigned long long tU = 0, tV = 0, tY = 0;
-                    if (SVB_TILED_CHROMA_GATHER && (lflags & SVB_LAYER_TEX)) tU = F->layers[p0.x >> 8].tex[1], tV = F->layers[p0.x >> 8].tex[2];
-                    if (SVB_TILED_LUMA_GATHER && (h1.w & SVB_FRAME_LUMA_TEX) && (lflags & SVB_LAYER_TEX)) tY = F->layers[p0.x >> 8].tex[0];
                     FillTerms ft;
                     if (mode == PLAN_STAGED_EDGE || !(lflags & SVB_LAYER_OPACITY_01)) {
                         const SvbLayerDesc* __restrict__ L = &F->layers[p0.x >> 8];
@@ -848,14 +812,14 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CT
                         const bool lean = (lflags & SVB_LAYER_OPACITY_01) && !__any_sync(__activemask(), mixed);
                         // (both inlined: called out of line, with the running picture through a local array, the edge bodies cost 8 % of
                         // the whole kernel although edge tiles are one layer-tile in ten -- profiles/r1_history.md)
-                        if (lean) fast_layer<2, true, false>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi, 0ull, 0ull, tY);
-                        else fast_layer<3, true, false>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi, 0ull, 0ull, tY);
+                        if (lean) fast_layer<2, true, false>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
+                        else fast_layer<3, true, false>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
                     } else if (lflags & SVB_LAYER_UNIT_OPACITY) {
-                        if (fmt == SVB_NV12) fast_layer<0, true, true>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi, tU, tV, tY);
-                        else fast_layer<0, true, false>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi, tU, tV, tY);
+                        if (fmt == SVB_NV12) fast_layer<0, true, true>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
+                        else fast_layer<0, true, false>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
                     } else {
-                        if (fmt == SVB_NV12) fast_layer<1, true, true>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi, tU, tV, tY);
-                        else fast_layer<1, true, false>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi, tU, tV, tY);
+                        if (fmt == SVB_NV12) fast_layer<1, true, true>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
+                        else fast_layer<1, true, false>(bY, bU, bV, sm.tabs[stage], lane, warp, p0.y, p0.z, p0.w, jc0, box_w, pitchC, stepC, alpha, one, ft, Yi, Ui, Vi);
                     }
                 }
                 stage ^= 1;

@@ -365,19 +365,10 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
             for (int l = 0; l < fr.nlayers; ++l)
                 if ((fr.layers[l].flags & SVB_LAYER_STAGED) && !(fr.layers[l].flags & SVB_LAYER_TEX)) gather = false;
         }
-        // (SVB_TILED_LUMA_GATHER builds) the TMA compositor gathers luma and copies no luma boxes when every staged layer has textures
-        bool lumaTex = SVB_TILED_LUMA_GATHER && tiled && !gather;
-        for (int i = 0; lumaTex && i < n; ++i) {
-            const SvbFrameDesc& fr = frames[start + i];
-            for (int l = 0; l < fr.nlayers; ++l)
-                if ((fr.layers[l].flags & SVB_LAYER_STAGED) && !(fr.layers[l].flags & SVB_LAYER_TEX)) lumaTex = false;
-        }
         for (int i = 0; i < n; ++i) {
             SvbFrameDesc& fr = frames[start + i];
             if (gather) fr.flags |= SVB_FRAME_GATHER;
             else fr.flags &= ~SVB_FRAME_GATHER;
-            if (lumaTex) fr.flags |= SVB_FRAME_LUMA_TEX;
-            else fr.flags &= ~SVB_FRAME_LUMA_TEX;
             for (int l = 0; l < fr.nlayers; ++l) {
                 const SvbLayerDesc& L = fr.layers[l];
                 if (!(L.flags & SVB_LAYER_STAGED)) continue;
@@ -439,7 +430,6 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
                 check(d.cuLaunchKernel(sh.fGather, grid, 1, 1, SVB_TILED_THREADS, 1, 1, 0, ic.compute, args, nullptr), "cuLaunchKernel(svb_mix_gather)");
                 noteKernelLaunch();
             } else {
-                if (lumaTex) boxY = 0;  // luma comes through the texture unit: no luma boxes in shared memory
                 void* args[] = {&dev, &plans, &total, &one, &counter, &boxY, &boxC};
                 // shared memory: the fixed part plus two box pairs sized for the largest staged footprint of this batch
                 size_t smem = SVB_TILED_SMEM_BYTES((size_t)boxY, (size_t)boxC);

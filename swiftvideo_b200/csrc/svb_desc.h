@@ -31,14 +31,8 @@ enum SvbFormat { SVB_NV12 = 0, SVB_Y420P = 1, SVB_BGRA = 2, SVB_RGBA = 3 };
 enum {
     SVB_FRAME_LOAD_CUR = 1,   // continue an earlier pass: start from the target's bytes, not from clear
     SVB_FRAME_SCALAR_FP = 2,  // tuning aid: spell the packed fp32x2 arithmetic as scalar instructions (same results)
-    SVB_FRAME_GATHER = 4,     // the batch goes to svb_mix_gather: plan separable YUV layers for the texture path (no staging limits)
-    SVB_FRAME_LUMA_TEX = 8    // (SVB_TILED_LUMA_GATHER builds) every staged layer of the batch has textures: svb_mix_tiled gathers luma, no luma boxes
+    SVB_FRAME_GATHER = 4      // the batch goes to svb_mix_gather: plan separable YUV layers for the texture path (no staging limits)
 };
-// EXPERIMENT, off and not yet measured: svb_mix_tiled fetches LUMA footprints with tex2Dgather and stages only chroma (see
-// kernels_tiled.cuh); host and device both need to know, hence here.
-#ifndef SVB_TILED_LUMA_GATHER
-#define SVB_TILED_LUMA_GATHER 0
-#endif
 enum {
     SVB_LAYER_SEPARABLE = 1,     // x outputs depend only on x and y outputs only on y (no rotation/shear)
     SVB_LAYER_UNIT_OPACITY = 2,  // opacity == 1: cur*(1-1) + v*1 == v exactly, the blend is skipped
