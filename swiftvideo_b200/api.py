@@ -18,7 +18,7 @@ KERNEL_CUSTOM = 15
 
 
 class MixMode:
-    FUSED, PER_LAYER, GENERIC, FUSED_GATHER = 0, 1, 2, 3
+    FUSED, PER_LAYER, GENERIC, FUSED_GATHER, FUSED_TILED = 0, 1, 2, 3, 4
 
 
 STATUS_NAMES = ["ok", "invalidPlatform", "invalidDevice", "invalidOperation", "invalidValue", "invalidProgram", "invalidContext",

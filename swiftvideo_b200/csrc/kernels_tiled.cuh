@@ -79,7 +79,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
     for (unsigned spin = 0; !mbar_try(bar, parity); ++spin)
         if (spin > (1u << 24)) __trap();
 }
-// descriptors are rewritten by the host between launches: make the tensormap proxy re-read them
+// a tensor-map slot that the host has REWRITTEN (SVB_FRAME_TMAP_FENCE, svb_desc.h): make the tensormap proxy re-read it
 __device__ __forceinline__ void tmap_acquire(const void* tmap) {
     asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmap) : "memory");
 }
@@ -539,7 +539,7 @@ __device__ __forceinline__ int plan_layer(const uint32_t* __restrict__ tables, c
         const bool n12 = L->format == SVB_NV12;
         const int cbytes = n12 ? L->box_cw * L->box_ch * 2 : L->box_cw * L->box_ch;
         const Tabs tb = layer_tabs(tables, F, l);
-        const unsigned long long m0 = (unsigned long long)L->tmap[0], m1 = (unsigned long long)L->tmap[1], m2 = n12 ? 0ull : (unsigned long long)L->tmap[2];
+        const unsigned long long m0 = L->tmap[0], m1 = L->tmap[1], m2 = n12 ? 0ull : L->tmap[2];
         const unsigned long long cb = (unsigned long long)(tb.col + (x0 / SVB_TILE_W) * SVB_TAB_COL_WORDS), rb = (unsigned long long)(tb.row + (y0 / SVB_TILE_H) * SVB_TAB_ROW_WORDS);
         out[2] = make_int4((int)(unsigned)m0, (int)(m0 >> 32), (int)(unsigned)m1, (int)(m1 >> 32));
         out[3] = make_int4((int)(unsigned)m2, (int)(m2 >> 32), (int)(unsigned)cb, (int)(cb >> 32));
@@ -691,14 +691,15 @@ extern "C" __global__ void __launch_bounds__(SVB_TILED_THREADS, SVB_TILED_MIN_CT
         auto issue = [&](const int4(*pl)[5], int i, int b) {
             const int4 q0 = pl[i][0], q1 = pl[i][1], q2 = pl[i][2], q3 = pl[i][3], q4 = pl[i][4];
             auto ptr = [](int lo, int hi) { return (const void*)(((unsigned long long)(unsigned)hi << 32) | (unsigned)lo); };
-            if (q4.w != fenced) {  // the host rewrites the descriptors between launches: acquire a frame's maps once per CTA
+            if (q4.w != fenced) {  // (only after the context's tensor-map table has wrapped) acquire a frame's maps once per CTA
                 const SvbFrameDesc* __restrict__ TF = frames + q4.w;
-                for (int q = 0; q < TF->nlayers; ++q)
-                    if (TF->layers[q].flags & SVB_LAYER_STAGED) {
-                        tmap_acquire(TF->layers[q].tmap[0]);
-                        tmap_acquire(TF->layers[q].tmap[1]);
-                        if (TF->layers[q].format != SVB_NV12) tmap_acquire(TF->layers[q].tmap[2]);
-                    }
+                if (TF->flags & SVB_FRAME_TMAP_FENCE)
+                    for (int q = 0; q < TF->nlayers; ++q)
+                        if (TF->layers[q].flags & SVB_LAYER_STAGED) {
+                            tmap_acquire((const void*)TF->layers[q].tmap[0]);
+                            tmap_acquire((const void*)TF->layers[q].tmap[1]);
+                            if (TF->layers[q].format != SVB_NV12) tmap_acquire((const void*)TF->layers[q].tmap[2]);
+                        }
                 fenced = q4.w;
             }
             uint8_t* const by = boxes + b * box_y_bytes;

@@ -40,11 +40,19 @@ struct MixerShared {
     CUdeviceptr tabBuf[kSegments] = {};
     size_t tabBytes[kSegments] = {};
     int next = 0;
-    std::map<std::array<uint64_t, 4>, std::array<uint8_t, 128>> tmaps;
-    CUfunction fTiled = nullptr, fGather = nullptr, fGeneric = nullptr, fTables = nullptr;
+    // Tensor maps: a table in device memory, grown by chunks.  A slot is written once (a synchronous 128-byte copy when a new
+    // plane geometry first appears) and never again, so kernels need no tensormap-proxy fence; only when the table would exceed
+    // kTmapMaxChunks does it wrap around, and from then on every launch carries SVB_FRAME_TMAP_FENCE.
+    static constexpr int kTmapChunk = 4096, kTmapMaxChunks = 64;
+    std::map<std::array<uint64_t, 4>, CUdeviceptr> tmaps;
+    std::vector<CUdeviceptr> tmapChunks;
+    int tmapChunkAt = -1, tmapUsed = 0;
+    bool tmapFence = false;
+    CUfunction fTiled = nullptr, fGather = nullptr, fGeneric = nullptr, fTables = nullptr, fStrip = nullptr, fStripTables = nullptr;
     int gatherCtasPerSm = 0;
     int texAlign = 512, texPitchAlign = 32;
     std::map<std::array<uint64_t, 3>, CUtexObject> texs;  // texture objects over source planes by (pointer, size, pitch | channels)
+    std::map<size_t, int> stripCtasPerSm;  // the same for svb_mix_strip
     std::map<size_t, int> tiledCtasPerSm;  // resident CTAs of svb_mix_tiled per SM by dynamic shared memory size: the persistent grid is smCount times this
     std::mutex mu;
     // optional per-launch device timing of the fused kernels (bench.py's roofline leg)
@@ -78,6 +86,7 @@ void freeShared(InternalContext* ic) {
     for (CUdeviceptr b : s->tabBuf)
         if (b) cu().cuMemFree(b);
     for (auto& kv : s->texs) cu().cuTexObjectDestroy(kv.second);
+    for (CUdeviceptr c : s->tmapChunks) cu().cuMemFree(c);
     if (s->prep) cu().cuStreamDestroy(s->prep);
     for (auto* v : {&s->timed, &s->spare})
         for (auto& pr : *v) {
@@ -115,6 +124,10 @@ MixerShared& shared(const std::shared_ptr<InternalContext>& ic) {  // caller hol
             if (s->texPitchAlign <= 0) s->texPitchAlign = 32;
         }
         s->fGeneric = ic->builtin("svb_mix_generic");
+        s->fStrip = ic->builtin("svb_mix_strip");
+        check(drv().cuFuncSetAttribute(s->fStrip, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, SVB_STRIP_SMEM_BYTES(SVB_SBOX_Y_BYTES, SVB_SBOX_C_BYTES, SVB_MAX_LAYERS)),
+              "cuFuncSetAttribute(max dynamic shared memory)");
+        s->fStripTables = ic->builtin("svb_strip_tables");
     }
     return *(MixerShared*)ic->mixerShared;
 }
@@ -137,8 +150,9 @@ bool finite16(const float* m) {
 
 int roundUp(int v, int m) { return (v + m - 1) / m * m; }
 
-// 2-D tensor map over one plane; cached, the encode costs ~1 us and layers rarely change geometry.
-bool tensorMap(MixerShared& sh, unsigned char out[128], CUdeviceptr ptr, int elemBytes, int w, int h, int strideBytes, int boxW, int boxH) {
+// 2-D tensor map over one plane, in the context's device table; cached by plane and box (the encode costs ~1 us, the first use of a
+// geometry one small synchronous copy; the device pool recycles blocks, so the same few planes come round).  out = the slot's address.
+bool tensorMap(MixerShared& sh, unsigned long long* out, CUdeviceptr ptr, int elemBytes, int w, int h, int strideBytes, int boxW, int boxH) {
     if ((ptr & 15) || (strideBytes & 15) || w <= 0 || h <= 0 || boxW > 256 || boxH > 256 || (boxW * elemBytes) % 16) return false;
     std::lock_guard<std::mutex> lock(sh.mu);  // mixers of one context may plan from different threads
     const std::array<uint64_t, 4> key = {(uint64_t)ptr, ((uint64_t)(uint32_t)w << 32) | (uint32_t)h,
@@ -147,6 +161,7 @@ bool tensorMap(MixerShared& sh, unsigned char out[128], CUdeviceptr ptr, int ele
     auto it = sh.tmaps.find(key);
     if (it == sh.tmaps.end()) {
         alignas(64) CUtensorMap tm;
+        static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
         const cuuint64_t gdim[2] = {(cuuint64_t)w, (cuuint64_t)h};
         const cuuint64_t gstride[1] = {(cuuint64_t)strideBytes};
         const cuuint32_t box[2] = {(cuuint32_t)boxW, (cuuint32_t)boxH};
@@ -156,13 +171,26 @@ bool tensorMap(MixerShared& sh, unsigned char out[128], CUdeviceptr ptr, int ele
                                                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return false;
-        if (sh.tmaps.size() > 8192) sh.tmaps.clear();
-        std::array<uint8_t, 128> bytes;
-        static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
-        std::memcpy(bytes.data(), &tm, 128);
-        it = sh.tmaps.emplace(key, bytes).first;
+        if (sh.tmapChunkAt < 0 || sh.tmapUsed == MixerShared::kTmapChunk) {
+            if ((int)sh.tmapChunks.size() < MixerShared::kTmapMaxChunks) {
+                CUdeviceptr c = 0;
+                if (drv().cuMemAlloc(&c, (size_t)MixerShared::kTmapChunk * 128) != CUDA_SUCCESS) return false;
+                sh.tmapChunks.push_back(c);
+                sh.tmapChunkAt = (int)sh.tmapChunks.size() - 1;
+            } else {  // wrap: slots are rewritten from here on -- launches in flight finish first, later ones fence
+                if (drv().cuCtxSynchronize() != CUDA_SUCCESS) return false;
+                sh.tmapChunkAt = (sh.tmapChunkAt + 1) % MixerShared::kTmapMaxChunks;
+                sh.tmaps.clear();
+                sh.tmapFence = true;
+            }
+            sh.tmapUsed = 0;
+        }
+        const CUdeviceptr slot = sh.tmapChunks[sh.tmapChunkAt] + (size_t)sh.tmapUsed * 128;
+        if (drv().cuMemcpyHtoD(slot, &tm, 128) != CUDA_SUCCESS) return false;
+        ++sh.tmapUsed;
+        it = sh.tmaps.emplace(key, slot).first;
     }
-    std::memcpy(out, it->second.data(), 128);
+    *out = (unsigned long long)it->second;
     return true;
 }
 
@@ -301,12 +329,32 @@ FramePlan planFrame(const ComputeContext& ctx, const PictureSample& target, cons
             const int cbytes = bcw * bch * (sf == SVB_NV12 ? 2 : 1);
             const bool fits = std::isfinite(sx) && std::isfinite(sy) && bw <= 256 && bh <= 256 && bw * bh <= SVB_BOX_Y_BYTES &&
                               bcw <= 256 && bch <= 256 && cbytes <= (sf == SVB_NV12 ? SVB_BOX_C_BYTES : SVB_BOX_C_BYTES / 2);
-            if (!noTma && fits && tensorMap(sh, L.tmap[0], L.plane[0], 1, L.width, L.height, L.stride[0], bw, bh) &&
-                (sf == SVB_NV12 ? tensorMap(sh, L.tmap[1], L.plane[1], 2, cw, ch, L.stride[1], bcw, bch)
-                                : (tensorMap(sh, L.tmap[1], L.plane[1], 1, cw, ch, L.stride[1], bcw, bch) &&
-                                   tensorMap(sh, L.tmap[2], L.plane[2], 1, cw, ch, L.stride[2], bcw, bch)))) {
+            if (!noTma && fits && tensorMap(sh, &L.tmap[0], L.plane[0], 1, L.width, L.height, L.stride[0], bw, bh) &&
+                (sf == SVB_NV12 ? tensorMap(sh, &L.tmap[1], L.plane[1], 2, cw, ch, L.stride[1], bcw, bch)
+                                : (tensorMap(sh, &L.tmap[1], L.plane[1], 1, cw, ch, L.stride[1], bcw, bch) &&
+                                   tensorMap(sh, &L.tmap[2], L.plane[2], 1, cw, ch, L.stride[2], bcw, bch)))) {
                 flags |= SVB_LAYER_STAGED;
                 L.box_w = bw, L.box_h = bh, L.box_cw = bcw, L.box_ch = bch;
+            }
+        }
+        if ((flags & SVB_LAYER_SEPARABLE) && (sf == SVB_NV12 || sf == SVB_Y420P) && L.width >= 2 && L.height >= 2) {
+            // svb_mix_strip: boxes that hold the footprint of one 64x8 unit (a warp stages its own)
+            const double sx = std::fabs((double)L.width * X[0] * T[0] * 2.0 / W), sy = std::fabs((double)L.height * X[5] * T[5] * 2.0 / H);
+            const int cw = L.width / 2, ch = L.height / 2;
+            const int bw = roundUp((int)std::ceil(sx * (SVB_UNIT_W - 1)) + 3 + 15, 16), bh = (int)std::ceil(sy * (SVB_UNIT_H - 1)) + 3;
+            const int bcw = sf == SVB_NV12 ? roundUp((int)std::ceil(sx * 0.5 * (SVB_UNIT_W - 2)) + 3 + 7, 8)
+                                           : roundUp((int)std::ceil(sx * 0.5 * (SVB_UNIT_W - 2)) + 3 + 15, 16);
+            const int bch = (int)std::ceil(sy * 0.5 * (SVB_UNIT_H - 2)) + 3;
+            const int cbytes = bcw * bch * (sf == SVB_NV12 ? 2 : 1);
+            const bool fits = std::isfinite(sx) && std::isfinite(sy) && bw <= 256 && bh <= 256 && bw * bh <= SVB_SBOX_Y_BYTES && bcw <= 256 && bch <= 256 &&
+                              cbytes <= (sf == SVB_NV12 ? SVB_SBOX_C_BYTES : SVB_SBOX_C_BYTES / 2);
+            if (!noTma && fits && tensorMap(sh, &L.stmap[0], L.plane[0], 1, L.width, L.height, L.stride[0], bw, bh) &&
+                (sf == SVB_NV12 ? tensorMap(sh, &L.stmap[1], L.plane[1], 2, cw, ch, L.stride[1], bcw, bch)
+                                : (tensorMap(sh, &L.stmap[1], L.plane[1], 1, cw, ch, L.stride[1], bcw, bch) &&
+                                   tensorMap(sh, &L.stmap[2], L.plane[2], 1, cw, ch, L.stride[2], bcw, bch)))) {
+                flags |= SVB_LAYER_STAGED_S;
+                L.sbox_w = bw, L.sbox_h = bh, L.sbox_cw = bcw, L.sbox_ch = bch;
+                L.stx_bytes = bw * bh + (sf == SVB_NV12 ? cbytes : 2 * cbytes) + SVB_STRIP_TAB_BYTES;
             }
         }
         if ((flags & SVB_LAYER_SEPARABLE) && (sf == SVB_NV12 || sf == SVB_Y420P) && L.width >= 2 && L.height >= 2) {
@@ -328,19 +376,22 @@ FramePlan planFrame(const ComputeContext& ctx, const PictureSample& target, cons
 
 namespace {
 
-// SVB_COMPOSITOR=gather|tma picks the fused compositor (default below); read once.
-bool gatherByDefault() {
+// SVB_COMPOSITOR=strip|tma|gather picks the fused compositor (default: strip = svb_mix_strip; tma = svb_mix_tiled, the round-1
+// kernel, which also takes the batches whose footprints are too large for a warp's own boxes); read once.
+int compositorChoice() {  // 0 strip, 1 tiled, 2 gather
     static const int v = [] {
         const char* e = std::getenv("SVB_COMPOSITOR");
-        if (e && std::strcmp(e, "gather") == 0) return 1;
-        if (e && std::strcmp(e, "tma") == 0) return 0;
-        return SVB_DEFAULT_GATHER;
+        if (e && std::strcmp(e, "gather") == 0) return 2;
+        if (e && (std::strcmp(e, "tma") == 0 || std::strcmp(e, "tiled") == 0)) return 1;
+        if (e && std::strcmp(e, "strip") == 0) return 0;
+        return SVB_DEFAULT_GATHER ? 2 : 0;
     }();
-    return v != 0;
+    return v;
 }
+bool gatherByDefault() { return compositorChoice() == 2; }
 
 // One launch over `frames` (all tiled-capable, or all generic).  Caller holds a CtxGuard.
-void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, bool tiled, bool wantGather) {
+void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, bool tiled, bool wantGather, bool wantTiled) {
     const CuDriver& d = drv();
     MixerShared& sh = shared(ctx.ctx);
     InternalContext& ic = *ctx.ctx;
@@ -365,22 +416,54 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
             for (int l = 0; l < fr.nlayers; ++l)
                 if ((fr.layers[l].flags & SVB_LAYER_STAGED) && !(fr.layers[l].flags & SVB_LAYER_TEX)) gather = false;
         }
+        // svb_mix_strip (a warp stages its own 64x8 footprint) unless a layer that the tiled kernel can stage does not fit a warp's boxes
+        bool strip = tiled && !gather && !wantTiled && compositorChoice() == 0;
+        for (int i = 0; strip && i < n; ++i) {
+            const SvbFrameDesc& fr = frames[start + i];
+            for (int l = 0; l < fr.nlayers; ++l)
+                if ((fr.layers[l].flags & SVB_LAYER_STAGED) && !(fr.layers[l].flags & SVB_LAYER_STAGED_S)) strip = false;
+        }
         for (int i = 0; i < n; ++i) {
             SvbFrameDesc& fr = frames[start + i];
             if (gather) fr.flags |= SVB_FRAME_GATHER;
             else fr.flags &= ~SVB_FRAME_GATHER;
+            if (sh.tmapFence) fr.flags |= SVB_FRAME_TMAP_FENCE;
             for (int l = 0; l < fr.nlayers; ++l) {
                 const SvbLayerDesc& L = fr.layers[l];
+                if (strip) {
+                    if (!(L.flags & SVB_LAYER_STAGED_S)) continue;
+                    boxY = std::max(boxY, roundUp(L.sbox_w * L.sbox_h, 128));
+                    boxC = std::max(boxC, L.format == SVB_NV12 ? roundUp(L.sbox_cw * L.sbox_ch * 2, 128) : 2 * roundUp(L.sbox_cw * L.sbox_ch, 128));
+                    continue;
+                }
                 if (!(L.flags & SVB_LAYER_STAGED)) continue;
                 boxY = std::max(boxY, roundUp(L.box_w * L.box_h, 256));
                 boxC = std::max(boxC, L.format == SVB_NV12 ? roundUp(L.box_cw * L.box_ch * 2, 256) : 2 * roundUp(L.box_cw * L.box_ch, 128));
             }
+            // (a strip batch counts 64x8 units where a tiled batch counts 128x32 tiles: same fields)
+            fr.tiles_x = strip ? SVB_UNITS_X(fr.width) : SVB_TILES_X(fr.width);
+            fr.tiles_y = strip ? SVB_UNITS_Y(fr.height) : SVB_TILES_Y(fr.height);
             fr.first_tile = total;
             total += fr.tiles_x * fr.tiles_y;
             maxTiles = std::max(maxTiles, fr.tiles_x * fr.tiles_y);
             maxW = std::max(maxW, fr.width), maxH = std::max(maxH, fr.height);
-            const int ents = SVB_TABLE_WORDS(fr.width, fr.height);  // 4-byte words per layer
+            const int ents = strip ? SVB_UTABLE_WORDS(fr.width, fr.height) : SVB_TABLE_WORDS(fr.width, fr.height);  // 4-byte words per layer
             fr.table_base = (int32_t)tableEnts;
+            if (strip)
+                for (int l = 0; l < fr.nlayers; ++l) {  // what a planning lane of svb_mix_strip reads of its layer
+                    SvbLayerDesc& L = fr.layers[l];
+                    SvbStripConsts& c = L.pc;
+                    c.stmapY[0] = (uint32_t)L.stmap[0], c.stmapY[1] = (uint32_t)(L.stmap[0] >> 32);
+                    c.stmapC[0] = (uint32_t)L.stmap[1], c.stmapC[1] = (uint32_t)(L.stmap[1] >> 32);
+                    c.stmapV[0] = (uint32_t)L.stmap[2], c.stmapV[1] = (uint32_t)(L.stmap[2] >> 32);
+                    c.stx_bytes = (uint32_t)L.stx_bytes;
+                    c.pitches = (uint32_t)L.sbox_w | ((uint32_t)(L.format == SVB_NV12 ? 2 * L.sbox_cw : L.sbox_cw) << 16);
+                    std::memcpy(&c.opacity_bits, &L.u.opacity, 4);
+                    c.fmtflags = (uint32_t)L.format | ((uint32_t)(L.flags & 0xff) << 8);
+                    c.tab = (uint32_t)(tableEnts + (size_t)l * (size_t)ents);
+                    c.rec = c.tab + (uint32_t)(fr.tiles_x * SVB_UCOL_WORDS + fr.tiles_y * SVB_UROW_WORDS);
+                    std::memcpy(c.rect, L.rect, sizeof(c.rect));
+                }
             tableEnts += (size_t)ents * (size_t)fr.nlayers;
             maxLayers = std::max(maxLayers, fr.nlayers), maxEnts = std::max(maxEnts, ents);
             // copy only the header and the layers in use
@@ -405,7 +488,7 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
             // tile; then the compositor (+ the tile counter it claims its work from, zeroed by the pre-pass)
             const size_t counterOff = (std::max<size_t>(tableEnts, 4) * 4 + 15) & ~(size_t)15;
             const size_t plansOff = counterOff + 16;
-            const size_t tableBytes = plansOff + (size_t)total * sizeof(SvbTilePlan);
+            const size_t tableBytes = plansOff + (strip ? 0 : (size_t)total * sizeof(SvbTilePlan));  // (a strip batch has no plans in global memory: warps plan their own units)
             if (sh.tabBytes[seg] < tableBytes) {  // the segment is idle here (ev[seg] waited for above)
                 if (sh.tabBuf[seg]) check(d.cuMemFree(sh.tabBuf[seg]), "cuMemFree");
                 sh.tabBuf[seg] = 0, sh.tabBytes[seg] = 0;
@@ -414,16 +497,43 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
             }
             CUdeviceptr tables = sh.tabBuf[seg];
             CUdeviceptr counter = tables + counterOff, plans = tables + plansOff;
-            int tableBlocks = (maxEnts / 2 + 255) / 256;
-            void* targs[] = {&dev, &tables, &counter, &plans, &tableBlocks, &maxLayers};
-            check(d.cuLaunchKernel(sh.fTables, (unsigned)(tableBlocks * maxLayers + (maxTiles + 7) / 8), 1, (unsigned)n, 256, 1, 1, 0, sh.prep, targs, nullptr),
-                  "cuLaunchKernel(svb_mix_tables)");
-            noteKernelLaunch();
+            if (strip) {
+                // one pre-pass launch: a block per unit column and per unit row of every layer fills its table block and its plan record
+                int blocks = 1;
+                for (int i = 0; i < n; ++i) blocks = std::max(blocks, frames[start + i].tiles_x + frames[start + i].tiles_y);
+                void* targs[] = {&dev, &tables, &counter};
+                check(d.cuLaunchKernel(sh.fStripTables, (unsigned)blocks, (unsigned)maxLayers, (unsigned)n, 96, 1, 1, 0, sh.prep, targs, nullptr), "cuLaunchKernel(svb_strip_tables)");
+                noteKernelLaunch();
+            } else {
+                int tableBlocks = (maxEnts / 2 + 255) / 256;
+                void* targs[] = {&dev, &tables, &counter, &plans, &tableBlocks, &maxLayers};
+                check(d.cuLaunchKernel(sh.fTables, (unsigned)(tableBlocks * maxLayers + (maxTiles + 7) / 8), 1, (unsigned)n, 256, 1, 1, 0, sh.prep, targs, nullptr),
+                      "cuLaunchKernel(svb_mix_tables)");
+                noteKernelLaunch();
+            }
             check(d.cuEventRecord(sh.evPrep[seg], sh.prep), "cuEventRecord");
             check(d.cuStreamWaitEvent(ic.compute, sh.evPrep[seg], 0), "cuStreamWaitEvent");
             if (tev.first) check(d.cuEventRecord(tev.first, ic.compute), "cuEventRecord");  // time svb_mix_tiled alone
             float one = 1.0f;  // see add2() in kernels_tiled.cuh
-            if (gather) {
+            if (strip) {
+                int nf = n, slotBytes = SVB_UPLAN_SLOT_BYTES(maxLayers);
+                void* args[] = {&dev, &tables, &nf, &total, &one, &counter, &boxY, &boxC, &slotBytes};
+                size_t smem = SVB_STRIP_SMEM_BYTES((size_t)boxY, (size_t)boxC, maxLayers);
+                int perSm;
+                {
+                    std::lock_guard<std::mutex> g(sh.mu);
+                    auto it = sh.stripCtasPerSm.find(smem);
+                    if (it == sh.stripCtasPerSm.end()) {
+                        int nb = 0;
+                        check(d.cuOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sh.fStrip, SVB_STRIP_THREADS, smem), "cuOccupancyMaxActiveBlocksPerMultiprocessor");
+                        it = sh.stripCtasPerSm.emplace(smem, std::max(1, nb)).first;
+                    }
+                    perSm = it->second;
+                }
+                const unsigned grid = (unsigned)std::min((total + SVB_STRIP_WARPS - 1) / SVB_STRIP_WARPS, ic.smCount * perSm);
+                check(d.cuLaunchKernel(sh.fStrip, grid, 1, 1, SVB_STRIP_THREADS, 1, 1, (unsigned)smem, ic.compute, args, nullptr), "cuLaunchKernel(svb_mix_strip)");
+                noteKernelLaunch();
+            } else if (gather) {
                 int units = total * SVB_GATHER_STRIPS;  // (tile, strip) pairs, claimed by warps
                 void* args[] = {&dev, &plans, &units, &one, &counter};
                 const unsigned grid = (unsigned)std::min((units + SVB_TILED_COMPUTE_WARPS - 1) / SVB_TILED_COMPUTE_WARPS, ic.smCount * sh.gatherCtasPerSm);
@@ -479,7 +589,7 @@ struct Job {
 };
 
 // Fused compose of several independent targets on one context.
-void composeFused(const ComputeContext& ctx, std::vector<Job>& jobs, bool forceGeneric, bool wantGather = false) {
+void composeFused(const ComputeContext& ctx, std::vector<Job>& jobs, bool forceGeneric, bool wantGather = false, bool wantTiled = false) {
     CtxGuard g(ctx.ctx);
     std::vector<FramePlan> plans;
     bool allTiled = !forceGeneric;
@@ -495,7 +605,7 @@ void composeFused(const ComputeContext& ctx, std::vector<Job>& jobs, bool forceG
         std::vector<SvbFrameDesc> frames;
         for (FramePlan& pl : plans)
             if (p < pl.passes.size()) frames.push_back(pl.passes[p]);
-        launchFrames(ctx, frames, allTiled, wantGather);
+        launchFrames(ctx, frames, allTiled, wantGather, wantTiled);
     }
     for (Job& j : jobs) markWritten(ctx, *j.target);
 }
@@ -615,7 +725,7 @@ ComputeContext VideoMixer::composeRaw(const ComputeContext& ctxIn, const Picture
     jobs[0].target = &target;
     jobs[0].layers = layers;
     jobs[0].uniforms.assign(uniforms, uniforms + layers.size());
-    composeFused(ctxIn, jobs, mode == Mode::generic, mode == Mode::fusedGather);
+    composeFused(ctxIn, jobs, mode == Mode::generic, mode == Mode::fusedGather, mode == Mode::fusedTiled);
     return ctxIn;
 }
 
@@ -652,7 +762,7 @@ void VideoMixer::mixMany(VideoMixer* const* mixers, int n, int64_t time, Picture
     ComputeContext ctx0 = mixers[0]->clContext;
     if (fusedAll) {
         jobs.resize(n);
-        bool generic = false, wantGather = false;
+        bool generic = false, wantGather = false, wantTiled = false;
         for (int i = 0; i < n; ++i) {
             Tick& tk = ticks[i];
             jobs[i].target = &tk.backing;
@@ -665,8 +775,9 @@ void VideoMixer::mixMany(VideoMixer* const* mixers, int n, int64_t time, Picture
             }
             generic = generic || mixers[i]->mode == Mode::generic;
             wantGather = wantGather || mixers[i]->mode == Mode::fusedGather;
+            wantTiled = wantTiled || mixers[i]->mode == Mode::fusedTiled;
         }
-        composeFused(ctx0, jobs, generic, wantGather);
+        composeFused(ctx0, jobs, generic, wantGather, wantTiled);
     } else {
         for (int i = 0; i < n; ++i) {
             Tick& tk = ticks[i];

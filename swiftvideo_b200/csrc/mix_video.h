@@ -26,7 +26,8 @@ class VideoMixer {
         fused = 0,     // tiled kernel where its preconditions hold, else the generic fused kernel
         perLayer = 1,  // the reference's own sequence: clear kernel + one applyComputeImage per layer
         generic = 2,   // the generic fused kernel only
-        fusedGather = 3  // fused, with svb_mix_gather (taps through the texture unit) wherever every staged layer can be bound as a texture
+        fusedGather = 3,  // fused, with svb_mix_gather (taps through the texture unit) wherever every staged layer can be bound as a texture
+        fusedTiled = 4    // fused, with svb_mix_tiled (the CTA-per-tile TMA compositor of round 1) instead of svb_mix_strip
     };
 
     VideoMixer(const ComputeContext* computeContext, Vector2 outputSize, PixelFormat outputFormat = PixelFormat::nv12,

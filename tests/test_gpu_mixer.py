@@ -28,11 +28,11 @@ def _oracle_mix(target_fmt, canvas, placed, images):
         C.memmove(C.byref(ou), C.byref(u), 236)
         us.append(ou)
     want = O.Image(target_fmt, canvas[0], canvas[1])
-    assert O.port().mix(want, images, us) == 0
+    assert O.best()[0].mix(want, images, us) == 0
     return want.data
 
 
-@pytest.mark.parametrize("mode", [sv.MixMode.FUSED, sv.MixMode.PER_LAYER, sv.MixMode.GENERIC])
+@pytest.mark.parametrize("mode", [sv.MixMode.FUSED, sv.MixMode.FUSED_TILED, sv.MixMode.PER_LAYER, sv.MixMode.GENERIC])
 def test_mixer_z_order_and_generations(mode):
     ctx = context()
     canvas = (256, 128)
@@ -57,7 +57,7 @@ def test_mixer_z_order_and_generations(mode):
     # ... and is gone one tick later: only the clear remains
     got3 = fetch(ctx, mixer.mix(3000))
     clear = O.Image(O.NV12, *canvas)
-    O.port().clear(clear)
+    O.best()[0].clear(clear)
     assert (got3 == clear.data).all()
     # a newer sample of the same revision replaces the older one
     mixer.push(placed[0])
@@ -97,7 +97,7 @@ def test_mixer_errors():
         mixer.mix(1)
     out = mixer.mix(2)
     clear = O.Image(O.NV12, 64, 32)
-    O.port().clear(clear)
+    O.best()[0].clear(clear)
     assert (fetch(ctx, out) == clear.data).all()
     # nv12 -> y420p has no kernel name in the map: defaultComputeKernelFromString throws invalidValue (compute.swift:105-108)
     m2 = sv.VideoMixer(ctx, 64, 32, sv.Y420P, asset_id="m2")
@@ -109,7 +109,7 @@ def test_mixer_errors():
     m3 = sv.VideoMixer(ctx, 64, 32, sv.BGRA, asset_id="m3")
     got = fetch(ctx, m3.mix(0))
     want = O.Image(O.BGRA, 64, 32)
-    O.port().clear(want)
+    O.best()[0].clear(want)
     assert (got == want.data).all()
     m3.push(to_gpu(ctx, scenes.random_image(O.BGRA, 64, 32, 2), "b"))
     with pytest.raises(sv.ComputeError) as e:

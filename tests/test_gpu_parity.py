@@ -1,7 +1,9 @@
 """-m gpu: the CUDA path through the C ABI against the oracle -- bit-exact bytes.
 
-Every case runs in all three compose modes: the tiled TMA kernel (FUSED), the generic fused kernel (GENERIC)
-and the reference's own per-layer launch sequence over the drop-in kernels (PER_LAYER)."""
+Every case runs in four compose modes: svb_mix_strip (FUSED, the product path: a warp stages and composites its own 64x8
+unit), svb_mix_tiled (FUSED_TILED, the CTA-per-tile TMA kernel of round 1), the generic fused kernel (GENERIC) and the
+reference's own per-layer launch sequence over the drop-in kernels (PER_LAYER).  The checker is O.best(): the reference's own
+OpenCL kernel text compiled as C++ (oracle/_ref) wherever that build is present, else the C restatement."""
 import numpy as np
 import pytest
 
@@ -12,7 +14,8 @@ from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
 
-MODES = [(sv.MixMode.FUSED, "fused"), (sv.MixMode.GENERIC, "generic"), (sv.MixMode.PER_LAYER, "per_layer")]
+MODES = [(sv.MixMode.FUSED, "fused"), (sv.MixMode.FUSED_TILED, "fused_tiled"), (sv.MixMode.GENERIC, "generic"), (sv.MixMode.PER_LAYER, "per_layer")]
+CHECKER = O.best()[0]
 # the fused compositor with its taps through the texture unit (svb_mix_gather): same plans, tables and bytes
 MODES_GATHER = MODES + [(sv.MixMode.FUSED_GATHER, "fused_gather")]
 CASES = scenes.parity_cases()
@@ -29,7 +32,7 @@ def test_unorm_identity():
 @pytest.mark.parametrize("mode,mname", MODES, ids=[m[1] for m in MODES])
 @pytest.mark.parametrize("case", CASES, ids=[c.name for c in CASES])
 def test_small_scenes(case, mode, mname):
-    rc, want = scenes.run_case(O.port(), case)
+    rc, want = scenes.run_case(CHECKER, case)
     assert rc == 0
     got = gpu_case(context(), case, mode)
     assert (got == want.data).all(), f"{case.name}/{mname}: {first_diff(got, want.data)}"
@@ -84,7 +87,7 @@ TILED = _tiled_cases()
 @pytest.mark.parametrize("mode,mname", MODES_GATHER, ids=[m[1] for m in MODES_GATHER])
 @pytest.mark.parametrize("case", TILED, ids=[c.name for c in TILED])
 def test_tiled_scenes(case, mode, mname):
-    rc, want = scenes.run_case(O.port(), case, threads=O.host_threads())
+    rc, want = scenes.run_case(CHECKER, case, threads=O.host_threads())
     assert rc == 0
     got = gpu_case(context(), case, mode)
     assert (got == want.data).all(), f"{case.name}/{mname}: {first_diff(got, want.data)}"
@@ -94,7 +97,7 @@ def test_cfg2_full_size():
     """BASELINE config 2 at full size: 1920x1080 NV12 -> 1280x720 NV12, bytes against the oracle."""
     canvas, tf, layers, us = scenes.cfg2_scene()
     case = scenes.Case("cfg2", tf, canvas, layers, us)
-    rc, want = scenes.run_case(O.port(), case, threads=O.host_threads())
+    rc, want = scenes.run_case(CHECKER, case, threads=O.host_threads())
     assert rc == 0
     for mode, mname in MODES:
         got = gpu_case(context(), case, mode)
@@ -107,7 +110,7 @@ def test_cfg34_full_size(nlayers):
     other and the per-layer sequence (a size-independent cross-check: three independent code paths, same bytes)."""
     canvas, tf, layers, us = scenes.cfg34_scene(nlayers)
     case = scenes.Case(f"cfg{3 if nlayers == 4 else 4}", tf, canvas, layers, us)
-    rc, want = scenes.run_case(O.port(), case, threads=O.host_threads())
+    rc, want = scenes.run_case(CHECKER, case, threads=O.host_threads())
     assert rc == 0
     ctx = context()
     outs = {}
@@ -127,9 +130,9 @@ def test_cfg4_variants_full_size():
     layers = [scenes.random_image(O.Y420P, ssz[0], ssz[1], scenes.cfg_seed(4, 1, k)) for k, (ssz, _, _, _) in enumerate(geo)]
     us = [scenes.layer_uniforms(canvas, ssz, pos, dsz, z=float(k + 1), opacity=op) for k, (ssz, pos, dsz, op) in enumerate(geo)]
     case = scenes.Case("cfg4_y420p", O.Y420P, canvas, layers, us)
-    rc, want = scenes.run_case(O.port(), case, threads=O.host_threads())
+    rc, want = scenes.run_case(CHECKER, case, threads=O.host_threads())
     assert rc == 0
-    for mode, mname in ((sv.MixMode.FUSED, "fused"), (sv.MixMode.FUSED_GATHER, "fused_gather")):
+    for mode, mname in ((sv.MixMode.FUSED, "fused"), (sv.MixMode.FUSED_TILED, "fused_tiled"), (sv.MixMode.FUSED_GATHER, "fused_gather")):
         got = gpu_case(ctx, case, mode)
         assert (got == want.data).all(), f"cfg4_y420p/{mname}: {first_diff(got, want.data)}"
     # (2) RGBA / BGRA overlays on an NV12 stack (4 layers keep the oracle's time down)
@@ -138,7 +141,7 @@ def test_cfg4_variants_full_size():
     layers = [scenes.random_image(f, ssz[0], ssz[1], scenes.cfg_seed(4, 2, k)) for k, (f, (ssz, _, _, _)) in enumerate(zip(fmts, geo))]
     us = [scenes.layer_uniforms(canvas, ssz, pos, dsz, z=float(k + 1), opacity=op) for k, (ssz, pos, dsz, op) in enumerate(geo)]
     case = scenes.Case("cfg4_rgba_overlays", O.NV12, canvas, layers, us)
-    rc, want = scenes.run_case(O.port(), case, threads=O.host_threads())
+    rc, want = scenes.run_case(CHECKER, case, threads=O.host_threads())
     assert rc == 0
     for mode, mname in MODES_GATHER:
         got = gpu_case(ctx, case, mode)
@@ -165,7 +168,7 @@ def test_properties_full_size():
     cleared = gpu_target(ctx, tf, *canvas)
     sv.compose(ctx, cleared, gl, zero, sv.MixMode.FUSED)
     want = O.Image(tf, *canvas)
-    O.port().clear(want)
+    CHECKER.clear(want)
     assert (fetch(ctx, cleared) == want.data).all()
 
 
@@ -189,7 +192,7 @@ def test_padded_strides(pads, mode, mname):
     base = TILED[1]  # y420p sources -> nv12 target: three planes per source
     layers = [_padded(l, pads) for l in base.layers]
     case = scenes.Case("padded", base.target_fmt, base.canvas, layers, base.uniforms)
-    rc, want = scenes.run_case(O.port(), base, threads=O.host_threads())
+    rc, want = scenes.run_case(CHECKER, base, threads=O.host_threads())
     assert rc == 0
     got = gpu_case(context(), case, mode)
     assert (got == want.data).all(), f"padded/{mname}: {first_diff(got, want.data)}"
@@ -199,10 +202,10 @@ def test_padded_target():
     """A target with padded rows (fused and generic take explicit output strides; the per-layer kernels infer the stride
     from the launch like the reference's, kernels.cuda.swift:151,205, so they only accept tight targets)."""
     base = TILED[0]
-    rc, want = scenes.run_case(O.port(), base, threads=O.host_threads())
+    rc, want = scenes.run_case(CHECKER, base, threads=O.host_threads())
     assert rc == 0
     W, H = base.canvas
-    for mode, mname in MODES[:2]:
+    for mode, mname in MODES[:3]:
         got = gpu_case(context(), base, mode, target_strides=[W + 64, W + 64])
         tight = np.concatenate([got[: (W + 64) * H].reshape(H, W + 64)[:, :W].reshape(-1),
                                 got[(W + 64) * H :].reshape(H // 2, W + 64)[:, :W].reshape(-1)])
@@ -212,3 +215,32 @@ def test_padded_target():
     with pytest.raises(sv.ComputeError) as e:
         gpu_case(context(), base, sv.MixMode.PER_LAYER, target_strides=[W + 64, W + 64])
     assert "badTarget" in str(e.value)
+
+
+GOLDEN = scenes.golden_cases()
+
+
+@pytest.mark.parametrize("mode,mname", MODES_GATHER, ids=[m[1] for m in MODES_GATHER])
+def test_golden_vectors_direct(mode, mname):
+    """tests/golden/cases.npz (inputs, uniforms and the bytes oracle/_ref -- the reference's kernel text -- produced) fed straight to
+    the CUDA path: no oracle runs in this test."""
+    for case, want in GOLDEN:
+        got = gpu_case(context(), case, mode)
+        assert (got == want).all(), f"golden {case.name}/{mname}: {first_diff(got, want)}"
+
+
+@pytest.mark.parametrize("mode,mname", MODES, ids=[m[1] for m in MODES])
+def test_equal_z_is_deterministic(mode, mname):
+    """Equal zIndex has no defined order upstream (an unstable sort over a dictionary, mix.video.swift:115); here ties keep the
+    order of the layer list, so the same call gives the same bytes every time, and those bytes are the fold in list order."""
+    canvas = (640, 352)
+    layers = [scenes.random_image(O.NV12, 640, 352, 9100), scenes.random_image(O.NV12, 400, 240, 9101), scenes.random_image(O.NV12, 400, 240, 9102)]
+    us = [scenes.layer_uniforms(canvas, (640, 352), (0, 0), canvas, z=1, opacity=1.0),
+          scenes.layer_uniforms(canvas, (400, 240), (60, 40), (400, 240), z=2, opacity=0.5),
+          scenes.layer_uniforms(canvas, (400, 240), (120, 70), (400, 240), z=2, opacity=0.5)]  # same z as the layer before, overlapping it
+    case = scenes.Case("equal_z", O.NV12, canvas, layers, us)
+    rc, want = scenes.run_case(CHECKER, case)
+    assert rc == 0
+    a = gpu_case(context(), case, mode)
+    b = gpu_case(context(), case, mode)
+    assert (a == b).all() and (a == want.data).all(), f"equal_z/{mname}: {first_diff(a, want.data)}"
