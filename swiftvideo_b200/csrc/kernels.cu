@@ -4,6 +4,7 @@
 //   kernels_fused.cuh   svb_mix_generic: clear + N layers in one launch, any transform / format
 //   kernels_tiled.cuh   svb_mix_tiled:   the TMA-staged tile path for separable YUV layers
 //   kernels_strip.cuh   svb_mix_strip:   the warp-autonomous TMA compositor (round 2): a warp stages and composites its own 64x8 unit
+//   kernels_ring.cuh    svb_mix_ring:    128x32 tiles planned and staged once per CTA, composited by eight free-running warps through a three-stage mbarrier ring
 //   kernels_gather.cuh  svb_mix_gather: the same compositor with the texture unit fetching the bilinear footprints (no staging, no barriers)
 //   kernels_scale.cuh   svb_scale_convert: NV12 / P010 -> BGRA with a bilinear / Lanczos-3 resize (an extension; no upstream counterpart)
 #include "kernels_dropin.cuh"
@@ -11,6 +12,7 @@
 #include "kernels_tiled.cuh"
 #include "kernels_gather.cuh"
 #include "kernels_strip.cuh"
+#include "kernels_ring.cuh"
 #include "kernels_scale.cuh"
 
 // 256 bytes -> 256 floats with the division-free UNORM8 read, and with a true division: the parity tests

@@ -1,0 +1,347 @@
+// kernels_ring.cuh -- svb_mix_ring: the fused compositor's fast path, third design (round 2).
+//
+// svb_mix_tiled (round 1) amortises planning and staging over a CTA -- one plan, one set of TMA copies per 128x32 tile and layer --
+// but its eight warps meet at a CTA barrier in front of every layer (20 % of its stall samples) and its layer bodies are large.
+// svb_mix_strip made the warp autonomous (no barrier, compact loops that carry converted taps from one output row to the next, the
+// running picture in shared memory) but pays planning, table copies and TMA issue per 64x8 unit: 43 % of its instructions were
+// overhead.  This kernel takes the halves that worked:
+//   * a CTA of eight warps owns a 128x32 tile: ONE warp plans it (lane = layer, from the column / row records svb_strip_tables
+//     leaves), ONE elected lane issues its copies -- per tile and layer two or three TMA tensor copies of the source footprint and two
+//     bulk copies of the table blocks;
+//   * each warp composites its own 64x8 unit of the tile with svb_mix_strip's layer bodies, at its own pace: the staged layers go
+//     through a ring of THREE stages with a `full` mbarrier (the copies' bytes) and an `empty` mbarrier (eight warp arrivals) per
+//     stage, so a warp waits for data, never for another warp, and the issuing lane only waits for a warp that lags by more than a layer;
+//   * the ring runs across tiles: the plan of the next tile is ready (its own pair of mbarriers) long before this tile's last
+//     layers are computed, so the first layers of the next tile are in flight by then.
+// Per-sample arithmetic: strip_layer / strip_layer_edge (kernels_strip.cuh), i.e. fast_layer's, operation for operation.
+#pragma once
+#include "kernels_strip.cuh"
+
+#ifndef SVB_RING_MIN_CTAS
+#define SVB_RING_MIN_CTAS 3
+#endif
+
+namespace svb {
+
+__device__ __forceinline__ void mbar_arrive(unsigned bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_wait_u32(unsigned bar, unsigned parity) {
+    unsigned ok;
+    unsigned spin = 0;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"  // (suspend-time hint: a waiting warp sleeps instead of spinning through issue slots)
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity), "r"(2000u)
+            : "memory");
+        if (++spin > (1u << 22)) __trap();  // a copy that never lands must not hang the GPU
+    } while (!ok);
+}
+
+}  // namespace svb
+
+#include "ring_layout.h"
+
+extern "C" __global__ void __launch_bounds__(SVB_RING_THREADS, SVB_RING_MIN_CTAS)
+    svb_mix_ring(const SvbFrameDesc* __restrict__ frames, const uint32_t* __restrict__ tables, int nframes, int total_tiles, float one, int* __restrict__ tile_counter, int box_y_bytes,
+                 int box_c_bytes, int plan_slot_bytes) {
+    using namespace svb;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // mbarriers: full[3] (copies landed), empty[3] (eight warps have left the stage), pfull[3] (plan written), pempty[3] (eight warps have left the plan)
+    const unsigned bars = smem_u32(smem_raw);
+    const unsigned full0 = bars, empty0 = bars + 24u, pfull0 = bars + 48u, pempty0 = bars + 72u;
+    const unsigned stage_bytes = (unsigned)(box_y_bytes + box_c_bytes) + SVB_RING_TAB_BYTES;
+    unsigned char* const my_state = smem_raw + SVB_RING_HDR_BYTES + (size_t)(warp & 7) * SVB_STRIP_STATE_BYTES;
+    float2* const sY = reinterpret_cast<float2*>(my_state);  // [12 rows][32 lanes]: luma pairs of rows 0..7, then (U, V) of chroma rows 0..3
+    const unsigned state = smem_u32(my_state) + 8u * lane;
+    const unsigned plan0 = smem_u32(smem_raw + SVB_RING_HDR_BYTES + SVB_RING_WARPS * SVB_STRIP_STATE_BYTES);
+    const unsigned stage0 = plan0 + (unsigned)SVB_RING_PLANS * (unsigned)plan_slot_bytes;
+    const unsigned tab_off = (unsigned)(box_y_bytes + box_c_bytes);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 3; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full0 + 8u * i), "r"(1));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty0 + 8u * i), "r"(SVB_RING_WARPS));
+        }
+        for (int i = 0; i < SVB_RING_PLANS; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pfull0 + 8u * i), "r"(1));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pempty0 + 8u * i), "r"(SVB_RING_WARPS));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();  // the only CTA-wide barrier of the kernel
+    const int firstA = lane < nframes ? frames[lane].first_tile : 0x7fffffff, firstB = lane + 32 < nframes ? frames[lane + 32].first_tile : 0x7fffffff;
+    auto sts4 = [](unsigned a, const uint4 v) { asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); };
+
+    // ---- the plan of tile t (t >= total_tiles: the end marker) into plan slot s: the planning warp, lane = layer ----------------
+    auto plan_tile = [&](int t, int s) {
+        const unsigned slot_a = plan0 + (unsigned)s * (unsigned)plan_slot_bytes;
+        if (t >= total_tiles) {
+            if (lane == 0) sts4(slot_a, make_uint4(0xffffu, 0u, 0u, 0u));
+            return;
+        }
+        const int f = __popc(__ballot_sync(0xffffffffu, t >= firstA)) + __popc(__ballot_sync(0xffffffffu, t >= firstB)) - 1;
+        const int first = f < 32 ? __shfl_sync(0xffffffffu, firstA, f) : __shfl_sync(0xffffffffu, firstB, f - 32);
+        const SvbFrameDesc* __restrict__ F = frames + f;
+        const int W = F->width, H = F->height, nl = F->nlayers, local = t - first;
+        const int tx_n = (W + 2 * SVB_UNIT_W - 1) / (2 * SVB_UNIT_W), ux_n = F->tiles_x, uy_n = F->tiles_y;  // (tiles_x / tiles_y hold the unit counts)
+        const int ty = local / tx_n, tx = local - ty * tx_n, x0 = tx * 2 * SVB_UNIT_W, y0 = ty * 4 * SVB_UNIT_H;
+        const int ncol = min(2, ux_n - 2 * tx), nrow = min(4, uy_n - 4 * ty);
+        unsigned mode = PLAN_SKIP;
+        bool covers = false, inner = false;
+        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, r2 = r0, r3 = r0, r4 = r0;
+        if (lane < nl) {
+            const uint4* __restrict__ pc = reinterpret_cast<const uint4*>(&F->layers[lane].pc);
+            const uint4 c2 = __ldg(pc + 2), c3 = __ldg(pc + 3);
+            const unsigned fmt = c2.y & 0xfu, lflags = (c2.y >> 4) & 0xffu;
+            if ((int)c3.x < x0 + 2 * SVB_UNIT_W && (int)c3.z > x0 && (int)c3.y < y0 + 4 * SVB_UNIT_H && (int)c3.w > y0) {  // the layer's rectangle touches the tile
+                r0.w = c2.x;
+                r1.z = c2.z + (unsigned)(2 * tx) * SVB_UCOL_WORDS, r1.w = c2.z + (unsigned)ux_n * SVB_UCOL_WORDS + (unsigned)(4 * ty) * SVB_UROW_WORDS;
+                r3.z = (unsigned)ncol * SVB_UCOL_WORDS * 4u, r3.w = (unsigned)nrow * SVB_UROW_WORDS * 4u;
+                if (!(lflags & SVB_LAYER_SEPARABLE)) {
+                    mode = PLAN_GENERIC;
+                } else if (fmt != SVB_NV12 && fmt != SVB_Y420P) {
+                    mode = PLAN_TABLE_RGBA;
+                } else {
+                    const uint4* __restrict__ rec = reinterpret_cast<const uint4*>(tables + c2.w);
+                    // the tile's unit columns and unit rows: first / last source index, flags
+                    unsigned lo = 0xffffu, loc = 0xffffu, hi = 0u, hic = 0u, all = ~0u, cf = 0u, rf = 0u, any_mixed = 0u;
+                    for (int k = 0; k < ncol; ++k) {
+                        const uint4 q = __ldg(rec + 2 * tx + k);
+                        const bool touch = (int)c3.x < x0 + (k + 1) * SVB_UNIT_W && (int)c3.z > x0 + k * SVB_UNIT_W;
+                        lo = min(lo, q.x & 0xffffu), loc = min(loc, q.x >> 16), hi = max(hi, q.y & 0xffffu), hic = max(hic, q.y >> 16);
+                        all &= q.z, any_mixed |= q.z;
+                        cf |= ((q.z & 0x7fu) | (touch ? SVB_RREC_TOUCH : 0u)) << (8 * k);
+                    }
+                    const unsigned ix0 = lo, ic0 = loc, ix1 = hi, ic1 = hic;
+                    lo = loc = 0xffffu, hi = hic = 0u;
+                    for (int k = 0; k < nrow; ++k) {
+                        const uint4 q = __ldg(rec + ux_n + 4 * ty + k);
+                        const bool touch = (int)c3.y < y0 + (k + 1) * SVB_UNIT_H && (int)c3.w > y0 + k * SVB_UNIT_H;
+                        lo = min(lo, q.x & 0xffffu), loc = min(loc, q.x >> 16), hi = max(hi, q.y & 0xffffu), hic = max(hic, q.y >> 16);
+                        all &= q.z | SVB_UREC_XFREE, any_mixed |= q.z;
+                        rf |= ((q.z & 0x7fu) | (touch ? SVB_RREC_TOUCH : 0u)) << (8 * k);
+                    }
+                    const uint4 c1 = __ldg(pc + 1);
+                    const unsigned box_w = c1.w & 0xffffu, box_h = (c2.y >> 12) & 0x3ffu, box_ch = c2.y >> 22;
+                    const unsigned box_cw = (c1.w >> 16) / (fmt == SVB_NV12 ? 2u : 1u);
+                    // (column records hold origins already rounded down for TMA; the footprint must fit the tile-sized boxes)
+                    const bool fits = (lflags & SVB_LAYER_STAGED) && ix1 - ix0 < box_w && hi - lo < box_h && ic1 - ic0 < box_cw && hic - loc < box_ch;
+                    mode = fits ? PLAN_STAGED : PLAN_GENERIC;
+                    covers = (all & SVB_UREC_FULL) && (lflags & SVB_LAYER_UNIT_OPACITY);
+                    inner = fits && (all & SVB_UREC_XFREE);  // every unit of the tile takes the interior body
+                    r0.y = ix0 | (lo << 16), r0.z = ic0 | (loc << 16);
+                    r1.x = c1.z + r3.z + r3.w, r1.y = c1.w;
+                    r2 = __ldg(pc);
+                    r3.x = c1.x, r3.y = c1.y;
+                    r4 = make_uint4(cf, rf, 0u, 0u);
+                }
+                r0.x = mode | ((unsigned)lane << 8) | (fmt << 16) | (lflags << 20);
+            }
+        }
+        unsigned act = __ballot_sync(0xffffffffu, mode != PLAN_SKIP);
+        const unsigned cov = __ballot_sync(0xffffffffu, covers), stg = __ballot_sync(0xffffffffu, mode >= PLAN_STAGED), inn = __ballot_sync(0xffffffffu, inner);
+        unsigned first_covers = 0;
+        if (cov) {
+            const unsigned top = 31u - (unsigned)__clz(cov);
+            act &= ~((1u << top) - 1u);  // drop what the topmost covering layer hides
+            first_covers = (inn >> top) & 1u;
+        }
+        const unsigned below = act & ((1u << lane) - 1u);
+        if ((act >> lane) & 1u) {
+            const unsigned a = slot_a + SVB_RPLAN_HDR_BYTES + SVB_RPLAN_REC_BYTES * (unsigned)__popc(below);
+            sts4(a, r0), sts4(a + 16, r1), sts4(a + 32, r2), sts4(a + 48, r3), sts4(a + 64, r4);
+        }
+        const unsigned smask = __reduce_or_sync(0xffffffffu, ((act & stg) >> lane) & 1u ? 1u << __popc(below) : 0u);
+        if (lane == 0) {
+            const unsigned long long p0 = F->out_plane[0], p1 = F->out_plane[1], p2 = F->out_plane[2];
+            sts4(slot_a, make_uint4((unsigned)__popc(act) | (smask << 16), (unsigned)x0 | ((unsigned)y0 << 16), (unsigned)f, first_covers));
+            sts4(slot_a + 16, make_uint4((unsigned)W, (unsigned)H, (unsigned)F->format | ((unsigned)F->flags << 8), (unsigned)F->out_stride[0]));
+            sts4(slot_a + 32, make_uint4((unsigned)p0, (unsigned)(p0 >> 32), (unsigned)p1, (unsigned)(p1 >> 32)));
+            sts4(slot_a + 48, make_uint4((unsigned)p2, (unsigned)(p2 >> 32), (unsigned)F->out_stride[1], (unsigned)F->out_stride[2]));
+        }
+    };
+    // the async copies of the staged layer whose plan record lies at shared-memory address ra, into stage b (one elected lane of the issuing warp)
+    auto issue = [&](unsigned ra, unsigned b) {
+        const uint4 r0 = lds_u4(ra), r1 = lds_u4(ra + 16), r2 = lds_u4(ra + 32), r3 = lds_u4(ra + 48);
+        if (elect_one()) {
+            const unsigned dst = stage0 + b * stage_bytes, mb = full0 + 8u * b;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(r1.x) : "memory");
+            auto tma = [&](unsigned d, unsigned long long tmap, unsigned x, unsigned y) {
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(d), "l"(tmap), "r"(x), "r"(y), "r"(mb)
+                             : "memory");
+            };
+            auto bulk = [&](unsigned d, const void* src, unsigned bytes) {
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(src), "r"(bytes), "r"(mb) : "memory");
+            };
+            tma(dst, ((unsigned long long)r2.y << 32) | r2.x, r0.y & 0xffffu, r0.y >> 16);
+            tma(dst + (unsigned)box_y_bytes, ((unsigned long long)r2.w << 32) | r2.z, r0.z & 0xffffu, r0.z >> 16);
+            if (((r0.x >> 16) & 0xfu) != SVB_NV12) tma(dst + (unsigned)box_y_bytes + (unsigned)box_c_bytes / 2u, ((unsigned long long)r3.y << 32) | r3.x, r0.z & 0xffffu, r0.z >> 16);
+            bulk(dst + tab_off, tables + r1.z, r3.z);
+            bulk(dst + tab_off + 2u * SVB_UCOL_WORDS * 4u, tables + r1.w, r3.w);
+        }
+        __syncwarp();
+    };
+
+    // Warp 8 is the producer: it claims tiles, plans them (three plan slots: up to three tiles ahead of the slowest consumer) and issues
+    // the copies of their staged layers in order, as far ahead as the ring allows.  Warps 0..7 are the consumers, one 64x8 unit each.
+    // `g` counts the staged layers of this CTA: staged layer g lives in stage g % 3 and its barriers are in their (g / 3)-th use -- the
+    // producer and every consumer count alike because they read the same plans, so nobody tracks barrier phases.  Tile n of this CTA
+    // has its plan in slot n % 3.
+    if (warp == SVB_RING_WARPS) {
+        unsigned gi = 0;  // staged layers issued
+        for (unsigned n = 0;; ++n) {
+            const unsigned slot = n % SVB_RING_PLANS;
+            if (n >= SVB_RING_PLANS) mbar_wait_u32(pempty0 + 8u * slot, ((n / SVB_RING_PLANS) - 1u) & 1u);  // every consumer has left the slot's previous plan
+            int t = 0;
+            if (lane == 0) t = atomicAdd(tile_counter, 1);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            plan_tile(t, (int)slot);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(pfull0 + 8u * slot);
+            if (t >= total_tiles) return;
+            const unsigned pa = plan0 + slot * (unsigned)plan_slot_bytes;
+            unsigned smask = lds_u4(pa).x >> 16;
+            for (unsigned i = 0; smask; smask >>= 1, ++i) {
+                if (!(smask & 1u)) continue;
+                const unsigned b = gi % SVB_RING_STAGES;
+                if (gi >= SVB_RING_STAGES) mbar_wait_u32(empty0 + 8u * b, ((gi / SVB_RING_STAGES) - 1u) & 1u);  // every consumer has left the stage's previous tenant
+                issue(pa + SVB_RPLAN_HDR_BYTES + SVB_RPLAN_REC_BYTES * i, b);
+                ++gi;
+            }
+        }
+    }
+    unsigned g = 0;  // staged layers met by this warp
+    for (unsigned n = 0;; ++n) {  // tile ordinal of this CTA
+        const unsigned slot = n % SVB_RING_PLANS, plan = plan0 + slot * (unsigned)plan_slot_bytes;
+        mbar_wait_u32(pfull0 + 8u * slot, (n / SVB_RING_PLANS) & 1u);  // this tile's plan
+        const uint4 h0 = lds_u4(plan);
+        const unsigned nact = h0.x & 0xffffu;
+        if (nact == 0xffffu) break;
+        const int x0 = (int)(h0.y & 0xffffu), y0 = (int)(h0.y >> 16), f = (int)h0.z;
+        const SvbFrameDesc* __restrict__ F = frames + f;
+        const uint4 h1 = lds_u4(plan + 16);
+        const int W = (int)h1.x, H = (int)h1.y, ofmt = (int)(h1.z & 0xffu), fflags = (int)(h1.z >> 8);
+#define SVB_RING_TARGET()                                                                    \
+    const uint4 h2 = lds_u4(plan + 32), h3 = lds_u4(plan + 48);                              \
+    const int sYb = (int)lds_u1(plan + 28), sUb = (int)h3.z, sVb = (int)h3.w;                \
+    uint8_t* const oY = (uint8_t*)(((unsigned long long)h2.y << 32) | h2.x);                 \
+    uint8_t* const oU = (uint8_t*)(((unsigned long long)h2.w << 32) | h2.z);                 \
+    uint8_t* const oV = (uint8_t*)(((unsigned long long)h3.y << 32) | h3.x);
+        const int ux = warp & 1, uy = warp >> 1;                                 // this warp's unit of the tile
+        const int xt = x0 + ux * SVB_UNIT_W + 2 * lane, yt = y0 + uy * SVB_UNIT_H;  // this lane's columns xt, xt+1 x rows yt .. yt+7
+        const bool live = xt < W && yt < H;                                      // W and H even are planner preconditions
+
+        // ---- running picture: img_clear_* (Y = 0, chroma = 0.5 -> 128), or the target's bytes when an earlier pass left them ----
+        if (fflags & SVB_FRAME_LOAD_CUR) {
+            SVB_RING_TARGET()
+#pragma unroll
+            for (int r = 0; r < SVB_UNIT_H; ++r) {
+                unsigned w0 = 0;
+                if (live && yt + r < H) w0 = *(const unsigned short*)(oY + (size_t)(yt + r) * sYb + xt);
+                sY[r * 32 + lane] = bytes2(opaque(w0 & 0xff), opaque(w0 >> 8));
+            }
+#pragma unroll
+            for (int k = 0; k < SVB_UNIT_H / 2; ++k) {
+                unsigned cu = 128, cv = 128;
+                if (live && yt + 2 * k < H) {
+                    if (ofmt == SVB_NV12) {
+                        const unsigned w0 = *(const unsigned short*)(oU + (size_t)((yt >> 1) + k) * sUb + xt);
+                        cu = w0 & 0xff, cv = w0 >> 8;
+                    } else {
+                        cu = oU[(size_t)((yt >> 1) + k) * sUb + (xt >> 1)], cv = oV[(size_t)((yt >> 1) + k) * sVb + (xt >> 1)];
+                    }
+                }
+                sY[(SVB_UNIT_H + k) * 32 + lane] = bytes2(opaque(cu), opaque(cv));
+            }
+        } else if (!(h0.w & 1u)) {  // (bit 0: the first listed layer overwrites every sample without reading it)
+#pragma unroll
+            for (int r = 0; r < SVB_UNIT_H; ++r) sY[r * 32 + lane] = splat(0.f);
+#pragma unroll
+            for (int k = 0; k < SVB_UNIT_H / 2; ++k) sY[(SVB_UNIT_H + k) * 32 + lane] = splat(128.f);
+        }
+
+#pragma unroll 1
+        for (unsigned i = 0; i < nact; ++i) {
+            const unsigned ra = plan + SVB_RPLAN_HDR_BYTES + SVB_RPLAN_REC_BYTES * i;
+            const uint4 r0 = lds_u4(ra), r1 = lds_u4(ra + 16);
+            const unsigned mode = r0.x & 0xffu;
+            if (mode >= PLAN_STAGED) {
+                const unsigned b = g % SVB_RING_STAGES, par = (g / SVB_RING_STAGES) & 1u;
+                const uint2 uf = lds_u2(ra + 64);
+                const unsigned cfl = (uf.x >> (8 * ux)) & 0xffu, rfl = (uf.y >> (8 * uy)) & 0xffu, both = cfl & rfl;
+                // (a warp the layer does not reach waits as well: an arrival on `empty` is only in the right phase once the stage's copies were issued)
+                mbar_wait_u32(full0 + 8u * b, par);
+                if (both & SVB_RREC_TOUCH) {  // the layer reaches into this warp's unit
+                    const unsigned fmt = (r0.x >> 16) & 0xfu, lflags = r0.x >> 20;
+                    const unsigned pitchY = r1.y & 0xffffu, pitchC = r1.y >> 16, cstep = fmt == SVB_NV12 ? 2u : 1u;
+                    const unsigned bY = stage0 + b * stage_bytes, bC = bY + (unsigned)box_y_bytes;
+                    const unsigned tabc = bY + tab_off + (unsigned)ux * SVB_UCOL_WORDS * 4u, tabr = bY + tab_off + 2u * SVB_UCOL_WORDS * 4u + (unsigned)uy * SVB_UROW_WORDS * 4u;
+                    const unsigned vofs = fmt == SVB_NV12 ? 1u : (unsigned)box_c_bytes / 2u;
+                    const unsigned colY = bY - (r0.y & 0xffffu) - (r0.y >> 16) * pitchY, colC = bC - (r0.z & 0xffffu) * cstep - (r0.z >> 16) * pitchC;
+                    const float alpha = __uint_as_float(r0.w);
+                    if (!((both & SVB_UREC_FULL) && (cfl & SVB_UREC_XFREE)) || !(lflags & SVB_LAYER_OPACITY_01)) {
+                        const SvbLayerDesc* __restrict__ L = &F->layers[(r0.x >> 8) & 0xffu];
+                        const float4 fc = ldrow(L->u.fillColor, 0);
+                        const float3 fl = rgb2yuv(fc.x, fc.y, fc.z);
+                        const float af = mul(alpha, fc.w);
+                        // lean: no sample of the unit lies inside the border rectangle but outside the picture (without a border or letterbox: none ever does)
+                        if ((lflags & SVB_LAYER_OPACITY_01) && !((cfl | rfl) & SVB_UREC_MIXED)) strip_layer_edge<true>(colY, colC, cstep, vofs, tabc, tabr, lane, alpha, one, make_float4(fl.x, fl.y, fl.z, 0.f), af, sY);
+                        else strip_layer_edge<false>(colY, colC, cstep, vofs, tabc, tabr, lane, alpha, one, make_float4(fl.x, fl.y, fl.z, 0.f), af, sY);
+                    } else if (lflags & SVB_LAYER_UNIT_OPACITY) {
+                        if (both & SVB_UREC_HALF) strip_layer<true, true>(colY, colC, cstep, vofs, tabc, tabr, lane, alpha, one, state);
+                        else strip_layer<true, false>(colY, colC, cstep, vofs, tabc, tabr, lane, alpha, one, state);
+                    } else {
+                        if (both & SVB_UREC_HALF) strip_layer<false, true>(colY, colC, cstep, vofs, tabc, tabr, lane, alpha, one, state);
+                        else strip_layer<false, false>(colY, colC, cstep, vofs, tabc, tabr, lane, alpha, one, state);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty0 + 8u * b);  // this warp has left the stage
+                ++g;
+            } else {
+                const SvbLayerDesc* __restrict__ L = &F->layers[(r0.x >> 8) & 0xffu];
+                float* const py = reinterpret_cast<float*>(sY + lane);
+                const uint32_t* __restrict__ colblk = tables + r1.z + ux * SVB_UCOL_WORDS;
+                const uint32_t* __restrict__ rowblk = tables + r1.w + uy * SVB_UROW_WORDS;
+                if (yt < H) {
+                    if (mode == PLAN_TABLE_RGBA) strip_rgba_layer(L, colblk, rowblk, lane, xt, yt, W, H, py, py + SVB_UNIT_W * SVB_UNIT_H);
+                    else strip_generic_layer(L, xt, yt, W, H, py, py + SVB_UNIT_W * SVB_UNIT_H);
+                }
+            }
+        }
+
+        // ---- the unit's bytes: two luma bytes per lane and row, one (U, V) pair per lane and chroma row -----------------------
+        if (live) {
+            SVB_RING_TARGET()
+            const float2 ONE = splat(one);
+            auto pack = [&](float2 v) {  // two integer-valued floats in 0..255 -> two bytes: + 2^23 leaves them in the low mantissa bits
+                const float2 x = add2<true>(v, splat(8388608.f), ONE);
+                return (unsigned short)__byte_perm(__float_as_uint(x.x), __float_as_uint(x.y), 0x0040);
+            };
+            uint8_t* pY = oY + (size_t)yt * sYb + xt;
+            const int nrow = min(SVB_UNIT_H, H - yt);
+#pragma unroll 1
+            for (int r = 0; r < nrow; ++r, pY += sYb) *(unsigned short*)pY = pack(sY[r * 32 + lane]);
+            if (ofmt == SVB_NV12) {
+                uint8_t* pC = oU + (size_t)(yt >> 1) * sUb + xt;
+#pragma unroll 1
+                for (int k = 0; 2 * k < nrow; ++k, pC += sUb) *(unsigned short*)pC = pack(sY[(SVB_UNIT_H + k) * 32 + lane]);
+            } else {
+                uint8_t* pU = oU + (size_t)(yt >> 1) * sUb + (xt >> 1);
+                uint8_t* pV = oV + (size_t)(yt >> 1) * sVb + (xt >> 1);
+#pragma unroll 1
+                for (int k = 0; 2 * k < nrow; ++k, pU += sUb, pV += sVb) {
+                    const unsigned short p = pack(sY[(SVB_UNIT_H + k) * 32 + lane]);
+                    *pU = (uint8_t)(p & 0xff), *pV = (uint8_t)(p >> 8);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pempty0 + 8u * slot);  // this warp has left the tile's plan
+    }
+#undef SVB_RING_TARGET
+}

@@ -65,13 +65,12 @@ __device__ __forceinline__ unsigned lds_u1(unsigned addr) {
 //           rint(v * 255) is rint(sum * 63.75).
 //   colY / colC: shared-memory address of the staged box minus its origin (ix0 + jy0 * pitch), so that a tap's address is
 //   colY + i0 + row offset;  cstep: bytes from a chroma texel to the next (2: NV12, 1: planar);  vofs: from a U byte to its V byte
-//   tab: shared-memory address of the stage's table blocks;  st: shared-memory address of this lane's slot in state row 0
+//   tab / rows: shared-memory addresses of the unit's column block and row block;  st: shared-memory address of this lane's slot in state row 0
 // Rows 0..7 are the luma rows, 8..11 the chroma rows of the unit; a row's two samples are (col 2l, col 2l+1) or (U, V).
 template <bool OPAQUE, bool HALF>
-__device__ __forceinline__ void strip_layer(unsigned colY, unsigned colC, unsigned cstep, unsigned vofs, unsigned tab, int lane, float alpha, float onef, unsigned st) {
+__device__ __forceinline__ void strip_layer(unsigned colY, unsigned colC, unsigned cstep, unsigned vofs, unsigned tab, unsigned rows, int lane, float alpha, float onef, unsigned st) {
     constexpr bool PK = true;
     const float2 AL = splat(alpha), NAL = splat(sub(1.f, alpha)), ONE = splat(onef);
-    const unsigned rows = tab + 4u * SVB_UCOL_WORDS;
     // which rows must fetch their upper source row: the first luma and the first chroma row, and every row whose upper row is not
     // the lower row of the row before (never at 1:1, one row in five at 1.2:1).  One vote per layer; the row loop tests a bit.
     unsigned reload;
@@ -161,14 +160,13 @@ __device__ __forceinline__ void strip_layer(unsigned colY, unsigned colC, unsign
 // skipped (warp-uniform), columns outside keep their value through a 0/1 mask.  Otherwise (MODE 3): per-sample class from the ok
 // bits -- picture / fill / untouched (kernels.cl.swift:77,84-85,96-105) -- and saturating stores.  One unit-layer in ten: no tap re-use.
 template <bool LEAN>
-__device__ __noinline__ void strip_layer_edge(unsigned colY, unsigned colC, unsigned cstep, unsigned vofs, unsigned tab, int lane, float alpha, float onef, const float4 fill,
+__device__ __noinline__ void strip_layer_edge(unsigned colY, unsigned colC, unsigned cstep, unsigned vofs, unsigned tab, unsigned rows, int lane, float alpha, float onef, const float4 fill,
                                               float af, float2* __restrict__ sY) {
     constexpr bool PK = true, GEN = !LEAN;
     const float2 AL = splat(alpha), NAL = splat(sub(1.f, alpha)), ONE = splat(onef), AF = splat(af), NAF = splat(sub(1.f, af));
     const uint2 aw = lds_u2(tab + 8u * lane), e = lds_u2(tab + 4u * SVB_UNIT_W + 8u * lane);
     const unsigned pc = lds_u1(tab + 4u * (2 * SVB_UNIT_W + SVB_UNIT_W / 2) + 4u * lane);
     const float ac = __uint_as_float(lds_u1(tab + 4u * (2 * SVB_UNIT_W) + 4u * lane));
-    const unsigned rows = tab + 4u * SVB_UCOL_WORDS;
 #pragma unroll 1
     for (int r = 0; r < 12; ++r) {
         const bool chroma = r >= 8;
@@ -270,7 +268,7 @@ __device__ __noinline__ void strip_rgba_layer(const SvbLayerDesc* __restrict__ L
 }
 
 __device__ __forceinline__ size_t strip_layer_words(const SvbFrameDesc* __restrict__ F) {  // tiles_x / tiles_y hold the unit counts in a strip batch
-    return (size_t)((F->tiles_x * (SVB_UCOL_WORDS + 2) + F->tiles_y * (SVB_UROW_WORDS + 2) + 3) / 4 * 4);
+    return (size_t)(F->tiles_x * (SVB_UCOL_WORDS + 4) + F->tiles_y * (SVB_UROW_WORDS + 4));
 }
 
 // exactly one lane of the (converged) warp: ptxas then issues the TMA instructions below without its one-lane-at-a-time loop
@@ -291,7 +289,8 @@ __device__ __forceinline__ bool elect_one() {
 // ---- pre-pass: the coordinate tables of every separable layer of every frame of the batch, unit-blocked (svb_desc.h), and the
 // column / row records a warp plans its units from.  grid (unit columns + unit rows of the largest frame, max layers, frames),
 // 96 threads: a block fills one column block (64 luma + 32 chroma entries) or one row block (8 + 4 entries) and writes its record.
-extern "C" __global__ void __launch_bounds__(96) svb_strip_tables(const SvbFrameDesc* __restrict__ frames, uint32_t* __restrict__ tables, int* __restrict__ unit_counter) {
+// (at most 32 registers: 96 x 32 fit beside the resident CTAs of the compositor launched before, so this pre-pass runs UNDER that launch)
+extern "C" __global__ void __launch_bounds__(96, 21) svb_strip_tables(const SvbFrameDesc* __restrict__ frames, uint32_t* __restrict__ tables, int* __restrict__ unit_counter) {
     using namespace svb;
     if ((blockIdx.x | blockIdx.y | blockIdx.z | threadIdx.x) == 0) *unit_counter = 0;  // svb_mix_strip claims its units from it
     const SvbFrameDesc* __restrict__ F = frames + blockIdx.z;
@@ -303,11 +302,13 @@ extern "C" __global__ void __launch_bounds__(96) svb_strip_tables(const SvbFrame
     const int b = (int)blockIdx.x, t = (int)threadIdx.x;
     if (b >= ux_n + uy_n) return;
     const bool yuv = L->format == SVB_NV12 || L->format == SVB_Y420P;  // BGRA / RGBA layers only use the luma-resolution entries
-    const bool staged = (L->flags & SVB_LAYER_STAGED_S) != 0;
+    const bool ring = (F->flags & SVB_FRAME_RING) != 0;  // svb_mix_ring stages tile-sized boxes (box_*), svb_mix_strip unit-sized ones (sbox_*)
+    const bool staged = (L->flags & (ring ? SVB_LAYER_STAGED : SVB_LAYER_STAGED_S)) != 0;
+    const int bx_w = ring ? L->box_w : L->sbox_w, bx_h = ring ? L->box_h : L->sbox_h, bx_cw = ring ? L->box_cw : L->sbox_cw, bx_ch = ring ? L->box_ch : L->sbox_ch;
     uint32_t* __restrict__ base = tables + F->table_base + (size_t)l * strip_layer_words(F);
     uint32_t* __restrict__ rbase = base + ux_n * SVB_UCOL_WORDS;
     uint32_t* __restrict__ crec = rbase + uy_n * SVB_UROW_WORDS;
-    uint32_t* __restrict__ rrec = crec + 2 * ux_n;
+    uint32_t* __restrict__ rrec = crec + 4 * ux_n;
     __shared__ int s_i0[96], s_i1[96], s_ok[96];
     auto odd = [](int ok) { return (ok & 1) != 0 && ok != 7; };
     const bool colblk = b < ux_n;
@@ -326,7 +327,7 @@ extern "C" __global__ void __launch_bounds__(96) svb_strip_tables(const SvbFrame
         }
     } else {
         const int r = b - ux_n;
-        const unsigned pitchY = staged ? (unsigned)L->sbox_w : 0u, pitchC = staged ? (unsigned)(L->format == SVB_NV12 ? 2 * L->sbox_cw : L->sbox_cw) : 0u;
+        const unsigned pitchY = staged ? (unsigned)bx_w : 0u, pitchC = staged ? (unsigned)(L->format == SVB_NV12 ? 2 * bx_cw : bx_cw) : 0u;
         uint32_t* __restrict__ blk = rbase + r * SVB_UROW_WORDS;
         if (t < SVB_UNIT_H) e = ent_row_y(L, H, r * SVB_UNIT_H + t), have = true;
         else if (t < SVB_UNIT_H + SVB_UNIT_H / 2 && yuv) e = ent_row_c(L, H, r * (SVB_UNIT_H / 2) + t - SVB_UNIT_H), have = true;
@@ -346,18 +347,20 @@ extern "C" __global__ void __launch_bounds__(96) svb_strip_tables(const SvbFrame
     if (colblk) {
         const int lastc = min(SVB_UNIT_W, W - b * SVB_UNIT_W) - 1, c0 = SVB_UNIT_W, c1 = SVB_UNIT_W + (lastc >> 1);
         const int ix0 = min(s_i0[0], s_i0[lastc]) & ~15, ic0 = yuv ? (min(s_i0[c0], s_i0[c1]) & (L->format == SVB_NV12 ? ~7 : ~15)) : 0;
-        bool fits = staged && max(s_i1[0], s_i1[lastc]) - ix0 < L->sbox_w, full = s_ok[0] == 7 && s_ok[lastc] == 7;
+        bool fits = staged && max(s_i1[0], s_i1[lastc]) - ix0 < bx_w, full = s_ok[0] == 7 && s_ok[lastc] == 7;
         bool xfree = s_i1[0] != s_i0[0] && s_i1[lastc] != s_i0[lastc];
-        if (yuv) fits = fits && max(s_i1[c0], s_i1[c1]) - ic0 < L->sbox_cw, xfree = xfree && s_i1[c0] != s_i0[c0] && s_i1[c1] != s_i0[c1];
+        if (yuv) fits = fits && max(s_i1[c0], s_i1[c1]) - ic0 < bx_cw, xfree = xfree && s_i1[c0] != s_i0[c0] && s_i1[c1] != s_i0[c1];
         flags |= (full ? SVB_UREC_FULL : 0u) | (xfree ? SVB_UREC_XFREE : 0u) | (fits ? SVB_UREC_FITS : 0u);
-        crec[2 * b] = (unsigned)ix0 | ((unsigned)ic0 << 16), crec[2 * b + 1] = flags;
+        const int ic1 = yuv ? max(s_i1[c0], s_i1[c1]) : 0;
+        reinterpret_cast<uint4*>(crec)[b] = make_uint4((unsigned)ix0 | ((unsigned)ic0 << 16), (unsigned)max(s_i1[0], s_i1[lastc]) | ((unsigned)ic1 << 16), flags, 0u);
     } else {
         const int r = b - ux_n, lastr = min(SVB_UNIT_H, H - r * SVB_UNIT_H) - 1, c0 = SVB_UNIT_H, c1 = SVB_UNIT_H + (lastr >> 1);
         const int jy0 = min(s_i0[0], s_i0[lastr]), jc0 = yuv ? min(s_i0[c0], s_i0[c1]) : 0;
-        bool fits = staged && max(s_i1[0], s_i1[lastr]) - jy0 < L->sbox_h, full = s_ok[0] == 7 && s_ok[lastr] == 7;
-        if (yuv) fits = fits && max(s_i1[c0], s_i1[c1]) - jc0 < L->sbox_ch;
+        bool fits = staged && max(s_i1[0], s_i1[lastr]) - jy0 < bx_h, full = s_ok[0] == 7 && s_ok[lastr] == 7;
+        if (yuv) fits = fits && max(s_i1[c0], s_i1[c1]) - jc0 < bx_ch;
         flags |= (full ? SVB_UREC_FULL : 0u) | (fits ? SVB_UREC_FITS : 0u);
-        rrec[2 * r] = (unsigned)jy0 | ((unsigned)jc0 << 16), rrec[2 * r + 1] = flags;
+        const int jc1 = yuv ? max(s_i1[c0], s_i1[c1]) : 0;
+        reinterpret_cast<uint4*>(rrec)[r] = make_uint4((unsigned)jy0 | ((unsigned)jc0 << 16), (unsigned)max(s_i1[0], s_i1[lastr]) | ((unsigned)jc1 << 16), flags, 0u);
     }
 }
 
@@ -412,8 +415,9 @@ extern "C" __global__ void __launch_bounds__(SVB_STRIP_THREADS, SVB_STRIP_MIN_CT
                 } else if (fmt != SVB_NV12 && fmt != SVB_Y420P) {
                     mode = PLAN_TABLE_RGBA;
                 } else {
-                    const uint2* __restrict__ rec = reinterpret_cast<const uint2*>(tables + c2.w);
-                    const uint2 cr = __ldg(rec + ux), rr = __ldg(rec + ux_n + uy);
+                    const uint4* __restrict__ rec = reinterpret_cast<const uint4*>(tables + c2.w);
+                    const uint4 cq = __ldg(rec + ux), rq = __ldg(rec + ux_n + uy);
+                    const uint2 cr = make_uint2(cq.x, cq.z), rr = make_uint2(rq.x, rq.z);
                     const uint4 c1 = __ldg(pc + 1);
                     r2 = __ldg(pc);
                     const unsigned both = cr.y & rr.y;
@@ -578,14 +582,14 @@ extern "C" __global__ void __launch_bounds__(SVB_STRIP_THREADS, SVB_STRIP_MIN_CT
                     const float3 fl = rgb2yuv(fc.x, fc.y, fc.z);
                     const float af = mul(alpha, fc.w);
                     // lean: no sample of the unit lies inside the border rectangle but outside the picture (without a border or letterbox: none ever does)
-                    if ((lflags & SVB_LAYER_OPACITY_01) && !(uflags & SVB_UREC_MIXED)) strip_layer_edge<true>(colY, colC, cstep, vofs, tab, lane, alpha, one, make_float4(fl.x, fl.y, fl.z, 0.f), af, sY);
-                    else strip_layer_edge<false>(colY, colC, cstep, vofs, tab, lane, alpha, one, make_float4(fl.x, fl.y, fl.z, 0.f), af, sY);
+                    if ((lflags & SVB_LAYER_OPACITY_01) && !(uflags & SVB_UREC_MIXED)) strip_layer_edge<true>(colY, colC, cstep, vofs, tab, tab + 4u * SVB_UCOL_WORDS, lane, alpha, one, make_float4(fl.x, fl.y, fl.z, 0.f), af, sY);
+                    else strip_layer_edge<false>(colY, colC, cstep, vofs, tab, tab + 4u * SVB_UCOL_WORDS, lane, alpha, one, make_float4(fl.x, fl.y, fl.z, 0.f), af, sY);
                 } else if (lflags & SVB_LAYER_UNIT_OPACITY) {
-                    if (uflags & SVB_UREC_HALF) strip_layer<true, true>(colY, colC, cstep, vofs, tab, lane, alpha, one, state);
-                    else strip_layer<true, false>(colY, colC, cstep, vofs, tab, lane, alpha, one, state);
+                    if (uflags & SVB_UREC_HALF) strip_layer<true, true>(colY, colC, cstep, vofs, tab, tab + 4u * SVB_UCOL_WORDS, lane, alpha, one, state);
+                    else strip_layer<true, false>(colY, colC, cstep, vofs, tab, tab + 4u * SVB_UCOL_WORDS, lane, alpha, one, state);
                 } else {
-                    if (uflags & SVB_UREC_HALF) strip_layer<false, true>(colY, colC, cstep, vofs, tab, lane, alpha, one, state);
-                    else strip_layer<false, false>(colY, colC, cstep, vofs, tab, lane, alpha, one, state);
+                    if (uflags & SVB_UREC_HALF) strip_layer<false, true>(colY, colC, cstep, vofs, tab, tab + 4u * SVB_UCOL_WORDS, lane, alpha, one, state);
+                    else strip_layer<false, false>(colY, colC, cstep, vofs, tab, tab + 4u * SVB_UCOL_WORDS, lane, alpha, one, state);
                 }
                 stage ^= 1;
             } else {

@@ -8,6 +8,7 @@
 #include <cstring>
 
 #include "cu_driver.h"
+#include "ring_layout.h"
 
 namespace svb {
 
@@ -48,11 +49,11 @@ struct MixerShared {
     std::vector<CUdeviceptr> tmapChunks;
     int tmapChunkAt = -1, tmapUsed = 0;
     bool tmapFence = false;
-    CUfunction fTiled = nullptr, fGather = nullptr, fGeneric = nullptr, fTables = nullptr, fStrip = nullptr, fStripTables = nullptr;
+    CUfunction fTiled = nullptr, fGather = nullptr, fGeneric = nullptr, fTables = nullptr, fStrip = nullptr, fStripTables = nullptr, fRing = nullptr;
     int gatherCtasPerSm = 0;
     int texAlign = 512, texPitchAlign = 32;
     std::map<std::array<uint64_t, 3>, CUtexObject> texs;  // texture objects over source planes by (pointer, size, pitch | channels)
-    std::map<size_t, int> stripCtasPerSm;  // the same for svb_mix_strip
+    std::map<size_t, int> stripCtasPerSm, ringCtasPerSm;  // the same for svb_mix_strip / svb_mix_ring
     std::map<size_t, int> tiledCtasPerSm;  // resident CTAs of svb_mix_tiled per SM by dynamic shared memory size: the persistent grid is smCount times this
     std::mutex mu;
     // optional per-launch device timing of the fused kernels (bench.py's roofline leg)
@@ -128,6 +129,8 @@ MixerShared& shared(const std::shared_ptr<InternalContext>& ic) {  // caller hol
         check(drv().cuFuncSetAttribute(s->fStrip, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, SVB_STRIP_SMEM_BYTES(SVB_SBOX_Y_BYTES, SVB_SBOX_C_BYTES, SVB_MAX_LAYERS)),
               "cuFuncSetAttribute(max dynamic shared memory)");
         s->fStripTables = ic->builtin("svb_strip_tables");
+        s->fRing = ic->builtin("svb_mix_ring");
+        check(drv().cuFuncSetAttribute(s->fRing, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, 200 * 1024), "cuFuncSetAttribute(max dynamic shared memory)");
     }
     return *(MixerShared*)ic->mixerShared;
 }
@@ -376,22 +379,23 @@ FramePlan planFrame(const ComputeContext& ctx, const PictureSample& target, cons
 
 namespace {
 
-// SVB_COMPOSITOR=strip|tma|gather picks the fused compositor (default: strip = svb_mix_strip; tma = svb_mix_tiled, the round-1
-// kernel, which also takes the batches whose footprints are too large for a warp's own boxes); read once.
-int compositorChoice() {  // 0 strip, 1 tiled, 2 gather
+// SVB_COMPOSITOR=ring|strip|tma|gather picks the fused compositor (default: ring = svb_mix_ring; strip = svb_mix_strip, which falls back to
+// tma = svb_mix_tiled, the round-1 kernel, for batches whose footprints are too large for a warp's own boxes); read once.
+int compositorChoice() {  // 0 strip, 1 tiled, 2 gather, 3 ring
     static const int v = [] {
         const char* e = std::getenv("SVB_COMPOSITOR");
+        if (e && std::strcmp(e, "ring") == 0) return 3;
         if (e && std::strcmp(e, "gather") == 0) return 2;
         if (e && (std::strcmp(e, "tma") == 0 || std::strcmp(e, "tiled") == 0)) return 1;
         if (e && std::strcmp(e, "strip") == 0) return 0;
-        return SVB_DEFAULT_GATHER ? 2 : 0;
+        return SVB_DEFAULT_GATHER ? 2 : 3;
     }();
     return v;
 }
 bool gatherByDefault() { return compositorChoice() == 2; }
 
 // One launch over `frames` (all tiled-capable, or all generic).  Caller holds a CtxGuard.
-void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, bool tiled, bool wantGather, bool wantTiled) {
+void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, bool tiled, bool wantGather, int want) {  // want: 0 default, 1 svb_mix_tiled, 2 svb_mix_strip, 3 svb_mix_ring
     const CuDriver& d = drv();
     MixerShared& sh = shared(ctx.ctx);
     InternalContext& ic = *ctx.ctx;
@@ -417,20 +421,24 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
                 if ((fr.layers[l].flags & SVB_LAYER_STAGED) && !(fr.layers[l].flags & SVB_LAYER_TEX)) gather = false;
         }
         // svb_mix_strip (a warp stages its own 64x8 footprint) unless a layer that the tiled kernel can stage does not fit a warp's boxes
-        bool strip = tiled && !gather && !wantTiled && compositorChoice() == 0;
+        const int pick = want ? want : (compositorChoice() == 0 ? 2 : compositorChoice() == 3 ? 3 : 1);
+        const bool ring = tiled && !gather && pick == 3;  // same tile boxes as svb_mix_tiled: whatever that kernel stages, this one does
+        bool strip = tiled && !gather && (pick == 2 || ring);  // (`strip` from here on: unit tables, planned in the compositor -- both kernels)
         for (int i = 0; strip && i < n; ++i) {
             const SvbFrameDesc& fr = frames[start + i];
             for (int l = 0; l < fr.nlayers; ++l)
-                if ((fr.layers[l].flags & SVB_LAYER_STAGED) && !(fr.layers[l].flags & SVB_LAYER_STAGED_S)) strip = false;
+                if (!ring && (fr.layers[l].flags & SVB_LAYER_STAGED) && !(fr.layers[l].flags & SVB_LAYER_STAGED_S)) strip = false;
         }
         for (int i = 0; i < n; ++i) {
             SvbFrameDesc& fr = frames[start + i];
             if (gather) fr.flags |= SVB_FRAME_GATHER;
             else fr.flags &= ~SVB_FRAME_GATHER;
             if (sh.tmapFence) fr.flags |= SVB_FRAME_TMAP_FENCE;
+            if (ring) fr.flags |= SVB_FRAME_RING;
+            else fr.flags &= ~SVB_FRAME_RING;
             for (int l = 0; l < fr.nlayers; ++l) {
                 const SvbLayerDesc& L = fr.layers[l];
-                if (strip) {
+                if (strip && !ring) {
                     if (!(L.flags & SVB_LAYER_STAGED_S)) continue;
                     boxY = std::max(boxY, roundUp(L.sbox_w * L.sbox_h, 128));
                     boxC = std::max(boxC, L.format == SVB_NV12 ? roundUp(L.sbox_cw * L.sbox_ch * 2, 128) : 2 * roundUp(L.sbox_cw * L.sbox_ch, 128));
@@ -444,7 +452,7 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
             fr.tiles_x = strip ? SVB_UNITS_X(fr.width) : SVB_TILES_X(fr.width);
             fr.tiles_y = strip ? SVB_UNITS_Y(fr.height) : SVB_TILES_Y(fr.height);
             fr.first_tile = total;
-            total += fr.tiles_x * fr.tiles_y;
+            total += ring ? SVB_TILES_X(fr.width) * SVB_TILES_Y(fr.height) : fr.tiles_x * fr.tiles_y;  // (svb_mix_ring claims 128x32 tiles; its tables are unit-blocked all the same)
             maxTiles = std::max(maxTiles, fr.tiles_x * fr.tiles_y);
             maxW = std::max(maxW, fr.width), maxH = std::max(maxH, fr.height);
             const int ents = strip ? SVB_UTABLE_WORDS(fr.width, fr.height) : SVB_TABLE_WORDS(fr.width, fr.height);  // 4-byte words per layer
@@ -453,13 +461,21 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
                 for (int l = 0; l < fr.nlayers; ++l) {  // what a planning lane of svb_mix_strip reads of its layer
                     SvbLayerDesc& L = fr.layers[l];
                     SvbStripConsts& c = L.pc;
-                    c.stmapY[0] = (uint32_t)L.stmap[0], c.stmapY[1] = (uint32_t)(L.stmap[0] >> 32);
-                    c.stmapC[0] = (uint32_t)L.stmap[1], c.stmapC[1] = (uint32_t)(L.stmap[1] >> 32);
-                    c.stmapV[0] = (uint32_t)L.stmap[2], c.stmapV[1] = (uint32_t)(L.stmap[2] >> 32);
-                    c.stx_bytes = (uint32_t)L.stx_bytes;
-                    c.pitches = (uint32_t)L.sbox_w | ((uint32_t)(L.format == SVB_NV12 ? 2 * L.sbox_cw : L.sbox_cw) << 16);
+                    const unsigned long long* tm = ring ? L.tmap : L.stmap;  // tile-sized boxes for svb_mix_ring, unit-sized ones for svb_mix_strip
+                    c.stmapY[0] = (uint32_t)tm[0], c.stmapY[1] = (uint32_t)(tm[0] >> 32);
+                    c.stmapC[0] = (uint32_t)tm[1], c.stmapC[1] = (uint32_t)(tm[1] >> 32);
+                    c.stmapV[0] = (uint32_t)tm[2], c.stmapV[1] = (uint32_t)(tm[2] >> 32);
                     std::memcpy(&c.opacity_bits, &L.u.opacity, 4);
-                    c.fmtflags = (uint32_t)L.format | ((uint32_t)(L.flags & 0xff) << 8);
+                    if (ring) {
+                        const int cb = L.box_cw * L.box_ch * (L.format == SVB_NV12 ? 2 : 1);
+                        c.stx_bytes = (L.flags & SVB_LAYER_STAGED) ? (uint32_t)(L.box_w * L.box_h + (L.format == SVB_NV12 ? cb : 2 * cb)) : 0u;  // the table blocks are added per tile
+                        c.pitches = (uint32_t)L.box_w | ((uint32_t)(L.format == SVB_NV12 ? 2 * L.box_cw : L.box_cw) << 16);
+                        c.fmtflags = (uint32_t)L.format | ((uint32_t)(L.flags & 0xff) << 4) | ((uint32_t)L.box_h << 12) | ((uint32_t)L.box_ch << 22);
+                    } else {
+                        c.stx_bytes = (uint32_t)L.stx_bytes;
+                        c.pitches = (uint32_t)L.sbox_w | ((uint32_t)(L.format == SVB_NV12 ? 2 * L.sbox_cw : L.sbox_cw) << 16);
+                        c.fmtflags = (uint32_t)L.format | ((uint32_t)(L.flags & 0xff) << 8);
+                    }
                     c.tab = (uint32_t)(tableEnts + (size_t)l * (size_t)ents);
                     c.rec = c.tab + (uint32_t)(fr.tiles_x * SVB_UCOL_WORDS + fr.tiles_y * SVB_UROW_WORDS);
                     std::memcpy(c.rect, L.rect, sizeof(c.rect));
@@ -489,11 +505,18 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
             const size_t counterOff = (std::max<size_t>(tableEnts, 4) * 4 + 15) & ~(size_t)15;
             const size_t plansOff = counterOff + 16;
             const size_t tableBytes = plansOff + (strip ? 0 : (size_t)total * sizeof(SvbTilePlan));  // (a strip batch has no plans in global memory: warps plan their own units)
-            if (sh.tabBytes[seg] < tableBytes) {  // the segment is idle here (ev[seg] waited for above)
-                if (sh.tabBuf[seg]) check(d.cuMemFree(sh.tabBuf[seg]), "cuMemFree");
-                sh.tabBuf[seg] = 0, sh.tabBytes[seg] = 0;
-                check(d.cuMemAlloc(&sh.tabBuf[seg], tableBytes + tableBytes / 4), "cuMemAlloc");
-                sh.tabBytes[seg] = tableBytes + tableBytes / 4;
+            if (sh.tabBytes[seg] < tableBytes) {
+                // cuMemAlloc / cuMemFree synchronise the device: when one segment's buffer must grow, grow them all, once, instead of
+                // stalling the next kSegments - 1 launches as well (a mixer's first ticks are often lighter than its steady state)
+                check(d.cuCtxSynchronize(), "cuCtxSynchronize");
+                const size_t want = tableBytes + tableBytes / 4;
+                for (int k = 0; k < kSegments; ++k) {
+                    if (sh.tabBytes[k] >= want) continue;
+                    if (sh.tabBuf[k]) check(d.cuMemFree(sh.tabBuf[k]), "cuMemFree");
+                    sh.tabBuf[k] = 0, sh.tabBytes[k] = 0;
+                    check(d.cuMemAlloc(&sh.tabBuf[k], want), "cuMemAlloc");
+                    sh.tabBytes[k] = want;
+                }
             }
             CUdeviceptr tables = sh.tabBuf[seg];
             CUdeviceptr counter = tables + counterOff, plans = tables + plansOff;
@@ -515,7 +538,25 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
             check(d.cuStreamWaitEvent(ic.compute, sh.evPrep[seg], 0), "cuStreamWaitEvent");
             if (tev.first) check(d.cuEventRecord(tev.first, ic.compute), "cuEventRecord");  // time svb_mix_tiled alone
             float one = 1.0f;  // see add2() in kernels_tiled.cuh
-            if (strip) {
+            if (ring) {
+                int nf = n, slotBytes = SVB_RPLAN_SLOT_BYTES(maxLayers);
+                void* args[] = {&dev, &tables, &nf, &total, &one, &counter, &boxY, &boxC, &slotBytes};
+                size_t smem = SVB_RING_SMEM_BYTES((size_t)boxY, (size_t)boxC, maxLayers);
+                int perSm;
+                {
+                    std::lock_guard<std::mutex> g(sh.mu);
+                    auto it = sh.ringCtasPerSm.find(smem);
+                    if (it == sh.ringCtasPerSm.end()) {
+                        int nb = 0;
+                        check(d.cuOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sh.fRing, SVB_RING_THREADS, smem), "cuOccupancyMaxActiveBlocksPerMultiprocessor");
+                        it = sh.ringCtasPerSm.emplace(smem, std::max(1, nb)).first;
+                    }
+                    perSm = it->second;
+                }
+                const unsigned grid = (unsigned)std::min(total, ic.smCount * perSm);
+                check(d.cuLaunchKernel(sh.fRing, grid, 1, 1, SVB_RING_THREADS, 1, 1, (unsigned)smem, ic.compute, args, nullptr), "cuLaunchKernel(svb_mix_ring)");
+                noteKernelLaunch();
+            } else if (strip) {
                 int nf = n, slotBytes = SVB_UPLAN_SLOT_BYTES(maxLayers);
                 void* args[] = {&dev, &tables, &nf, &total, &one, &counter, &boxY, &boxC, &slotBytes};
                 size_t smem = SVB_STRIP_SMEM_BYTES((size_t)boxY, (size_t)boxC, maxLayers);
@@ -589,7 +630,7 @@ struct Job {
 };
 
 // Fused compose of several independent targets on one context.
-void composeFused(const ComputeContext& ctx, std::vector<Job>& jobs, bool forceGeneric, bool wantGather = false, bool wantTiled = false) {
+void composeFused(const ComputeContext& ctx, std::vector<Job>& jobs, bool forceGeneric, bool wantGather = false, int want = 0) {
     CtxGuard g(ctx.ctx);
     std::vector<FramePlan> plans;
     bool allTiled = !forceGeneric;
@@ -605,7 +646,7 @@ void composeFused(const ComputeContext& ctx, std::vector<Job>& jobs, bool forceG
         std::vector<SvbFrameDesc> frames;
         for (FramePlan& pl : plans)
             if (p < pl.passes.size()) frames.push_back(pl.passes[p]);
-        launchFrames(ctx, frames, allTiled, wantGather, wantTiled);
+        launchFrames(ctx, frames, allTiled, wantGather, want);
     }
     for (Job& j : jobs) markWritten(ctx, *j.target);
 }
@@ -725,7 +766,7 @@ ComputeContext VideoMixer::composeRaw(const ComputeContext& ctxIn, const Picture
     jobs[0].target = &target;
     jobs[0].layers = layers;
     jobs[0].uniforms.assign(uniforms, uniforms + layers.size());
-    composeFused(ctxIn, jobs, mode == Mode::generic, mode == Mode::fusedGather, mode == Mode::fusedTiled);
+    composeFused(ctxIn, jobs, mode == Mode::generic, mode == Mode::fusedGather, mode == Mode::fusedTiled ? 1 : mode == Mode::fusedStrip ? 2 : mode == Mode::fusedRing ? 3 : 0);
     return ctxIn;
 }
 
@@ -762,7 +803,8 @@ void VideoMixer::mixMany(VideoMixer* const* mixers, int n, int64_t time, Picture
     ComputeContext ctx0 = mixers[0]->clContext;
     if (fusedAll) {
         jobs.resize(n);
-        bool generic = false, wantGather = false, wantTiled = false;
+        bool generic = false, wantGather = false;
+        int want = 0;
         for (int i = 0; i < n; ++i) {
             Tick& tk = ticks[i];
             jobs[i].target = &tk.backing;
@@ -775,9 +817,11 @@ void VideoMixer::mixMany(VideoMixer* const* mixers, int n, int64_t time, Picture
             }
             generic = generic || mixers[i]->mode == Mode::generic;
             wantGather = wantGather || mixers[i]->mode == Mode::fusedGather;
-            wantTiled = wantTiled || mixers[i]->mode == Mode::fusedTiled;
+            if (mixers[i]->mode == Mode::fusedTiled) want = 1;
+            if (mixers[i]->mode == Mode::fusedStrip) want = 2;
+            if (mixers[i]->mode == Mode::fusedRing) want = 3;
         }
-        composeFused(ctx0, jobs, generic, wantGather, wantTiled);
+        composeFused(ctx0, jobs, generic, wantGather, want);
     } else {
         for (int i = 0; i < n; ++i) {
             Tick& tk = ticks[i];

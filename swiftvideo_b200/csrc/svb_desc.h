@@ -32,6 +32,7 @@ enum {
     SVB_FRAME_LOAD_CUR = 1,   // continue an earlier pass: start from the target's bytes, not from clear
     SVB_FRAME_SCALAR_FP = 2,  // tuning aid: spell the packed fp32x2 arithmetic as scalar instructions (same results)
     SVB_FRAME_GATHER = 4,     // the batch goes to svb_mix_gather: plan separable YUV layers for the texture path (no staging limits)
+    SVB_FRAME_RING = 16,      // the batch goes to svb_mix_ring: the unit tables carry the pitch of the TILE-sized staged boxes
     SVB_FRAME_TMAP_FENCE = 8  // tensor-map slots of the context's table have been rewritten: acquire the frame's maps before the first copy
 };
 enum {
@@ -126,17 +127,17 @@ typedef struct __attribute__((aligned(64))) SvbFrameDesc {
 //                                                  b, 1-b, j0*pitch, j1*pitch      (pitch = the layer's staged box pitch in bytes:
 //                                                  a tap's shared-memory address is a per-lane column term plus the row's offset)
 //                                                  then 12 words  ok | (j1-j0) << 3 | j0 << 4  (edge and RGBA bodies), 4 words of padding
-//   column records (one per unit column, 2 words) and row records (one per unit row, 2 words): what a unit's plan needs of the
-//   blocks -- (origin of the staged luma box | origin of the chroma box << 16, SVB_UREC_* flags) -- so that a warp plans its
-//   unit from two 8-byte loads per layer (the plan is separable: a unit is inside a picture iff its column range and its row range are).
+//   column records (one per unit column, 4 words) and row records (one per unit row, 4 words): what a plan needs of the
+//   blocks -- (first source index luma | chroma << 16, last source index luma | chroma << 16, SVB_UREC_* flags, 0) -- so that a unit
+//   (or a tile of units) is planned from two 16-byte loads per layer (the plan is separable: a unit is inside a picture iff its column range and its row range are).
 #define SVB_UNIT_W 64
 #define SVB_UNIT_H 8
 #define SVB_UCOL_WORDS (3 * SVB_UNIT_W)
 #define SVB_UROW_WORDS 64
 #define SVB_UNITS_X(W) (((W) + SVB_UNIT_W - 1) / SVB_UNIT_W)
 #define SVB_UNITS_Y(H) (((H) + SVB_UNIT_H - 1) / SVB_UNIT_H)
-// words of one layer's tables: column blocks, row blocks, column records, row records (a multiple of 4: blocks stay 16-byte aligned)
-#define SVB_UTABLE_WORDS(W, H) ((SVB_UNITS_X(W) * (SVB_UCOL_WORDS + 2) + SVB_UNITS_Y(H) * (SVB_UROW_WORDS + 2) + 3) / 4 * 4)
+// words of one layer's tables: column blocks, row blocks, column records, row records
+#define SVB_UTABLE_WORDS(W, H) (SVB_UNITS_X(W) * (SVB_UCOL_WORDS + 4) + SVB_UNITS_Y(H) * (SVB_UROW_WORDS + 4))
 enum {
     SVB_UREC_FULL = 1,   // every entry of the block has border, tx and uv inside [0,1]: the range lies inside the picture
     SVB_UREC_XFREE = 2,  // (columns) no tap is clamped: i1 == i0 + 1 throughout
