@@ -223,7 +223,7 @@ def run_ours(args):
             for c in range(2):
                 dev[c][s][k] = host[s][k].upload(ctx)
     mixers = [sv.VideoMixer(ctx, CANVAS[0], CANVAS[1], yuv_fmt, asset_id=f"mixer{rank * S + s}", workspace_id="bench") for s in range(S)]
-    mode = {"fused": sv.MixMode.FUSED, "generic": sv.MixMode.GENERIC, "per_layer": sv.MixMode.PER_LAYER, "fused_gather": sv.MixMode.FUSED_GATHER, "fused_tiled": sv.MixMode.FUSED_TILED, "fused_strip": sv.MixMode.FUSED_STRIP, "fused_ring": sv.MixMode.FUSED_RING}[args.mode]
+    mode = {"fused": sv.MixMode.FUSED, "generic": sv.MixMode.GENERIC, "per_layer": sv.MixMode.PER_LAYER, "fused_gather": sv.MixMode.FUSED_GATHER, "fused_tiled": sv.MixMode.FUSED_TILED, "fused_ring": sv.MixMode.FUSED_RING}[args.mode]
     for m in mixers:
         m.set_mode(mode)
     for i in range(10):  # setup, untimed: fill every mixer's backing ring (10 targets, allocated on first use upstream too)
@@ -304,7 +304,7 @@ def run_ours(args):
         # warm-up launches are inside the timing window too; they run the same work, so the average stands
         achieved = ALG_BYTES_PER_FRAME * S / (per_launch_ms / 1e3) / 1e9
         roof = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": None, "peak_source": peak_src, "kernel": {"fused": {"gather": "svb_mix_gather", "tma": "svb_mix_tiled", "tiled": "svb_mix_tiled", "strip": "svb_mix_strip", "ring": "svb_mix_ring"}.get(os.environ.get("SVB_COMPOSITOR", ""), DEFAULT_COMPOSITOR), "fused_gather": "svb_mix_gather", "fused_tiled": "svb_mix_tiled", "fused_strip": "svb_mix_strip", "fused_ring": "svb_mix_ring"}.get(args.mode, "svb_mix_generic"), "kernel_ms_per_launch": round(per_launch_ms, 4),
+                "traffic": None, "peak_source": peak_src, "kernel": {"fused": {"gather": "svb_mix_gather", "tma": "svb_mix_tiled", "tiled": "svb_mix_tiled", "ring": "svb_mix_ring"}.get(os.environ.get("SVB_COMPOSITOR", ""), DEFAULT_COMPOSITOR), "fused_gather": "svb_mix_gather", "fused_tiled": "svb_mix_tiled", "fused_ring": "svb_mix_ring"}.get(args.mode, "svb_mix_generic"), "kernel_ms_per_launch": round(per_launch_ms, 4),
                 "algorithmic_bytes_per_launch": ALG_BYTES_PER_FRAME * S, "launches_timed": int(kern_n)}
         tr = ROOT / "profiles" / "traffic.json"
         if tr.exists() and args.mode.startswith("fused"):
@@ -563,8 +563,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to the CPU cores local to its GPU")
-    ap.add_argument("--mode", default="fused", choices=["fused", "fused_ring", "fused_strip", "fused_tiled", "fused_gather", "generic", "per_layer"],
-                    help="compose strategy: fused (default, svb_mix_strip), fused_tiled (svb_mix_tiled, the CTA-per-tile TMA compositor of round 1), fused_gather (svb_mix_gather: taps through the texture unit), "
+    ap.add_argument("--mode", default="fused", choices=["fused", "fused_ring", "fused_tiled", "fused_gather", "generic", "per_layer"],
+                    help="compose strategy: fused (default, svb_mix_ring), fused_tiled (svb_mix_tiled, the CTA-per-tile TMA compositor of round 1), fused_gather (svb_mix_gather: taps through the texture unit), "
                          "generic (svb_mix_generic), per_layer (the reference's own launch sequence over the drop-in kernels: clear + one "
                          "launch per layer)")
     ap.add_argument("--pip-opacity", type=float, default=None,

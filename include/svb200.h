@@ -75,7 +75,7 @@ typedef enum svb_compute_kernel {
 /* VideoMixer compose strategy (ours; the reference only has the per-layer sequence) */
 /* SVB_MIX_FUSED_GATHER: the fused compositor fetching its taps through the texture unit (svb_mix_gather) wherever every
  * staged layer's planes can be bound as textures (base and pitch alignment); same bytes, see DESIGN.md section 5 */
-typedef enum svb_mix_mode { SVB_MIX_FUSED = 0, SVB_MIX_PER_LAYER = 1, SVB_MIX_GENERIC = 2, SVB_MIX_FUSED_GATHER = 3, SVB_MIX_FUSED_TILED = 4, SVB_MIX_FUSED_STRIP = 5, SVB_MIX_FUSED_RING = 6 } svb_mix_mode;
+typedef enum svb_mix_mode { SVB_MIX_FUSED = 0, SVB_MIX_PER_LAYER = 1, SVB_MIX_GENERIC = 2, SVB_MIX_FUSED_GATHER = 3, SVB_MIX_FUSED_TILED = 4, SVB_MIX_FUSED_RING = 5 } svb_mix_mode;
 
 typedef struct svb_context svb_context; /* ComputeContext  (compute.cuda.swift:60-73) */
 typedef struct svb_picture svb_picture; /* PictureSample   (sample.pict.linux.swift:105-249), immutable */

@@ -18,7 +18,7 @@ KERNEL_CUSTOM = 15
 
 
 class MixMode:
-    FUSED, PER_LAYER, GENERIC, FUSED_GATHER, FUSED_TILED, FUSED_STRIP, FUSED_RING = 0, 1, 2, 3, 4, 5, 6
+    FUSED, PER_LAYER, GENERIC, FUSED_GATHER, FUSED_TILED, FUSED_RING = 0, 1, 2, 3, 4, 5
 
 
 STATUS_NAMES = ["ok", "invalidPlatform", "invalidDevice", "invalidOperation", "invalidValue", "invalidProgram", "invalidContext",

@@ -309,7 +309,7 @@ const char* svb_video_mixer_asset_id(const svb_mixer* mixer) { return mixer ? mi
 svb_status svb_video_mixer_set_mode(svb_mixer* mixer, int mode) {
     return guard([&] {
         need(mixer, "mixer");
-        if (mode < 0 || mode > 6) throw ComputeError(ErrorCode::invalidValue, "bad mix mode");
+        if (mode < 0 || mode > 5) throw ComputeError(ErrorCode::invalidValue, "bad mix mode");
         mixer->m->setMode((VideoMixer::Mode)mode);
     });
 }
@@ -356,7 +356,7 @@ svb_status svb_compose(svb_context* ctx, const svb_picture* target, const svb_pi
     return guard([&] {
         need(ctx, "ctx");
         need(target, "target");
-        if (mode < 0 || mode > 6) throw ComputeError(ErrorCode::invalidValue, "bad mix mode");
+        if (mode < 0 || mode > 5) throw ComputeError(ErrorCode::invalidValue, "bad mix mode");
         std::vector<const PictureSample*> ls;
         for (int i = 0; i < count; ++i) {
             need(layers[i], "layer");

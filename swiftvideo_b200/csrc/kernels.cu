@@ -3,7 +3,7 @@
 //   kernels_dropin.cuh  the ten per-layer kernels under the reference's names and parameter convention
 //   kernels_fused.cuh   svb_mix_generic: clear + N layers in one launch, any transform / format
 //   kernels_tiled.cuh   svb_mix_tiled:   the TMA-staged tile path for separable YUV layers
-//   kernels_strip.cuh   svb_mix_strip:   the warp-autonomous TMA compositor (round 2): a warp stages and composites its own 64x8 unit
+//   kernels_strip.cuh   the unit-level layer bodies (taps carried from row to row, half-texel body) and svb_strip_tables, the pre-pass
 //   kernels_ring.cuh    svb_mix_ring:    128x32 tiles planned and staged once per CTA, composited by eight free-running warps through a three-stage mbarrier ring
 //   kernels_gather.cuh  svb_mix_gather: the same compositor with the texture unit fetching the bilinear footprints (no staging, no barriers)
 //   kernels_scale.cuh   svb_scale_convert: NV12 / P010 -> BGRA with a bilinear / Lanczos-3 resize (an extension; no upstream counterpart)

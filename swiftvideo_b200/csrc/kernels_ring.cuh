@@ -2,13 +2,13 @@
 //
 // svb_mix_tiled (round 1) amortises planning and staging over a CTA -- one plan, one set of TMA copies per 128x32 tile and layer --
 // but its eight warps meet at a CTA barrier in front of every layer (20 % of its stall samples) and its layer bodies are large.
-// svb_mix_strip made the warp autonomous (no barrier, compact loops that carry converted taps from one output row to the next, the
-// running picture in shared memory) but pays planning, table copies and TMA issue per 64x8 unit: 43 % of its instructions were
-// overhead.  This kernel takes the halves that worked:
+// A second design of this round made the warp autonomous -- every warp planned, staged and composited its own 64x8 unit with the
+// compact loops of kernels_strip.cuh, no barrier at all -- but paid planning, table copies and TMA issue per unit: 43 % of its
+// instructions were overhead, and it only drew level with svb_mix_tiled (profiles/r2_history.md).  This kernel takes the halves that worked:
 //   * a CTA of eight warps owns a 128x32 tile: ONE warp plans it (lane = layer, from the column / row records svb_strip_tables
 //     leaves), ONE elected lane issues its copies -- per tile and layer two or three TMA tensor copies of the source footprint and two
 //     bulk copies of the table blocks;
-//   * each warp composites its own 64x8 unit of the tile with svb_mix_strip's layer bodies, at its own pace: the staged layers go
+//   * each warp composites its own 64x8 unit of the tile with the layer bodies of kernels_strip.cuh, at its own pace: the staged layers go
 //     through a ring of THREE stages with a `full` mbarrier (the copies' bytes) and an `empty` mbarrier (eight warp arrivals) per
 //     stage, so a warp waits for data, never for another warp, and the issuing lane only waits for a warp that lags by more than a layer;
 //   * the ring runs across tiles: the plan of the next tile is ready (its own pair of mbarriers) long before this tile's last
@@ -24,6 +24,19 @@
 namespace svb {
 
 __device__ __forceinline__ void mbar_arrive(unsigned bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ bool mbar_try_u32(unsigned bar, unsigned parity, unsigned hint_ns) {  // one try, sleeping up to hint_ns for the phase
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(hint_ns)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait_u32(unsigned bar, unsigned parity) {
     unsigned ok;
     unsigned spin = 0;
@@ -38,6 +51,9 @@ __device__ __forceinline__ void mbar_wait_u32(unsigned bar, unsigned parity) {
             : "r"(bar), "r"(parity), "r"(2000u)
             : "memory");
         if (++spin > (1u << 22)) __trap();  // a copy that never lands must not hang the GPU
+#ifdef SVB_RING_WAIT_SLEEP
+        if (!ok) __nanosleep(SVB_RING_WAIT_SLEEP);
+#endif
     } while (!ok);
 }
 
@@ -53,7 +69,7 @@ extern "C" __global__ void __launch_bounds__(SVB_RING_THREADS, SVB_RING_MIN_CTAS
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // mbarriers: full[3] (copies landed), empty[3] (eight warps have left the stage), pfull[3] (plan written), pempty[3] (eight warps have left the plan)
     const unsigned bars = smem_u32(smem_raw);
-    const unsigned full0 = bars, empty0 = bars + 24u, pfull0 = bars + 48u, pempty0 = bars + 72u;
+    const unsigned full0 = bars, empty0 = full0 + 8u * SVB_RING_STAGES, pfull0 = empty0 + 8u * SVB_RING_STAGES, pempty0 = pfull0 + 8u * SVB_RING_PLANS;
     const unsigned stage_bytes = (unsigned)(box_y_bytes + box_c_bytes) + SVB_RING_TAB_BYTES;
     unsigned char* const my_state = smem_raw + SVB_RING_HDR_BYTES + (size_t)(warp & 7) * SVB_STRIP_STATE_BYTES;
     float2* const sY = reinterpret_cast<float2*>(my_state);  // [12 rows][32 lanes]: luma pairs of rows 0..7, then (U, V) of chroma rows 0..3
@@ -62,7 +78,7 @@ extern "C" __global__ void __launch_bounds__(SVB_RING_THREADS, SVB_RING_MIN_CTAS
     const unsigned stage0 = plan0 + (unsigned)SVB_RING_PLANS * (unsigned)plan_slot_bytes;
     const unsigned tab_off = (unsigned)(box_y_bytes + box_c_bytes);
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < SVB_RING_STAGES; ++i) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full0 + 8u * i), "r"(1));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty0 + 8u * i), "r"(SVB_RING_WARPS));
         }
@@ -94,48 +110,55 @@ extern "C" __global__ void __launch_bounds__(SVB_RING_THREADS, SVB_RING_MIN_CTAS
         bool covers = false, inner = false;
         uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, r2 = r0, r3 = r0, r4 = r0;
         if (lane < nl) {
+            // every load of the plan is issued here, before anything is looked at (one trip to L2, not six): the layer's constants and
+            // the records of the tile's two unit columns and four unit rows (indices clamped: an absent unit is masked below)
             const uint4* __restrict__ pc = reinterpret_cast<const uint4*>(&F->layers[lane].pc);
-            const uint4 c2 = __ldg(pc + 2), c3 = __ldg(pc + 3);
+            const size_t lw = (size_t)F->table_base + (size_t)lane * strip_layer_words(F);
+            const uint4* __restrict__ rec = reinterpret_cast<const uint4*>(tables + lw + (size_t)ux_n * SVB_UCOL_WORDS + (size_t)uy_n * SVB_UROW_WORDS);
+            const uint4 c0 = __ldg(pc), c1 = __ldg(pc + 1), c2 = __ldg(pc + 2), c3 = __ldg(pc + 3);
+            uint4 q[6];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) q[k] = __ldg(rec + min(2 * tx + k, ux_n - 1));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) q[2 + k] = __ldg(rec + ux_n + min(4 * ty + k, uy_n - 1));
             const unsigned fmt = c2.y & 0xfu, lflags = (c2.y >> 4) & 0xffu;
             if ((int)c3.x < x0 + 2 * SVB_UNIT_W && (int)c3.z > x0 && (int)c3.y < y0 + 4 * SVB_UNIT_H && (int)c3.w > y0) {  // the layer's rectangle touches the tile
                 r0.w = c2.x;
-                r1.z = c2.z + (unsigned)(2 * tx) * SVB_UCOL_WORDS, r1.w = c2.z + (unsigned)ux_n * SVB_UCOL_WORDS + (unsigned)(4 * ty) * SVB_UROW_WORDS;
+                r1.z = (unsigned)lw + (unsigned)(2 * tx) * SVB_UCOL_WORDS, r1.w = (unsigned)lw + (unsigned)ux_n * SVB_UCOL_WORDS + (unsigned)(4 * ty) * SVB_UROW_WORDS;
                 r3.z = (unsigned)ncol * SVB_UCOL_WORDS * 4u, r3.w = (unsigned)nrow * SVB_UROW_WORDS * 4u;
                 if (!(lflags & SVB_LAYER_SEPARABLE)) {
                     mode = PLAN_GENERIC;
                 } else if (fmt != SVB_NV12 && fmt != SVB_Y420P) {
                     mode = PLAN_TABLE_RGBA;
                 } else {
-                    const uint4* __restrict__ rec = reinterpret_cast<const uint4*>(tables + c2.w);
-                    // the tile's unit columns and unit rows: first / last source index, flags
-                    unsigned lo = 0xffffu, loc = 0xffffu, hi = 0u, hic = 0u, all = ~0u, cf = 0u, rf = 0u, any_mixed = 0u;
-                    for (int k = 0; k < ncol; ++k) {
-                        const uint4 q = __ldg(rec + 2 * tx + k);
-                        const bool touch = (int)c3.x < x0 + (k + 1) * SVB_UNIT_W && (int)c3.z > x0 + k * SVB_UNIT_W;
-                        lo = min(lo, q.x & 0xffffu), loc = min(loc, q.x >> 16), hi = max(hi, q.y & 0xffffu), hic = max(hic, q.y >> 16);
-                        all &= q.z, any_mixed |= q.z;
-                        cf |= ((q.z & 0x7fu) | (touch ? SVB_RREC_TOUCH : 0u)) << (8 * k);
-                    }
-                    const unsigned ix0 = lo, ic0 = loc, ix1 = hi, ic1 = hic;
-                    lo = loc = 0xffffu, hi = hic = 0u;
-                    for (int k = 0; k < nrow; ++k) {
-                        const uint4 q = __ldg(rec + ux_n + 4 * ty + k);
-                        const bool touch = (int)c3.y < y0 + (k + 1) * SVB_UNIT_H && (int)c3.w > y0 + k * SVB_UNIT_H;
-                        lo = min(lo, q.x & 0xffffu), loc = min(loc, q.x >> 16), hi = max(hi, q.y & 0xffffu), hic = max(hic, q.y >> 16);
-                        all &= q.z | SVB_UREC_XFREE, any_mixed |= q.z;
-                        rf |= ((q.z & 0x7fu) | (touch ? SVB_RREC_TOUCH : 0u)) << (8 * k);
-                    }
-                    const uint4 c1 = __ldg(pc + 1);
+                    // first / last source index over the tile's unit columns and unit rows; their flags
+                    unsigned ix0 = 0xffffu, ic0 = 0xffffu, ix1 = 0u, ic1 = 0u, jy0 = 0xffffu, jc0 = 0xffffu, jy1 = 0u, jc1 = 0u, all = ~0u, cf = 0u, rf = 0u;
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+                        if (k < ncol) {
+                            const bool touch = (int)c3.x < x0 + (k + 1) * SVB_UNIT_W && (int)c3.z > x0 + k * SVB_UNIT_W;
+                            ix0 = min(ix0, q[k].x & 0xffffu), ic0 = min(ic0, q[k].x >> 16), ix1 = max(ix1, q[k].y & 0xffffu), ic1 = max(ic1, q[k].y >> 16);
+                            all &= q[k].z;
+                            cf |= ((q[k].z & 0x7fu) | (touch ? SVB_RREC_TOUCH : 0u)) << (8 * k);
+                        }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (k < nrow) {
+                            const bool touch = (int)c3.y < y0 + (k + 1) * SVB_UNIT_H && (int)c3.w > y0 + k * SVB_UNIT_H;
+                            jy0 = min(jy0, q[2 + k].x & 0xffffu), jc0 = min(jc0, q[2 + k].x >> 16), jy1 = max(jy1, q[2 + k].y & 0xffffu), jc1 = max(jc1, q[2 + k].y >> 16);
+                            all &= q[2 + k].z | SVB_UREC_XFREE;
+                            rf |= ((q[2 + k].z & 0x7fu) | (touch ? SVB_RREC_TOUCH : 0u)) << (8 * k);
+                        }
                     const unsigned box_w = c1.w & 0xffffu, box_h = (c2.y >> 12) & 0x3ffu, box_ch = c2.y >> 22;
                     const unsigned box_cw = (c1.w >> 16) / (fmt == SVB_NV12 ? 2u : 1u);
                     // (column records hold origins already rounded down for TMA; the footprint must fit the tile-sized boxes)
-                    const bool fits = (lflags & SVB_LAYER_STAGED) && ix1 - ix0 < box_w && hi - lo < box_h && ic1 - ic0 < box_cw && hic - loc < box_ch;
+                    const bool fits = (lflags & SVB_LAYER_STAGED) && ix1 - ix0 < box_w && jy1 - jy0 < box_h && ic1 - ic0 < box_cw && jc1 - jc0 < box_ch;
                     mode = fits ? PLAN_STAGED : PLAN_GENERIC;
                     covers = (all & SVB_UREC_FULL) && (lflags & SVB_LAYER_UNIT_OPACITY);
                     inner = fits && (all & SVB_UREC_XFREE);  // every unit of the tile takes the interior body
-                    r0.y = ix0 | (lo << 16), r0.z = ic0 | (loc << 16);
+                    r0.y = ix0 | (jy0 << 16), r0.z = ic0 | (jc0 << 16);
                     r1.x = c1.z + r3.z + r3.w, r1.y = c1.w;
-                    r2 = __ldg(pc);
+                    r2 = c0;
                     r3.x = c1.x, r3.y = c1.y;
                     r4 = make_uint4(cf, rf, 0u, 0u);
                 }
@@ -192,25 +215,50 @@ extern "C" __global__ void __launch_bounds__(SVB_RING_THREADS, SVB_RING_MIN_CTAS
     // producer and every consumer count alike because they read the same plans, so nobody tracks barrier phases.  Tile n of this CTA
     // has its plan in slot n % 3.
     if (warp == SVB_RING_WARPS) {
-        unsigned gi = 0;  // staged layers issued
-        for (unsigned n = 0;; ++n) {
-            const unsigned slot = n % SVB_RING_PLANS;
-            if (n >= SVB_RING_PLANS) mbar_wait_u32(pempty0 + 8u * slot, ((n / SVB_RING_PLANS) - 1u) & 1u);  // every consumer has left the slot's previous plan
-            int t = 0;
-            if (lane == 0) t = atomicAdd(tile_counter, 1);
-            t = __shfl_sync(0xffffffffu, t, 0);
-            plan_tile(t, (int)slot);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(pfull0 + 8u * slot);
-            if (t >= total_tiles) return;
-            const unsigned pa = plan0 + slot * (unsigned)plan_slot_bytes;
-            unsigned smask = lds_u4(pa).x >> 16;
-            for (unsigned i = 0; smask; smask >>= 1, ++i) {
-                if (!(smask & 1u)) continue;
-                const unsigned b = gi % SVB_RING_STAGES;
-                if (gi >= SVB_RING_STAGES) mbar_wait_u32(empty0 + 8u * b, ((gi / SVB_RING_STAGES) - 1u) & 1u);  // every consumer has left the stage's previous tenant
-                issue(pa + SVB_RPLAN_HDR_BYTES + SVB_RPLAN_REC_BYTES * i, b);
-                ++gi;
+        // The producer serves two queues and never blocks on one while the other has work: a stage that the consumers have left is
+        // refilled at once (first priority: a consumer may be waiting for those bytes), and whenever a plan slot is free the next tile
+        // is claimed and planned -- up to three tiles ahead, so a consumer never waits for a plan.
+        unsigned gi = 0;       // staged layers issued
+        unsigned planned = 0;  // tiles planned
+        unsigned n = 0, i = 0, smask = 0;  // the tile whose staged layers are being issued, its next listed layer, the staged layers left (bit 0 = layer i)
+        bool have_tile = false, last_planned = false;
+        for (unsigned idle = 0;;) {
+            if (!have_tile && planned > n) {
+                const unsigned hx = lds_u4(plan0 + (n % SVB_RING_PLANS) * (unsigned)plan_slot_bytes).x;
+                if ((hx & 0xffffu) == 0xffffu) return;  // the end marker
+                smask = hx >> 16, i = 0, have_tile = true;
+            }
+            if (have_tile) {
+                if (!smask) {
+                    ++n, have_tile = false;
+                    continue;
+                }
+                const unsigned skip = (unsigned)__ffs(smask) - 1u;
+                smask >>= skip, i += skip;
+            }
+            bool did = false;
+            const unsigned b = gi % SVB_RING_STAGES;
+            if (have_tile && (gi < SVB_RING_STAGES || mbar_try_u32(empty0 + 8u * b, ((gi / SVB_RING_STAGES) - 1u) & 1u, 0u))) {  // every consumer has left the stage's previous tenant
+                issue(plan0 + (n % SVB_RING_PLANS) * (unsigned)plan_slot_bytes + SVB_RPLAN_HDR_BYTES + SVB_RPLAN_REC_BYTES * i, b);
+                ++gi, smask >>= 1, ++i, did = true;
+            } else if (!last_planned && planned < n + SVB_RING_PLANS) {
+                const unsigned slot = planned % SVB_RING_PLANS;
+                if (planned < SVB_RING_PLANS || mbar_try_u32(pempty0 + 8u * slot, ((planned / SVB_RING_PLANS) - 1u) & 1u, 0u)) {  // every consumer has left the slot's previous plan
+                    int t = 0;
+                    if (lane == 0) t = atomicAdd(tile_counter, 1);
+                    t = __shfl_sync(0xffffffffu, t, 0);
+                    plan_tile(t, (int)slot);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(pfull0 + 8u * slot);
+                    ++planned, did = true, last_planned = t >= total_tiles;
+                }
+            }
+            if (did) {
+                idle = 0;
+            } else {  // nothing to do right now: sleep on the barrier that matters most
+                if (have_tile) mbar_try_u32(empty0 + 8u * b, ((gi / SVB_RING_STAGES) - 1u) & 1u, 1000u);
+                else mbar_try_u32(pempty0 + 8u * (planned % SVB_RING_PLANS), ((planned / SVB_RING_PLANS) - 1u) & 1u, 1000u);
+                if (++idle > (1u << 22)) __trap();  // a barrier that never completes must not hang the GPU
             }
         }
     }

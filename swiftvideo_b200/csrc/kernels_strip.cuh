@@ -1,32 +1,23 @@
-// kernels_strip.cuh -- svb_mix_strip: the fused compositor's fast path, second design (round 2).
+// kernels_strip.cuh -- the unit-level machinery of the fused compositor's fast path (round 2): the layer bodies that composite one
+// 64x8 unit of an output frame, and svb_strip_tables, the pre-pass that feeds them.  svb_mix_ring (kernels_ring.cuh) is the
+// compositor built on them.
 //
-// What the profile of svb_mix_tiled said (profiles/r2_history.md): its layer bodies would saturate the issue port on their
-// own, but a warp spent 56 % of its time outside them -- at the CTA barrier of every staged layer (20 %), waiting for plan /
-// descriptor loads, and in per-layer and per-tile set-up code (a third of all instructions).  Hence here:
-//   * a WARP is the unit of work and never waits for another warp: it owns a 64x8 unit of an output frame (claimed from a
-//     counter in row-major order) and stages ITS OWN source footprint -- one TMA 2-D tensor copy per plane into a private
-//     double buffer, completion on a private mbarrier; the copies of the next layer (or of the next unit's first layer) fly
-//     while the current one is computed;
-//   * a warp plans its own units, one ahead, lane = layer: which layers touch the unit, how (interior / edge / per-pixel), where
-//     their boxes start -- two 8-byte loads per layer, because the plan is separable (svb_strip_tables leaves a record per unit
-//     column and per unit row of every layer); a layer's table slices (the reference's coordinate chain, kernels.cl.swift:70-78,
-//     per output column and row, in the form the inner loop consumes -- weights with their complements, row offsets already
-//     multiplied by the box pitch) arrive with its boxes by two bulk copies;
-//   * free-running warps do not share an instruction stream, so the hot code must fit the instruction cache of a scheduler on its
-//     own: ONE loop of two output rows (~2 KB) serves luma and chroma rows, NV12 and planar sources alike;
-//   * a lane owns two adjacent luma columns x 8 rows and the chroma texel column under them, and walks DOWN its rows: the
-//     converted taps of a source row stay in registers and serve the next output row when it continues from there (always at
-//     1:1, four rows in five at the 1.2:1 of the headline workload), so a sample costs two or three new taps, not four;
-//   * the running picture of the unit lives in shared memory (3 KB per warp, integer-valued floats, re-quantised after
-//     every layer exactly like the reference's 8-bit target, mix.video.swift:113-125).
-// The per-sample arithmetic is fast_layer's (kernels_tiled.cuh), operation for operation: packed fp32x2, every multiply and
-// add rounded on its own.
+//   * a warp owns a 64x8 unit; a lane owns two adjacent luma columns x 8 rows and the chroma texel column under them, and walks DOWN
+//     its rows: the converted taps of a source row stay in registers and serve the next output row when it continues from there
+//     (always at 1:1, four rows in five at the 1.2:1 of the headline workload), so a sample costs two or three new taps, not four;
+//   * warps that do not run in lock-step do not share an instruction stream, so the hot code must fit the instruction cache of a
+//     scheduler on its own: ONE loop of two output rows (~2 KB) serves luma and chroma rows, NV12 and planar sources alike (a first
+//     version with a 5 KB body per mode spent a quarter of its stall samples on instruction fetch, profiles/r2_history.md);
+//   * the running picture of the unit lives in shared memory (3 KB per warp, integer-valued floats, re-quantised after every layer
+//     exactly like the reference's 8-bit target, mix.video.swift:113-125): the row loop stays rolled without register rotation;
+//   * everything a row needs arrives in the form the loop consumes: svb_strip_tables evaluates the reference's coordinate chain
+//     (kernels.cl.swift:70-78) once per output column and row, bit-exactly, and stores weights with their complements and row
+//     offsets already multiplied by the staged box pitch, blocked per unit; it also leaves one record per unit column and unit row
+//     (footprint, inside / edge / fill classes) from which a tile is planned with a handful of loads, because the plan is separable.
+// The per-sample arithmetic is fast_layer's (kernels_tiled.cuh), operation for operation: packed fp32x2, every multiply and add
+// rounded on its own.
 #pragma once
 #include "kernels_tiled.cuh"
-
-#ifndef SVB_STRIP_MIN_CTAS
-#define SVB_STRIP_MIN_CTAS 5
-#endif
 
 namespace svb {
 
@@ -267,7 +258,7 @@ __device__ __noinline__ void strip_rgba_layer(const SvbLayerDesc* __restrict__ L
     }
 }
 
-__device__ __forceinline__ size_t strip_layer_words(const SvbFrameDesc* __restrict__ F) {  // tiles_x / tiles_y hold the unit counts in a strip batch
+__device__ __forceinline__ size_t strip_layer_words(const SvbFrameDesc* __restrict__ F) {  // tiles_x / tiles_y hold the unit counts in a ring batch
     return (size_t)(F->tiles_x * (SVB_UCOL_WORDS + 4) + F->tiles_y * (SVB_UROW_WORDS + 4));
 }
 
@@ -292,7 +283,7 @@ __device__ __forceinline__ bool elect_one() {
 // (at most 32 registers: 96 x 32 fit beside the resident CTAs of the compositor launched before, so this pre-pass runs UNDER that launch)
 extern "C" __global__ void __launch_bounds__(96, 21) svb_strip_tables(const SvbFrameDesc* __restrict__ frames, uint32_t* __restrict__ tables, int* __restrict__ unit_counter) {
     using namespace svb;
-    if ((blockIdx.x | blockIdx.y | blockIdx.z | threadIdx.x) == 0) *unit_counter = 0;  // svb_mix_strip claims its units from it
+    if ((blockIdx.x | blockIdx.y | blockIdx.z | threadIdx.x) == 0) *unit_counter = 0;  // svb_mix_ring claims its tiles from it
     const SvbFrameDesc* __restrict__ F = frames + blockIdx.z;
     const int l = (int)blockIdx.y;
     if (l >= F->nlayers) return;
@@ -302,9 +293,8 @@ extern "C" __global__ void __launch_bounds__(96, 21) svb_strip_tables(const SvbF
     const int b = (int)blockIdx.x, t = (int)threadIdx.x;
     if (b >= ux_n + uy_n) return;
     const bool yuv = L->format == SVB_NV12 || L->format == SVB_Y420P;  // BGRA / RGBA layers only use the luma-resolution entries
-    const bool ring = (F->flags & SVB_FRAME_RING) != 0;  // svb_mix_ring stages tile-sized boxes (box_*), svb_mix_strip unit-sized ones (sbox_*)
-    const bool staged = (L->flags & (ring ? SVB_LAYER_STAGED : SVB_LAYER_STAGED_S)) != 0;
-    const int bx_w = ring ? L->box_w : L->sbox_w, bx_h = ring ? L->box_h : L->sbox_h, bx_cw = ring ? L->box_cw : L->sbox_cw, bx_ch = ring ? L->box_ch : L->sbox_ch;
+    const bool staged = (L->flags & SVB_LAYER_STAGED) != 0;
+    const int bx_w = L->box_w, bx_h = L->box_h, bx_cw = L->box_cw, bx_ch = L->box_ch;  // the tile-sized staged boxes (row offsets carry their pitch)
     uint32_t* __restrict__ base = tables + F->table_base + (size_t)l * strip_layer_words(F);
     uint32_t* __restrict__ rbase = base + ux_n * SVB_UCOL_WORDS;
     uint32_t* __restrict__ crec = rbase + uy_n * SVB_UROW_WORDS;
@@ -361,273 +351,5 @@ extern "C" __global__ void __launch_bounds__(96, 21) svb_strip_tables(const SvbF
         flags |= (full ? SVB_UREC_FULL : 0u) | (fits ? SVB_UREC_FITS : 0u);
         const int jc1 = yuv ? max(s_i1[c0], s_i1[c1]) : 0;
         reinterpret_cast<uint4*>(rrec)[r] = make_uint4((unsigned)jy0 | ((unsigned)jc0 << 16), (unsigned)max(s_i1[0], s_i1[lastr]) | ((unsigned)jc1 << 16), flags, 0u);
-    }
-}
-
-// ---- the compositor ---------------------------------------------------------------------------------------------------------
-extern "C" __global__ void __launch_bounds__(SVB_STRIP_THREADS, SVB_STRIP_MIN_CTAS)
-    svb_mix_strip(const SvbFrameDesc* __restrict__ frames, const uint32_t* __restrict__ tables, int nframes, int total_units, float one, int* __restrict__ unit_counter, int box_y_bytes,
-                  int box_c_bytes, int plan_slot_bytes) {
-    using namespace svb;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint64_t* const bar = reinterpret_cast<uint64_t*>(smem_raw) + 2 * warp;  // this warp's two stages
-    const unsigned stage_bytes = (unsigned)(box_y_bytes + box_c_bytes) + SVB_STRIP_TAB_BYTES;
-    unsigned char* const mine = smem_raw + SVB_STRIP_HDR_BYTES + (size_t)warp * (size_t)(SVB_STRIP_STATE_BYTES + 2 * plan_slot_bytes + 2 * stage_bytes);
-    float2* const sY = reinterpret_cast<float2*>(mine);  // [12 rows][32 lanes]: luma pairs of rows 0..7, then (U, V) of chroma rows 0..3
-    const unsigned state = smem_u32(mine) + 8u * lane;
-    const unsigned plan0 = smem_u32(mine + SVB_STRIP_STATE_BYTES);    // two plan slots
-    const unsigned stage0 = plan0 + 2u * (unsigned)plan_slot_bytes;  // stage s: luma box, chroma box, table blocks
-    const unsigned tab_off = (unsigned)(box_y_bytes + box_c_bytes);
-    if (lane == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    const unsigned mb0 = smem_u32(&bar[0]);
-    // first unit of every frame of the batch (at most 64 frames: two per lane), to find a unit's frame with two votes
-    const int firstA = lane < nframes ? frames[lane].first_tile : 0x7fffffff, firstB = lane + 32 < nframes ? frames[lane + 32].first_tile : 0x7fffffff;
-    int fenced = -1;  // (after the tensor-map table has wrapped) frame whose maps the issuing lane has acquired
-    unsigned phase0 = 0, phase1 = 0;
-    int stage = 0;        // buffer that holds (or is about to receive) the next staged layer to consume
-    bool primed = false;  // this unit's first staged layer was put in flight by the previous unit
-
-    // ---- the plan of unit u, into plan slot s: lane = layer (svb_desc.h: header + one record per layer that touches the unit) ----
-    auto plan_unit = [&](int u, int s) {
-        const int f = __popc(__ballot_sync(0xffffffffu, u >= firstA)) + __popc(__ballot_sync(0xffffffffu, u >= firstB)) - 1;
-        const int first = f < 32 ? __shfl_sync(0xffffffffu, firstA, f) : __shfl_sync(0xffffffffu, firstB, f - 32);
-        const SvbFrameDesc* __restrict__ F = frames + f;
-        const int ux_n = F->tiles_x, nl = F->nlayers, local = u - first;
-        const int uy = local / ux_n, ux = local - uy * ux_n, x0 = ux * SVB_UNIT_W, y0 = uy * SVB_UNIT_H;
-        unsigned mode = PLAN_SKIP;
-        bool covers = false;
-        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, r2 = r0, r3 = r0;
-        if (lane < nl) {
-            const uint4* __restrict__ pc = reinterpret_cast<const uint4*>(&F->layers[lane].pc);
-            const uint4 c2 = __ldg(pc + 2), c3 = __ldg(pc + 3);
-            const unsigned fmt = c2.y & 0xffu, lflags = c2.y >> 8;
-            if ((int)c3.x < x0 + SVB_UNIT_W && (int)c3.z > x0 && (int)c3.y < y0 + SVB_UNIT_H && (int)c3.w > y0) {  // the layer's rectangle touches the unit
-                r0.w = c2.x;
-                r1.z = c2.z + (unsigned)ux * SVB_UCOL_WORDS, r1.w = c2.z + (unsigned)ux_n * SVB_UCOL_WORDS + (unsigned)uy * SVB_UROW_WORDS;
-                if (!(lflags & SVB_LAYER_SEPARABLE)) {
-                    mode = PLAN_GENERIC;
-                } else if (fmt != SVB_NV12 && fmt != SVB_Y420P) {
-                    mode = PLAN_TABLE_RGBA;
-                } else {
-                    const uint4* __restrict__ rec = reinterpret_cast<const uint4*>(tables + c2.w);
-                    const uint4 cq = __ldg(rec + ux), rq = __ldg(rec + ux_n + uy);
-                    const uint2 cr = make_uint2(cq.x, cq.z), rr = make_uint2(rq.x, rq.z);
-                    const uint4 c1 = __ldg(pc + 1);
-                    r2 = __ldg(pc);
-                    const unsigned both = cr.y & rr.y;
-                    const bool full = (both & SVB_UREC_FULL) != 0u;
-                    mode = !(both & SVB_UREC_FITS) ? PLAN_GENERIC : (full && (cr.y & SVB_UREC_XFREE) ? PLAN_STAGED : PLAN_STAGED_EDGE);
-                    covers = full && (lflags & SVB_LAYER_UNIT_OPACITY);
-                    r0.y = (cr.x & 0xffffu) | (rr.x << 16), r0.z = (cr.x >> 16) | (rr.x & 0xffff0000u);
-                    r1.x = c1.z, r1.y = c1.w;
-                    r3 = make_uint4(c1.x, c1.y, (both & SVB_UREC_HALF) | ((cr.y | rr.y) & SVB_UREC_MIXED), 0u);
-                }
-                r0.x = mode | ((unsigned)lane << 8) | (fmt << 16) | (lflags << 20);
-            }
-        }
-        unsigned act = __ballot_sync(0xffffffffu, mode != PLAN_SKIP);
-        const unsigned cov = __ballot_sync(0xffffffffu, covers), stg = __ballot_sync(0xffffffffu, mode >= PLAN_STAGED), inner = __ballot_sync(0xffffffffu, mode == PLAN_STAGED);
-        unsigned first_covers = 0;
-        if (cov) {
-            const unsigned top = 31u - (unsigned)__clz(cov);
-            act &= ~((1u << top) - 1u);  // drop what the topmost covering layer hides
-            first_covers = (inner >> top) & 1u;
-        }
-        const unsigned slot_a = plan0 + (unsigned)s * (unsigned)plan_slot_bytes, below = act & ((1u << lane) - 1u);
-        auto sts4 = [](unsigned a, const uint4 v) { asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); };
-        if ((act >> lane) & 1u) {
-            const unsigned a = slot_a + SVB_UPLAN_HDR_BYTES + SVB_UPLAN_REC_BYTES * (unsigned)__popc(below);
-            sts4(a, r0), sts4(a + 16, r1), sts4(a + 32, r2), sts4(a + 48, r3);
-        }
-        // bit i of the staged mask: the i-th listed layer is staged -- every listed staged layer sets the bit of its own position
-        const unsigned smask = __reduce_or_sync(0xffffffffu, ((act & stg) >> lane) & 1u ? 1u << __popc(below) : 0u);
-        if (lane == 0) sts4(slot_a, make_uint4((unsigned)__popc(act) | (smask << 16), (unsigned)x0 | ((unsigned)y0 << 16), (unsigned)f, first_covers));
-        __syncwarp();
-    };
-    auto bulk = [&](unsigned dst, const void* src, unsigned bytes, unsigned mb) {
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(mb) : "memory");
-    };
-    // the async copies of the staged layer whose plan record lies at shared-memory address ra, into stage b (one elected lane); f = its frame
-    auto issue = [&](unsigned ra, int f, int b) {
-        const uint4 r0 = lds_u4(ra), r1 = lds_u4(ra + 16), r2 = lds_u4(ra + 32), r3 = lds_u4(ra + 48);
-        if (elect_one()) {
-            if (f != fenced) {
-                const SvbFrameDesc* __restrict__ TF = frames + f;
-                if (TF->flags & SVB_FRAME_TMAP_FENCE)
-                    for (int q = 0; q < TF->nlayers; ++q)
-                        if (TF->layers[q].flags & SVB_LAYER_STAGED_S) {
-                            tmap_acquire((const void*)TF->layers[q].stmap[0]);
-                            tmap_acquire((const void*)TF->layers[q].stmap[1]);
-                            if (TF->layers[q].format != SVB_NV12) tmap_acquire((const void*)TF->layers[q].stmap[2]);
-                        }
-                fenced = f;
-            }
-            const unsigned dst = stage0 + (unsigned)b * stage_bytes, mb = mb0 + 8u * (unsigned)b;
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(r1.x) : "memory");
-            auto tma = [&](unsigned d, unsigned long long tmap, unsigned x, unsigned y) {
-                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(d), "l"(tmap), "r"(x), "r"(y), "r"(mb)
-                             : "memory");
-            };
-            tma(dst, ((unsigned long long)r2.y << 32) | r2.x, r0.y & 0xffffu, r0.y >> 16);
-            tma(dst + (unsigned)box_y_bytes, ((unsigned long long)r2.w << 32) | r2.z, r0.z & 0xffffu, r0.z >> 16);
-            if (((r0.x >> 16) & 0xfu) != SVB_NV12) tma(dst + (unsigned)box_y_bytes + (unsigned)box_c_bytes / 2u, ((unsigned long long)r3.y << 32) | r3.x, r0.z & 0xffffu, r0.z >> 16);
-            bulk(dst + tab_off, tables + r1.z, SVB_UCOL_WORDS * 4, mb);
-            bulk(dst + tab_off + SVB_UCOL_WORDS * 4, tables + r1.w, SVB_UROW_WORDS * 4, mb);
-        }
-        __syncwarp();
-    };
-
-    // Units are claimed two ahead by lane 0 (the atomic's latency is nobody's wait).  Every pass of the loop below plans the NEXT unit
-    // (one call site: the planning code exists once) and then computes the current one, whose plan the pass before left in `slot`.
-    int c0 = 0, c1 = 0;  // lane 0's: the next two units to plan
-    if (lane == 0) {
-        c0 = atomicAdd(unit_counter, 1);
-        c1 = atomicAdd(unit_counter, 1);
-    }
-    bool have_cur = false;
-    int slot = 1;  // plan slot of the current unit (the first pass has none and plans into slot 0)
-    for (;;) {
-        const int un = __shfl_sync(0xffffffffu, c0, 0);  // (claimed at least a whole unit ago, but for the first two)
-        const bool have_nxt = un < total_units;
-        if (lane == 0) c0 = c1, c1 = atomicAdd(unit_counter, 1);
-        const unsigned plan = plan0 + (unsigned)slot * (unsigned)plan_slot_bytes, nplan = plan0 + (unsigned)(slot ^ 1) * (unsigned)plan_slot_bytes;
-        uint4 h0 = make_uint4(0, 0, 0, 0);
-        if (have_cur) {  // this unit's first staged layer goes out before anything else
-            h0 = lds_u4(plan);
-            if (!primed && (h0.x >> 16)) issue(plan + SVB_UPLAN_HDR_BYTES + SVB_UPLAN_REC_BYTES * (unsigned)(__ffs(h0.x >> 16) - 1), (int)h0.z, stage);
-        }
-        primed = false;
-        if (have_nxt) plan_unit(un, slot ^ 1);  // (every lane is past its reads of that slot: it held the unit before this one)
-        if (!have_cur) {
-            if (!have_nxt) break;
-            have_cur = true, slot ^= 1;
-            continue;
-        }
-        const int nact = (int)(h0.x & 0xffffu), x0 = (int)(h0.y & 0xffffu), y0 = (int)(h0.y >> 16), f = (int)h0.z;
-        const unsigned smask = h0.x >> 16;
-        const SvbFrameDesc* __restrict__ F = frames + f;
-        const int W = F->width, H = F->height, ofmt = F->format, fflags = F->flags;
-        const int xt = x0 + 2 * lane, yt = y0;  // this lane's columns xt, xt+1 x rows yt .. yt+7
-        const bool live = xt < W;               // W and H even are planner preconditions
-
-        // ---- running picture: img_clear_* (Y = 0, chroma = 0.5 -> 128), or the target's bytes when an earlier pass left them ----
-        if (fflags & SVB_FRAME_LOAD_CUR) {
-            const uint8_t* const oY = (const uint8_t*)F->out_plane[0];
-            const uint8_t* const oU = (const uint8_t*)F->out_plane[1];
-            const uint8_t* const oV = (const uint8_t*)F->out_plane[2];
-            const int sYb = F->out_stride[0], sUb = F->out_stride[1], sVb = F->out_stride[2];
-#pragma unroll
-            for (int r = 0; r < SVB_UNIT_H; ++r) {
-                unsigned w0 = 0;
-                if (live && yt + r < H) w0 = *(const unsigned short*)(oY + (size_t)(yt + r) * sYb + xt);
-                sY[r * 32 + lane] = bytes2(opaque(w0 & 0xff), opaque(w0 >> 8));
-            }
-#pragma unroll
-            for (int k = 0; k < SVB_UNIT_H / 2; ++k) {
-                unsigned cu = 128, cv = 128;
-                if (live && yt + 2 * k < H) {
-                    if (ofmt == SVB_NV12) {
-                        const unsigned w0 = *(const unsigned short*)(oU + (size_t)((yt >> 1) + k) * sUb + xt);
-                        cu = w0 & 0xff, cv = w0 >> 8;
-                    } else {
-                        cu = oU[(size_t)((yt >> 1) + k) * sUb + (xt >> 1)], cv = oV[(size_t)((yt >> 1) + k) * sVb + (xt >> 1)];
-                    }
-                }
-                sY[(SVB_UNIT_H + k) * 32 + lane] = bytes2(opaque(cu), opaque(cv));
-            }
-        } else if (!(h0.w & 1u)) {  // (bit 0: the first listed layer overwrites every sample without reading it)
-#pragma unroll
-            for (int r = 0; r < SVB_UNIT_H; ++r) sY[r * 32 + lane] = splat(0.f);
-#pragma unroll
-            for (int k = 0; k < SVB_UNIT_H / 2; ++k) sY[(SVB_UNIT_H + k) * 32 + lane] = splat(128.f);
-        }
-
-#pragma unroll 1
-        for (int i = 0; i < nact; ++i) {
-            const unsigned ra = plan + SVB_UPLAN_HDR_BYTES + SVB_UPLAN_REC_BYTES * (unsigned)i;
-            const uint4 r0 = lds_u4(ra), r1 = lds_u4(ra + 16);
-            const int mode = (int)(r0.x & 0xffu);
-            if (mode >= PLAN_STAGED) {
-                __syncwarp();  // every lane is past its reads of the other stage
-                // refill the other stage: the next staged layer of this unit, else the first one of the next unit
-                const unsigned rest = smask >> (i + 1);
-                if (rest) {
-                    issue(ra + SVB_UPLAN_REC_BYTES * (unsigned)__ffs(rest), f, stage ^ 1);
-                } else if (have_nxt) {
-                    const uint4 g0 = lds_u4(nplan);
-                    const unsigned smn = g0.x >> 16;
-                    if (smn) {
-                        issue(nplan + SVB_UPLAN_HDR_BYTES + SVB_UPLAN_REC_BYTES * (unsigned)(__ffs(smn) - 1), (int)g0.z, stage ^ 1);
-                        primed = true;
-                    }
-                }
-                if (stage == 0) mbar_wait(&bar[0], phase0), phase0 ^= 1;
-                else mbar_wait(&bar[1], phase1), phase1 ^= 1;
-                const unsigned fmt = (r0.x >> 16) & 0xfu, lflags = r0.x >> 20;
-                const unsigned pitchY = r1.y & 0xffffu, pitchC = r1.y >> 16, cstep = fmt == SVB_NV12 ? 2u : 1u;
-                const unsigned bY = stage0 + (unsigned)stage * stage_bytes, bC = bY + (unsigned)box_y_bytes, tab = bY + tab_off;
-                const unsigned vofs = fmt == SVB_NV12 ? 1u : (unsigned)box_c_bytes / 2u;
-                const unsigned colY = bY - (r0.y & 0xffffu) - (r0.y >> 16) * pitchY, colC = bC - (r0.z & 0xffffu) * cstep - (r0.z >> 16) * pitchC;
-                const float alpha = __uint_as_float(r0.w);
-                const unsigned uflags = lds_u1(ra + 56);  // SVB_UREC_HALF / SVB_UREC_MIXED of the unit
-                if (mode == PLAN_STAGED_EDGE || !(lflags & SVB_LAYER_OPACITY_01)) {
-                    const SvbLayerDesc* __restrict__ L = &F->layers[(r0.x >> 8) & 0xffu];
-                    const float4 fc = ldrow(L->u.fillColor, 0);
-                    const float3 fl = rgb2yuv(fc.x, fc.y, fc.z);
-                    const float af = mul(alpha, fc.w);
-                    // lean: no sample of the unit lies inside the border rectangle but outside the picture (without a border or letterbox: none ever does)
-                    if ((lflags & SVB_LAYER_OPACITY_01) && !(uflags & SVB_UREC_MIXED)) strip_layer_edge<true>(colY, colC, cstep, vofs, tab, tab + 4u * SVB_UCOL_WORDS, lane, alpha, one, make_float4(fl.x, fl.y, fl.z, 0.f), af, sY);
-                    else strip_layer_edge<false>(colY, colC, cstep, vofs, tab, tab + 4u * SVB_UCOL_WORDS, lane, alpha, one, make_float4(fl.x, fl.y, fl.z, 0.f), af, sY);
-                } else if (lflags & SVB_LAYER_UNIT_OPACITY) {
-                    if (uflags & SVB_UREC_HALF) strip_layer<true, true>(colY, colC, cstep, vofs, tab, tab + 4u * SVB_UCOL_WORDS, lane, alpha, one, state);
-                    else strip_layer<true, false>(colY, colC, cstep, vofs, tab, tab + 4u * SVB_UCOL_WORDS, lane, alpha, one, state);
-                } else {
-                    if (uflags & SVB_UREC_HALF) strip_layer<false, true>(colY, colC, cstep, vofs, tab, tab + 4u * SVB_UCOL_WORDS, lane, alpha, one, state);
-                    else strip_layer<false, false>(colY, colC, cstep, vofs, tab, tab + 4u * SVB_UCOL_WORDS, lane, alpha, one, state);
-                }
-                stage ^= 1;
-            } else {
-                const SvbLayerDesc* __restrict__ L = &F->layers[(r0.x >> 8) & 0xffu];
-                float* const py = reinterpret_cast<float*>(sY + lane);
-                if (mode == PLAN_TABLE_RGBA) strip_rgba_layer(L, tables + r1.z, tables + r1.w, lane, xt, yt, W, H, py, py + SVB_UNIT_W * SVB_UNIT_H);
-                else strip_generic_layer(L, xt, yt, W, H, py, py + SVB_UNIT_W * SVB_UNIT_H);
-            }
-        }
-
-        // ---- the unit's bytes: two luma bytes per lane and row, one (U, V) pair per lane and chroma row -----------------------
-        if (live) {
-            const int sYb = F->out_stride[0], sUb = F->out_stride[1], sVb = F->out_stride[2];
-            const float2 ONE = splat(one);
-            auto pack = [&](float2 v) {  // two integer-valued floats in 0..255 -> two bytes: + 2^23 leaves them in the low mantissa bits
-                const float2 x = add2<true>(v, splat(8388608.f), ONE);
-                return (unsigned short)__byte_perm(__float_as_uint(x.x), __float_as_uint(x.y), 0x0040);
-            };
-            uint8_t* pY = (uint8_t*)F->out_plane[0] + (size_t)yt * sYb + xt;
-            const int nrow = min(SVB_UNIT_H, H - yt);
-#pragma unroll 1
-            for (int r = 0; r < nrow; ++r, pY += sYb) *(unsigned short*)pY = pack(sY[r * 32 + lane]);
-            if (ofmt == SVB_NV12) {
-                uint8_t* pC = (uint8_t*)F->out_plane[1] + (size_t)(yt >> 1) * sUb + xt;
-#pragma unroll 1
-                for (int k = 0; 2 * k < nrow; ++k, pC += sUb) *(unsigned short*)pC = pack(sY[(SVB_UNIT_H + k) * 32 + lane]);
-            } else {
-                uint8_t* pU = (uint8_t*)F->out_plane[1] + (size_t)(yt >> 1) * sUb + (xt >> 1);
-                uint8_t* pV = (uint8_t*)F->out_plane[2] + (size_t)(yt >> 1) * sVb + (xt >> 1);
-#pragma unroll 1
-                for (int k = 0; 2 * k < nrow; ++k, pU += sUb, pV += sVb) {
-                    const unsigned short p = pack(sY[(SVB_UNIT_H + k) * 32 + lane]);
-                    *pU = (uint8_t)(p & 0xff), *pV = (uint8_t)(p >> 8);
-                }
-            }
-        }
-        __syncwarp();  // the plan slot and the state are free
-        if (!have_nxt) break;
-        slot ^= 1;
     }
 }

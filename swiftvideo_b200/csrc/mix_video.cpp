@@ -49,11 +49,11 @@ struct MixerShared {
     std::vector<CUdeviceptr> tmapChunks;
     int tmapChunkAt = -1, tmapUsed = 0;
     bool tmapFence = false;
-    CUfunction fTiled = nullptr, fGather = nullptr, fGeneric = nullptr, fTables = nullptr, fStrip = nullptr, fStripTables = nullptr, fRing = nullptr;
+    CUfunction fTiled = nullptr, fGather = nullptr, fGeneric = nullptr, fTables = nullptr, fStripTables = nullptr, fRing = nullptr;
     int gatherCtasPerSm = 0;
     int texAlign = 512, texPitchAlign = 32;
     std::map<std::array<uint64_t, 3>, CUtexObject> texs;  // texture objects over source planes by (pointer, size, pitch | channels)
-    std::map<size_t, int> stripCtasPerSm, ringCtasPerSm;  // the same for svb_mix_strip / svb_mix_ring
+    std::map<size_t, int> ringCtasPerSm;  // the same for svb_mix_ring
     std::map<size_t, int> tiledCtasPerSm;  // resident CTAs of svb_mix_tiled per SM by dynamic shared memory size: the persistent grid is smCount times this
     std::mutex mu;
     // optional per-launch device timing of the fused kernels (bench.py's roofline leg)
@@ -125,9 +125,6 @@ MixerShared& shared(const std::shared_ptr<InternalContext>& ic) {  // caller hol
             if (s->texPitchAlign <= 0) s->texPitchAlign = 32;
         }
         s->fGeneric = ic->builtin("svb_mix_generic");
-        s->fStrip = ic->builtin("svb_mix_strip");
-        check(drv().cuFuncSetAttribute(s->fStrip, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, SVB_STRIP_SMEM_BYTES(SVB_SBOX_Y_BYTES, SVB_SBOX_C_BYTES, SVB_MAX_LAYERS)),
-              "cuFuncSetAttribute(max dynamic shared memory)");
         s->fStripTables = ic->builtin("svb_strip_tables");
         s->fRing = ic->builtin("svb_mix_ring");
         check(drv().cuFuncSetAttribute(s->fRing, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, 200 * 1024), "cuFuncSetAttribute(max dynamic shared memory)");
@@ -341,26 +338,6 @@ FramePlan planFrame(const ComputeContext& ctx, const PictureSample& target, cons
             }
         }
         if ((flags & SVB_LAYER_SEPARABLE) && (sf == SVB_NV12 || sf == SVB_Y420P) && L.width >= 2 && L.height >= 2) {
-            // svb_mix_strip: boxes that hold the footprint of one 64x8 unit (a warp stages its own)
-            const double sx = std::fabs((double)L.width * X[0] * T[0] * 2.0 / W), sy = std::fabs((double)L.height * X[5] * T[5] * 2.0 / H);
-            const int cw = L.width / 2, ch = L.height / 2;
-            const int bw = roundUp((int)std::ceil(sx * (SVB_UNIT_W - 1)) + 3 + 15, 16), bh = (int)std::ceil(sy * (SVB_UNIT_H - 1)) + 3;
-            const int bcw = sf == SVB_NV12 ? roundUp((int)std::ceil(sx * 0.5 * (SVB_UNIT_W - 2)) + 3 + 7, 8)
-                                           : roundUp((int)std::ceil(sx * 0.5 * (SVB_UNIT_W - 2)) + 3 + 15, 16);
-            const int bch = (int)std::ceil(sy * 0.5 * (SVB_UNIT_H - 2)) + 3;
-            const int cbytes = bcw * bch * (sf == SVB_NV12 ? 2 : 1);
-            const bool fits = std::isfinite(sx) && std::isfinite(sy) && bw <= 256 && bh <= 256 && bw * bh <= SVB_SBOX_Y_BYTES && bcw <= 256 && bch <= 256 &&
-                              cbytes <= (sf == SVB_NV12 ? SVB_SBOX_C_BYTES : SVB_SBOX_C_BYTES / 2);
-            if (!noTma && fits && tensorMap(sh, &L.stmap[0], L.plane[0], 1, L.width, L.height, L.stride[0], bw, bh) &&
-                (sf == SVB_NV12 ? tensorMap(sh, &L.stmap[1], L.plane[1], 2, cw, ch, L.stride[1], bcw, bch)
-                                : (tensorMap(sh, &L.stmap[1], L.plane[1], 1, cw, ch, L.stride[1], bcw, bch) &&
-                                   tensorMap(sh, &L.stmap[2], L.plane[2], 1, cw, ch, L.stride[2], bcw, bch)))) {
-                flags |= SVB_LAYER_STAGED_S;
-                L.sbox_w = bw, L.sbox_h = bh, L.sbox_cw = bcw, L.sbox_ch = bch;
-                L.stx_bytes = bw * bh + (sf == SVB_NV12 ? cbytes : 2 * cbytes) + SVB_STRIP_TAB_BYTES;
-            }
-        }
-        if ((flags & SVB_LAYER_SEPARABLE) && (sf == SVB_NV12 || sf == SVB_Y420P) && L.width >= 2 && L.height >= 2) {
             const int cw = L.width / 2, ch = L.height / 2;
             const CUtexObject t0 = textureObject(sh, L.plane[0], 1, L.width, L.height, L.stride[0]);
             const CUtexObject t1 = sf == SVB_NV12 ? textureObject(sh, L.plane[1], 2, cw, ch, L.stride[1]) : textureObject(sh, L.plane[1], 1, cw, ch, L.stride[1]);
@@ -379,15 +356,14 @@ FramePlan planFrame(const ComputeContext& ctx, const PictureSample& target, cons
 
 namespace {
 
-// SVB_COMPOSITOR=ring|strip|tma|gather picks the fused compositor (default: ring = svb_mix_ring; strip = svb_mix_strip, which falls back to
-// tma = svb_mix_tiled, the round-1 kernel, for batches whose footprints are too large for a warp's own boxes); read once.
-int compositorChoice() {  // 0 strip, 1 tiled, 2 gather, 3 ring
+// SVB_COMPOSITOR=ring|tma|gather picks the fused compositor (default: ring = svb_mix_ring; tma = svb_mix_tiled, the round-1 kernel;
+// gather = svb_mix_gather, taps through the texture unit); read once.
+int compositorChoice() {  // 1 tiled, 2 gather, 3 ring
     static const int v = [] {
         const char* e = std::getenv("SVB_COMPOSITOR");
         if (e && std::strcmp(e, "ring") == 0) return 3;
         if (e && std::strcmp(e, "gather") == 0) return 2;
         if (e && (std::strcmp(e, "tma") == 0 || std::strcmp(e, "tiled") == 0)) return 1;
-        if (e && std::strcmp(e, "strip") == 0) return 0;
         return SVB_DEFAULT_GATHER ? 2 : 3;
     }();
     return v;
@@ -395,7 +371,7 @@ int compositorChoice() {  // 0 strip, 1 tiled, 2 gather, 3 ring
 bool gatherByDefault() { return compositorChoice() == 2; }
 
 // One launch over `frames` (all tiled-capable, or all generic).  Caller holds a CtxGuard.
-void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, bool tiled, bool wantGather, int want) {  // want: 0 default, 1 svb_mix_tiled, 2 svb_mix_strip, 3 svb_mix_ring
+void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, bool tiled, bool wantGather, int want) {  // want: 0 default, 1 svb_mix_tiled, 3 svb_mix_ring
     const CuDriver& d = drv();
     MixerShared& sh = shared(ctx.ctx);
     InternalContext& ic = *ctx.ctx;
@@ -420,15 +396,9 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
             for (int l = 0; l < fr.nlayers; ++l)
                 if ((fr.layers[l].flags & SVB_LAYER_STAGED) && !(fr.layers[l].flags & SVB_LAYER_TEX)) gather = false;
         }
-        // svb_mix_strip (a warp stages its own 64x8 footprint) unless a layer that the tiled kernel can stage does not fit a warp's boxes
-        const int pick = want ? want : (compositorChoice() == 0 ? 2 : compositorChoice() == 3 ? 3 : 1);
+        // which TMA compositor: svb_mix_ring by default (SVB_COMPOSITOR / the mixer's mode can ask for svb_mix_tiled)
+        const int pick = want ? want : (compositorChoice() == 3 ? 3 : 1);
         const bool ring = tiled && !gather && pick == 3;  // same tile boxes as svb_mix_tiled: whatever that kernel stages, this one does
-        bool strip = tiled && !gather && (pick == 2 || ring);  // (`strip` from here on: unit tables, planned in the compositor -- both kernels)
-        for (int i = 0; strip && i < n; ++i) {
-            const SvbFrameDesc& fr = frames[start + i];
-            for (int l = 0; l < fr.nlayers; ++l)
-                if (!ring && (fr.layers[l].flags & SVB_LAYER_STAGED) && !(fr.layers[l].flags & SVB_LAYER_STAGED_S)) strip = false;
-        }
         for (int i = 0; i < n; ++i) {
             SvbFrameDesc& fr = frames[start + i];
             if (gather) fr.flags |= SVB_FRAME_GATHER;
@@ -438,44 +408,32 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
             else fr.flags &= ~SVB_FRAME_RING;
             for (int l = 0; l < fr.nlayers; ++l) {
                 const SvbLayerDesc& L = fr.layers[l];
-                if (strip && !ring) {
-                    if (!(L.flags & SVB_LAYER_STAGED_S)) continue;
-                    boxY = std::max(boxY, roundUp(L.sbox_w * L.sbox_h, 128));
-                    boxC = std::max(boxC, L.format == SVB_NV12 ? roundUp(L.sbox_cw * L.sbox_ch * 2, 128) : 2 * roundUp(L.sbox_cw * L.sbox_ch, 128));
-                    continue;
-                }
                 if (!(L.flags & SVB_LAYER_STAGED)) continue;
                 boxY = std::max(boxY, roundUp(L.box_w * L.box_h, 256));
                 boxC = std::max(boxC, L.format == SVB_NV12 ? roundUp(L.box_cw * L.box_ch * 2, 256) : 2 * roundUp(L.box_cw * L.box_ch, 128));
             }
-            // (a strip batch counts 64x8 units where a tiled batch counts 128x32 tiles: same fields)
-            fr.tiles_x = strip ? SVB_UNITS_X(fr.width) : SVB_TILES_X(fr.width);
-            fr.tiles_y = strip ? SVB_UNITS_Y(fr.height) : SVB_TILES_Y(fr.height);
+            // (a ring batch counts its 64x8 units here -- its tables are unit-blocked -- where a tiled batch counts 128x32 tiles: same fields)
+            fr.tiles_x = ring ? SVB_UNITS_X(fr.width) : SVB_TILES_X(fr.width);
+            fr.tiles_y = ring ? SVB_UNITS_Y(fr.height) : SVB_TILES_Y(fr.height);
             fr.first_tile = total;
             total += ring ? SVB_TILES_X(fr.width) * SVB_TILES_Y(fr.height) : fr.tiles_x * fr.tiles_y;  // (svb_mix_ring claims 128x32 tiles; its tables are unit-blocked all the same)
             maxTiles = std::max(maxTiles, fr.tiles_x * fr.tiles_y);
             maxW = std::max(maxW, fr.width), maxH = std::max(maxH, fr.height);
-            const int ents = strip ? SVB_UTABLE_WORDS(fr.width, fr.height) : SVB_TABLE_WORDS(fr.width, fr.height);  // 4-byte words per layer
+            const int ents = ring ? SVB_UTABLE_WORDS(fr.width, fr.height) : SVB_TABLE_WORDS(fr.width, fr.height);  // 4-byte words per layer
             fr.table_base = (int32_t)tableEnts;
-            if (strip)
-                for (int l = 0; l < fr.nlayers; ++l) {  // what a planning lane of svb_mix_strip reads of its layer
+            if (ring)
+                for (int l = 0; l < fr.nlayers; ++l) {  // what a planning lane of svb_mix_ring reads of its layer
                     SvbLayerDesc& L = fr.layers[l];
                     SvbStripConsts& c = L.pc;
-                    const unsigned long long* tm = ring ? L.tmap : L.stmap;  // tile-sized boxes for svb_mix_ring, unit-sized ones for svb_mix_strip
+                    const unsigned long long* tm = L.tmap;
                     c.stmapY[0] = (uint32_t)tm[0], c.stmapY[1] = (uint32_t)(tm[0] >> 32);
                     c.stmapC[0] = (uint32_t)tm[1], c.stmapC[1] = (uint32_t)(tm[1] >> 32);
                     c.stmapV[0] = (uint32_t)tm[2], c.stmapV[1] = (uint32_t)(tm[2] >> 32);
                     std::memcpy(&c.opacity_bits, &L.u.opacity, 4);
-                    if (ring) {
-                        const int cb = L.box_cw * L.box_ch * (L.format == SVB_NV12 ? 2 : 1);
-                        c.stx_bytes = (L.flags & SVB_LAYER_STAGED) ? (uint32_t)(L.box_w * L.box_h + (L.format == SVB_NV12 ? cb : 2 * cb)) : 0u;  // the table blocks are added per tile
-                        c.pitches = (uint32_t)L.box_w | ((uint32_t)(L.format == SVB_NV12 ? 2 * L.box_cw : L.box_cw) << 16);
-                        c.fmtflags = (uint32_t)L.format | ((uint32_t)(L.flags & 0xff) << 4) | ((uint32_t)L.box_h << 12) | ((uint32_t)L.box_ch << 22);
-                    } else {
-                        c.stx_bytes = (uint32_t)L.stx_bytes;
-                        c.pitches = (uint32_t)L.sbox_w | ((uint32_t)(L.format == SVB_NV12 ? 2 * L.sbox_cw : L.sbox_cw) << 16);
-                        c.fmtflags = (uint32_t)L.format | ((uint32_t)(L.flags & 0xff) << 8);
-                    }
+                    const int cb = L.box_cw * L.box_ch * (L.format == SVB_NV12 ? 2 : 1);
+                    c.stx_bytes = (L.flags & SVB_LAYER_STAGED) ? (uint32_t)(L.box_w * L.box_h + (L.format == SVB_NV12 ? cb : 2 * cb)) : 0u;  // the table blocks are added per tile
+                    c.pitches = (uint32_t)L.box_w | ((uint32_t)(L.format == SVB_NV12 ? 2 * L.box_cw : L.box_cw) << 16);
+                    c.fmtflags = (uint32_t)L.format | ((uint32_t)(L.flags & 0xff) << 4) | ((uint32_t)L.box_h << 12) | ((uint32_t)L.box_ch << 22);
                     c.tab = (uint32_t)(tableEnts + (size_t)l * (size_t)ents);
                     c.rec = c.tab + (uint32_t)(fr.tiles_x * SVB_UCOL_WORDS + fr.tiles_y * SVB_UROW_WORDS);
                     std::memcpy(c.rect, L.rect, sizeof(c.rect));
@@ -504,7 +462,7 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
             // tile; then the compositor (+ the tile counter it claims its work from, zeroed by the pre-pass)
             const size_t counterOff = (std::max<size_t>(tableEnts, 4) * 4 + 15) & ~(size_t)15;
             const size_t plansOff = counterOff + 16;
-            const size_t tableBytes = plansOff + (strip ? 0 : (size_t)total * sizeof(SvbTilePlan));  // (a strip batch has no plans in global memory: warps plan their own units)
+            const size_t tableBytes = plansOff + (ring ? 0 : (size_t)total * sizeof(SvbTilePlan));  // (a ring batch has no plans in global memory: its producer warps plan their own tiles)
             if (sh.tabBytes[seg] < tableBytes) {
                 // cuMemAlloc / cuMemFree synchronise the device: when one segment's buffer must grow, grow them all, once, instead of
                 // stalling the next kSegments - 1 launches as well (a mixer's first ticks are often lighter than its steady state)
@@ -520,7 +478,7 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
             }
             CUdeviceptr tables = sh.tabBuf[seg];
             CUdeviceptr counter = tables + counterOff, plans = tables + plansOff;
-            if (strip) {
+            if (ring) {
                 // one pre-pass launch: a block per unit column and per unit row of every layer fills its table block and its plan record
                 int blocks = 1;
                 for (int i = 0; i < n; ++i) blocks = std::max(blocks, frames[start + i].tiles_x + frames[start + i].tiles_y);
@@ -555,24 +513,6 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
                 }
                 const unsigned grid = (unsigned)std::min(total, ic.smCount * perSm);
                 check(d.cuLaunchKernel(sh.fRing, grid, 1, 1, SVB_RING_THREADS, 1, 1, (unsigned)smem, ic.compute, args, nullptr), "cuLaunchKernel(svb_mix_ring)");
-                noteKernelLaunch();
-            } else if (strip) {
-                int nf = n, slotBytes = SVB_UPLAN_SLOT_BYTES(maxLayers);
-                void* args[] = {&dev, &tables, &nf, &total, &one, &counter, &boxY, &boxC, &slotBytes};
-                size_t smem = SVB_STRIP_SMEM_BYTES((size_t)boxY, (size_t)boxC, maxLayers);
-                int perSm;
-                {
-                    std::lock_guard<std::mutex> g(sh.mu);
-                    auto it = sh.stripCtasPerSm.find(smem);
-                    if (it == sh.stripCtasPerSm.end()) {
-                        int nb = 0;
-                        check(d.cuOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sh.fStrip, SVB_STRIP_THREADS, smem), "cuOccupancyMaxActiveBlocksPerMultiprocessor");
-                        it = sh.stripCtasPerSm.emplace(smem, std::max(1, nb)).first;
-                    }
-                    perSm = it->second;
-                }
-                const unsigned grid = (unsigned)std::min((total + SVB_STRIP_WARPS - 1) / SVB_STRIP_WARPS, ic.smCount * perSm);
-                check(d.cuLaunchKernel(sh.fStrip, grid, 1, 1, SVB_STRIP_THREADS, 1, 1, (unsigned)smem, ic.compute, args, nullptr), "cuLaunchKernel(svb_mix_strip)");
                 noteKernelLaunch();
             } else if (gather) {
                 int units = total * SVB_GATHER_STRIPS;  // (tile, strip) pairs, claimed by warps
@@ -766,7 +706,7 @@ ComputeContext VideoMixer::composeRaw(const ComputeContext& ctxIn, const Picture
     jobs[0].target = &target;
     jobs[0].layers = layers;
     jobs[0].uniforms.assign(uniforms, uniforms + layers.size());
-    composeFused(ctxIn, jobs, mode == Mode::generic, mode == Mode::fusedGather, mode == Mode::fusedTiled ? 1 : mode == Mode::fusedStrip ? 2 : mode == Mode::fusedRing ? 3 : 0);
+    composeFused(ctxIn, jobs, mode == Mode::generic, mode == Mode::fusedGather, mode == Mode::fusedTiled ? 1 : mode == Mode::fusedRing ? 3 : 0);
     return ctxIn;
 }
 
@@ -818,7 +758,6 @@ void VideoMixer::mixMany(VideoMixer* const* mixers, int n, int64_t time, Picture
             generic = generic || mixers[i]->mode == Mode::generic;
             wantGather = wantGather || mixers[i]->mode == Mode::fusedGather;
             if (mixers[i]->mode == Mode::fusedTiled) want = 1;
-            if (mixers[i]->mode == Mode::fusedStrip) want = 2;
             if (mixers[i]->mode == Mode::fusedRing) want = 3;
         }
         composeFused(ctx0, jobs, generic, wantGather, want);

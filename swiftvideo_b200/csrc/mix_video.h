@@ -23,13 +23,12 @@ namespace svb {
 class VideoMixer {
   public:
     enum class Mode : int {
-        fused = 0,     // tiled kernel where its preconditions hold, else the generic fused kernel
+        fused = 0,     // svb_mix_ring where the tile preconditions hold, else the generic fused kernel
         perLayer = 1,  // the reference's own sequence: clear kernel + one applyComputeImage per layer
         generic = 2,   // the generic fused kernel only
         fusedGather = 3,  // fused, with svb_mix_gather (taps through the texture unit) wherever every staged layer can be bound as a texture
         fusedTiled = 4,   // fused, with svb_mix_tiled (the CTA-per-tile TMA compositor of round 1)
-        fusedStrip = 5,   // fused, with svb_mix_strip (a warp stages and composites its own 64x8 unit)
-        fusedRing = 6     // fused, with svb_mix_ring (tiles planned and staged per CTA, eight free-running warps, three-stage ring)
+        fusedRing = 5     // fused, with svb_mix_ring (tiles planned and staged per CTA, eight free-running warps, three-stage ring)
     };
 
     VideoMixer(const ComputeContext* computeContext, Vector2 outputSize, PixelFormat outputFormat = PixelFormat::nv12,

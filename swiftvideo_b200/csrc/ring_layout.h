@@ -14,7 +14,9 @@
 #define SVB_RPLAN_REC_BYTES 80
 #define SVB_RREC_TOUCH 0x80u  // the layer's rectangle reaches into this unit column / unit row
 #define SVB_RPLAN_SLOT_BYTES(layers) ((SVB_RPLAN_HDR_BYTES + SVB_RPLAN_REC_BYTES * (layers) + 127) / 128 * 128)
+#ifndef SVB_RING_STAGES
 #define SVB_RING_STAGES 3
+#endif
 #define SVB_RING_WARPS 8
 #define SVB_RING_THREADS (32 * (SVB_RING_WARPS + 1))  // eight consumer warps and the producer warp
 #define SVB_RING_PLANS 3

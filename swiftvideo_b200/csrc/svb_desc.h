@@ -32,7 +32,7 @@ enum {
     SVB_FRAME_LOAD_CUR = 1,   // continue an earlier pass: start from the target's bytes, not from clear
     SVB_FRAME_SCALAR_FP = 2,  // tuning aid: spell the packed fp32x2 arithmetic as scalar instructions (same results)
     SVB_FRAME_GATHER = 4,     // the batch goes to svb_mix_gather: plan separable YUV layers for the texture path (no staging limits)
-    SVB_FRAME_RING = 16,      // the batch goes to svb_mix_ring: the unit tables carry the pitch of the TILE-sized staged boxes
+    SVB_FRAME_RING = 16,      // the batch goes to svb_mix_ring (unit-blocked tables, tiles planned in the compositor)
     SVB_FRAME_TMAP_FENCE = 8  // tensor-map slots of the context's table have been rewritten: acquire the frame's maps before the first copy
 };
 enum {
@@ -40,8 +40,7 @@ enum {
     SVB_LAYER_UNIT_OPACITY = 2,  // opacity == 1: cur*(1-1) + v*1 == v exactly, the blend is skipped
     SVB_LAYER_STAGED = 4,        // tensor maps below are valid: source footprints are staged by TMA
     SVB_LAYER_OPACITY_01 = 8,    // 0 <= opacity <= 1: blended values cannot leave [0,1], store clamps are no-ops
-    SVB_LAYER_TEX = 16,          // tex[] below holds texture objects over the source planes (svb_mix_gather)
-    SVB_LAYER_STAGED_S = 32      // stmap[] / sbox_* below are valid: svb_mix_strip stages a warp's own footprint by TMA
+    SVB_LAYER_TEX = 16           // tex[] below holds texture objects over the source planes (svb_mix_gather)
 };
 
 // ImageUniforms as uploaded by applyComputeImage (reference compute.swift:76-86; device mirror
@@ -59,11 +58,11 @@ typedef struct __attribute__((aligned(16))) SvbUniforms {
     float pad_;
 } SvbUniforms;
 
-// What a warp of svb_mix_strip needs of a layer to plan and stage a unit, gathered in 64 bytes (four 16-byte loads by the planning lane)
+// What the producer warp of svb_mix_ring needs of a layer to plan and stage a tile, gathered in 64 bytes (four 16-byte loads by the planning lane)
 typedef struct __attribute__((aligned(16))) SvbStripConsts {
-    uint32_t stmapY[2], stmapC[2];                 // device addresses of the unit-sized tensor maps (luma, chroma / U)
-    uint32_t stmapV[2], stx_bytes, pitches;        // (V plane of a planar source); bytes a stage receives; box pitch luma | chroma << 16, in bytes
-    uint32_t opacity_bits, fmtflags, tab, rec;     // format | SVB_LAYER_* << 8; word offsets into the batch's table buffer: the layer's tables, its column records (row records follow)
+    uint32_t stmapY[2], stmapC[2];                 // device addresses of the tensor maps (luma, chroma / U)
+    uint32_t stmapV[2], stx_bytes, pitches;        // (V plane of a planar source); bytes of the staged boxes; box pitch luma | chroma << 16, in bytes
+    uint32_t opacity_bits, fmtflags, tab, rec;     // format | SVB_LAYER_* << 4 | box_h << 12 | box_ch << 22; word offsets into the batch's table buffer: the layer's tables, its column records (row records follow)
     int32_t rect[4];                               // = SvbLayerDesc::rect
 } SvbStripConsts;
 
@@ -83,13 +82,8 @@ typedef struct __attribute__((aligned(64))) SvbLayerDesc {
     int32_t box_cw, box_ch;
     int32_t pad0_;
     unsigned long long tex[3];   // CUtexObject per source plane (valid when SVB_LAYER_TEX): UNORM8, clamp, unnormalised coordinates
-    // svb_mix_strip (valid when SVB_LAYER_STAGED_S): tensor maps whose boxes cover the footprint of ONE 64x8 unit, the box
-    // sizes in elements (chroma: texels), and the bytes one stage receives (luma box + chroma box(es) + the table blocks)
-    unsigned long long stmap[3];
-    int32_t sbox_w, sbox_h, sbox_cw, sbox_ch;
-    int32_t stx_bytes;
-    int32_t pad_[5];
-    SvbStripConsts pc;           // filled by the host at launch (mix_video.cpp: launchFrames)
+    int32_t pad_[16];
+    SvbStripConsts pc;           // svb_mix_ring: filled by the host at launch (mix_video.cpp: launchFrames)
 } SvbLayerDesc;
 
 typedef struct __attribute__((aligned(64))) SvbFrameDesc {
@@ -119,7 +113,7 @@ typedef struct __attribute__((aligned(64))) SvbFrameDesc {
 #define SVB_TILES_Y(H) (((H) + SVB_TILE_H - 1) / SVB_TILE_H)
 #define SVB_TABLE_WORDS(W, H) (SVB_TILES_X(W) * SVB_TAB_COL_WORDS + SVB_TILES_Y(H) * SVB_TAB_ROW_WORDS)
 
-// ---- svb_mix_strip: a warp owns a 64x8 unit (a lane: two adjacent luma columns x 8 rows and the chroma texel column under
+// ---- svb_mix_ring: a warp owns a 64x8 unit (a lane: two adjacent luma columns x 8 rows and the chroma texel column under
 // them).  Tables of one layer (svb_strip_tables), blocked by unit so that a unit's slices arrive in the warp's shared memory by
 // two bulk copies:
 //   column block (one per unit column, 192 words): aY[64] pY[64] aC[32] pC[32]   (a = weight of the i1 tap, p as above)
@@ -145,28 +139,7 @@ enum {
     SVB_UREC_HALF = 8,   // every weight of the block is exactly 1/2: the four bilinear weights are 1/4 each
     SVB_UREC_MIXED = 16  // the block holds an entry inside the border rectangle but outside the picture (a fill sample)
 };
-// Plan of one unit, built by its warp in shared memory: a 16-byte header and 64 bytes per layer that touches the unit, bottom to top.
-//   header  (n | staged mask << 16, x0 | y0 << 16, frame, bit0: the first listed layer overwrites every sample without reading it)
-//   layer   [0] = (mode | layer << 8 | format << 16 | layer flags << 20, ix0 | jy0 << 16, ic0 | jc0 << 16, opacity bits)
-//           [1] = (bytes a stage receives, pitchY | pitchC << 16, column block, row block)   -- blocks as word offsets into the table buffer
-//           [2] = (&tensor map Y, &tensor map C)   [3] = (&tensor map V, SVB_UREC_* of the unit: HALF and MIXED, 0)
-//           ix0, jy0 / ic0, jc0 = origin of the staged luma / chroma box in the source planes
-#define SVB_UPLAN_HDR_BYTES 16
-#define SVB_UPLAN_REC_BYTES 64
-#define SVB_UPLAN_SLOT_BYTES(layers) ((SVB_UPLAN_HDR_BYTES + SVB_UPLAN_REC_BYTES * (layers) + 127) / 128 * 128)
-#define SVB_STRIP_WARPS 4
-#define SVB_STRIP_THREADS (32 * SVB_STRIP_WARPS)
-#define SVB_STRIP_STATE_BYTES (SVB_UNIT_W * SVB_UNIT_H * 4 + (SVB_UNIT_W / 2) * (SVB_UNIT_H / 2) * 8)  // the unit's running picture as floats: 12 rows x 32 lanes x 8 bytes
-#define SVB_STRIP_TAB_BYTES ((SVB_UCOL_WORDS + SVB_UROW_WORDS) * 4)                                      // a stage's table blocks
-#ifndef SVB_SBOX_Y_BYTES
-#define SVB_SBOX_Y_BYTES 6144  // largest luma / chroma footprint of a unit that is staged (about 3 : 1 downscale); larger ones go to the per-pixel path
-#endif
-#ifndef SVB_SBOX_C_BYTES
-#define SVB_SBOX_C_BYTES 4096
-#endif
-#define SVB_STRIP_HDR_BYTES 128  // mbarriers: per warp two stages
-#define SVB_STRIP_WARP_BYTES(boxY, boxC, layers) (SVB_STRIP_STATE_BYTES + 2 * SVB_UPLAN_SLOT_BYTES(layers) + 2 * ((boxY) + (boxC) + SVB_STRIP_TAB_BYTES))
-#define SVB_STRIP_SMEM_BYTES(boxY, boxC, layers) (SVB_STRIP_HDR_BYTES + SVB_STRIP_WARPS * SVB_STRIP_WARP_BYTES(boxY, boxC, layers))
+#define SVB_STRIP_STATE_BYTES (SVB_UNIT_W * SVB_UNIT_H * 4 + (SVB_UNIT_W / 2) * (SVB_UNIT_H / 2) * 8)  // a unit's running picture as floats: 12 rows x 32 lanes x 8 bytes
 
 // Plan of one tile, written by svb_mix_plan and fetched by the compositor's CTAs with one bulk copy.  Five 16-byte words
 // per entry; entry 0 is the header, entries 1..n the layers that touch the tile, bottom to top (kernels_tiled.cuh):

@@ -41,7 +41,7 @@ def test_module_image_has_the_reference_entry_points():
     img = sv.kernel_module_image()
     assert img[:4] == b"\x7fELF"
     for n in ("img_clear_nv12", "img_clear_y420p", "img_clear_bgra", "img_nv12_nv12", "img_y420p_nv12", "img_y420p_y420p",
-              "img_bgra_nv12", "img_rgba_nv12", "img_bgra_y420p", "img_rgba_y420p", "svb_mix_tiled", "svb_mix_tables", "svb_mix_strip", "svb_strip_tables", "svb_mix_generic",
+              "img_bgra_nv12", "img_rgba_nv12", "img_bgra_y420p", "img_rgba_y420p", "svb_mix_tiled", "svb_mix_tables", "svb_mix_ring", "svb_strip_tables", "svb_mix_generic",
               "svb_scale_convert"):
         assert n.encode() in img
     # upstream has no img_bgra_bgra on Linux (compute.swift:54 names it, only a half-written Metal body exists): neither have we

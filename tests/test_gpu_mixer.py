@@ -32,7 +32,7 @@ def _oracle_mix(target_fmt, canvas, placed, images):
     return want.data
 
 
-@pytest.mark.parametrize("mode", [sv.MixMode.FUSED, sv.MixMode.FUSED_RING, sv.MixMode.FUSED_STRIP, sv.MixMode.FUSED_TILED, sv.MixMode.PER_LAYER, sv.MixMode.GENERIC])
+@pytest.mark.parametrize("mode", [sv.MixMode.FUSED, sv.MixMode.FUSED_RING, sv.MixMode.FUSED_TILED, sv.MixMode.PER_LAYER, sv.MixMode.GENERIC])
 def test_mixer_z_order_and_generations(mode):
     ctx = context()
     canvas = (256, 128)

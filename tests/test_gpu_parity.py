@@ -14,7 +14,7 @@ from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
 
-MODES = [(sv.MixMode.FUSED, "fused"), (sv.MixMode.FUSED_RING, "fused_ring"), (sv.MixMode.FUSED_STRIP, "fused_strip"), (sv.MixMode.FUSED_TILED, "fused_tiled"),
+MODES = [(sv.MixMode.FUSED, "fused"), (sv.MixMode.FUSED_RING, "fused_ring"), (sv.MixMode.FUSED_TILED, "fused_tiled"),
          (sv.MixMode.GENERIC, "generic"), (sv.MixMode.PER_LAYER, "per_layer")]
 CHECKER = O.best()[0]
 # the fused compositor with its taps through the texture unit (svb_mix_gather): same plans, tables and bytes
@@ -133,7 +133,7 @@ def test_cfg4_variants_full_size():
     case = scenes.Case("cfg4_y420p", O.Y420P, canvas, layers, us)
     rc, want = scenes.run_case(CHECKER, case, threads=O.host_threads())
     assert rc == 0
-    for mode, mname in ((sv.MixMode.FUSED, "fused"), (sv.MixMode.FUSED_RING, "fused_ring"), (sv.MixMode.FUSED_STRIP, "fused_strip"), (sv.MixMode.FUSED_TILED, "fused_tiled"),
+    for mode, mname in ((sv.MixMode.FUSED, "fused"), (sv.MixMode.FUSED_RING, "fused_ring"), (sv.MixMode.FUSED_TILED, "fused_tiled"),
                         (sv.MixMode.FUSED_GATHER, "fused_gather")):
         got = gpu_case(ctx, case, mode)
         assert (got == want.data).all(), f"cfg4_y420p/{mname}: {first_diff(got, want.data)}"
@@ -207,7 +207,7 @@ def test_padded_target():
     rc, want = scenes.run_case(CHECKER, base, threads=O.host_threads())
     assert rc == 0
     W, H = base.canvas
-    for mode, mname in MODES[:5]:
+    for mode, mname in MODES[:4]:
         got = gpu_case(context(), base, mode, target_strides=[W + 64, W + 64])
         tight = np.concatenate([got[: (W + 64) * H].reshape(H, W + 64)[:, :W].reshape(-1),
                                 got[(W + 64) * H :].reshape(H // 2, W + 64)[:, :W].reshape(-1)])

@@ -53,7 +53,7 @@ def test_random_scene(seed):
     case = random_case(seed)
     rc, want = scenes.run_case(O.best()[0], case)  # the reference's kernel text where that build is present
     assert rc == 0
-    for mode, name in ((sv.MixMode.FUSED, "fused"), (sv.MixMode.FUSED_RING, "fused_ring"), (sv.MixMode.FUSED_STRIP, "fused_strip"), (sv.MixMode.FUSED_TILED, "fused_tiled"),
+    for mode, name in ((sv.MixMode.FUSED, "fused"), (sv.MixMode.FUSED_RING, "fused_ring"), (sv.MixMode.FUSED_TILED, "fused_tiled"),
                        (sv.MixMode.GENERIC, "generic")):
         got = gpu_case(context(), case, mode)
         assert (got == want.data).all(), f"seed {seed}/{name}: {first_diff(got, want.data)}"
