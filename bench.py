@@ -160,7 +160,16 @@ def bind_to_gpu_numa(index):
         if node >= 0 and cpus:
             os.sched_setaffinity(0, cpus)
             return f"numa node {node} ({len(cpus)} cpus)"
-        return f"numa node {node} (not bound)"
+        # no NUMA information (these VMs report numa_node -1): give every rank of the node its own even share of the allowed cores, so
+        # that eight ranks do not pile their copy-issuing threads onto the same few
+        world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", 1)))
+        allowed = sorted(os.sched_getaffinity(0))
+        if world > 1 and len(allowed) >= world:
+            per = len(allowed) // world
+            mine = set(allowed[index * per:(index + 1) * per])
+            os.sched_setaffinity(0, mine)
+            return f"numa node {node}: even split, cores {min(mine)}-{max(mine)} of {len(allowed)}"
+        return f"numa node {node} (not bound: single rank)"
     except Exception as e:
         return f"unbound ({type(e).__name__})"
 
@@ -184,6 +193,32 @@ def measure_link(torch, device, nbytes=256 << 20, reps=5):
             best = min(best, a.elapsed_time(b))
         out[name] = round(nbytes / (best / 1e3) / 1e9, 1)
     return out
+
+
+def measure_link_duplex(torch, device, in_bytes, out_bytes, barrier, reps=6):
+    """What the e2e leg can reach at most on this box: every rank copies one step's input bytes host -> device and one step's output
+    bytes device -> host AT THE SAME TIME (two streams, pinned memory), all ranks together (`barrier` lines them up).  Returns this
+    rank's seconds per step-equivalent (best of reps); the caller takes the max over ranks."""
+    hi = torch.empty(in_bytes, dtype=torch.uint8).pin_memory()
+    di = torch.empty(in_bytes, dtype=torch.uint8, device=device)
+    ho = torch.empty(out_bytes, dtype=torch.uint8).pin_memory()
+    do = torch.empty(out_bytes, dtype=torch.uint8, device=device)
+    s1, s2 = torch.cuda.Stream(device), torch.cuda.Stream(device)
+    best = 1e30
+    for _ in range(reps):
+        barrier()
+        a, b, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        s1.wait_event(a), s2.wait_event(a)
+        with torch.cuda.stream(s1):
+            di.copy_(hi, non_blocking=True)
+            b.record()
+        with torch.cuda.stream(s2):
+            ho.copy_(do, non_blocking=True)
+            c.record()
+        b.synchronize(), c.synchronize()
+        best = min(best, max(a.elapsed_time(b), a.elapsed_time(c)) / 1e3)
+    return best
 
 
 def run_ours(args):
@@ -235,14 +270,15 @@ def run_ours(args):
             mixers[s].push_many(dev[i & 1][s])
         return sv.VideoMixer.mix_many(mixers, i, wait=False)
 
-    def step_e2e(i):
-        ups = []
+    def step_e2e(i):  # host buffers in, host buffers out: ONE call across the boundary (upload, push, mix, download of all S mixers)
+        return sv.VideoMixer.tick_many(mixers, host, i, wait=False)
+
+    def step_per_mixer(i):  # the reference's own call pattern: one VideoMixer.mix(at:) per mixer (mix.video.swift:95-99) = one frame per launch
+        outs = []
         for s in range(S):
-            up = [host[s][k].upload(ctx, retain_cpu_buffer=False) for k in range(NLAYERS)]
-            mixers[s].push_many(up)
-            ups.append(up)
-        outs = sv.VideoMixer.mix_many(mixers, i, wait=False)
-        return [o.download(ctx, retain_gpu_buffer=True, wait=False) for o in outs]
+            mixers[s].push_many(dev[i & 1][s])
+            outs.append(mixers[s].mix(i, wait=False))
+        return outs
 
     def barrier():
         torch.cuda.synchronize()
@@ -251,8 +287,9 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def timed(fn, steps, warmup):
+        last = None
         for i in range(warmup):
-            fn(i)
+            last = fn(i)  # (kept until the next step returns, exactly like the timed steps: the buffer pools then reach their steady state here)
         ctx.synchronize()
         barrier()
         timer = sv.Timer(ctx)
@@ -281,19 +318,35 @@ def run_ours(args):
     ctx.launch_timing(True)
     ms, launches, host_ms = timed(step_resident, args.steps, args.warmup)
     kern_ms, kern_n = ctx.launch_timing_read()
+    host_c_ms, host_c_calls = ctx.host_timing_read()
     ctx.launch_timing(False)
     frames = S * world * args.steps
     value = frames / (ms / 1e3)
 
+    # ---- the same, one frame per launch (S launches per step): the reference's call pattern
+    ctx.launch_timing(True)
+    pm_ms, _, pm_host_ms = timed(step_per_mixer, args.steps, args.warmup)
+    pm_kern_ms, pm_kern_n = ctx.launch_timing_read()
+    ctx.launch_timing(False)
+
     # ---- e2e: host buffers in, host buffers out
     e2e_steps = max(3, min(args.steps, args.e2e_steps))
-    e_ms, _, e_host_ms = timed(step_e2e, e2e_steps, max(3, min(args.warmup, 3)))
+    if os.environ.get("SVB_DEBUG_POOL"):
+        print("[bench] e2e leg starts", file=sys.stderr, flush=True)
+    e_ms, _, e_host_ms = timed(step_e2e, e2e_steps, max(4, min(args.warmup, 6)))
+    if os.environ.get("SVB_DEBUG_POOL"):
+        print("[bench] e2e leg ends", file=sys.stderr, flush=True)
     clocks = sampler.stop()
     e2e_value = S * world * e2e_steps / (e_ms / 1e3)
     h2d = S * sum(ssz[0] * ssz[1] * 3 // 2 for ssz, _, _, _ in geo)
     d2h = S * CANVAS[0] * CANVAS[1] * 3 // 2
 
     link = measure_link(torch, torch.device("cuda", local))
+    # the ceiling of the e2e leg, measured: every rank moves one step's bytes in and out at once, all ranks together
+    duplex_s = measure_link_duplex(torch, torch.device("cuda", local), h2d, d2h, barrier)
+    duplex_s = max_over_ranks(duplex_s * 1e3, world, dist, "cuda") / 1e3
+    link["duplex_all_ranks"] = {"frames_per_s": round(S * world / duplex_s, 1), "h2d_gbs_per_gpu": round(h2d / duplex_s / 1e9, 1), "d2h_gbs_per_gpu": round(d2h / duplex_s / 1e9, 1),
+                                "what": "one step's input bytes host->device and output bytes device->host at the same time on two streams, every rank at once (best of 6)"}
     # both directions run at once (separate copy engines); indicative only -- the H2D rate of one big copy varies run to run (39-53 GB/s seen)
     link["frames_per_s_at_this_copy_rate"] = round(S * world / max(h2d / (link["h2d_gbs"] * 1e9), d2h / (link["d2h_gbs"] * 1e9)), 1)
 
@@ -315,7 +368,9 @@ def run_ours(args):
 
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(ms / args.steps, 4), "host_queue_ms_per_step": round(host_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": round(ms / args.steps, 4), "host_queue_ms_per_step": round(host_ms / args.steps, 4),
+        "host_queue_in_library_ms_per_step": round(host_c_ms / max(1, host_c_calls), 4),  # the C++ side alone (plan + driver calls), without the Python binding
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8 (fp32 arithmetic, no FMA contraction)", "data": "synthetic (uniform u8 planes, seeded)",
         "config": {"workload": (WORKLOAD if args.pip_opacity is None else WORKLOAD + f" -- NOT the headline: picture-in-picture opacity forced to {args.pip_opacity}") +
                                (f" -- NOT the headline: the top {args.rgba_pips} pictures-in-picture are RGBA overlays" if args.rgba_pips else "") +
@@ -326,7 +381,12 @@ def run_ours(args):
                           f"({2 * ALG_BYTES_PER_FRAME * S / 1e6:.0f} MB over two steps)"),
                    "bit_exact_vs_oracle": "tests/test_gpu_parity.py::test_cfg2_full_size" if CANVAS == (1280, 720) else "tests/test_gpu_parity.py::test_cfg34_full_size"},
         "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                "ms_per_step": round(e_ms / e2e_steps, 4), "host_queue_ms_per_step": round(e_host_ms / e2e_steps, 4), "host_link": link},
+                "ms_per_step": round(e_ms / e2e_steps, 4), "host_queue_ms_per_step": round(e_host_ms / e2e_steps, 4), "calls_per_step": 1,
+                "frac_of_link_ceiling": round(e2e_value / link["duplex_all_ranks"]["frames_per_s"], 3), "host_link": link},
+        # the reference's own call pattern, for comparison with the headline: one VideoMixer.mix(at:) per mixer = one 4K frame per launch
+        "one_frame_per_launch": {"value": round(frames / (pm_ms / 1e3), 2), "unit": "frames/s", "ms_per_step": round(pm_ms / args.steps, 4),
+                                 "launches_per_step": S, "kernel_ms_per_launch": round(pm_kern_ms / max(1, pm_kern_n), 4),
+                                 "host_queue_ms_per_step": round(pm_host_ms / args.steps, 4)},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
         "hbm_gbs_per_gpu_algorithmic": round(ALG_BYTES_PER_FRAME * value / world / 1e9, 1),
     }
@@ -384,7 +444,7 @@ def run_scale(args):
         return [devs[k].scale_convert(ctx, dw, dh, sv.BGRA, filt, wait=False) for k in range(N)]
 
     def step_e2e(i):
-        outs = [hosts[k].upload(ctx, retain_cpu_buffer=False).scale_convert(ctx, dw, dh, sv.BGRA, filt, wait=False) for k in range(N)]
+        outs = [hosts[k].upload(ctx, retain_cpu_buffer=False, wait=False).scale_convert(ctx, dw, dh, sv.BGRA, filt, wait=False) for k in range(N)]
         return [o.download(ctx, retain_gpu_buffer=True, wait=False) for o in outs]
 
     def timed(fn, steps, warmup):

@@ -157,12 +157,30 @@ svb_status svb_picture_with(const svb_picture* other, const float* matrix, const
                             const float* fill_color, const float* opacity, const char* revision, const char* asset_id,
                             svb_picture** out);
 svb_status svb_picture_info_get(const svb_picture* pict, svb_picture_info* out);
+unsigned long long svb_picture_identity(const svb_picture* pict); /* equal for two handles of the same (immutable) sample; 0 for NULL */
 svb_status svb_picture_wait(const svb_picture* pict);          /* block until an asynchronously produced sample is complete */
 void svb_picture_release(svb_picture* pict);
-/* uploadComputePicture / downloadComputePicture compute.cuda.swift:359-402.  wait=1 is upstream's
- * endComputePass(ctx, true); wait=0 returns at once (call svb_picture_wait before touching host bytes). */
-svb_status svb_upload_compute_picture(svb_context* ctx, const svb_picture* pict, int max_planes, int retain_cpu_buffer, svb_picture** out);
+/* uploadComputePicture / downloadComputePicture compute.cuda.swift:359-402.  wait=1 is upstream's behaviour (synchronous copies,
+ * endComputePass(ctx, true)).  wait=0 returns at once with the copies queued:
+ *   upload:   the SOURCE sample's host bytes -- above all a page-locked staging buffer that a decoder refills -- must stay untouched
+ *             until svb_picture_wait(result) returns (consumers on the GPU side are ordered behind the copy by the library itself);
+ *   download: call svb_picture_wait(result) before touching the result's host bytes.  The result always owns fresh host buffers: a
+ *             download never changes the bytes of the sample that was uploaded, as upstream's value-type Data guarantees.
+ * A mixer may recycle the GPU sample that is being downloaded (its backing ring comes round every ten ticks): the next compose into
+ * those planes waits for the copy on the device, so asynchronous consumers need no frame-period bookkeeping. */
+svb_status svb_upload_compute_picture(svb_context* ctx, const svb_picture* pict, int max_planes, int retain_cpu_buffer, int wait, svb_picture** out);
 svb_status svb_download_compute_picture(svb_context* ctx, const svb_picture* pict, int retain_gpu_buffer, int wait, svb_picture** out);
+/* GPUBarrierUpload / GPUBarrierDownload compute.swift:175-198, :232-255: the pipeline stages around the two calls above.  A sample that
+ * already lives on the right side passes through (*out is another handle of the SAME sample); a failure returns the status and fills
+ * *err (may be NULL) with the event error upstream emits: EventError("barrier.upload" | "barrier.download", -1, "<error>", assetId:). */
+typedef struct svb_event_error {
+    char domain[32];
+    int code;
+    char description[256];
+    char asset_id[128];
+} svb_event_error;
+svb_status svb_gpu_barrier_upload(svb_context* ctx, const svb_picture* pict, int retain_cpu_buffer, int wait, svb_picture** out, svb_event_error* err);
+svb_status svb_gpu_barrier_download(svb_context* ctx, const svb_picture* pict, int retain_gpu_buffer, int wait, svb_picture** out, svb_event_error* err);
 
 /* ---- convert + scale (an extension: no upstream counterpart) ------------------------------------------------ */
 /* The reference has no resize filter beyond the OpenCL linear sampler (kernels.cl.swift:61), no high-bit-depth format
@@ -209,6 +227,14 @@ svb_status svb_video_mixer_push_many(svb_mixer* mixer, const svb_picture* const*
 svb_status svb_video_mixer_mix(svb_mixer* mixer, int64_t time, int wait, svb_picture** out);
 /* several mixers of one context folded into one launch */
 svb_status svb_video_mixer_mix_many(svb_mixer* const* mixers, int count, int64_t time, int wait, svb_picture** outs);
+/* One tick of `count` mixers of one context, host buffers in and host buffers out, in ONE call (ours): every CPU sample of `layers`
+ * (layer_counts[i] of them for mixer i, in order; they carry their placement like any pushed sample) goes through GPUBarrierUpload,
+ * is pushed, the mixers are mixed in one launch, and each emitted frame goes through GPUBarrierDownload.  Nothing is waited for
+ * unless wait != 0: outs[i] are CPU samples whose bytes are valid after svb_picture_wait(outs[i]), and the layers' host bytes must
+ * stay untouched until then.  GPU samples among `layers` are pushed as they are.  (Per step of 8 mixers x 8 layers this replaces
+ * 81 calls across the boundary by one.) */
+svb_status svb_video_mixer_tick_many(svb_mixer* const* mixers, int count, const svb_picture* const* layers, const int* layer_counts, int64_t time,
+                                     int wait, svb_picture** outs);
 /* clear + fold with explicit uniforms (layers already in z-order) */
 svb_status svb_compose(svb_context* ctx, const svb_picture* target, const svb_picture* const* layers, const svb_image_uniforms* uniforms,
                        int count, int mode);
@@ -223,6 +249,8 @@ void svb_timer_destroy(svb_timer* t);
  * since timing was (re-)enabled.  Reading waits for the launches queued so far. */
 svb_status svb_launch_timing(svb_context* ctx, int enable);
 svb_status svb_launch_timing_read(svb_context* ctx, double* total_ms, unsigned long long* launches);
+/* host time spent inside the fused compose calls while launch timing was on (planner + driver calls: what the calling thread pays per tick) */
+svb_status svb_host_timing_read(svb_context* ctx, double* total_ms, unsigned long long* calls);
 /* launches of our kernels issued by this process so far */
 unsigned long long svb_kernel_launch_count(void);
 /* 256 floats each: UNORM8 read by the division-free identity and by true division (device self-test) */

@@ -35,6 +35,12 @@ class ComputeError(RuntimeError):
         self.name = STATUS_NAMES[code] if 0 <= code < len(STATUS_NAMES) else str(code)
 
 
+class EventError(C.Structure):
+    """svb_event_error: EventError(domain, code, description, assetId:) as the barriers emit it (compute.swift:190,247)."""
+
+    _fields_ = [("domain", C.c_char * 32), ("code", C.c_int), ("description", C.c_char * 256), ("asset_id", C.c_char * 128)]
+
+
 class ImageUniforms(C.Structure):
     """svb_image_uniforms == ImageUniforms (compute.swift:76-86), 236 bytes."""
 
@@ -88,8 +94,13 @@ def _load():
     l.svb_picture_info_get.argtypes = [C.c_void_p, C.c_void_p]
     l.svb_picture_wait.argtypes = [C.c_void_p]
     l.svb_picture_release.argtypes = [C.c_void_p]
-    l.svb_upload_compute_picture.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    l.svb_upload_compute_picture.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
     l.svb_download_compute_picture.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    l.svb_video_mixer_tick_many.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
+    l.svb_picture_identity.restype = C.c_ulonglong
+    l.svb_picture_identity.argtypes = [C.c_void_p]
+    l.svb_gpu_barrier_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    l.svb_gpu_barrier_download.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     l.svb_compose.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     l.svb_run_compute_kernel.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_void_p,
                                          C.c_size_t, C.c_int]
@@ -116,6 +127,7 @@ def _load():
     l.svb_animate_picture.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_float, C.c_char_p, C.c_void_p]
     l.svb_launch_timing.argtypes = [C.c_void_p, C.c_int]
     l.svb_launch_timing_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    l.svb_host_timing_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     l.svb_selftest_unorm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     l.svb_scale_convert_picture.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p]
     l.svb_scale_filter_table.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
@@ -202,6 +214,12 @@ class ComputeContext:
         """(total device ms, launches) of the fused kernels since timing was enabled."""
         ms, n = C.c_double(), C.c_ulonglong()
         _check(lib.svb_launch_timing_read(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def host_timing_read(self):
+        """(total host ms, calls) spent inside the library's fused compose calls since launch timing was enabled."""
+        ms, n = C.c_double(), C.c_ulonglong()
+        _check(lib.svb_host_timing_read(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
     def close(self):
@@ -298,10 +316,10 @@ class PictureSample:
         _check(lib.svb_animate_picture(self._h, float(canvas[0]), float(canvas[1]), C.byref(st), float(parent_opacity), _b(revision), C.byref(h)))
         return PictureSample(h)
 
-    def upload(self, ctx, max_planes=3, retain_cpu_buffer=True):
-        """uploadComputePicture"""
+    def upload(self, ctx, max_planes=3, retain_cpu_buffer=True, wait=True):
+        """uploadComputePicture; wait=False queues the copies and returns at once (keep the source bytes untouched until result.wait())"""
         h = C.c_void_p()
-        _check(lib.svb_upload_compute_picture(ctx._h, self._h, max_planes, int(retain_cpu_buffer), C.byref(h)))
+        _check(lib.svb_upload_compute_picture(ctx._h, self._h, max_planes, int(retain_cpu_buffer), int(wait), C.byref(h)))
         return PictureSample(h)
 
     def download(self, ctx, retain_gpu_buffer=False, wait=True):
@@ -312,6 +330,23 @@ class PictureSample:
 
     def wait(self):
         _check(lib.svb_picture_wait(self._h))
+
+    def same_sample(self, other):
+        """True when both handles refer to the same immutable sample (a barrier's pass-through)."""
+        return lib.svb_picture_identity(self._h) == lib.svb_picture_identity(other._h) != 0
+
+    def barrier_upload(self, ctx, retain_cpu_buffer=True, wait=True):
+        """GPUBarrierUpload (compute.swift:175-198): (sample, None) or (None, EventError)."""
+        return self._barrier(lib.svb_gpu_barrier_upload, ctx, retain_cpu_buffer, wait)
+
+    def barrier_download(self, ctx, retain_gpu_buffer=True, wait=True):
+        """GPUBarrierDownload (compute.swift:232-255): (sample, None) or (None, EventError)."""
+        return self._barrier(lib.svb_gpu_barrier_download, ctx, retain_gpu_buffer, wait)
+
+    def _barrier(self, fn, ctx, retain, wait):
+        h, err = C.c_void_p(), EventError()
+        rc = fn(ctx._h, self._h, int(retain), int(wait), C.byref(h), C.byref(err))
+        return (PictureSample(h), None) if rc == 0 else (None, err)
 
     def scale_convert(self, ctx, width, height, pixel_format=BGRA, filter=FILTER_BILINEAR, wait=True):
         """svb_scale_convert_picture (ours; no upstream counterpart): a GPU NV12 / P010 sample -> a new GPU BGRA sample."""
@@ -410,6 +445,19 @@ class VideoMixer:
         arr = (C.c_void_p * n)(*[m._h for m in mixers])
         outs = (C.c_void_p * n)()
         _check(lib.svb_video_mixer_mix_many(arr, n, time, int(wait), outs))
+        return [PictureSample(C.c_void_p(outs[i])) for i in range(n)]
+
+    @staticmethod
+    def tick_many(mixers, layers_per_mixer, time, wait=False):
+        """svb_video_mixer_tick_many: upload + push + mix + download of one tick of several mixers in ONE call across the boundary.
+        layers_per_mixer: a list of lists of (CPU or GPU) samples; returns the emitted frames as CPU samples (wait() before reading)."""
+        n = len(mixers)
+        flat = [p for ls in layers_per_mixer for p in ls]
+        arr = (C.c_void_p * n)(*[m._h for m in mixers])
+        larr = (C.c_void_p * max(1, len(flat)))(*[p._h for p in flat])
+        counts = (C.c_int * n)(*[len(ls) for ls in layers_per_mixer])
+        outs = (C.c_void_p * n)()
+        _check(lib.svb_video_mixer_tick_many(arr, n, larr, counts, time, int(wait), outs))
         return [PictureSample(C.c_void_p(outs[i])) for i in range(n)]
 
     def close(self):

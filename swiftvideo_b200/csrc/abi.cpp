@@ -129,6 +129,8 @@ svb_status svb_run_compute_kernel(svb_context* ctx, const svb_picture* const* im
         need(ctx, "ctx");
         need(target, "target");
         std::vector<const PictureSample*> im;
+        if (image_count < 0) throw ComputeError(ErrorCode::invalidValue, "negative image count");
+        if (image_count > 0) need(images, "images");
         for (int i = 0; i < image_count; ++i) {
             need(images[i], "image");
             im.push_back(images[i]->p.get());
@@ -143,6 +145,7 @@ svb_status svb_apply_compute_image(svb_context* ctx, const svb_picture* image, c
         need(ctx, "ctx");
         need(image, "image");
         need(target, "target");
+        if (kernel < 0 || kernel > (int)ComputeKernel::custom) throw ComputeError(ErrorCode::invalidValue, "bad kernel id");
         ctx->c = applyComputeImage(ctx->c, *image->p, *target->p, (ComputeKernel)kernel);
     });
 }
@@ -232,14 +235,52 @@ svb_status svb_picture_wait(const svb_picture* pict) {
     });
 }
 void svb_picture_release(svb_picture* pict) { delete pict; }
+unsigned long long svb_picture_identity(const svb_picture* pict) { return pict ? (unsigned long long)(uintptr_t)pict->p.get() : 0ull; }
 
-svb_status svb_upload_compute_picture(svb_context* ctx, const svb_picture* pict, int max_planes, int retain_cpu_buffer, svb_picture** out) {
+svb_status svb_upload_compute_picture(svb_context* ctx, const svb_picture* pict, int max_planes, int retain_cpu_buffer, int wait, svb_picture** out) {
     return guard([&] {
         need(ctx, "ctx");
         need(pict, "pict");
         need(out, "out");
-        *out = wrap(uploadComputePicture(ctx->c, *pict->p, max_planes, retain_cpu_buffer != 0));
+        *out = wrap(uploadComputePicture(ctx->c, *pict->p, max_planes, retain_cpu_buffer != 0, wait != 0));
     });
+}
+static svb_status barrier(const BarrierResult& r, const svb_picture* pict, svb_picture** out, svb_event_error* err) {
+    if (r.ok) {
+        // an untouched sample passes through as another handle of the same sample
+        *out = r.sample.bufferType() == pict->p->bufferType() ? new svb_picture{pict->p} : wrap(PictureSample(r.sample));
+        g_err.clear();
+        return SVB_OK;
+    }
+    g_err = r.error.description;
+    if (err) {
+        std::memset(err, 0, sizeof(*err));
+        std::strncpy(err->domain, r.error.domain.c_str(), sizeof(err->domain) - 1);
+        err->code = r.error.code;
+        std::strncpy(err->description, r.error.description.c_str(), sizeof(err->description) - 1);
+        std::strncpy(err->asset_id, r.error.assetId.c_str(), sizeof(err->asset_id) - 1);
+    }
+    return SVB_ERROR_UNKNOWN;
+}
+svb_status svb_gpu_barrier_upload(svb_context* ctx, const svb_picture* pict, int retain_cpu_buffer, int wait, svb_picture** out, svb_event_error* err) {
+    svb_status st = SVB_OK;
+    const svb_status g = guard([&] {
+        need(ctx, "ctx");
+        need(pict, "pict");
+        need(out, "out");
+        st = barrier(GPUBarrierUpload(ctx->c, retain_cpu_buffer != 0)(*pict->p, wait != 0), pict, out, err);
+    });
+    return g != SVB_OK ? g : st;
+}
+svb_status svb_gpu_barrier_download(svb_context* ctx, const svb_picture* pict, int retain_gpu_buffer, int wait, svb_picture** out, svb_event_error* err) {
+    svb_status st = SVB_OK;
+    const svb_status g = guard([&] {
+        need(ctx, "ctx");
+        need(pict, "pict");
+        need(out, "out");
+        st = barrier(GPUBarrierDownload(ctx->c, retain_gpu_buffer != 0)(*pict->p, wait != 0), pict, out, err);
+    });
+    return g != SVB_OK ? g : st;
 }
 svb_status svb_download_compute_picture(svb_context* ctx, const svb_picture* pict, int retain_gpu_buffer, int wait, svb_picture** out) {
     return guard([&] {
@@ -351,12 +392,45 @@ svb_status svb_video_mixer_mix_many(svb_mixer* const* mixers, int count, int64_t
         for (int i = 0; i < count; ++i) outs[i] = wrap(std::move(res[i]));
     });
 }
+svb_status svb_video_mixer_tick_many(svb_mixer* const* mixers, int count, const svb_picture* const* layers, const int* layer_counts, int64_t time,
+                                     int wait, svb_picture** outs) {
+    return guard([&] {
+        need(mixers, "mixers");
+        need(outs, "outs");
+        if (count <= 0) throw ComputeError(ErrorCode::invalidValue, "tick_many: no mixers");
+        need(layer_counts, "layer_counts");
+        std::vector<VideoMixer*> ms;
+        size_t at = 0;
+        for (int i = 0; i < count; ++i) {
+            need(mixers[i], "mixer");
+            ms.push_back(mixers[i]->m.get());
+            ComputeContext* c = ms.back()->computeContext();
+            if (!c) throw ComputeError(ErrorCode::badContextState, "No context");
+            if (layer_counts[i] < 0) throw ComputeError(ErrorCode::invalidValue, "negative layer count");
+            if (layer_counts[i] > 0) need(layers, "layers");
+            for (int k = 0; k < layer_counts[i]; ++k, ++at) {
+                need(layers[at], "layer");
+                const PictureSample& src = *layers[at]->p;
+                if (src.bufferType() == BufferType::cpu) ms.back()->push(uploadComputePicture(*c, src, 3, false, false));
+                else ms.back()->push(layers[at]->p);
+            }
+        }
+        std::vector<PictureSample> res(count);
+        VideoMixer::mixMany(ms.data(), count, time, res.data(), false);
+        for (int i = 0; i < count; ++i) outs[i] = wrap(downloadComputePicture(*ms[i]->computeContext(), res[i], true, wait != 0));
+    });
+}
 svb_status svb_compose(svb_context* ctx, const svb_picture* target, const svb_picture* const* layers, const svb_image_uniforms* uniforms,
                        int count, int mode) {
     return guard([&] {
         need(ctx, "ctx");
         need(target, "target");
         if (mode < 0 || mode > 5) throw ComputeError(ErrorCode::invalidValue, "bad mix mode");
+        if (count < 0) throw ComputeError(ErrorCode::invalidValue, "negative layer count");
+        if (count > 0) {
+            need(layers, "layers");
+            need(uniforms, "uniforms");
+        }
         std::vector<const PictureSample*> ls;
         for (int i = 0; i < count; ++i) {
             need(layers[i], "layer");
@@ -439,6 +513,16 @@ svb_status svb_launch_timing_read(svb_context* ctx, double* total_ms, unsigned l
         need(launches, "launches");
         if (!ctx->c.ctx) throw ComputeError(ErrorCode::badContextState, "No context");
         readLaunchTiming(ctx->c, total_ms, launches);
+    });
+}
+
+svb_status svb_host_timing_read(svb_context* ctx, double* total_ms, unsigned long long* calls) {
+    return guard([&] {
+        need(ctx, "ctx");
+        need(total_ms, "total_ms");
+        need(calls, "calls");
+        if (!ctx->c.ctx) throw ComputeError(ErrorCode::badContextState, "No context");
+        readHostTiming(ctx->c, total_ms, calls);
     });
 }
 

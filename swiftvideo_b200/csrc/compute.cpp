@@ -4,6 +4,8 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdlib>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -135,9 +137,10 @@ CUdeviceptr InternalContext::alloc(size_t size) {
     }
     CUdeviceptr p = 0;
     check(drv().cuMemAlloc(&p, size), "cuMemAlloc");
+    if (std::getenv("SVB_DEBUG_POOL")) fprintf(stderr, "[svb] cuMemAlloc %zu\n", size);
     return p;
 }
-void InternalContext::release(CUdeviceptr p, size_t size) {
+void InternalContext::release(CUdeviceptr p, size_t size, bool usedByDownload) {
     size = (size + 255) & ~(size_t)255;
     Block b;
     b.p = p;
@@ -145,6 +148,9 @@ void InternalContext::release(CUdeviceptr p, size_t size) {
         cu().cuCtxPushCurrent(ctx);
         CUstream all[3] = {compute, upload, download};
         for (int i = 0; i < 3; ++i) {
+            // (a block the download stream never read -- an uploaded layer -- does not wait for that stream's tail: it would order the next
+            // tick's uploads behind this tick's downloads and halve the link's duplex rate)
+            if (i == 2 && !usedByDownload) continue;
             CUevent e = nullptr;
             {
                 std::lock_guard<std::mutex> g(mu);
@@ -164,7 +170,7 @@ void InternalContext::release(CUdeviceptr p, size_t size) {
 }
 
 // caller holds a CtxGuard
-void* InternalContext::allocHost(size_t size) {
+void* InternalContext::allocHost(size_t size, CUstream writer) {
     size = (size + 4095) & ~(size_t)4095;
     HostBlock b;
     {
@@ -178,7 +184,8 @@ void* InternalContext::allocHost(size_t size) {
     if (b.p) {
         for (CUevent e : b.after) {
             if (!e) continue;
-            cu().cuEventSynchronize(e);  // normally long fired
+            if (writer) cu().cuStreamWaitEvent(writer, e, 0);  // the block is written by `writer`'s copies: order them behind whatever still reads it
+            else cu().cuEventSynchronize(e);                   // the host writes it: normally long fired
             std::lock_guard<std::mutex> g(mu);
             spareEvents.push_back(e);
         }
@@ -186,6 +193,7 @@ void* InternalContext::allocHost(size_t size) {
     }
     void* p = nullptr;
     check(drv().cuMemHostAlloc(&p, size, 0), "cuMemHostAlloc");
+    if (std::getenv("SVB_DEBUG_POOL")) fprintf(stderr, "[svb] cuMemHostAlloc %zu\n", size);
     return p;
 }
 void InternalContext::releaseHost(void* p, size_t size) {
@@ -233,7 +241,7 @@ Event::~Event() {
 }
 
 ComputeBuffer::~ComputeBuffer() {  // compute.cuda.swift:82-88
-    if (mem && ctx) ctx->release(mem, size);
+    if (mem && ctx) ctx->release(mem, size, usedByDownload);
 }
 
 CUDAProgram::~CUDAProgram() {
@@ -382,6 +390,7 @@ std::shared_ptr<ComputeBuffer> uploadComputeBuffer(const ComputeContext& ctx, co
 void downloadComputeBuffer(const ComputeContext& ctx, const ComputeBuffer& src, void* dst, size_t dstSize) {  // :344-357
     if (dstSize < src.size) throw ComputeError(ErrorCode::badInputData, "Destination data buffer must be >= buffer.size");
     CtxGuard g(ctx.ctx);
+    const_cast<ComputeBuffer&>(src).usedByDownload = true;
     check(drv().cuMemcpyDtoHAsync(dst, src.mem, src.size, ctx.ctx->download), "cuMemcpyDtoHAsync");
 }
 
@@ -410,7 +419,7 @@ std::vector<Plane> planesForFormat(PixelFormat f, Vector2 size) {  // sample.pic
 }
 
 PictureSample createPictureSample(Vector2 size, PixelFormat format, const std::string& assetId,
-                                  const std::string& workspaceId, ComputeContext* pinnedFrom) {  // :254-273
+                                  const std::string& workspaceId, ComputeContext* pinnedFrom, CUstream writer) {  // :254-273
     if (!(size.x > 0 && size.y > 0)) throw ComputeError(ErrorCode::invalidOperation, "createPictureSample: empty size");
     PictureSample s;
     s.imgBuffer.planes = planesForFormat(format, size);
@@ -420,7 +429,7 @@ PictureSample createPictureSample(Vector2 size, PixelFormat format, const std::s
     if (pinnedFrom && pinnedFrom->ctx) {
         CtxGuard g(pinnedFrom->ctx);
         auto ic = pinnedFrom->ctx;
-        void* p = ic->allocHost(std::max<size_t>(total, 1));
+        void* p = ic->allocHost(std::max<size_t>(total, 1), writer);
         const size_t n = std::max<size_t>(total, 1);
         base = std::shared_ptr<uint8_t>((uint8_t*)p, [ic, n](uint8_t* q) { ic->releaseHost(q, n); });
     } else {
@@ -492,7 +501,7 @@ static std::vector<std::shared_ptr<ComputeBuffer>> createTexture(const ComputeCo
     return out;
 }
 
-PictureSample uploadComputePicture(const ComputeContext& ctx, const PictureSample& pict, int maxPlanes, bool retainCpuBuffer) {  // :359-381
+PictureSample uploadComputePicture(const ComputeContext& ctx, const PictureSample& pict, int maxPlanes, bool retainCpuBuffer, bool wait) {  // :359-381
     if (pict.bufferType() != BufferType::cpu) return pict;
     if (pict.imgBuffer.planes.empty()) throw ComputeError(ErrorCode::badInputData, "Missing image buffer");
     if (!ctx.ctx) throw ComputeError(ErrorCode::badContextState, "No context");
@@ -506,6 +515,16 @@ PictureSample uploadComputePicture(const ComputeContext& ctx, const PictureSampl
     out.imgBuffer.computeTextures = textures;
     if (!retainCpuBuffer) out.imgBuffer.buffers.clear();
     out.imgBuffer.bufferType = BufferType::gpu;
+    out.done = nullptr;
+    {
+        CtxGuard g(ctx.ctx);
+        if (wait) {
+            check(drv().cuStreamSynchronize(ctx.ctx->upload), "cuStreamSynchronize");  // upstream: synchronous copies + endComputePass(ctx, true)
+        } else {  // the caller learns from `done` when the source bytes may be reused
+            out.done = std::make_shared<Event>(ctx.ctx);
+            check(drv().cuEventRecord(out.done->e, ctx.ctx->upload), "cuEventRecord");
+        }
+    }
     return out;
 }
 
@@ -521,18 +540,31 @@ PictureSample downloadComputePicture(const ComputeContext& ctx, const PictureSam
     if (!ctx.ctx) throw ComputeError(ErrorCode::badContextState, "No context");
     PictureSample out = pict;
     const size_t n = pict.imgBuffer.computeTextures.size();
-    if (out.imgBuffer.buffers.size() < n) {  // upstream: `dst ?? Data(capacity:)` -- allocate what is missing
-        // page-locked (pooled): a copy into pageable memory is staged by the driver at a fraction of the link rate
-        ComputeContext pin = ctx;
-        PictureSample host = createPictureSample(pict.size(), pict.pixelFormat(), pict.idAsset, pict.idWorkspace, &pin);
-        out.imgBuffer.buffers = host.imgBuffer.buffers;
-    }
     CtxGuard g(ctx.ctx);
+    {
+        // Always fresh host buffers: upstream's `dst` is a value-type Data (copy on write), so a download never changes the bytes of the
+        // sample that was uploaded, nor of its copies; the buffers a GPU sample retained from its upload alias that allocation here.
+        // Page-locked and pooled: a copy into pageable memory is staged by the driver at a fraction of the link rate.
+        ComputeContext pin = ctx;
+        PictureSample host = createPictureSample(pict.size(), pict.pixelFormat(), pict.idAsset, pict.idWorkspace, &pin, ctx.ctx->download);
+        out.imgBuffer.buffers = host.imgBuffer.buffers;
+        for (size_t i = 0; i < n && i < out.imgBuffer.buffers.size(); ++i)  // (decoder-style padded planes: the device plane may be larger than the tight layout)
+            if (out.imgBuffer.buffers[i].size < pict.imgBuffer.computeTextures[i]->size) {
+                const size_t len = pict.imgBuffer.computeTextures[i]->size;
+                void* q = ctx.ctx->allocHost(len, ctx.ctx->download);
+                auto ic = ctx.ctx;
+                std::shared_ptr<uint8_t> base((uint8_t*)q, [ic, len](uint8_t* z) { ic->releaseHost(z, len); });
+                out.imgBuffer.buffers[i] = HostData{base, base.get(), len};
+            }
+    }
     if (pict.done) check(drv().cuStreamWaitEvent(ctx.ctx->download, pict.done->e, 0), "cuStreamWaitEvent");
     for (size_t i = 0; i < n; ++i) {
         const auto& tex = pict.imgBuffer.computeTextures[i];
         if (tex->ready) check(drv().cuStreamWaitEvent(ctx.ctx->download, tex->ready->e, 0), "cuStreamWaitEvent");
         downloadComputeBuffer(ctx, *tex, out.imgBuffer.buffers[i].ptr, out.imgBuffer.buffers[i].size);
+        // whoever overwrites this plane next (the mixer recycles its backing ring) waits for this copy first
+        if (!tex->lastRead) tex->lastRead = std::make_shared<Event>(ctx.ctx);
+        check(drv().cuEventRecord(tex->lastRead->e, ctx.ctx->download), "cuEventRecord");
     }
     out.done = nullptr;
     if (wait) {
@@ -544,6 +576,35 @@ PictureSample downloadComputePicture(const ComputeContext& ctx, const PictureSam
     if (!retainGpuBuffer) out.imgBuffer.computeTextures.clear();
     out.imgBuffer.bufferType = BufferType::cpu;
     return out;
+}
+
+BarrierResult GPUBarrierUpload::operator()(const PictureSample& sample, bool wait) const {  // compute.swift:183-195
+    BarrierResult r;
+    if (sample.bufferType() != BufferType::cpu) {
+        r.sample = sample;  // .just($0)
+        return r;
+    }
+    try {
+        r.sample = uploadComputePicture(context, sample, 3, retainCpuBuffer, wait);
+    } catch (const std::exception& e) {
+        r.ok = false;
+        r.error = EventError{"barrier.upload", -1, e.what(), sample.assetId()};
+    }
+    return r;
+}
+BarrierResult GPUBarrierDownload::operator()(const PictureSample& sample, bool wait) const {  // compute.swift:240-252
+    BarrierResult r;
+    if (sample.bufferType() != BufferType::gpu) {
+        r.sample = sample;
+        return r;
+    }
+    try {
+        r.sample = downloadComputePicture(context, sample, retainGpuBuffer, wait);
+    } catch (const std::exception& e) {
+        r.ok = false;
+        r.error = EventError{"barrier.download", -1, e.what(), sample.assetId()};
+    }
+    return r;
 }
 
 // ---- kernels --------------------------------------------------------------------------------------------

@@ -103,6 +103,8 @@ class ComputeBuffer {    // compute.cuda.swift:75-92: owns device memory, releas
     CUdeviceptr mem;  // non-const: its address is what cuLaunchKernel's param array points at (:297)
     const size_t size;
     std::shared_ptr<Event> ready;  // recorded after the last async write (upload); consumers wait on it
+    bool usedByDownload = false;   // the download stream has read this block (set by downloadComputeBuffer)
+    std::shared_ptr<Event> lastRead;  // recorded after the last async READ on another stream (download): a writer waits on it before it overwrites (the mixer's backing ring)
     std::shared_ptr<uint8_t> hostKeep;  // source of an in-flight async upload stays alive with the texture
     std::shared_ptr<InternalContext> ctx;
 };
@@ -151,7 +153,7 @@ std::vector<Plane> planesForFormat(PixelFormat f, Vector2 size);  // :275-294
 // createPictureSample (:254-273): one contiguous CPU allocation sliced into planes. `pinned` (ours) asks
 // for page-locked memory from `ctx` so uploads/downloads run at PCIe rate; the layout is unchanged.
 PictureSample createPictureSample(Vector2 size, PixelFormat format, const std::string& assetId,
-                                  const std::string& workspaceId, struct ComputeContext* pinnedFrom = nullptr);
+                                  const std::string& workspaceId, struct ComputeContext* pinnedFrom = nullptr, CUstream writer = nullptr);
 
 // ImageBuffer(pixelFormat:bufferType:size:buffers:planes:) + PictureSample(img, ...) (sample.pict.linux.swift:23-39,160-189):
 // a CPU sample over caller-described planes -- what the FFmpeg decoder builds with its own linesize as stride
@@ -206,12 +208,46 @@ ComputeContext usingContext(const ComputeContext& ctx, F&& fn) {  // compute.swi
 std::shared_ptr<ComputeBuffer> uploadComputeBuffer(const ComputeContext& ctx, const void* src, size_t size,
                                                    std::shared_ptr<ComputeBuffer> dst);  // :330-342
 void downloadComputeBuffer(const ComputeContext& ctx, const ComputeBuffer& src, void* dst, size_t dstSize);  // :344-357
+// `wait` = upstream's behaviour (a synchronous cuMemcpyHtoD, then endComputePass(ctx, true), :339,:379): the source bytes may be
+// reused as soon as the call returns.  wait=false (ours) queues the copies on the upload stream and returns at once with `done` set:
+// the SOURCE buffers -- above all a page-locked staging buffer that a decoder refills -- must stay untouched until waitPicture(result).
 PictureSample uploadComputePicture(const ComputeContext& ctx, const PictureSample& pict, int maxPlanes = 3,
-                                   bool retainCpuBuffer = true);                          // :359-381
+                                   bool retainCpuBuffer = true, bool wait = true);        // :359-381
 // `wait` = upstream's endComputePass(ctx, true) at :396; wait=false (ours) returns at once with `done` set.
 PictureSample downloadComputePicture(const ComputeContext& ctx, const PictureSample& pict,
                                      bool retainGpuBuffer = false, bool wait = true);     // :383-402
 void waitPicture(const PictureSample& pict);  // block until `done` (if any) has fired
+
+// GPUBarrierUpload / GPUBarrierDownload (compute.swift:175-198, :232-255): the pipeline stages around the two calls above.  A sample
+// that already lives on the right side passes through untouched (`.just($0)`); a failure becomes the event error upstream emits:
+// EventError("barrier.upload" | "barrier.download", -1, "<error>", assetId:).
+struct EventError {
+    std::string domain;
+    int code = 0;
+    std::string description;
+    std::string assetId;
+};
+struct BarrierResult {
+    bool ok = true;        // .just(sample) / .error(error)
+    PictureSample sample;
+    EventError error;
+};
+class GPUBarrierUpload {
+  public:
+    explicit GPUBarrierUpload(const ComputeContext& context, bool retainCpuBuffer = true) : context(createComputeContext(context)), retainCpuBuffer(retainCpuBuffer) {}
+    BarrierResult operator()(const PictureSample& sample, bool wait = true) const;
+  private:
+    ComputeContext context;
+    bool retainCpuBuffer;
+};
+class GPUBarrierDownload {
+  public:
+    explicit GPUBarrierDownload(const ComputeContext& context, bool retainGpuBuffer = true) : context(createComputeContext(context)), retainGpuBuffer(retainGpuBuffer) {}
+    BarrierResult operator()(const PictureSample& sample, bool wait = true) const;
+  private:
+    ComputeContext context;
+    bool retainGpuBuffer;
+};
 
 // runComputeKernel<T> (:260-306): params [outputs..., inputs..., uniforms, inStride[]], block (gcd(W,16),
 // gcd(H,16)), grid (W/bx, H/by), 0 B smem.  `blends` is accepted and ignored exactly as upstream (:267).
@@ -273,7 +309,9 @@ struct InternalContext {
         CUevent after[2] = {nullptr, nullptr};  // tails of upload/download at release time: an async copy may still touch it
     };
     std::multimap<size_t, HostBlock> hostPool;
-    void* allocHost(size_t size);
+    // a pooled page-locked block.  writer == nullptr: the HOST will write it (waits until no copy still touches the recycled block);
+    // writer = a stream: that stream's copies will write it (the stream is ordered behind those copies instead: nobody blocks)
+    void* allocHost(size_t size, CUstream writer = nullptr);
     void releaseHost(void* p, size_t size);
     std::vector<CUevent> spareEvents;
     // state shared by every VideoMixer of this context (descriptor ring, tensor-map cache); owned by mix_video.cpp
@@ -284,7 +322,7 @@ struct InternalContext {
     void (*scaleSharedFree)(InternalContext*) = nullptr;
     ~InternalContext();
     CUdeviceptr alloc(size_t size);
-    void release(CUdeviceptr p, size_t size);
+    void release(CUdeviceptr p, size_t size, bool usedByDownload = true);  // usedByDownload=false: the block never met the download stream, whose tail it then need not wait for
     CUfunction builtin(const char* name);
 };
 struct CtxGuard {  // cuCtxPushCurrent / cuCtxPopCurrent pair

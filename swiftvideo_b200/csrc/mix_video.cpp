@@ -3,6 +3,8 @@
 
 #include <algorithm>
 #include <array>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -56,11 +58,15 @@ struct MixerShared {
     std::map<size_t, int> ringCtasPerSm;  // the same for svb_mix_ring
     std::map<size_t, int> tiledCtasPerSm;  // resident CTAs of svb_mix_tiled per SM by dynamic shared memory size: the persistent grid is smCount times this
     std::mutex mu;
+    std::mutex launchMu;  // one launch at a time per context: the descriptor ring, the table buffers and the timing lists are per context
     // optional per-launch device timing of the fused kernels (bench.py's roofline leg)
     bool timing = false;
     std::vector<std::pair<CUevent, CUevent>> timed, spare;
     double timedMs = 0.0;
     unsigned long long timedLaunches = 0;
+    // host time spent inside mixMany / composeRaw while timing is on (plan + driver calls; what the caller's thread pays per tick)
+    double hostMs = 0.0;
+    unsigned long long hostCalls = 0;
 };
 
 void harvest(MixerShared& s) {  // caller holds a CtxGuard
@@ -255,7 +261,7 @@ void layerRect(const SvbUniforms& u, int W, int H, int32_t rect[4]) {
 // ---- planner --------------------------------------------------------------------------------------------
 
 FramePlan planFrame(const ComputeContext& ctx, const PictureSample& target, const std::vector<const PictureSample*>& layers,
-                    const ImageUniforms* uniforms) {
+                    const ImageUniforms* uniforms, const SvbLayerDesc* const* cached) {
     FramePlan plan;
     const int tf = svbFormat(target.pixelFormat());
     if (tf != SVB_NV12 && tf != SVB_Y420P) throw ComputeError(ErrorCode::badTarget, "fused compose needs an nv12 or y420p target");
@@ -291,6 +297,10 @@ FramePlan planFrame(const ComputeContext& ctx, const PictureSample& target, cons
     for (size_t k = 0; k < n; ++k) {
         SvbFrameDesc& F = plan.passes[k / SVB_MAX_LAYERS];
         SvbLayerDesc& L = F.layers[F.nlayers++];
+        if (cached && cached[k]) {  // planned before for this very sample and a target of this size
+            L = *cached[k];
+            continue;
+        }
         const PictureSample& img = *layers[k];
         const int sf = svbFormat(img.pixelFormat());
         if (sf < 0) throw ComputeError(ErrorCode::computeKernelNotFound, std::string("computeKernelNotFound(img_") + pixelFormatName(img.pixelFormat()) + "_" + pixelFormatName(target.pixelFormat()) + ")");
@@ -375,6 +385,7 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
     const CuDriver& d = drv();
     MixerShared& sh = shared(ctx.ctx);
     InternalContext& ic = *ctx.ctx;
+    std::lock_guard<std::mutex> launchLock(sh.launchMu);  // mixers of one context may be driven from different threads
     for (size_t start = 0; start < frames.size(); start += kSegFrames) {
         const int n = (int)std::min<size_t>(kSegFrames, frames.size() - start);
         int seg;
@@ -558,28 +569,45 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
     }
 }
 
-void waitInputs(const ComputeContext& ctx, const PictureSample& p) {
-    for (const auto& t : p.imgBuffer.computeTextures)
+void waitInputs(const ComputeContext& ctx, const PictureSample& p, bool willWrite = false) {
+    for (const auto& t : p.imgBuffer.computeTextures) {
         if (t->ready) check(drv().cuStreamWaitEvent(ctx.ctx->compute, t->ready->e, 0), "cuStreamWaitEvent");
+        // a target: an asynchronous download of what the plane held before may still be reading it (the backing ring comes round
+        // every ten ticks and a compose is an order of magnitude faster than the copy over PCIe)
+        if (willWrite && t->lastRead) check(drv().cuStreamWaitEvent(ctx.ctx->compute, t->lastRead->e, 0), "cuStreamWaitEvent");
+    }
 }
 
 struct Job {
     const PictureSample* target;
     std::vector<const PictureSample*> layers;
     std::vector<ImageUniforms> uniforms;
+    std::vector<const SvbLayerDesc*> cached;    // per layer: a descriptor planned earlier for the same sample, or nullptr (empty: none)
+    std::vector<SvbLayerDesc>* planned = nullptr;  // out: the descriptors as planned now, in layer order
 };
 
 // Fused compose of several independent targets on one context.
 void composeFused(const ComputeContext& ctx, std::vector<Job>& jobs, bool forceGeneric, bool wantGather = false, int want = 0) {
     CtxGuard g(ctx.ctx);
+    struct HostClock {  // (only while launch timing is on)
+        MixerShared& sh;
+        std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+        ~HostClock() {
+            if (sh.timing) sh.hostMs += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), ++sh.hostCalls;
+        }
+    } hostClock{shared(ctx.ctx)};
     std::vector<FramePlan> plans;
     bool allTiled = !forceGeneric;
     size_t maxPass = 0;
     for (Job& j : jobs) {
-        plans.push_back(planFrame(ctx, *j.target, j.layers, j.uniforms.data()));
+        plans.push_back(planFrame(ctx, *j.target, j.layers, j.uniforms.data(), j.cached.empty() ? nullptr : j.cached.data()));
+        if (j.planned) {
+            j.planned->clear();
+            for (const SvbFrameDesc& f : plans.back().passes) j.planned->insert(j.planned->end(), f.layers, f.layers + f.nlayers);
+        }
         allTiled = allTiled && plans.back().tiledOk;
         maxPass = std::max(maxPass, plans.back().passes.size());
-        waitInputs(ctx, *j.target);
+        waitInputs(ctx, *j.target, true);
         for (const PictureSample* l : j.layers) waitInputs(ctx, *l);
     }
     for (size_t p = 0; p < maxPass; ++p) {  // a later pass of a frame reads what its earlier pass wrote: separate launches
@@ -600,6 +628,14 @@ void setLaunchTiming(const ComputeContext& ctx, bool on) {
     sh.timing = on;
     sh.timedMs = 0.0;
     sh.timedLaunches = 0;
+    sh.hostMs = 0.0;
+    sh.hostCalls = 0;
+}
+void readHostTiming(const ComputeContext& ctx, double* totalMs, unsigned long long* calls) {
+    CtxGuard g(ctx.ctx);
+    MixerShared& sh = shared(ctx.ctx);
+    *totalMs = sh.hostMs;
+    *calls = sh.hostCalls;
 }
 void readLaunchTiming(const ComputeContext& ctx, double* totalMs, unsigned long long* launches) {
     CtxGuard g(ctx.ctx);
@@ -626,7 +662,7 @@ VideoMixer::VideoMixer(const ComputeContext* computeContext, Vector2 outputSize,
             hasContext = false;  // upstream prints "Error making compute context!" and carries on without one
         }
     }
-    static int counter = 0;
+    static std::atomic<int> counter{0};
     idAsset = assetId.empty() ? "mixer-" + std::to_string(++counter) : assetId;  // upstream: UUID().uuidString
 }
 
@@ -648,14 +684,16 @@ ComputeKernel VideoMixer::findKernel(const PictureSample* image, const PictureSa
 PictureSample VideoMixer::getBacking() {  // :148-165
     if (!hasContext) throw ComputeError(ErrorCode::badContextState, "No context");
     if ((int)backing.size() < numberBackingImages) {
-        // page-locked CPU side (ours): downloads of emitted frames then run at PCIe rate
-        PictureSample image = createPictureSample(backingSize, backingFormat, idAsset, idWorkspace, &clContext);
-        // upstream uploads the (uninitialised) CPU image to obtain the GPU planes; the bytes are never read
-        // because every compose starts with the clear kernel, so only the allocation is kept here.
-        PictureSample gpu = image;
-        gpu.imgBuffer.computeTextures.clear();
+        // upstream uploads an (uninitialised) CPU image to obtain the GPU planes; the bytes are never read because every compose starts
+        // with the clear kernel, so only the plane layout and the device allocations are made here -- no host side at all (a download
+        // brings its own page-locked buffers, compute.cpp: downloadComputePicture).
+        PictureSample gpu;
+        gpu.imgBuffer.planes = planesForFormat(backingFormat, backingSize);
+        gpu.imgBuffer.pixelFormat = backingFormat;
+        gpu.imgBuffer.size = backingSize;
+        gpu.idAsset = idAsset, gpu.idWorkspace = idWorkspace, gpu.idRevision = idAsset;
         CtxGuard g(clContext.ctx);
-        for (const Plane& p : image.imgBuffer.planes) {
+        for (const Plane& p : gpu.imgBuffer.planes) {
             const size_t sz = (size_t)p.stride * (size_t)(int)p.size.y;
             gpu.imgBuffer.computeTextures.push_back(std::make_shared<ComputeBuffer>(clContext.ctx->alloc(sz), sz, clContext.ctx));
         }
@@ -743,17 +781,30 @@ void VideoMixer::mixMany(VideoMixer* const* mixers, int n, int64_t time, Picture
     ComputeContext ctx0 = mixers[0]->clContext;
     if (fusedAll) {
         jobs.resize(n);
+        std::vector<std::vector<SvbLayerDesc>> plannedNow(n);
         bool generic = false, wantGather = false;
         int want = 0;
         for (int i = 0; i < n; ++i) {
             Tick& tk = ticks[i];
+            VideoMixer& mx = *mixers[i];
+            ++mx.tickNo;
             jobs[i].target = &tk.backing;
-            mixers[i]->findKernel(nullptr, tk.backing);
+            jobs[i].planned = &plannedNow[i];
+            mx.findKernel(nullptr, tk.backing);
             for (const auto& im : tk.images) {
-                const ComputeKernel k = mixers[i]->findKernel(im.get(), tk.backing);  // throws invalidValue for an unknown pair, as upstream
+                auto hit = mx.planned.find(im.get());
+                if (hit != mx.planned.end() && hit->second.who.lock().get() == im.get()) {  // seen before (and still the same object): nothing to derive again
+                    hit->second.tick = mx.tickNo;
+                    jobs[i].layers.push_back(im.get());
+                    jobs[i].uniforms.push_back(hit->second.uniforms);
+                    jobs[i].cached.push_back(&hit->second.desc);
+                    continue;
+                }
+                const ComputeKernel k = mx.findKernel(im.get(), tk.backing);  // throws invalidValue for an unknown pair, as upstream
                 if (k == ComputeKernel::img_bgra_bgra) throw ComputeError(ErrorCode::computeKernelNotFound, "computeKernelNotFound(img_bgra_bgra)");
                 jobs[i].layers.push_back(im.get());
                 jobs[i].uniforms.push_back(makeImageUniforms(*im, tk.backing));
+                jobs[i].cached.push_back(nullptr);
             }
             generic = generic || mixers[i]->mode == Mode::generic;
             wantGather = wantGather || mixers[i]->mode == Mode::fusedGather;
@@ -761,6 +812,17 @@ void VideoMixer::mixMany(VideoMixer* const* mixers, int n, int64_t time, Picture
             if (mixers[i]->mode == Mode::fusedRing) want = 3;
         }
         composeFused(ctx0, jobs, generic, wantGather, want);
+        for (int i = 0; i < n; ++i) {  // remember what was derived; forget the samples that are gone or have not been seen for a while
+            VideoMixer& mx = *mixers[i];
+            const Tick& tk = ticks[i];
+            for (size_t k = 0; k < tk.images.size() && k < plannedNow[i].size(); ++k)
+                if (!jobs[i].cached[k]) {
+                    VideoMixer::Planned& p = mx.planned[tk.images[k].get()];
+                    p.who = tk.images[k], p.uniforms = jobs[i].uniforms[k], p.desc = plannedNow[i][k], p.tick = mx.tickNo;
+                }
+            for (auto it = mx.planned.begin(); it != mx.planned.end();)
+                it = (mx.tickNo - it->second.tick > 8u || it->second.who.expired()) ? mx.planned.erase(it) : std::next(it);
+        }
     } else {
         for (int i = 0; i < n; ++i) {
             Tick& tk = ticks[i];

@@ -76,6 +76,16 @@ class VideoMixer {
     ComputeContext clContext;
     bool hasContext = false;
     std::map<std::string, std::shared_ptr<const PictureSample>> samples[2];
+    // what was derived from a sample the last time it was composed (its uniforms and its planned layer descriptor), by identity; an
+    // entry lives while its sample does and is seen every few ticks
+    struct Planned {
+        std::weak_ptr<const PictureSample> who;
+        ImageUniforms uniforms;
+        SvbLayerDesc desc;
+        unsigned tick = 0;
+    };
+    std::map<const PictureSample*, Planned> planned;
+    unsigned tickNo = 0;
     std::string idAsset, idWorkspace;
     Mode mode = Mode::fused;
 };
@@ -83,13 +93,18 @@ class VideoMixer {
 // Device time of the fused launches (CUDA events around each kernel on the compute stream), for the roofline.
 void setLaunchTiming(const ComputeContext& ctx, bool on);
 void readLaunchTiming(const ComputeContext& ctx, double* totalMs, unsigned long long* launches);
+// Host time spent inside the fused compose calls since timing was enabled (plan + driver calls: what the caller's thread pays per tick)
+void readHostTiming(const ComputeContext& ctx, double* totalMs, unsigned long long* calls);
 
 // Planner: fills frame descriptors (one per pass of 16 layers) for one target.  Exposed for tests.
 struct FramePlan {
     std::vector<SvbFrameDesc> passes;
     bool tiledOk = false;
 };
+// `cached` (optional, one entry per layer, nullptr = plan it): a layer descriptor planned earlier for the SAME sample on a target of the
+// same size -- samples are immutable, so a mixer that sees a sample again (a still picture, a layer that persists one extra tick) skips
+// the tensor-map / texture lookups and the rectangle arithmetic for it.
 FramePlan planFrame(const ComputeContext& ctx, const PictureSample& target, const std::vector<const PictureSample*>& layers,
-                    const ImageUniforms* uniforms);
+                    const ImageUniforms* uniforms, const SvbLayerDesc* const* cached = nullptr);
 
 }  // namespace svb

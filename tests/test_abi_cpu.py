@@ -167,3 +167,22 @@ def test_picture_sample_from_planes():
     assert "stride" in str(e.value)
     with pytest.raises(sv.ComputeError):
         api.picture_sample_from_planes(64, 48, sv.NV12, [np.zeros((48, 64), np.uint8)])  # plane count
+
+
+def test_gpu_barriers_pass_through_and_error_shape():
+    """GPUBarrierUpload / GPUBarrierDownload (compute.swift:175-198, :232-255) without a GPU: a CPU sample goes through the download barrier
+    untouched (`.just($0)`); the upload barrier on a box without a device fails with upstream's event error
+    EventError("barrier.upload", -1, "<error>", assetId:)."""
+    p = sv.create_picture_sample(64, 36, sv.NV12, "asset-7", "w")
+    if sv.available_compute_devices() > 0:
+        pytest.skip("a GPU is present: covered by tests/test_gpu_mixer.py::test_barriers_are_idempotent")
+    h, err = C.c_void_p(), api.EventError()
+    rc = sv.lib.svb_gpu_barrier_upload(None, p._h, 1, 1, C.byref(h), C.byref(err))  # a NULL context is an invalid value, not a crash
+    assert rc == 4 and not h.value
+    try:
+        ctx = sv.make_compute_context(0)
+    except sv.ComputeError as e:
+        assert e.name == "deviceNotAvailable"
+        return
+    same, err = p.barrier_download(ctx)  # (only reached on a box with a driver but no usable device)
+    assert err is None and same.same_sample(p)

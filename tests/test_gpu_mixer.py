@@ -175,7 +175,7 @@ def test_async_upload_mix_download_pipeline():
             h = sv.create_picture_sample(256, 144, sv.NV12, f"a{i}", "w", pinned_from=ctx)
             h.set_host_bytes(im.data)
             hosts.append(h)
-        placed = [_place(h.upload(ctx, retain_cpu_buffer=False), canvas, (256, 144), (40 * i, 20 * i), (400, 200), z=i, opacity=0.9 - 0.2 * i)
+        placed = [_place(h.upload(ctx, retain_cpu_buffer=False, wait=False), canvas, (256, 144), (40 * i, 20 * i), (400, 200), z=i, opacity=0.9 - 0.2 * i)
                   for i, h in enumerate(hosts)]
         mixer.push_many(placed)
         out = mixer.mix(f, wait=False).download(ctx, retain_gpu_buffer=True, wait=False)
@@ -186,3 +186,108 @@ def test_async_upload_mix_download_pipeline():
         got = out.host_bytes()
         assert (got == want).all(), first_diff(got, want)
     mixer.close()
+
+
+def test_barriers_are_idempotent():
+    """GPUBarrierUpload / GPUBarrierDownload (compute.swift:175-198, :232-255): a sample already on the right side passes through as the
+    SAME sample (`.just($0)`), a CPU sample is uploaded, a GPU sample downloaded; bytes survive the round trip."""
+    ctx = context()
+    img = scenes.random_image(O.NV12, 128, 72, 4242)
+    cpu = sv.create_picture_sample(128, 72, sv.NV12, "bar", "w")
+    cpu.set_host_bytes(img.data)
+    gpu, err = cpu.barrier_upload(ctx)
+    assert err is None and gpu.info().buffer_type == sv.BUFFER_GPU
+    again, err = gpu.barrier_upload(ctx)          # already on the GPU: untouched
+    assert err is None and again.info().buffer_type == sv.BUFFER_GPU and again.same_sample(gpu)
+    back, err = gpu.barrier_download(ctx)
+    assert err is None and back.info().buffer_type == sv.BUFFER_CPU
+    assert (back.host_bytes() == img.data).all()
+    still, err = back.barrier_download(ctx)       # already on the CPU: untouched
+    assert err is None and still.same_sample(back)
+
+
+def test_async_upload_sets_done_and_source_is_reusable_after_wait():
+    """uploadComputePicture(wait=false) returns at once with `done` set (a page-locked staging buffer that the host refills
+    raced the copy): after wait() the source bytes may be overwritten, and every uploaded sample keeps the bytes it was given."""
+    ctx = context()
+    staging = sv.create_picture_sample(1920, 1080, sv.NV12, "stage", "w", pinned_from=ctx)
+    frames = [scenes.random_image(O.NV12, 1920, 1080, 5000 + i).data for i in range(4)]
+    ups = []
+    for f in frames:
+        staging.set_host_bytes(f)
+        up = staging.upload(ctx, retain_cpu_buffer=False, wait=False)
+        up.wait()                                  # the copy has left the staging buffer
+        ups.append(up)
+    for f, up in zip(frames, ups):
+        assert (fetch(ctx, up) == f).all()
+
+
+def test_download_never_touches_the_uploaded_sample():
+    """downloadComputePicture allocates its own host buffers (upstream: a value-type Data): the CPU sample that was uploaded, and its
+    copies, keep their bytes when the GPU sample is composed into and downloaded."""
+    ctx = context()
+    canvas = (256, 144)
+    stale = sv.create_picture_sample(canvas[0], canvas[1], sv.NV12, "t", "w")
+    stale.set_host_bytes(np.full(canvas[0] * canvas[1] * 3 // 2, 0xA5, dtype=np.uint8))
+    target = stale.upload(ctx)                     # retain_cpu_buffer=True: the GPU sample still refers to stale's host bytes
+    layer = to_gpu(ctx, scenes.random_image(O.NV12, 256, 144, 77), "l")
+    u = scenes.layer_uniforms(canvas, (256, 144), (0, 0), canvas, z=1, opacity=1.0)
+    sv.compose(ctx, target, [layer], [u], sv.MixMode.FUSED)
+    out = target.download(ctx, retain_gpu_buffer=True)
+    assert (out.host_bytes() != 0xA5).any()
+    assert (stale.host_bytes() == 0xA5).all(), "the download wrote into the uploaded sample's host bytes"
+
+
+def test_backing_ring_lapped_by_async_downloads():
+    """25 ticks with mix(wait=false) + download(wait=false) and nothing waited on: the backing ring of 10 comes round twice while earlier
+    downloads may still be reading (a compose is an order of magnitude faster than the copy over PCIe).  Every downloaded frame must
+    hold its own tick's bytes (write-after-read on a recycled backing)."""
+    ctx = context()
+    canvas = (1920, 1088)
+    mixer = sv.VideoMixer(ctx, canvas[0], canvas[1], sv.NV12, asset_id="lap")
+    imgs = [scenes.random_image(O.NV12, 1920, 1088, 6000 + i) for i in range(5)]
+    # (one revision for all five: a sample of the tick before would otherwise persist one extra frame, mix.video.swift:104-107,114)
+    gl = [_place(to_gpu(ctx, im, f"lap{i}"), canvas, (1920, 1088), (0, 0), canvas, z=0, opacity=1.0, revision="lap") for i, im in enumerate(imgs)]
+    outs = []
+    for t in range(25):
+        mixer.push_many([gl[t % 5]])
+        outs.append((t, mixer.mix(t, wait=False).download(ctx, retain_gpu_buffer=True, wait=False)))
+    want = {}
+    for t, o in outs:
+        o.wait()
+        k = t % 5
+        if k not in want:
+            want[k] = _oracle_mix(O.NV12, canvas, [gl[k]], [imgs[k]])
+        got = o.host_bytes()
+        assert (got == want[k]).all(), f"tick {t}: {first_diff(got, want[k])}"
+    mixer.close()
+
+
+def test_tick_many_one_call_end_to_end():
+    """svb_video_mixer_tick_many: upload + push + mix + download of two mixers in one call, nothing waited for until the end; the bytes are
+    the oracle's fold of each mixer's own layers."""
+    ctx = context()
+    canvas = (512, 256)
+    mixers = [sv.VideoMixer(ctx, canvas[0], canvas[1], sv.NV12, asset_id=f"tick{m}") for m in range(2)]
+    results = []
+    for f in range(4):
+        per_mixer, keep = [], []
+        for m in range(2):
+            imgs = [scenes.random_image(O.NV12, 256, 144, 3000 + 100 * f + 10 * m + i) for i in range(3)]
+            hosts = []
+            for i, im in enumerate(imgs):
+                h = sv.create_picture_sample(256, 144, sv.NV12, f"t{m}a{i}", "w", pinned_from=ctx)
+                h.set_host_bytes(im.data)
+                hosts.append(_place(h, canvas, (256, 144), (30 * i + 17 * m, 25 * i), (380, 190), z=i, opacity=0.95 - 0.2 * i))
+            per_mixer.append(hosts)
+            keep.append((hosts, imgs))
+        outs = sv.VideoMixer.tick_many(mixers, per_mixer, f, wait=False)
+        results.append((outs, keep))
+    for outs, keep in results:
+        for o, (hosts, imgs) in zip(outs, keep):
+            o.wait()
+            want = _oracle_mix(O.NV12, canvas, hosts, imgs)
+            got = o.host_bytes()
+            assert (got == want).all(), first_diff(got, want)
+    for m in mixers:
+        m.close()

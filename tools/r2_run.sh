@@ -1,4 +1,3 @@
-set -x
-timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
-timeout 300 python bench.py --steps 30 --warmup 3 --no-cpu-baseline --e2e-steps 5 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['kernel'], d['roofline']['kernel_ms_per_launch'], d['roofline']['frac'], d['e2e']['value'], d['host_queue_ms_per_step'])"
-python -c "import __graft_entry__ as g; g.smoke()"
+SVB_DEBUG_POOL=1 timeout 600 python bench.py --no-cpu-baseline > gpurun_out/bench_dbg.json 2> gpurun_out/bench_dbg.err
+awk '/e2e leg starts/{on=1} on{print} /e2e leg ends/{on=0}' gpurun_out/bench_dbg.err | sort | uniq -c | sort -rn | head
+grep -c cuMemHostAlloc gpurun_out/bench_dbg.err; grep -c "cuMemAlloc " gpurun_out/bench_dbg.err
