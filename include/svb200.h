@@ -132,6 +132,12 @@ svb_status svb_default_compute_kernel_from_string(const char* name, int* kernel)
 const char* svb_compute_kernel_name(int kernel);               /* String(describing: kernel) */
 /* buildComputeKernel compute.cuda.swift:171-201; image NULL = the built-in module, else a cubin/PTX image */
 svb_status svb_build_compute_kernel(svb_context* ctx, const char* name, const void* image);
+/* buildComputeKernel(_:name:source:) as upstream has it (compute.cuda.swift:171-201): CUDA C source -> NVRTC (--gpu-architecture=sm_100a where
+ * upstream says compute_30, --fmad=false as upstream, :177) -> module -> function `name`, registered in the context's library under `name`:
+ * svb_run_compute_kernel(..., SVB_KERNEL_CUSTOM, name, ...) launches it with the reference's argument convention ([out planes..., in planes...,
+ * uniforms, inStride], block gcd(W,16) x gcd(H,16)); registered under a built-in's name it replaces that built-in for this context (:210-212).
+ * SVB_ERROR_COMPILER_NOT_AVAILABLE without libnvrtc, SVB_ERROR_COMPILER_ERROR (log in svb_last_error) when the source does not compile. */
+svb_status svb_build_compute_kernel_from_source(svb_context* ctx, const char* name, const char* source);
 /* runComputeKernel<T> compute.cuda.swift:260-306 */
 svb_status svb_run_compute_kernel(svb_context* ctx, const svb_picture* const* images, int image_count, const svb_picture* target,
                                   int kernel, const char* custom_name, int max_planes, const void* uniforms, size_t uniforms_size,

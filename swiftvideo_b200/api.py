@@ -202,6 +202,10 @@ class ComputeContext:
         buf = None if image is None else C.create_string_buffer(image, len(image))
         _check(lib.svb_build_compute_kernel(self._h, name.encode(), buf))
 
+    def build_compute_kernel_from_source(self, name, source):
+        """buildComputeKernel(_:name:source:): CUDA C source through NVRTC (sm_100a, --fmad=false) into the context's library."""
+        _check(lib.svb_build_compute_kernel_from_source(self._h, name.encode(), source.encode()))
+
     def selftest_unorm(self):
         a, b = np.zeros(256, np.float32), np.zeros(256, np.float32)
         _check(lib.svb_selftest_unorm(self._h, a.ctypes.data, b.ctypes.data))

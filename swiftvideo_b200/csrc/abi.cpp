@@ -123,6 +123,14 @@ svb_status svb_build_compute_kernel(svb_context* ctx, const char* name, const vo
         ctx->c = buildComputeKernel(ctx->c, name, image);
     });
 }
+svb_status svb_build_compute_kernel_from_source(svb_context* ctx, const char* name, const char* source) {
+    return guard([&] {
+        need(ctx, "ctx");
+        need(name, "name");
+        need(source, "source");
+        ctx->c = buildComputeKernelFromSource(ctx->c, name, source);
+    });
+}
 svb_status svb_run_compute_kernel(svb_context* ctx, const svb_picture* const* images, int image_count, const svb_picture* target, int kernel,
                                   const char* custom_name, int max_planes, const void* uniforms, size_t uniforms_size, int blends) {
     return guard([&] {

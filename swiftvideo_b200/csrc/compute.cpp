@@ -1,6 +1,8 @@
 // compute.cpp -- host side of the compute path (see compute.h for the reference map).
 #include "compute.h"
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <atomic>
 #include <cstdlib>
@@ -335,6 +337,82 @@ ComputeContext buildComputeKernel(const ComputeContext& ctx, const std::string& 
     ComputeContext out = ctx;
     out.library[name] = prog;  // merging { $1 }: the new program replaces an older one of the same name
     return out;
+}
+
+// ---- NVRTC, bound lazily like the driver (dlopen: the library itself must load on a box without the toolkit) ------------------
+namespace {
+struct Nvrtc {
+    void* h = nullptr;
+    int (*createProgram)(void**, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+    int (*compileProgram)(void*, int, const char* const*) = nullptr;
+    int (*getPTXSize)(void*, size_t*) = nullptr;
+    int (*getPTX)(void*, char*) = nullptr;
+    int (*getCUBINSize)(void*, size_t*) = nullptr;
+    int (*getCUBIN)(void*, char*) = nullptr;
+    int (*getLogSize)(void*, size_t*) = nullptr;
+    int (*getLog)(void*, char*) = nullptr;
+    int (*destroyProgram)(void**) = nullptr;
+    bool ok = false;
+};
+const Nvrtc& nvrtc() {
+    static const Nvrtc n = [] {
+        Nvrtc r;
+        for (const char* name : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so.13"})
+            if ((r.h = dlopen(name, RTLD_NOW | RTLD_LOCAL))) break;
+        if (!r.h) return r;
+        auto sym = [&](const char* s) { return dlsym(r.h, s); };
+        r.createProgram = (decltype(r.createProgram))sym("nvrtcCreateProgram");
+        r.compileProgram = (decltype(r.compileProgram))sym("nvrtcCompileProgram");
+        r.getPTXSize = (decltype(r.getPTXSize))sym("nvrtcGetPTXSize");
+        r.getPTX = (decltype(r.getPTX))sym("nvrtcGetPTX");
+        r.getCUBINSize = (decltype(r.getCUBINSize))sym("nvrtcGetCUBINSize");
+        r.getCUBIN = (decltype(r.getCUBIN))sym("nvrtcGetCUBIN");
+        r.getLogSize = (decltype(r.getLogSize))sym("nvrtcGetProgramLogSize");
+        r.getLog = (decltype(r.getLog))sym("nvrtcGetProgramLog");
+        r.destroyProgram = (decltype(r.destroyProgram))sym("nvrtcDestroyProgram");
+        r.ok = r.createProgram && r.compileProgram && r.getPTXSize && r.getPTX && r.getLogSize && r.getLog && r.destroyProgram;
+        return r;
+    }();
+    return n;
+}
+}  // namespace
+
+ComputeContext buildComputeKernelFromSource(const ComputeContext& ctx, const std::string& name, const std::string& source) {  // :171-201
+    if (!ctx.ctx) throw ComputeError(ErrorCode::badContextState, "No context");
+    const Nvrtc& rt = nvrtc();
+    if (!rt.ok) throw ComputeError(ErrorCode::compilerNotAvailable, "compilerNotAvailable: libnvrtc could not be loaded");
+    void* prog = nullptr;
+    if (rt.createProgram(&prog, source.c_str(), name.c_str(), 0, nullptr, nullptr) != 0) throw ComputeError(ErrorCode::invalidProgram, "nvrtcCreateProgram failed");
+    struct Destroy {
+        const Nvrtc& rt;
+        void** p;
+        ~Destroy() { rt.destroyProgram(p); }
+    } destroy{rt, &prog};
+    // upstream: ["--gpu-architecture=compute_30", "--fmad=false"] (:177).  A real architecture (sm_100a) yields a cubin directly; every
+    // multiply and add must round on its own, as in every other kernel of the path.
+    const char* opts[] = {"--gpu-architecture=sm_100a", "--fmad=false", "-default-device"};
+    const int rc = rt.compileProgram(prog, 3, opts);
+    if (rc != 0) {
+        size_t n = 0;
+        std::string log;
+        if (rt.getLogSize(prog, &n) == 0 && n > 1) {
+            log.resize(n);
+            rt.getLog(prog, &log[0]);
+        }
+        throw ComputeError(ErrorCode::compilerError, "compilerError(" + name + "): " + log);
+    }
+    std::vector<char> image;
+    size_t n = 0;
+    if (rt.getCUBINSize && rt.getCUBIN && rt.getCUBINSize(prog, &n) == 0 && n > 0) {
+        image.resize(n);
+        if (rt.getCUBIN(prog, image.data()) != 0) image.clear();
+    }
+    if (image.empty()) {  // (a virtual architecture: PTX, finished by the driver's JIT)
+        if (rt.getPTXSize(prog, &n) != 0 || n == 0) throw ComputeError(ErrorCode::invalidProgram, "nvrtcGetPTXSize failed");
+        image.resize(n);
+        if (rt.getPTX(prog, image.data()) != 0) throw ComputeError(ErrorCode::invalidProgram, "nvrtcGetPTX failed");
+    }
+    return buildComputeKernel(ctx, name, image.data());
 }
 
 // maybeBuildKernel (:203-218): a name already in the library wins; otherwise the built-in of that name is

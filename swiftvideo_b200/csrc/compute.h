@@ -197,6 +197,11 @@ void kernelModuleImage(const void** image, size_t* size);
 // buildComputeKernel (:171-201).  Upstream compiles `source` with NVRTC then cuModuleLoadData +
 // cuModuleGetFunction(name); here `image` is a ready cubin/PTX (NULL = our built-in module).
 ComputeContext buildComputeKernel(const ComputeContext& ctx, const std::string& name, const void* image);
+// buildComputeKernel(_:name:source:) (compute.cuda.swift:171-201) as upstream has it: CUDA C source -> NVRTC (--fmad=false, :177; the
+// architecture option is sm_100a here: upstream's compute_30 is rejected by CUDA 12.9) -> cuModuleLoadData -> cuModuleGetFunction(name).
+// The compiled kernel joins the context's library under `name` (merging { $1 }), where a custom(name:) launch or a built-in's name finds it.
+// Fails with compilerNotAvailable when libnvrtc cannot be loaded, compilerError (with the NVRTC log) when the source does not compile.
+ComputeContext buildComputeKernelFromSource(const ComputeContext& ctx, const std::string& name, const std::string& source);
 
 ComputeContext beginComputePass(const ComputeContext& ctx);                        // :308-311
 ComputeContext endComputePass(const ComputeContext& ctx, bool waitForCompletion);  // :313-319

@@ -291,3 +291,50 @@ def test_tick_many_one_call_end_to_end():
             assert (got == want).all(), first_diff(got, want)
     for m in mixers:
         m.close()
+
+
+CUSTOM_SOURCE = r"""
+// a caller's own kernel in the reference's argument convention (compute.cuda.swift:294-297): [out planes..., in planes..., uniforms, inStride];
+// the launch is gcd(W,16) x gcd(H,16) blocks over the target, the output pitch is the launch width (kernels.cuda.swift:151)
+struct ImageUniforms { float transform[16], textureTx[16], borderMatrix[16], fillColor[4], inSize[2], outSize[2], opacity, sampleTime, targetTime; };
+extern "C" __global__ void my_invert_nv12(unsigned char* oY, unsigned char* oC, const unsigned char* iY, const unsigned char* iC,
+                                          const ImageUniforms* u, const int* inStride) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, W = gridDim.x * blockDim.x;
+    const float v = 255.0f - (float)iY[y * inStride[0] + x];
+    oY[y * W + x] = (unsigned char)(v * u->opacity + 0.5f);            // --fmad=false: the product is rounded before the sum
+    if (!(x & 1) && !(y & 1)) {
+        oC[(y / 2) * W + x] = iC[(y / 2) * inStride[1] + x + 1];         // swap U and V
+        oC[(y / 2) * W + x + 1] = iC[(y / 2) * inStride[1] + x];
+    }
+}
+"""
+
+
+def test_custom_kernel_from_source():
+    """buildComputeKernel(_:name:source:) (compute.cuda.swift:171-201) and ComputeKernel.custom(name:) (compute.swift:73): CUDA C source is
+    compiled by NVRTC for sm_100a with --fmad=false, registered under its name, and launched by runComputeKernel with the reference's
+    argument order and geometry."""
+    ctx = context().sharing()
+    ctx.build_compute_kernel_from_source("my_invert_nv12", CUSTOM_SOURCE)
+    W, H = 320, 180
+    src = scenes.random_image(O.NV12, W, H, 31337)
+    g = to_gpu(ctx, src, "src")
+    target = gpu_target(ctx, O.NV12, W, H)
+    u = api.ImageUniforms()
+    u.opacity = 0.5
+    api.run_compute_kernel(ctx, [g], target, api.KERNEL_CUSTOM, uniforms=u, custom_name="my_invert_nv12", blends=True)
+    ctx.synchronize()
+    got = fetch(ctx, target)
+    y = src.data[: W * H].astype(np.float32)
+    want_y = ((np.float32(255.0) - y) * np.float32(0.5) + np.float32(0.5)).astype(np.uint8)
+    c = src.data[W * H:].reshape(H // 2, W // 2, 2)
+    want_c = c[:, :, ::-1].reshape(-1)
+    assert (got[: W * H] == want_y).all(), first_diff(got[: W * H], want_y)
+    assert (got[W * H:] == want_c).all(), first_diff(got[W * H:], want_c)
+    # a name that was never built is not found; source that does not compile reports the compiler's log
+    with pytest.raises(sv.ComputeError) as e:
+        api.run_compute_kernel(ctx, [g], target, api.KERNEL_CUSTOM, uniforms=u, custom_name="nobody", blends=True)
+    assert e.value.name == "computeKernelNotFound"
+    with pytest.raises(sv.ComputeError) as e:
+        ctx.build_compute_kernel_from_source("broken", 'extern "C" __global__ void broken() { this does not compile; }')
+    assert e.value.name == "compilerError" and "error" in str(e.value)
