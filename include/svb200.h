@@ -163,6 +163,9 @@ svb_status svb_picture_with(const svb_picture* other, const float* matrix, const
                             const float* fill_color, const float* opacity, const char* revision, const char* asset_id,
                             svb_picture** out);
 svb_status svb_picture_info_get(const svb_picture* pict, svb_picture_info* out);
+/* revision() / assetId() sample.pict.linux.swift:130,142: valid while the handle lives */
+const char* svb_picture_revision(const svb_picture* pict);
+const char* svb_picture_asset_id(const svb_picture* pict);
 unsigned long long svb_picture_identity(const svb_picture* pict); /* equal for two handles of the same (immutable) sample; 0 for NULL */
 svb_status svb_picture_wait(const svb_picture* pict);          /* block until an asynchronously produced sample is complete */
 void svb_picture_release(svb_picture* pict);
@@ -213,11 +216,40 @@ typedef struct svb_element_state {   /* the ElementState fields computePictureSt
     int32_t pic_aspect;              /* 0 none, 1 aspectFit, 2 aspectFill */
     int32_t pic_origin;              /* 0 centre, 1 top-left */
     int32_t has_fill_color;
+    int32_t hidden;                  /* impl() emits nothing for a hidden element (animator.pic.swift:108-110) */
+    uint32_t parent_anchors;         /* set of SVB_ANCHOR_*; 0 = { top-left } (:62) */
 } svb_element_state;
+enum { SVB_ANCHOR_TOP_LEFT = 1, SVB_ANCHOR_TOP_RIGHT = 2, SVB_ANCHOR_BOTTOM_LEFT = 4, SVB_ANCHOR_BOTTOM_RIGHT = 8 }; /* 1 << PictureAnchor */
+typedef struct svb_computed_picture_state { /* ComputedPictureState animator.pic.swift:141-147; matrices unprojected, Matrix4 memory order */
+    float matrix[16], texture_matrix[16], border_matrix[16];
+    float fill_color[4];
+    float opacity;
+} svb_computed_picture_state;
 /* PictureAnimator.impl: `pict` re-issued with matrix = ortho(canvas) * T(pos) * Rz(rotation) * S(size), textureMatrix by
  * aspect mode, borderMatrix, fillColor, opacity = (1 - transparency) * parent_opacity, revision (NULL keeps it). */
 svb_status svb_animate_picture(const svb_picture* pict, float canvas_width, float canvas_height, const svb_element_state* state,
                                float parent_opacity, const char* revision, svb_picture** out);
+/* computePictureState animator.pic.swift:229-272 as a pure function: `next` + `pct` (both non-NULL) interpolate the transition
+ * (computeElementState :193-205); parent_matrix / initial_parent_matrix are the parent's unprojected ComputedPictureState.matrix now and
+ * when the element first saw it (NULL = none: position 0, size 0); anchors move the parent's size change onto the element's edges
+ * (computePositionSize :149-191). */
+svb_status svb_compute_picture_state(float sample_width, float sample_height, const svb_element_state* current, const svb_element_state* next,
+                                     const float* pct, uint32_t anchors, const float* parent_matrix, const float* initial_parent_matrix,
+                                     svb_computed_picture_state* out);
+/* PictureAnimator animator.pic.swift:29-139 without its Clock: the caller passes `now` (seconds) wherever the reference reads clock.current();
+ * a transition ends -- next state becomes current, anchors re-read (:67-75) -- the first time `now` reaches start + duration. */
+typedef struct svb_animator svb_animator;
+svb_status svb_animator_create(float canvas_width, float canvas_height, svb_animator* parent, uint32_t parent_anchors, svb_animator** out); /* init :30-51 */
+void svb_animator_destroy(svb_animator* animator);
+const char* svb_animator_revision(const svb_animator* animator);
+svb_status svb_animator_set_state(svb_animator* animator, const svb_element_state* state, double duration_seconds, double now);          /* setState :54-80 */
+svb_status svb_animator_set_parent(svb_animator* animator, svb_animator* parent);                                                      /* setParent :104-106 */
+/* computedState :82-102; SVB_ERROR_INVALID_VALUE ("noCurrentState") before the first setState */
+svb_status svb_animator_computed_state(svb_animator* animator, float sample_width, float sample_height, double now,
+                                       const svb_computed_picture_state* parent_state, svb_computed_picture_state* out);
+/* impl :107-128: *out = the sample re-issued with projected matrices, fill colour, opacity x parent opacity and the animator's revision;
+ * *out = NULL (status OK) when the reference returns .nothing (hidden element, no state on the element or its parent) */
+svb_status svb_animator_apply(svb_animator* animator, const svb_picture* pict, double now, svb_picture** out);
 
 /* ---- VideoMixer -------------------------------------------------------------------------------------- */
 /* VideoMixer.init mix.video.swift:22-30; ctx NULL = makeComputeContext(forType: .GPU); asset_id NULL = generated */

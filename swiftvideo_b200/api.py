@@ -54,7 +54,17 @@ class ElementState(C.Structure):
 
     _fields_ = [("pic_pos", C.c_float * 3), ("size", C.c_float * 2), ("texture_offset", C.c_float * 2), ("border_size", C.c_float * 4),
                 ("fill_color", C.c_float * 4), ("rotation", C.c_float), ("transparency", C.c_float), ("pic_aspect", C.c_int32),
-                ("pic_origin", C.c_int32), ("has_fill_color", C.c_int32)]
+                ("pic_origin", C.c_int32), ("has_fill_color", C.c_int32), ("hidden", C.c_int32), ("parent_anchors", C.c_uint32)]
+
+
+class ComputedPictureState(C.Structure):
+    """svb_computed_picture_state: unprojected matrices (Matrix4 memory order), fill colour, opacity."""
+
+    _fields_ = [("matrix", C.c_float * 16), ("texture_matrix", C.c_float * 16), ("border_matrix", C.c_float * 16),
+                ("fill_color", C.c_float * 4), ("opacity", C.c_float)]
+
+
+ANCHOR_TOP_LEFT, ANCHOR_TOP_RIGHT, ANCHOR_BOTTOM_LEFT, ANCHOR_BOTTOM_RIGHT = 1, 2, 4, 8
 
 
 class _PlaneInfo(C.Structure):
@@ -98,6 +108,9 @@ def _load():
     l.svb_download_compute_picture.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     l.svb_video_mixer_tick_many.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
     l.svb_picture_identity.restype = C.c_ulonglong
+    for n in ("svb_picture_revision", "svb_picture_asset_id"):
+        getattr(l, n).restype = C.c_char_p
+        getattr(l, n).argtypes = [C.c_void_p]
     l.svb_picture_identity.argtypes = [C.c_void_p]
     l.svb_gpu_barrier_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     l.svb_gpu_barrier_download.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
@@ -125,6 +138,16 @@ def _load():
     l.svb_picture_sample_from_planes.argtypes = [C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_void_p,
                                                  C.c_void_p]
     l.svb_animate_picture.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_float, C.c_char_p, C.c_void_p]
+    l.svb_compute_picture_state.argtypes = [C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    l.svb_animator_create.argtypes = [C.c_float, C.c_float, C.c_void_p, C.c_uint32, C.c_void_p]
+    l.svb_animator_destroy.argtypes = [C.c_void_p]
+    l.svb_animator_destroy.restype = None
+    l.svb_animator_revision.argtypes = [C.c_void_p]
+    l.svb_animator_revision.restype = C.c_char_p
+    l.svb_animator_set_state.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double]
+    l.svb_animator_set_parent.argtypes = [C.c_void_p, C.c_void_p]
+    l.svb_animator_computed_state.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_double, C.c_void_p, C.c_void_p]
+    l.svb_animator_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
     l.svb_launch_timing.argtypes = [C.c_void_p, C.c_int]
     l.svb_launch_timing_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     l.svb_host_timing_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -303,19 +326,17 @@ class PictureSample:
                                     C.cast(C.pointer(op), C.c_void_p) if op is not None else None, _b(revision), _b(asset_id), C.byref(h)))
         return PictureSample(h)
 
+    def revision(self):
+        return lib.svb_picture_revision(self._h).decode()
+
+    def asset_id(self):
+        return lib.svb_picture_asset_id(self._h).decode()
+
     def animate(self, canvas, pos, size, rotation=0.0, border=(0, 0, 0, 0), aspect=0, tex_offset=(0, 0), fill=None, transparency=0.0,
                 top_left=True, parent_opacity=1.0, revision=None):
         """PictureAnimator.impl in native code (svb_animate_picture)."""
-        st = ElementState()
-        st.pic_pos[:] = [float(v) for v in (tuple(pos) + (0.0,))[:3]]
-        st.size[:] = [float(size[0]), float(size[1])]
-        st.texture_offset[:] = [float(tex_offset[0]), float(tex_offset[1])]
-        st.border_size[:] = [float(v) for v in border]
-        if fill is not None:
-            st.fill_color[:] = [float(v) for v in fill]
-            st.has_fill_color = 1
-        st.rotation, st.transparency = float(rotation), float(transparency)
-        st.pic_aspect, st.pic_origin = int(aspect), 1 if top_left else 0
+        st = element_state(pos, size, rotation=rotation, border=border, aspect=aspect, tex_offset=tex_offset, fill=fill, transparency=transparency,
+                           top_left=top_left)
         h = C.c_void_p()
         _check(lib.svb_animate_picture(self._h, float(canvas[0]), float(canvas[1]), C.byref(st), float(parent_opacity), _b(revision), C.byref(h)))
         return PictureSample(h)
@@ -357,6 +378,70 @@ class PictureSample:
         h = C.c_void_p()
         _check(lib.svb_scale_convert_picture(ctx._h, self._h, width, height, pixel_format, filter, int(wait), C.byref(h)))
         return PictureSample(h)
+
+
+def element_state(pos, size, rotation=0.0, border=(0, 0, 0, 0), aspect=0, tex_offset=(0, 0), fill=None, transparency=0.0, top_left=True,
+                  hidden=False, anchors=0):
+    """An svb_element_state (Proto/Composition.proto ElementState, the fields the picture animator reads)."""
+    st = ElementState()
+    st.pic_pos[:] = [float(v) for v in (tuple(pos) + (0.0,))[:3]]
+    st.size[:] = [float(size[0]), float(size[1])]
+    st.texture_offset[:] = [float(tex_offset[0]), float(tex_offset[1])]
+    st.border_size[:] = [float(v) for v in border]
+    if fill is not None:
+        st.fill_color[:] = [float(v) for v in fill]
+        st.has_fill_color = 1
+    st.rotation, st.transparency = float(rotation), float(transparency)
+    st.pic_aspect, st.pic_origin = int(aspect), 1 if top_left else 0
+    st.hidden, st.parent_anchors = int(bool(hidden)), int(anchors)
+    return st
+
+
+def compute_picture_state(sample_size, current, next=None, pct=None, anchors=ANCHOR_TOP_LEFT, parent_matrix=None, initial_parent_matrix=None):
+    """computePictureState (svb_compute_picture_state): the unprojected ComputedPictureState of an element."""
+    out = ComputedPictureState()
+    p = None if pct is None else C.c_float(pct)
+    _check(lib.svb_compute_picture_state(float(sample_size[0]), float(sample_size[1]), C.byref(current), C.byref(next) if next is not None else None,
+                                         C.cast(C.pointer(p), C.c_void_p) if p is not None else None, int(anchors), _f(parent_matrix, 16),
+                                         _f(initial_parent_matrix, 16), C.byref(out)))
+    return out
+
+
+class PictureAnimator:
+    """PictureAnimator (animator.pic.swift:29-139) in native code; `now` is passed in seconds where upstream reads its Clock."""
+
+    def __init__(self, canvas, parent=None, parent_anchors=ANCHOR_TOP_LEFT):
+        self._h = C.c_void_p()
+        self._parent = parent  # upstream holds the parent weakly; the caller keeps it alive, as here
+        _check(lib.svb_animator_create(float(canvas[0]), float(canvas[1]), parent._h if parent is not None else None, int(parent_anchors), C.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.svb_animator_destroy(self._h)
+            self._h = None
+
+    @property
+    def revision(self):
+        return lib.svb_animator_revision(self._h).decode()
+
+    def set_state(self, state, duration=0.0, now=0.0):
+        _check(lib.svb_animator_set_state(self._h, C.byref(state), float(duration), float(now)))
+
+    def set_parent(self, parent):
+        self._parent = parent
+        _check(lib.svb_animator_set_parent(self._h, parent._h if parent is not None else None))
+
+    def computed_state(self, sample_size, now=0.0, parent_state=None):
+        out = ComputedPictureState()
+        _check(lib.svb_animator_computed_state(self._h, float(sample_size[0]), float(sample_size[1]), float(now),
+                                               C.byref(parent_state) if parent_state is not None else None, C.byref(out)))
+        return out
+
+    def apply(self, pict, now=0.0):
+        """impl(): the re-issued sample, or None where upstream emits nothing (hidden / no state)."""
+        h = C.c_void_p()
+        _check(lib.svb_animator_apply(self._h, pict._h, float(now), C.byref(h)))
+        return PictureSample(h) if h else None
 
 
 def scale_filter_table(filter, src_n, dst_n):

@@ -21,6 +21,9 @@ struct svb_picture {
 struct svb_mixer {
     std::unique_ptr<VideoMixer> m;
 };
+struct svb_animator {
+    std::shared_ptr<PictureAnimator> a;
+};
 struct svb_timer {
     std::shared_ptr<InternalContext> ic;
     CUevent e0 = nullptr, e1 = nullptr, tmp = nullptr;
@@ -243,6 +246,8 @@ svb_status svb_picture_wait(const svb_picture* pict) {
     });
 }
 void svb_picture_release(svb_picture* pict) { delete pict; }
+const char* svb_picture_revision(const svb_picture* pict) { return pict ? pict->p->revision().c_str() : nullptr; }
+const char* svb_picture_asset_id(const svb_picture* pict) { return pict ? pict->p->assetId().c_str() : nullptr; }
 unsigned long long svb_picture_identity(const svb_picture* pict) { return pict ? (unsigned long long)(uintptr_t)pict->p.get() : 0ull; }
 
 svb_status svb_upload_compute_picture(svb_context* ctx, const svb_picture* pict, int max_planes, int retain_cpu_buffer, int wait, svb_picture** out) {
@@ -324,22 +329,109 @@ svb_status svb_scale_filter_table(int filter, int src_n, int dst_n, int32_t* fir
     });
 }
 
+static ElementState elementState(const svb_element_state* st) {
+    ElementState e;
+    e.picPos = Vector3{st->pic_pos[0], st->pic_pos[1], st->pic_pos[2]};
+    e.size = Vector2{st->size[0], st->size[1]};
+    e.textureOffset = Vector2{st->texture_offset[0], st->texture_offset[1]};
+    e.borderSize = Vector4{st->border_size[0], st->border_size[1], st->border_size[2], st->border_size[3]};
+    e.fillColor = Vector4{st->fill_color[0], st->fill_color[1], st->fill_color[2], st->fill_color[3]};
+    e.rotation = st->rotation, e.transparency = st->transparency;
+    if (st->pic_aspect < 0 || st->pic_aspect > 2 || st->pic_origin < 0 || st->pic_origin > 1 || st->parent_anchors > 15u)
+        throw ComputeError(ErrorCode::invalidValue, "bad element state");
+    e.picAspect = (AspectMode)st->pic_aspect, e.picOrigin = (PicOrigin)st->pic_origin, e.hasFillColor = st->has_fill_color != 0;
+    e.hidden = st->hidden != 0, e.parentAnchor = st->parent_anchors;
+    return e;
+}
+
+static void computedOut(const ComputedPictureState& cs, svb_computed_picture_state* out) {
+    std::memcpy(out->matrix, cs.matrix.data(), 64);
+    std::memcpy(out->texture_matrix, cs.textureMatrix.data(), 64);
+    std::memcpy(out->border_matrix, cs.borderMatrix.data(), 64);
+    out->fill_color[0] = cs.fillColor.x, out->fill_color[1] = cs.fillColor.y, out->fill_color[2] = cs.fillColor.z, out->fill_color[3] = cs.fillColor.w;
+    out->opacity = cs.opacity;
+}
+
 svb_status svb_animate_picture(const svb_picture* pict, float canvas_width, float canvas_height, const svb_element_state* st, float parent_opacity,
                                const char* revision, svb_picture** out) {
     return guard([&] {
         need(pict, "pict");
         need(st, "state");
         need(out, "out");
-        ElementState e;
-        e.picPos = Vector3{st->pic_pos[0], st->pic_pos[1], st->pic_pos[2]};
-        e.size = Vector2{st->size[0], st->size[1]};
-        e.textureOffset = Vector2{st->texture_offset[0], st->texture_offset[1]};
-        e.borderSize = Vector4{st->border_size[0], st->border_size[1], st->border_size[2], st->border_size[3]};
-        e.fillColor = Vector4{st->fill_color[0], st->fill_color[1], st->fill_color[2], st->fill_color[3]};
-        e.rotation = st->rotation, e.transparency = st->transparency;
-        if (st->pic_aspect < 0 || st->pic_aspect > 2 || st->pic_origin < 0 || st->pic_origin > 1) throw ComputeError(ErrorCode::invalidValue, "bad element state");
-        e.picAspect = (AspectMode)st->pic_aspect, e.picOrigin = (PicOrigin)st->pic_origin, e.hasFillColor = st->has_fill_color != 0;
-        *out = wrap(animatePicture(*pict->p, Vector2{canvas_width, canvas_height}, e, parent_opacity, revision ? revision : ""));
+        *out = wrap(animatePicture(*pict->p, Vector2{canvas_width, canvas_height}, elementState(st), parent_opacity, revision ? revision : ""));
+    });
+}
+
+svb_status svb_compute_picture_state(float sample_width, float sample_height, const svb_element_state* current, const svb_element_state* next,
+                                     const float* pct, uint32_t anchors, const float* parent_matrix, const float* initial_parent_matrix,
+                                     svb_computed_picture_state* out) {
+    return guard([&] {
+        need(current, "current");
+        need(out, "out");
+        if (anchors > 15u) throw ComputeError(ErrorCode::invalidValue, "bad anchor set");
+        const ElementState cur = elementState(current);
+        ElementState nxt;
+        Matrix4 parent, initial;
+        PictureStateInputs in;
+        if (next) nxt = elementState(next), in.next = &nxt;
+        if (pct) in.pct = *pct;
+        if (parent_matrix) parent = Matrix4::from_array(parent_matrix), in.parent = &parent;
+        if (initial_parent_matrix) initial = Matrix4::from_array(initial_parent_matrix), in.initialParent = &initial;
+        in.anchors = anchors ? anchors : (unsigned)anchorTopLeft;
+        computedOut(computePictureState(Vector2{sample_width, sample_height}, cur, in), out);
+    });
+}
+
+svb_status svb_animator_create(float canvas_width, float canvas_height, svb_animator* parent, uint32_t parent_anchors, svb_animator** out) {
+    return guard([&] {
+        need(out, "out");
+        if (parent_anchors > 15u) throw ComputeError(ErrorCode::invalidValue, "bad anchor set");
+        auto* h = new svb_animator;
+        h->a = std::make_shared<PictureAnimator>(Vector2{canvas_width, canvas_height}, parent ? parent->a : nullptr, parent_anchors);
+        *out = h;
+    });
+}
+
+void svb_animator_destroy(svb_animator* animator) { delete animator; }
+
+const char* svb_animator_revision(const svb_animator* animator) { return animator ? animator->a->revision().c_str() : nullptr; }
+
+svb_status svb_animator_set_state(svb_animator* animator, const svb_element_state* state, double duration_seconds, double now) {
+    return guard([&] {
+        need(animator, "animator");
+        need(state, "state");
+        animator->a->setState(elementState(state), duration_seconds, now);
+    });
+}
+
+svb_status svb_animator_set_parent(svb_animator* animator, svb_animator* parent) {
+    return guard([&] {
+        need(animator, "animator");
+        animator->a->setParent(parent ? parent->a : nullptr);
+    });
+}
+
+svb_status svb_animator_computed_state(svb_animator* animator, float sample_width, float sample_height, double now,
+                                       const svb_computed_picture_state* parent_state, svb_computed_picture_state* out) {
+    return guard([&] {
+        need(animator, "animator");
+        need(out, "out");
+        ComputedPictureState ps;
+        if (parent_state) {
+            ps.matrix = Matrix4::from_array(parent_state->matrix);
+            ps.opacity = parent_state->opacity;
+        }
+        computedOut(animator->a->computedState(Vector2{sample_width, sample_height}, now, parent_state ? &ps : nullptr), out);
+    });
+}
+
+svb_status svb_animator_apply(svb_animator* animator, const svb_picture* pict, double now, svb_picture** out) {
+    return guard([&] {
+        need(animator, "animator");
+        need(pict, "pict");
+        need(out, "out");
+        PictureSample res;
+        *out = animator->a->apply(*pict->p, now, &res) ? wrap(std::move(res)) : nullptr;
     });
 }
 

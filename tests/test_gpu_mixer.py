@@ -338,3 +338,61 @@ def test_custom_kernel_from_source():
     with pytest.raises(sv.ComputeError) as e:
         ctx.build_compute_kernel_from_source("broken", 'extern "C" __global__ void broken() { this does not compile; }')
     assert e.value.name == "compilerError" and "error" in str(e.value)
+
+
+@pytest.mark.parametrize("mode", [sv.MixMode.FUSED_RING, sv.MixMode.FUSED_TILED, sv.MixMode.PER_LAYER])
+def test_layers_placed_by_the_native_animator(mode):
+    """layers placed the way bench.py and a SwiftVideo composition place them -- svb_animate_picture and
+    PictureAnimator (parent, anchors, a transition under way) -- composed by the mixer and compared byte for byte with the
+    oracle fold; the uniforms the host derives are also checked against a float64 inverse of the restated animator's matrices."""
+    from oracle import animator_ref as R
+    ctx = context()
+    canvas = (384, 216)
+    mixer = sv.VideoMixer(ctx, canvas[0], canvas[1], sv.NV12, asset_id="mixer", workspace_id="ws")
+    mixer.set_mode(mode)
+    fmts = [O.NV12, O.Y420P, O.BGRA, O.NV12]
+    imgs = [scenes.random_image(f, 128, 72, 4200 + i) for i, f in enumerate(fmts)]
+    gpu = [to_gpu(ctx, im, f"asset{i}") for i, im in enumerate(imgs)]
+    base = dict(rotation=0.0, border=(0, 0, 0, 0), tex_offset=(0, 0), transparency=0.0)
+    # layer 0: the bench's placement call, full canvas
+    placed = [gpu[0].animate(canvas, (0, 0, 0.0), canvas, transparency=0.0)]
+    # layer 1: a panel in mid-transition (grows and fades), layer 2 rides its bottom-right corner, layer 3 stretches with it
+    panel = sv.PictureAnimator(canvas)
+    p0, p1 = dict(base, pos=(20, 16, 1.0), size=(160, 90)), dict(base, pos=(20, 16, 1.0), size=(240, 150), transparency=0.4)
+    panel.set_state(sv.element_state(p0["pos"], p0["size"]), 0.0, 0.0)
+    badge = sv.PictureAnimator(canvas, parent=panel)
+    bs = dict(base, pos=(100, 50, 2.0), size=(48, 28), transparency=0.25, border=(2, 2, 2, 2), fill=(0.9, 0.1, 0.1, 1.0))
+    badge.set_state(sv.element_state(bs["pos"], bs["size"], transparency=0.25, border=bs["border"], fill=bs["fill"], anchors=sv.ANCHOR_BOTTOM_RIGHT))
+    strip = sv.PictureAnimator(canvas, parent=panel)
+    ss = dict(base, pos=(8, 60, 3.0), size=(140, 24), aspect=2)
+    strip.set_state(sv.element_state(ss["pos"], ss["size"], aspect=2, anchors=sv.ANCHOR_TOP_LEFT | sv.ANCHOR_TOP_RIGHT))
+    for a, g in ((panel, gpu[1]), (badge, gpu[2]), (strip, gpu[3])):   # first frame latches the initial parent state
+        assert a.apply(g, 0.0) is not None
+    panel.set_state(sv.element_state(p1["pos"], p1["size"], transparency=0.4), 2.0, 1.0)
+    now = 1.5
+    placed += [panel.apply(gpu[1], now), badge.apply(gpu[2], now), strip.apply(gpu[3], now)]
+    assert [p.z_index() for p in placed] == [1, 2, 3, 4]
+    # the restated animator says where they are
+    pm0 = R.picture_state((128, 72), p0)["matrix"]
+    pst = R.picture_state((128, 72), p0, nxt=p1, pct=0.25)
+    want_states = [R.picture_state((128, 72), dict(base, pos=(0, 0, 0.0), size=canvas)), pst,
+                   R.picture_state((128, 72), bs, anchors=[R.BR], parent=pst["matrix"], initial_parent=pm0),
+                   R.picture_state((128, 72), ss, anchors=[R.TL, R.TR], parent=pst["matrix"], initial_parent=pm0)]
+    tgt = sv.create_picture_sample(canvas[0], canvas[1], sv.NV12, "t", "w")
+    for p, w, op in zip(placed, want_states, (1.0, 0.9, 0.75 * 0.9, 1.0 * 0.9)):
+        i = p.info()
+        assert np.allclose(np.array(i.matrix[:]), R.project(canvas, w["matrix"]), rtol=1e-5, atol=1e-6)
+        assert abs(i.opacity - op) < 1e-6
+        u = api.make_image_uniforms(p, tgt)
+        for got, mem in ((u.transform, R.project(canvas, w["matrix"])), (u.border_matrix, R.project(canvas, w["border_matrix"])), (u.texture_transform, w["texture_matrix"])):
+            inv = np.linalg.inv(np.asarray(mem, dtype=np.float64).reshape(4, 4).T)     # standard (row, col); uniforms hold its rows
+            assert np.allclose(np.array(got[:]).reshape(4, 4), inv, rtol=3e-6, atol=3e-6)
+    # the badge sits at panel origin + its own position + the panel's growth so far (20, 15)
+    bm = np.array(placed[2].info().matrix[:]).reshape(4, 4)
+    assert abs((bm[3, 0] + 1) * canvas[0] / 2 - (20 + 100 + 20)) < 1e-3 and abs((bm[3, 1] + 1) * canvas[1] / 2 - (16 + 50 + 15)) < 1e-3
+    for p in placed:
+        assert mixer.push(p)
+    got = fetch(ctx, mixer.mix(1000))
+    want = _oracle_mix(O.NV12, canvas, placed, imgs)
+    assert (got == want).all(), first_diff(got, want)
+    mixer.close()
