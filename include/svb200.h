@@ -205,6 +205,29 @@ svb_status svb_scale_convert_picture(svb_context* ctx, const svb_picture* src, f
  * with first = weights = NULL to learn *taps.  No device needed. */
 svb_status svb_scale_filter_table(int filter, int src_n, int dst_n, int32_t* first, float* weights, int weights_capacity, int* taps);
 
+/* ---- device hand-off: a composited frame consumed where it lies -------------------------------------------
+ * Upstream downloads every mixed frame to feed libavcodec (its h264_nvenc line is commented out, enc.video.ffmpeg.swift:169-170) and relies
+ * on "done within ten ticks" for the backing ring (mix.video.swift:152-164).  These three calls let an on-device consumer (an NVENC
+ * session on the same context, or a peer GPU that gathers several mixers' frames) take the planes directly and hand them back explicitly. */
+typedef struct svb_device_frame {
+    int32_t device_index;            /* CUDA ordinal the planes live on */
+    int32_t pixel_format;            /* svb_pixel_format */
+    int32_t plane_count;
+    float width, height;
+    struct { unsigned long long ptr; int32_t pitch; int32_t width_bytes; int32_t rows; int32_t pad_; } planes[3];
+    void* context;                   /* CUcontext (the device's primary context) the pointers belong to */
+    void* ready_event;               /* CUevent: cuStreamWaitEvent(consumer_stream, ready_event, 0) before reading; NULL = nothing pending.
+                                        Owned by the picture handle: valid until svb_picture_release */
+} svb_device_frame;
+svb_status svb_picture_device_frame(const svb_picture* pict, svb_device_frame* out);
+/* the consumer has queued its reads on `consumer_stream` (a CUstream of frame.context): the producer's next write of these planes
+ * (backing-ring reuse, pool reuse after release) is ordered behind that point */
+svb_status svb_picture_consumed_on(const svb_picture* pict, void* consumer_stream);
+/* copy a GPU sample that lives on another device into dst_ctx (cuMemcpyPeerAsync, direct over NVLink when the devices are peers),
+ * ordered behind the sample's completion on its own device; a sample already on dst_ctx's device comes back as another handle of itself.
+ * wait = 0 returns at once (svb_picture_wait / the result's ready_event to join). */
+svb_status svb_gather_picture(svb_context* dst_ctx, const svb_picture* pict, int wait, svb_picture** out);
+
 /* ---- PictureAnimator's state -> matrices (animator.pic.swift:107-128,207-272,326-333) ------------------ */
 typedef struct svb_element_state {   /* the ElementState fields computePictureState reads (Proto/Composition.proto:56-71) */
     float pic_pos[3];

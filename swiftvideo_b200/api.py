@@ -67,6 +67,17 @@ class ComputedPictureState(C.Structure):
 ANCHOR_TOP_LEFT, ANCHOR_TOP_RIGHT, ANCHOR_BOTTOM_LEFT, ANCHOR_BOTTOM_RIGHT = 1, 2, 4, 8
 
 
+class _DevicePlane(C.Structure):
+    _fields_ = [("ptr", C.c_ulonglong), ("pitch", C.c_int32), ("width_bytes", C.c_int32), ("rows", C.c_int32), ("pad_", C.c_int32)]
+
+
+class DeviceFrame(C.Structure):
+    """svb_device_frame: a GPU sample's planes for an on-device consumer (device pointers, pitches, CUcontext, completion CUevent)."""
+
+    _fields_ = [("device_index", C.c_int32), ("pixel_format", C.c_int32), ("plane_count", C.c_int32), ("width", C.c_float), ("height", C.c_float),
+                ("planes", _DevicePlane * 3), ("context", C.c_void_p), ("ready_event", C.c_void_p)]
+
+
 class _PlaneInfo(C.Structure):
     _fields_ = [("width", C.c_float), ("height", C.c_float), ("stride", C.c_int32), ("bit_depth", C.c_int32),
                 ("components", C.c_int32), ("host", C.c_void_p), ("device", C.c_ulonglong), ("size", C.c_size_t)]
@@ -138,6 +149,9 @@ def _load():
     l.svb_picture_sample_from_planes.argtypes = [C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_void_p,
                                                  C.c_void_p]
     l.svb_animate_picture.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_float, C.c_char_p, C.c_void_p]
+    l.svb_picture_device_frame.argtypes = [C.c_void_p, C.c_void_p]
+    l.svb_picture_consumed_on.argtypes = [C.c_void_p, C.c_void_p]
+    l.svb_gather_picture.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     l.svb_compute_picture_state.argtypes = [C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
     l.svb_animator_create.argtypes = [C.c_float, C.c_float, C.c_void_p, C.c_uint32, C.c_void_p]
     l.svb_animator_destroy.argtypes = [C.c_void_p]
@@ -328,6 +342,22 @@ class PictureSample:
 
     def revision(self):
         return lib.svb_picture_revision(self._h).decode()
+
+    def device_frame(self):
+        """svb_picture_device_frame: where the planes lie, for a consumer that reads them on the device."""
+        f = DeviceFrame()
+        _check(lib.svb_picture_device_frame(self._h, C.byref(f)))
+        return f
+
+    def consumed_on(self, stream):
+        """svb_picture_consumed_on: the consumer's reads are queued on `stream` (a CUstream handle); writers wait for that point."""
+        _check(lib.svb_picture_consumed_on(self._h, C.c_void_p(stream)))
+
+    def gather(self, ctx, wait=True):
+        """svb_gather_picture: this GPU sample copied onto ctx's device (peer copy); itself when it already lives there."""
+        h = C.c_void_p()
+        _check(lib.svb_gather_picture(ctx._h, self._h, 1 if wait else 0, C.byref(h)))
+        return PictureSample(h)
 
     def asset_id(self):
         return lib.svb_picture_asset_id(self._h).decode()

@@ -329,6 +329,46 @@ svb_status svb_scale_filter_table(int filter, int src_n, int dst_n, int32_t* fir
     });
 }
 
+svb_status svb_picture_device_frame(const svb_picture* pict, svb_device_frame* out) {
+    return guard([&] {
+        need(pict, "pict");
+        need(out, "out");
+        const PictureSample& p = *pict->p;
+        if (p.bufferType() != BufferType::gpu || p.imgBuffer.computeTextures.empty()) throw ComputeError(ErrorCode::badInputData, "not a GPU sample");
+        std::memset(out, 0, sizeof *out);
+        const auto& ic = p.imgBuffer.computeTextures[0]->ctx;
+        out->device_index = ic->deviceIndex;
+        out->pixel_format = (int32_t)p.pixelFormat();
+        out->width = p.size().x, out->height = p.size().y;
+        out->plane_count = (int32_t)std::min<size_t>(3, p.imgBuffer.computeTextures.size());
+        for (int i = 0; i < out->plane_count; ++i) {
+            const Plane& pl = p.imgBuffer.planes[i];
+            out->planes[i].ptr = (unsigned long long)p.imgBuffer.computeTextures[i]->mem;
+            out->planes[i].pitch = pl.stride;
+            out->planes[i].width_bytes = (int32_t)pl.size.x * (int32_t)pl.components.size() * ((pl.bitDepth + 7) / 8);
+            out->planes[i].rows = (int32_t)pl.size.y;
+        }
+        out->context = ic->ctx;
+        out->ready_event = pictureReadyEvent(p);
+    });
+}
+
+svb_status svb_picture_consumed_on(const svb_picture* pict, void* consumer_stream) {
+    return guard([&] {
+        need(pict, "pict");
+        pictureConsumedOn(*pict->p, (CUstream)consumer_stream);
+    });
+}
+
+svb_status svb_gather_picture(svb_context* dst_ctx, const svb_picture* pict, int wait, svb_picture** out) {
+    return guard([&] {
+        need(dst_ctx, "dst_ctx");
+        need(pict, "pict");
+        need(out, "out");
+        *out = wrap(gatherComputePicture(dst_ctx->c, *pict->p, wait != 0));
+    });
+}
+
 static ElementState elementState(const svb_element_state* st) {
     ElementState e;
     e.picPos = Vector3{st->pic_pos[0], st->pic_pos[1], st->pic_pos[2]};

@@ -135,6 +135,8 @@ CUdeviceptr InternalContext::alloc(size_t size) {
             std::lock_guard<std::mutex> g(mu);
             spareEvents.push_back(e);
         }
+        if (b.consumer && cu().cuEventQuery(b.consumer->e) != CUDA_SUCCESS)
+            for (CUstream s : all) cu().cuStreamWaitEvent(s, b.consumer->e, 0);
         return b.p;
     }
     CUdeviceptr p = 0;
@@ -142,10 +144,11 @@ CUdeviceptr InternalContext::alloc(size_t size) {
     if (std::getenv("SVB_DEBUG_POOL")) fprintf(stderr, "[svb] cuMemAlloc %zu\n", size);
     return p;
 }
-void InternalContext::release(CUdeviceptr p, size_t size, bool usedByDownload) {
+void InternalContext::release(CUdeviceptr p, size_t size, bool usedByDownload, std::shared_ptr<Event> consumer) {
     size = (size + 255) & ~(size_t)255;
     Block b;
     b.p = p;
+    b.consumer = std::move(consumer);
     if (cu().ok && ctx) {
         cu().cuCtxPushCurrent(ctx);
         CUstream all[3] = {compute, upload, download};
@@ -243,7 +246,7 @@ Event::~Event() {
 }
 
 ComputeBuffer::~ComputeBuffer() {  // compute.cuda.swift:82-88
-    if (mem && ctx) ctx->release(mem, size, usedByDownload);
+    if (mem && ctx) ctx->release(mem, size, usedByDownload, consumerRead);
 }
 
 CUDAProgram::~CUDAProgram() {
@@ -610,6 +613,63 @@ void waitPicture(const PictureSample& pict) {
     if (!pict.done) return;
     CtxGuard g(pict.done->ctx);
     check(drv().cuEventSynchronize(pict.done->e), "cuEventSynchronize");
+}
+
+CUevent pictureReadyEvent(const PictureSample& pict) {
+    if (pict.done) return pict.done->e;
+    // the planes of one sample are written in plane order by one stream: the last plane's event covers them all
+    for (auto t = pict.imgBuffer.computeTextures.rbegin(); t != pict.imgBuffer.computeTextures.rend(); ++t)
+        if ((*t)->ready) return (*t)->ready->e;
+    return nullptr;
+}
+
+void pictureConsumedOn(const PictureSample& pict, CUstream consumer) {
+    if (pict.bufferType() != BufferType::gpu) throw ComputeError(ErrorCode::badInputData, "not a GPU sample");
+    for (const auto& t : pict.imgBuffer.computeTextures) {
+        CtxGuard g(t->ctx);
+        auto e = std::make_shared<Event>(t->ctx);
+        check(drv().cuEventRecord(e->e, consumer), "cuEventRecord");
+        t->consumerRead = e;
+    }
+}
+
+PictureSample gatherComputePicture(const ComputeContext& dst, const PictureSample& pict, bool wait) {
+    if (pict.bufferType() != BufferType::gpu) throw ComputeError(ErrorCode::badInputData, "not a GPU sample");
+    if (!dst.ctx) throw ComputeError(ErrorCode::badContextState, "No context");
+    if (pict.imgBuffer.computeTextures.empty()) throw ComputeError(ErrorCode::badInputData, "Missing image buffer");
+    const auto& src = pict.imgBuffer.computeTextures[0]->ctx;
+    if (src->device == dst.ctx->device) return pict;
+    CtxGuard g(dst.ctx);
+    {   // direct access when the two devices are peers (NVLink / NVSwitch); otherwise the driver stages the copy
+        int can = 0;
+        if (drv().cuDeviceCanAccessPeer(&can, dst.ctx->device, src->device) == CUDA_SUCCESS && can) {
+            CUresult r = drv().cuCtxEnablePeerAccess(src->ctx, 0);
+            if (r != CUDA_SUCCESS && r != CUDA_ERROR_PEER_ACCESS_ALREADY_ENABLED) check(r, "cuCtxEnablePeerAccess");
+        }
+    }
+    PictureSample out = pict;
+    out.imgBuffer.computeTextures.clear();
+    out.imgBuffer.buffers.clear();
+    CUstream st = dst.ctx->upload;
+    if (pict.done) check(drv().cuStreamWaitEvent(st, pict.done->e, 0), "cuStreamWaitEvent");
+    for (const auto& t : pict.imgBuffer.computeTextures) {
+        if (t->ready) check(drv().cuStreamWaitEvent(st, t->ready->e, 0), "cuStreamWaitEvent");
+        auto copy = createBuffer(dst, t->size);
+        check(drv().cuMemcpyPeerAsync(copy->mem, dst.ctx->ctx, t->mem, src->ctx, t->size, st), "cuMemcpyPeerAsync");
+        auto e = std::make_shared<Event>(dst.ctx);
+        check(drv().cuEventRecord(e->e, st), "cuEventRecord");
+        t->consumerRead = e;  // the source's next writer (its mixer's ring, its pool) waits for this copy
+        copy->ready = e;      // and readers on dst's other streams order themselves behind it
+        out.imgBuffer.computeTextures.push_back(copy);
+    }
+    out.done = nullptr;
+    if (wait) {
+        check(drv().cuStreamSynchronize(st), "cuStreamSynchronize");
+    } else {
+        out.done = std::make_shared<Event>(dst.ctx);
+        check(drv().cuEventRecord(out.done->e, st), "cuEventRecord");
+    }
+    return out;
 }
 
 PictureSample downloadComputePicture(const ComputeContext& ctx, const PictureSample& pict, bool retainGpuBuffer, bool wait) {  // :383-402

@@ -105,6 +105,7 @@ class ComputeBuffer {    // compute.cuda.swift:75-92: owns device memory, releas
     std::shared_ptr<Event> ready;  // recorded after the last async write (upload); consumers wait on it
     bool usedByDownload = false;   // the download stream has read this block (set by downloadComputeBuffer)
     std::shared_ptr<Event> lastRead;  // recorded after the last async READ on another stream (download): a writer waits on it before it overwrites (the mixer's backing ring)
+    std::shared_ptr<Event> consumerRead;  // recorded by a reader outside this context's streams (an encoder's stream, a peer GPU's gather): writers and the pool wait on it
     std::shared_ptr<uint8_t> hostKeep;  // source of an in-flight async upload stays alive with the texture
     std::shared_ptr<InternalContext> ctx;
 };
@@ -221,7 +222,17 @@ PictureSample uploadComputePicture(const ComputeContext& ctx, const PictureSampl
 // `wait` = upstream's endComputePass(ctx, true) at :396; wait=false (ours) returns at once with `done` set.
 PictureSample downloadComputePicture(const ComputeContext& ctx, const PictureSample& pict,
                                      bool retainGpuBuffer = false, bool wait = true);     // :383-402
-void waitPicture(const PictureSample& pict);  // block until `done` (if any) has fired
+void waitPicture(const PictureSample& pict);
+// ---- device hand-off (upstream's commented-out h264_nvenc path, enc.video.ffmpeg.swift:169-170) ----------
+// A consumer that reads a GPU sample where it lies (an encoder session on the same CUDA context) orders itself behind
+// pictureReadyEvent() with cuStreamWaitEvent and, once its reads are queued, calls pictureConsumedOn(its stream): the mixer's
+// backing ring and the block pool then wait for that point instead of the ten-tick convention of mix.video.swift:152-164.
+CUevent pictureReadyEvent(const PictureSample& pict);                  // nullptr: nothing pending
+void pictureConsumedOn(const PictureSample& pict, CUstream consumer);  // consumer: a stream of the sample's own context
+// A GPU sample that lives on another device copied into `dst` (cuMemcpyPeerAsync on dst's upload stream -- NVLink when the
+// devices are peers -- ordered behind the sample's completion; the source planes' next writer waits for the copy).
+// A sample already on dst's device is returned as it is.  wait=false returns at once with `done` set.
+PictureSample gatherComputePicture(const ComputeContext& dst, const PictureSample& pict, bool wait = true);  // block until `done` (if any) has fired
 
 // GPUBarrierUpload / GPUBarrierDownload (compute.swift:175-198, :232-255): the pipeline stages around the two calls above.  A sample
 // that already lives on the right side passes through untouched (`.just($0)`); a failure becomes the event error upstream emits:
@@ -305,6 +316,7 @@ struct InternalContext {
     struct Block {
         CUdeviceptr p = 0;
         CUevent after[3] = {nullptr, nullptr, nullptr};  // tails of compute/upload/download at release time
+        std::shared_ptr<Event> consumer;                   // a foreign reader's completion (ComputeBuffer::consumerRead)
     };
     std::multimap<size_t, Block> pool;  // freed device blocks by size (upstream cuMemAllocs per upload)
     // page-locked host blocks by size (createPictureSample(pinnedFrom:), and the destination of a download that has none):
@@ -327,7 +339,7 @@ struct InternalContext {
     void (*scaleSharedFree)(InternalContext*) = nullptr;
     ~InternalContext();
     CUdeviceptr alloc(size_t size);
-    void release(CUdeviceptr p, size_t size, bool usedByDownload = true);  // usedByDownload=false: the block never met the download stream, whose tail it then need not wait for
+    void release(CUdeviceptr p, size_t size, bool usedByDownload = true, std::shared_ptr<Event> consumer = nullptr);  // usedByDownload=false: the block never met the download stream, whose tail it then need not wait for
     CUfunction builtin(const char* name);
 };
 struct CtxGuard {  // cuCtxPushCurrent / cuCtxPopCurrent pair

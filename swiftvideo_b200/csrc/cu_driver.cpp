@@ -48,6 +48,9 @@ static void load() {
     SVB_CU_FN(cuMemcpyDtoHAsync)
     SVB_CU_FN(cuMemcpy2DAsync)
     SVB_CU_FN(cuMemsetD8Async)
+    SVB_CU_FN(cuMemcpyPeerAsync)
+    SVB_CU_FN(cuDeviceCanAccessPeer)
+    SVB_CU_FN(cuCtxEnablePeerAccess)
     SVB_CU_FN(cuModuleLoadData)
     SVB_CU_FN(cuModuleUnload)
     SVB_CU_FN(cuModuleGetFunction)

@@ -575,6 +575,7 @@ void waitInputs(const ComputeContext& ctx, const PictureSample& p, bool willWrit
         // a target: an asynchronous download of what the plane held before may still be reading it (the backing ring comes round
         // every ten ticks and a compose is an order of magnitude faster than the copy over PCIe)
         if (willWrite && t->lastRead) check(drv().cuStreamWaitEvent(ctx.ctx->compute, t->lastRead->e, 0), "cuStreamWaitEvent");
+        if (willWrite && t->consumerRead) check(drv().cuStreamWaitEvent(ctx.ctx->compute, t->consumerRead->e, 0), "cuStreamWaitEvent");
     }
 }
 
