@@ -411,6 +411,7 @@ SCALE_WORKLOADS = {
     # name: (source format, filter, source size, destination size, swscale names)
     "cfg5": ("p010", "lanczos3", (3840, 2160), (1920, 1080)),
     "cfg2": ("nv12", "bilinear", (1920, 1080), (1280, 720)),
+    "cfg2chain": ("nv12", "bilinear", (1920, 1080), (1280, 720)),
 }
 
 
@@ -440,11 +441,23 @@ def run_scale(args):
         devs.append(h.upload(ctx))
     ctx.synchronize()
 
+    chain = args.workload == "cfg2chain"
+    mixers = [sv.VideoMixer(ctx, dw, dh, sv.NV12, asset_id=f"mixer{k}", workspace_id="bench") for k in range(N)] if chain else []
+
+    def compose_back(bgra, i):
+        """cfg 2's chain: the scaled BGRA pictures go back to NV12 through the reference's img_bgra_nv12 (the mixer, one layer)"""
+        for k in range(N):
+            mixers[k].push(bgra[k].animate((dw, dh), (0, 0, 0.0), (dw, dh), revision="src"))
+        return sv.VideoMixer.mix_many(mixers, 1000 * (i + 1), wait=False)
+
     def step_resident(i):
-        return [devs[k].scale_convert(ctx, dw, dh, sv.BGRA, filt, wait=False) for k in range(N)]
+        outs = [devs[k].scale_convert(ctx, dw, dh, sv.BGRA, filt, wait=False) for k in range(N)]
+        return compose_back(outs, i) if chain else outs
 
     def step_e2e(i):
         outs = [hosts[k].upload(ctx, retain_cpu_buffer=False, wait=False).scale_convert(ctx, dw, dh, sv.BGRA, filt, wait=False) for k in range(N)]
+        if chain:
+            outs = compose_back(outs, i)
         return [o.download(ctx, retain_gpu_buffer=True, wait=False) for o in outs]
 
     def timed(fn, steps, warmup):
@@ -476,21 +489,26 @@ def run_scale(args):
     per_launch_ms = ms / (N * args.steps)
     peak, peak_src = peaks()
     alg = src_bytes + dst_bytes
+    if chain:  # + the BGRA picture read back and the NV12 frame written by the compositor
+        alg += dst_bytes + dw * dh * 3 // 2
+        dst_bytes = dw * dh * 3 // 2
     achieved = alg / (per_launch_ms / 1e3) / 1e9
     line = {
         "metric": f"{sw}x{sh} {fmt_name} -> {dw}x{dh} bgra {filt_name} frames/sec (side workload, not the headline)", "value": round(value, 2), "unit": "frames/s",
         "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/u16 in, fp32 fused multiply-add arithmetic, u8 out", "data": "synthetic (uniform random codes, seeded)",
-        "config": {"workload": f"{args.workload}: {sw}x{sh} {fmt_name} -> {dw}x{dh} BGRA, {filt_name}, {N} frames per step over {N} distinct sources",
+        "config": {"workload": f"{args.workload}: {sw}x{sh} {fmt_name} -> {dw}x{dh} BGRA, {filt_name}, {N} frames per step over {N} distinct sources" +
+                               (" -> NV12 through the compositor's img_bgra_nv12 (BASELINE cfg 2's convert -> scale -> convert chain: 2 kernels + the table pre-pass per step)" if chain else ""),
                    "l2": f"{N * (src_bytes + dst_bytes) / 1e6:.0f} MB of distinct sources+targets per step (> 126 MB L2)" if N * (src_bytes + dst_bytes) > 126e6 else
                          f"{N * (src_bytes + dst_bytes) / 1e6:.0f} MB per step: FITS in the 126 MB L2 (the sources are re-read from L2, not HBM)",
-                   "bit_exact_vs_oracle": "tests/test_scale.py::test_gpu_scale_full_size"},
+                   "bit_exact_vs_oracle": "tests/test_scale.py::test_cfg2_chain_full_size" if chain else "tests/test_scale.py::test_gpu_scale_full_size"},
         "e2e": {"value": round(N * e2e_steps / (e_ms / 1e3), 2), "unit": "frames/s", "h2d_bytes_per_step": N * src_bytes, "d2h_bytes_per_step": N * dst_bytes,
                 "steps": e2e_steps, "ms_per_step": round(e_ms / e2e_steps, 4)},
         "gpu_launches": int(launches), "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
-                     "kernel": "svb_scale_convert", "kernel_ms_per_launch": round(per_launch_ms, 4), "algorithmic_bytes_per_launch": alg,
-                     "note": "launch time = step time / launches (back to back on one stream, gaps included)"},
+                     "kernel": "svb_scale_convert" + (" + svb_mix_ring" if chain else ""), "kernel_ms_per_launch": round(per_launch_ms, 4), "algorithmic_bytes_per_launch": alg,
+                     "note": ("per FRAME of the chain (scale launch + its share of the compose launch), = step time / frames" if chain else
+                              "launch time = step time / launches (back to back on one stream, gaps included)")},
     }
     if not args.no_cpu_baseline and SW.available():
         # libswscale, the comparator BASELINE.json names, one SwsContext per host thread, default (fast) mode
@@ -632,14 +650,15 @@ def main():
                          "whatever they cover)")
     ap.add_argument("--format", default="nv12", choices=["nv12", "y420p"], help="side experiment, not the headline: y420p layers and target (the Linux Composer's format)")
     ap.add_argument("--rgba-pips", type=int, default=0, help="side experiment, not the headline: the topmost N pictures-in-picture are RGBA overlays")
-    ap.add_argument("--workload", default="cfg4", choices=["cfg4", "cfg3", "cfg2mix", "cfg5", "cfg2"],
+    ap.add_argument("--workload", default="cfg4", choices=["cfg4", "cfg3", "cfg2mix", "cfg5", "cfg2", "cfg2chain"],
                     help="cfg4 (default) = the headline; cfg3 / cfg2mix = BASELINE.md's other compositor rows through the same code; "
-                         "cfg5 / cfg2 = the convert+scale operator's side workloads (1 GPU, our arm only)")
+                         "cfg5 / cfg2 = the convert+scale operator's side workloads (1 GPU, our arm only); cfg2chain = cfg 2's whole chain: convert+scale to BGRA, then "
+                         "img_bgra_nv12 through the compositor")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.workload in ("cfg3", "cfg2mix"):
         configure_workload(args.workload)
-    if args.workload in ("cfg5", "cfg2") and args.impl == "ours":
+    if args.workload in ("cfg5", "cfg2", "cfg2chain") and args.impl == "ours":
         run_scale(args)
     elif args.impl == "reference":
         run_reference(args)

@@ -69,7 +69,9 @@ typedef enum svb_compute_kernel {
     SVB_KERNEL_IMG_NV12_NV12 = 0, SVB_KERNEL_IMG_BGRA_NV12, SVB_KERNEL_IMG_RGBA_NV12, SVB_KERNEL_IMG_BGRA_BGRA,
     SVB_KERNEL_IMG_Y420P_Y420P, SVB_KERNEL_IMG_Y420P_NV12, SVB_KERNEL_IMG_CLEAR_NV12, SVB_KERNEL_IMG_CLEAR_YUVS,
     SVB_KERNEL_IMG_CLEAR_BGRA, SVB_KERNEL_IMG_CLEAR_Y420P, SVB_KERNEL_IMG_CLEAR_RGBA, SVB_KERNEL_IMG_RGBA_Y420P,
-    SVB_KERNEL_IMG_BGRA_Y420P, SVB_KERNEL_SND_S16I_S16I, SVB_KERNEL_ME_FULLSEARCH, SVB_KERNEL_CUSTOM
+    SVB_KERNEL_IMG_BGRA_Y420P, SVB_KERNEL_SND_S16I_S16I, SVB_KERNEL_ME_FULLSEARCH, SVB_KERNEL_CUSTOM,
+    /* ours: sources the reference's PixelFormat names but has no kernel for, named by findKernel's own rule */
+    SVB_KERNEL_IMG_NV21_NV12, SVB_KERNEL_IMG_Y422P_NV12, SVB_KERNEL_IMG_Y444P_NV12, SVB_KERNEL_IMG_Y422P_Y420P, SVB_KERNEL_IMG_Y444P_Y420P
 } svb_compute_kernel;
 
 /* VideoMixer compose strategy (ours; the reference only has the per-layer sequence) */

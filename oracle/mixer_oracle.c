@@ -106,6 +106,31 @@ int64_t svo_layout(svo_image* img, int32_t format, int32_t width, int32_t height
         img->planes[0] = (svo_plane){base ? base : 0, width, height, width * 4, 4};
         off = (int64_t)width * 4 * height;
         break;
+    /* ---- extensions: layouts by analogy with the cases above (componentsForPlane, sample.pict.swift:84-96) ---- */
+    case SVO_NV21:
+        img->nplanes = 2;
+        img->planes[0] = (svo_plane){base ? base : 0, width, height, width, 1};
+        off = (int64_t)width * height;
+        img->planes[1] = (svo_plane){base ? base + off : 0, width / 2, height / 2, width, 2};
+        off += (int64_t)width * (height / 2);
+        break;
+    case SVO_Y422P:
+    case SVO_Y444P: {
+        const int cw = format == SVO_Y444P ? width : width / 2;
+        img->nplanes = 3;
+        img->planes[0] = (svo_plane){base ? base : 0, width, height, width, 1};
+        off = (int64_t)width * height;
+        img->planes[1] = (svo_plane){base ? base + off : 0, cw, height, cw, 1};
+        off += (int64_t)cw * height;
+        img->planes[2] = (svo_plane){base ? base + off : 0, cw, height, cw, 1};
+        off += (int64_t)cw * height;
+        break;
+    }
+    case SVO_YUVS: /* packed 4:2:2, two bytes per pixel (sample.pict.linux.swift:283) */
+        img->nplanes = 1;
+        img->planes[0] = (svo_plane){base ? base : 0, width, height, width * 2, 2};
+        off = (int64_t)width * 2 * height;
+        break;
     default:
         return SVO_ERR_BAD_INPUT;
     }
@@ -136,9 +161,39 @@ int svo_clear(svo_image* t) {
             }
         }
         return SVO_OK;
+    case SVO_YUVS: /* EXTENSION, unpinned: img_clear_yuvs is named (compute.swift:58) but has no body anywhere; cleared like the other YUV
+                      targets -- luma (even bytes: y cb y cr, sample.pict.swift:91-92) 0, chroma 0.5 */
+        for (int y = 0; y < t->height; ++y) {
+            uint8_t* row = t->planes[0].data + (int64_t)y * t->planes[0].stride;
+            for (int x = 0; x < t->width; ++x) {
+                row[2 * x + 0] = rte8(0.0f);
+                row[2 * x + 1] = rte8(0.5f);
+            }
+        }
+        return SVO_OK;
     default:
         return SVO_ERR_BAD_TARGET;
     }
+}
+
+/* ---- EXTENSION, pinned only by the text it restates: img_bgra_bgra exists upstream as a Metal body alone (kernels.metal:51-62, marked
+ * "TODO: apply transformations"): nearest texel at trunc(gid * inputSize / outputSize), source-over with the source's own alpha, alpha 1
+ * out.  Metal's BGRA8Unorm read/write swizzle cancels, so the arithmetic is per byte; UNORM8 conversions as everywhere else here. */
+int svo_apply_bgra_bgra(svo_image* t, const svo_image* s, const svo_uniforms* un) {
+    if (t->format != SVO_BGRA || s->format != SVO_BGRA) return SVO_ERR_KERNEL_NOT_FOUND;
+    const float sx = un->inSize[0] / un->outSize[0], sy = un->inSize[1] / un->outSize[1];
+    for (int y = 0; y < t->height; ++y)
+        for (int x = 0; x < t->width; ++x) {
+            int ix = (int)((float)x * sx), iy = (int)((float)y * sy);
+            if (ix > s->width - 1) ix = s->width - 1;
+            if (iy > s->height - 1) iy = s->height - 1;
+            const uint8_t* in = s->planes[0].data + (int64_t)iy * s->planes[0].stride + 4 * ix;
+            uint8_t* out = t->planes[0].data + (int64_t)y * t->planes[0].stride + 4 * x;
+            const float a = (float)in[3] / 255.0f;
+            for (int c = 0; c < 3; ++c) out[c] = rte8(((float)in[c] / 255.0f) * a + ((float)out[c] / 255.0f) * (1.0f - a));
+            out[3] = 255;
+        }
+    return SVO_OK;
 }
 
 /* ---- one work-item of img_<src>_<dst> -------------------------------------------------- */
@@ -182,8 +237,8 @@ static void work_item(svo_image* t, const svo_image* s, const svo_uniforms* un, 
     float curC[2] = {0.f, 0.f};
     if (chroma) cur_chroma(t, x, y, curC); /* :80-83 */
 
-    if (s->format == SVO_NV12 || s->format == SVO_Y420P) {
-        /* img_nv12_nv12 :84-105, img_y420p_nv12 :149-170, img_y420p_y420p :228-252 */
+    if (s->format == SVO_NV12 || s->format == SVO_Y420P || s->format == SVO_NV21 || s->format == SVO_Y422P || s->format == SVO_Y444P) {
+        /* img_nv12_nv12 :84-105, img_y420p_nv12 :149-170, img_y420p_y420p :228-252 (and, as extensions, the same body over NV21 / 4:2:2 / 4:4:4 planes) */
         if (in01(tx[0], tx[1]) && in01(uv[0], uv[1])) {
             float luma[4], alpha = un->opacity;
             lin(&s->planes[0], uv[0], uv[1], luma);
@@ -194,6 +249,10 @@ static void work_item(svo_image* t, const svo_image* s, const svo_uniforms* un, 
                     lin(&s->planes[1], uv[0], uv[1], tmp);
                     cb = tmp[0];
                     cr = tmp[1];
+                } else if (s->format == SVO_NV21) { /* extension: (Cr, Cb) pairs */
+                    lin(&s->planes[1], uv[0], uv[1], tmp);
+                    cb = tmp[1];
+                    cr = tmp[0];
                 } else {
                     lin(&s->planes[1], uv[0], uv[1], tmp);
                     cb = tmp[0];
@@ -246,7 +305,8 @@ static int check_pair(const svo_image* t, const svo_image* s) {
         return SVO_ERR_KERNEL_NOT_FOUND; /* no img_*_bgra kernel exists on Linux (compute.swift:54) */
     if (s->format == SVO_NV12 && t->format == SVO_Y420P)
         return SVO_ERR_KERNEL_NOT_FOUND; /* img_nv12_y420p is not in the enum (compute.swift:49-63) */
-    if (s->format < SVO_NV12 || s->format > SVO_RGBA) return SVO_ERR_KERNEL_NOT_FOUND;
+    if (s->format == SVO_NV21 && t->format == SVO_Y420P) return SVO_ERR_KERNEL_NOT_FOUND; /* extension: like img_nv12_y420p, not offered */
+    if (s->format < SVO_NV12 || s->format > SVO_Y444P) return SVO_ERR_KERNEL_NOT_FOUND;
     if ((t->width & 1) || (t->height & 1)) return SVO_ERR_BAD_TARGET;
     return SVO_OK;
 }

@@ -51,7 +51,11 @@ typedef struct svo_uniforms {
 } svo_uniforms;
 
 /* PixelFormat cases that have kernels (sample.pict.swift:20-33). */
-enum { SVO_NV12 = 0, SVO_Y420P = 1, SVO_BGRA = 2, SVO_RGBA = 3 };
+enum { SVO_NV12 = 0, SVO_Y420P = 1, SVO_BGRA = 2, SVO_RGBA = 3,
+       /* EXTENSIONS -- PARITY UNPINNED: formats the reference's PixelFormat names (sample.pict.swift:22-27) but has no
+        * kernel for.  As sources they run the img_nv12_nv12 / img_y420p_* body over their own planes (NV21 = (Cr, Cb) pairs; 4:2:2 and 4:4:4
+        * chroma planes sampled at their own size); YUVS exists only as a clear target (img_clear_yuvs, compute.swift:58). */
+       SVO_NV21 = 4, SVO_Y422P = 5, SVO_Y444P = 6, SVO_YUVS = 7 };
 
 /* One Plane (sample.pict.swift:46-56) plus its bytes. width/height are the plane's own
  * size (chroma planes: W/2 x H/2), stride in bytes, ncomp = components per texel. */
@@ -76,6 +80,8 @@ enum {
 
 /* Fill planes[] for a contiguous allocation laid out as planesForFormat/buffersForPlanes do
  * (sample.pict.linux.swift:275-311).  Returns total bytes, or <0. base may be NULL (sizing). */
+/* EXTENSION: img_bgra_bgra after the Metal text (kernels.metal:51-62); both images BGRA */
+int svo_apply_bgra_bgra(svo_image* t, const svo_image* s, const svo_uniforms* u);
 int64_t svo_layout(svo_image* img, int32_t format, int32_t width, int32_t height, uint8_t* base);
 
 /* img_clear_{nv12,y420p,bgra}  (kernels.cl.swift:38-46,174-185,257-265). */

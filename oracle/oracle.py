@@ -13,7 +13,9 @@ import numpy as np
 HERE = Path(__file__).resolve().parent
 
 NV12, Y420P, BGRA, RGBA = 0, 1, 2, 3
-FORMAT_NAMES = {NV12: "nv12", Y420P: "y420p", BGRA: "bgra", RGBA: "rgba"}
+# extensions (parity unpinned, mixer_oracle.h): sources the reference names without a kernel, and the packed 4:2:2 clear target
+NV21, Y422P, Y444P, YUVS = 4, 5, 6, 7
+FORMAT_NAMES = {NV12: "nv12", Y420P: "y420p", BGRA: "bgra", RGBA: "rgba", NV21: "nv21", Y422P: "y422p", Y444P: "y444p", YUVS: "yuvs"}
 OK, ERR_KERNEL_NOT_FOUND, ERR_BAD_TARGET, ERR_BAD_INPUT = 0, -1, -2, -3
 
 
@@ -54,6 +56,13 @@ def plane_layout(fmt, w, h):
         return [(0, w, h, w, 1), (w * h, w // 2, h // 2, w // 2, 1), (w * h + c, w // 2, h // 2, w // 2, 1)], w * h + 2 * c
     if fmt in (BGRA, RGBA):
         return [(0, w, h, 4 * w, 4)], 4 * w * h
+    if fmt == NV21:
+        return [(0, w, h, w, 1), (w * h, w // 2, h // 2, w, 2)], w * h + w * (h // 2)
+    if fmt in (Y422P, Y444P):
+        cw = w if fmt == Y444P else w // 2
+        return [(0, w, h, w, 1), (w * h, cw, h, cw, 1), (w * h + cw * h, cw, h, cw, 1)], w * h + 2 * cw * h
+    if fmt == YUVS:
+        return [(0, w, h, 2 * w, 2)], 2 * w * h
     raise ValueError(fmt)
 
 
@@ -117,6 +126,13 @@ class _Lib:
     def apply(self, target, src, uniforms):
         t, s = target._c(), src._c()
         return getattr(self.lib, f"{self.prefix}_apply")(C.byref(t), C.byref(s), C.byref(uniforms))
+
+    def apply_bgra_bgra(self, target, src, uniforms):
+        """EXTENSION: img_bgra_bgra after upstream's Metal text (the restatement only)."""
+        fn = getattr(self.lib, f"{self.prefix}_apply_bgra_bgra")
+        fn.restype = C.c_int
+        t, s = target._c(), src._c()
+        return fn(C.byref(t), C.byref(s), C.byref(uniforms))
 
     def mix(self, target, layers, uniforms, threads=0):
         """clear + fold layers (already z-sorted) into target, in place. Returns the status code."""

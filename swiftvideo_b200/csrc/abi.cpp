@@ -146,7 +146,7 @@ svb_status svb_run_compute_kernel(svb_context* ctx, const svb_picture* const* im
             need(images[i], "image");
             im.push_back(images[i]->p.get());
         }
-        if (kernel < 0 || kernel > (int)ComputeKernel::custom) throw ComputeError(ErrorCode::invalidValue, "bad kernel id");
+        if (kernel < 0 || kernel >= (int)ComputeKernel::count_) throw ComputeError(ErrorCode::invalidValue, "bad kernel id");
         ctx->c = runComputeKernel(ctx->c, im, *target->p, (ComputeKernel)kernel, custom_name ? custom_name : "", max_planes, uniforms,
                                   uniforms_size, blends != 0);
     });
@@ -156,7 +156,7 @@ svb_status svb_apply_compute_image(svb_context* ctx, const svb_picture* image, c
         need(ctx, "ctx");
         need(image, "image");
         need(target, "target");
-        if (kernel < 0 || kernel > (int)ComputeKernel::custom) throw ComputeError(ErrorCode::invalidValue, "bad kernel id");
+        if (kernel < 0 || kernel >= (int)ComputeKernel::count_) throw ComputeError(ErrorCode::invalidValue, "bad kernel id");
         ctx->c = applyComputeImage(ctx->c, *image->p, *target->p, (ComputeKernel)kernel);
     });
 }

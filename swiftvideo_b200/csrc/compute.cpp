@@ -52,7 +52,8 @@ static const CuDriver& drv() {
 static const char* kKernelNames[] = {"img_nv12_nv12",  "img_bgra_nv12",  "img_rgba_nv12",  "img_bgra_bgra",   "img_y420p_y420p",
                                      "img_y420p_nv12", "img_clear_nv12", "img_clear_yuvs", "img_clear_bgra",  "img_clear_y420p",
                                      "img_clear_rgba", "img_rgba_y420p", "img_bgra_y420p", "snd_s16i_s16i",   "me_fullsearch",
-                                     "custom"};
+                                     "custom",         "img_nv21_nv12",  "img_y422p_nv12", "img_y444p_nv12",  "img_y422p_y420p",
+                                     "img_y444p_y420p"};
 
 const char* computeKernelName(ComputeKernel k) { return kKernelNames[(int)k]; }
 
@@ -64,7 +65,11 @@ ComputeKernel defaultComputeKernelFromString(const std::string& name) {  // comp
         {"img_clear_nv12", ComputeKernel::img_clear_nv12},   {"img_clear_yuvs", ComputeKernel::img_clear_yuvs},
         {"img_clear_bgra", ComputeKernel::img_clear_bgra},   {"img_clear_rgba", ComputeKernel::img_clear_bgra},  // :101
         {"img_rgba_y420p", ComputeKernel::img_rgba_y420p},   {"img_bgra_y420p", ComputeKernel::img_bgra_y420p},
-        {"img_clear_y420p", ComputeKernel::img_clear_y420p}};
+        {"img_clear_y420p", ComputeKernel::img_clear_y420p},
+        // ours: the sources upstream names without a kernel
+        {"img_nv21_nv12", ComputeKernel::img_nv21_nv12},     {"img_y422p_nv12", ComputeKernel::img_y422p_nv12},
+        {"img_y444p_nv12", ComputeKernel::img_y444p_nv12},   {"img_y422p_y420p", ComputeKernel::img_y422p_y420p},
+        {"img_y444p_y420p", ComputeKernel::img_y444p_y420p}};
     auto it = m.find(name);
     if (it == m.end()) throw ComputeError(ErrorCode::invalidValue, "no default compute kernel named " + name);
     return it->second;
@@ -494,6 +499,16 @@ std::vector<Plane> planesForFormat(PixelFormat f, Vector2 size) {  // sample.pic
         return {Plane{size, width * 2, 8, {Component::y, Component::cb, Component::y, Component::cr}}};
     case PixelFormat::y420p:
         return {Plane{size, width, 8, {Component::y}}, Plane{half, width / 2, 8, {Component::cb}}, Plane{half, width / 2, 8, {Component::cr}}};
+    // ours: upstream's planesForFormat throws for these three (it has no kernels for them); the layouts follow componentsForPlane
+    // (sample.pict.swift:84-90) and the tight strides of the cases above
+    case PixelFormat::nv21:
+        return {Plane{size, width, 8, {Component::y}}, Plane{half, width, 8, {Component::cr, Component::cb}}};
+    case PixelFormat::y422p: {
+        const Vector2 c{size.x / 2, size.y};
+        return {Plane{size, width, 8, {Component::y}}, Plane{c, width / 2, 8, {Component::cb}}, Plane{c, width / 2, 8, {Component::cr}}};
+    }
+    case PixelFormat::y444p:
+        return {Plane{size, width, 8, {Component::y}}, Plane{size, width, 8, {Component::cb}}, Plane{size, width, 8, {Component::cr}}};
     default:
         throw ComputeError(ErrorCode::badInputData, "Invalid pixel format");
     }
@@ -765,7 +780,8 @@ ComputeContext runComputeKernel(const ComputeContext& ctxIn, const std::vector<c
     if (target.imgBuffer.planes.empty() || target.imgBuffer.computeTextures.empty()) throw ComputeError(ErrorCode::badTarget, "badTarget");
     if (kernel != ComputeKernel::custom)  // the built-in kernels derive the output pitch from the launch size, as upstream's do
         for (const Plane& p : target.imgBuffer.planes)
-            if (p.stride != (int)p.size.x * (int)p.components.size())
+            // (the packed 4:2:2 formats list the four components of a two-pixel group, sample.pict.linux.swift:283-285: two bytes per pixel)
+            if (p.stride != (int)p.size.x * (target.pixelFormat() == PixelFormat::yuvs || target.pixelFormat() == PixelFormat::zvuy ? 2 : (int)p.components.size()))
                 throw ComputeError(ErrorCode::badTarget, "badTarget: the per-layer kernels need a target without row padding");
     ComputeContext ctx = maybeBuildKernel(ctxIn, kernel, customName);
     const std::string name = kernel == ComputeKernel::custom ? customName : computeKernelName(kernel);

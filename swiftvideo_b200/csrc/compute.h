@@ -68,6 +68,13 @@ enum class ComputeKernel : int {
     snd_s16i_s16i,
     me_fullsearch,
     custom,
+    // ours: sources upstream's PixelFormat names but has no kernel for, under findKernel's own img_<source>_<target> rule;
+    // after `custom` so that the upstream cases keep their order
+    img_nv21_nv12,
+    img_y422p_nv12,
+    img_y444p_nv12,
+    img_y422p_y420p,
+    img_y444p_y420p,
     count_
 };
 const char* computeKernelName(ComputeKernel k);                          // String(describing:)

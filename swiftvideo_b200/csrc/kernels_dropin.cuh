@@ -53,11 +53,11 @@ __device__ __forceinline__ Src make_src(int format, const uint8_t* p0, const uin
     s.p[2] = p2;
     s.w = (int)__ldg(&U->inSize[0]);
     s.h = (int)__ldg(&U->inSize[1]);
-    s.cw = s.w / 2;
-    s.ch = s.h / 2;
+    s.cw = SVB_FORMAT_CHROMA_W(format, s.w);
+    s.ch = SVB_FORMAT_CHROMA_H(format, s.h);
     s.stride[0] = __ldg(inStride);
-    s.stride[1] = format == SVB_NV12 || format == SVB_Y420P ? __ldg(inStride + 1) : 0;
-    s.stride[2] = format == SVB_Y420P ? __ldg(inStride + 2) : 0;
+    s.stride[1] = SVB_FORMAT_IS_YUV(format) ? __ldg(inStride + 1) : 0;
+    s.stride[2] = SVB_FORMAT_IS_YUV(format) && !SVB_FORMAT_IS_SEMIPLANAR(format) ? __ldg(inStride + 2) : 0;
     return s;
 }
 
@@ -113,6 +113,57 @@ __global__ void img_bgra_y420p(uint8_t* oY, uint8_t* oU, uint8_t* oV, const uint
 __global__ void img_rgba_y420p(uint8_t* oY, uint8_t* oU, uint8_t* oV, const uint8_t* iP, const ImageUniforms* U,
                                const int* inStride) {
     svb::dropin_blend<SVB_Y420P>(oY, oU, oV, svb::make_src(SVB_RGBA, iP, nullptr, nullptr, U, inStride), U);
+}
+
+// ---- operators the reference names but has no OpenCL / CUDA kernel for ------------------------------------------
+// Sources: the same body as img_nv12_nv12 / img_y420p_* with the source's own plane plumbing (the sampler works on each plane's own size,
+// so 4:2:2 and 4:4:4 chroma need nothing else).  Names follow findKernel's img_<source>_<target> rule (mix.video.swift:142-146).
+__global__ void img_nv21_nv12(uint8_t* oY, uint8_t* oC, const uint8_t* iY, const uint8_t* iC, const ImageUniforms* U, const int* inStride) {
+    svb::dropin_blend<SVB_NV12>(oY, oC, nullptr, svb::make_src(SVB_NV21, iY, iC, nullptr, U, inStride), U);
+}
+__global__ void img_y422p_nv12(uint8_t* oY, uint8_t* oC, const uint8_t* iY, const uint8_t* iU, const uint8_t* iV, const ImageUniforms* U, const int* inStride) {
+    svb::dropin_blend<SVB_NV12>(oY, oC, nullptr, svb::make_src(SVB_Y422P, iY, iU, iV, U, inStride), U);
+}
+__global__ void img_y444p_nv12(uint8_t* oY, uint8_t* oC, const uint8_t* iY, const uint8_t* iU, const uint8_t* iV, const ImageUniforms* U, const int* inStride) {
+    svb::dropin_blend<SVB_NV12>(oY, oC, nullptr, svb::make_src(SVB_Y444P, iY, iU, iV, U, inStride), U);
+}
+__global__ void img_y422p_y420p(uint8_t* oY, uint8_t* oU, uint8_t* oV, const uint8_t* iY, const uint8_t* iU, const uint8_t* iV, const ImageUniforms* U,
+                                const int* inStride) {
+    svb::dropin_blend<SVB_Y420P>(oY, oU, oV, svb::make_src(SVB_Y422P, iY, iU, iV, U, inStride), U);
+}
+__global__ void img_y444p_y420p(uint8_t* oY, uint8_t* oU, uint8_t* oV, const uint8_t* iY, const uint8_t* iU, const uint8_t* iV, const ImageUniforms* U,
+                                const int* inStride) {
+    svb::dropin_blend<SVB_Y420P>(oY, oU, oV, svb::make_src(SVB_Y444P, iY, iU, iV, U, inStride), U);
+}
+
+// img_bgra_bgra: the only text upstream has is the Metal body (kernels.metal:51-62, "TODO: apply transformations"): the source texel at
+// trunc(gid * inputSize / outputSize) -- no filtering, no transform -- laid source-over onto the target with the source's own alpha, result
+// alpha 1.  Metal reads a BGRA8Unorm texture as (r, g, b, a) = bytes (2, 1, 0, 3) / 255 and writes with round-to-nearest-even; the channel
+// order cancels out (the same swizzle on the way in and out), so the arithmetic is per byte.
+__global__ void img_bgra_bgra(uint8_t* o, const uint8_t* i, const ImageUniforms* U, const int* inStride) {
+    using namespace svb;
+    const int W = gridDim.x * blockDim.x;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    const float sx = __fdiv_rn(__ldg(&U->inSize[0]), __ldg(&U->outSize[0])), sy = __fdiv_rn(__ldg(&U->inSize[1]), __ldg(&U->outSize[1]));
+    const int ix = min((int)mul((float)x, sx), (int)__ldg(&U->inSize[0]) - 1), iy = min((int)mul((float)y, sy), (int)__ldg(&U->inSize[1]) - 1);
+    const uchar4 in = *(const uchar4*)(i + (size_t)iy * __ldg(inStride) + 4 * ix);
+    uchar4* const out = (uchar4*)o + (size_t)y * W + x;
+    const uchar4 cur = *out;
+    const float a = unorm(opaque(in.w)), na = sub(1.f, a);
+    uchar4 r;
+    r.x = (uint8_t)rte8(add(mul(unorm(opaque(in.x)), a), mul(unorm(opaque(cur.x)), na)));
+    r.y = (uint8_t)rte8(add(mul(unorm(opaque(in.y)), a), mul(unorm(opaque(cur.y)), na)));
+    r.z = (uint8_t)rte8(add(mul(unorm(opaque(in.z)), a), mul(unorm(opaque(cur.z)), na)));
+    r.w = 255;
+    *out = r;
+}
+
+// img_clear_yuvs: named in the enum (compute.swift:58), no body anywhere upstream.  'yuvs' is packed 4:2:2, two bytes per pixel, luma in the
+// even bytes (componentsForPlane, sample.pict.swift:91-92: y cb y cr); cleared like the other YUV targets: Y = 0, chroma = 0.5 -> 128.
+__global__ void img_clear_yuvs(uint8_t* __restrict__ o) {
+    const int W = gridDim.x * blockDim.x;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    ((uchar2*)o)[(size_t)y * W + x] = make_uchar2(0, 128);
 }
 
 }  // extern "C"

@@ -21,8 +21,8 @@ __device__ __forceinline__ Src layer_src(const SvbLayerDesc* __restrict__ L) {
     s.stride[2] = L->stride[2];
     s.w = L->width;
     s.h = L->height;
-    s.cw = L->width / 2;
-    s.ch = L->height / 2;
+    s.cw = SVB_FORMAT_CHROMA_W(L->format, L->width);
+    s.ch = SVB_FORMAT_CHROMA_H(L->format, L->height);
     return s;
 }
 

@@ -144,6 +144,9 @@ int svbFormat(PixelFormat f) {
     case PixelFormat::y420p: return SVB_Y420P;
     case PixelFormat::BGRA: return SVB_BGRA;
     case PixelFormat::RGBA: return SVB_RGBA;
+    case PixelFormat::nv21: return SVB_NV21;
+    case PixelFormat::y422p: return SVB_Y422P;
+    case PixelFormat::y444p: return SVB_Y444P;
     default: return -1;
     }
 }
@@ -299,13 +302,14 @@ FramePlan planFrame(const ComputeContext& ctx, const PictureSample& target, cons
         SvbLayerDesc& L = F.layers[F.nlayers++];
         if (cached && cached[k]) {  // planned before for this very sample and a target of this size
             L = *cached[k];
+            if (L.format >= SVB_NV21) plan.tiledOk = false;
             continue;
         }
         const PictureSample& img = *layers[k];
         const int sf = svbFormat(img.pixelFormat());
         if (sf < 0) throw ComputeError(ErrorCode::computeKernelNotFound, std::string("computeKernelNotFound(img_") + pixelFormatName(img.pixelFormat()) + "_" + pixelFormatName(target.pixelFormat()) + ")");
         if (img.bufferType() != BufferType::gpu) throw ComputeError(ErrorCode::badInputData, "Input images must be uploaded to GPU");
-        const size_t snp = sf == SVB_NV12 ? 2 : (sf == SVB_Y420P ? 3 : 1);
+        const size_t snp = SVB_FORMAT_IS_SEMIPLANAR(sf) ? 2 : (SVB_FORMAT_IS_YUV(sf) ? 3 : 1);
         if (img.imgBuffer.computeTextures.size() < snp || img.imgBuffer.planes.size() < snp) throw ComputeError(ErrorCode::badInputData, "Bad input image");
         std::memcpy(&L.u, &uniforms[k], sizeof(ImageUniforms));
         L.u.pad_ = 0.f;
@@ -316,6 +320,7 @@ FramePlan planFrame(const ComputeContext& ctx, const PictureSample& target, cons
         L.width = (int)img.imgBuffer.planes[0].size.x;
         L.height = (int)img.imgBuffer.planes[0].size.y;
         L.format = sf;
+        if (sf >= SVB_NV21) plan.tiledOk = false;  // the tile compositors know the reference's four source formats; these go through svb_mix_generic
         const SvbUniforms& u = L.u;
         const float *T = u.transform, *X = u.textureTx, *B = u.borderMatrix;
         const bool finite = finite16(T) && finite16(X) && finite16(B) && std::isfinite(u.opacity);

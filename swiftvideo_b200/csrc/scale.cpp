@@ -22,7 +22,7 @@ static const CuDriver& drv() {
 
 namespace {
 
-constexpr int kTileW = SVB_SCALE_TW, kTileH = SVB_SCALE_TH, kMaxTaps = SVB_SCALE_MAX_TAPS;
+constexpr int kTileW = SVB_SCALE_TW, kTileH = SVB_SCALE_TH;
 
 double filterWeight(ScaleFilter f, double t) {
     t = std::fabs(t);
@@ -36,12 +36,23 @@ double filterWeight(ScaleFilter f, double t) {
 struct DeviceTable {
     ScaleTable host;
     CUdeviceptr first = 0, weights = 0;
-    int span32 = 0, span64 = 0;  // most source samples any aligned run of kTileH (span32) / kTileW (span64) consecutive outputs reaches
+    // most source samples any aligned run of `run` consecutive outputs reaches; with chunk > 1 the window starts at a multiple
+    // of `chunk` samples and covers whole chunks (the kernel stages 16-byte chunks)
+    int span(int run, int chunk = 1) const {
+        int best = 0;
+        const int n = (int)host.first.size();
+        for (int a = 0; a < n; a += run) {
+            const int b = std::min(a + run, n) - 1;
+            const int lo = host.first[(size_t)a] & ~(chunk - 1), hi = host.first[(size_t)b] + host.taps - 1;
+            best = std::max(best, ((hi - lo) / chunk + 1) * chunk);
+        }
+        return best;
+    }
 };
 struct ScaleShared {
     std::mutex mu;
     std::map<std::array<int, 3>, DeviceTable> tables;
-    CUfunction fn = nullptr;
+    CUfunction fn = nullptr, fnAny = nullptr;  // compile-time window pitches / pitches from the descriptor
 };
 
 void freeScaleShared(InternalContext* ic) {
@@ -60,7 +71,9 @@ ScaleShared& shared(const std::shared_ptr<InternalContext>& ic) {  // caller hol
     if (!ic->scaleShared) {
         auto* s = new ScaleShared();
         s->fn = ic->builtin("svb_scale_convert");
+        s->fnAny = ic->builtin("svb_scale_convert_any");
         check(drv().cuFuncSetAttribute(s->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, 200 * 1024), "cuFuncSetAttribute(max dynamic shared memory)");
+        check(drv().cuFuncSetAttribute(s->fnAny, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, 200 * 1024), "cuFuncSetAttribute(max dynamic shared memory)");
         ic->scaleShared = s;
         ic->scaleSharedFree = freeScaleShared;
     }
@@ -75,14 +88,6 @@ const DeviceTable& deviceTable(const std::shared_ptr<InternalContext>& ic, Scale
     if (it != sh.tables.end()) return it->second;
     DeviceTable t;
     t.host = makeScaleTable(f, srcN, dstN);
-    for (int a = 0; a < dstN; a += kTileH) {
-        const int b = std::min(a + kTileH, dstN) - 1;
-        t.span32 = std::max(t.span32, t.host.first[b] + t.host.taps - t.host.first[a]);
-    }
-    for (int a = 0; a < dstN; a += kTileW) {
-        const int b = std::min(a + kTileW, dstN) - 1;
-        t.span64 = std::max(t.span64, t.host.first[b] + t.host.taps - t.host.first[a]);
-    }
     check(drv().cuMemAlloc(&t.first, sizeof(int32_t) * (size_t)dstN), "cuMemAlloc");
     check(drv().cuMemAlloc(&t.weights, sizeof(float) * t.host.weights.size()), "cuMemAlloc");
     check(drv().cuMemcpyHtoD(t.first, t.host.first.data(), sizeof(int32_t) * (size_t)dstN), "cuMemcpyHtoD");
@@ -140,12 +145,31 @@ PictureSample scaleConvertPicture(const ComputeContext& ctx, const PictureSample
     const DeviceTable& yy = deviceTable(ctx.ctx, sh, filter, srcH, dstH);
     const DeviceTable& cx = deviceTable(ctx.ctx, sh, filter, srcW / 2, dstW);
     const DeviceTable& cy = deviceTable(ctx.ctx, sh, filter, srcH / 2, dstH);
-    if (std::max(std::max(yx.host.taps, yy.host.taps), std::max(cx.host.taps, cy.host.taps)) > kMaxTaps)
-        throw ComputeError(ErrorCode::notImplemented, "scaleConvertPicture: this ratio needs more than 16 filter taps");
-    // filtered rows (luma + U + V, 64 floats each) + the staged source window (luma, reused for the two chroma components)
-    const size_t window = std::max((size_t)yy.span32 * (size_t)yx.span64, 2 * (size_t)cy.span32 * (size_t)cx.span64);
-    const size_t smem = (((size_t)yy.span32 + 2 * (size_t)cy.span32) * kTileW + window) * sizeof(float);
-    if (smem > 200 * 1024) throw ComputeError(ErrorCode::notImplemented, "scaleConvertPicture: vertical footprint too large for one tile");
+    // Shared memory of one CTA: the horizontally filtered rows (luma + U + V, 64 floats each, row counts rounded up to 4) and the
+    // transposed source window (luma, reused for the two chroma components).  The tile is 16 output rows high unless the vertical
+    // footprint of a strong minification needs a shorter one to fit; beyond that the ratio is refused.
+    const bool p010 = sf == PixelFormat::p010;
+    const int chunkY = p010 ? 8 : 16, chunkC = p010 ? 4 : 8;  // samples / (U, V) pairs per 16 bytes
+    const int spanYx = yx.span(kTileW, chunkY), spanCx = cx.span(kTileW, chunkC);
+    auto pitchOf = [](int rows) {  // 16-byte aligned columns; an odd number of 16-byte groups spreads the columns over the banks
+        int p = (rows + 3) & ~3;
+        return ((p >> 2) & 1) ? p : p + 4;
+    };
+    int tileH = kTileH, spanYy = 0, spanCy = 0, pitchY = 0, pitchC = 0;
+    size_t smem = 0;
+    bool fixedPitch = false;
+    for (;; tileH >>= 1) {
+        spanYy = yy.span(tileH), spanCy = cy.span(tileH);
+        // the kernel with compile-time pitches when the tile's rows fit them (every ratio down to 2 : 1 Lanczos-3 at 16 rows)
+        fixedPitch = ((spanYy + 3) & ~3) <= SVB_SCALE_PITCH_Y && ((spanCy + 3) & ~3) <= SVB_SCALE_PITCH_C;
+        pitchY = fixedPitch ? SVB_SCALE_PITCH_Y : pitchOf(spanYy), pitchC = fixedPitch ? SVB_SCALE_PITCH_C : pitchOf(spanCy);
+        const size_t window = std::max((size_t)spanYx * (size_t)pitchY, 2 * (size_t)spanCx * (size_t)pitchC);
+        smem = ((size_t)(2 * kTileH * 16) + (size_t)(((spanYy + 3) & ~3) + 2 * ((spanCy + 3) & ~3)) * SVB_SCALE_HP + window) * sizeof(float);
+        if (smem <= 200 * 1024 || tileH == 1) break;
+    }
+    if (smem > 200 * 1024)
+        throw ComputeError(ErrorCode::notImplemented, "scaleConvertPicture: the filter footprint of this ratio (" + std::to_string(yy.host.taps) + " x " +
+                                                          std::to_string(yx.host.taps) + " taps) does not fit one tile");
 
     PictureSample out;
     out.imgBuffer.planes = planesForFormat(PixelFormat::BGRA, dstSize);
@@ -167,13 +191,18 @@ PictureSample scaleConvertPicture(const ComputeContext& ctx, const PictureSample
     desc.srcW = srcW, desc.srcH = srcH, desc.dstW = dstW, desc.dstH = dstH;
     desc.format = sf == PixelFormat::p010 ? 1 : 0;
     desc.nYx = yx.host.taps, desc.nYy = yy.host.taps, desc.nCx = cx.host.taps, desc.nCy = cy.host.taps;
-    desc.spanYy = yy.span32, desc.spanCy = cy.span32, desc.spanYx = yx.span64, desc.spanCx = cx.span64;
+    desc.spanYy = spanYy, desc.spanCy = spanCy, desc.spanYx = spanYx, desc.spanCx = spanCx;
+    desc.pitchY = pitchY, desc.pitchC = pitchC, desc.tileH = tileH;
+    // 16-byte accesses need an aligned base and stride, and rows long enough to read the chunk that holds the last sample
+    desc.vecY = (desc.srcY % 16 == 0 && desc.strideY % 16 == 0 && desc.strideY >= ((srcW + chunkY - 1) / chunkY) * 16) ? 1 : 0;
+    desc.vecC = (desc.srcC % 16 == 0 && desc.strideC % 16 == 0 && desc.strideC >= ((srcW / 2 + chunkC - 1) / chunkC) * 16) ? 1 : 0;
+    desc.vecDst = (desc.dst % 16 == 0 && desc.dstStride % 16 == 0) ? 1 : 0;
 
     if (src.done) check(d.cuStreamWaitEvent(ic.compute, src.done->e, 0), "cuStreamWaitEvent");
     for (const auto& t : src.imgBuffer.computeTextures)
         if (t->ready) check(d.cuStreamWaitEvent(ic.compute, t->ready->e, 0), "cuStreamWaitEvent");
     void* args[] = {&desc};
-    check(d.cuLaunchKernel(sh.fn, (unsigned)((dstW + kTileW - 1) / kTileW), (unsigned)((dstH + kTileH - 1) / kTileH), 1, 256, 1, 1, (unsigned)smem, ic.compute, args, nullptr),
+    check(d.cuLaunchKernel(fixedPitch ? sh.fn : sh.fnAny, (unsigned)((dstW + kTileW - 1) / kTileW), (unsigned)((dstH + tileH - 1) / tileH), 1, 256, 1, 1, (unsigned)smem, ic.compute, args, nullptr),
           "cuLaunchKernel(svb_scale_convert)");
     noteKernelLaunch();
     markWritten(ctx, out);

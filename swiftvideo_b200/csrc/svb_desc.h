@@ -26,7 +26,14 @@
 #define SVB_BOX_C_BYTES (SVB_TILE_H * 384)
 #endif
 
-enum SvbFormat { SVB_NV12 = 0, SVB_Y420P = 1, SVB_BGRA = 2, SVB_RGBA = 3 };
+// 0..3: the formats the reference has kernels for.  4..6: sources the reference's PixelFormat names (sample.pict.swift:22-27) but has no kernel
+// for -- composed by the generic and per-layer kernels: NV21 = NV12 with (Cr, Cb) pairs, Y422P / Y444P = three planes with
+// chroma at half width / full size.
+enum SvbFormat { SVB_NV12 = 0, SVB_Y420P = 1, SVB_BGRA = 2, SVB_RGBA = 3, SVB_NV21 = 4, SVB_Y422P = 5, SVB_Y444P = 6 };
+#define SVB_FORMAT_IS_YUV(f) ((f) == SVB_NV12 || (f) == SVB_Y420P || (f) >= SVB_NV21)
+#define SVB_FORMAT_IS_SEMIPLANAR(f) ((f) == SVB_NV12 || (f) == SVB_NV21)
+#define SVB_FORMAT_CHROMA_W(f, w) ((f) == SVB_Y444P ? (w) : (w) / 2)
+#define SVB_FORMAT_CHROMA_H(f, h) ((f) == SVB_Y444P || (f) == SVB_Y422P ? (h) : (h) / 2)
 
 enum {
     SVB_FRAME_LOAD_CUR = 1,   // continue an earlier pass: start from the target's bytes, not from clear
@@ -162,7 +169,14 @@ typedef struct __attribute__((aligned(16))) SvbTilePlan {
 #ifndef SVB_SCALE_TH
 #define SVB_SCALE_TH 16  // 16 rows: 47 KB of shared memory per CTA at 4K -> 1080p Lanczos (4 CTAs per SM); 32 rows halve the halo but leave 2 CTAs per SM (92 vs 66 us)
 #endif
-#define SVB_SCALE_MAX_TAPS 16
+// row pitches (floats) of the transposed source windows when the tile's vertical footprint allows the compile-time ones: multiples of 4
+// (16-byte aligned columns) whose quarter is odd (columns spread over the banks).  44 = 16 rows x 2 + 12 taps: 2 : 1 Lanczos-3.
+// pitch (floats) of the horizontally filtered rows: the tile width + 4, so that the two row groups a warp of the horizontal pass writes
+// (rows 4 apart) land 16 banks apart
+#define SVB_SCALE_HP (SVB_SCALE_TW + 4)
+#define SVB_SCALE_PITCH_Y 44
+#define SVB_SCALE_PITCH_C 28
+#define SVB_SCALE_MAX_TAPS 16  // tap counts up to this are compiled per count; larger ones loop at run time
 
 // svb_scale_convert (kernels_scale.cuh): NV12 / P010 -> BGRA with a separable resize, passed by value as the kernel argument.
 // Tables per axis and plane kind (Y = luma plane, C = chroma plane): first[dstN] = first source index of each output
@@ -174,8 +188,11 @@ typedef struct SvbScaleDesc {
     int32_t srcW, srcH, dstW, dstH;
     int32_t format;          // 0 NV12, 1 P010 (10 bits in the MSBs of little-endian 16-bit words)
     int32_t nYx, nYy, nCx, nCy;
-    int32_t spanYy, spanCy;  // most source rows (luma / chroma) one 32-row output tile reaches: shared-memory sizing
-    int32_t spanYx, spanCx;  // most source columns one 64-column output tile reaches = pitch of the staged window
+    int32_t spanYy, spanCy;  // most source rows (luma / chroma) one tileH-row output tile reaches: shared-memory sizing
+    int32_t spanYx, spanCx;  // most source columns (chunk-aligned) one 64-column output tile stages
+    int32_t pitchY, pitchC;  // row pitch (floats) of the transposed windows: a multiple of 4 whose quarter is odd
+    int32_t tileH;           // output rows per CTA (<= SVB_SCALE_TH)
+    int32_t vecY, vecC, vecDst;  // plane base and stride allow 16-byte accesses (else sample-by-sample staging / 4-byte stores)
 } SvbScaleDesc;
 
 #ifdef __cplusplus

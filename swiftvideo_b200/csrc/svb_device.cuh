@@ -190,7 +190,7 @@ __device__ __forceinline__ bool eval_pixel(const ImageUniforms* __restrict__ U, 
     const float4 fc = ldrow(U->fillColor, 0);
     const bool in_tx = in01(t0, t1), in_uv = in01(uu, vv);
 
-    if (s.format == SVB_NV12 || s.format == SVB_Y420P) {
+    if (SVB_FORMAT_IS_YUV(s.format)) {
         if (in_tx && in_uv) {
             const float na = sub(1.f, opacity);
             Taps k = make_taps(uu, vv, s.w, s.h);
@@ -198,9 +198,10 @@ __device__ __forceinline__ bool eval_pixel(const ImageUniforms* __restrict__ U, 
             if (chroma) {
                 Taps kc = make_taps(uu, vv, s.cw, s.ch);
                 float cb, cr;
-                if (s.format == SVB_NV12) {
-                    cb = sample1(s.p[1], s.stride[1], 2, 0, kc);
-                    cr = sample1(s.p[1], s.stride[1], 2, 1, kc);
+                if (SVB_FORMAT_IS_SEMIPLANAR(s.format)) {
+                    const int swap = s.format == SVB_NV21 ? 1 : 0;  // NV21 stores (Cr, Cb)
+                    cb = sample1(s.p[1], s.stride[1], 2, swap, kc);
+                    cr = sample1(s.p[1], s.stride[1], 2, 1 - swap, kc);
                 } else {
                     cb = sample1(s.p[1], s.stride[1], 1, 0, kc);
                     cr = sample1(s.p[2], s.stride[2], 1, 0, kc);

@@ -4,7 +4,7 @@ import numpy as np
 import swiftvideo_b200 as sv
 from oracle import oracle as O
 
-FMT = {O.NV12: sv.NV12, O.Y420P: sv.Y420P, O.BGRA: sv.BGRA, O.RGBA: sv.RGBA}
+FMT = {O.NV12: sv.NV12, O.Y420P: sv.Y420P, O.BGRA: sv.BGRA, O.RGBA: sv.RGBA, O.NV21: sv.NV21, O.Y422P: sv.Y422P, O.Y444P: sv.Y444P, O.YUVS: sv.YUVS}
 
 _ctx = None
 

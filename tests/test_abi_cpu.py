@@ -42,15 +42,17 @@ def test_module_image_has_the_reference_entry_points():
     assert img[:4] == b"\x7fELF"
     for n in ("img_clear_nv12", "img_clear_y420p", "img_clear_bgra", "img_nv12_nv12", "img_y420p_nv12", "img_y420p_y420p",
               "img_bgra_nv12", "img_rgba_nv12", "img_bgra_y420p", "img_rgba_y420p", "svb_mix_tiled", "svb_mix_tables", "svb_mix_ring", "svb_strip_tables", "svb_mix_generic",
-              "svb_scale_convert"):
+              "svb_scale_convert", "svb_scale_convert_any",
+              # the operators upstream names without a Linux kernel: img_bgra_bgra after its Metal text, the yuvs clear,
+              # and the NV21 / 4:2:2 / 4:4:4 sources under findKernel's naming rule
+              "img_bgra_bgra", "img_clear_yuvs", "img_nv21_nv12", "img_y422p_nv12", "img_y444p_nv12", "img_y422p_y420p", "img_y444p_y420p"):
         assert n.encode() in img
-    # upstream has no img_bgra_bgra on Linux (compute.swift:54 names it, only a half-written Metal body exists): neither have we
-    assert b"img_bgra_bgra" not in img
 
 
 def test_picture_layouts():
     """planesForFormat / buffersForPlanes (sample.pict.linux.swift:275-311): one allocation, planes back to back."""
-    for fmt, ofmt in ((sv.NV12, O.NV12), (sv.Y420P, O.Y420P), (sv.BGRA, O.BGRA), (sv.RGBA, O.RGBA)):
+    for fmt, ofmt in ((sv.NV12, O.NV12), (sv.Y420P, O.Y420P), (sv.BGRA, O.BGRA), (sv.RGBA, O.RGBA), (sv.NV21, O.NV21), (sv.Y422P, O.Y422P),
+                      (sv.Y444P, O.Y444P)):
         p = sv.create_picture_sample(64, 36, fmt, "a", "w")
         i = p.info()
         layout, total = O.plane_layout(ofmt, 64, 36)
@@ -73,7 +75,7 @@ def test_picture_layouts():
         sv.create_picture_sample(16, 16, 13)  # past the last pixel format
     assert e.value.name == "badInputData"
     with pytest.raises(sv.ComputeError) as e:
-        sv.create_picture_sample(16, 16, api.Y444P)
+        sv.create_picture_sample(16, 16, api.SHAPE)  # planesForFormat's default branch (sample.pict.linux.swift:289-291)
     assert e.value.name == "badInputData"
 
 

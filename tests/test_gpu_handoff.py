@@ -102,7 +102,7 @@ def test_gather_on_one_device_is_the_identity():
     img = scenes.random_image(O.NV12, 128, 72, 7200)
     g = to_gpu(ctx, img, "a")
     same = g.gather(ctx)
-    assert same.same_sample(g)
+    assert same.device_frame().planes[0].ptr == g.device_frame().planes[0].ptr  # the same planes, no copy
     with pytest.raises(sv.ComputeError):
         sv.create_picture_sample(64, 64, sv.NV12, "c", "w").gather(ctx)
 

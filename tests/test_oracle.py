@@ -99,3 +99,123 @@ def test_unsupported_pairs_and_sizes():
     odd = O.Image(O.NV12, 18, 8)
     odd.width = 17
     assert O.port().apply(odd, nv, u) == O.ERR_BAD_TARGET
+
+
+def test_cfg1_cpu_plumbing():
+    """BASELINE.json configs[0] ("cfg 1", the reference's own CPU-runnable case): ONE 640x360 NV12 sample in CPU buffers through
+    img_clear_nv12 + img_nv12_nv12 placed over the whole 640x360 canvas -- 345 600 source bytes in, 345 600 target bytes out
+     -- and the same picture through the NV12 -> BGRA leg against libswscale.  No GPU anywhere in this test."""
+    w, h = 640, 360
+    src = scenes.random_image(O.NV12, w, h, scenes.cfg_seed(1, 0, 0))
+    assert src.nbytes == 345600
+    u = scenes.layer_uniforms((w, h), (w, h), (0, 0), (w, h), z=1.0)
+    outs = []
+    for lib in [O.port()] + ([O.ref()] if O.ref_available() else []):
+        for threads in (0, 4):
+            t = O.Image(O.NV12, w, h)
+            t.data[:] = 0xA5
+            assert lib.mix(t, [src], [u], threads) == 0
+            outs.append(t.data.copy())
+    assert all((o == outs[0]).all() for o in outs[1:])                  # restatement == reference text, single- and multi-threaded
+    got = O.Image(O.NV12, w, h)
+    got.data[:] = outs[0]
+    # the kernel has no half-texel offset (kernels.cl.swift:72): a same-size picture lands as the rounded mean of each 2x2
+    # neighbourhood (edge-clamped), in luma and in each chroma component -- predicted here in float64, so allow the half code of rounding
+    for plane, ncomp in ((0, 1), (1, 2)):
+        a = src.plane(plane).astype(np.float64).reshape(src.plane(plane).shape[0], -1, ncomp)
+        yy, xx = np.mgrid[0:a.shape[0], 0:a.shape[1]]
+        ym, xm = np.maximum(yy - 1, 0), np.maximum(xx - 1, 0)
+        pred = (a[ym, xm] + a[ym, xx] + a[yy, xm] + a[yy, xx]) / 4
+        out = got.plane(plane).astype(np.float64).reshape(a.shape)
+        assert np.abs(out - pred).max() <= 0.5 + 1e-6
+    # the BGRA leg of the same configuration: the convert+scale definition at 1:1 against libswscale's NV12 -> BGRA
+    import swscale_util as S
+    if S.available():
+        smooth = S.smooth_picture(8, w, h, seed=1)
+        ours = O.scale_convert(O.SC_NV12, O.SC_BILINEAR, smooth, w, h, w, h).astype(np.int32)
+        sc = S.Scaler("nv12", w, h, w, h, S.SWS_BILINEAR | S.SWS_ACCURATE_RND | S.SWS_FULL_CHR_H_INT)
+        ref = sc.run(smooth).astype(np.int32)
+        sc.close()
+        assert np.abs(ours - ref).max() <= 1                              # TOLERANCE: one 8-bit code value
+
+
+# ---- extensions (SURVEY.md 8 f-3): operators the reference names but never implemented.  PARITY UNPINNED: these tests hold the
+# ---- definitions in oracle/mixer_oracle.c against properties that follow from the reference kernels they extend. -------------------
+
+def _ext_scene(src_fmt, tgt_fmt, canvas=(96, 64), size=(64, 48), seed=11):
+    src = scenes.random_image(src_fmt, size[0], size[1], seed)
+    u = scenes.layer_uniforms(canvas, size, (10, 6), (70, 50), z=1, opacity=0.7, border=(2, 2, 2, 2), fill=(0.3, 0.6, 0.1, 0.9))
+    return src, u
+
+
+def test_extension_nv21_is_nv12_with_swapped_pairs():
+    src, u = _ext_scene(O.NV12, O.NV12)
+    swapped = O.Image(O.NV21, src.width, src.height)
+    swapped.plane(0)[:] = src.plane(0)
+    swapped.plane(1)[:, 0::2] = src.plane(1)[:, 1::2]
+    swapped.plane(1)[:, 1::2] = src.plane(1)[:, 0::2]
+    a, b = O.Image(O.NV12, 96, 64), O.Image(O.NV12, 96, 64)
+    assert O.port().mix(a, [src], [u]) == 0 and O.port().mix(b, [swapped], [u]) == 0
+    assert (a.data == b.data).all()
+    assert O.port().mix(O.Image(O.Y420P, 96, 64), [swapped], [u]) == O.ERR_KERNEL_NOT_FOUND   # like img_nv12_y420p: not offered
+
+
+@pytest.mark.parametrize("fmt", [O.Y422P, O.Y444P])
+@pytest.mark.parametrize("tgt", [O.NV12, O.Y420P])
+def test_extension_planar_sources_share_the_y420p_body(fmt, tgt):
+    """Luma is filtered exactly as for a Y420P source; chroma planes are sampled at their own size, so constant chroma planes give what
+    a Y420P source with the same constants gives."""
+    base, u = _ext_scene(O.Y420P, tgt)
+    base.plane(1)[:] = 90
+    base.plane(2)[:] = 200
+    other = O.Image(fmt, base.width, base.height)
+    other.plane(0)[:] = base.plane(0)
+    other.plane(1)[:] = 90
+    other.plane(2)[:] = 200
+    a, b = O.Image(tgt, 96, 64), O.Image(tgt, 96, 64)
+    assert O.port().mix(a, [base], [u]) == 0 and O.port().mix(b, [other], [u]) == 0
+    assert (a.data == b.data).all()
+    # and a chroma plane with structure is really read at full height (4:2:2) / full size (4:4:4): a vertical ramp survives
+    other.plane(1)[:] = (np.arange(other.plane(1).shape[0])[:, None] * 3) % 256
+    c = O.Image(tgt, 96, 64)
+    assert O.port().mix(c, [other], [u]) == 0
+    assert (c.data != b.data).any()
+
+
+def test_extension_bgra_bgra_follows_the_metal_text():
+    """kernels.metal:51-62: nearest texel at trunc(gid * in/out), source-over with the source alpha, alpha 1 out."""
+    rng = np.random.default_rng(4)
+    src = O.Image(O.BGRA, 32, 16)
+    src.data[:] = rng.integers(0, 256, src.nbytes, dtype=np.uint8)
+    tgt = O.Image(O.BGRA, 16, 8)
+    tgt.data[:] = rng.integers(0, 256, tgt.nbytes, dtype=np.uint8)
+    before = tgt.data.copy().reshape(8, 16, 4)
+    u = O.Uniforms()
+    u.inSize[:] = [32, 16]
+    u.outSize[:] = [16, 8]
+    s = src.data.reshape(16, 32, 4).copy()
+    s[:, :, 3] = np.where(np.arange(32)[None, :] % 4 == 0, 255, s[:, :, 3])   # opaque columns
+    s[:, :, 3] = np.where(np.arange(32)[None, :] % 4 == 2, 0, s[:, :, 3])     # transparent columns
+    src.data[:] = s.reshape(-1)
+    assert O.port().apply_bgra_bgra(tgt, src, u) == 0
+    out = tgt.data.reshape(8, 16, 4)
+    assert (out[:, :, 3] == 255).all()
+    pick = s[::2, ::2]                                                        # texel (2x, 2y)
+    assert (out[:, 0::2, :3] == pick[:, 0::2, :3]).all()                      # source columns 0, 4, 8...: opaque -> copied
+    assert (out[:, 1::2, :3] == before[:, 1::2, :3]).all()                    # source columns 2, 6, ...: transparent -> untouched
+    # a half-transparent texel: rint((s * a + d * (1 - a)) * 255) within a code of the float64 value
+    s[:, :, 3] = 128
+    src.data[:] = s.reshape(-1)
+    tgt.data[:] = before.reshape(-1)
+    assert O.port().apply_bgra_bgra(tgt, src, u) == 0
+    a = 128 / 255
+    pred = s[::2, ::2, :3].astype(np.float64) * a + before[:, :, :3].astype(np.float64) * (1 - a)
+    assert np.abs(tgt.data.reshape(8, 16, 4)[:, :, :3] - pred).max() <= 0.5 + 1e-4
+    assert O.port().apply_bgra_bgra(O.Image(O.NV12, 16, 8), src, u) == O.ERR_KERNEL_NOT_FOUND
+
+
+def test_extension_clear_yuvs():
+    t = O.Image(O.YUVS, 16, 4)
+    t.data[:] = 9
+    assert O.port().clear(t) == 0
+    assert (t.data.reshape(-1, 2) == [0, 128]).all()

@@ -134,6 +134,10 @@ GPU_CASES = [
     (O.SC_P010, O.SC_LANCZOS3, (258, 130), (101, 67)),    # ragged, 2.55 : 1 (16 taps: the most the kernel takes)
     (O.SC_NV12, O.SC_LANCZOS3, (2, 2), (5, 3)),           # the smallest source
     (O.SC_NV12, O.SC_BILINEAR, (256, 64), (33, 9)),       # 7.8 : 1 bilinear (16 taps)
+    (O.SC_NV12, O.SC_LANCZOS3, (512, 256), (128, 64)),    # 4 : 1 Lanczos: 24 taps, the run-time tap loops
+    (O.SC_P010, O.SC_LANCZOS3, (768, 384), (128, 64)),    # 6 : 1 Lanczos: 36 taps, the tile shrinks to 8 rows to fit shared memory
+    (O.SC_NV12, O.SC_BILINEAR, (768, 96), (64, 8)),       # 12 : 1 bilinear: 24 taps
+    (O.SC_P010, O.SC_BILINEAR, (3840, 64), (1280, 48)),   # wide: many column tiles, 3 : 1 across, 1.33 : 1 down
 ]
 
 
@@ -149,6 +153,30 @@ def test_gpu_scale_bit_exact(fmt, filt, src, dst):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("fmt,filt,strides", [(O.SC_NV12, O.SC_LANCZOS3, (650, 652)),    # neither 16-byte chunks nor aligned rows: sample-by-sample staging
+                                              (O.SC_NV12, O.SC_BILINEAR, (704, 672)),    # padded but aligned: 16-byte staging reads into the padding at the right edge
+                                              (O.SC_P010, O.SC_LANCZOS3, (1284, 1300)),  # P010 rows that are only 4-byte aligned
+                                              (O.SC_P010, O.SC_BILINEAR, (1344, 1280))])
+def test_gpu_scale_decoder_strides(fmt, filt, strides):
+    """Planes with the decoder's own linesize (dec.video.ffmpeg.swift:183): the aligned and the unaligned staging paths give the definition's bytes."""
+    import gpu_util
+    import swiftvideo_b200 as sv
+    from swiftvideo_b200 import api
+    w, h, dst = 640, 360, (300, 170)
+    bps = 1 if fmt == O.SC_NV12 else 2
+    pic = _random_picture(fmt, w, h, seed=77 + strides[0])
+    rng = np.random.default_rng(9)
+    y = rng.integers(0, 256, (h, strides[0]), dtype=np.uint8)          # the padding holds noise the kernel must never let through
+    c = rng.integers(0, 256, (h // 2, strides[1]), dtype=np.uint8)
+    y[:, :w * bps] = pic[:w * h * bps].reshape(h, w * bps)
+    c[:, :w * bps] = pic[w * h * bps:].reshape(h // 2, w * bps)
+    src = api.picture_sample_from_planes(w, h, sv.NV12 if fmt == O.SC_NV12 else sv.P010, [y, c], "cam", "ws").upload(gpu_util.context())
+    got = src.scale_convert(gpu_util.context(), dst[0], dst[1], sv.BGRA, filt).download(gpu_util.context()).host_bytes().reshape(dst[1], dst[0], 4)
+    want = O.scale_convert(fmt, filt, pic, w, h, dst[0], dst[1])
+    assert int((got != want).sum()) == 0
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("fmt,filt,src,dst", [(O.SC_NV12, O.SC_BILINEAR, (1920, 1080), (1280, 720)),     # BASELINE cfg 2's convert + scale
                                               (O.SC_P010, O.SC_LANCZOS3, (3840, 2160), (1920, 1080))])  # BASELINE cfg 5
 def test_gpu_scale_full_size(fmt, filt, src, dst):
@@ -157,6 +185,40 @@ def test_gpu_scale_full_size(fmt, filt, src, dst):
     got = _gpu_scale(gpu_util.context(), fmt, filt, pic, src, dst)
     want = O.scale_convert(fmt, filt, pic, src[0], src[1], dst[0], dst[1])
     assert int((got != want).sum()) == 0
+
+
+@pytest.mark.gpu
+def test_cfg2_chain_full_size():
+    """BASELINE cfg 2's reported extra, whole: 1920x1080 NV12 -> (convert + bilinear scale) -> 1280x720 BGRA -> the reference's img_bgra_nv12
+    through the mixer -> 1280x720 NV12.  Each stage against its definition: the BGRA bytes equal oracle/scale_oracle.c's, the NV12 bytes equal
+    the OpenCL-text oracle's clear + img_bgra_nv12 over those BGRA bytes."""
+    import ctypes as C
+
+    import gpu_util
+    import swiftvideo_b200 as sv
+    from oracle import oracle as MO
+    from swiftvideo_b200 import api
+    ctx = gpu_util.context()
+    src, dst = (1920, 1080), (1280, 720)
+    pic = _random_picture(O.SC_NV12, src[0], src[1], seed=2002)
+    p = sv.create_picture_sample(src[0], src[1], sv.NV12, "cam", "test")
+    p.set_host_bytes(pic)
+    bgra = p.upload(ctx).scale_convert(ctx, dst[0], dst[1], sv.BGRA, O.SC_BILINEAR)
+    want_bgra = O.scale_convert(O.SC_NV12, O.SC_BILINEAR, pic, src[0], src[1], dst[0], dst[1])
+    assert (bgra.download(ctx, retain_gpu_buffer=True).host_bytes().reshape(dst[1], dst[0], 4) == want_bgra).all()
+    mixer = sv.VideoMixer(ctx, dst[0], dst[1], sv.NV12, asset_id="mixer", workspace_id="ws")
+    placed = bgra.animate(dst, (0, 0, 0.0), dst)
+    mixer.push(placed)
+    got = mixer.mix(1000).download(ctx).host_bytes()
+    layer = MO.Image(MO.BGRA, dst[0], dst[1])
+    layer.data[:] = want_bgra.reshape(-1)
+    u = api.make_image_uniforms(placed, sv.create_picture_sample(dst[0], dst[1], sv.NV12, "t", "w"))
+    ou = MO.Uniforms()
+    C.memmove(C.byref(ou), C.byref(u), 236)
+    want = MO.Image(MO.NV12, dst[0], dst[1])
+    assert MO.best()[0].mix(want, [layer], [ou]) == 0
+    assert (got == want.data).all()
+    mixer.close()
 
 
 @pytest.mark.gpu
@@ -184,9 +246,10 @@ def test_gpu_scale_errors():
     with pytest.raises(sv.ComputeError) as e:  # only BGRA targets exist
         nv.scale_convert(ctx, 32, 18, sv.NV12)
     assert e.value.name == "computeKernelNotFound"
-    with pytest.raises(sv.ComputeError) as e:  # Lanczos-3 at 4 : 1 would need 24 taps
-        nv.scale_convert(ctx, 16, 9, sv.BGRA, sv.FILTER_LANCZOS3)
-    assert e.value.name == "notImplemented"
+    wide = sv.create_picture_sample(2048, 64, sv.NV12, "w", "t").upload(ctx)
+    with pytest.raises(sv.ComputeError) as e:  # Lanczos-3 at 128 : 1 is 768 taps a column: no tile of it fits shared memory
+        wide.scale_convert(ctx, 16, 8, sv.BGRA, sv.FILTER_LANCZOS3)
+    assert e.value.name == "notImplemented" and "768" in str(e.value)
     bgra = sv.create_picture_sample(64, 36, sv.BGRA, "b", "t").upload(ctx)
     with pytest.raises(sv.ComputeError) as e:  # sources are NV12 / P010
         bgra.scale_convert(ctx, 32, 18)
