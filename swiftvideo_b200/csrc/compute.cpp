@@ -430,7 +430,10 @@ static ComputeContext maybeBuildKernel(const ComputeContext& ctx, ComputeKernel 
     if (ctx.library.count(name)) return ctx;
     static const char* builtins[] = {"img_clear_nv12", "img_clear_y420p", "img_clear_bgra", "img_nv12_nv12",
                                      "img_y420p_nv12", "img_y420p_y420p", "img_bgra_nv12",  "img_rgba_nv12",
-                                     "img_bgra_y420p", "img_rgba_y420p"};
+                                     "img_bgra_y420p", "img_rgba_y420p",
+                                     // ours: the operators upstream names without a Linux kernel (kernels_dropin.cuh)
+                                     "img_bgra_bgra",  "img_clear_yuvs",  "img_nv21_nv12",  "img_y422p_nv12",
+                                     "img_y444p_nv12", "img_y422p_y420p", "img_y444p_y420p"};
     bool have = false;
     for (const char* b : builtins) have = have || name == b;
     if (!have) throw ComputeError(ErrorCode::computeKernelNotFound, "computeKernelNotFound(" + name + ")");

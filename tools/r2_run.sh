@@ -1,1 +1,4 @@
-bash tools/ab_scale.sh "stage4+spread" "" "stage1+spread" "-DSVB_SCALE_STAGE4=0" "stage4+nospread" "-DSVB_SCALE_SPREAD=0" "stage1+nospread" "-DSVB_SCALE_STAGE4=0 -DSVB_SCALE_SPREAD=0" "stage4+spread+3ctas" "-DSVB_SCALE_MIN_CTAS=3" "stage1+spread+3ctas" "-DSVB_SCALE_STAGE4=0 -DSVB_SCALE_MIN_CTAS=3" 2>&1 | tee gpurun_out/r2_ab_scale.log
+set -x
+timeout 1200 python -m pytest tests -m gpu -q -x 2>&1 | tail -15
+for w in cfg5 cfg2 cfg2chain; do timeout 300 python bench.py --workload $w 2>/dev/null | tail -1 > gpurun_out/r2_bench_$w.json; cut -c1-400 gpurun_out/r2_bench_$w.json; done
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:svb_scale -s 30 -c 1 -f -o gpurun_out/r2_prof_scale python bench.py --workload cfg5 --steps 3 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
