@@ -142,6 +142,8 @@ CUdeviceptr InternalContext::alloc(size_t size) {
         }
         if (b.consumer && cu().cuEventQuery(b.consumer->e) != CUDA_SUCCESS)
             for (CUstream s : all) cu().cuStreamWaitEvent(s, b.consumer->e, 0);
+        if (b.lastUse && cu().cuEventQuery(b.lastUse->e) != CUDA_SUCCESS)
+            for (CUstream s : all) cu().cuStreamWaitEvent(s, b.lastUse->e, 0);
         return b.p;
     }
     CUdeviceptr p = 0;
@@ -149,11 +151,12 @@ CUdeviceptr InternalContext::alloc(size_t size) {
     if (std::getenv("SVB_DEBUG_POOL")) fprintf(stderr, "[svb] cuMemAlloc %zu\n", size);
     return p;
 }
-void InternalContext::release(CUdeviceptr p, size_t size, bool usedByDownload, std::shared_ptr<Event> consumer) {
+void InternalContext::release(CUdeviceptr p, size_t size, bool usedByDownload, std::shared_ptr<Event> consumer, std::shared_ptr<Event> lastUse) {
     size = (size + 255) & ~(size_t)255;
     Block b;
     b.p = p;
     b.consumer = std::move(consumer);
+    b.lastUse = std::move(lastUse);
     if (cu().ok && ctx) {
         cu().cuCtxPushCurrent(ctx);
         CUstream all[3] = {compute, upload, download};
@@ -161,6 +164,7 @@ void InternalContext::release(CUdeviceptr p, size_t size, bool usedByDownload, s
             // (a block the download stream never read -- an uploaded layer -- does not wait for that stream's tail: it would order the next
             // tick's uploads behind this tick's downloads and halve the link's duplex rate)
             if (i == 2 && !usedByDownload) continue;
+            if (i < 2 && b.lastUse) continue;  // the last compose that read the block is known: later work on these streams never touched it
             CUevent e = nullptr;
             {
                 std::lock_guard<std::mutex> g(mu);
@@ -251,7 +255,14 @@ Event::~Event() {
 }
 
 ComputeBuffer::~ComputeBuffer() {  // compute.cuda.swift:82-88
-    if (mem && ctx) ctx->release(mem, size, usedByDownload, consumerRead);
+    if (whole) {  // a plane of a picture's allocation: what the pool must know travels to the owner
+        whole->usedByDownload = whole->usedByDownload || usedByDownload;
+        if (consumerRead) whole->consumerRead = consumerRead;
+        if (lastUse) whole->lastUse = lastUse;
+        else whole->lastUseUnknown = true;
+        return;
+    }
+    if (mem && ctx) ctx->release(mem, size, usedByDownload, consumerRead, lastUseUnknown ? nullptr : lastUse);
 }
 
 CUDAProgram::~CUDAProgram() {
@@ -587,17 +598,43 @@ PictureSample pictureSampleFromPlanes(PixelFormat format, Vector2 size, const ui
     return s;
 }
 
-// createTexture (compute.cuda.swift:413-431): one device buffer of stride*height per plane.
+std::vector<std::shared_ptr<ComputeBuffer>> allocPictureTextures(const ComputeContext& ctx, const std::vector<Plane>& planes, int maxPlanes) {
+    const int n = std::min((int)planes.size(), maxPlanes);
+    std::vector<size_t> off((size_t)n + 1, 0);
+    bool together = n > 1;
+    for (int i = 0; i < n; ++i) {
+        off[(size_t)i + 1] = off[(size_t)i] + (size_t)(int)planes[(size_t)i].size.y * (size_t)planes[(size_t)i].stride;
+        together = together && off[(size_t)i] % 256 == 0;
+    }
+    std::vector<std::shared_ptr<ComputeBuffer>> out;
+    if (together) {
+        auto whole = createBuffer(ctx, off[(size_t)n]);
+        for (int i = 0; i < n; ++i) out.push_back(std::make_shared<ComputeBuffer>(whole, off[(size_t)i], off[(size_t)i + 1] - off[(size_t)i]));
+    } else {
+        for (int i = 0; i < n; ++i) out.push_back(createBuffer(ctx, off[(size_t)i + 1] - off[(size_t)i]));
+    }
+    return out;
+}
+
+// createTexture (compute.cuda.swift:413-431): device memory of stride*height per plane.
 static std::vector<std::shared_ptr<ComputeBuffer>> createTexture(const ComputeContext& ctx, const ImageBuffer& image, int maxPlanes) {
     if (image.bufferType != BufferType::cpu) return image.computeTextures;
     const int planeCount = (int)image.planes.size();
     if (!(planeCount <= 3 && planeCount > 0)) throw ComputeError(ErrorCode::badInputData, "Input image must have 1, 2, or 3 planes");
     if (planeCount != (int)image.buffers.size())
         throw ComputeError(ErrorCode::badInputData, "Input image must have the same number of buffers as planes");
-    std::vector<std::shared_ptr<ComputeBuffer>> out;
-    for (int i = 0; i < std::min(planeCount, maxPlanes); ++i)
-        out.push_back(createBuffer(ctx, (size_t)(int)image.planes[i].size.y * (size_t)image.planes[i].stride));
-    return out;
+    return allocPictureTextures(ctx, image.planes, maxPlanes);
+}
+
+// the planes of `textures` are one allocation and `buffers` lie back to back in host memory at the same offsets: one copy moves the picture
+static bool oneCopy(const std::vector<std::shared_ptr<ComputeBuffer>>& textures, const std::vector<HostData>& buffers) {
+    if (textures.size() < 2 || buffers.size() < textures.size() || !textures[0]->whole) return false;
+    for (size_t i = 0; i < textures.size(); ++i) {
+        if (textures[i]->whole != textures[0]->whole) return false;
+        if (buffers[i].size < textures[i]->size) return false;
+        if ((size_t)(buffers[i].ptr - buffers[0].ptr) != (size_t)(textures[i]->mem - textures[0]->mem)) return false;
+    }
+    return textures[0]->mem == textures[0]->whole->mem;
 }
 
 PictureSample uploadComputePicture(const ComputeContext& ctx, const PictureSample& pict, int maxPlanes, bool retainCpuBuffer, bool wait) {  // :359-381
@@ -605,10 +642,18 @@ PictureSample uploadComputePicture(const ComputeContext& ctx, const PictureSampl
     if (pict.imgBuffer.planes.empty()) throw ComputeError(ErrorCode::badInputData, "Missing image buffer");
     if (!ctx.ctx) throw ComputeError(ErrorCode::badContextState, "No context");
     auto textures = createTexture(ctx, pict.imgBuffer, maxPlanes);
-    for (size_t i = 0; i < textures.size(); ++i)
-    {
-        uploadComputeBuffer(ctx, pict.imgBuffer.buffers[i].ptr, std::min(pict.imgBuffer.buffers[i].size, textures[i]->size), textures[i]);
-        textures[i]->hostKeep = pict.imgBuffer.buffers[i].base;
+    if (oneCopy(textures, pict.imgBuffer.buffers)) {
+        CtxGuard g(ctx.ctx);
+        const auto& last = textures.back();
+        check(drv().cuMemcpyHtoDAsync(textures[0]->mem, pict.imgBuffer.buffers[0].ptr, (size_t)(last->mem - textures[0]->mem) + last->size, ctx.ctx->upload), "cuMemcpyHtoDAsync");
+        auto ready = std::make_shared<Event>(ctx.ctx);
+        check(drv().cuEventRecord(ready->e, ctx.ctx->upload), "cuEventRecord");
+        for (size_t i = 0; i < textures.size(); ++i) textures[i]->ready = ready, textures[i]->hostKeep = pict.imgBuffer.buffers[i].base;
+    } else {
+        for (size_t i = 0; i < textures.size(); ++i) {
+            uploadComputeBuffer(ctx, pict.imgBuffer.buffers[i].ptr, std::min(pict.imgBuffer.buffers[i].size, textures[i]->size), textures[i]);
+            textures[i]->hostKeep = pict.imgBuffer.buffers[i].base;
+        }
     }
     PictureSample out = pict;
     out.imgBuffer.computeTextures = textures;
@@ -714,6 +759,15 @@ PictureSample downloadComputePicture(const ComputeContext& ctx, const PictureSam
             }
     }
     if (pict.done) check(drv().cuStreamWaitEvent(ctx.ctx->download, pict.done->e, 0), "cuStreamWaitEvent");
+    if (oneCopy(pict.imgBuffer.computeTextures, out.imgBuffer.buffers)) {
+        const auto& tx = pict.imgBuffer.computeTextures;
+        for (const auto& tex : tx)
+            if (tex->ready) check(drv().cuStreamWaitEvent(ctx.ctx->download, tex->ready->e, 0), "cuStreamWaitEvent");
+        check(drv().cuMemcpyDtoHAsync(out.imgBuffer.buffers[0].ptr, tx[0]->mem, (size_t)(tx.back()->mem - tx[0]->mem) + tx.back()->size, ctx.ctx->download), "cuMemcpyDtoHAsync");
+        auto read = std::make_shared<Event>(ctx.ctx);
+        check(drv().cuEventRecord(read->e, ctx.ctx->download), "cuEventRecord");
+        for (const auto& tex : tx) tex->usedByDownload = true, tex->lastRead = read;
+    } else
     for (size_t i = 0; i < n; ++i) {
         const auto& tex = pict.imgBuffer.computeTextures[i];
         if (tex->ready) check(drv().cuStreamWaitEvent(ctx.ctx->download, tex->ready->e, 0), "cuStreamWaitEvent");
@@ -800,6 +854,7 @@ ComputeContext runComputeKernel(const ComputeContext& ctxIn, const std::vector<c
     for (const PictureSample* im : images) {
         for (const auto& t : im->imgBuffer.computeTextures) {
             if (t->ready) check(d.cuStreamWaitEvent(ctx.ctx->compute, t->ready->e, 0), "cuStreamWaitEvent");
+            t->lastUse = nullptr, t->lastUseUnknown = true;  // read by this launch: the pool falls back to the stream tails
             keep.push_back(t);
         }
         for (const Plane& p : im->imgBuffer.planes) inputStride.push_back((int32_t)p.stride);

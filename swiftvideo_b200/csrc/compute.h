@@ -105,6 +105,11 @@ struct Event {           // a CUevent that dies with its last holder
 class ComputeBuffer {    // compute.cuda.swift:75-92: owns device memory, released in the destructor
   public:
     ComputeBuffer(CUdeviceptr p, size_t size, std::shared_ptr<InternalContext> ctx) : mem(p), size(size), ctx(std::move(ctx)) {}
+    // a plane inside a picture's single allocation: `whole` owns the memory and returns it to the pool when its last plane is gone.
+    // Upstream allocates per plane (createTexture, compute.cuda.swift:413-431); one block per picture lets a picture whose host planes
+    // lie back to back travel as ONE copy -- over a link busy in both directions, 64 copies a tick reach 1350 frames/s where 128 reach
+    // 1240 (profiles/r2_copy_probe.log)
+    ComputeBuffer(const std::shared_ptr<ComputeBuffer>& owner, size_t offset, size_t size) : mem(owner->mem + offset), size(size), whole(owner), ctx(owner->ctx) {}
     ~ComputeBuffer();
     ComputeBuffer(const ComputeBuffer&) = delete;
     CUdeviceptr mem;  // non-const: its address is what cuLaunchKernel's param array points at (:297)
@@ -113,6 +118,12 @@ class ComputeBuffer {    // compute.cuda.swift:75-92: owns device memory, releas
     bool usedByDownload = false;   // the download stream has read this block (set by downloadComputeBuffer)
     std::shared_ptr<Event> lastRead;  // recorded after the last async READ on another stream (download): a writer waits on it before it overwrites (the mixer's backing ring)
     std::shared_ptr<Event> consumerRead;  // recorded by a reader outside this context's streams (an encoder's stream, a peer GPU's gather): writers and the pool wait on it
+    // recorded on the compute stream right after the last compose that read this block (mix_video.cpp); nullptr = unknown.  With it the pool
+    // orders a recycled block behind THAT launch instead of behind whatever the streams hold when the block is released -- two ticks later
+    // for a layer, by when the compute stream's tail is a compose that itself waits for uploads still in flight (a 0.5 ms bubble per tick)
+    std::shared_ptr<Event> lastUse;
+    bool lastUseUnknown = false;  // some launch other than a compose read the block (per-layer kernels, the scale operator): use the tails
+    std::shared_ptr<ComputeBuffer> whole;  // set on a plane carved out of a picture's allocation
     std::shared_ptr<uint8_t> hostKeep;  // source of an in-flight async upload stays alive with the texture
     std::shared_ptr<InternalContext> ctx;
 };
@@ -230,6 +241,9 @@ PictureSample uploadComputePicture(const ComputeContext& ctx, const PictureSampl
 PictureSample downloadComputePicture(const ComputeContext& ctx, const PictureSample& pict,
                                      bool retainGpuBuffer = false, bool wait = true);     // :383-402
 void waitPicture(const PictureSample& pict);
+// Device planes for a picture with the given plane shapes: one allocation when every plane starts at a multiple of 256 bytes in the
+// tight back-to-back layout (true of every even-sized 8-bit picture of video size), else one allocation per plane.
+std::vector<std::shared_ptr<ComputeBuffer>> allocPictureTextures(const ComputeContext& ctx, const std::vector<Plane>& planes, int maxPlanes = 3);
 // ---- device hand-off (upstream's commented-out h264_nvenc path, enc.video.ffmpeg.swift:169-170) ----------
 // A consumer that reads a GPU sample where it lies (an encoder session on the same CUDA context) orders itself behind
 // pictureReadyEvent() with cuStreamWaitEvent and, once its reads are queued, calls pictureConsumedOn(its stream): the mixer's
@@ -324,6 +338,7 @@ struct InternalContext {
         CUdeviceptr p = 0;
         CUevent after[3] = {nullptr, nullptr, nullptr};  // tails of compute/upload/download at release time
         std::shared_ptr<Event> consumer;                   // a foreign reader's completion (ComputeBuffer::consumerRead)
+        std::shared_ptr<Event> lastUse;                    // ComputeBuffer::lastUse: stands in for the compute and upload tails
     };
     std::multimap<size_t, Block> pool;  // freed device blocks by size (upstream cuMemAllocs per upload)
     // page-locked host blocks by size (createPictureSample(pinnedFrom:), and the destination of a download that has none):
@@ -346,7 +361,7 @@ struct InternalContext {
     void (*scaleSharedFree)(InternalContext*) = nullptr;
     ~InternalContext();
     CUdeviceptr alloc(size_t size);
-    void release(CUdeviceptr p, size_t size, bool usedByDownload = true, std::shared_ptr<Event> consumer = nullptr);  // usedByDownload=false: the block never met the download stream, whose tail it then need not wait for
+    void release(CUdeviceptr p, size_t size, bool usedByDownload = true, std::shared_ptr<Event> consumer = nullptr, std::shared_ptr<Event> lastUse = nullptr);  // usedByDownload=false: the block never met the download stream, whose tail it then need not wait for
     CUfunction builtin(const char* name);
 };
 struct CtxGuard {  // cuCtxPushCurrent / cuCtxPopCurrent pair

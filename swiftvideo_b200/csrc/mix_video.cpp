@@ -623,6 +623,12 @@ void composeFused(const ComputeContext& ctx, std::vector<Job>& jobs, bool forceG
         launchFrames(ctx, frames, allTiled, wantGather, want);
     }
     for (Job& j : jobs) markWritten(ctx, *j.target);
+    // every layer plane learns the point on the compute stream after which this compose no longer reads it (ComputeBuffer::lastUse)
+    auto used = std::make_shared<Event>(ctx.ctx);
+    check(drv().cuEventRecord(used->e, ctx.ctx->compute), "cuEventRecord");
+    for (Job& j : jobs)
+        for (const PictureSample* l : j.layers)
+            for (const auto& t : l->imgBuffer.computeTextures) t->lastUse = used;
 }
 
 }  // namespace
@@ -699,10 +705,7 @@ PictureSample VideoMixer::getBacking() {  // :148-165
         gpu.imgBuffer.size = backingSize;
         gpu.idAsset = idAsset, gpu.idWorkspace = idWorkspace, gpu.idRevision = idAsset;
         CtxGuard g(clContext.ctx);
-        for (const Plane& p : gpu.imgBuffer.planes) {
-            const size_t sz = (size_t)p.stride * (size_t)(int)p.size.y;
-            gpu.imgBuffer.computeTextures.push_back(std::make_shared<ComputeBuffer>(clContext.ctx->alloc(sz), sz, clContext.ctx));
-        }
+        gpu.imgBuffer.computeTextures = allocPictureTextures(clContext, gpu.imgBuffer.planes);  // one block: an emitted frame downloads as one copy
         gpu.imgBuffer.bufferType = BufferType::gpu;
         gpu.done = std::make_shared<Event>(clContext.ctx);
         backing.push_back(gpu);

@@ -199,8 +199,10 @@ PictureSample scaleConvertPicture(const ComputeContext& ctx, const PictureSample
     desc.vecDst = (desc.dst % 16 == 0 && desc.dstStride % 16 == 0) ? 1 : 0;
 
     if (src.done) check(d.cuStreamWaitEvent(ic.compute, src.done->e, 0), "cuStreamWaitEvent");
-    for (const auto& t : src.imgBuffer.computeTextures)
+    for (const auto& t : src.imgBuffer.computeTextures) {
         if (t->ready) check(d.cuStreamWaitEvent(ic.compute, t->ready->e, 0), "cuStreamWaitEvent");
+        t->lastUse = nullptr, t->lastUseUnknown = true;
+    }
     void* args[] = {&desc};
     check(d.cuLaunchKernel(fixedPitch ? sh.fn : sh.fnAny, (unsigned)((dstW + kTileW - 1) / kTileW), (unsigned)((dstH + tileH - 1) / tileH), 1, 256, 1, 1, (unsigned)smem, ic.compute, args, nullptr),
           "cuLaunchKernel(svb_scale_convert)");

@@ -24,7 +24,11 @@ def one_call(i):
     return sv.VideoMixer.tick_many(mixers, host, i, wait=False)
 def upload_only(i):
     return [[host[s][k].upload(ctx, retain_cpu_buffer=False, wait=False) for k in range(NL)] for s in range(S)]
-for name, fn in (("upload_only", upload_only), ("per_object", per_object), ("one_call", one_call), ("per_object", per_object), ("one_call", one_call)):
+def upload_mix(i):
+    for s in range(S):
+        mixers[s].push_many([host[s][k].upload(ctx, retain_cpu_buffer=False, wait=False) for k in range(NL)])
+    return sv.VideoMixer.mix_many(mixers, i, wait=False)
+for name, fn in (("upload_only", upload_only), ("upload_mix", upload_mix), ("per_object", per_object), ("one_call", one_call), ("per_object", per_object), ("one_call", one_call)):
     for i in range(4): last = fn(i)
     ctx.synchronize()
     t0 = time.perf_counter(); hq = 0.0

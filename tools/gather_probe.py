@@ -4,7 +4,9 @@ import json
 import sys
 import time
 
-sys.path.insert(0, "tests")
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import numpy as np
 
 import swiftvideo_b200 as sv
