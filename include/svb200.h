@@ -312,8 +312,10 @@ void svb_timer_destroy(svb_timer* t);
  * since timing was (re-)enabled.  Reading waits for the launches queued so far. */
 svb_status svb_launch_timing(svb_context* ctx, int enable);
 svb_status svb_launch_timing_read(svb_context* ctx, double* total_ms, unsigned long long* launches);
-/* host time spent inside the fused compose calls while launch timing was on (planner + driver calls: what the calling thread pays per tick) */
+/* host time spent inside the fused compose calls while launch timing was on (planner + driver calls: what the calling thread pays per tick),
+ * not counting the time the thread was blocked because it ran eight launches ahead of the GPU; that back-pressure is *wait_ms (may be NULL) */
 svb_status svb_host_timing_read(svb_context* ctx, double* total_ms, unsigned long long* calls);
+svb_status svb_host_timing_read2(svb_context* ctx, double* total_ms, unsigned long long* calls, double* wait_ms);
 /* launches of our kernels issued by this process so far */
 unsigned long long svb_kernel_launch_count(void);
 /* 256 floats each: UNORM8 read by the division-free identity and by true division (device self-test) */

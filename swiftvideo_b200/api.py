@@ -165,6 +165,7 @@ def _load():
     l.svb_launch_timing.argtypes = [C.c_void_p, C.c_int]
     l.svb_launch_timing_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     l.svb_host_timing_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    l.svb_host_timing_read2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     l.svb_selftest_unorm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     l.svb_scale_convert_picture.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p]
     l.svb_scale_filter_table.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
@@ -257,11 +258,12 @@ class ComputeContext:
         _check(lib.svb_launch_timing_read(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
-    def host_timing_read(self):
-        """(total host ms, calls) spent inside the library's fused compose calls since launch timing was enabled."""
-        ms, n = C.c_double(), C.c_ulonglong()
-        _check(lib.svb_host_timing_read(self._h, C.byref(ms), C.byref(n)))
-        return ms.value, n.value
+    def host_timing_read(self, with_wait=False):
+        """(total host ms, calls[, back-pressure ms]) spent inside the library's fused compose calls since launch timing was enabled; the
+        total does not count the time blocked on a GPU that is eight launches behind (that is the back-pressure figure)."""
+        ms, n, w = C.c_double(), C.c_ulonglong(), C.c_double()
+        _check(lib.svb_host_timing_read2(self._h, C.byref(ms), C.byref(n), C.byref(w)))
+        return (ms.value, n.value, w.value) if with_wait else (ms.value, n.value)
 
     def close(self):
         if self._h:

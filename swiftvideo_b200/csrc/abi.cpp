@@ -9,6 +9,7 @@
 #include "cu_driver.h"
 #include "mix_video.h"
 #include "animator.h"
+#include "host_prof.h"
 
 using namespace svb;
 
@@ -245,7 +246,10 @@ svb_status svb_picture_wait(const svb_picture* pict) {
         waitPicture(*pict->p);
     });
 }
-void svb_picture_release(svb_picture* pict) { delete pict; }
+void svb_picture_release(svb_picture* pict) {
+    SVB_PROF(23, "abi: picture_release");
+    delete pict;
+}
 const char* svb_picture_revision(const svb_picture* pict) { return pict ? pict->p->revision().c_str() : nullptr; }
 const char* svb_picture_asset_id(const svb_picture* pict) { return pict ? pict->p->assetId().c_str() : nullptr; }
 unsigned long long svb_picture_identity(const svb_picture* pict) { return pict ? (unsigned long long)(uintptr_t)pict->p.get() : 0ull; }
@@ -503,6 +507,7 @@ svb_status svb_video_mixer_push(svb_mixer* mixer, const svb_picture* pict, int* 
     });
 }
 svb_status svb_video_mixer_push_many(svb_mixer* mixer, const svb_picture* const* picts, int count) {
+    SVB_PROF(20, "abi: push_many");
     return guard([&] {
         need(mixer, "mixer");
         for (int i = 0; i < count; ++i) {
@@ -512,6 +517,7 @@ svb_status svb_video_mixer_push_many(svb_mixer* mixer, const svb_picture* const*
     });
 }
 svb_status svb_video_mixer_mix(svb_mixer* mixer, int64_t time, int wait, svb_picture** out) {
+    SVB_PROF(21, "abi: mix");
     return guard([&] {
         need(mixer, "mixer");
         need(out, "out");
@@ -519,6 +525,7 @@ svb_status svb_video_mixer_mix(svb_mixer* mixer, int64_t time, int wait, svb_pic
     });
 }
 svb_status svb_video_mixer_mix_many(svb_mixer* const* mixers, int count, int64_t time, int wait, svb_picture** outs) {
+    SVB_PROF(22, "abi: mix_many");
     return guard([&] {
         need(mixers, "mixers");
         need(outs, "outs");
@@ -663,6 +670,16 @@ svb_status svb_host_timing_read(svb_context* ctx, double* total_ms, unsigned lon
         need(calls, "calls");
         if (!ctx->c.ctx) throw ComputeError(ErrorCode::badContextState, "No context");
         readHostTiming(ctx->c, total_ms, calls);
+    });
+}
+
+svb_status svb_host_timing_read2(svb_context* ctx, double* total_ms, unsigned long long* calls, double* wait_ms) {
+    return guard([&] {
+        need(ctx, "ctx");
+        need(total_ms, "total_ms");
+        need(calls, "calls");
+        if (!ctx->c.ctx) throw ComputeError(ErrorCode::badContextState, "No context");
+        readHostTiming(ctx->c, total_ms, calls, wait_ms);
     });
 }
 

@@ -157,14 +157,18 @@ void InternalContext::release(CUdeviceptr p, size_t size, bool usedByDownload, s
     b.p = p;
     b.consumer = std::move(consumer);
     b.lastUse = std::move(lastUse);
+    bool lastUseKnown = (bool)b.lastUse;
     if (cu().ok && ctx) {
         cu().cuCtxPushCurrent(ctx);
+        // (an Event refers to its context: one that has fired is dropped here rather than parked in the context's own pool)
+        if (b.consumer && cu().cuEventQuery(b.consumer->e) == CUDA_SUCCESS) b.consumer = nullptr;
+        if (b.lastUse && cu().cuEventQuery(b.lastUse->e) == CUDA_SUCCESS) b.lastUse = nullptr;
         CUstream all[3] = {compute, upload, download};
         for (int i = 0; i < 3; ++i) {
             // (a block the download stream never read -- an uploaded layer -- does not wait for that stream's tail: it would order the next
             // tick's uploads behind this tick's downloads and halve the link's duplex rate)
             if (i == 2 && !usedByDownload) continue;
-            if (i < 2 && b.lastUse) continue;  // the last compose that read the block is known: later work on these streams never touched it
+            if (i < 2 && lastUseKnown) continue;  // the last compose that read the block is known: later work on these streams never touched it
             CUevent e = nullptr;
             {
                 std::lock_guard<std::mutex> g(mu);
@@ -241,11 +245,29 @@ CUfunction InternalContext::builtin(const char* name) {
     return f;
 }
 
+// Events are recycled through the context's spare list: a tick creates and drops a handful (completion of the mix, last use of the
+// layers, last read of a download) and cuEventCreate / cuEventDestroy each cost a context push and a driver call.  Re-recording a
+// recycled event is safe: a wait already queued on it refers to the record that was current when the wait was queued.
 Event::Event(std::shared_ptr<InternalContext> c) : ctx(std::move(c)) {
+    {
+        std::lock_guard<std::mutex> g(ctx->mu);
+        if (!ctx->spareEvents.empty()) {
+            e = ctx->spareEvents.back();
+            ctx->spareEvents.pop_back();
+        }
+    }
+    if (e) return;
     CtxGuard g(ctx);
     check(drv().cuEventCreate(&e, CU_EVENT_DISABLE_TIMING), "cuEventCreate");
 }
 Event::~Event() {
+    if (e && ctx) {
+        std::lock_guard<std::mutex> g(ctx->mu);
+        if (ctx->ctx && ctx->spareEvents.size() < 4096) {
+            ctx->spareEvents.push_back(e);
+            e = nullptr;
+        }
+    }
     if (e && cu().ok) {
         cu().cuCtxPushCurrent(ctx->ctx);
         cu().cuEventDestroy(e);
@@ -484,6 +506,7 @@ std::shared_ptr<ComputeBuffer> uploadComputeBuffer(const ComputeContext& ctx, co
     check(drv().cuMemcpyHtoDAsync(buf->mem, src, size, ctx.ctx->upload), "cuMemcpyHtoDAsync");
     if (!buf->ready) buf->ready = std::make_shared<Event>(ctx.ctx);
     check(drv().cuEventRecord(buf->ready->e, ctx.ctx->upload), "cuEventRecord");
+    buf->noteWrite(ctx.ctx->upload);
     return buf;
 }
 
@@ -648,7 +671,7 @@ PictureSample uploadComputePicture(const ComputeContext& ctx, const PictureSampl
         check(drv().cuMemcpyHtoDAsync(textures[0]->mem, pict.imgBuffer.buffers[0].ptr, (size_t)(last->mem - textures[0]->mem) + last->size, ctx.ctx->upload), "cuMemcpyHtoDAsync");
         auto ready = std::make_shared<Event>(ctx.ctx);
         check(drv().cuEventRecord(ready->e, ctx.ctx->upload), "cuEventRecord");
-        for (size_t i = 0; i < textures.size(); ++i) textures[i]->ready = ready, textures[i]->hostKeep = pict.imgBuffer.buffers[i].base;
+        for (size_t i = 0; i < textures.size(); ++i) textures[i]->ready = ready, textures[i]->noteWrite(ctx.ctx->upload), textures[i]->hostKeep = pict.imgBuffer.buffers[i].base;
     } else {
         for (size_t i = 0; i < textures.size(); ++i) {
             uploadComputeBuffer(ctx, pict.imgBuffer.buffers[i].ptr, std::min(pict.imgBuffer.buffers[i].size, textures[i]->size), textures[i]);
@@ -670,6 +693,15 @@ PictureSample uploadComputePicture(const ComputeContext& ctx, const PictureSampl
         }
     }
     return out;
+}
+
+void waitReady(CUstream s, ComputeBuffer& t) {
+    if (!t.ready || t.readyStream == s || t.readyFired.load(std::memory_order_relaxed)) return;
+    if (cu().cuEventQuery(t.ready->e) == CUDA_SUCCESS) {
+        t.readyFired.store(true, std::memory_order_relaxed);
+        return;
+    }
+    check(drv().cuStreamWaitEvent(s, t.ready->e, 0), "cuStreamWaitEvent");
 }
 
 void waitPicture(const PictureSample& pict) {
@@ -716,13 +748,14 @@ PictureSample gatherComputePicture(const ComputeContext& dst, const PictureSampl
     CUstream st = dst.ctx->upload;
     if (pict.done) check(drv().cuStreamWaitEvent(st, pict.done->e, 0), "cuStreamWaitEvent");
     for (const auto& t : pict.imgBuffer.computeTextures) {
-        if (t->ready) check(drv().cuStreamWaitEvent(st, t->ready->e, 0), "cuStreamWaitEvent");
+        if (t->ready) check(drv().cuStreamWaitEvent(st, t->ready->e, 0), "cuStreamWaitEvent");  // (another context's event: always waited for)
         auto copy = createBuffer(dst, t->size);
         check(drv().cuMemcpyPeerAsync(copy->mem, dst.ctx->ctx, t->mem, src->ctx, t->size, st), "cuMemcpyPeerAsync");
         auto e = std::make_shared<Event>(dst.ctx);
         check(drv().cuEventRecord(e->e, st), "cuEventRecord");
         t->consumerRead = e;  // the source's next writer (its mixer's ring, its pool) waits for this copy
         copy->ready = e;      // and readers on dst's other streams order themselves behind it
+        copy->noteWrite(st);
         out.imgBuffer.computeTextures.push_back(copy);
     }
     out.done = nullptr;
@@ -762,7 +795,7 @@ PictureSample downloadComputePicture(const ComputeContext& ctx, const PictureSam
     if (oneCopy(pict.imgBuffer.computeTextures, out.imgBuffer.buffers)) {
         const auto& tx = pict.imgBuffer.computeTextures;
         for (const auto& tex : tx)
-            if (tex->ready) check(drv().cuStreamWaitEvent(ctx.ctx->download, tex->ready->e, 0), "cuStreamWaitEvent");
+            waitReady(ctx.ctx->download, *tex);
         check(drv().cuMemcpyDtoHAsync(out.imgBuffer.buffers[0].ptr, tx[0]->mem, (size_t)(tx.back()->mem - tx[0]->mem) + tx.back()->size, ctx.ctx->download), "cuMemcpyDtoHAsync");
         auto read = std::make_shared<Event>(ctx.ctx);
         check(drv().cuEventRecord(read->e, ctx.ctx->download), "cuEventRecord");
@@ -770,7 +803,7 @@ PictureSample downloadComputePicture(const ComputeContext& ctx, const PictureSam
     } else
     for (size_t i = 0; i < n; ++i) {
         const auto& tex = pict.imgBuffer.computeTextures[i];
-        if (tex->ready) check(drv().cuStreamWaitEvent(ctx.ctx->download, tex->ready->e, 0), "cuStreamWaitEvent");
+        waitReady(ctx.ctx->download, *tex);
         downloadComputeBuffer(ctx, *tex, out.imgBuffer.buffers[i].ptr, out.imgBuffer.buffers[i].size);
         // whoever overwrites this plane next (the mixer recycles its backing ring) waits for this copy first
         if (!tex->lastRead) tex->lastRead = std::make_shared<Event>(ctx.ctx);
@@ -853,14 +886,13 @@ ComputeContext runComputeKernel(const ComputeContext& ctxIn, const std::vector<c
     std::vector<int32_t> inputStride;
     for (const PictureSample* im : images) {
         for (const auto& t : im->imgBuffer.computeTextures) {
-            if (t->ready) check(d.cuStreamWaitEvent(ctx.ctx->compute, t->ready->e, 0), "cuStreamWaitEvent");
+            waitReady(ctx.ctx->compute, *t);
             t->lastUse = nullptr, t->lastUseUnknown = true;  // read by this launch: the pool falls back to the stream tails
             keep.push_back(t);
         }
         for (const Plane& p : im->imgBuffer.planes) inputStride.push_back((int32_t)p.stride);
     }
-    for (const auto& t : target.imgBuffer.computeTextures)
-        if (t->ready) check(d.cuStreamWaitEvent(ctx.ctx->compute, t->ready->e, 0), "cuStreamWaitEvent");
+    for (const auto& t : target.imgBuffer.computeTextures) waitReady(ctx.ctx->compute, *t);
     // uniforms and the stride array travel as two small device buffers, as upstream (:278-289); both copies are
     // ordered on the compute stream ahead of the launch.
     if (uniforms && uniformsSize) {
@@ -889,6 +921,7 @@ void markWritten(const ComputeContext& ctx, const PictureSample& target) {  // c
     for (const auto& t : target.imgBuffer.computeTextures) {
         if (!t->ready) t->ready = std::make_shared<Event>(ctx.ctx);
         check(drv().cuEventRecord(t->ready->e, ctx.ctx->compute), "cuEventRecord");
+        t->noteWrite(ctx.ctx->compute);
     }
 }
 

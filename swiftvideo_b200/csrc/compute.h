@@ -10,6 +10,7 @@
 // The reference is Swift; no Swift toolchain exists in this image, so the host side is C++ above the same
 // driver API and below the C ABI in include/svb200.h.
 #pragma once
+#include <atomic>
 #include <cuda.h>
 #include <stdint.h>
 
@@ -114,7 +115,10 @@ class ComputeBuffer {    // compute.cuda.swift:75-92: owns device memory, releas
     ComputeBuffer(const ComputeBuffer&) = delete;
     CUdeviceptr mem;  // non-const: its address is what cuLaunchKernel's param array points at (:297)
     const size_t size;
-    std::shared_ptr<Event> ready;  // recorded after the last async write (upload); consumers wait on it
+    std::shared_ptr<Event> ready;  // recorded after the last async write (upload); consumers wait on it (waitReady)
+    CUstream readyStream = nullptr;          // the stream `ready` was recorded on: work queued on that stream is ordered already
+    std::atomic<bool> readyFired{false};     // `ready` was seen complete: a resident layer costs no driver call per tick after that
+    void noteWrite(CUstream s) { readyStream = s, readyFired.store(false, std::memory_order_relaxed); }
     bool usedByDownload = false;   // the download stream has read this block (set by downloadComputeBuffer)
     std::shared_ptr<Event> lastRead;  // recorded after the last async READ on another stream (download): a writer waits on it before it overwrites (the mixer's backing ring)
     std::shared_ptr<Event> consumerRead;  // recorded by a reader outside this context's streams (an encoder's stream, a peer GPU's gather): writers and the pool wait on it
@@ -241,6 +245,9 @@ PictureSample uploadComputePicture(const ComputeContext& ctx, const PictureSampl
 PictureSample downloadComputePicture(const ComputeContext& ctx, const PictureSample& pict,
                                      bool retainGpuBuffer = false, bool wait = true);     // :383-402
 void waitPicture(const PictureSample& pict);
+// order stream `s` behind the last asynchronous write of `t`: nothing to do when that write was queued on `s` itself or is known to be
+// complete (the caller holds a CtxGuard)
+void waitReady(CUstream s, ComputeBuffer& t);
 // Device planes for a picture with the given plane shapes: one allocation when every plane starts at a multiple of 256 bytes in the
 // tight back-to-back layout (true of every even-sized 8-bit picture of video size), else one allocation per plane.
 std::vector<std::shared_ptr<ComputeBuffer>> allocPictureTextures(const ComputeContext& ctx, const std::vector<Plane>& planes, int maxPlanes = 3);

@@ -10,6 +10,7 @@
 #include <cstring>
 
 #include "cu_driver.h"
+#include "host_prof.h"
 #include "ring_layout.h"
 
 namespace svb {
@@ -65,7 +66,8 @@ struct MixerShared {
     double timedMs = 0.0;
     unsigned long long timedLaunches = 0;
     // host time spent inside mixMany / composeRaw while timing is on (plan + driver calls; what the caller's thread pays per tick)
-    double hostMs = 0.0;
+    double hostMs = 0.0;      // host time inside composeFused while timing is on, WITHOUT ...
+    double hostWaitMs = 0.0;  // ... the time spent blocked on a descriptor segment the GPU has not released yet (back-pressure)
     unsigned long long hostCalls = 0;
 };
 
@@ -399,7 +401,13 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
             seg = sh.next;
             sh.next = (sh.next + 1) % kSegments;
         }
-        if (sh.used[seg]) check(d.cuEventSynchronize(sh.ev[seg]), "cuEventSynchronize");
+        if (sh.used[seg]) {  // eight segments: the host may run eight launches ahead of the GPU, then it waits here
+            SVB_PROF(8, "launch: wait for segment (GPU back-pressure)");
+            const auto w0 = std::chrono::steady_clock::now();
+            check(d.cuEventSynchronize(sh.ev[seg]), "cuEventSynchronize");
+            sh.hostWaitMs += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
+        }
+        SVB_PROF(9, "launch: fill + copy + 2 launches");
         SvbFrameDesc* host = (SvbFrameDesc*)(sh.host + (size_t)seg * kSegFrames * sizeof(SvbFrameDesc));
         int total = 0, maxW = 0, maxH = 0, maxLayers = 1, maxEnts = 1, maxTiles = 1;
         size_t tableEnts = 0;
@@ -576,7 +584,7 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
 
 void waitInputs(const ComputeContext& ctx, const PictureSample& p, bool willWrite = false) {
     for (const auto& t : p.imgBuffer.computeTextures) {
-        if (t->ready) check(drv().cuStreamWaitEvent(ctx.ctx->compute, t->ready->e, 0), "cuStreamWaitEvent");
+        waitReady(ctx.ctx->compute, *t);
         // a target: an asynchronous download of what the plane held before may still be reading it (the backing ring comes round
         // every ten ticks and a compose is an order of magnitude faster than the copy over PCIe)
         if (willWrite && t->lastRead) check(drv().cuStreamWaitEvent(ctx.ctx->compute, t->lastRead->e, 0), "cuStreamWaitEvent");
@@ -597,15 +605,18 @@ void composeFused(const ComputeContext& ctx, std::vector<Job>& jobs, bool forceG
     CtxGuard g(ctx.ctx);
     struct HostClock {  // (only while launch timing is on)
         MixerShared& sh;
+        double waited0;
         std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
         ~HostClock() {
-            if (sh.timing) sh.hostMs += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), ++sh.hostCalls;
+            if (sh.timing) sh.hostMs += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() - (sh.hostWaitMs - waited0), ++sh.hostCalls;
         }
-    } hostClock{shared(ctx.ctx)};
+    } hostClock{shared(ctx.ctx), shared(ctx.ctx).hostWaitMs};
+    SVB_PROF(3, "composeFused");
     std::vector<FramePlan> plans;
     bool allTiled = !forceGeneric;
     size_t maxPass = 0;
     for (Job& j : jobs) {
+        SVB_PROF(4, "compose: planFrame + waitInputs (per frame)");
         plans.push_back(planFrame(ctx, *j.target, j.layers, j.uniforms.data(), j.cached.empty() ? nullptr : j.cached.data()));
         if (j.planned) {
             j.planned->clear();
@@ -622,6 +633,7 @@ void composeFused(const ComputeContext& ctx, std::vector<Job>& jobs, bool forceG
             if (p < pl.passes.size()) frames.push_back(pl.passes[p]);
         launchFrames(ctx, frames, allTiled, wantGather, want);
     }
+    SVB_PROF(10, "compose: markWritten + lastUse");
     for (Job& j : jobs) markWritten(ctx, *j.target);
     // every layer plane learns the point on the compute stream after which this compose no longer reads it (ComputeBuffer::lastUse)
     auto used = std::make_shared<Event>(ctx.ctx);
@@ -641,13 +653,15 @@ void setLaunchTiming(const ComputeContext& ctx, bool on) {
     sh.timedMs = 0.0;
     sh.timedLaunches = 0;
     sh.hostMs = 0.0;
+    sh.hostWaitMs = 0.0;
     sh.hostCalls = 0;
 }
-void readHostTiming(const ComputeContext& ctx, double* totalMs, unsigned long long* calls) {
+void readHostTiming(const ComputeContext& ctx, double* totalMs, unsigned long long* calls, double* waitMs) {
     CtxGuard g(ctx.ctx);
     MixerShared& sh = shared(ctx.ctx);
     *totalMs = sh.hostMs;
     *calls = sh.hostCalls;
+    if (waitMs) *waitMs = sh.hostWaitMs;
 }
 void readLaunchTiming(const ComputeContext& ctx, double* totalMs, unsigned long long* launches) {
     CtxGuard g(ctx.ctx);
@@ -719,17 +733,28 @@ PictureSample VideoMixer::getBacking() {  // :148-165
 VideoMixer::Tick VideoMixer::beginTick() {  // :113-115
     Tick tk;
     tk.backing = getBacking();
-    std::map<std::string, std::shared_ptr<const PictureSample>> merged = samples[1];
-    for (const auto& kv : samples[0]) merged[kv.first] = kv.second;  // merging { lhs, _ in lhs }: generation 0 wins
-    for (const auto& kv : merged) tk.images.push_back(kv.second);
+    // merging { lhs, _ in lhs }: generation 0 wins; both maps are ordered by revision, so a two-way merge visits the union in
+    // revision order without building a third map
+    std::vector<std::pair<int, const std::shared_ptr<const PictureSample>*>> order;
+    order.reserve(samples[0].size() + samples[1].size());
+    auto a = samples[0].begin(), b = samples[1].begin();
+    while (a != samples[0].end() || b != samples[1].end()) {
+        const int c = a == samples[0].end() ? 1 : b == samples[1].end() ? -1 : a->first.compare(b->first);
+        const std::shared_ptr<const PictureSample>& pick = c <= 0 ? a->second : b->second;
+        order.emplace_back(pick->zIndex(), &pick);
+        if (c <= 0) ++a;
+        if (c >= 0) ++b;
+    }
     // upstream's sort is unstable and the source is a dictionary: equal zIndex has no defined order there.
-    // Here ties fall back to the revision string so that a frame is reproducible.
-    std::stable_sort(tk.images.begin(), tk.images.end(), [](const std::shared_ptr<const PictureSample>& a, const std::shared_ptr<const PictureSample>& b) { return a->zIndex() < b->zIndex(); });
+    // Here ties keep the revision order so that a frame is reproducible.
+    std::stable_sort(order.begin(), order.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
+    tk.images.reserve(order.size());
+    for (const auto& o : order) tk.images.push_back(*o.second);
     return tk;
 }
 
 void VideoMixer::endTick() {  // the `defer` block, :104-107
-    samples[1] = samples[0];
+    samples[1].swap(samples[0]);
     samples[0].clear();
 }
 
@@ -778,11 +803,13 @@ void VideoMixer::mixMany(VideoMixer* const* mixers, int n, int64_t time, Picture
         }
     } defer{mixers, n};
 
+    SVB_PROF(0, "mixMany");
     std::vector<Tick> ticks;
     ticks.reserve(n);
     std::vector<Job> jobs;
     bool fusedAll = true;
     for (int i = 0; i < n; ++i) {
+        SVB_PROF(1, "mixMany: beginTick (per mixer)");
         ticks.push_back(mixers[i]->beginTick());
         const int tf = svbFormat(ticks.back().backing.pixelFormat());
         fusedAll = fusedAll && mixers[i]->mode != Mode::perLayer && (tf == SVB_NV12 || tf == SVB_Y420P);
@@ -794,6 +821,7 @@ void VideoMixer::mixMany(VideoMixer* const* mixers, int n, int64_t time, Picture
         bool generic = false, wantGather = false;
         int want = 0;
         for (int i = 0; i < n; ++i) {
+            SVB_PROF(2, "mixMany: plan-cache lookup (per mixer)");
             Tick& tk = ticks[i];
             VideoMixer& mx = *mixers[i];
             ++mx.tickNo;
@@ -821,6 +849,7 @@ void VideoMixer::mixMany(VideoMixer* const* mixers, int n, int64_t time, Picture
             if (mixers[i]->mode == Mode::fusedRing) want = 3;
         }
         composeFused(ctx0, jobs, generic, wantGather, want);
+        SVB_PROF(11, "mixMany: cache update");
         for (int i = 0; i < n; ++i) {  // remember what was derived; forget the samples that are gone or have not been seen for a while
             VideoMixer& mx = *mixers[i];
             const Tick& tk = ticks[i];
@@ -845,6 +874,7 @@ void VideoMixer::mixMany(VideoMixer* const* mixers, int n, int64_t time, Picture
         }
     }
     {
+        SVB_PROF(12, "mixMany: outputs");
         CtxGuard g(ctx0.ctx);
         for (int i = 0; i < n; ++i) {
             PictureSample& b = ticks[i].backing;

@@ -94,7 +94,7 @@ class VideoMixer {
 void setLaunchTiming(const ComputeContext& ctx, bool on);
 void readLaunchTiming(const ComputeContext& ctx, double* totalMs, unsigned long long* launches);
 // Host time spent inside the fused compose calls since timing was enabled (plan + driver calls: what the caller's thread pays per tick)
-void readHostTiming(const ComputeContext& ctx, double* totalMs, unsigned long long* calls);
+void readHostTiming(const ComputeContext& ctx, double* totalMs, unsigned long long* calls, double* waitMs = nullptr);
 
 // Planner: fills frame descriptors (one per pass of 16 layers) for one target.  Exposed for tests.
 struct FramePlan {

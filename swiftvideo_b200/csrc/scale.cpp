@@ -200,7 +200,7 @@ PictureSample scaleConvertPicture(const ComputeContext& ctx, const PictureSample
 
     if (src.done) check(d.cuStreamWaitEvent(ic.compute, src.done->e, 0), "cuStreamWaitEvent");
     for (const auto& t : src.imgBuffer.computeTextures) {
-        if (t->ready) check(d.cuStreamWaitEvent(ic.compute, t->ready->e, 0), "cuStreamWaitEvent");
+        waitReady(ic.compute, *t);
         t->lastUse = nullptr, t->lastUseUnknown = true;
     }
     void* args[] = {&desc};

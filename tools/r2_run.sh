@@ -1,7 +1,9 @@
 set -x
-for tool in memcheck racecheck synccheck; do
-  timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 --log-file gpurun_out/r2_sanitizer_$tool.log python -m pytest tests/test_gpu_parity.py tests/test_gpu_handoff.py tests/test_gpu_formats.py -m gpu -q -x -k "fused_ring or fused-0 or handoff or consumer or new_sources or bgra_mixer or padded or tiled_scenes" 2>&1 | tail -2
-  tail -3 gpurun_out/r2_sanitizer_$tool.log
-done
-timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 --log-file gpurun_out/r2_sanitizer_scale.log python -m pytest tests/test_scale.py -m gpu -q -x -k "bit_exact or strides" 2>&1 | tail -2
-tail -3 gpurun_out/r2_sanitizer_scale.log
+timeout 1200 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
+SVB_HOST_PROFILE=1 timeout 600 python bench.py --no-cpu-baseline > gpurun_out/r2_bench_b.json 2> gpurun_out/r2_bench_b.err
+grep "svb host" gpurun_out/r2_bench_b.err
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/r2_bench_b.json'))
+print({k:d[k] for k in ('value','ms_per_step','host_queue_ms_per_step','host_queue_in_library_ms_per_step','host_backpressure_ms_per_step')}, d['e2e']['value'], d['one_frame_per_launch'])
+PY
