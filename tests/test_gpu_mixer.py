@@ -397,3 +397,47 @@ def test_layers_placed_by_the_native_animator(mode):
     want = _oracle_mix(O.NV12, canvas, placed, imgs)
     assert (got == want).all(), first_diff(got, want)
     mixer.close()
+
+
+def test_two_threads_drive_mixers_of_one_context():
+    """any thread may call; mixers sharing one context are serialised on its compute stream.  Two host threads tick two
+    mixers of the same context concurrently (asynchronous mixes, downloads joined at the end): every frame of both is bit-exact."""
+    import threading
+    ctx = context()
+    canvas = (256, 144)
+    results, errors = {}, []
+
+    def worker(idx):
+        try:
+            mixer = sv.VideoMixer(ctx, canvas[0], canvas[1], sv.NV12, asset_id=f"mixer{idx}", workspace_id="ws")
+            imgs = [scenes.random_image(O.NV12, 128, 72, 9000 + 10 * idx + k) for k in range(3)]
+            gpu = [to_gpu(ctx, im, f"t{idx}a{k}") for k, im in enumerate(imgs)]
+            frames = []
+            for tick in range(24):
+                placed = [_place(gpu[0], canvas, (128, 72), (0, 0), canvas, z=0, revision="a"),
+                          _place(gpu[1], canvas, (128, 72), (8 + 4 * tick, 6 + idx), (140, 80), z=1, opacity=0.6, revision="b"),
+                          _place(gpu[2], canvas, (128, 72), (60, 20 + 2 * tick), (150, 90), z=2, opacity=0.85, revision="c")]
+                for p in placed:
+                    mixer.push(p)
+                out = mixer.mix(1000 * (tick + 1), wait=False).download(ctx, retain_gpu_buffer=True, wait=False)
+                frames.append((out, placed))
+            got = []
+            for out, placed in frames:
+                out.wait()
+                got.append((out.host_bytes().copy(), placed))
+            results[idx] = (got, imgs)
+            mixer.close()
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for idx in range(2):
+        got, imgs = results[idx]
+        for tick, (bytes_, placed) in enumerate(got):
+            want = _oracle_mix(O.NV12, canvas, placed, imgs)
+            assert (bytes_ == want).all(), (idx, tick, first_diff(bytes_, want))
