@@ -180,6 +180,12 @@ void svb_picture_release(svb_picture* pict);
  * A mixer may recycle the GPU sample that is being downloaded (its backing ring comes round every ten ticks): the next compose into
  * those planes waits for the copy on the device, so asynchronous consumers need no frame-period bookkeeping. */
 svb_status svb_upload_compute_picture(svb_context* ctx, const svb_picture* pict, int max_planes, int retain_cpu_buffer, int wait, svb_picture** out);
+/* the same for several pictures at once (a tick's layers).  CPU pictures that lie next to each other in page-locked host memory --
+ * svb_create_picture_sample(pinned_from) hands out neighbours when called in sequence -- share one device block and travel as ONE copy
+ * (a link busy in both directions gives 64 separate pictures 86 % of what it gives one copy); others go up one by one; GPU pictures pass
+ * through.  svb_video_mixer_tick_many uploads its CPU layers this way. */
+svb_status svb_upload_compute_pictures(svb_context* ctx, const svb_picture* const* picts, int count, int max_planes, int retain_cpu_buffer, int wait,
+                                       svb_picture** outs);
 svb_status svb_download_compute_picture(svb_context* ctx, const svb_picture* pict, int retain_gpu_buffer, int wait, svb_picture** out);
 /* GPUBarrierUpload / GPUBarrierDownload compute.swift:175-198, :232-255: the pipeline stages around the two calls above.  A sample that
  * already lives on the right side passes through (*out is another handle of the SAME sample); a failure returns the status and fills

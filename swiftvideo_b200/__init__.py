@@ -11,7 +11,7 @@ import importlib
 
 _API = ("BUFFER_CPU", "BUFFER_GPU", "EventError", "BGRA", "NV12", "RGBA", "Y420P", "P010", "NV21", "Y422P", "Y444P", "YUVS", "ZVUY", "FILTER_BILINEAR", "FILTER_LANCZOS3", "scale_filter_table", "ComputeContext", "ComputeError", "ImageUniforms", "MixMode", "PictureSample", "Timer",
         "VideoMixer", "PictureAnimator", "DeviceFrame", "ElementState", "ComputedPictureState", "element_state", "compute_picture_state",
-        "ANCHOR_TOP_LEFT", "ANCHOR_TOP_RIGHT", "ANCHOR_BOTTOM_LEFT", "ANCHOR_BOTTOM_RIGHT", "available_compute_devices", "compose", "create_picture_sample", "kernel_launch_count",
+        "ANCHOR_TOP_LEFT", "ANCHOR_TOP_RIGHT", "ANCHOR_BOTTOM_LEFT", "ANCHOR_BOTTOM_RIGHT", "available_compute_devices", "compose", "create_picture_sample", "upload_many", "kernel_launch_count",
         "kernel_module_image", "lib", "make_compute_context")
 
 

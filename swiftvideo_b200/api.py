@@ -149,6 +149,7 @@ def _load():
     l.svb_picture_sample_from_planes.argtypes = [C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_void_p,
                                                  C.c_void_p]
     l.svb_animate_picture.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_float, C.c_char_p, C.c_void_p]
+    l.svb_upload_compute_pictures.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     l.svb_picture_device_frame.argtypes = [C.c_void_p, C.c_void_p]
     l.svb_picture_consumed_on.argtypes = [C.c_void_p, C.c_void_p]
     l.svb_gather_picture.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
@@ -474,6 +475,15 @@ class PictureAnimator:
         h = C.c_void_p()
         _check(lib.svb_animator_apply(self._h, pict._h, float(now), C.byref(h)))
         return PictureSample(h) if h else None
+
+
+def upload_many(ctx, picts, max_planes=3, retain_cpu_buffer=True, wait=True):
+    """svb_upload_compute_pictures: a batch upload; neighbours in page-locked host memory travel as one copy."""
+    n = len(picts)
+    arr = (C.c_void_p * max(n, 1))(*[p._h for p in picts])
+    outs = (C.c_void_p * max(n, 1))()
+    _check(lib.svb_upload_compute_pictures(ctx._h, arr, n, int(max_planes), int(retain_cpu_buffer), int(wait), outs))
+    return [PictureSample(C.c_void_p(outs[i])) for i in range(n)]
 
 
 def scale_filter_table(filter, src_n, dst_n):

@@ -262,6 +262,23 @@ svb_status svb_upload_compute_picture(svb_context* ctx, const svb_picture* pict,
         *out = wrap(uploadComputePicture(ctx->c, *pict->p, max_planes, retain_cpu_buffer != 0, wait != 0));
     });
 }
+svb_status svb_upload_compute_pictures(svb_context* ctx, const svb_picture* const* picts, int count, int max_planes, int retain_cpu_buffer, int wait, svb_picture** outs) {
+    return guard([&] {
+        need(ctx, "ctx");
+        if (count < 0) throw ComputeError(ErrorCode::invalidValue, "negative picture count");
+        if (count > 0) {
+            need(picts, "picts");
+            need(outs, "outs");
+        }
+        std::vector<const PictureSample*> ps;
+        for (int i = 0; i < count; ++i) {
+            need(picts[i], "pict");
+            ps.push_back(picts[i]->p.get());
+        }
+        std::vector<PictureSample> up = uploadComputePictures(ctx->c, ps, max_planes, retain_cpu_buffer != 0, wait != 0);
+        for (int i = 0; i < count; ++i) outs[i] = wrap(std::move(up[(size_t)i]));
+    });
+}
 static svb_status barrier(const BarrierResult& r, const svb_picture* pict, svb_picture** out, svb_event_error* err) {
     if (r.ok) {
         // an untouched sample passes through as another handle of the same sample
@@ -548,20 +565,29 @@ svb_status svb_video_mixer_tick_many(svb_mixer* const* mixers, int count, const 
         need(layer_counts, "layer_counts");
         std::vector<VideoMixer*> ms;
         size_t at = 0;
+        std::vector<const PictureSample*> all;
         for (int i = 0; i < count; ++i) {
             need(mixers[i], "mixer");
             ms.push_back(mixers[i]->m.get());
-            ComputeContext* c = ms.back()->computeContext();
-            if (!c) throw ComputeError(ErrorCode::badContextState, "No context");
+            if (!ms.back()->computeContext()) throw ComputeError(ErrorCode::badContextState, "No context");
             if (layer_counts[i] < 0) throw ComputeError(ErrorCode::invalidValue, "negative layer count");
             if (layer_counts[i] > 0) need(layers, "layers");
             for (int k = 0; k < layer_counts[i]; ++k, ++at) {
                 need(layers[at], "layer");
-                const PictureSample& src = *layers[at]->p;
-                if (src.bufferType() == BufferType::cpu) ms.back()->push(uploadComputePicture(*c, src, 3, false, false));
-                else ms.back()->push(layers[at]->p);
+                all.push_back(layers[at]->p.get());
             }
         }
+        // the tick's CPU layers go up together: neighbours in page-locked memory travel as one copy (mixers of one tick share a context:
+        // mixMany checks it)
+        for (VideoMixer* m : ms)
+            if (m->computeContext()->ctx != ms[0]->computeContext()->ctx) throw ComputeError(ErrorCode::invalidContext, "tick_many: mixers must share one compute context");
+        std::vector<PictureSample> up = uploadComputePictures(*ms[0]->computeContext(), all, 3, false, false);
+        at = 0;
+        for (int i = 0; i < count; ++i)
+            for (int k = 0; k < layer_counts[i]; ++k, ++at) {
+                if (layers[at]->p->bufferType() == BufferType::cpu) ms[i]->push(std::move(up[at]));
+                else ms[i]->push(layers[at]->p);
+            }
         std::vector<PictureSample> res(count);
         VideoMixer::mixMany(ms.data(), count, time, res.data(), false);
         for (int i = 0; i < count; ++i) outs[i] = wrap(downloadComputePicture(*ms[i]->computeContext(), res[i], true, wait != 0));

@@ -99,11 +99,10 @@ InternalContext::~InternalContext() {
         for (CUevent e : kv.second.after)
             if (e) cu().cuEventDestroy(e);
     }
-    for (auto& kv : hostPool) {
-        cu().cuMemFreeHost(kv.second.p);
+    for (auto& kv : hostPool)  // (the blocks are pieces of the chunks below)
         for (CUevent e : kv.second.after)
             if (e) cu().cuEventDestroy(e);
-    }
+    for (void* c : hostChunks) cu().cuMemFreeHost(c);
     for (CUevent e : spareEvents) cu().cuEventDestroy(e);
     if (module) cu().cuModuleUnload(module);
     if (compute) cu().cuStreamDestroy(compute);
@@ -209,9 +208,17 @@ void* InternalContext::allocHost(size_t size, CUstream writer) {
         }
         return b.p;
     }
-    void* p = nullptr;
-    check(drv().cuMemHostAlloc(&p, size, 0), "cuMemHostAlloc");
-    if (std::getenv("SVB_DEBUG_POOL")) fprintf(stderr, "[svb] cuMemHostAlloc %zu\n", size);
+    std::lock_guard<std::mutex> g(mu);
+    if (hostArenaLeft < size) {  // (what is left of the old chunk stays unused: at most one picture's worth)
+        const size_t chunk = std::max<size_t>(size, (size_t)128 << 20);
+        void* c = nullptr;
+        check(drv().cuMemHostAlloc(&c, chunk, 0), "cuMemHostAlloc");
+        if (std::getenv("SVB_DEBUG_POOL")) fprintf(stderr, "[svb] cuMemHostAlloc %zu\n", chunk);
+        hostChunks.push_back(c);
+        hostArena = (uint8_t*)c, hostArenaLeft = chunk;
+    }
+    void* p = hostArena;
+    hostArena += size, hostArenaLeft -= size;
     return p;
 }
 void InternalContext::releaseHost(void* p, size_t size) {
@@ -690,6 +697,99 @@ PictureSample uploadComputePicture(const ComputeContext& ctx, const PictureSampl
         } else {  // the caller learns from `done` when the source bytes may be reused
             out.done = std::make_shared<Event>(ctx.ctx);
             check(drv().cuEventRecord(out.done->e, ctx.ctx->upload), "cuEventRecord");
+        }
+    }
+    return out;
+}
+
+namespace {
+// the tight back-to-back layout of a CPU picture's planes: offsets, total; false when the planes do not lie that way in host memory
+// or would not be 256-byte aligned on the device
+bool tightLayout(const PictureSample& p, int maxPlanes, std::vector<size_t>& off) {
+    const int n = std::min((int)p.imgBuffer.planes.size(), maxPlanes);
+    if (n < 1 || (int)p.imgBuffer.buffers.size() < n) return false;
+    off.assign((size_t)n + 1, 0);
+    for (int i = 0; i < n; ++i) {
+        const size_t bytes = (size_t)(int)p.imgBuffer.planes[(size_t)i].size.y * (size_t)p.imgBuffer.planes[(size_t)i].stride;
+        if (off[(size_t)i] % 256 || p.imgBuffer.buffers[(size_t)i].size < bytes || p.imgBuffer.buffers[(size_t)i].ptr != p.imgBuffer.buffers[0].ptr + off[(size_t)i]) return false;
+        off[(size_t)i + 1] = off[(size_t)i] + bytes;
+    }
+    return true;
+}
+}  // namespace
+
+std::vector<PictureSample> uploadComputePictures(const ComputeContext& ctx, const std::vector<const PictureSample*>& picts, int maxPlanes, bool retainCpuBuffer,
+                                                 bool wait) {
+    if (!ctx.ctx) throw ComputeError(ErrorCode::badContextState, "No context");
+    const size_t n = picts.size();
+    std::vector<PictureSample> out(n);
+    constexpr size_t kMaxRun = (size_t)96 << 20;  // bytes per copy: large enough to amortise, small enough that the first layers land early
+    bool any = false;
+    size_t i = 0;
+    std::vector<size_t> off, offj;
+    while (i < n) {
+        const PictureSample& p = *picts[i];
+        if (p.bufferType() != BufferType::cpu) {
+            out[i] = p;
+            ++i;
+            continue;
+        }
+        any = true;
+        size_t j = i;
+        std::vector<std::vector<size_t>> offs;
+        std::vector<size_t> at;  // byte offset of each picture of the run from the first one's first byte
+        if (tightLayout(p, maxPlanes, off)) {
+            offs.push_back(off), at.push_back(0);
+            const uint8_t* base = p.imgBuffer.buffers[0].ptr;
+            size_t end = off.back();
+            for (j = i + 1; j < n; ++j) {
+                const PictureSample& q = *picts[j];
+                if (q.bufferType() != BufferType::cpu || !tightLayout(q, maxPlanes, offj)) break;
+                const size_t next = (end + 4095) & ~(size_t)4095;  // the page-locked pool hands out multiples of 4 KB
+                if (q.imgBuffer.buffers[0].ptr != base + next || next + offj.back() > kMaxRun) break;
+                offs.push_back(offj), at.push_back(next);
+                end = next + offj.back();
+            }
+            if (j - i < 2) j = i;  // a run of one: the ordinary path
+            else {
+                CtxGuard g(ctx.ctx);
+                auto whole = createBuffer(ctx, end);
+                check(drv().cuMemcpyHtoDAsync(whole->mem, base, end, ctx.ctx->upload), "cuMemcpyHtoDAsync");
+                auto ready = std::make_shared<Event>(ctx.ctx);
+                check(drv().cuEventRecord(ready->e, ctx.ctx->upload), "cuEventRecord");
+                for (size_t k = i; k < j; ++k) {
+                    const PictureSample& q = *picts[k];
+                    PictureSample& o = out[k];
+                    o = q;
+                    o.imgBuffer.computeTextures.clear();
+                    const std::vector<size_t>& ok = offs[k - i];
+                    for (size_t pl = 0; pl + 1 < ok.size(); ++pl) {
+                        auto t = std::make_shared<ComputeBuffer>(whole, at[k - i] + ok[pl], ok[pl + 1] - ok[pl]);
+                        t->ready = ready, t->noteWrite(ctx.ctx->upload), t->hostKeep = q.imgBuffer.buffers[pl].base;
+                        o.imgBuffer.computeTextures.push_back(t);
+                    }
+                    if (!retainCpuBuffer) o.imgBuffer.buffers.clear();
+                    o.imgBuffer.bufferType = BufferType::gpu;
+                    o.done = nullptr;
+                }
+            }
+        }
+        if (j == i) {
+            out[i] = uploadComputePicture(ctx, p, maxPlanes, retainCpuBuffer, false);
+            out[i].done = nullptr;
+            j = i + 1;
+        }
+        i = j;
+    }
+    if (any) {
+        CtxGuard g(ctx.ctx);
+        if (wait) {
+            check(drv().cuStreamSynchronize(ctx.ctx->upload), "cuStreamSynchronize");
+        } else {  // one completion for the whole batch: the last copy queued
+            auto done = std::make_shared<Event>(ctx.ctx);
+            check(drv().cuEventRecord(done->e, ctx.ctx->upload), "cuEventRecord");
+            for (size_t k = 0; k < n; ++k)
+                if (picts[k]->bufferType() == BufferType::cpu) out[k].done = done;
         }
     }
     return out;

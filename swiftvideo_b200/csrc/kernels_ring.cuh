@@ -37,7 +37,25 @@ __device__ __forceinline__ bool mbar_try_u32(unsigned bar, unsigned parity, unsi
         : "memory");
     return ok != 0;
 }
+#ifndef SVB_RING_WAIT_HINT
+#define SVB_RING_WAIT_HINT 2000u
+#endif
 __device__ __forceinline__ void mbar_wait_u32(unsigned bar, unsigned parity) {
+#ifdef SVB_RING_LEAN_WAIT
+    // the whole loop in PTX: try-wait, branch -- no counter, no trap (three instructions a round instead of six)
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "SVB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra SVB_DONE;\n"
+        "bra SVB_WAIT;\n"
+        "SVB_DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity), "r"(SVB_RING_WAIT_HINT)
+        : "memory");
+    return;
+#endif
     unsigned ok;
     unsigned spin = 0;
     do {
@@ -48,7 +66,7 @@ __device__ __forceinline__ void mbar_wait_u32(unsigned bar, unsigned parity) {
             "selp.u32 %0, 1, 0, p;\n"
             "}\n"
             : "=r"(ok)
-            : "r"(bar), "r"(parity), "r"(2000u)
+            : "r"(bar), "r"(parity), "r"(SVB_RING_WAIT_HINT)
             : "memory");
         if (++spin > (1u << 22)) __trap();  // a copy that never lands must not hang the GPU
 #ifdef SVB_RING_WAIT_SLEEP

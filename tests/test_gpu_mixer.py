@@ -441,3 +441,42 @@ def test_two_threads_drive_mixers_of_one_context():
         for tick, (bytes_, placed) in enumerate(got):
             want = _oracle_mix(O.NV12, canvas, placed, imgs)
             assert (bytes_ == want).all(), (idx, tick, first_diff(bytes_, want))
+
+
+def test_batch_upload_coalesces_neighbours():
+    """svb_upload_compute_pictures: pictures created one after the other from the context's page-locked pool lie next to each other in host
+    memory and go up as ONE copy into ONE device block (device offsets mirror host offsets); a pageable picture in between and a GPU picture
+    take the ordinary paths; every picture's bytes arrive intact and compose bit-exactly."""
+    ctx = sv.make_compute_context(0)  # a context of its own: its page-locked pool holds no recycled blocks yet, so neighbours are neighbours
+    canvas = (256, 144)
+    fmts = [O.NV12, O.NV12, O.BGRA, O.Y420P, O.NV12, O.NV12]
+    sizes = [(256, 144), (128, 72), (64, 32), (128, 72), (130, 70), (128, 72)]   # 130x70: planes not 256-byte aligned -> its own copy
+    imgs = [scenes.random_image(f, w, h, 9500 + i) for i, (f, (w, h)) in enumerate(zip(fmts, sizes))]
+    host = []
+    for i, im in enumerate(imgs):
+        p = sv.create_picture_sample(im.width, im.height, FMT[im.format], f"p{i}", "w", pinned_from=None if i == 3 else ctx)  # 3: pageable
+        p.set_host_bytes(im.data)
+        host.append(p)
+    already = to_gpu(ctx, imgs[0], "gpu0")
+    ups = sv.upload_many(ctx, host + [already], retain_cpu_buffer=False, wait=False)
+    assert len(ups) == 7 and ups[6].device_frame().planes[0].ptr == already.device_frame().planes[0].ptr
+    for u in ups[:6]:
+        u.wait()
+    hp = [h.info().planes[0].host for h in host]
+    dp = [u.device_frame().planes[0].ptr for u in ups]
+    # 0, 1, 2 are neighbours in the pool (created in sequence, all tightly laid out): one block, device offsets = host offsets
+    assert dp[1] - dp[0] == hp[1] - hp[0] > 0 and dp[2] - dp[0] == hp[2] - hp[0]
+    f0 = ups[0].device_frame()
+    assert f0.planes[1].ptr - f0.planes[0].ptr == 256 * 144
+    for u, im in zip(ups[:6], imgs):
+        assert (fetch(ctx, u) == im.data).all()
+    placed = [_place(ups[0], canvas, sizes[0], (0, 0), canvas, z=0), _place(ups[1], canvas, sizes[1], (10, 8), (150, 84), z=1, opacity=0.7),
+              _place(ups[2], canvas, sizes[2], (100, 40), (96, 48), z=2, opacity=0.9), _place(ups[3], canvas, sizes[3], (30, 60), (128, 72), z=3, opacity=0.5),
+              _place(ups[4], canvas, sizes[4], (140, 10), (100, 54), z=4), _place(ups[5], canvas, sizes[5], (4, 90), (96, 50), z=5, opacity=0.8)]
+    mixer = sv.VideoMixer(ctx, canvas[0], canvas[1], sv.NV12, asset_id="m", workspace_id="w")
+    for p in placed:
+        assert mixer.push(p)
+    got = fetch(ctx, mixer.mix(1000))
+    want = _oracle_mix(O.NV12, canvas, placed, imgs)
+    assert (got == want).all(), first_diff(got, want)
+    mixer.close()
