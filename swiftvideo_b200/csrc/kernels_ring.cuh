@@ -90,7 +90,7 @@ extern "C" __global__ void __launch_bounds__(SVB_RING_THREADS, SVB_RING_MIN_CTAS
     const unsigned full0 = bars, empty0 = full0 + 8u * SVB_RING_STAGES, pfull0 = empty0 + 8u * SVB_RING_STAGES, pempty0 = pfull0 + 8u * SVB_RING_PLANS;
     const unsigned stage_bytes = (unsigned)(box_y_bytes + box_c_bytes) + SVB_RING_TAB_BYTES;
     unsigned char* const my_state = smem_raw + SVB_RING_HDR_BYTES + (size_t)(warp & 7) * SVB_STRIP_STATE_BYTES;
-    float2* const sY = reinterpret_cast<float2*>(my_state);  // [12 rows][32 lanes]: luma pairs of rows 0..7, then (U, V) of chroma rows 0..3
+    float2* const sY = reinterpret_cast<float2*>(my_state);  // [12 rows][SVB_STATE_PITCH_F2: 32 lanes + padding]: luma pairs of rows 0..7, then (U, V) of chroma rows 0..3
     const unsigned state = smem_u32(my_state) + 8u * lane;
     const unsigned plan0 = smem_u32(smem_raw + SVB_RING_HDR_BYTES + SVB_RING_WARPS * SVB_STRIP_STATE_BYTES);
     const unsigned stage0 = plan0 + (unsigned)SVB_RING_PLANS * (unsigned)plan_slot_bytes;
@@ -111,11 +111,11 @@ extern "C" __global__ void __launch_bounds__(SVB_RING_THREADS, SVB_RING_MIN_CTAS
     auto sts4 = [](unsigned a, const uint4 v) { asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); };
 
     // ---- the plan of tile t (t >= total_tiles: the end marker) into plan slot s: the planning warp, lane = layer ----------------
-    auto plan_tile = [&](int t, int s) {
+    auto plan_tile = [&](int t, int s, unsigned gbase) -> unsigned {  // gbase: staged layers planned before this tile; returns those of this tile
         const unsigned slot_a = plan0 + (unsigned)s * (unsigned)plan_slot_bytes;
         if (t >= total_tiles) {
             if (lane == 0) sts4(slot_a, make_uint4(0xffffu, 0u, 0u, 0u));
-            return;
+            return 0u;
         }
         const int f = __popc(__ballot_sync(0xffffffffu, t >= firstA)) + __popc(__ballot_sync(0xffffffffu, t >= firstB)) - 1;
         const int first = f < 32 ? __shfl_sync(0xffffffffu, firstA, f) : __shfl_sync(0xffffffffu, firstB, f - 32);
@@ -127,6 +127,7 @@ extern "C" __global__ void __launch_bounds__(SVB_RING_THREADS, SVB_RING_MIN_CTAS
         unsigned mode = PLAN_SKIP;
         bool covers = false, inner = false;
         uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, r2 = r0, r3 = r0, r4 = r0;
+        unsigned relY = 0, relC = 0, c1y = 0, codes = 0;  // the consumers' part of the record (below)
         if (lane < nl) {
             // every load of the plan is issued here, before anything is looked at (one trip to L2, not six): the layer's constants and
             // the records of the tile's two unit columns and four unit rows (indices clamped: an absent unit is masked below)
@@ -179,6 +180,24 @@ extern "C" __global__ void __launch_bounds__(SVB_RING_THREADS, SVB_RING_MIN_CTAS
                     r2 = c0;
                     r3.x = c1.x, r3.y = c1.y;
                     r4 = make_uint4(cf, rf, 0u, 0u);
+                    if (fits) {
+                        // what a consumer warp would otherwise derive per layer and unit: the staged boxes' addresses minus the footprint's
+                        // origin (relative to the stage), and the body each of the tile's eight units takes (four bits per unit, SVB_BODY_*)
+                        const unsigned pitchY = c1.w & 0xffffu, pitchC = c1.w >> 16, cstep = fmt == SVB_NV12 ? 2u : 1u;
+                        relY = 0u - ix0 - jy0 * pitchY, relC = (unsigned)box_y_bytes - ic0 * cstep - jc0 * pitchC;
+                        c1y = cstep | ((fmt == SVB_NV12 ? 1u : (unsigned)box_c_bytes / 2u) << 8);
+                        const bool op01 = (lflags & SVB_LAYER_OPACITY_01) != 0, unit = (lflags & SVB_LAYER_UNIT_OPACITY) != 0;
+#pragma unroll
+                        for (int u = 0; u < SVB_RING_WARPS; ++u) {
+                            const unsigned cfl = (cf >> (8 * (u & 1))) & 0xffu, rfl = (rf >> (8 * (u >> 1))) & 0xffu, both = cfl & rfl;
+                            unsigned code = SVB_BODY_NONE;
+                            if (both & SVB_RREC_TOUCH) {
+                                if (!((both & SVB_UREC_FULL) && (cfl & SVB_UREC_XFREE)) || !op01) code = op01 && !((cfl | rfl) & SVB_UREC_MIXED) ? SVB_BODY_EDGE_LEAN : SVB_BODY_EDGE;
+                                else code = (unit ? SVB_BODY_OPAQUE : SVB_BODY_BLEND) + ((both & SVB_UREC_HALF) ? 1u : 0u);
+                            }
+                            codes |= code << (4 * u);
+                        }
+                    }
                 }
                 r0.x = mode | ((unsigned)lane << 8) | (fmt << 16) | (lflags << 20);
             }
@@ -194,7 +213,13 @@ extern "C" __global__ void __launch_bounds__(SVB_RING_THREADS, SVB_RING_MIN_CTAS
         const unsigned below = act & ((1u << lane) - 1u);
         if ((act >> lane) & 1u) {
             const unsigned a = slot_a + SVB_RPLAN_HDR_BYTES + SVB_RPLAN_REC_BYTES * (unsigned)__popc(below);
-            sts4(a, r0), sts4(a + 16, r1), sts4(a + 32, r2), sts4(a + 48, r3), sts4(a + 64, r4);
+            uint4 k0 = make_uint4(0u, 0u, 0u, 0u);
+            if (mode >= PLAN_STAGED) {  // staged layer number gs of this CTA lives in stage gs % 3 and its barriers are in their (gs / 3)-th use
+                const unsigned gs = gbase + (unsigned)__popc(below & stg), b = gs % SVB_RING_STAGES, bY = stage0 + b * stage_bytes;
+                k0 = make_uint4(bY + relY, bY + relC, bY + tab_off, (full0 + 8u * b) | 0x40000000u | (((gs / SVB_RING_STAGES) & 1u) << 31));
+            }
+            sts4(a, k0), sts4(a + 16, make_uint4(r0.w, c1y, codes, r0.x));
+            sts4(a + 32, r0), sts4(a + 48, r1), sts4(a + 64, r2), sts4(a + 80, r3), sts4(a + 96, r4);
         }
         const unsigned smask = __reduce_or_sync(0xffffffffu, ((act & stg) >> lane) & 1u ? 1u << __popc(below) : 0u);
         if (lane == 0) {
@@ -204,10 +229,11 @@ extern "C" __global__ void __launch_bounds__(SVB_RING_THREADS, SVB_RING_MIN_CTAS
             sts4(slot_a + 32, make_uint4((unsigned)p0, (unsigned)(p0 >> 32), (unsigned)p1, (unsigned)(p1 >> 32)));
             sts4(slot_a + 48, make_uint4((unsigned)p2, (unsigned)(p2 >> 32), (unsigned)F->out_stride[1], (unsigned)F->out_stride[2]));
         }
+        return (unsigned)__popc(act & stg);
     };
     // the async copies of the staged layer whose plan record lies at shared-memory address ra, into stage b (one elected lane of the issuing warp)
     auto issue = [&](unsigned ra, unsigned b) {
-        const uint4 r0 = lds_u4(ra), r1 = lds_u4(ra + 16), r2 = lds_u4(ra + 32), r3 = lds_u4(ra + 48);
+        const uint4 r0 = lds_u4(ra + 32), r1 = lds_u4(ra + 48), r2 = lds_u4(ra + 64), r3 = lds_u4(ra + 80);
         if (elect_one()) {
             const unsigned dst = stage0 + b * stage_bytes, mb = full0 + 8u * b;
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(r1.x) : "memory");
@@ -238,6 +264,7 @@ extern "C" __global__ void __launch_bounds__(SVB_RING_THREADS, SVB_RING_MIN_CTAS
         // is claimed and planned -- up to three tiles ahead, so a consumer never waits for a plan.
         unsigned gi = 0;       // staged layers issued
         unsigned planned = 0;  // tiles planned
+        unsigned gplan = 0;    // staged layers planned
         unsigned n = 0, i = 0, smask = 0;  // the tile whose staged layers are being issued, its next listed layer, the staged layers left (bit 0 = layer i)
         bool have_tile = false, last_planned = false;
         for (unsigned idle = 0;;) {
@@ -265,7 +292,7 @@ extern "C" __global__ void __launch_bounds__(SVB_RING_THREADS, SVB_RING_MIN_CTAS
                     int t = 0;
                     if (lane == 0) t = atomicAdd(tile_counter, 1);
                     t = __shfl_sync(0xffffffffu, t, 0);
-                    plan_tile(t, (int)slot);
+                    gplan += plan_tile(t, (int)slot, gplan);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(pfull0 + 8u * slot);
                     ++planned, did = true, last_planned = t >= total_tiles;
@@ -280,7 +307,9 @@ extern "C" __global__ void __launch_bounds__(SVB_RING_THREADS, SVB_RING_MIN_CTAS
             }
         }
     }
-    unsigned g = 0;  // staged layers met by this warp
+    // (per-warp constants of the layer loop: this warp's unit of a tile and where its table blocks lie inside a stage)
+    const int ux = warp & 1, uy = warp >> 1;
+    const unsigned tabc_off = (unsigned)ux * SVB_UCOL_WORDS * 4u, tabr_off = 2u * SVB_UCOL_WORDS * 4u + (unsigned)uy * SVB_UROW_WORDS * 4u, code_shift = 4u * (unsigned)warp;
     for (unsigned n = 0;; ++n) {  // tile ordinal of this CTA
         const unsigned slot = n % SVB_RING_PLANS, plan = plan0 + slot * (unsigned)plan_slot_bytes;
         mbar_wait_u32(pfull0 + 8u * slot, (n / SVB_RING_PLANS) & 1u);  // this tile's plan
@@ -297,7 +326,6 @@ extern "C" __global__ void __launch_bounds__(SVB_RING_THREADS, SVB_RING_MIN_CTAS
     uint8_t* const oY = (uint8_t*)(((unsigned long long)h2.y << 32) | h2.x);                 \
     uint8_t* const oU = (uint8_t*)(((unsigned long long)h2.w << 32) | h2.z);                 \
     uint8_t* const oV = (uint8_t*)(((unsigned long long)h3.y << 32) | h3.x);
-        const int ux = warp & 1, uy = warp >> 1;                                 // this warp's unit of the tile
         const int xt = x0 + ux * SVB_UNIT_W + 2 * lane, yt = y0 + uy * SVB_UNIT_H;  // this lane's columns xt, xt+1 x rows yt .. yt+7
         const bool live = xt < W && yt < H;                                      // W and H even are planner preconditions
 
@@ -308,7 +336,7 @@ extern "C" __global__ void __launch_bounds__(SVB_RING_THREADS, SVB_RING_MIN_CTAS
             for (int r = 0; r < SVB_UNIT_H; ++r) {
                 unsigned w0 = 0;
                 if (live && yt + r < H) w0 = *(const unsigned short*)(oY + (size_t)(yt + r) * sYb + xt);
-                sY[r * 32 + lane] = bytes2(opaque(w0 & 0xff), opaque(w0 >> 8));
+                sY[r * SVB_STATE_PITCH_F2 + lane] = bytes2(opaque(w0 & 0xff), opaque(w0 >> 8));
             }
 #pragma unroll
             for (int k = 0; k < SVB_UNIT_H / 2; ++k) {
@@ -321,88 +349,104 @@ extern "C" __global__ void __launch_bounds__(SVB_RING_THREADS, SVB_RING_MIN_CTAS
                         cu = oU[(size_t)((yt >> 1) + k) * sUb + (xt >> 1)], cv = oV[(size_t)((yt >> 1) + k) * sVb + (xt >> 1)];
                     }
                 }
-                sY[(SVB_UNIT_H + k) * 32 + lane] = bytes2(opaque(cu), opaque(cv));
+                sY[(SVB_UNIT_H + k) * SVB_STATE_PITCH_F2 + lane] = bytes2(opaque(cu), opaque(cv));
             }
         } else if (!(h0.w & 1u)) {  // (bit 0: the first listed layer overwrites every sample without reading it)
 #pragma unroll
-            for (int r = 0; r < SVB_UNIT_H; ++r) sY[r * 32 + lane] = splat(0.f);
+            for (int r = 0; r < SVB_UNIT_H; ++r) sY[r * SVB_STATE_PITCH_F2 + lane] = splat(0.f);
 #pragma unroll
-            for (int k = 0; k < SVB_UNIT_H / 2; ++k) sY[(SVB_UNIT_H + k) * 32 + lane] = splat(128.f);
+            for (int k = 0; k < SVB_UNIT_H / 2; ++k) sY[(SVB_UNIT_H + k) * SVB_STATE_PITCH_F2 + lane] = splat(128.f);
         }
 
 #pragma unroll 1
         for (unsigned i = 0; i < nact; ++i) {
             const unsigned ra = plan + SVB_RPLAN_HDR_BYTES + SVB_RPLAN_REC_BYTES * i;
-            const uint4 r0 = lds_u4(ra), r1 = lds_u4(ra + 16);
-            const unsigned mode = r0.x & 0xffu;
-            if (mode >= PLAN_STAGED) {
-                const unsigned b = g % SVB_RING_STAGES, par = (g / SVB_RING_STAGES) & 1u;
-                const uint2 uf = lds_u2(ra + 64);
-                const unsigned cfl = (uf.x >> (8 * ux)) & 0xffu, rfl = (uf.y >> (8 * uy)) & 0xffu, both = cfl & rfl;
+            const uint4 k0 = lds_u4(ra), k1 = lds_u4(ra + 16);  // the consumers' part of the record: everything below is ready to use (ring_layout.h)
+            if (k0.w) {                                         // a staged layer
+                const unsigned code = (k1.z >> code_shift) & 0xfu, mb = k0.w & 0x00ffffffu;
                 // (a warp the layer does not reach waits as well: an arrival on `empty` is only in the right phase once the stage's copies were issued)
-                mbar_wait_u32(full0 + 8u * b, par);
-                if (both & SVB_RREC_TOUCH) {  // the layer reaches into this warp's unit
-                    const unsigned fmt = (r0.x >> 16) & 0xfu, lflags = r0.x >> 20;
-                    const unsigned pitchY = r1.y & 0xffffu, pitchC = r1.y >> 16, cstep = fmt == SVB_NV12 ? 2u : 1u;
-                    const unsigned bY = stage0 + b * stage_bytes, bC = bY + (unsigned)box_y_bytes;
-                    const unsigned tabc = bY + tab_off + (unsigned)ux * SVB_UCOL_WORDS * 4u, tabr = bY + tab_off + 2u * SVB_UCOL_WORDS * 4u + (unsigned)uy * SVB_UROW_WORDS * 4u;
-                    const unsigned vofs = fmt == SVB_NV12 ? 1u : (unsigned)box_c_bytes / 2u;
-                    const unsigned colY = bY - (r0.y & 0xffffu) - (r0.y >> 16) * pitchY, colC = bC - (r0.z & 0xffffu) * cstep - (r0.z >> 16) * pitchC;
-                    const float alpha = __uint_as_float(r0.w);
-                    if (!((both & SVB_UREC_FULL) && (cfl & SVB_UREC_XFREE)) || !(lflags & SVB_LAYER_OPACITY_01)) {
-                        const SvbLayerDesc* __restrict__ L = &F->layers[(r0.x >> 8) & 0xffu];
+                mbar_wait_u32(mb, k0.w >> 31);
+                if (code != SVB_BODY_NONE) {  // the layer reaches into this warp's unit
+                    const unsigned colY = k0.x, colC = k0.y, tabc = k0.z + tabc_off, tabr = k0.z + tabr_off, cstep = k1.y & 0xffu, vofs = k1.y >> 8;
+                    const float alpha = __uint_as_float(k1.x);
+                    if (code == SVB_BODY_BLEND) strip_layer<false, false>(colY, colC, cstep, vofs, tabc, tabr, lane, alpha, one, state);
+                    else if (code == SVB_BODY_OPAQUE) strip_layer<true, false>(colY, colC, cstep, vofs, tabc, tabr, lane, alpha, one, state);
+                    else if (code == SVB_BODY_OPAQUE_HALF) strip_layer<true, true>(colY, colC, cstep, vofs, tabc, tabr, lane, alpha, one, state);
+                    else if (code == SVB_BODY_BLEND_HALF) strip_layer<false, true>(colY, colC, cstep, vofs, tabc, tabr, lane, alpha, one, state);
+                    else {
+                        const SvbLayerDesc* __restrict__ L = &F->layers[(k1.w >> 8) & 0xffu];
                         const float4 fc = ldrow(L->u.fillColor, 0);
                         const float3 fl = rgb2yuv(fc.x, fc.y, fc.z);
                         const float af = mul(alpha, fc.w);
                         // lean: no sample of the unit lies inside the border rectangle but outside the picture (without a border or letterbox: none ever does)
-                        if ((lflags & SVB_LAYER_OPACITY_01) && !((cfl | rfl) & SVB_UREC_MIXED)) strip_layer_edge<true>(colY, colC, cstep, vofs, tabc, tabr, lane, alpha, one, make_float4(fl.x, fl.y, fl.z, 0.f), af, sY);
+                        if (code == SVB_BODY_EDGE_LEAN) strip_layer_edge<true>(colY, colC, cstep, vofs, tabc, tabr, lane, alpha, one, make_float4(fl.x, fl.y, fl.z, 0.f), af, sY);
                         else strip_layer_edge<false>(colY, colC, cstep, vofs, tabc, tabr, lane, alpha, one, make_float4(fl.x, fl.y, fl.z, 0.f), af, sY);
-                    } else if (lflags & SVB_LAYER_UNIT_OPACITY) {
-                        if (both & SVB_UREC_HALF) strip_layer<true, true>(colY, colC, cstep, vofs, tabc, tabr, lane, alpha, one, state);
-                        else strip_layer<true, false>(colY, colC, cstep, vofs, tabc, tabr, lane, alpha, one, state);
-                    } else {
-                        if (both & SVB_UREC_HALF) strip_layer<false, true>(colY, colC, cstep, vofs, tabc, tabr, lane, alpha, one, state);
-                        else strip_layer<false, false>(colY, colC, cstep, vofs, tabc, tabr, lane, alpha, one, state);
                     }
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(empty0 + 8u * b);  // this warp has left the stage
-                ++g;
+                if (lane == 0) mbar_arrive(mb + 8u * SVB_RING_STAGES);  // this warp has left the stage (`empty` lies SVB_RING_STAGES barriers behind `full`)
             } else {
-                const SvbLayerDesc* __restrict__ L = &F->layers[(r0.x >> 8) & 0xffu];
+                const uint4 r1 = lds_u4(ra + 48);
+                const SvbLayerDesc* __restrict__ L = &F->layers[(k1.w >> 8) & 0xffu];
                 float* const py = reinterpret_cast<float*>(sY + lane);
                 const uint32_t* __restrict__ colblk = tables + r1.z + ux * SVB_UCOL_WORDS;
                 const uint32_t* __restrict__ rowblk = tables + r1.w + uy * SVB_UROW_WORDS;
                 if (yt < H) {
-                    if (mode == PLAN_TABLE_RGBA) strip_rgba_layer(L, colblk, rowblk, lane, xt, yt, W, H, py, py + SVB_UNIT_W * SVB_UNIT_H);
-                    else strip_generic_layer(L, xt, yt, W, H, py, py + SVB_UNIT_W * SVB_UNIT_H);
+                    if ((k1.w & 0xffu) == PLAN_TABLE_RGBA) strip_rgba_layer(L, colblk, rowblk, lane, xt, yt, W, H, py, py + SVB_STATE_PITCH_F * SVB_UNIT_H);
+                    else strip_generic_layer(L, xt, yt, W, H, py, py + SVB_STATE_PITCH_F * SVB_UNIT_H);
                 }
             }
         }
 
-        // ---- the unit's bytes: two luma bytes per lane and row, one (U, V) pair per lane and chroma row -----------------------
+        // ---- the unit's bytes.  A whole unit of an NV12 target whose planes allow 16-byte stores leaves as TWO stores per warp: the
+        // state is read transposed -- a lane takes 16 consecutive samples of one row (rows are padded so that these reads spread over
+        // all banks, svb_desc.h) -- so that one st.v4 covers the eight luma rows (64 bytes each) and a second one, of the lower half
+        // warp, the four chroma rows.  Anything else (a unit cut by the picture's edge, planar chroma, odd alignment): two bytes per
+        // lane and row.
+        __syncwarp();
         if (live) {
             SVB_RING_TARGET()
             const float2 ONE = splat(one);
-            auto pack = [&](float2 v) {  // two integer-valued floats in 0..255 -> two bytes: + 2^23 leaves them in the low mantissa bits
-                const float2 x = add2<true>(v, splat(8388608.f), ONE);
-                return (unsigned short)__byte_perm(__float_as_uint(x.x), __float_as_uint(x.y), 0x0040);
-            };
-            uint8_t* pY = oY + (size_t)yt * sYb + xt;
-            const int nrow = min(SVB_UNIT_H, H - yt);
-#pragma unroll 1
-            for (int r = 0; r < nrow; ++r, pY += sYb) *(unsigned short*)pY = pack(sY[r * 32 + lane]);
-            if (ofmt == SVB_NV12) {
-                uint8_t* pC = oU + (size_t)(yt >> 1) * sUb + xt;
-#pragma unroll 1
-                for (int k = 0; 2 * k < nrow; ++k, pC += sUb) *(unsigned short*)pC = pack(sY[(SVB_UNIT_H + k) * 32 + lane]);
+            const int xu = x0 + ux * SVB_UNIT_W;
+            if (ofmt == SVB_NV12 && xu + SVB_UNIT_W <= W && yt + SVB_UNIT_H <= H && ((h2.x | h2.z | (unsigned)sYb | (unsigned)sUb) & 15u) == 0u) {
+                auto pack4 = [&](const float4 v) {  // four integer-valued floats in 0..255 -> four bytes: + 2^23 leaves them in the low mantissa bits
+                    const float2 a = add2<true>(make_float2(v.x, v.y), splat(8388608.f), ONE), b = add2<true>(make_float2(v.z, v.w), splat(8388608.f), ONE);
+                    return __byte_perm(__byte_perm(__float_as_uint(a.x), __float_as_uint(a.y), 0x0040), __byte_perm(__float_as_uint(b.x), __float_as_uint(b.y), 0x0040), 0x5410);
+                };
+                auto row16 = [&](unsigned a) {
+                    const float4 v0 = lds_f4(a), v1 = lds_f4(a + 16u), v2 = lds_f4(a + 32u), v3 = lds_f4(a + 48u);
+                    return make_uint4(pack4(v0), pack4(v1), pack4(v2), pack4(v3));
+                };
+                const unsigned sbase = smem_u32(my_state);
+                {
+                    const int r = lane & 7, seg = lane >> 3;
+                    *reinterpret_cast<uint4*>(oY + (size_t)(yt + r) * sYb + xu + 16 * seg) = row16(sbase + (unsigned)r * SVB_STATE_PITCH_B + 64u * (unsigned)seg);
+                }
+                if (lane < 16) {
+                    const int r = lane & 3, seg = lane >> 2;
+                    *reinterpret_cast<uint4*>(oU + (size_t)((yt >> 1) + r) * sUb + xu + 16 * seg) = row16(sbase + (unsigned)(SVB_UNIT_H + r) * SVB_STATE_PITCH_B + 64u * (unsigned)seg);
+                }
             } else {
-                uint8_t* pU = oU + (size_t)(yt >> 1) * sUb + (xt >> 1);
-                uint8_t* pV = oV + (size_t)(yt >> 1) * sVb + (xt >> 1);
+                auto pack = [&](float2 v) {  // two integer-valued floats in 0..255 -> two bytes
+                    const float2 x = add2<true>(v, splat(8388608.f), ONE);
+                    return (unsigned short)__byte_perm(__float_as_uint(x.x), __float_as_uint(x.y), 0x0040);
+                };
+                uint8_t* pY = oY + (size_t)yt * sYb + xt;
+                const int nrow = min(SVB_UNIT_H, H - yt);
 #pragma unroll 1
-                for (int k = 0; 2 * k < nrow; ++k, pU += sUb, pV += sVb) {
-                    const unsigned short p = pack(sY[(SVB_UNIT_H + k) * 32 + lane]);
-                    *pU = (uint8_t)(p & 0xff), *pV = (uint8_t)(p >> 8);
+                for (int r = 0; r < nrow; ++r, pY += sYb) *(unsigned short*)pY = pack(sY[r * SVB_STATE_PITCH_F2 + lane]);
+                if (ofmt == SVB_NV12) {
+                    uint8_t* pC = oU + (size_t)(yt >> 1) * sUb + xt;
+#pragma unroll 1
+                    for (int k = 0; 2 * k < nrow; ++k, pC += sUb) *(unsigned short*)pC = pack(sY[(SVB_UNIT_H + k) * SVB_STATE_PITCH_F2 + lane]);
+                } else {
+                    uint8_t* pU = oU + (size_t)(yt >> 1) * sUb + (xt >> 1);
+                    uint8_t* pV = oV + (size_t)(yt >> 1) * sVb + (xt >> 1);
+#pragma unroll 1
+                    for (int k = 0; 2 * k < nrow; ++k, pU += sUb, pV += sVb) {
+                        const unsigned short p = pack(sY[(SVB_UNIT_H + k) * SVB_STATE_PITCH_F2 + lane]);
+                        *pU = (uint8_t)(p & 0xff), *pV = (uint8_t)(p >> 8);
+                    }
                 }
             }
         }

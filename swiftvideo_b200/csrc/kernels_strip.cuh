@@ -118,7 +118,7 @@ __device__ __forceinline__ void strip_layer(unsigned colY, unsigned colC, unsign
         }
         raw(q1, w1.w);
         raw(q2, w2.w);
-        const float2 ci1 = lds_state(sa), ci2 = lds_state(sa + 256u);
+        const float2 ci1 = lds_state(sa), ci2 = lds_state(sa + SVB_STATE_PITCH_B);
         conv(B, q1);
         out_row(T, B, w1, ci1, sa);
         if (fetch2) {
@@ -127,7 +127,7 @@ __device__ __forceinline__ void strip_layer(unsigned colY, unsigned colC, unsign
             conv(B, q0);
         }
         conv(T, q2);
-        out_row(B, T, w2, ci2, sa + 256u);
+        out_row(B, T, w2, ci2, sa + SVB_STATE_PITCH_B);
     };
     unsigned ent = rows, sa = st;
 #pragma unroll 1
@@ -141,7 +141,7 @@ __device__ __forceinline__ void strip_layer(unsigned colY, unsigned colC, unsign
 #pragma unroll 1
         for (int n = half ? 2 : 4; n > 0; --n) {  // two rows per pass: the tap registers trade roles row by row and are back in place after a pass
             pass(ent, sa, (reload & 1u) != 0u, (reload & 2u) != 0u);
-            reload >>= 2, ent += 32u, sa += 512u;
+            reload >>= 2, ent += 32u, sa += 2u * SVB_STATE_PITCH_B;
         }
     }
 }
@@ -179,7 +179,7 @@ __device__ __noinline__ void strip_layer_edge(unsigned colY, unsigned colC, unsi
         const float2 t00 = unorm2<PK>(bytes2(lds_u8(b00 + w.z), lds_u8(b10 + w.z))), t10 = unorm2<PK>(bytes2(lds_u8(b01 + w.z), lds_u8(b11 + w.z)));
         const float2 t01 = unorm2<PK>(bytes2(lds_u8(b00 + w.w), lds_u8(b10 + w.w))), t11 = unorm2<PK>(bytes2(lds_u8(b01 + w.w), lds_u8(b11 + w.w)));
         const float2 v = bilin2<PK>(mul2<PK>(NA, NB), mul2<PK>(A, NB), mul2<PK>(NA, Bf), mul2<PK>(A, Bf), t00, t10, t01, t11, ONE);
-        float2* __restrict__ st = sY + r * 32 + lane;
+        float2* __restrict__ st = sY + r * SVB_STATE_PITCH_F2 + lane;
         const float2 cur_i = *st;
         const float2 cur = unorm2<PK>(cur_i);
         const float2 qi = quant2<GEN, PK>(add2<PK>(mul2<PK>(cur, NAL), mul2<PK>(v, AL), ONE), ONE);
@@ -202,7 +202,7 @@ __device__ __noinline__ void strip_layer_edge(unsigned colY, unsigned colC, unsi
 }
 
 // ---- layers that are not staged (rotation, footprint too large; BGRA / RGBA overlays): per-pixel evaluators over the lane's 2x8
-// block of the running picture in shared memory (sY: the lane's first luma pair; rows are SVB_UNIT_W floats apart.  sC likewise). ------
+// block of the running picture in shared memory (sY: the lane's first luma pair; rows are SVB_STATE_PITCH_F floats apart.  sC likewise). ------
 __device__ __noinline__ void strip_generic_layer(const SvbLayerDesc* __restrict__ L, int xt, int yt, int W, int H, float* __restrict__ sY, float* __restrict__ sC) {
     const Src s = layer_src(L);
     const SvbUniforms* __restrict__ U = &L->u;
@@ -213,8 +213,8 @@ __device__ __noinline__ void strip_generic_layer(const SvbLayerDesc* __restrict_
         if (yt + r >= H) break;
         if (xt + c >= W) continue;
         const bool chroma = ((r | c) & 1) == 0;
-        float* __restrict__ py = sY + r * SVB_UNIT_W + c;
-        float* __restrict__ pc = sC + (r >> 1) * SVB_UNIT_W;
+        float* __restrict__ py = sY + r * SVB_STATE_PITCH_F + c;
+        float* __restrict__ pc = sC + (r >> 1) * SVB_STATE_PITCH_F;
         float oy, ou, ov;
         if (eval_pixel(U, s, xt + c, yt + r, fW, fH, chroma, unorm_f(*py), chroma ? unorm_f(pc[0]) : 0.f, chroma ? unorm_f(pc[1]) : 0.f, oy, ou, ov)) {
             *py = quantf(oy);
@@ -248,8 +248,8 @@ __device__ __noinline__ void strip_rgba_layer(const SvbLayerDesc* __restrict__ L
             k.i0 = ce[c].i0, k.i1 = ce[c].i1, k.j0 = (int)(q >> 4), k.j1 = (int)(q >> 4) + (int)((q >> 3) & 1u);
             const float na = sub(1.f, ce[c].a);
             k.w00 = mul(na, nb), k.w10 = mul(ce[c].a, nb), k.w01 = mul(na, b), k.w11 = mul(ce[c].a, b);  // make_taps' weights
-            float* __restrict__ py = sY + r * SVB_UNIT_W + c;
-            float* __restrict__ pc = sC + (r >> 1) * SVB_UNIT_W;
+            float* __restrict__ py = sY + r * SVB_STATE_PITCH_F + c;
+            float* __restrict__ pc = sC + (r >> 1) * SVB_STATE_PITCH_F;
             float oy, ou, ov;
             rgba_pixel(s, opacity, fc, (ok & 4) != 0, k, unorm_f(*py), chroma ? unorm_f(pc[0]) : 0.f, chroma ? unorm_f(pc[1]) : 0.f, oy, ou, ov);
             *py = quantf(oy);

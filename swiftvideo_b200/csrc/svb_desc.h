@@ -146,7 +146,13 @@ enum {
     SVB_UREC_HALF = 8,   // every weight of the block is exactly 1/2: the four bilinear weights are 1/4 each
     SVB_UREC_MIXED = 16  // the block holds an entry inside the border rectangle but outside the picture (a fill sample)
 };
-#define SVB_STRIP_STATE_BYTES (SVB_UNIT_W * SVB_UNIT_H * 4 + (SVB_UNIT_W / 2) * (SVB_UNIT_H / 2) * 8)  // a unit's running picture as floats: 12 rows x 32 lanes x 8 bytes
+// a unit's running picture as floats: 12 rows (8 luma, 4 chroma) of 32 lanes x 8 bytes, rows 272 bytes apart -- 16 bytes of padding per
+// row turn the rows by four banks each, so that the epilogue's transposed reads (a lane fetches 16 consecutive floats of ONE row, eight
+// rows per quarter-warp) are free of bank conflicts while the layer bodies' row-wise accesses stay so
+#define SVB_STATE_PITCH_F 68                         // floats from a state row to the next
+#define SVB_STATE_PITCH_F2 (SVB_STATE_PITCH_F / 2)   // the same in (pair) slots
+#define SVB_STATE_PITCH_B (SVB_STATE_PITCH_F * 4)    // and in bytes
+#define SVB_STRIP_STATE_BYTES ((SVB_UNIT_H + SVB_UNIT_H / 2) * SVB_STATE_PITCH_B)
 
 // Plan of one tile, written by svb_mix_plan and fetched by the compositor's CTAs with one bulk copy.  Five 16-byte words
 // per entry; entry 0 is the header, entries 1..n the layers that touch the tile, bottom to top (kernels_tiled.cuh):
