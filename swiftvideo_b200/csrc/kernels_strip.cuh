@@ -63,13 +63,9 @@ __device__ __forceinline__ void strip_layer(unsigned colY, unsigned colC, unsign
     constexpr bool PK = true;
     const float2 AL = splat(alpha), NAL = splat(sub(1.f, alpha)), ONE = splat(onef);
     // which rows must fetch their upper source row: the first luma and the first chroma row, and every row whose upper row is not
-    // the lower row of the row before (never at 1:1, one row in five at 1.2:1).  One vote per layer; the row loop tests a bit.
-    unsigned reload;
-    {
-        const unsigned r = (unsigned)lane < 12u ? (unsigned)lane : 0u;
-        const unsigned top = lds_u1(rows + 16u * r + 8u), prev = lds_u1(rows + 16u * (r ? r - 1u : 0u) + 12u);
-        reload = __ballot_sync(0xffffffffu, (unsigned)lane < 12u && (r == 0u || r == 8u || top != prev));
-    }
+    // the lower row of the row before (never at 1:1, one row in five at 1.2:1) -- one bit per row, left in the row block by the
+    // pre-pass; the row loop tests a bit.
+    unsigned reload = lds_u1(rows + 4u * SVB_UROW_RELOAD_WORD);
     const uint2 aw = lds_u2(tab + 8u * lane), e = lds_u2(tab + 4u * SVB_UNIT_W + 8u * lane);
     float2 A = make_float2(__uint_as_float(aw.x), __uint_as_float(aw.y));
     float2 NA = make_float2(sub(1.f, A.x), sub(1.f, A.y));
@@ -91,7 +87,7 @@ __device__ __forceinline__ void strip_layer(unsigned colY, unsigned colC, unsign
         }
         float2 out;
         if (OPAQUE) {
-            if (HALF) out = add2<PK>(add2<PK>(mul2<PK>(v, splat(63.75f)), splat(8388608.f), ONE), splat(-8388608.f), ONE);
+            if (HALF) out = __fadd2_rn(add2<PK>(mul2<PK>(v, splat(63.75f)), splat(8388608.f), ONE), splat(-8388608.f));
             else out = quant2<false, PK>(v, ONE);
         } else {
             if (HALF) v = mul2<PK>(v, splat(0.25f));
@@ -351,5 +347,10 @@ extern "C" __global__ void __launch_bounds__(96, 21) svb_strip_tables(const SvbF
         flags |= (full ? SVB_UREC_FULL : 0u) | (fits ? SVB_UREC_FITS : 0u);
         const int jc1 = yuv ? max(s_i1[c0], s_i1[c1]) : 0;
         reinterpret_cast<uint4*>(rrec)[r] = make_uint4((unsigned)jy0 | ((unsigned)jc0 << 16), (unsigned)max(s_i1[0], s_i1[lastr]) | ((unsigned)jc1 << 16), flags, 0u);
+        unsigned reload = 0x101u;  // (strip_layer: the rows that cannot take over the converted taps of the row before)
+#pragma unroll 1
+        for (int k = 1; k < SVB_UNIT_H + SVB_UNIT_H / 2; ++k)
+            if (k != SVB_UNIT_H && s_i0[k] != s_i1[k - 1]) reload |= 1u << k;
+        rbase[r * SVB_UROW_WORDS + SVB_UROW_RELOAD_WORD] = reload;
     }
 }

@@ -140,7 +140,9 @@ template <bool PK> __device__ __forceinline__ float2 mul2(float2 a, float2 b) {
 // ptxas 12.9 contracts  mul.rn.f32x2 + add.rn.f32x2  into FFMA2 even under -fmad=false (it does not for the scalar
 // .rn forms), which would round once where the reference rounds twice.  The packed add is therefore issued as
 // fma(a, ONE, b) with ONE == 1.0f arriving as a kernel argument: bit-identical to a + b (a*1 is exact), one
-// instruction like FADD2, and opaque to the contraction because the multiplicand is not a compile-time constant.
+// instruction like FADD2, and opaque to the contraction because the multiplicand is not a compile-time constant.  (Measured in round 2:
+// with the multiplicand as the IMMEDIATE 1.0 -- one register operand less to read, tools/ubench3.cu -- ptxas folds the fma back into
+// FADD2 and contracts it with the FMUL2 in front: 19 FFMA2 with three register operands appear in svb_mix_ring.  Not usable.)
 template <bool PK> __device__ __forceinline__ float2 add2(float2 a, float2 b, float2 one) {
     return PK ? __ffma2_rn(a, one, b) : make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y));
 }
@@ -160,7 +162,10 @@ __device__ __forceinline__ float2 quant2(float2 v, float2 one) {
         x.x = fminf(fmaxf(x.x, 0.f), 255.f);
         x.y = fminf(fmaxf(x.y, 0.f), 255.f);
     }
-    return add2<PK>(add2<PK>(x, splat(8388608.f), one), splat(-8388608.f), one);
+    // (the second addition takes a SUM, not a product: nothing for ptxas to contract it with, so it may be a plain packed add --
+    // one register operand less to read than fma(x, ONE, -2^23); the layer bodies are bound by register reads, tools/ubench3.cu)
+    const float2 y = add2<PK>(x, splat(8388608.f), one);
+    return PK ? __fadd2_rn(y, splat(-8388608.f)) : make_float2(__fadd_rn(y.x, -8388608.f), __fadd_rn(y.y, -8388608.f));
 }
 template <bool PK>
 __device__ __forceinline__ float2 bilin2(float2 w00, float2 w10, float2 w01, float2 w11, float2 t00, float2 t10, float2 t01, float2 t11,

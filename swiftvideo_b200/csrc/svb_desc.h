@@ -127,7 +127,8 @@ typedef struct __attribute__((aligned(64))) SvbFrameDesc {
 //   row block    (one per unit row, 64 words)    : 12 entries of 4 words, luma rows 0..7 then chroma rows 0..3:
 //                                                  b, 1-b, j0*pitch, j1*pitch      (pitch = the layer's staged box pitch in bytes:
 //                                                  a tap's shared-memory address is a per-lane column term plus the row's offset)
-//                                                  then 12 words  ok | (j1-j0) << 3 | j0 << 4  (edge and RGBA bodies), 4 words of padding
+//                                                  then 12 words  ok | (j1-j0) << 3 | j0 << 4  (edge and RGBA bodies), then one word: bit r set = row r
+//                                                  starts from a source row that is not the lower source row of row r-1 (SVB_UROW_RELOAD_WORD), 3 words of padding
 //   column records (one per unit column, 4 words) and row records (one per unit row, 4 words): what a plan needs of the
 //   blocks -- (first source index luma | chroma << 16, last source index luma | chroma << 16, SVB_UREC_* flags, 0) -- so that a unit
 //   (or a tile of units) is planned from two 16-byte loads per layer (the plan is separable: a unit is inside a picture iff its column range and its row range are).
@@ -135,6 +136,7 @@ typedef struct __attribute__((aligned(64))) SvbFrameDesc {
 #define SVB_UNIT_H 8
 #define SVB_UCOL_WORDS (3 * SVB_UNIT_W)
 #define SVB_UROW_WORDS 64
+#define SVB_UROW_RELOAD_WORD 60
 #define SVB_UNITS_X(W) (((W) + SVB_UNIT_W - 1) / SVB_UNIT_W)
 #define SVB_UNITS_Y(H) (((H) + SVB_UNIT_H - 1) / SVB_UNIT_H)
 // words of one layer's tables: column blocks, row blocks, column records, row records
