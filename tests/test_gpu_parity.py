@@ -202,18 +202,21 @@ def test_padded_strides(pads, mode, mname):
 
 def test_padded_target():
     """A target with padded rows (fused and generic take explicit output strides; the per-layer kernels infer the stride
-    from the launch like the reference's, kernels.cuda.swift:151,205, so they only accept tight targets)."""
+    from the launch like the reference's, kernels.cuda.swift:151,205, so they only accept tight targets).  A pad of 64 keeps the
+    rows 16-byte aligned (svb_mix_ring's whole units leave as 16-byte stores), a pad of 6 does not (two bytes per lane and row)."""
     base = TILED[0]
     rc, want = scenes.run_case(CHECKER, base, threads=O.host_threads())
     assert rc == 0
     W, H = base.canvas
-    for mode, mname in MODES[:4]:
-        got = gpu_case(context(), base, mode, target_strides=[W + 64, W + 64])
-        tight = np.concatenate([got[: (W + 64) * H].reshape(H, W + 64)[:, :W].reshape(-1),
-                                got[(W + 64) * H :].reshape(H // 2, W + 64)[:, :W].reshape(-1)])
-        assert (tight == want.data).all(), f"padded target/{mname}: {first_diff(tight, want.data)}"
-        pad = got[: (W + 64) * H].reshape(H, W + 64)[:, W:]
-        assert (pad == 0xA5).all(), "padding bytes of the target were written"
+    for padb in (64, 6):
+        S = W + padb
+        for mode, mname in MODES[:4]:
+            got = gpu_case(context(), base, mode, target_strides=[S, S])
+            tight = np.concatenate([got[: S * H].reshape(H, S)[:, :W].reshape(-1),
+                                    got[S * H :].reshape(H // 2, S)[:, :W].reshape(-1)])
+            assert (tight == want.data).all(), f"padded target {padb}/{mname}: {first_diff(tight, want.data)}"
+            pad = np.concatenate([got[: S * H].reshape(H, S)[:, W:].reshape(-1), got[S * H :].reshape(H // 2, S)[:, W:].reshape(-1)])
+            assert (pad == 0xA5).all(), "padding bytes of the target were written"
     with pytest.raises(sv.ComputeError) as e:
         gpu_case(context(), base, sv.MixMode.PER_LAYER, target_strides=[W + 64, W + 64])
     assert "badTarget" in str(e.value)
