@@ -277,8 +277,9 @@ __device__ __forceinline__ bool elect_one() {
 // column / row records a warp plans its units from.  grid (unit columns + unit rows of the largest frame, max layers, frames),
 // 96 threads: a block fills one column block (64 luma + 32 chroma entries) or one row block (8 + 4 entries) and writes its record.
 // (at most 32 registers, so that many blocks start at once in the tail of the compositor launched before, as its CTAs retire.  It does
-// not run UNDER that launch's resident CTAs: registers are per scheduler, and 7 warps x 72 registers fill three of an SM's four
-// schedulers -- measured in round 2, profiles/r2_history.md section 9.  The pre-pass's ~5 us stand between two compositor launches.)
+// not run UNDER that launch's resident CTAs: three CTAs of nine warps at 72 registers leave no scheduler of an SM room that the
+// block scheduler will use -- not even for one-warp blocks; with the compositor held to 64 registers they do run under it --
+// measured in round 2, profiles/r2_history.md section 9.  About half of the 4 - 8 us between two compositor launches is this pre-pass.)
 extern "C" __global__ void __launch_bounds__(96, 21) svb_strip_tables(const SvbFrameDesc* __restrict__ frames, uint32_t* __restrict__ tables, int* __restrict__ unit_counter) {
     using namespace svb;
     if ((blockIdx.x | blockIdx.y | blockIdx.z | threadIdx.x) == 0) *unit_counter = 0;  // svb_mix_ring claims its tiles from it

@@ -37,8 +37,8 @@ struct MixerShared {
     CUevent ev[kSegments] = {};
     bool used[kSegments] = {};
     // The descriptor copy and the pre-pass of a batch run on their own stream: nothing in them depends on the compositor launch
-    // queued before them: the copy runs ahead, the pre-pass's blocks start as that launch's CTAs retire (they do not fit beside its
-    // resident CTAs: registers are per scheduler, profiles/r2_history.md section 9) and cost the step 4 - 8 us.  Each segment
+    // queued before them: the copy runs ahead, the pre-pass's blocks start as that launch's CTAs retire (nothing of this stream starts
+    // beside its resident CTAs, profiles/r2_history.md section 9): the step is the compositor + 4 - 8 us.  Each segment
     // owns its table / plan buffer (free again once ev[seg] has fired, which the host waits for before reusing the segment).
     CUstream prep = nullptr;
     CUevent evPrep[kSegments] = {};
