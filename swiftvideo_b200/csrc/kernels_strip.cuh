@@ -8,7 +8,7 @@
 //   * warps that do not run in lock-step do not share an instruction stream, so the hot code must fit the instruction cache of a
 //     scheduler on its own: ONE loop of two output rows (~2 KB) serves luma and chroma rows, NV12 and planar sources alike (a first
 //     version with a 5 KB body per mode spent a quarter of its stall samples on instruction fetch, profiles/r2_history.md);
-//   * the running picture of the unit lives in shared memory (3 KB per warp, integer-valued floats, re-quantised after every layer
+//   * the running picture of the unit lives in shared memory (3.2 KB per warp -- twelve rows 272 bytes apart, svb_desc.h -- integer-valued floats, re-quantised after every layer
 //     exactly like the reference's 8-bit target, mix.video.swift:113-125): the row loop stays rolled without register rotation;
 //   * everything a row needs arrives in the form the loop consumes: svb_strip_tables evaluates the reference's coordinate chain
 //     (kernels.cl.swift:70-78) once per output column and row, bit-exactly, and stores weights with their complements and row
