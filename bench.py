@@ -86,6 +86,20 @@ def configure_workload(name):
                     "-- 36 MB per step: FITS in the 126 MB L2")
 
 
+def workload_config(args, world):
+    """The `config` object of the JSON line: what is measured, identical for both arms (`--impl ours` / `--impl reference`)."""
+    S = STREAMS_PER_GPU
+    return {"workload": (WORKLOAD if args.pip_opacity is None else WORKLOAD + f" -- NOT the headline: picture-in-picture opacity forced to {args.pip_opacity}") +
+                        (f" -- NOT the headline: the top {args.rgba_pips} pictures-in-picture are RGBA overlays" if args.rgba_pips else "") +
+                        (" -- NOT the headline: YUV420P layers and target instead of NV12" if args.format == "y420p" else ""),
+            "mode": args.mode, "streams_total": S * world, "frames_per_step": S * world, "parallelism": f"streams sharded, {S}/GPU, no collective",
+            "l2": (f"{ALG_BYTES_PER_FRAME * S / 1e6:.0f} MB of distinct sources+targets per step (> 126 MB L2); sources alternate between two device copies"
+                   if ALG_BYTES_PER_FRAME * S > 126e6 else
+                   f"{ALG_BYTES_PER_FRAME * S / 1e6:.0f} MB of distinct sources+targets per step: FITS in the 126 MB L2; sources alternate between two device copies "
+                   f"({2 * ALG_BYTES_PER_FRAME * S / 1e6:.0f} MB over two steps)"),
+            "bit_exact_vs_oracle": "tests/test_gpu_parity.py::test_cfg2_full_size" if CANVAS == (1280, 720) else "tests/test_gpu_parity.py::test_cfg34_full_size"}
+
+
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -379,14 +393,7 @@ def run_ours(args):
         "host_backpressure_ms_per_step": round(host_c_wait / max(1, host_c_calls), 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8 (fp32 arithmetic, no FMA contraction)", "data": "synthetic (uniform u8 planes, seeded)",
-        "config": {"workload": (WORKLOAD if args.pip_opacity is None else WORKLOAD + f" -- NOT the headline: picture-in-picture opacity forced to {args.pip_opacity}") +
-                               (f" -- NOT the headline: the top {args.rgba_pips} pictures-in-picture are RGBA overlays" if args.rgba_pips else "") +
-                               (" -- NOT the headline: YUV420P layers and target instead of NV12" if args.format == "y420p" else ""), "mode": args.mode, "streams_total": S * world, "frames_per_step": S * world, "parallelism": f"streams sharded, {S}/GPU, no collective", "host_affinity": numa,
-                   "l2": (f"{ALG_BYTES_PER_FRAME * S / 1e6:.0f} MB of distinct sources+targets per step (> 126 MB L2); sources alternate between two device copies"
-                          if ALG_BYTES_PER_FRAME * S > 126e6 else
-                          f"{ALG_BYTES_PER_FRAME * S / 1e6:.0f} MB of distinct sources+targets per step: FITS in the 126 MB L2; sources alternate between two device copies "
-                          f"({2 * ALG_BYTES_PER_FRAME * S / 1e6:.0f} MB over two steps)"),
-                   "bit_exact_vs_oracle": "tests/test_gpu_parity.py::test_cfg2_full_size" if CANVAS == (1280, 720) else "tests/test_gpu_parity.py::test_cfg34_full_size"},
+        "config": workload_config(args, world), "host_affinity": numa,
         "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "ms_per_step": round(e_ms / e2e_steps, 4), "host_queue_ms_per_step": round(e_host_ms / e2e_steps, 4), "calls_per_step": 1,
                 "frac_of_link_ceiling": round(e2e_value / link["duplex_all_ranks"]["frames_per_s"], 3), "host_link": link},
@@ -635,7 +642,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": base["ms_per_frame"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8 (fp32 arithmetic, no FMA contraction)", "data": "synthetic (uniform u8 planes, seeded)",
-            "config": {"workload": WORKLOAD, "note": "host CPU only: one step = one 4K 8-layer frame of one stream"},
+            "config": workload_config(args, world), "note": "host CPU only: one step = one 4K 8-layer frame of one stream of this workload (rows split over all host threads)",
             "cpu_baseline": base, "e2e": {"value": base["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": round(time.perf_counter() - t0, 2)}
     print(json.dumps(line), flush=True)
