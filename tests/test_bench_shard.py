@@ -55,3 +55,17 @@ def test_reference_arm_runs_on_rank0_only(tmp_path):
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0 and d["cpu_baseline"]["kind"] in ("reference", "port")
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["unit"] == "frames/s"
+
+
+def test_both_arms_print_the_same_config():
+    """`bench.py --impl ours` and `--impl reference` describe the workload with one function: the driver compares the two lines' `config`."""
+    import argparse
+    sys.path.insert(0, str(ROOT))
+    import bench
+    args = argparse.Namespace(pip_opacity=None, rgba_pips=0, format="nv12", mode="fused")
+    for world in (1, 2, 8):
+        a, b = bench.workload_config(args, world), bench.workload_config(args, world)
+        assert a == b and a["streams_total"] == bench.STREAMS_PER_GPU * world
+        assert a["workload"].startswith("cfg4: 3840x2160 NV12 target, 8 NV12 layers")
+    src = (ROOT / "bench.py").read_text()
+    assert src.count('"config": workload_config(args, world)') == 2  # the line of either arm
