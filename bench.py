@@ -100,6 +100,21 @@ def workload_config(args, world):
             "bit_exact_vs_oracle": "tests/test_gpu_parity.py::test_cfg2_full_size" if CANVAS == (1280, 720) else "tests/test_gpu_parity.py::test_cfg34_full_size"}
 
 
+def e2e_limiter(e2e_fps, link, host_ms, step_ms, resident_step_ms, world):
+    """Name what bounds the end-to-end number, from what the same process measured: the host link with every rank copying at once
+    (PCIe and the host-memory path behind it, shared by the ranks of a box), the calling thread, or the GPU itself."""
+    ceiling = link["duplex_all_ranks"]["frames_per_s"]
+    if e2e_fps >= 0.85 * ceiling:
+        return (f"host link: {e2e_fps / ceiling:.2f} of what the box moves with all {world} rank(s) copying one step's bytes both ways at once "
+                f"({link['duplex_all_ranks']['h2d_gbs_per_gpu']} GB/s in + {link['duplex_all_ranks']['d2h_gbs_per_gpu']} GB/s out per GPU); "
+                f"the GPU needs {resident_step_ms:.2f} ms of the {step_ms:.2f} ms step, the calling thread {host_ms:.2f} ms")
+    if host_ms >= 0.8 * step_ms:
+        return f"calling thread (vCPU): busy {host_ms:.2f} ms of the {step_ms:.2f} ms step"
+    if resident_step_ms >= 0.8 * step_ms:
+        return f"GPU: the resident step alone takes {resident_step_ms:.2f} ms of {step_ms:.2f} ms"
+    return f"unattributed: {e2e_fps / ceiling:.2f} of the link ceiling, calling thread {host_ms:.2f} ms, GPU {resident_step_ms:.2f} ms of the {step_ms:.2f} ms step"
+
+
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -396,7 +411,8 @@ def run_ours(args):
         "config": workload_config(args, world), "host_affinity": numa,
         "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "ms_per_step": round(e_ms / e2e_steps, 4), "host_queue_ms_per_step": round(e_host_ms / e2e_steps, 4), "calls_per_step": 1,
-                "frac_of_link_ceiling": round(e2e_value / link["duplex_all_ranks"]["frames_per_s"], 3), "host_link": link},
+                "frac_of_link_ceiling": round(e2e_value / link["duplex_all_ranks"]["frames_per_s"], 3), "host_link": link,
+                "limiter": e2e_limiter(e2e_value, link, e_host_ms / e2e_steps, e_ms / e2e_steps, ms / args.steps, world)},
         # the reference's own call pattern, for comparison with the headline: one VideoMixer.mix(at:) per mixer = one 4K frame per launch
         "one_frame_per_launch": {"value": round(frames / (pm_ms / 1e3), 2), "unit": "frames/s", "ms_per_step": round(pm_ms / args.steps, 4),
                                  "launches_per_step": S, "kernel_ms_per_launch": round(pm_kern_ms / max(1, pm_kern_n), 4),
