@@ -322,6 +322,12 @@ svb_status svb_launch_timing_read(svb_context* ctx, double* total_ms, unsigned l
  * not counting the time the thread was blocked because it ran eight launches ahead of the GPU; that back-pressure is *wait_ms (may be NULL) */
 svb_status svb_host_timing_read(svb_context* ctx, double* total_ms, unsigned long long* calls);
 svb_status svb_host_timing_read2(svb_context* ctx, double* total_ms, unsigned long long* calls, double* wait_ms);
+/* An extension (the reference recomputes every pixel's coordinates in every launch, kernels.cl.swift:70-78; it has nothing to cache): the
+ * fused compositor derives per-column / per-row coordinate tables from the layers' uniforms in a pre-pass, and keeps them while a batch's
+ * geometry -- frame sizes, every layer's ImageUniforms, source size and format -- stays what it was when the batch's buffer was last filled
+ * (a mixer whose layout does not move: the steady state of a live mix).  Pixels are never cached.  enable = 0: run the pre-pass for every
+ * launch.  Default: on. */
+svb_status svb_table_cache(svb_context* ctx, int enable);
 /* launches of our kernels issued by this process so far */
 unsigned long long svb_kernel_launch_count(void);
 /* 256 floats each: UNORM8 read by the division-free identity and by true division (device self-test) */

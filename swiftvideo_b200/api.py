@@ -165,6 +165,7 @@ def _load():
     l.svb_animator_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
     l.svb_launch_timing.argtypes = [C.c_void_p, C.c_int]
     l.svb_launch_timing_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    l.svb_table_cache.argtypes = [C.c_void_p, C.c_int]
     l.svb_host_timing_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     l.svb_host_timing_read2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     l.svb_selftest_unorm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -252,6 +253,10 @@ class ComputeContext:
 
     def launch_timing(self, enable=True):
         _check(lib.svb_launch_timing(self._h, int(enable)))
+
+    def table_cache(self, enable=True):
+        """Keep a batch's coordinate tables while its geometry does not change (default on); off: the table pre-pass runs for every launch."""
+        _check(lib.svb_table_cache(self._h, int(enable)))
 
     def launch_timing_read(self):
         """(total device ms, launches) of the fused kernels since timing was enabled."""

@@ -679,6 +679,13 @@ svb_status svb_launch_timing(svb_context* ctx, int enable) {
         setLaunchTiming(ctx->c, enable != 0);
     });
 }
+svb_status svb_table_cache(svb_context* ctx, int enable) {
+    return guard([&] {
+        need(ctx, "ctx");
+        if (!ctx->c.ctx) throw ComputeError(ErrorCode::badContextState, "No context");
+        setTableCache(ctx->c, enable != 0);
+    });
+}
 svb_status svb_launch_timing_read(svb_context* ctx, double* total_ms, unsigned long long* launches) {
     return guard([&] {
         need(ctx, "ctx");

@@ -270,7 +270,11 @@ extern "C" __global__ void __launch_bounds__(SVB_RING_THREADS, SVB_RING_MIN_CTAS
         for (unsigned idle = 0;;) {
             if (!have_tile && planned > n) {
                 const unsigned hx = lds_u4(plan0 + (n % SVB_RING_PLANS) * (unsigned)plan_slot_bytes).x;
-                if ((hx & 0xffffu) == 0xffffu) return;  // the end marker
+                if ((hx & 0xffffu) == 0xffffu) {  // the end marker: this CTA claims no more.  The last CTA to get here leaves the batch's
+                    // counters at zero, so that the next launch on this buffer can start without the pre-pass (mix_video.cpp: tabSig)
+                    if (lane == 0 && atomicAdd(tile_counter + 1, 1) == (int)gridDim.x - 1) tile_counter[0] = 0, tile_counter[1] = 0;
+                    return;
+                }
                 smask = hx >> 16, i = 0, have_tile = true;
             }
             if (have_tile) {

@@ -44,6 +44,13 @@ struct MixerShared {
     CUevent evPrep[kSegments] = {};
     CUdeviceptr tabBuf[kSegments] = {};
     size_t tabBytes[kSegments] = {};
+    // What a segment's buffer holds: everything svb_strip_tables' output depends on for the ring batch that last filled it (frame
+    // sizes, per layer the uniforms, source size, format, flags, staged boxes and the tables' place in the buffer).  A batch with the
+    // same signature -- a mixer whose layout did not change since this segment's last turn, the steady state of a live mix -- finds
+    // its tables in place and goes without the pre-pass; anything else that writes the buffer clears the signature.
+    std::vector<uint8_t> tabSig[kSegments];
+    std::vector<uint8_t> sigScratch;
+    bool tableCache = true;  // (setTableCache: off = every ring batch runs its pre-pass, as before round 2's second session)
     int next = 0;
     // Tensor maps: a table in device memory, grown by chunks.  A slot is written once (a synchronous 128-byte copy when a new
     // plane geometry first appears) and never again, so kernels need no tensormap-proxy fence; only when the table would exceed
@@ -499,18 +506,39 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
                     sh.tabBuf[k] = 0, sh.tabBytes[k] = 0;
                     check(d.cuMemAlloc(&sh.tabBuf[k], want), "cuMemAlloc");
                     sh.tabBytes[k] = want;
+                    sh.tabSig[k].clear();
                 }
             }
             CUdeviceptr tables = sh.tabBuf[seg];
             CUdeviceptr counter = tables + counterOff, plans = tables + plansOff;
             if (ring) {
-                // one pre-pass launch: a block per unit column and per unit row of every layer fills its table block and its plan record
-                int blocks = 1;
-                for (int i = 0; i < n; ++i) blocks = std::max(blocks, frames[start + i].tiles_x + frames[start + i].tiles_y);
-                void* targs[] = {&dev, &tables, &counter};
-                check(d.cuLaunchKernel(sh.fStripTables, (unsigned)blocks, (unsigned)maxLayers, (unsigned)n, 96, 1, 1, 0, sh.prep, targs, nullptr), "cuLaunchKernel(svb_strip_tables)");
-                noteKernelLaunch();
+                // the batch's signature (see tabSig): when the segment's buffer already holds these tables the pre-pass is not launched --
+                // svb_mix_ring leaves the tile counter at zero behind itself
+                std::vector<uint8_t>& sig = sh.sigScratch;
+                sig.clear();
+                auto put = [&sig](const void* p, size_t bytes) { sig.insert(sig.end(), (const uint8_t*)p, (const uint8_t*)p + bytes); };
+                for (int i = 0; i < n; ++i) {
+                    const SvbFrameDesc& fr = frames[start + i];
+                    const int32_t head[8] = {fr.width, fr.height, fr.nlayers, fr.tiles_x, fr.tiles_y, fr.table_base, fr.first_tile, fr.format};
+                    put(head, sizeof(head));
+                    for (int l = 0; l < fr.nlayers; ++l) {
+                        const SvbLayerDesc& L = fr.layers[l];
+                        put(&L.u, sizeof(L.u));
+                        const int32_t geo[10] = {L.width, L.height, L.format, L.flags, L.box_w, L.box_h, L.box_cw, L.box_ch, (int32_t)L.pc.tab, (int32_t)L.pc.rec};
+                        put(geo, sizeof(geo));
+                    }
+                }
+                if (!sh.tableCache || sig != sh.tabSig[seg]) {
+                    // one pre-pass launch: a block per unit column and per unit row of every layer fills its table block and its plan record
+                    int blocks = 1;
+                    for (int i = 0; i < n; ++i) blocks = std::max(blocks, frames[start + i].tiles_x + frames[start + i].tiles_y);
+                    void* targs[] = {&dev, &tables, &counter};
+                    check(d.cuLaunchKernel(sh.fStripTables, (unsigned)blocks, (unsigned)maxLayers, (unsigned)n, 96, 1, 1, 0, sh.prep, targs, nullptr), "cuLaunchKernel(svb_strip_tables)");
+                    noteKernelLaunch();
+                    sh.tabSig[seg] = sig;
+                }
             } else {
+                sh.tabSig[seg].clear();  // (the other compositors lay the buffer out differently)
                 int tableBlocks = (maxEnts / 2 + 255) / 256;
                 void* targs[] = {&dev, &tables, &counter, &plans, &tableBlocks, &maxLayers};
                 check(d.cuLaunchKernel(sh.fTables, (unsigned)(tableBlocks * maxLayers + (maxTiles + 7) / 8), 1, (unsigned)n, 256, 1, 1, 0, sh.prep, targs, nullptr),
@@ -645,6 +673,12 @@ void composeFused(const ComputeContext& ctx, std::vector<Job>& jobs, bool forceG
 }
 
 }  // namespace
+
+void setTableCache(const ComputeContext& ctx, bool on) {
+    MixerShared& sh = shared(ctx.ctx);
+    std::lock_guard<std::mutex> launchLock(sh.launchMu);
+    sh.tableCache = on;
+}
 
 void setLaunchTiming(const ComputeContext& ctx, bool on) {
     CtxGuard g(ctx.ctx);

@@ -92,6 +92,9 @@ class VideoMixer {
 
 // Device time of the fused launches (CUDA events around each kernel on the compute stream), for the roofline.
 void setLaunchTiming(const ComputeContext& ctx, bool on);
+// The fused compositor keeps the coordinate tables of a batch whose geometry (frame sizes, layer uniforms, source sizes and formats) did
+// not change since the batch's buffer was last filled, and launches its table pre-pass only otherwise (default: on).
+void setTableCache(const ComputeContext& ctx, bool on);
 void readLaunchTiming(const ComputeContext& ctx, double* totalMs, unsigned long long* launches);
 // Host time spent inside the fused compose calls since timing was enabled (plan + driver calls: what the caller's thread pays per tick)
 void readHostTiming(const ComputeContext& ctx, double* totalMs, unsigned long long* calls, double* waitMs = nullptr);

@@ -249,3 +249,27 @@ def test_equal_z_is_deterministic(mode, mname):
     a = gpu_case(context(), case, mode)
     b = gpu_case(context(), case, mode)
     assert (a == b).all() and (a == want.data).all(), f"equal_z/{mname}: {first_diff(a, want.data)}"
+
+
+def test_table_cache_follows_the_geometry():
+    """svb_mix_ring keeps a batch's coordinate tables while the batch's geometry is what it was when the batch's buffer (one of eight,
+    used in turn) was last filled, and runs its table pre-pass otherwise (svb_table_cache, include/svb200.h).  Launch patterns with a
+    period of eight make every launch of rounds 1 and 3 find its buffer's tables in place, and every launch of rounds 0 and 2 find
+    another scene's; with the cache off the pre-pass runs every time.  Every output is compared with the reference's."""
+    ctx = context()
+    cases = [TILED[0], TILED[1 % len(TILED)], TILED[2 % len(TILED)]]
+    wants = []
+    for c in cases:
+        rc, want = scenes.run_case(CHECKER, c, threads=O.host_threads())
+        assert rc == 0
+        wants.append(want.data)
+    try:
+        for enabled in (True, False, True):
+            ctx.table_cache(enabled)
+            for rnd in range(4):
+                for i in range(8):
+                    k = (i + rnd // 2) % len(cases)
+                    got = gpu_case(ctx, cases[k], sv.MixMode.FUSED_RING)
+                    assert (got == wants[k]).all(), f"cache {enabled}, round {rnd}, launch {i}, {cases[k].name}: {first_diff(got, wants[k])}"
+    finally:
+        ctx.table_cache(True)
