@@ -344,7 +344,7 @@ def run_ours(args):
     # clocks and throttle reasons are sampled (nvidia-smi, every 50 ms) from here to the end of the e2e leg: the GPU is
     # busy throughout, and the resident leg alone can be shorter than one sampling period
     # set-up, untimed: one turn of the library's eight table buffers with the workload's geometry, so that the warm-up and the timed steps
-    # see what a mixer that has been running for more than eight ticks sees (coordinate tables and tile order in place, `table_cache` below)
+    # see what a mixer that has been running for more than eight ticks sees (coordinate tables in place, `table_cache` below)
     last = None
     for i in range(8):
         last = step_resident(-100 - i)
@@ -424,7 +424,7 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8 (fp32 arithmetic, no FMA contraction)", "data": "synthetic (uniform u8 planes, seeded)",
         "config": workload_config(args, world), "host_affinity": numa,
-        "table_cache": {"enabled": True, "what": "coordinate tables and the tile claim order of a batch are kept while its layers' uniforms, sizes and formats do not change (svb_table_cache, include/svb200.h); pixels are never cached",
+        "table_cache": {"enabled": True, "what": "coordinate tables of a batch are kept while its layers' uniforms, sizes and formats do not change (svb_table_cache, include/svb200.h); pixels are never cached",
                         "primed_in_setup_steps": 8,
                         "value_without": round(frames / (nc_ms / 1e3), 2), "ms_per_step_without": round(nc_ms / args.steps, 4)},
         "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,

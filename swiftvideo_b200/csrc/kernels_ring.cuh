@@ -81,7 +81,7 @@ __device__ __forceinline__ void mbar_wait_u32(unsigned bar, unsigned parity) {
 
 extern "C" __global__ void __launch_bounds__(SVB_RING_THREADS, SVB_RING_MIN_CTAS)
     svb_mix_ring(const SvbFrameDesc* __restrict__ frames, const uint32_t* __restrict__ tables, int nframes, int total_tiles, float one, int* __restrict__ tile_counter, int box_y_bytes,
-                 int box_c_bytes, int plan_slot_bytes, int use_order) {
+                 int box_c_bytes, int plan_slot_bytes) {
     using namespace svb;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -294,10 +294,7 @@ extern "C" __global__ void __launch_bounds__(SVB_RING_THREADS, SVB_RING_MIN_CTAS
                 const unsigned slot = planned % SVB_RING_PLANS;
                 if (planned < SVB_RING_PLANS || mbar_try_u32(pempty0 + 8u * slot, ((planned / SVB_RING_PLANS) - 1u) & 1u, 0u)) {  // every consumer has left the slot's previous plan
                     int t = 0;
-                    if (lane == 0) {  // the k-th claim takes the k-th heaviest tile when svb_ring_order left an order behind the control block
-                        t = atomicAdd(tile_counter, 1);
-                        if (use_order && t < total_tiles) t = __ldg(tile_counter + SVB_RING_ORDER_OFFSET + t);
-                    }
+                    if (lane == 0) t = atomicAdd(tile_counter, 1);
                     t = __shfl_sync(0xffffffffu, t, 0);
                     gplan += plan_tile(t, (int)slot, gplan);
                     __syncwarp();
@@ -461,34 +458,4 @@ extern "C" __global__ void __launch_bounds__(SVB_RING_THREADS, SVB_RING_MIN_CTAS
         if (lane == 0) mbar_arrive(pempty0 + 8u * slot);  // this warp has left the tile's plan
     }
 #undef SVB_RING_TARGET
-}
-
-
-// ---- the order in which svb_mix_ring's CTAs claim their tiles: heaviest first.  A tile costs about as much as the layers that reach
-// into it (one to four in the headline workload), and a persistent grid that claims tiles in raster order ends on whatever the last
-// rows hold: with the heavy tiles first the tail of a launch is made of the light ones (-2 % per 8-frame launch).  A counting sort by
-// the number of layers whose rectangle touches the tile, in two launches: phase 0 counts the tiles of every weight, phase 1 hands out
-// the places.  The order depends on the batch's geometry alone, so it is computed with the tables and kept with them (the table cache):
-// run for every launch it would cost the step more than it gains (profiles/r2_history.md section 9).  ctl: ring_layout.h.
-extern "C" __global__ void __launch_bounds__(96, 21) svb_ring_order(const SvbFrameDesc* __restrict__ frames, int nframes, int total_tiles, int* __restrict__ ctl, int phase) {
-    const int t = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-    if (t >= total_tiles) return;
-    int f = 0;
-    while (f + 1 < nframes && t >= frames[f + 1].first_tile) ++f;
-    const SvbFrameDesc* __restrict__ F = frames + f;
-    const int tx_n = (F->width + 2 * SVB_UNIT_W - 1) / (2 * SVB_UNIT_W), local = t - F->first_tile;
-    const int ty = local / tx_n, tx = local - ty * tx_n, x0 = tx * 2 * SVB_UNIT_W, y0 = ty * 4 * SVB_UNIT_H;
-    int c = 0;
-    for (int l = 0; l < F->nlayers; ++l) {
-        const int4 r = *reinterpret_cast<const int4*>(F->layers[l].pc.rect);
-        c += r.x < x0 + 2 * SVB_UNIT_W && r.z > x0 && r.y < y0 + 4 * SVB_UNIT_H && r.w > y0;
-    }
-    c = min(c, SVB_MAX_LAYERS);
-    if (phase == 0) {
-        atomicAdd(ctl + SVB_RING_HIST + c, 1);
-    } else {
-        int at = 0;  // tiles heavier than this one come first
-        for (int k = SVB_MAX_LAYERS; k > c; --k) at += ctl[SVB_RING_HIST + k];
-        ctl[SVB_RING_ORDER_OFFSET + at + atomicAdd(ctl + SVB_RING_CURSOR + c, 1)] = t;
-    }
 }

@@ -282,7 +282,7 @@ __device__ __forceinline__ bool elect_one() {
 // measured in round 2, profiles/r2_history.md section 9.  About half of the 4 - 8 us between two compositor launches is this pre-pass.)
 extern "C" __global__ void __launch_bounds__(96, 21) svb_strip_tables(const SvbFrameDesc* __restrict__ frames, uint32_t* __restrict__ tables, int* __restrict__ unit_counter) {
     using namespace svb;
-    if ((blockIdx.x | blockIdx.y | blockIdx.z) == 0 && threadIdx.x < 64) unit_counter[threadIdx.x] = 0;  // the batch's control block (ring_layout.h): svb_mix_ring claims its tiles from word 0 and counts its finished CTAs in word 1 (it leaves both at zero: a batch that finds its tables in place skips this pre-pass); svb_ring_order counts in the rest
+    if ((blockIdx.x | blockIdx.y | blockIdx.z | threadIdx.x) == 0) unit_counter[0] = 0, unit_counter[1] = 0;  // svb_mix_ring claims its tiles from word 0 and counts its finished CTAs in word 1 (it leaves both at zero: a batch that finds its tables in place skips this pre-pass)
     const SvbFrameDesc* __restrict__ F = frames + blockIdx.z;
     const int l = (int)blockIdx.y;
     if (l >= F->nlayers) return;

@@ -60,7 +60,7 @@ struct MixerShared {
     std::vector<CUdeviceptr> tmapChunks;
     int tmapChunkAt = -1, tmapUsed = 0;
     bool tmapFence = false;
-    CUfunction fTiled = nullptr, fGather = nullptr, fGeneric = nullptr, fTables = nullptr, fStripTables = nullptr, fRingOrder = nullptr, fRing = nullptr;
+    CUfunction fTiled = nullptr, fGather = nullptr, fGeneric = nullptr, fTables = nullptr, fStripTables = nullptr, fRing = nullptr;
     int gatherCtasPerSm = 0;
     int texAlign = 512, texPitchAlign = 32;
     std::map<std::array<uint64_t, 3>, CUtexObject> texs;  // texture objects over source planes by (pointer, size, pitch | channels)
@@ -142,7 +142,6 @@ MixerShared& shared(const std::shared_ptr<InternalContext>& ic) {  // caller hol
         }
         s->fGeneric = ic->builtin("svb_mix_generic");
         s->fStripTables = ic->builtin("svb_strip_tables");
-        s->fRingOrder = ic->builtin("svb_ring_order");
         s->fRing = ic->builtin("svb_mix_ring");
         check(drv().cuFuncSetAttribute(s->fRing, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, 200 * 1024), "cuFuncSetAttribute(max dynamic shared memory)");
     }
@@ -494,8 +493,8 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
             // pre-pass (one launch): per-column / per-row coordinate tables of the batch (two words per entry) and the plan of every
             // tile; then the compositor (+ the tile counter it claims its work from, zeroed by the pre-pass)
             const size_t counterOff = (std::max<size_t>(tableEnts, 4) * 4 + 15) & ~(size_t)15;
-            const size_t plansOff = counterOff + (ring ? SVB_RING_ORDER_OFFSET * sizeof(int32_t) : 16);  // (a ring batch: the control block of ring_layout.h, the claim order behind it)
-            const size_t tableBytes = plansOff + (ring ? (size_t)total * sizeof(int32_t) : (size_t)total * sizeof(SvbTilePlan));  // (a ring batch has no plans in global memory -- its producer warps plan their own tiles -- but the order in which they claim them)
+            const size_t plansOff = counterOff + 16;
+            const size_t tableBytes = plansOff + (ring ? 0 : (size_t)total * sizeof(SvbTilePlan));  // (a ring batch has no plans in global memory: its producer warps plan their own tiles)
             if (sh.tabBytes[seg] < tableBytes) {
                 // cuMemAlloc / cuMemFree synchronise the device: when one segment's buffer must grow, grow them all, once, instead of
                 // stalling the next kSegments - 1 launches as well (a mixer's first ticks are often lighter than its steady state)
@@ -536,19 +535,7 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
                     void* targs[] = {&dev, &tables, &counter};
                     check(d.cuLaunchKernel(sh.fStripTables, (unsigned)blocks, (unsigned)maxLayers, (unsigned)n, 96, 1, 1, 0, sh.prep, targs, nullptr), "cuLaunchKernel(svb_strip_tables)");
                     noteKernelLaunch();
-                    if (sh.tableCache) sh.tabSig[seg] = sig;
-                    else sh.tabSig[seg].clear();  // (no order is computed while the cache is off: nothing to find in place later)
-                    if (sh.tableCache) {
-                        // ... and the order in which the compositor's CTAs claim the batch's tiles, heaviest first: count, then place.  Kept with the
-                        // tables; with the cache off the compositor claims in raster order (the two launches cost a step more than the order gains)
-                        static_assert(SVB_RING_HIST + SVB_MAX_LAYERS < SVB_RING_CURSOR && SVB_RING_CURSOR + SVB_MAX_LAYERS < SVB_RING_ORDER_OFFSET && SVB_RING_ORDER_OFFSET == 64, "control block layout");
-                        int nf = n;
-                        for (int phase = 0; phase < 2; ++phase) {
-                            void* oargs[] = {&dev, &nf, &total, &counter, &phase};
-                            check(d.cuLaunchKernel(sh.fRingOrder, (unsigned)((total + 95) / 96), 1, 1, 96, 1, 1, 0, sh.prep, oargs, nullptr), "cuLaunchKernel(svb_ring_order)");
-                            noteKernelLaunch();
-                        }
-                    }
+                    sh.tabSig[seg] = sig;
                 }
             } else {
                 sh.tabSig[seg].clear();  // (the other compositors lay the buffer out differently)
@@ -563,8 +550,8 @@ void launchFrames(const ComputeContext& ctx, std::vector<SvbFrameDesc>& frames, 
             if (tev.first) check(d.cuEventRecord(tev.first, ic.compute), "cuEventRecord");  // time svb_mix_tiled alone
             float one = 1.0f;  // see add2() in kernels_tiled.cuh
             if (ring) {
-                int nf = n, slotBytes = SVB_RPLAN_SLOT_BYTES(maxLayers), useOrder = sh.tableCache ? 1 : 0;
-                void* args[] = {&dev, &tables, &nf, &total, &one, &counter, &boxY, &boxC, &slotBytes, &useOrder};
+                int nf = n, slotBytes = SVB_RPLAN_SLOT_BYTES(maxLayers);
+                void* args[] = {&dev, &tables, &nf, &total, &one, &counter, &boxY, &boxC, &slotBytes};
                 size_t smem = SVB_RING_SMEM_BYTES((size_t)boxY, (size_t)boxC, maxLayers);
                 int perSm;
                 {

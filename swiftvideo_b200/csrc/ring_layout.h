@@ -28,13 +28,6 @@ enum { SVB_BODY_NONE = 0, SVB_BODY_BLEND = 1, SVB_BODY_BLEND_HALF = 2, SVB_BODY_
 #define SVB_RING_PLANS 3
 #define SVB_RING_TAB_BYTES (2 * SVB_UCOL_WORDS * 4 + 4 * SVB_UROW_WORDS * 4)  // a stage's table blocks: two unit columns, four unit rows
 #define SVB_RING_HDR_BYTES 128
-// Control block of a ring batch in its table buffer (ints): [0] the tile counter svb_mix_ring claims from, [1] its CTAs that ran out of
-// tiles (the last one zeroes both); svb_ring_order's tiles per weight [SVB_RING_HIST + w] and places handed out per weight
-// [SVB_RING_CURSOR + w] (zeroed by svb_strip_tables, which always runs right before it); then the claim order itself:
-// order[k] = the k-th tile to claim.  The order is part of what the table cache keeps (mix_video.cpp: tabSig).
-#define SVB_RING_HIST 4
-#define SVB_RING_CURSOR 24
-#define SVB_RING_ORDER_OFFSET 64
 #define SVB_RING_SMEM_BYTES(boxY, boxC, layers) \
     (SVB_RING_HDR_BYTES + SVB_RING_WARPS * SVB_STRIP_STATE_BYTES + SVB_RING_PLANS * SVB_RPLAN_SLOT_BYTES(layers) + SVB_RING_STAGES * ((boxY) + (boxC) + SVB_RING_TAB_BYTES))
 
